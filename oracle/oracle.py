@@ -1,0 +1,220 @@
+"""ctypes wrapper around oracle/sim_oracle.c — TEST INFRASTRUCTURE, never imported by the product.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs use it.
+The model constants come from the committed compiled model (learninghumanoidwalking_b200/model/*.json,
+produced by tools/compile_model.py) and the gait clocks from tests/golden/gait_clocks.json (produced by
+running the reference's tasks/rewards.py:create_phase_reward — i.e. pinned to the reference itself).
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "_build", "liboracle.so")
+NOBS, NREW, NU, NV, NQ = 37, 10, 12, 18, 19
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(HERE, "sim_oracle.c"), os.path.join(HERE, "sim_oracle.h")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
+        os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-std=gnu11", "-o", LIB_PATH, src[0], "-lm"])
+    return LIB_PATH
+
+
+def load_model_json(name: str = "jvrc_walk") -> dict:
+    return json.load(open(os.path.join(ROOT, "learninghumanoidwalking_b200", "model", name + ".json")))
+
+
+def load_clocks() -> dict:
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "gait_clocks.json")))
+
+
+def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: int = 0, iterations: int | None = None):
+    """Flat double layout consumed by orc_model_from_flat (keep in sync with sim_oracle.c)."""
+    b: list[float] = []
+    links = mj["links"]
+    b.append(len(links))
+    for i, lk in enumerate(links):
+        b.append(lk["parent"])
+        b += lk["pos"]
+        b += list(np.array(lk["rot"]).reshape(-1))
+        b += lk["joint"].get("axis", [0.0, 0.0, 0.0])
+        b.append(lk["mass"])
+        b += lk["com"]
+        a = lk["inertia"]
+        b += [a[0], a[3], a[4], a[3], a[1], a[5], a[4], a[5], a[2]]
+        b += mj["link_invweight0"][i]
+    nv = 6 + len(links) - 1
+    for d in range(nv):
+        if d < 6:
+            b += [0.0, 0.0, 0.0, 0.0, 0.0, mj["dof_invweight0"][d]]
+        else:
+            j = links[d - 5]["joint"]
+            b += [j["armature"], j["damping"], j["range"][0], j["range"][1], 1.0, mj["dof_invweight0"][d]]
+    b.append(len(mj["geoms"]))
+    for g in mj["geoms"]:
+        b.append(g["link"])
+        b += g["pos"]
+        b += g["size"]
+    o = mj["opt"]
+    b.append(o["timestep"])
+    b += o["gravity"]
+    b += o["solref"]
+    b += o["solimp"]
+    b += [o["friction"][0], o["impratio"], mj["meaninertia"], o["tolerance"] if tolerance is None else tolerance,
+          o["iterations"] if iterations is None else iterations, solver]
+    c = mj["cfg"]
+    b += c["kp"]
+    b += c["kd"]
+    b += c["nominal_qpos"]
+    b += [c["frame_skip"], c["action_smoothing"], mj["rfoot_link"], mj["lfoot_link"]]
+    b += mj["head_in_root"]
+    b += [mj["total_mass"], c["task"]["goal_height"], clocks["period"]]
+    for k in ("r_frc", "r_vel", "l_frc", "l_vel"):
+        b += clocks[k]
+    return np.array(b, dtype=np.float64)
+
+
+class Oracle:
+    """One compiled model + helpers to own N environments."""
+
+    def __init__(self, name: str = "jvrc_walk", tolerance: float | None = None, solver: int = 0,
+                 iterations: int | None = None):
+        self.lib = ctypes.CDLL(build())
+        L = self.lib
+        L.orc_energy.restype = ctypes.c_double
+        self.mj = load_model_json(name)
+        self.clocks = load_clocks()
+        flat = pack_model(self.mj, self.clocks, tolerance, solver, iterations)
+        self._model = ctypes.create_string_buffer(L.orc_sizeof_model())
+        rc = L.orc_model_from_flat(self._model, flat.ctypes.data_as(ctypes.c_void_p), len(flat))
+        if rc != 0:
+            raise RuntimeError(f"orc_model_from_flat failed: {rc}")
+        self.env_size = L.orc_sizeof_env()
+
+    # ---- single/batched env management
+    def make_envs(self, n: int, seed: int = 0, first_id: int = 0):
+        buf = ctypes.create_string_buffer(self.env_size * n)
+        for i in range(n):
+            self.lib.orc_env_init(self._model, ctypes.byref(buf, i * self.env_size), ctypes.c_uint32(seed),
+                                  ctypes.c_uint32(first_id + i))
+        return buf
+
+    def env_ptr(self, envs, i=0):
+        return ctypes.byref(envs, i * self.env_size)
+
+    def field(self, envs, i, name):
+        """Read a field of env i by name (offsets mirror orc_env)."""
+        off, cnt, typ = _ENV_FIELDS[name]
+        raw = np.frombuffer(envs, dtype=np.uint8, count=self.env_size, offset=i * self.env_size)
+        return raw[off:off + cnt * np.dtype(typ).itemsize].view(typ).copy()
+
+    def set_field(self, envs, i, name, value):
+        off, cnt, typ = _ENV_FIELDS[name]
+        raw = np.frombuffer(envs, dtype=np.uint8, count=self.env_size, offset=i * self.env_size)
+        raw[off:off + cnt * np.dtype(typ).itemsize] = np.asarray(value, dtype=typ).reshape(cnt).view(np.uint8)
+
+    def reset(self, envs, i=0):
+        obs = np.zeros(NOBS)
+        self.lib.orc_reset(self._model, self.env_ptr(envs, i), obs.ctypes.data_as(ctypes.c_void_p))
+        return obs
+
+    def mj_step(self, envs, i, ctrl):
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        self.lib.orc_mj_step(self._model, self.env_ptr(envs, i), ctrl.ctypes.data_as(ctypes.c_void_p))
+
+    def step(self, envs, i, action):
+        action = np.ascontiguousarray(action, dtype=np.float64)
+        obs, terms = np.zeros(NOBS), np.zeros(NREW)
+        rew, done = ctypes.c_double(), ctypes.c_int()
+        self.lib.orc_step(self._model, self.env_ptr(envs, i), action.ctypes.data_as(ctypes.c_void_p),
+                          obs.ctypes.data_as(ctypes.c_void_p), terms.ctypes.data_as(ctypes.c_void_p),
+                          ctypes.byref(rew), ctypes.byref(done))
+        return obs, rew.value, bool(done.value), terms
+
+    def batch_reset(self, envs, n, nthreads=0):
+        obs = np.zeros((n, NOBS))
+        self.lib.orc_batch_reset(self._model, envs, n, obs.ctypes.data_as(ctypes.c_void_p), nthreads)
+        return obs
+
+    def batch_step(self, envs, n, actions, max_traj_len=400, nthreads=0):
+        actions = np.ascontiguousarray(actions, dtype=np.float64)
+        assert actions.shape == (n, NU)
+        obs, tobs, terms = np.zeros((n, NOBS)), np.zeros((n, NOBS)), np.zeros((n, NREW))
+        rew = np.zeros(n)
+        done, ended = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self.lib.orc_batch_step_autoreset(self._model, envs, n, p(actions), max_traj_len, p(obs), p(tobs), p(terms),
+                                          p(rew), p(done), p(ended), nthreads)
+        return obs, tobs, terms, rew, done, ended
+
+    # ---- building blocks
+    def mass_matrix(self, qpos):
+        qpos = np.ascontiguousarray(qpos, dtype=np.float64)
+        M = np.zeros((NV, NV))
+        self.lib.orc_mass_matrix(self._model, qpos.ctypes.data_as(ctypes.c_void_p), M.ctypes.data_as(ctypes.c_void_p))
+        return M
+
+    def bias(self, qpos, qvel):
+        qpos = np.ascontiguousarray(qpos, dtype=np.float64)
+        qvel = np.ascontiguousarray(qvel, dtype=np.float64)
+        c = np.zeros(NV)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self.lib.orc_bias(self._model, p(qpos), p(qvel), p(c))
+        return c
+
+    def energy(self, qpos, qvel):
+        qpos = np.ascontiguousarray(qpos, dtype=np.float64)
+        qvel = np.ascontiguousarray(qvel, dtype=np.float64)
+        ke, pe = ctypes.c_double(), ctypes.c_double()
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self.lib.orc_energy(self._model, p(qpos), p(qvel), ctypes.byref(ke), ctypes.byref(pe))
+        return ke.value, pe.value
+
+    def philox(self, seed, env_id, ctr, stream):
+        out = (ctypes.c_uint32 * 4)()
+        self.lib.orc_philox(ctypes.c_uint32(seed), ctypes.c_uint32(env_id), ctypes.c_uint32(ctr),
+                            ctypes.c_uint32(stream), out)
+        return list(out)
+
+    def quat2rp(self, quat):
+        quat = np.ascontiguousarray(quat, dtype=np.float64)
+        r, p = ctypes.c_double(), ctypes.c_double()
+        self.lib.orc_quat2rp(quat.ctypes.data_as(ctypes.c_void_p), ctypes.byref(r), ctypes.byref(p))
+        return r.value, p.value
+
+    def max_threads(self):
+        return self.lib.orc_max_threads()
+
+
+def _layout():
+    """Offsets of orc_env fields (mirrors the struct in sim_oracle.h; doubles first then ints, natural alignment)."""
+    fields = [
+        ("qpos", NQ, "f8"), ("qvel", NV, "f8"), ("qacc_warm", NV, "f8"), ("qacc", NV, "f8"),
+        ("act_len", NU, "f8"), ("act_vel", NU, "f8"), ("act_force", NU, "f8"),
+        ("root_xpos", 3, "f8"), ("root_xmat", 9, "f8"), ("head_xpos", 3, "f8"), ("root_vlin", 3, "f8"),
+        ("rfoot_vel", 3, "f8"), ("lfoot_vel", 3, "f8"), ("rfoot_grf", 1, "f8"), ("lfoot_grf", 1, "f8"),
+        ("contact_z_min", 1, "f8"),
+        ("ncon_r", 1, "i4"), ("ncon_l", 1, "i4"), ("ncon", 1, "i4"), ("self_collision", 1, "i4"),
+        ("prev_prediction", NU, "f8"), ("prev_action", NU, "f8"), ("prev_torque", NU, "f8"),
+        ("have_prev", 1, "i4"), ("phase", 1, "i4"), ("mode", 1, "i4"), ("_pad0", 1, "i4"),
+        ("mode_ref", 3, "f8"),
+        ("traj_len", 1, "i4"), ("ep_len", 1, "i4"), ("ep_rew", 1, "f8"),
+        ("seed", 1, "u4"), ("env_id", 1, "u4"), ("rng_ctr", 1, "u4"), ("last_solver_iter", 1, "i4"),
+        ("last_kkt_residual", 1, "f8"), ("status", 1, "i4"), ("nsubsteps", 1, "i4"),
+    ]
+    out, off = {}, 0
+    for name, cnt, typ in fields:
+        out[name] = (off, cnt, np.dtype(typ))
+        off += cnt * np.dtype(typ).itemsize
+    return out, off
+
+
+_ENV_FIELDS, _ENV_SIZE = _layout()

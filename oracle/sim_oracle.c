@@ -1,0 +1,916 @@
+/*
+ * oracle/sim_oracle.c — TEST INFRASTRUCTURE (see sim_oracle.h for the parity statement).
+ *
+ * Formulations are deliberately the dense textbook ones (explicit link Jacobians, M = sum J^T I J,
+ * projected Newton-Euler bias, dense Cholesky) so that this file is an independent check of the
+ * tree-structured CUDA kernel, not a transliteration of it.
+ *
+ * Reference call chain restated (file:line relative to /root/reference):
+ *   envs/common/base_humanoid_env.py:199-227  step        -> orc_step
+ *   envs/common/base_humanoid_env.py:247-276  reset_model -> orc_reset
+ *   robots/robot_base.py:41-98                _do_simulation/step (PD loop, prev_action/torque)
+ *   envs/common/robot_interface.py:493-546    step_pd / set_motor_torque / step (mj_step)
+ *   tasks/walking_task.py:85-205              calc_reward / step / done / reset
+ *   tasks/rewards.py:9-174                    reward terms
+ *   envs/jvrc/jvrc_base.py:133-145, envs/jvrc/jvrc_walk.py:65-67, tasks/observations.py:12-72  obs
+ *   mujoco.mj_step (external)                                  -> orc_mj_step
+ */
+#include "sim_oracle.h"
+
+#include <math.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define L ORC_MAXLINK
+#define NV ORC_NV
+#define MINVAL 1e-15
+
+/* ------------------------------------------------------------------ small linear algebra */
+static void cross3(const double* a, const double* b, double* c) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  c[0] = x; c[1] = y; c[2] = z;
+}
+static double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static void matvec3(const double* R, const double* v, double* out) {
+  double x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  double y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  double z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  out[0] = x; out[1] = y; out[2] = z;
+}
+static void mattvec3(const double* R, const double* v, double* out) {
+  double x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+  double y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+  double z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  out[0] = x; out[1] = y; out[2] = z;
+}
+static void matmul3(const double* A, const double* B, double* C) {
+  double T[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) T[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+  memcpy(C, T, sizeof(T));
+}
+static void quat2mat(const double* q, double* R) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+}
+/* dense Cholesky A = G G^T (lower), in place; returns 0 on success */
+static int chol(double* A, int n) {
+  for (int j = 0; j < n; j++) {
+    double d = A[j * n + j];
+    for (int k = 0; k < j; k++) d -= A[j * n + k] * A[j * n + k];
+    if (!(d > 0)) return 1;
+    d = sqrt(d);
+    A[j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      double s = A[i * n + j];
+      for (int k = 0; k < j; k++) s -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = s / d;
+    }
+  }
+  return 0;
+}
+static void chol_solve(const double* G, int n, double* b) {
+  for (int i = 0; i < n; i++) {
+    double s = b[i];
+    for (int k = 0; k < i; k++) s -= G[i * n + k] * b[k];
+    b[i] = s / G[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    double s = b[i];
+    for (int k = i + 1; k < n; k++) s -= G[k * n + i] * b[k];
+    b[i] = s / G[i * n + i];
+  }
+}
+
+/* ------------------------------------------------------------------ model packing */
+int orc_sizeof_env(void) { return (int)sizeof(orc_env); }
+int orc_sizeof_model(void) { return (int)sizeof(orc_model); }
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+int orc_model_from_flat(orc_model* m, const double* b, int n) {
+  int p = 0;
+#define RD() (p < n ? b[p++] : (p++, 0.0))
+  memset(m, 0, sizeof(*m));
+  m->nlink = (int)RD();
+  if (m->nlink > L || m->nlink < 1) return -1;
+  m->nv = 6 + m->nlink - 1; m->nq = m->nv + 1; m->nu = m->nlink - 1;
+  if (m->nv > NV) return -2;
+  for (int i = 0; i < m->nlink; i++) {
+    m->parent[i] = (int)RD();
+    for (int k = 0; k < 3; k++) m->pos[i][k] = RD();
+    for (int k = 0; k < 9; k++) m->rot[i][k] = RD();
+    for (int k = 0; k < 3; k++) m->axis[i][k] = RD();
+    m->mass[i] = RD();
+    for (int k = 0; k < 3; k++) m->com[i][k] = RD();
+    for (int k = 0; k < 9; k++) m->inertia[i][k] = RD();
+    for (int k = 0; k < 2; k++) m->link_invweight0[i][k] = RD();
+  }
+  for (int d = 0; d < m->nv; d++) {
+    m->armature[d] = RD(); m->damping[d] = RD(); m->range[d][0] = RD(); m->range[d][1] = RD();
+    m->limited[d] = (int)RD(); m->dof_invweight0[d] = RD();
+  }
+  m->ngeom = (int)RD();
+  if (m->ngeom > ORC_MAXGEOM) return -3;
+  for (int g = 0; g < m->ngeom; g++) {
+    m->geom_link[g] = (int)RD();
+    for (int k = 0; k < 3; k++) m->geom_pos[g][k] = RD();
+    for (int k = 0; k < 3; k++) m->geom_size[g][k] = RD();
+  }
+  m->timestep = RD();
+  for (int k = 0; k < 3; k++) m->gravity[k] = RD();
+  for (int k = 0; k < 2; k++) m->solref[k] = RD();
+  for (int k = 0; k < 5; k++) m->solimp[k] = RD();
+  m->mu = RD(); m->impratio = RD(); m->meaninertia = RD(); m->tolerance = RD();
+  m->iterations = (int)RD(); m->solver = (int)RD();
+  for (int k = 0; k < m->nu; k++) m->kp[k] = RD();
+  for (int k = 0; k < m->nu; k++) m->kd[k] = RD();
+  for (int k = 0; k < m->nq; k++) m->nominal_qpos[k] = RD();
+  m->frame_skip = (int)RD(); m->action_smoothing = RD();
+  m->rfoot_link = (int)RD(); m->lfoot_link = (int)RD();
+  for (int k = 0; k < 3; k++) m->head_in_root[k] = RD();
+  m->total_mass = RD(); m->goal_height = RD();
+  m->period = (int)RD();
+  if (m->period > ORC_MAXPERIOD) return -4;
+  for (int c = 0; c < 4; c++)
+    for (int k = 0; k < m->period; k++) m->clock[c][k] = RD();
+#undef RD
+  return p == n ? 0 : -100 - (p > n);
+}
+
+/* ------------------------------------------------------------------ rng (philox4x32-10) */
+static inline uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
+  uint64_t p = (uint64_t)a * b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+void orc_philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t stream, uint32_t out[4]) {
+  uint32_t c0 = ctr, c1 = stream, c2 = env_id, c3 = 0x4c485742u; /* 'LHWB' */
+  uint32_t k0 = seed, k1 = 0x9E3779B9u ^ (seed * 0x85EBCA6Bu + 1u);
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0, hi1;
+    uint32_t lo0 = mulhilo(0xD2511F53u, c0, &hi0);
+    uint32_t lo1 = mulhilo(0xCD9E8D57u, c2, &hi1);
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static inline double u01(uint32_t u) { return (double)(u >> 8) * (1.0 / 16777216.0); } /* 24 bit, exact in f32 too */
+static inline int randint(uint32_t u, int n) { return (int)(((uint64_t)u * (uint64_t)n) >> 32); }
+
+/* ------------------------------------------------------------------ kinematics */
+typedef struct {
+  double xpos[L][3], xmat[L][9], xaxis[L][3], xcom[L][3], Iw[L][9];
+} kin_t;
+
+static void fk(const orc_model* m, const double* qpos, kin_t* k) {
+  double q[4] = {qpos[3], qpos[4], qpos[5], qpos[6]};
+  double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; i++) q[i] /= nrm;
+  for (int i = 0; i < m->nlink; i++) {
+    if (i == 0) {
+      memcpy(k->xpos[0], qpos, 3 * sizeof(double));
+      quat2mat(q, k->xmat[0]);
+      k->xaxis[0][0] = k->xaxis[0][1] = k->xaxis[0][2] = 0;
+    } else {
+      int p = m->parent[i];
+      double off[3], R0[9], Rj[9];
+      matvec3(k->xmat[p], m->pos[i], off);
+      for (int c = 0; c < 3; c++) k->xpos[i][c] = k->xpos[p][c] + off[c];
+      matmul3(k->xmat[p], m->rot[i], R0);
+      /* Rodrigues about the (unit) hinge axis */
+      const double* a = m->axis[i];
+      double ang = qpos[6 + i], s = sin(ang), c = cos(ang), t = 1 - c;
+      Rj[0] = c + a[0] * a[0] * t;        Rj[1] = a[0] * a[1] * t - a[2] * s; Rj[2] = a[0] * a[2] * t + a[1] * s;
+      Rj[3] = a[0] * a[1] * t + a[2] * s; Rj[4] = c + a[1] * a[1] * t;        Rj[5] = a[1] * a[2] * t - a[0] * s;
+      Rj[6] = a[0] * a[2] * t - a[1] * s; Rj[7] = a[1] * a[2] * t + a[0] * s; Rj[8] = c + a[2] * a[2] * t;
+      matmul3(R0, Rj, k->xmat[i]);
+      matvec3(k->xmat[i], a, k->xaxis[i]);
+    }
+    double sc[3], T[9], Rt[9];
+    matvec3(k->xmat[i], m->com[i], sc);
+    for (int c = 0; c < 3; c++) k->xcom[i][c] = k->xpos[i][c] + sc[c];
+    matmul3(k->xmat[i], m->inertia[i], T);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Rt[3 * r + c] = k->xmat[i][3 * c + r];
+    matmul3(T, Rt, k->Iw[i]);
+  }
+}
+
+/* translational (jp) and rotational (jr) Jacobians (3 x nv, row major with stride NV) of a world point
+ * rigidly attached to `link`; free joint: dofs 0-2 world translation, 3-5 body-frame rotation */
+static void jac_point(const orc_model* m, const kin_t* k, int link, const double* point, double* jp, double* jr) {
+  memset(jp, 0, 3 * NV * sizeof(double));
+  if (jr) memset(jr, 0, 3 * NV * sizeof(double));
+  for (int b = link; b >= 0; b = m->parent[b]) {
+    if (b == 0) {
+      for (int c = 0; c < 3; c++) jp[c * NV + c] = 1.0;
+      double r[3] = {point[0] - k->xpos[0][0], point[1] - k->xpos[0][1], point[2] - k->xpos[0][2]};
+      for (int kk = 0; kk < 3; kk++) {
+        double a[3] = {k->xmat[0][kk], k->xmat[0][3 + kk], k->xmat[0][6 + kk]}, v[3];
+        cross3(a, r, v);
+        for (int c = 0; c < 3; c++) {
+          jp[c * NV + 3 + kk] = v[c];
+          if (jr) jr[c * NV + 3 + kk] = a[c];
+        }
+      }
+    } else {
+      int d = 5 + b;
+      double r[3] = {point[0] - k->xpos[b][0], point[1] - k->xpos[b][1], point[2] - k->xpos[b][2]}, v[3];
+      cross3(k->xaxis[b], r, v);
+      for (int c = 0; c < 3; c++) {
+        jp[c * NV + d] = v[c];
+        if (jr) jr[c * NV + d] = k->xaxis[b][c];
+      }
+    }
+  }
+}
+
+static void mass_matrix_k(const orc_model* m, const kin_t* k, double* M) {
+  int nv = m->nv;
+  memset(M, 0, NV * NV * sizeof(double));
+  double jp[3 * NV], jr[3 * NV], IJ[3 * NV];
+  for (int i = 0; i < m->nlink; i++) {
+    jac_point(m, k, i, k->xcom[i], jp, jr);
+    for (int c = 0; c < 3; c++)
+      for (int d = 0; d < nv; d++)
+        IJ[c * NV + d] = k->Iw[i][3 * c] * jr[d] + k->Iw[i][3 * c + 1] * jr[NV + d] + k->Iw[i][3 * c + 2] * jr[2 * NV + d];
+    for (int a = 0; a < nv; a++)
+      for (int b = 0; b < nv; b++) {
+        double s = 0;
+        for (int c = 0; c < 3; c++) s += m->mass[i] * jp[c * NV + a] * jp[c * NV + b] + jr[c * NV + a] * IJ[c * NV + b];
+        M[a * NV + b] += s;
+      }
+  }
+  for (int d = 0; d < nv; d++) M[d * NV + d] += m->armature[d];
+}
+
+void orc_mass_matrix(const orc_model* m, const double* qpos, double* Mout) {
+  kin_t k; double M[NV * NV];
+  fk(m, qpos, &k);
+  mass_matrix_k(m, &k, M);
+  for (int a = 0; a < m->nv; a++)
+    for (int b = 0; b < m->nv; b++) Mout[a * m->nv + b] = M[a * NV + b];
+}
+
+/* qfrc_bias = C(q,v) v + gravity term, by projecting each link's Newton-Euler equation (qacc = 0) on its Jacobians */
+static void bias_k(const orc_model* m, const kin_t* k, const double* qvel, double* c) {
+  int nv = m->nv;
+  double w[L][3], al[L][3], ao[L][3];
+  memset(c, 0, NV * sizeof(double));
+  double jp[3 * NV], jr[3 * NV];
+  for (int i = 0; i < m->nlink; i++) {
+    if (i == 0) {
+      matvec3(k->xmat[0], qvel + 3, w[0]);
+      for (int x = 0; x < 3; x++) { al[0][x] = 0; ao[0][x] = 0; }
+    } else {
+      int p = m->parent[i];
+      double qd = qvel[5 + i], r[3], t[3], t2[3];
+      for (int x = 0; x < 3; x++) w[i][x] = w[p][x] + k->xaxis[i][x] * qd;
+      cross3(w[p], k->xaxis[i], t);
+      for (int x = 0; x < 3; x++) al[i][x] = al[p][x] + t[x] * qd;
+      for (int x = 0; x < 3; x++) r[x] = k->xpos[i][x] - k->xpos[p][x];
+      cross3(al[p], r, t);
+      cross3(w[p], r, t2);
+      cross3(w[p], t2, t2);
+      for (int x = 0; x < 3; x++) ao[i][x] = ao[p][x] + t[x] + t2[x];
+    }
+    double s[3], t[3], t2[3], ac[3], F[3], N[3], Iw_w[3], Iw_al[3];
+    for (int x = 0; x < 3; x++) s[x] = k->xcom[i][x] - k->xpos[i][x];
+    cross3(al[i], s, t);
+    cross3(w[i], s, t2);
+    cross3(w[i], t2, t2);
+    for (int x = 0; x < 3; x++) ac[x] = ao[i][x] + t[x] + t2[x];
+    for (int x = 0; x < 3; x++) F[x] = m->mass[i] * (ac[x] - m->gravity[x]);
+    matvec3(k->Iw[i], w[i], Iw_w);
+    matvec3(k->Iw[i], al[i], Iw_al);
+    cross3(w[i], Iw_w, t);
+    for (int x = 0; x < 3; x++) N[x] = Iw_al[x] + t[x];
+    jac_point(m, k, i, k->xcom[i], jp, jr);
+    for (int d = 0; d < nv; d++)
+      for (int x = 0; x < 3; x++) c[d] += jp[x * NV + d] * F[x] + jr[x * NV + d] * N[x];
+  }
+}
+
+void orc_bias(const orc_model* m, const double* qpos, const double* qvel, double* c) {
+  kin_t k; double cc[NV];
+  fk(m, qpos, &k);
+  bias_k(m, &k, qvel, cc);
+  memcpy(c, cc, m->nv * sizeof(double));
+}
+
+double orc_energy(const orc_model* m, const double* qpos, const double* qvel, double* kinetic, double* potential) {
+  kin_t k; double M[NV * NV];
+  fk(m, qpos, &k);
+  mass_matrix_k(m, &k, M);
+  double ke = 0, pe = 0;
+  for (int a = 0; a < m->nv; a++)
+    for (int b = 0; b < m->nv; b++) ke += 0.5 * qvel[a] * M[a * NV + b] * qvel[b];
+  for (int i = 0; i < m->nlink; i++) pe -= m->mass[i] * dot3(m->gravity, k.xcom[i]);
+  if (kinetic) *kinetic = ke;
+  if (potential) *potential = pe;
+  return ke + pe;
+}
+
+/* ------------------------------------------------------------------ constraints */
+typedef struct {
+  int nrow, ncon;
+  double J[ORC_MAXROW][NV];
+  double pos[ORC_MAXROW], D[ORC_MAXROW], aref[ORC_MAXROW], R[ORC_MAXROW];
+  int con_row[ORC_MAXCON], con_geom[ORC_MAXCON];
+  double con_pos[ORC_MAXCON][3], con_dist[ORC_MAXCON];
+} efc_t;
+
+/* MuJoCo getimpedance(): power-law sigmoid between solimp[0] and solimp[1] over |pos|/width */
+static double impedance(const double* solimp, double pos) {
+  double d0 = solimp[0], dw = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  if (d0 < 0.0001) d0 = 0.0001; if (d0 > 0.9999) d0 = 0.9999;
+  if (dw < 0.0001) dw = 0.0001; if (dw > 0.9999) dw = 0.9999;
+  if (width < MINVAL) return 0.5 * (d0 + dw);
+  double x = fabs(pos) / width;
+  if (x >= 1) return dw;
+  if (x <= 0) return d0;
+  double y;
+  if (power < 1.0000001) y = x;
+  else if (x <= mid) y = pow(x / mid, power) * mid;           /* a*x^p with a = 1/mid^(p-1) */
+  else y = 1 - pow((1 - x) / (1 - mid), power) * (1 - mid);   /* 1 - b*(1-x)^p */
+  return d0 + y * (dw - d0);
+}
+
+static void make_constraints(const orc_model* m, const kin_t* k, const double* qpos, const double* qvel, efc_t* e) {
+  int nv = m->nv;
+  e->nrow = 0; e->ncon = 0;
+  double tau = m->solref[0], zeta = m->solref[1];
+  if (tau < 2 * m->timestep) tau = 2 * m->timestep; /* refsafe */
+  double dmax = m->solimp[1];
+  double K = 1.0 / fmax(MINVAL, dmax * dmax * tau * tau * zeta * zeta);
+  double B = 2.0 / fmax(MINVAL, dmax * tau);
+  /* joint limits (rows precede contacts, as in mj_makeConstraint) */
+  for (int d = 6; d < nv; d++) {
+    if (!m->limited[d]) continue;
+    double q = qpos[d + 1];
+    for (int side = 0; side < 2; side++) {
+      double dist = side == 0 ? q - m->range[d][0] : m->range[d][1] - q;
+      if (dist < 0) {
+        int r = e->nrow++;
+        memset(e->J[r], 0, sizeof(e->J[r]));
+        e->J[r][d] = side == 0 ? 1.0 : -1.0;
+        double imp = impedance(m->solimp, dist);
+        double vel = e->J[r][d] * qvel[d];
+        e->pos[r] = dist;
+        e->R[r] = fmax(MINVAL, (1 - imp) / imp * m->dof_invweight0[d]);
+        e->D[r] = 1.0 / e->R[r];
+        e->aref[r] = -B * vel - K * imp * dist;
+      }
+    }
+  }
+  /* foot box vs ground plane z=0, normal +z (mjc_PlaneBox: at most 4 corners, in corner-index order) */
+  for (int g = 0; g < m->ngeom; g++) {
+    int lk = m->geom_link[g];
+    double off[3], ctr[3];
+    matvec3(k->xmat[lk], m->geom_pos[g], off);
+    for (int x = 0; x < 3; x++) ctr[x] = k->xpos[lk][x] + off[x];
+    double dist0 = ctr[2];
+    int cnt = 0;
+    for (int i = 0; i < 8 && cnt < 4; i++) {
+      double v[3] = {(i & 1 ? 1 : -1) * m->geom_size[g][0], (i & 2 ? 1 : -1) * m->geom_size[g][1],
+                     (i & 4 ? 1 : -1) * m->geom_size[g][2]};
+      double corner[3];
+      matvec3(k->xmat[lk], v, corner);
+      double ldist = corner[2];
+      if (dist0 + ldist > 0 || ldist > 0) continue;
+      double cd = dist0 + ldist;
+      int ci = e->ncon++;
+      e->con_geom[ci] = g;
+      e->con_dist[ci] = cd;
+      e->con_pos[ci][0] = corner[0] + ctr[0];
+      e->con_pos[ci][1] = corner[1] + ctr[1];
+      e->con_pos[ci][2] = corner[2] + ctr[2] - 0.5 * cd;
+      cnt++;
+    }
+  }
+  /* pyramidal rows: frame (n,t1,t2) = (+z, +y, -x) from mju_makeFrame on n = (0,0,1) */
+  double mu = m->mu * sqrt(1.0 / fmax(MINVAL, m->impratio));
+  for (int ci = 0; ci < e->ncon; ci++) {
+    int lk = m->geom_link[e->con_geom[ci]];
+    double jp[3 * NV];
+    jac_point(m, k, lk, e->con_pos[ci], jp, 0);
+    double imp = impedance(m->solimp, e->con_dist[ci]);
+    double tran = m->link_invweight0[lk][0]; /* world body contributes 0 */
+    double diagApprox = tran + m->mu * m->mu * tran;
+    double Rn = fmax(MINVAL, (1 - imp) / imp * diagApprox);
+    double Rpy = 2 * mu * mu * Rn;
+    e->con_row[ci] = e->nrow;
+    for (int j = 0; j < 4; j++) {
+      int r = e->nrow++;
+      double vel = 0;
+      for (int d = 0; d < nv; d++) {
+        double jn = jp[2 * NV + d], jt = (j < 2) ? jp[1 * NV + d] : -jp[0 * NV + d];
+        e->J[r][d] = jn + ((j & 1) ? -m->mu : m->mu) * jt;
+        vel += e->J[r][d] * qvel[d];
+      }
+      for (int d = nv; d < NV; d++) e->J[r][d] = 0;
+      e->pos[r] = e->con_dist[ci];
+      e->R[r] = Rpy;
+      e->D[r] = 1.0 / Rpy;
+      e->aref[r] = -B * vel - K * imp * e->con_dist[ci];
+    }
+  }
+}
+
+/* primal Newton with exact (piecewise-quadratic) line search; qacc in: warmstart, out: solution */
+static int solve_newton(const orc_model* m, const double* M, const efc_t* e, const double* qfs, double* qacc,
+                        double* force, double* kkt) {
+  int nv = m->nv, nr = e->nrow, it;
+  double scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
+  double Ma[NV], jar[ORC_MAXROW], grad[NV], H[NV * NV], s[NV], jv[ORC_MAXROW], Ms[NV];
+  double gnorm = 0;
+  for (it = 0; it <= m->iterations; it++) {
+    for (int a = 0; a < nv; a++) {
+      double t = 0;
+      for (int b = 0; b < nv; b++) t += M[a * NV + b] * qacc[b];
+      Ma[a] = t;
+    }
+    for (int r = 0; r < nr; r++) {
+      double t = -e->aref[r];
+      for (int d = 0; d < nv; d++) t += e->J[r][d] * qacc[d];
+      jar[r] = t;
+      force[r] = t < 0 ? -e->D[r] * t : 0.0;
+    }
+    gnorm = 0;
+    for (int a = 0; a < nv; a++) {
+      double t = Ma[a] - qfs[a];
+      for (int r = 0; r < nr; r++) t -= e->J[r][a] * force[r];
+      grad[a] = t;
+      gnorm += t * t;
+    }
+    gnorm = sqrt(gnorm);
+    if (gnorm * scale < m->tolerance || it == m->iterations) break;
+    for (int a = 0; a < nv; a++)
+      for (int b = 0; b < nv; b++) {
+        double t = M[a * NV + b];
+        for (int r = 0; r < nr; r++)
+          if (jar[r] < 0) t += e->D[r] * e->J[r][a] * e->J[r][b];
+        H[a * nv + b] = t;
+      }
+    if (chol(H, nv)) break;
+    for (int a = 0; a < nv; a++) s[a] = -grad[a];
+    chol_solve(H, nv, s);
+    /* line search on phi(alpha) = cost(qacc + alpha s): phi' is continuous, piecewise linear, increasing */
+    double sMs = 0, sg = 0;
+    for (int a = 0; a < nv; a++) {
+      double t = 0;
+      for (int b = 0; b < nv; b++) t += M[a * NV + b] * s[b];
+      Ms[a] = t;
+      sMs += s[a] * t;
+      sg += s[a] * (Ma[a] - qfs[a]);
+    }
+    for (int r = 0; r < nr; r++) {
+      double t = 0;
+      for (int d = 0; d < nv; d++) t += e->J[r][d] * s[d];
+      jv[r] = t;
+    }
+    double bp[ORC_MAXROW];
+    int nbp = 0;
+    for (int r = 0; r < nr; r++)
+      if (jv[r] != 0) {
+        double a0 = -jar[r] / jv[r];
+        if (a0 > 0) bp[nbp++] = a0;
+      }
+    for (int i = 1; i < nbp; i++) { /* insertion sort */
+      double v = bp[i]; int j = i - 1;
+      while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; j--; }
+      bp[j + 1] = v;
+    }
+#define DPHI(al, out)                                                       \
+  do {                                                                      \
+    double _d = (al) * sMs + sg;                                            \
+    for (int r = 0; r < nr; r++) {                                          \
+      double x = jar[r] + (al) * jv[r];                                     \
+      if (x < 0) _d += e->D[r] * x * jv[r];                                 \
+    }                                                                       \
+    (out) = _d;                                                             \
+  } while (0)
+    double lo = 0, dlo, alpha = -1;
+    DPHI(0.0, dlo);
+    if (!(dlo < 0)) break; /* not a descent direction: converged to roundoff */
+    for (int i = 0; i < nbp; i++) {
+      double dhi;
+      DPHI(bp[i], dhi);
+      if (dhi >= 0) { alpha = lo - dlo * (bp[i] - lo) / (dhi - dlo); break; }
+      lo = bp[i]; dlo = dhi;
+    }
+    if (alpha < 0) { /* beyond the last breakpoint: slope is constant */
+      double slope = sMs, mid = lo + 1.0;
+      for (int r = 0; r < nr; r++)
+        if (jar[r] + mid * jv[r] < 0) slope += e->D[r] * jv[r] * jv[r];
+      alpha = lo - dlo / slope;
+    }
+#undef DPHI
+    for (int a = 0; a < nv; a++) qacc[a] += alpha * s[a];
+  }
+  if (kkt) *kkt = gnorm;
+  return it;
+}
+
+/* dual projected Gauss-Seidel on  min_{f>=0} 1/2 f^T (J M^-1 J^T + R) f + f^T (J a_s - aref)  (tests only) */
+static int solve_pgs(const orc_model* m, const double* M, const efc_t* e, const double* qfs, double* qacc,
+                     double* force, double* kkt) {
+  int nv = m->nv, nr = e->nrow;
+  double G[NV * NV], as[NV], MinvJt[ORC_MAXROW][NV];
+  static __thread double A[ORC_MAXROW][ORC_MAXROW];
+  double b[ORC_MAXROW];
+  for (int a = 0; a < nv; a++)
+    for (int c = 0; c < nv; c++) G[a * nv + c] = M[a * NV + c];
+  chol(G, nv);
+  memcpy(as, qfs, nv * sizeof(double));
+  chol_solve(G, nv, as);
+  for (int r = 0; r < nr; r++) {
+    memcpy(MinvJt[r], e->J[r], nv * sizeof(double));
+    chol_solve(G, nv, MinvJt[r]);
+  }
+  for (int r = 0; r < nr; r++) {
+    for (int c = 0; c < nr; c++) {
+      double t = 0;
+      for (int d = 0; d < nv; d++) t += e->J[r][d] * MinvJt[c][d];
+      A[r][c] = t + (r == c ? e->R[r] : 0);
+    }
+    double t = -e->aref[r];
+    for (int d = 0; d < nv; d++) t += e->J[r][d] * as[d];
+    b[r] = t;
+    force[r] = 0;
+  }
+  int it, maxit = m->iterations * 2000;
+  for (it = 0; it < maxit; it++) {
+    double change = 0;
+    for (int r = 0; r < nr; r++) {
+      double res = b[r];
+      for (int c = 0; c < nr; c++) res += A[r][c] * force[c];
+      double fn = force[r] - res / A[r][r];
+      if (fn < 0) fn = 0;
+      change += fabs(fn - force[r]);
+      force[r] = fn;
+    }
+    if (change < 1e-14) break;
+  }
+  for (int a = 0; a < nv; a++) {
+    double t = as[a];
+    for (int r = 0; r < nr; r++) t += MinvJt[r][a] * force[r];
+    qacc[a] = t;
+  }
+  if (kkt) {
+    double g2 = 0;
+    for (int a = 0; a < nv; a++) {
+      double t = -qfs[a];
+      for (int c = 0; c < nv; c++) t += M[a * NV + c] * qacc[c];
+      for (int r = 0; r < nr; r++) {
+        double jr_ = -e->aref[r];
+        for (int d = 0; d < nv; d++) jr_ += e->J[r][d] * qacc[d];
+        t -= e->J[r][a] * (jr_ < 0 ? -e->D[r] * jr_ : 0);
+      }
+      g2 += t * t;
+    }
+    *kkt = sqrt(g2);
+  }
+  return it;
+}
+
+/* ------------------------------------------------------------------ mj_step */
+void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
+  int nv = m->nv, nu = m->nu;
+  double h = m->timestep;
+  kin_t k;
+  efc_t efc;
+  double M[NV * NV], bias[NV], qfs[NV], force[ORC_MAXROW], qacc[NV];
+  fk(m, e->qpos, &k);
+  mass_matrix_k(m, &k, M);
+  make_constraints(m, &k, e->qpos, e->qvel, &efc);
+  bias_k(m, &k, e->qvel, bias);
+  for (int d = 0; d < nv; d++) qfs[d] = -m->damping[d] * e->qvel[d] - bias[d];
+  for (int u = 0; u < nu; u++) qfs[6 + u] += ctrl[u]; /* motors, gear 1 */
+  memcpy(qacc, e->qacc_warm, sizeof(qacc));
+  double kkt = 0;
+  if (efc.nrow == 0) {
+    double G[NV * NV];
+    for (int a = 0; a < nv; a++)
+      for (int c = 0; c < nv; c++) G[a * nv + c] = M[a * NV + c];
+    chol(G, nv);
+    memcpy(qacc, qfs, nv * sizeof(double));
+    chol_solve(G, nv, qacc);
+    e->last_solver_iter = 0;
+  } else if (m->solver == ORC_SOLVER_PGS) {
+    e->last_solver_iter = solve_pgs(m, M, &efc, qfs, qacc, force, &kkt);
+  } else {
+    e->last_solver_iter = solve_newton(m, M, &efc, qfs, qacc, force, &kkt);
+  }
+  e->last_kkt_residual = kkt;
+  /* ---- quantities mjData keeps after mj_step (all refer to the pre-integration state) */
+  memcpy(e->qacc, qacc, nv * sizeof(double));
+  for (int u = 0; u < nu; u++) {
+    e->act_len[u] = e->qpos[7 + u];
+    e->act_vel[u] = e->qvel[6 + u];
+    e->act_force[u] = ctrl[u];
+  }
+  memcpy(e->root_xpos, k.xpos[0], sizeof(e->root_xpos));
+  memcpy(e->root_xmat, k.xmat[0], sizeof(e->root_xmat));
+  memcpy(e->root_vlin, e->qvel, sizeof(e->root_vlin));
+  {
+    double t[3];
+    matvec3(k.xmat[0], m->head_in_root, t);
+    for (int x = 0; x < 3; x++) e->head_xpos[x] = k.xpos[0][x] + t[x];
+  }
+  for (int f = 0; f < 2; f++) {
+    int lk = f == 0 ? m->rfoot_link : m->lfoot_link;
+    double jp[3 * NV], v[3] = {0, 0, 0};
+    jac_point(m, &k, lk, k.xpos[lk], jp, 0);
+    for (int x = 0; x < 3; x++)
+      for (int d = 0; d < nv; d++) v[x] += jp[x * NV + d] * e->qvel[d];
+    memcpy(f == 0 ? e->rfoot_vel : e->lfoot_vel, v, sizeof(v));
+  }
+  e->rfoot_grf = e->lfoot_grf = 0;
+  e->ncon_r = e->ncon_l = 0;
+  e->ncon = efc.ncon;
+  e->contact_z_min = 0;
+  e->self_collision = 0;
+  int first = 1;
+  for (int ci = 0; ci < efc.ncon; ci++) {
+    const double* f = force + efc.con_row[ci];
+    double fn = f[0] + f[1] + f[2] + f[3], f1 = m->mu * (f[0] - f[1]), f2 = m->mu * (f[2] - f[3]);
+    double nrm = sqrt(fn * fn + f1 * f1 + f2 * f2); /* robot_interface.py:310-312 norm of mj_contactForce */
+    int lk = m->geom_link[efc.con_geom[ci]];
+    if (lk == m->rfoot_link) { e->rfoot_grf += nrm; e->ncon_r++; }
+    else if (lk == m->lfoot_link) { e->lfoot_grf += nrm; e->ncon_l++; }
+    if (first || efc.con_pos[ci][2] < e->contact_z_min) e->contact_z_min = efc.con_pos[ci][2];
+    first = 0;
+  }
+  /* ---- mj_Euler with implicit joint damping: (M + h B) qacc' = qfrc_smooth + qfrc_constraint */
+  double rhs[NV], G[NV * NV];
+  int any_damp = 0;
+  for (int d = 0; d < nv; d++) {
+    double t = qfs[d];
+    for (int r = 0; r < efc.nrow; r++) t += efc.J[r][d] * force[r];
+    rhs[d] = t;
+    if (m->damping[d] > 0) any_damp = 1;
+  }
+  if (efc.nrow == 0) memset(force, 0, sizeof(force));
+  if (any_damp) {
+    for (int a = 0; a < nv; a++)
+      for (int c = 0; c < nv; c++) G[a * nv + c] = M[a * NV + c] + (a == c ? h * m->damping[a] : 0);
+    chol(G, nv);
+    chol_solve(G, nv, rhs);
+  } else {
+    memcpy(rhs, qacc, nv * sizeof(double));
+  }
+  int bad = 0;
+  for (int d = 0; d < nv; d++) {
+    if (!(fabs(rhs[d]) < 1e10)) bad = 1;
+    e->qvel[d] += h * rhs[d];
+  }
+  for (int x = 0; x < 3; x++) e->qpos[x] += h * e->qvel[x];
+  {
+    double* q = e->qpos + 3;
+    double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; i++) q[i] /= nq;
+    const double* w = e->qvel + 3;
+    double wn = sqrt(dot3(w, w));
+    if (wn > MINVAL) {
+      double ang = h * wn, sa = sin(0.5 * ang) / wn, ca = cos(0.5 * ang);
+      double r[4] = {ca, w[0] * sa, w[1] * sa, w[2] * sa};
+      double o[4] = {q[0] * r[0] - q[1] * r[1] - q[2] * r[2] - q[3] * r[3],
+                     q[0] * r[1] + q[1] * r[0] + q[2] * r[3] - q[3] * r[2],
+                     q[0] * r[2] - q[1] * r[3] + q[2] * r[0] + q[3] * r[1],
+                     q[0] * r[3] + q[1] * r[2] - q[2] * r[1] + q[3] * r[0]};
+      double no = sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
+      for (int i = 0; i < 4; i++) q[i] = o[i] / no;
+    }
+  }
+  for (int u = 0; u < nu; u++) e->qpos[7 + u] += h * e->qvel[6 + u];
+  memcpy(e->qacc_warm, qacc, nv * sizeof(double));
+  if (bad) e->status |= 1;
+  e->nsubsteps++;
+}
+
+/* ------------------------------------------------------------------ observation / task */
+/* transforms3d.euler.quat2euler(q) (axes 'sxyz') roll and pitch, via quat2mat (tasks/observations.py:22) */
+void orc_quat2rp(const double* q, double* roll, double* pitch) {
+  double Nq = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  double s = 2.0 / Nq;
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  double X = x * s, Y = y * s, Z = z * s;
+  double wX = w * X, wY = w * Y, wZ = w * Z, xX = x * X, xY = x * Y, xZ = x * Z, yY = y * Y, yZ = y * Z;
+  double M00 = 1 - (yY + z * Z), M10 = xY + wZ, M20 = xZ - wY, M21 = yZ + wX, M22 = 1 - (xX + yY);
+  double cy = sqrt(M00 * M00 + M10 * M10);
+  if (cy > 4 * 2.220446049250313e-16) {
+    *roll = atan2(M21, M22);
+    *pitch = atan2(-M20, cy);
+  } else {
+    double M12 = yZ - wX, M11 = 1 - (xX + z * Z);
+    *roll = atan2(-M12, M11);
+    *pitch = atan2(-M20, cy);
+  }
+}
+
+static void get_obs(const orc_model* m, const orc_env* e, double* obs) {
+  int nu = m->nu, o = 0;
+  double r, p;
+  orc_quat2rp(e->qpos + 3, &r, &p);
+  obs[o++] = r; obs[o++] = p;
+  for (int x = 0; x < 3; x++) obs[o++] = e->qvel[3 + x];
+  for (int u = 0; u < nu; u++) obs[o++] = e->act_len[u];
+  for (int u = 0; u < nu; u++) obs[o++] = e->act_vel[u];
+  obs[o++] = sin(2 * M_PI * e->phase / m->period);
+  obs[o++] = cos(2 * M_PI * e->phase / m->period);
+  /* WalkModes.encode: STANDING [0,0,1], INPLACE [0,1,0], FORWARD [1,0,0] */
+  obs[o++] = e->mode == ORC_FORWARD; obs[o++] = e->mode == ORC_INPLACE; obs[o++] = e->mode == ORC_STANDING;
+  for (int x = 0; x < 3; x++) obs[o++] = e->mode_ref[x];
+}
+
+static void sample_ref(orc_env* e, uint32_t stream) {
+  uint32_t u[4];
+  orc_philox(e->seed, e->env_id, e->rng_ctr, stream, u);
+  if (e->mode == ORC_STANDING) {
+    for (int x = 0; x < 3; x++) e->mode_ref[x] = -1.0 + 2.0 * u01(u[x]);
+  } else if (e->mode == ORC_INPLACE) {
+    e->mode_ref[0] = -0.5 + u01(u[0]); e->mode_ref[1] = 0; e->mode_ref[2] = 0;
+  } else {
+    e->mode_ref[0] = 0; e->mode_ref[1] = 0.4 * u01(u[0]); e->mode_ref[2] = 0;
+  }
+}
+
+static void task_reset(const orc_model* m, orc_env* e) {
+  uint32_t u[4];
+  orc_philox(e->seed, e->env_id, e->rng_ctr, 3, u);
+  double c = u01(u[0]);
+  e->mode = c < 0.6 ? ORC_STANDING : (c < 0.8 ? ORC_INPLACE : ORC_FORWARD);
+  sample_ref(e, 4);
+  e->phase = randint(u[1], m->period);
+}
+
+static void task_step(const orc_model* m, orc_env* e) {
+  uint32_t u[4];
+  e->phase += 1;
+  if (e->phase >= m->period) e->phase = 0;
+  orc_philox(e->seed, e->env_id, e->rng_ctr, 0, u);
+  int dbl = m->clock[0][e->phase] == 1.0 && m->clock[2][e->phase] == 1.0;
+  if (randint(u[0], 100) == 0 && dbl) {
+    if (e->mode == ORC_INPLACE) e->mode = ORC_STANDING;
+    else if (e->mode == ORC_STANDING) e->mode = ORC_INPLACE;
+    sample_ref(e, 1);
+  }
+  if (randint(u[1], 200) == 0 && e->mode != ORC_STANDING) {
+    if (e->mode == ORC_FORWARD) e->mode = ORC_INPLACE;
+    else if (e->mode == ORC_INPLACE) e->mode = ORC_FORWARD;
+    sample_ref(e, 2);
+  }
+}
+
+/* WalkingTask.calc_reward (tasks/walking_task.py:85-147); t[10] in the dict's insertion order */
+static void calc_reward(const orc_model* m, const orc_env* e, const double* action, double* t) {
+  int nu = m->nu;
+  double rfc = m->clock[0][e->phase], rvc = m->clock[1][e->phase], lfc = m->clock[2][e->phase],
+         lvc = m->clock[3][e->phase];
+  double yaw_ref = e->mode_ref[0], vx = e->mode_ref[1], vy = e->mode_ref[2];
+  if (e->mode == ORC_STANDING) { rfc = lfc = 1; rvc = lvc = -1; yaw_ref = vx = vy = 0; }
+  else if (e->mode == ORC_INPLACE) { vx = vy = 0; }
+  else { yaw_ref = 0; }
+  double goal_speed = sqrt(vx * vx + vy * vy);
+  /* foot force / velocity clock scores (rewards.py:107-174) */
+  double fcap = m->total_mass * 9.8 * 0.5;
+  double nl = fmin(e->lfoot_grf, fcap) / fcap * 2 - 1, nr = fmin(e->rfoot_grf, fcap) / fcap * 2 - 1;
+  t[0] = 0.225 * ((tan(M_PI / 4 * lfc * nl) + tan(M_PI / 4 * rfc * nr)) / 2);
+  double lv = sqrt(dot3(e->lfoot_vel, e->lfoot_vel)), rv = sqrt(dot3(e->rfoot_vel, e->rfoot_vel));
+  double vl = fmin(lv, 0.2) / 0.2 * 2 - 1, vr = fmin(rv, 0.2) / 0.2 * 2 - 1;
+  t[1] = 0.225 * ((tan(M_PI / 4 * lvc * vl) + tan(M_PI / 4 * rvc * vr)) / 2);
+  /* root accel (rewards.py:93-104): current qvel[3:6], lagged qacc[0:3] */
+  double err = 0;
+  for (int x = 0; x < 3; x++) err += fabs(e->qvel[3 + x]);
+  for (int x = 0; x < 3; x++) err += fabs(e->qacc[x]);
+  t[2] = 0.05 * exp(-0.25 * err);
+  /* height (rewards.py:68-90) */
+  double cz = (e->ncon_r + e->ncon_l) > 0 ? e->contact_z_min : 0.0;
+  double herr = fabs(e->root_xpos[2] - cz - m->goal_height);
+  if (herr < 0.01 + 0.05 * goal_speed) herr = 0;
+  t[3] = 0.05 * exp(-40 * herr * herr);
+  /* planar velocity of the root origin in the root's local frame (mj_objectVelocity, flg_local=1) */
+  double vloc[3];
+  mattvec3(e->root_xmat, e->root_vlin, vloc);
+  double ex = vloc[0] - vx, ey = vloc[1] - vy;
+  t[4] = 0.15 * exp(-10 * (ex * ex + ey * ey));
+  double ye = fabs(e->qvel[5] - yaw_ref);
+  t[5] = 0.15 * exp(-10 * ye * ye * ye);
+  double hx = e->head_xpos[0] - e->root_xpos[0], hy = e->head_xpos[1] - e->root_xpos[1];
+  t[6] = 0.05 * exp(-10 * sqrt(hx * hx + hy * hy));
+  double pe = 0, te = 0, ae = 0;
+  for (int u = 0; u < nu; u++) {
+    double d = m->nominal_qpos[7 + u] - e->act_len[u];
+    pe += d * d;
+    te += fabs(e->prev_torque[u] - e->act_force[u]);
+    ae += fabs(e->prev_action[u] - action[u]);
+  }
+  t[7] = 0.05 * exp(-sqrt(pe));
+  t[8] = 0.025 * exp(-0.25 * (te / nu));
+  t[9] = 0.025 * exp(-5 * ae / nu);
+}
+
+void orc_env_init(const orc_model* m, orc_env* e, uint32_t seed, uint32_t env_id) {
+  (void)m;
+  memset(e, 0, sizeof(*e));
+  e->seed = seed;
+  e->env_id = env_id;
+  e->qpos[3] = 1.0;
+}
+
+void orc_reset(const orc_model* m, orc_env* e, double* obs) {
+  /* mj_resetData (mujoco_env.py:114): qvel, warmstart, ctrl <- 0 ; then reset_model: nominal pose, 3 zero-ctrl steps */
+  double zero[ORC_NU] = {0};
+  memcpy(e->qpos, m->nominal_qpos, m->nq * sizeof(double));
+  memset(e->qvel, 0, sizeof(e->qvel));
+  memset(e->qacc_warm, 0, sizeof(e->qacc_warm));
+  for (int i = 0; i < 3; i++) orc_mj_step(m, e, zero);
+  e->rng_ctr++;
+  task_reset(m, e);
+  memset(e->prev_prediction, 0, sizeof(e->prev_prediction));
+  e->traj_len = 0; e->ep_len = 0; e->ep_rew = 0;
+  if (obs) get_obs(m, e, obs);
+}
+
+void orc_step(const orc_model* m, orc_env* e, const double* action, double* obs, double* rew_terms, double* reward,
+              int* done) {
+  int nu = m->nu;
+  double target[ORC_NU], ctrl[ORC_NU], t[ORC_NREW];
+  /* base_humanoid_env.py:209-212 smoothing + nominal offsets ; robot_base.py:80 */
+  for (int u = 0; u < nu; u++)
+    target[u] = m->action_smoothing * action[u] + (1 - m->action_smoothing) * e->prev_prediction[u] + m->nominal_qpos[7 + u];
+  if (!e->have_prev) { /* robot_base.py:82-85 */
+    memcpy(e->prev_action, target, sizeof(target));
+    memcpy(e->prev_torque, e->act_force, sizeof(e->prev_torque));
+    e->have_prev = 1;
+  }
+  for (int s = 0; s < m->frame_skip; s++) {
+    for (int u = 0; u < nu; u++) ctrl[u] = m->kp[u] * (target[u] - e->act_len[u]) + m->kd[u] * (0.0 - e->act_vel[u]);
+    orc_mj_step(m, e, ctrl);
+  }
+  e->rng_ctr++;
+  task_step(m, e);
+  calc_reward(m, e, target, t);
+  int d = (e->qpos[2] < 0.6) || (e->qpos[2] > 1.4) || e->self_collision || e->status;
+  memcpy(e->prev_action, target, sizeof(target));
+  memcpy(e->prev_torque, e->act_force, sizeof(e->prev_torque));
+  if (obs) get_obs(m, e, obs);
+  memcpy(e->prev_prediction, action, nu * sizeof(double));
+  double sum = 0;
+  for (int i = 0; i < ORC_NREW; i++) sum += t[i];
+  if (rew_terms) memcpy(rew_terms, t, sizeof(t));
+  if (reward) *reward = sum;
+  if (done) *done = d;
+}
+
+void orc_step_autoreset(const orc_model* m, orc_env* e, const double* action, int max_traj_len, double* obs,
+                        double* term_obs, double* rew_terms, double* reward, int* done, int* ended) {
+  double r; int d;
+  double o[ORC_NOBS];
+  orc_step(m, e, action, o, rew_terms, &r, &d);
+  e->traj_len++; e->ep_len++; e->ep_rew += r;
+  int end = d || (e->traj_len >= max_traj_len);
+  if (term_obs) memcpy(term_obs, o, sizeof(o));
+  if (end) {
+    e->status = 0;
+    orc_reset(m, e, o);
+  }
+  if (obs) memcpy(obs, o, sizeof(o));
+  if (reward) *reward = r;
+  if (done) *done = d;
+  if (ended) *ended = end;
+}
+
+void orc_batch_reset(const orc_model* m, orc_env* envs, int n, double* obs, int nthreads) {
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : omp_get_max_threads()) schedule(static)
+#endif
+  for (int i = 0; i < n; i++) orc_reset(m, envs + i, obs ? obs + (size_t)i * ORC_NOBS : 0);
+  (void)nthreads;
+}
+
+void orc_batch_step_autoreset(const orc_model* m, orc_env* envs, int n, const double* actions, int max_traj_len,
+                              double* obs, double* term_obs, double* rew_terms, double* reward, int* done, int* ended,
+                              int nthreads) {
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : omp_get_max_threads()) schedule(dynamic, 4)
+#endif
+  for (int i = 0; i < n; i++)
+    orc_step_autoreset(m, envs + i, actions + (size_t)i * m->nu, max_traj_len, obs ? obs + (size_t)i * ORC_NOBS : 0,
+                       term_obs ? term_obs + (size_t)i * ORC_NOBS : 0, rew_terms ? rew_terms + (size_t)i * ORC_NREW : 0,
+                       reward ? reward + i : 0, done ? done + i : 0, ended ? ended + i : 0);
+  (void)nthreads;
+}

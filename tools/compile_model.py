@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""Model compiler: reference MJCF -> packed constant block for the on-device simulator.
+
+Runs in the build container only (it reads /root/reference, which does not exist on
+the GPU box); its OUTPUT (learninghumanoidwalking_b200/model/*.json) is committed.
+
+What it restates (never copies) from the reference:
+  * envs/jvrc/gen_xml.py:58-164   the MJCF surgery the reference performs with dm_control
+    (drop every joint except `root` + LEG_JOINTS, fix the arm pose through body eulers,
+    keep only leg collision geoms, add one collision box per foot, wrap the floor plane in
+    a body, export with precision=5 i.e. '%.5g' on every numeric attribute).
+  * models/jvrc_mj_description/xml/jvrc1.xml  (tree, inertials, joint axes/ranges/armature,
+    defaults: joint damping 0.2 + limited, option timestep/solver/cone).
+  * envs/jvrc/configs/base.yaml   (kp/kd, half-sitting pose, task durations).
+  * MuJoCo compile-time constants the runtime needs:
+    body_invweight0 / dof_invweight0 / stat.meaninertia at qpos0 (mj_setConst).
+
+dm_control and mujoco are not installed, so the surgery is re-done with xml.etree and the
+jointless bodies are welded into their nearest jointed ancestor ("link"): dynamics are
+identical (no DoF between them), 45 inertial bodies -> 13 links.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import xml.etree.ElementTree as ET
+
+import numpy as np
+import yaml
+
+REF = os.environ.get("LHW_REFERENCE", "/root/reference")
+
+JVRC_LEG_JOINTS = [
+    "R_HIP_P", "R_HIP_R", "R_HIP_Y", "R_KNEE", "R_ANKLE_R", "R_ANKLE_P",
+    "L_HIP_P", "L_HIP_R", "L_HIP_Y", "L_KNEE", "L_ANKLE_R", "L_ANKLE_P",
+]
+# gen_xml.py:92-101 — arm pose fixed through body eulers (radians, xyz)
+JVRC_ARM_EULER = {
+    "R_SHOULDER_P_S": [0, -0.052, 0],
+    "R_SHOULDER_R_S": [-0.17, 0, 0],
+    "R_ELBOW_P_S": [0, -0.524, 0],
+    "L_SHOULDER_P_S": [0, -0.052, 0],
+    "L_SHOULDER_R_S": [0.17, 0, 0],
+    "L_ELBOW_P_S": [0, -0.524, 0],
+}
+# gen_xml.py:104-111 — bodies whose collision meshes are kept (self-collision only)
+JVRC_COLLISION_BODIES = ["R_HIP_R_S", "R_HIP_Y_S", "R_KNEE_S", "L_HIP_R_S", "L_HIP_Y_S", "L_KNEE_S"]
+
+
+def r5(x: float) -> float:
+    """dm_control export_with_assets(precision=5) writes every number as '%.5g'."""
+    return float("%.5g" % float(x))
+
+
+def vec(s, n=None, default=None):
+    if s is None:
+        return None if default is None else np.array(default, dtype=float)
+    v = np.array([r5(t) for t in s.split()], dtype=float)
+    if n is not None:
+        assert v.shape == (n,), (s, n)
+    return v
+
+
+def quat2mat(q):
+    q = np.asarray(q, dtype=float)
+    q = q / np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)],
+    ])
+
+
+def euler_xyz2mat(e):
+    """MuJoCo eulerseq 'xyz' (intrinsic): R = Rx(e0) Ry(e1) Rz(e2)."""
+    cx, sx = np.cos(e[0]), np.sin(e[0])
+    cy, sy = np.cos(e[1]), np.sin(e[1])
+    cz, sz = np.cos(e[2]), np.sin(e[2])
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rx @ Ry @ Rz
+
+
+def skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+
+class Link:
+    def __init__(self, name, parent, pos, rot):
+        self.name = name
+        self.parent = parent  # link index or -1
+        self.pos = pos        # origin in parent-link frame
+        self.rot = rot        # orientation in parent-link frame (3x3)
+        self.joint = None     # dict(type, axis, armature, damping, range, name)
+        self.mass = 0.0
+        self.mc = np.zeros(3)         # sum m*c (link frame)
+        self.Io = np.zeros((3, 3))    # inertia about link origin (link frame)
+        self.members = {}     # xml body name -> (pos, rot) in link frame
+        self.geoms = []
+
+    def add_inertial(self, m, c, Ic):
+        """Add a rigid piece: mass m, com c, inertia about its com Ic — all in link frame."""
+        self.mass += m
+        self.mc += m * c
+        self.Io += Ic + m * (np.dot(c, c) * np.eye(3) - np.outer(c, c))
+
+    def finalize(self):
+        c = self.mc / self.mass
+        Ic = self.Io - self.mass * (np.dot(c, c) * np.eye(3) - np.outer(c, c))
+        return c, 0.5 * (Ic + Ic.T)
+
+
+def compile_jvrc(boxes: bool = False):
+    xml_dir = os.path.join(REF, "models/jvrc_mj_description/xml")
+    root = ET.parse(os.path.join(xml_dir, "jvrc1.xml")).getroot()
+    cfg = yaml.safe_load(open(os.path.join(REF, "envs/jvrc/configs/base.yaml")))
+
+    opt = root.find("option").attrib
+    timestep = r5(opt["timestep"])
+    assert opt["solver"] == "Newton" and opt["cone"] == "pyramidal"
+    jdef = root.find("default").find("joint").attrib
+    joint_damping_default = r5(jdef["damping"])
+    assert jdef["limited"] == "true"
+
+    keep = set(JVRC_LEG_JOINTS)
+    links: list[Link] = []
+
+    def walk(body, link_idx, pos_in_link, rot_in_link):
+        """body: xml element; (pos,rot) of this xml body's frame expressed in link link_idx."""
+        name = body.attrib["name"]
+        jel = body.find("joint")
+        fj = body.find("freejoint")
+        jointed = fj is not None or (jel is not None and jel.attrib["name"] in keep)
+        if jointed:
+            lk = Link(name, link_idx, pos_in_link, rot_in_link)
+            if fj is not None:
+                # <freejoint> takes no defaults: damping 0, armature 0 (MuJoCo XML reference)
+                lk.joint = dict(type="free", name=fj.attrib["name"])
+            else:
+                lk.joint = dict(
+                    type="hinge", name=jel.attrib["name"],
+                    axis=vec(jel.attrib["axis"], 3),
+                    armature=r5(jel.attrib.get("armature", 0)),
+                    damping=r5(jel.attrib.get("damping", joint_damping_default)),
+                    range=vec(jel.attrib["range"], 2),
+                )
+                assert np.allclose(vec(jel.attrib.get("pos", "0 0 0"), 3), 0)
+            links.append(lk)
+            link_idx = len(links) - 1
+            pos_in_link, rot_in_link = np.zeros(3), np.eye(3)
+        lk = links[link_idx]
+        lk.members[name] = (pos_in_link.copy(), rot_in_link.copy())
+        ine = body.find("inertial")
+        m = r5(ine.attrib["mass"])
+        ipos = vec(ine.attrib.get("pos", "0 0 0"), 3)
+        iquat = vec(ine.attrib.get("quat", "1 0 0 0"), 4)
+        diag = vec(ine.attrib["diaginertia"], 3)
+        Ri = rot_in_link @ quat2mat(iquat)
+        lk.add_inertial(m, pos_in_link + rot_in_link @ ipos, Ri @ np.diag(diag) @ Ri.T)
+        for child in body.findall("body"):
+            cpos = vec(child.attrib.get("pos", "0 0 0"), 3)
+            crot = np.eye(3)
+            if "quat" in child.attrib:
+                crot = quat2mat(vec(child.attrib["quat"], 4))
+            if child.attrib["name"] in JVRC_ARM_EULER:
+                crot = euler_xyz2mat([r5(e) for e in JVRC_ARM_EULER[child.attrib["name"]]])
+            walk(child, link_idx, pos_in_link + rot_in_link @ cpos, rot_in_link @ crot)
+
+    pelvis = root.find("worldbody").find("body")
+    assert pelvis.attrib["name"] == "PELVIS_S"
+    qpos0_root = vec(pelvis.attrib["pos"], 3)
+    walk(pelvis, -1, np.zeros(3), np.eye(3))
+
+    # dof order = joint order in the XML depth-first traversal == LEG_JOINTS order (gen_xml.py:42-55)
+    names = [lk.joint["name"] for lk in links[1:]]
+    assert names == JVRC_LEG_JOINTS, names
+
+    model = dict(name="jvrc_step" if boxes else "jvrc_walk")
+    model["opt"] = dict(
+        timestep=timestep, gravity=[0.0, 0.0, -9.81],
+        solver="Newton", iterations=int(opt["iterations"]), tolerance=float(opt["tolerance"]),
+        cone="pyramidal", impratio=1.0,
+        # MuJoCo defaults, nothing in the reference overrides them
+        solref=[0.02, 1.0], solimp=[0.9, 0.95, 0.001, 0.5, 2.0], friction=[1.0, 0.005, 0.0001],
+    )
+    out_links = []
+    for i, lk in enumerate(links):
+        c, Ic = lk.finalize()
+        d = dict(name=lk.name, parent=lk.parent, pos=lk.pos.tolist(), rot=lk.rot.tolist(),
+                 mass=lk.mass, com=c.tolist(),
+                 inertia=[Ic[0, 0], Ic[1, 1], Ic[2, 2], Ic[0, 1], Ic[0, 2], Ic[1, 2]],
+                 members=sorted(lk.members))
+        j = lk.joint
+        if j["type"] == "free":
+            d["joint"] = dict(type="free", name=j["name"])
+        else:
+            d["joint"] = dict(type="hinge", name=j["name"], axis=j["axis"].tolist(), armature=j["armature"],
+                              damping=j["damping"], range=j["range"].tolist())
+        out_links.append(d)
+    model["links"] = out_links
+    model["qpos0"] = qpos0_root.tolist() + [1.0, 0.0, 0.0, 0.0] + [0.0] * 12
+
+    # feet: gen_xml.py:125-130 (collision box per foot, class collision => condim 3)
+    foot_size = [r5(0.1), r5(0.05), r5(0.01)]
+    foot_pos = [r5(0.029), 0.0, r5(-0.09778)]
+    li = {lk.name: i for i, lk in enumerate(links)}
+    model["geoms"] = [
+        dict(name="R_ANKLE_P_S-foot", type="box", link=li["R_ANKLE_P_S"], pos=foot_pos, size=foot_size),
+        dict(name="L_ANKLE_P_S-foot", type="box", link=li["L_ANKLE_P_S"], pos=foot_pos, size=foot_size),
+    ]
+    model["rfoot_link"] = li["R_ANKLE_P_S"]
+    model["lfoot_link"] = li["L_ANKLE_P_S"]
+    # head body NECK_P_S is welded into the root link; its origin in the root frame:
+    model["head_in_root"] = links[0].members["NECK_P_S"][0].tolist()
+    model["total_mass"] = float(sum(lk.mass for lk in links))
+
+    # env config (envs/jvrc/configs/base.yaml, envs/jvrc/jvrc_base.py:38-67)
+    model["cfg"] = dict(
+        sim_dt=cfg["sim_dt"], control_dt=cfg["control_dt"], frame_skip=int(round(cfg["control_dt"] / cfg["sim_dt"])),
+        action_smoothing=cfg["action_smoothing"], obs_history_len=cfg["obs_history_len"],
+        kp=[float(x) for x in cfg["kp"]], kd=[float(x) for x in cfg["kd"]],
+        half_sitting_pose_deg=[float(x) for x in cfg["half_sitting_pose"]],
+        nominal_qpos=[0.0, 0.0, 0.81, 1.0, 0.0, 0.0, 0.0] + np.deg2rad(cfg["half_sitting_pose"]).tolist(),
+        task=dict(cfg["task"]),
+    )
+    add_setconst(model)
+    return model
+
+
+# ----------------------------------------------------------------------------------------------
+# mj_setConst restatement: mass matrix at qpos0 -> dof_invweight0, body_invweight0, meaninertia
+# (numpy, generic tree; also used by tests as a third independent mass-matrix implementation)
+# ----------------------------------------------------------------------------------------------
+
+def kinematics(model, qpos):
+    links = model["links"]
+    n = len(links)
+    xpos = np.zeros((n, 3))
+    xmat = np.zeros((n, 3, 3))
+    adr = 7
+    for i, lk in enumerate(links):
+        if lk["joint"]["type"] == "free":
+            xpos[i] = qpos[0:3]
+            xmat[i] = quat2mat(qpos[3:7])
+        else:
+            p = lk["parent"]
+            ax = np.array(lk["joint"]["axis"])
+            q = qpos[adr]
+            adr += 1
+            K = skew(ax / np.linalg.norm(ax))
+            Rj = np.eye(3) + np.sin(q) * K + (1 - np.cos(q)) * K @ K
+            xpos[i] = xpos[p] + xmat[p] @ np.array(lk["pos"])
+            xmat[i] = xmat[p] @ np.array(lk["rot"]) @ Rj
+    return xpos, xmat
+
+
+def dof_jacobians(model, qpos, point, link):
+    """3xnv translational jacobian of world `point` rigidly attached to `link`, and 3xnv rotational."""
+    links = model["links"]
+    xpos, xmat = kinematics(model, qpos)
+    nv = 6 + len(links) - 1
+    jp = np.zeros((3, nv))
+    jr = np.zeros((3, nv))
+    b = link
+    while b >= 0:
+        lk = links[b]
+        if lk["joint"]["type"] == "free":
+            jp[:, 0:3] = np.eye(3)
+            for k in range(3):
+                a = xmat[b][:, k]
+                jr[:, 3 + k] = a
+                jp[:, 3 + k] = np.cross(a, point - xpos[b])
+        else:
+            d = 6 + (b - 1)
+            a = xmat[b] @ np.array(lk["joint"]["axis"])
+            jr[:, d] = a
+            jp[:, d] = np.cross(a, point - xpos[b])
+        b = lk["parent"]
+    return jp, jr
+
+
+def mass_matrix(model, qpos):
+    links = model["links"]
+    xpos, xmat = kinematics(model, qpos)
+    nv = 6 + len(links) - 1
+    M = np.zeros((nv, nv))
+    for i, lk in enumerate(links):
+        c = xpos[i] + xmat[i] @ np.array(lk["com"])
+        a = lk["inertia"]
+        Ib = np.array([[a[0], a[3], a[4]], [a[3], a[1], a[5]], [a[4], a[5], a[2]]])
+        Iw = xmat[i] @ Ib @ xmat[i].T
+        jp, jr = dof_jacobians(model, qpos, c, i)
+        M += lk["mass"] * jp.T @ jp + jr.T @ Iw @ jr
+    for i, lk in enumerate(links):
+        if lk["joint"]["type"] == "hinge":
+            M[6 + i - 1, 6 + i - 1] += lk["joint"]["armature"]
+    return M
+
+
+def add_setconst(model):
+    qpos0 = np.array(model["qpos0"])
+    M = mass_matrix(model, qpos0)
+    Minv = np.linalg.inv(M)
+    nv = M.shape[0]
+    dofw = np.diag(Minv).copy()
+    # free joint: translational and rotational dofs each share their mean (engine_setconst.c set0)
+    dofw[0:3] = dofw[0:3].mean()
+    dofw[3:6] = dofw[3:6].mean()
+    xpos, xmat = kinematics(model, qpos0)
+    bw = []
+    for i, lk in enumerate(model["links"]):
+        c = xpos[i] + xmat[i] @ np.array(lk["com"])
+        jp, jr = dof_jacobians(model, qpos0, c, i)
+        J = np.vstack([jp, jr])
+        A = J @ Minv @ J.T
+        bw.append([float(np.trace(A[:3, :3]) / 3), float(np.trace(A[3:, 3:]) / 3)])
+    model["dof_invweight0"] = dofw.tolist()
+    model["link_invweight0"] = bw
+    model["meaninertia"] = float(np.trace(M) / nv)
+    # MuJoCo's body_invweight0 is per *xml body*; the only bodies that ever carry contact rows here
+    # are the feet (leaf links, no welded children => identical to the link value) and the world (0).
+    # For welded members that differ from their link com the value would differ; record the caveat.
+    model["notes"] = [
+        "numeric attributes rounded with '%.5g' (dm_control export precision=5) — unverified against a live export",
+        "link_invweight0 evaluated at the LINK com; equals MuJoCo body_invweight0 only for links without welded children",
+    ]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..",
+                                                  "learninghumanoidwalking_b200", "model"))
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+    m = compile_jvrc()
+    path = os.path.join(args.out, "jvrc_walk.json")
+    with open(path, "w") as f:
+        json.dump(m, f, indent=1)
+    print("wrote", path, "mass", m["total_mass"], "links", len(m["links"]), "meaninertia", m["meaninertia"])
+    for lk in m["links"]:
+        print(f"  {lk['name']:14s} parent {lk['parent']:2d} mass {lk['mass']:.4f} com {np.round(lk['com'], 4)}")
+    print("foot invweight0", m["link_invweight0"][m["rfoot_link"]], "dof_invweight0", np.round(m["dof_invweight0"], 4))
+
+
+if __name__ == "__main__":
+    main()
