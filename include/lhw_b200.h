@@ -1,0 +1,102 @@
+/*
+ * lhw_b200.h — C-ABI of the B200-native rollout / PPO data path (liblhw_b200.so).
+ *
+ * The reference (rohanpsingh/LearningHumanoidWalking) has no FFI of its own: its seams are Python
+ * duck-typed protocols and the arithmetic sits behind the `mujoco` pybind module.  Each entry point
+ * below names the reference interface it replaces (paths relative to the reference repo root).
+ * Plain pointers and sizes only; all buffers are caller-owned DEVICE memory (the Python host uses
+ * torch tensors) unless a parameter says "host".  `stream` is a cudaStream_t passed as void*.
+ * Every function returns 0 on success, a negative code on error (lhw_last_error() has the text).
+ *
+ * `precision` is 64 (float64 state and arithmetic, the reference's numeric type) or 32 (float32).
+ * Typed `void*` buffers hold doubles or floats accordingly.
+ */
+#ifndef LHW_B200_H
+#define LHW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lhw_sim lhw_sim;
+
+int lhw_version(void);
+const char* lhw_last_error(void);
+
+/* ---- environment batch --------------------------------------------------------------------------
+ * lhw_sim_create: replaces MujocoEnv.__init__ (envs/common/mujoco_env.py:16-36: MjSpec.compile +
+ * MjData) and JvrcBaseEnv._setup_robot (envs/jvrc/jvrc_base.py:38-67): takes the compiled model
+ * constants as a flat HOST float64 array (layout: learninghumanoidwalking_b200/model/loader.py). */
+int lhw_sim_create(lhw_sim** out, const double* model_flat_host, int n_flat, int precision, int device);
+int lhw_sim_destroy(lhw_sim* sim);
+int lhw_sim_state_reals(const lhw_sim* sim); /* real words per env in the state record */
+int lhw_sim_state_ints(const lhw_sim* sim);  /* int32 words per env in the state record */
+int lhw_sim_obs_dim(const lhw_sim* sim);     /* env.observation_space.shape[0] (37 for jvrc_walk) */
+int lhw_sim_act_dim(const lhw_sim* sim);     /* env.action_space.shape[0] (12) */
+int lhw_sim_smem_bytes_per_env(const lhw_sim* sim);
+
+/* lhw_sim_reset: MujocoEnv.reset + BaseHumanoidEnv.reset_model + WalkingTask.reset
+ * (envs/common/mujoco_env.py:113-116, envs/common/base_humanoid_env.py:247-276,
+ * tasks/walking_task.py:194-205) for every env whose mask[i] != 0 (mask == NULL: all).
+ * `fresh` != 0 zero-initialises the record first (a newly constructed env).
+ * state_r: [n_envs, state_reals] reals; state_i: [n_envs, state_ints] int32; obs: [n_envs, obs_dim]. */
+int lhw_sim_reset(lhw_sim* sim, void* state_r, int32_t* state_i, int n_envs, uint32_t seed, uint32_t first_env_id,
+                  const int32_t* mask, int fresh, void* obs, void* stream);
+
+/* lhw_sim_step: BaseHumanoidEnv.step (envs/common/base_humanoid_env.py:199-227) ->
+ * RobotBase.step/_do_simulation (robots/robot_base.py:41-98) -> frame_skip x {RobotInterface.step_pd,
+ * set_motor_torque, mujoco.mj_step} (envs/common/robot_interface.py:493-546) -> WalkingTask.step /
+ * calc_reward / done (tasks/walking_task.py:85-192) -> get_obs (base_humanoid_env.py:177-197), for
+ * n_envs environments in one launch.  With autoreset != 0 it also does the RolloutWorker's episode
+ * bookkeeping (rl/workers/rollout_worker.py:146-176): ended = done || traj_len >= max_traj_len; an ended env
+ * is reset inside the same launch and `obs` is the post-reset observation while `term_obs` keeps the
+ * pre-reset one (for the truncation bootstrap critic(next_state)).
+ * actions [n,act_dim]; obs, term_obs [n,obs_dim]; reward [n]; rew_terms [n,10] (may be NULL);
+ * done, ended, ep_len [n] int32; ep_rew [n]  (ep_len/ep_rew written only where ended). */
+int lhw_sim_step(lhw_sim* sim, void* state_r, int32_t* state_i, int n_envs, uint32_t seed, uint32_t first_env_id,
+                 const void* actions, int max_traj_len, int autoreset, void* obs, void* term_obs, void* reward,
+                 void* rew_terms, int32_t* done, int32_t* ended, int32_t* ep_len, void* ep_rew, void* stream);
+
+/* number of kernels this library has launched since load (the bench's gpu_launches claim) */
+long long lhw_launch_count(void);
+
+/* ---- PPO data path (float32, as rl/algos/ppo.py:474-477 casts the batch) ---------------------------
+ * lhw_gae: PPOBuffer.finish_path (rl/storage/rollout_storage.py:53-85) for a [T, N] rollout stored time-major:
+ * per env a reverse scan with the path broken wherever ended[t] != 0, bootstrapping with boot[t] there
+ * ((not done) * critic(next_state), rl/workers/rollout_worker.py:166) and with last_val[n] after t = T-1
+ * when the final transition did not end an episode (rollout_worker.py:183-186).
+ * rewards, values, boot [T,N] f32; ended [T,N] int32; last_val [N]; returns [T,N] out. */
+int lhw_gae(const float* rewards, const float* values, const int32_t* ended, const float* boot, const float* last_val,
+            float* returns, int T, int N, float gamma, float lam, void* stream);
+
+/* lhw_adv_norm: rl/algos/ppo.py:484-485 — adv = returns - values; (adv - mean) / (std_unbiased + eps).
+ * stats: device scratch of lhw_adv_stats_words() doubles, {sum, sumsq, mean, std, per-block partials...}
+ * (partials are combined in a fixed order, so the result is run-to-run deterministic). With world > 1 the
+ * caller all-reduces stats[0:2] between lhw_adv_stats and lhw_adv_apply (count_total = global sample count). */
+int lhw_adv_stats_words(void);
+int lhw_adv_stats(const float* returns, const float* values, double* stats, long long count, void* stream);
+int lhw_adv_apply(const float* returns, const float* values, float* adv, double* stats, long long count,
+                  long long count_total, float eps, void* stream);
+
+/* lhw_gather_minibatch: the fancy-index gathers of rl/algos/ppo.py:535-538 in one launch.
+ * idx [B] int64 sample indices into the flattened batch. */
+int lhw_gather_minibatch(const float* obs, const float* act, const float* ret, const float* adv, const int64_t* idx,
+                         float* obs_b, float* act_b, float* ret_b, float* adv_b, int B, int obs_dim, int act_dim,
+                         void* stream);
+
+/* lhw_clip_adam: torch.nn.utils.clip_grad_norm_(params, max_norm) followed by optim.Adam.step
+ * (rl/algos/ppo.py:393-396, Adam(lr, eps) created at :429-430) over ONE flat parameter buffer:
+ * lhw_grad_sumsq accumulates sum(g^2) into norm_scratch[0] (zeroed by the call), lhw_clip_adam applies
+ * clip_coef = min(1, max_norm / (sqrt(sumsq) + 1e-6)) and the Adam update (beta1 .9, beta2 .999, no weight
+ * decay, no amsgrad). grad_scale multiplies g first (1/world after a sum all-reduce). */
+int lhw_grad_sumsq(const float* grad, float* norm_scratch, long long n, float grad_scale, void* stream);
+int lhw_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* norm_scratch,
+                  long long n, int step, float lr, float beta1, float beta2, float eps, float max_norm,
+                  float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,72 @@
+"""ctypes binding of liblhw_b200.so (include/lhw_b200.h).  No fallback: if the CUDA library is missing the
+import of any product module that needs it raises — the hot path never silently runs on the CPU."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "liblhw_b200.so")
+
+c_void_p, c_int, c_uint32, c_float, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_float, ctypes.c_longlong
+
+# name -> (restype, argtypes); mirrors include/lhw_b200.h one to one
+SIGNATURES = {
+    "lhw_version": (c_int, []),
+    "lhw_last_error": (ctypes.c_char_p, []),
+    "lhw_sim_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int, c_int, c_int]),
+    "lhw_sim_destroy": (c_int, [c_void_p]),
+    "lhw_sim_state_reals": (c_int, [c_void_p]),
+    "lhw_sim_state_ints": (c_int, [c_void_p]),
+    "lhw_sim_obs_dim": (c_int, [c_void_p]),
+    "lhw_sim_act_dim": (c_int, [c_void_p]),
+    "lhw_sim_smem_bytes_per_env": (c_int, [c_void_p]),
+    "lhw_sim_reset": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_void_p, c_int, c_void_p, c_void_p]),
+    "lhw_sim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_void_p, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lhw_launch_count": (c_ll, []),
+    "lhw_gae": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
+    "lhw_adv_stats_words": (c_int, []),
+    "lhw_adv_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "lhw_adv_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_float, c_void_p]),
+    "lhw_gather_minibatch": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p]),
+    "lhw_grad_sumsq": (c_int, [c_void_p, c_void_p, c_ll, c_float, c_void_p]),
+    "lhw_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_float,
+                              c_float, c_float, c_float, c_void_p]),
+}
+
+_lib = None
+
+
+class LhwError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LhwError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built (python -m learninghumanoidwalking_b200.build "
+                "or __graft_entry__.build()). There is no CPU fallback for the rollout / PPO data path.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise LhwError(f"{what} failed (rc={rc}): {lib().lhw_last_error().decode(errors='replace')}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None passes NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

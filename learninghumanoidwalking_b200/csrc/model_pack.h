@@ -1,0 +1,87 @@
+// model_pack.h — host-side: fill lhw::Model<real,NJ> from the flat double array the Python host passes over the
+// C-ABI (layout produced by learninghumanoidwalking_b200/model/loader.py:pack_model; keep in sync).
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include "sim_core.h"
+
+namespace lhw {
+
+// returns 0 on success, negative on malformed input
+template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b, int n) {
+  constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ;
+  int p = 0;
+  auto rd = [&]() -> double { return p < n ? b[p++] : (p++, 0.0); };
+  memset(&m, 0, sizeof(m));
+  if ((int)rd() != NJ) return -1;
+  for (int i = 0; i < NL; i++) {
+    for (int k = 0; k < 3; k++) m.link_pos[i][k] = (real)rd();
+    for (int k = 0; k < 9; k++) m.link_rot[i][k] = (real)rd();
+    for (int k = 0; k < 3; k++) m.axis[i][k] = (real)rd();
+    m.mass[i] = (real)rd();
+    for (int k = 0; k < 3; k++) m.com[i][k] = (real)rd();
+    for (int k = 0; k < 6; k++) m.inertia[i][k] = (real)rd();
+  }
+  m.any_damping = 0;
+  for (int d = 0; d < NV; d++) {
+    m.armature[d] = (real)rd();
+    m.damping[d] = (real)rd();
+    m.range_lo[d] = (real)rd();
+    m.range_hi[d] = (real)rd();
+    m.dof_invw[d] = (real)rd();
+    if (m.damping[d] > 0) m.any_damping = 1;
+  }
+  for (int f = 0; f < 2; f++) {
+    for (int k = 0; k < 3; k++) m.foot_pos[f][k] = (real)rd();
+    for (int k = 0; k < 3; k++) m.foot_size[f][k] = (real)rd();
+    m.foot_invw[f] = (real)rd();
+  }
+  const double h = rd();
+  m.h = (real)h;
+  for (int k = 0; k < 3; k++) m.grav[k] = (real)rd();
+  double solref[2], solimp[5];
+  for (int k = 0; k < 2; k++) solref[k] = rd();
+  for (int k = 0; k < 5; k++) solimp[k] = rd();
+  const double mu = rd(), impratio = rd(), meaninertia = rd(), tolerance = rd();
+  m.max_iter = (int)rd();
+  // MuJoCo mj_makeImpedance: refsafe clamps the time constant to 2 h; K, B from (timeconst, dampratio) and dmax
+  double tau = solref[0] < 2 * h ? 2 * h : solref[0], zeta = solref[1];
+  for (int k = 0; k < 2; k++) solimp[k] = solimp[k] < 0.0001 ? 0.0001 : (solimp[k] > 0.9999 ? 0.9999 : solimp[k]);
+  const double dmax = solimp[1];
+  m.K = (real)(1.0 / fmax(1e-15, dmax * dmax * tau * tau * zeta * zeta));
+  m.B = (real)(2.0 / fmax(1e-15, dmax * tau));
+  for (int k = 0; k < 5; k++) m.solimp[k] = (real)solimp[k];
+  m.mu = (real)mu;
+  m.mu_reg = (real)(mu * sqrt(1.0 / fmax(1e-15, impratio)));
+  const double t = tolerance * meaninertia * (NV > 1 ? NV : 1);
+  m.tol2 = (real)(t * t);
+  for (int k = 0; k < NU; k++) m.kp[k] = (real)rd();
+  for (int k = 0; k < NU; k++) m.kd[k] = (real)rd();
+  for (int k = 0; k < NQ; k++) m.nominal[k] = (real)rd();
+  m.smoothing = (real)rd();
+  m.frame_skip = (int)rd();
+  for (int k = 0; k < 3; k++) m.head[k] = (real)rd();
+  const double total_mass = rd();
+  m.fcap = (real)(total_mass * 9.8 * 0.5);  // tasks/rewards.py:129
+  m.goal_height = (real)rd();
+  m.period = (int)rd();
+  if (m.period < 1 || m.period > MAXPERIOD) return -2;
+  for (int c = 0; c < 4; c++)
+    for (int k = 0; k < m.period; k++) m.clock[c][k] = (real)rd();
+  if (p != n) return -3;
+  // structurally non-zero lower-triangle entries of the arrow matrix
+  int t_ = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j <= i; j++) { m.h_i[t_] = (unsigned char)i; m.h_j[t_] = (unsigned char)j; t_++; }
+  for (int c = 0; c < 2; c++)
+    for (int k = 0; k < NJ; k++) {
+      const int i = 6 + c * NJ + k;
+      for (int j = 0; j < 6; j++) { m.h_i[t_] = (unsigned char)i; m.h_j[t_] = (unsigned char)j; t_++; }
+      for (int kk = 0; kk <= k; kk++) { m.h_i[t_] = (unsigned char)i; m.h_j[t_] = (unsigned char)(6 + c * NJ + kk); t_++; }
+    }
+  if (t_ != Model<real, NJ>::NT) return -4;
+  return 0;
+}
+
+}  // namespace lhw

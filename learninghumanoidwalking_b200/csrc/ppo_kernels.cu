@@ -1,0 +1,212 @@
+// ppo_kernels.cu — sm_100a kernels for the PPO data path (include/lhw_b200.h, "PPO data path").
+// All of these are HBM-streaming ops; the rollout is stored time-major [T, N, .] so that every access below is
+// coalesced across the env index.  Replaces rl/storage/rollout_storage.py:53-85 (GAE), rl/algos/ppo.py:484-485
+// (advantage normalisation), :535-538 (minibatch gathers) and :393-396 (clip_grad_norm_ + Adam.step).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/lhw_b200.h"
+
+extern "C" void lhw_count_launch(void);
+
+namespace {
+
+thread_local std::string g_perr;
+
+// GAE(lambda): one thread per env, reverse scan over time; float64 accumulation like the reference's buffers
+__global__ void gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const int32_t* __restrict__ ended,
+                           const float* __restrict__ boot, const float* __restrict__ last_val, float* __restrict__ ret,
+                           int T, int N, double gamma, double lam) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double next_val = (double)last_val[n], gae = 0.0;
+  const double gl = gamma * lam;
+  for (int t = T - 1; t >= 0; t--) {
+    const size_t i = (size_t)t * N + n;
+    if (ended[i]) { next_val = (double)boot[i]; gae = 0.0; }
+    const double v = (double)val[i];
+    const double delta = (double)rew[i] + gamma * next_val - v;
+    gae = delta + gl * gae;
+    ret[i] = (float)(gae + v);
+    next_val = v;
+  }
+}
+
+// deterministic block reduction helper (fixed tree)
+template <int BLOCK> __device__ __forceinline__ double block_sum(double v, double* sh) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  v = threadIdx.x < BLOCK / 32 ? sh[threadIdx.x] : 0.0;
+  if (warp == 0)
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  return v;  // valid in warp 0
+}
+
+constexpr int STAT_BLOCKS = 148;  // one partial per SM; partials are combined in a fixed order -> deterministic
+// stats layout (double[4 + 2*STAT_BLOCKS]): {sum, sumsq, mean, std, partial sums..., partial sumsq...}
+__global__ void __launch_bounds__(1024) adv_partial_kernel(const float* __restrict__ ret, const float* __restrict__ val,
+                                                           double* __restrict__ stats, long long n) {
+  __shared__ double sh[32];
+  double s = 0, ss = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = (double)ret[i] - (double)val[i];
+    s += a;
+    ss += a * a;
+  }
+  s = block_sum<1024>(s, sh);
+  ss = block_sum<1024>(ss, sh);
+  if (threadIdx.x == 0) {
+    stats[4 + blockIdx.x] = s;
+    stats[4 + STAT_BLOCKS + blockIdx.x] = ss;
+  }
+}
+__global__ void adv_final_kernel(double* __restrict__ stats) {
+  if (threadIdx.x == 0) {
+    double s = 0, ss = 0;
+    for (int b = 0; b < STAT_BLOCKS; b++) { s += stats[4 + b]; ss += stats[4 + STAT_BLOCKS + b]; }
+    stats[0] = s;
+    stats[1] = ss;
+  }
+}
+__global__ void adv_apply_kernel(const float* __restrict__ ret, const float* __restrict__ val, float* __restrict__ adv,
+                                 double* __restrict__ stats, long long n, long long n_total, double eps) {
+  const double mean = stats[0] / (double)n_total;
+  double var = (stats[1] - (double)n_total * mean * mean) / (double)(n_total - 1);  // unbiased, torch.std default
+  if (var < 0) var = 0;
+  const double sd = sqrt(var);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { stats[2] = mean; stats[3] = sd; }
+  const float fm = (float)mean, inv = (float)(1.0 / (sd + eps));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    adv[i] = ((ret[i] - val[i]) - fm) * inv;
+}
+
+__global__ void gather_kernel(const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ ret,
+                              const float* __restrict__ adv, const int64_t* __restrict__ idx, float* __restrict__ obs_b,
+                              float* __restrict__ act_b, float* __restrict__ ret_b, float* __restrict__ adv_b, int B,
+                              int obs_dim, int act_dim) {
+  const int cols = obs_dim + act_dim + 2;
+  const long long total = (long long)B * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / cols), c = (int)(i - (long long)b * cols);
+    const long long src = idx[b];
+    if (c < obs_dim) obs_b[(size_t)b * obs_dim + c] = obs[src * obs_dim + c];
+    else if (c < obs_dim + act_dim) act_b[(size_t)b * act_dim + (c - obs_dim)] = act[src * act_dim + (c - obs_dim)];
+    else if (c == obs_dim + act_dim) ret_b[b] = ret[src];
+    else adv_b[b] = adv[src];
+  }
+}
+
+// ||g||^2 with a single block: fixed summation order -> run-to-run deterministic (the reference's determinism
+// tests demand bit-identical weights for identical seeds, tests/test_determinism.py:79-146)
+__global__ void __launch_bounds__(1024) sumsq_kernel(const float* __restrict__ g, float* __restrict__ out, long long n,
+                                                     float scale) {
+  __shared__ double sh[32];
+  double s = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = (double)(g[i] * scale);
+    s += v * v;
+  }
+  s = block_sum<1024>(s, sh);
+  if (threadIdx.x == 0) out[0] = (float)s;
+}
+
+__global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, const float* __restrict__ sumsq, long long n, float lr, float b1,
+                                 float b2, float eps, float max_norm, float scale, float bc1, float bc2_sqrt) {
+  const float total_norm = sqrtf(sumsq[0]);
+  float coef = max_norm / (total_norm + 1e-6f);
+  coef = coef > 1.0f ? 1.0f : coef;
+  const float gs = scale * coef, step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float mi = m[i] + (1.0f - b1) * (gi - m[i]);
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
+int perr(int code, const char* what, cudaError_t e) {
+  g_perr = std::string(what) + ": " + cudaGetErrorString(e);
+  return code;
+}
+#define KCHECK(what)                                   \
+  do {                                                 \
+    lhw_count_launch();                                \
+    cudaError_t _e = cudaGetLastError();               \
+    if (_e != cudaSuccess) return perr(-10, what, _e); \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int lhw_gae(const float* rewards, const float* values, const int32_t* ended, const float* boot, const float* last_val,
+            float* returns, int T, int N, float gamma, float lam, void* stream) {
+  if (T <= 0 || N <= 0) return 0;
+  gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, values, ended, boot, last_val, returns, T, N,
+                                                                (double)gamma, (double)lam);
+  KCHECK("gae_kernel");
+  return 0;
+}
+
+int lhw_adv_stats_words(void) { return 4 + 2 * STAT_BLOCKS; }
+
+int lhw_adv_stats(const float* returns, const float* values, double* stats, long long count, void* stream) {
+  adv_partial_kernel<<<STAT_BLOCKS, 1024, 0, (cudaStream_t)stream>>>(returns, values, stats, count);
+  KCHECK("adv_partial_kernel");
+  adv_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats);
+  KCHECK("adv_final_kernel");
+  return 0;
+}
+
+int lhw_adv_apply(const float* returns, const float* values, float* adv, double* stats, long long count,
+                  long long count_total, float eps, void* stream) {
+  int grid = (int)((count + 1023) / 1024);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  adv_apply_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(returns, values, adv, stats, count, count_total, (double)eps);
+  KCHECK("adv_apply_kernel");
+  return 0;
+}
+
+int lhw_gather_minibatch(const float* obs, const float* act, const float* ret, const float* adv, const int64_t* idx,
+                         float* obs_b, float* act_b, float* ret_b, float* adv_b, int B, int obs_dim, int act_dim,
+                         void* stream) {
+  if (B <= 0) return 0;
+  const long long total = (long long)B * (obs_dim + act_dim + 2);
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(obs, act, ret, adv, idx, obs_b, act_b, ret_b, adv_b, B, obs_dim,
+                                                        act_dim);
+  KCHECK("gather_kernel");
+  return 0;
+}
+
+int lhw_grad_sumsq(const float* grad, float* norm_scratch, long long n, float grad_scale, void* stream) {
+  sumsq_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(grad, norm_scratch, n, grad_scale);
+  KCHECK("sumsq_kernel");
+  return 0;
+}
+
+int lhw_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* norm_scratch,
+                  long long n, int step, float lr, float beta1, float beta2, float eps, float max_norm,
+                  float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 4) grid = 148 * 4;
+  clip_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, norm_scratch, n, lr, beta1,
+                                                           beta2, eps, max_norm, grad_scale, bc1, bc2_sqrt);
+  KCHECK("clip_adam_kernel");
+  return 0;
+}
+
+}  // extern "C"

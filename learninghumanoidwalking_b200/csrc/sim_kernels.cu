@@ -1,0 +1,223 @@
+// sim_kernels.cu — sm_100a kernels + C-ABI for the batched environment (see include/lhw_b200.h).
+//
+// One environment per warp.  A warp streams its env's state record (env-major, contiguous -> coalesced
+// 128 B lines) from HBM into its private slice of shared memory, runs frame_skip physics substeps + reward /
+// observation / termination / auto-reset entirely on chip, and streams the record back: one HBM round trip
+// per control step (1220 B algorithmic per env-step in fp32).  Only __syncwarp() is used, so
+// warps of a block never wait on each other; the block size only sets how the shared memory is carved.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/lhw_b200.h"
+#include "model_pack.h"
+
+using namespace lhw;
+
+namespace {
+
+constexpr int NJ_JVRC = 6;
+__constant__ Model<double, NJ_JVRC> c_model_d;
+__constant__ Model<float, NJ_JVRC> c_model_f;
+
+template <class real> __device__ __forceinline__ const Model<real, NJ_JVRC>& cmodel();
+template <> __device__ __forceinline__ const Model<double, NJ_JVRC>& cmodel<double>() { return c_model_d; }
+template <> __device__ __forceinline__ const Model<float, NJ_JVRC>& cmodel<float>() { return c_model_f; }
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+const void* g_owner[2] = {nullptr, nullptr};  // which sim's model currently sits in constant memory (per precision)
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_OK(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) return fail(-10, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+template <class real>
+__global__ void __launch_bounds__(128) reset_kernel(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs,
+                                                    uint32_t seed, uint32_t first_id, const int32_t* __restrict__ mask,
+                                                    int fresh, real* __restrict__ obs_out) {
+  constexpr int NJ = NJ_JVRC;
+  using W = Work<real, NJ>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= n_envs) return;
+  if (mask && !mask[env]) return;
+  W& w = reinterpret_cast<W*>(smem_raw)[warp];
+  const Model<real, NJ>& m = cmodel<real>();
+  constexpr int NR = Dims<real, NJ>::NSTATE_R;
+  real* sr = state_r + (size_t)env * NR;
+  int32_t* si = state_i + (size_t)env * NSTATE_I;
+  if (fresh) {
+    for (int it = lane; it < NR; it += 32) sr[it] = 0;
+    if (lane < NSTATE_I) si[lane] = 0;
+    __syncwarp();
+  }
+  load_state<real, NJ>(w, sr, si, first_id + env);
+  env_reset<real, NJ>(w, m, seed);
+  store_state<real, NJ>(w, sr, si);
+  if (obs_out)
+    for (int it = lane; it < W::NOBS; it += 32) obs_out[(size_t)env * W::NOBS + it] = w.obs[it];
+}
+
+template <class real>
+__global__ void __launch_bounds__(128)
+    step_kernel(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs, uint32_t seed, uint32_t first_id,
+                const real* __restrict__ actions, int max_traj_len, int autoreset, real* __restrict__ obs,
+                real* __restrict__ term_obs, real* __restrict__ reward, real* __restrict__ rew_terms,
+                int32_t* __restrict__ done, int32_t* __restrict__ ended, int32_t* __restrict__ ep_len,
+                real* __restrict__ ep_rew) {
+  constexpr int NJ = NJ_JVRC;
+  using W = Work<real, NJ>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= n_envs) return;
+  W& w = reinterpret_cast<W*>(smem_raw)[warp];
+  const Model<real, NJ>& m = cmodel<real>();
+  constexpr int NR = Dims<real, NJ>::NSTATE_R, NU = 2 * NJ;
+  real* sr = state_r + (size_t)env * NR;
+  int32_t* si = state_i + (size_t)env * NSTATE_I;
+  load_state<real, NJ>(w, sr, si, first_id + env);
+  env_step<real, NJ>(w, m, actions + (size_t)env * NU, seed, max_traj_len, autoreset, obs + (size_t)env * W::NOBS,
+                     term_obs ? term_obs + (size_t)env * W::NOBS : nullptr, reward + env,
+                     rew_terms ? rew_terms + (size_t)env * NREW : nullptr, done + env, ended + env,
+                     ep_len ? ep_len + env : nullptr, ep_rew ? ep_rew + env : nullptr);
+  store_state<real, NJ>(w, sr, si);
+}
+
+}  // namespace
+
+struct lhw_sim {
+  int precision, device, warps_per_block;
+  Model<double, NJ_JVRC> md;
+  Model<float, NJ_JVRC> mf;
+  size_t work_bytes;
+};
+
+namespace {
+
+int upload_model(lhw_sim* s, cudaStream_t st) {
+  const int slot = s->precision == 64 ? 0 : 1;
+  if (g_owner[slot] == s) return 0;
+  if (s->precision == 64) CUDA_OK(cudaMemcpyToSymbolAsync(c_model_d, &s->md, sizeof(s->md), 0, cudaMemcpyHostToDevice, st));
+  else CUDA_OK(cudaMemcpyToSymbolAsync(c_model_f, &s->mf, sizeof(s->mf), 0, cudaMemcpyHostToDevice, st));
+  g_owner[slot] = s;
+  return 0;
+}
+
+template <class K> int prepare_kernel(K kernel, size_t smem) {
+  CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lhw_version(void) { return 1; }
+const char* lhw_last_error(void) { return g_err.c_str(); }
+long long lhw_launch_count(void) { return g_launches.load(); }
+void lhw_count_launch(void) { g_launches++; }
+
+int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision, int device) {
+  if (!out || !flat) return fail(-1, "null argument");
+  if (precision != 64 && precision != 32) return fail(-2, "precision must be 32 or 64");
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device");
+  CUDA_OK(cudaSetDevice(device));
+  lhw_sim* s = new lhw_sim();
+  s->precision = precision;
+  s->device = device;
+  int rc = fill_model(s->md, flat, n_flat);
+  if (rc == 0) rc = fill_model(s->mf, flat, n_flat);
+  if (rc != 0) {
+    delete s;
+    return fail(-4, "malformed model array (fill_model rc " + std::to_string(rc) + ")");
+  }
+  s->work_bytes = precision == 64 ? sizeof(Work<double, NJ_JVRC>) : sizeof(Work<float, NJ_JVRC>);
+  // carve shared memory: as many whole warps per block as fit in ~1/2 .. 1 SM worth, capped at 4
+  const char* env_wpb = getenv("LHW_WARPS_PER_BLOCK");
+  s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? 2 : 4);
+  if (s->warps_per_block < 1 || s->warps_per_block > 4) s->warps_per_block = 2;
+  const size_t smem = s->work_bytes * s->warps_per_block;
+  int maxsmem = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if ((int)smem > maxsmem) {
+    delete s;
+    return fail(-5, "working set does not fit in shared memory");
+  }
+  if (precision == 64) {
+    if (prepare_kernel(step_kernel<double>, smem) || prepare_kernel(reset_kernel<double>, smem)) { delete s; return -10; }
+  } else {
+    if (prepare_kernel(step_kernel<float>, smem) || prepare_kernel(reset_kernel<float>, smem)) { delete s; return -10; }
+  }
+  *out = s;
+  return 0;
+}
+
+int lhw_sim_destroy(lhw_sim* s) {
+  if (!s) return 0;
+  for (int k = 0; k < 2; k++)
+    if (g_owner[k] == s) g_owner[k] = nullptr;
+  delete s;
+  return 0;
+}
+
+int lhw_sim_state_reals(const lhw_sim*) { return Dims<double, NJ_JVRC>::NSTATE_R; }
+int lhw_sim_state_ints(const lhw_sim*) { return NSTATE_I; }
+int lhw_sim_obs_dim(const lhw_sim*) { return Work<double, NJ_JVRC>::NOBS; }
+int lhw_sim_act_dim(const lhw_sim*) { return 2 * NJ_JVRC; }
+int lhw_sim_smem_bytes_per_env(const lhw_sim* s) { return (int)s->work_bytes; }
+
+int lhw_sim_reset(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint32_t seed, uint32_t first_env_id,
+                  const int32_t* mask, int fresh, void* obs, void* stream) {
+  if (!s || !state_r || !state_i) return fail(-1, "null argument");
+  if (n_envs <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (upload_model(s, st)) return -10;
+  const int wpb = s->warps_per_block, grid = (n_envs + wpb - 1) / wpb;
+  const size_t smem = s->work_bytes * wpb;
+  if (s->precision == 64)
+    reset_kernel<double><<<grid, wpb * 32, smem, st>>>((double*)state_r, state_i, n_envs, seed, first_env_id, mask, fresh, (double*)obs);
+  else
+    reset_kernel<float><<<grid, wpb * 32, smem, st>>>((float*)state_r, state_i, n_envs, seed, first_env_id, mask, fresh, (float*)obs);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lhw_sim_step(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint32_t seed, uint32_t first_env_id,
+                 const void* actions, int max_traj_len, int autoreset, void* obs, void* term_obs, void* reward,
+                 void* rew_terms, int32_t* done, int32_t* ended, int32_t* ep_len, void* ep_rew, void* stream) {
+  if (!s || !state_r || !state_i || !actions || !obs || !reward || !done || !ended) return fail(-1, "null argument");
+  if (n_envs <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (upload_model(s, st)) return -10;
+  const int wpb = s->warps_per_block, grid = (n_envs + wpb - 1) / wpb;
+  const size_t smem = s->work_bytes * wpb;
+  if (s->precision == 64)
+    step_kernel<double><<<grid, wpb * 32, smem, st>>>((double*)state_r, state_i, n_envs, seed, first_env_id,
+                                                      (const double*)actions, max_traj_len, autoreset, (double*)obs,
+                                                      (double*)term_obs, (double*)reward, (double*)rew_terms, done,
+                                                      ended, ep_len, (double*)ep_rew);
+  else
+    step_kernel<float><<<grid, wpb * 32, smem, st>>>((float*)state_r, state_i, n_envs, seed, first_env_id,
+                                                     (const float*)actions, max_traj_len, autoreset, (float*)obs,
+                                                     (float*)term_obs, (float*)reward, (float*)rew_terms, done, ended,
+                                                     ep_len, (float*)ep_rew);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

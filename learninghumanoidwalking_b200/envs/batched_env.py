@@ -1,0 +1,135 @@
+"""BatchedHumanoidEnv — N device-resident copies of a reference humanoid env stepped by one CUDA launch.
+
+Mirrors, per environment, the reference's env protocol (envs/common/base_humanoid_env.py:177-276,
+envs/jvrc/jvrc_walk.py): `reset() -> obs`, `step(actions) -> (obs, reward, done, info)`, `observation_space`,
+`action_space`, `obs_mean`, `obs_std`, `robot.{mirrored_obs, mirrored_acts, clock_inds, iteration_count}`.
+All state lives in two torch CUDA tensors (the HBM records the kernel streams); nothing touches the host
+inside a control step.
+"""
+from __future__ import annotations
+
+import ctypes
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..model import load_model, pack_model
+
+REWARD_NAMES = ("foot_frc_score", "foot_vel_score", "root_accel", "height_error", "com_vel_error", "yaw_vel_error",
+                "upper_body_reward", "posture_error", "torque_penalty", "action_penalty")  # tasks/walking_task.py:131-146
+
+
+class BatchedHumanoidEnv:
+    def __init__(self, num_envs: int, model: str = "jvrc_walk", precision: int = 32, seed: int = 0,
+                 first_env_id: int = 0, device: int | torch.device | None = None, max_traj_len: int = 400,
+                 tolerance: float | None = None, max_iter: int | None = None):
+        if not torch.cuda.is_available():
+            raise _lib.LhwError("BatchedHumanoidEnv needs a CUDA device (no CPU fallback on the rollout path)")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.num_envs, self.precision, self.seed, self.first_env_id = int(num_envs), int(precision), int(seed), int(first_env_id)
+        self.max_traj_len = int(max_traj_len)
+        self.dtype = torch.float64 if precision == 64 else torch.float32
+        self.model_name = model
+        self.mj = load_model(model)
+        if tolerance is None and precision == 32:
+            tolerance = 1e-6  # fp32 cannot reach the reference's 1e-10; gradient floor is ~1e-6 of the force scale
+        flat = pack_model(self.mj, tolerance=tolerance, max_iter=max_iter)
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        _lib.check(L.lhw_sim_create(ctypes.byref(h), flat.ctypes.data_as(ctypes.c_void_p), len(flat), self.precision,
+                                    self.device.index), "lhw_sim_create")
+        self._h = h
+        self.obs_dim, self.act_dim = L.lhw_sim_obs_dim(h), L.lhw_sim_act_dim(h)
+        n, dev = self.num_envs, self.device
+        self.state_r = torch.zeros(n, L.lhw_sim_state_reals(h), dtype=self.dtype, device=dev)
+        self.state_i = torch.zeros(n, L.lhw_sim_state_ints(h), dtype=torch.int32, device=dev)
+        self.obs = torch.zeros(n, self.obs_dim, dtype=self.dtype, device=dev)
+        self.term_obs = torch.zeros(n, self.obs_dim, dtype=self.dtype, device=dev)
+        self.reward = torch.zeros(n, dtype=self.dtype, device=dev)
+        self.rew_terms = torch.zeros(n, len(REWARD_NAMES), dtype=self.dtype, device=dev)
+        self.done = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ended = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ep_rew = torch.zeros(n, dtype=self.dtype, device=dev)
+        self._fresh = True
+        # ---- reference-facing attributes (envs/jvrc/jvrc_base.py:69-131, envs/jvrc/jvrc_walk.py:43-63)
+        cfg = self.mj["cfg"]
+        self.history_len = cfg["obs_history_len"]
+        self.base_obs_len = self.obs_dim
+        self.dt = cfg["control_dt"]
+        self.action_space = np.zeros(self.act_dim)
+        self.observation_space = np.zeros(self.obs_dim * self.history_len)
+        half = np.deg2rad(cfg["half_sitting_pose_deg"])
+        self.obs_mean = np.concatenate((np.zeros(5), half, np.zeros(12), [0, 0, 0.5, 0.5, 0.5, 0, 0, 0]))
+        self.obs_std = np.concatenate(([0.2, 0.2, 1, 1, 1], 0.5 * np.ones(12), 4 * np.ones(12), [1, 1, 1, 1, 1, 0.5, 0.5, 0.5]))
+        base_mir_obs = [-0.1, 1, -2, 3, -4, 11, -12, -13, 14, -15, 16, 5, -6, -7, 8, -9, 10,
+                        23, -24, -25, 26, -27, 28, 17, -18, -19, 20, -21, 22]
+        append_obs = [len(base_mir_obs) + i for i in range(8)]
+        self.robot = SimpleNamespace(mirrored_obs=base_mir_obs + append_obs,
+                                     mirrored_acts=[6, -7, -8, 9, -10, 11, 0.1, -1, -2, 3, -4, 5],
+                                     clock_inds=append_obs[0:2], iteration_count=np.inf)
+
+    # ------------------------------------------------------------------ device API (torch tensors in / out)
+    def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:
+        """Reset all envs (or those where mask != 0); returns the [N, obs_dim] observation tensor."""
+        L = _lib.lib()
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(L.lhw_sim_reset(self._h, self.state_r.data_ptr(), self.state_i.data_ptr(), self.num_envs, self.seed,
+                                       self.first_env_id, _lib.ptr(mask), int(self._fresh and mask is None),
+                                       self.obs.data_ptr(), _lib.current_stream_ptr()), "lhw_sim_reset")
+        if mask is None:
+            self._fresh = False
+        return self.obs
+
+    def step(self, actions: torch.Tensor, autoreset: bool = True):
+        """actions [N, act_dim] (device, env dtype). Returns (obs, reward, done, ended) device tensors.
+        With autoreset the RolloutWorker semantics apply (see include/lhw_b200.h: lhw_sim_step)."""
+        if actions.dtype != self.dtype or not actions.is_contiguous() or actions.device != self.device:
+            actions = actions.to(device=self.device, dtype=self.dtype).contiguous()
+        assert actions.shape == (self.num_envs, self.act_dim), actions.shape
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            _lib.check(L.lhw_sim_step(self._h, self.state_r.data_ptr(), self.state_i.data_ptr(), self.num_envs, self.seed,
+                                      self.first_env_id, actions.data_ptr(), self.max_traj_len, int(autoreset),
+                                      self.obs.data_ptr(), self.term_obs.data_ptr(), self.reward.data_ptr(),
+                                      self.rew_terms.data_ptr(), self.done.data_ptr(), self.ended.data_ptr(),
+                                      self.ep_len.data_ptr(), self.ep_rew.data_ptr(), _lib.current_stream_ptr()),
+                       "lhw_sim_step")
+        return self.obs, self.reward, self.done, self.ended
+
+    # ------------------------------------------------------------------ host API (numpy in / out, copies inside)
+    def step_host(self, actions: np.ndarray, autoreset: bool = True):
+        """Reference-facing batched call with HOST buffers: H2D actions, one launch, D2H obs/reward/done."""
+        a = torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float64 if self.precision == 64 else np.float32))
+        obs, rew, done, ended = self.step(a.to(self.device, non_blocking=True), autoreset)
+        return obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy().astype(bool), ended.cpu().numpy().astype(bool)
+
+    # ------------------------------------------------------------------ state access (tests / checkpointing)
+    @property
+    def qpos(self) -> torch.Tensor:
+        return self.state_r[:, 0:19]
+
+    @property
+    def qvel(self) -> torch.Tensor:
+        return self.state_r[:, 19:37]
+
+    def solver_iterations(self) -> torch.Tensor:
+        """Newton iterations spent in the last launch, per env."""
+        return self.state_i[:, 7]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().lhw_sim_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

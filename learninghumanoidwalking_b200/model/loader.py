@@ -1,0 +1,70 @@
+"""Load a compiled robot model (tools/compile_model.py output) and pack it for the C-ABI.
+
+The flat float64 layout below is what lhw_sim_create() consumes (csrc/model_pack.h:fill_model).
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from ..tasks.gait_clock import phase_clock_table
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_model(name: str = "jvrc_walk") -> dict:
+    with open(os.path.join(_HERE, name + ".json")) as f:
+        return json.load(f)
+
+
+def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = None, kp=None, kd=None) -> np.ndarray:
+    links = mj["links"]
+    nl = len(links)
+    assert (nl - 1) % 2 == 0, "expected a free root + two equal serial chains"
+    nj = (nl - 1) // 2
+    for c in range(2):
+        for k in range(nj):
+            i = 1 + c * nj + k
+            assert links[i]["parent"] == (0 if k == 0 else i - 1), "links must be ordered root, chain0, chain1"
+    assert mj["rfoot_link"] == nj and mj["lfoot_link"] == 2 * nj
+    b: list[float] = [nj]
+    for lk in links:
+        b += lk["pos"]
+        b += list(np.asarray(lk["rot"], dtype=float).reshape(-1))
+        b += lk["joint"].get("axis", [0.0, 0.0, 0.0])
+        b.append(lk["mass"])
+        b += lk["com"]
+        b += lk["inertia"]
+    nv = 6 + 2 * nj
+    for d in range(nv):
+        if d < 6:
+            b += [0.0, 0.0, 0.0, 0.0, mj["dof_invweight0"][d]]
+        else:
+            j = links[d - 5]["joint"]
+            b += [j["armature"], j["damping"], j["range"][0], j["range"][1], mj["dof_invweight0"][d]]
+    for g in mj["geoms"]:
+        assert g["type"] == "box"
+        b += g["pos"]
+        b += g["size"]
+        b.append(mj["link_invweight0"][g["link"]][0])
+    o = mj["opt"]
+    b.append(o["timestep"])
+    b += o["gravity"]
+    b += o["solref"]
+    b += o["solimp"]
+    b += [o["friction"][0], o["impratio"], mj["meaninertia"],
+          o["tolerance"] if tolerance is None else tolerance, o["iterations"] if max_iter is None else max_iter]
+    c = mj["cfg"]
+    b += list(c["kp"] if kp is None else kp)
+    b += list(c["kd"] if kd is None else kd)
+    b += c["nominal_qpos"]
+    b += [c["action_smoothing"], c["frame_skip"]]
+    b += mj["head_in_root"]
+    t = c["task"]
+    period, table = phase_clock_table(t["swing_duration"], t["stance_duration"], 0.1, "grounded", 1.0 / c["control_dt"],
+                                      total_duration=t["total_duration"])
+    b += [mj["total_mass"], t["goal_height"], period]
+    b += list(table.reshape(-1))
+    return np.asarray(b, dtype=np.float64)

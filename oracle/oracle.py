@@ -190,6 +190,13 @@ class Oracle:
         self.lib.orc_quat2rp(quat.ctypes.data_as(ctypes.c_void_p), ctypes.byref(r), ctypes.byref(p))
         return r.value, p.value
 
+    def calc_reward(self, envs, i, target):
+        target = np.ascontiguousarray(target, dtype=np.float64)
+        t = np.zeros(NREW)
+        self.lib.orc_calc_reward(self._model, self.env_ptr(envs, i), target.ctypes.data_as(ctypes.c_void_p),
+                                 t.ctypes.data_as(ctypes.c_void_p))
+        return t
+
     def max_threads(self):
         return self.lib.orc_max_threads()
 

@@ -914,3 +914,8 @@ void orc_batch_step_autoreset(const orc_model* m, orc_env* envs, int n, const do
                        reward ? reward + i : 0, done ? done + i : 0, ended ? ended + i : 0);
   (void)nthreads;
 }
+
+/* test hook: reward terms for the current env fields (lets tests/ pin calc_reward to the golden vectors) */
+void orc_calc_reward(const orc_model* m, const orc_env* e, const double* target, double* terms) {
+  calc_reward(m, e, target, terms);
+}

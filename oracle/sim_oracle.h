@@ -134,6 +134,7 @@ double orc_energy(const orc_model* m, const double* qpos, const double* qvel, do
 void orc_philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t stream, uint32_t out[4]);
 void orc_quat2rp(const double* quat, double* roll, double* pitch);
 int orc_max_threads(void);
+void orc_calc_reward(const orc_model* m, const orc_env* e, const double* target, double* terms);
 
 #ifdef __cplusplus
 }

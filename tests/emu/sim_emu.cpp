@@ -1,0 +1,81 @@
+// tests/emu/sim_emu.cpp — TEST HARNESS ONLY.  Compiles the product's per-environment kernel source
+// (learninghumanoidwalking_b200/csrc/sim_core.h) with LHW_CPU_EMU so the 32 lanes of a warp run sequentially
+// on the host.  This lets the `-m "not gpu"` test tier check the exact arithmetic the CUDA kernel executes
+// against oracle/ without a GPU.  It is never linked into, loaded by, or reachable from the product.
+#define LHW_CPU_EMU 1
+#include "../../learninghumanoidwalking_b200/csrc/model_pack.h"
+
+#include <stdlib.h>
+
+using namespace lhw;
+
+template <class real, int NJ> struct Emu {
+  Model<real, NJ> model;
+  Work<real, NJ> work;
+};
+
+template <class real, int NJ> static void* create(const double* flat, int n) {
+  auto* e = new Emu<real, NJ>();
+  if (fill_model(e->model, flat, n) != 0) { delete e; return nullptr; }
+  return e;
+}
+
+template <class real, int NJ>
+static void reset_all(void* h, real* sr, int32_t* si, int n_envs, uint32_t seed, uint32_t first_id, real* obs) {
+  auto* e = (Emu<real, NJ>*)h;
+  constexpr int NR = Dims<real, NJ>::NSTATE_R, NOBS = Work<real, NJ>::NOBS;
+  for (int i = 0; i < n_envs; i++) {
+    for (int k = 0; k < NR; k++) sr[(size_t)i * NR + k] = 0;
+    for (int k = 0; k < NSTATE_I; k++) si[(size_t)i * NSTATE_I + k] = 0;
+    load_state(e->work, sr + (size_t)i * NR, si + (size_t)i * NSTATE_I, first_id + i);
+    env_reset(e->work, e->model, seed);
+    store_state(e->work, sr + (size_t)i * NR, si + (size_t)i * NSTATE_I);
+    for (int k = 0; k < NOBS; k++) obs[(size_t)i * NOBS + k] = e->work.obs[k];
+  }
+}
+
+template <class real, int NJ>
+static void step_all(void* h, real* sr, int32_t* si, int n_envs, uint32_t seed, uint32_t first_id, const real* actions,
+                     int max_traj_len, int autoreset, real* obs, real* term_obs, real* reward, real* rew_terms,
+                     int32_t* done, int32_t* ended, int32_t* ep_len, real* ep_rew) {
+  auto* e = (Emu<real, NJ>*)h;
+  constexpr int NR = Dims<real, NJ>::NSTATE_R, NOBS = Work<real, NJ>::NOBS, NU = 2 * NJ;
+  for (int i = 0; i < n_envs; i++) {
+    load_state(e->work, sr + (size_t)i * NR, si + (size_t)i * NSTATE_I, first_id + i);
+    env_step(e->work, e->model, actions + (size_t)i * NU, seed, max_traj_len, autoreset, obs + (size_t)i * NOBS,
+             term_obs + (size_t)i * NOBS, reward + i, rew_terms + (size_t)i * NREW, done + i, ended + i, ep_len + i,
+             ep_rew + i);
+    store_state(e->work, sr + (size_t)i * NR, si + (size_t)i * NSTATE_I);
+  }
+}
+
+extern "C" {
+void* emu_create(const double* flat, int n, int precision) {
+  return precision == 64 ? create<double, 6>(flat, n) : create<float, 6>(flat, n);
+}
+int emu_state_words(int precision) { (void)precision; return Dims<double, 6>::NSTATE_R; }
+void emu_reset(void* h, int precision, void* sr, int32_t* si, int n, uint32_t seed, uint32_t first_id, void* obs) {
+  if (precision == 64) reset_all<double, 6>(h, (double*)sr, si, n, seed, first_id, (double*)obs);
+  else reset_all<float, 6>(h, (float*)sr, si, n, seed, first_id, (float*)obs);
+}
+void emu_step(void* h, int precision, void* sr, int32_t* si, int n, uint32_t seed, uint32_t first_id,
+              const void* actions, int max_traj_len, int autoreset, void* obs, void* term_obs, void* reward,
+              void* rew_terms, int32_t* done, int32_t* ended, int32_t* ep_len, void* ep_rew) {
+  if (precision == 64)
+    step_all<double, 6>(h, (double*)sr, si, n, seed, first_id, (const double*)actions, max_traj_len, autoreset,
+                        (double*)obs, (double*)term_obs, (double*)reward, (double*)rew_terms, done, ended, ep_len,
+                        (double*)ep_rew);
+  else
+    step_all<float, 6>(h, (float*)sr, si, n, seed, first_id, (const float*)actions, max_traj_len, autoreset,
+                       (float*)obs, (float*)term_obs, (float*)reward, (float*)rew_terms, done, ended, ep_len,
+                       (float*)ep_rew);
+}
+// single physics substep on a raw state record with explicit ctrl (for mj_step-level parity)
+void emu_substep64(void* h, double* sr, int32_t* si, const double* ctrl, int nsteps) {
+  auto* e = (Emu<double, 6>*)h;
+  load_state(e->work, sr, si, 0);
+  for (int k = 0; k < 12; k++) e->work.ctrl[k] = ctrl[k];
+  for (int s = 0; s < nsteps; s++) substep<double, 6>(e->work, e->model, true);
+  store_state(e->work, sr, si);
+}
+}

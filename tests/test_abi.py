@@ -1,0 +1,48 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/lhw_b200.h declares
+(no compute calls here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "lhw_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lhw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from learninghumanoidwalking_b200 import _lib
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/lhw_b200.h but not exported"
+    assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
+    assert L.lhw_version() == 1
+
+
+def test_product_fails_loudly_without_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from learninghumanoidwalking_b200 import _lib
+    from learninghumanoidwalking_b200.envs import BatchedHumanoidEnv
+    with pytest.raises(_lib.LhwError):
+        BatchedHumanoidEnv(4)
+
+
+def test_product_never_imports_the_oracle():
+    """No product source may import, include, link or dlopen anything under oracle/ (comments may mention it)."""
+    pkg = os.path.join(ROOT, "learninghumanoidwalking_b200")
+    bad = re.compile(r"(^\s*(from|import)\s+oracle\b)|(#include\s*[\"<][^\">]*oracle)|liboracle|sim_oracle|ppo_oracle", re.M)
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(d, f)).read()
+                assert not bad.search(src), f"{f} reaches into oracle/"

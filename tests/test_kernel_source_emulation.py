@@ -1,0 +1,70 @@
+"""The product's kernel source (csrc/sim_core.h) compiled for the host with the 32 lanes of a warp run
+sequentially (tests/emu/, test harness only) against the oracle: the same arithmetic the GPU executes,
+checked on the CPU tier.  The GPU tier (test_gpu_parity.py) repeats this through the C-ABI on the device."""
+import numpy as np
+
+from emu import Emu
+from learninghumanoidwalking_b200.model import load_model, pack_model
+
+
+def test_substep_parity_through_contact_switches(oracle_tight):
+    o = oracle_tight
+    mj = load_model()
+    e = Emu(pack_model(mj, tolerance=1e-14), 64, 1)
+    envs = o.make_envs(1)
+    rng = np.random.RandomState(1)
+    q = np.array(mj["cfg"]["nominal_qpos"])
+    q[2] = 0.805
+    q[3:7] += rng.normal(size=4) * 0.02
+    q[3:7] /= np.linalg.norm(q[3:7])
+    q[7:] += rng.uniform(-0.1, 0.1, 12)
+    v = rng.normal(size=18) * 0.3
+    o.set_field(envs, 0, "qpos", q)
+    o.set_field(envs, 0, "qvel", v)
+    e.sr[0, 0:19], e.sr[0, 19:37] = q, v
+    ctrl = rng.uniform(-20, 20, 12)
+    seen = set()
+    for _ in range(400):
+        o.mj_step(envs, 0, ctrl)
+        e.substep(0, ctrl, 1)
+        seen.add(int(o.field(envs, 0, "ncon")[0]))
+        assert np.abs(o.field(envs, 0, "qpos") - e.qpos[0]).max() < 1e-11
+        assert np.abs(o.field(envs, 0, "qvel") - e.qvel[0]).max() < 1e-10
+    assert len(seen) >= 3, seen  # went through several contact configurations
+
+
+def test_env_level_parity_with_autoreset_fp64(oracle_tight):
+    o = oracle_tight
+    N = 3
+    e = Emu(pack_model(load_model(), tolerance=1e-14), 64, N, seed=5, first_id=10)
+    envs = o.make_envs(N, seed=5, first_id=10)
+    assert np.abs(o.batch_reset(envs, N) - e.reset()).max() < 1e-12
+    rng = np.random.RandomState(2)
+    n_end = 0
+    for _ in range(150):
+        a = rng.normal(size=(N, 12)) * 0.3
+        oo, to, tt, rr, dd, ee = o.batch_step(envs, N, a, max_traj_len=40)
+        eo, et, etm, er, ed, een, eplen, eprew = e.step(a, max_traj_len=40)
+        assert (dd == ed).all() and (ee == een).all()
+        assert np.abs(oo - eo).max() < 1e-9 and np.abs(rr - er).max() < 1e-10 and np.abs(tt - etm).max() < 1e-10
+        m = ee.astype(bool)
+        if m.any():
+            assert np.abs(to[m] - et[m]).max() < 1e-9
+            n_end += int(m.sum())
+    assert n_end >= 6
+    assert (e.si[:, 1] == [int(o.field(envs, i, "mode")[0]) for i in range(N)]).all()   # same RNG stream
+    assert (e.si[:, 0] == [int(o.field(envs, i, "phase")[0]) for i in range(N)]).all()
+
+
+def test_fp32_kernel_source_stays_close_for_a_short_horizon(oracle_tight):
+    o = oracle_tight
+    N = 2
+    e = Emu(pack_model(load_model(), tolerance=1e-6), 32, N, seed=1)
+    envs = o.make_envs(N, seed=1)
+    assert np.abs(o.batch_reset(envs, N) - e.reset()).max() < 1e-5
+    for _ in range(10):
+        a = np.zeros((N, 12))
+        oo, _, _, rr, dd, ee = o.batch_step(envs, N, a)
+        eo, _, _, er, ed, een, _, _ = e.step(a)
+        assert (ee == een).all()
+        assert np.abs(oo - eo).max() < 2e-3 and np.abs(rr - er).max() < 2e-3
