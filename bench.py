@@ -1,0 +1,239 @@
+#!/usr/bin/env python3
+"""bench.py — env-steps/sec of jvrc_walk (BASELINE.json metric) on N x B200, one JSON line on rank 0.
+
+A "step" is one pass of the rollout hot path over one batch: one control step (25 physics substeps + reward +
+observation + termination + auto-reset) for every environment of the batch — the work of
+BaseHumanoidEnv.step x num_envs in the reference.  Workload: BASELINE.json configs[1], jvrc_walk, 4096
+environments per GPU (weak scaling: envs shard by index, no data-path collective), actions ~ N(0, 0.223^2)
+(the action distribution of the reference's freshly initialised Gaussian_FF_Actor: output layer x0.01,
+std_dev 0.223), synthetic, generated up front.
+
+  value   device-resident: actions already in HBM, one lhw_sim_step launch per step.
+  e2e     the same steps through the host-facing API: actions from pinned host memory (H2D every step),
+          observation / reward / done read back to pinned host memory (D2H every step).
+  roofline  the step kernel: algorithmic HBM bytes per env-step x envs / CUDA-event time of
+          the launches, against the measured HBM peak (MEASURED_PEAKS.json).  The kernel is ALU/latency bound;
+          the honest secondary bound is reported beside it.
+  cpu_baseline / --impl reference   the CPU restatement (oracle/, "port": the reference's own MuJoCo path is
+          not installable here) on the box's host cores, same workload, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec jvrc_walk"
+UNIT = "env-steps/s"
+SIGMA = 0.223
+ALG_BYTES = {32: 1220, 64: 2288}   # state read+write, action read, obs/reward/done write
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference(n_envs: int, steps: int, warmup: int, seed: int, nthreads: int = 0):
+    """The oracle (CPU port of the reference path) on the host cores: env-steps/s, threads used."""
+    import numpy as np
+    from oracle.oracle import Oracle
+    o = Oracle()
+    nthreads = nthreads or (os.cpu_count() or 1)
+    envs = o.make_envs(n_envs, seed=seed)
+    o.batch_reset(envs, n_envs, nthreads)
+    rng = np.random.RandomState(seed)
+    for _ in range(warmup):
+        o.batch_step(envs, n_envs, rng.normal(size=(n_envs, 12)) * SIGMA, 400, nthreads)
+    acts = [rng.normal(size=(n_envs, 12)) * SIGMA for _ in range(steps)]
+    t0 = time.perf_counter()
+    for a in acts:
+        o.batch_step(envs, n_envs, a, 400, nthreads)
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, nthreads, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("LHW_BENCH_PRECISION", "64")), choices=[32, 64])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(3, args.warmup)
+    config = {"workload": f"jvrc_walk {args.envs} envs/GPU (BASELINE configs[1]), JVRC-1 sim_dt=0.001 control_dt=0.025 flat terrain",
+              "envs_per_gpu": args.envs, "global_envs": args.envs * world, "actions": f"N(0,{SIGMA}^2) synthetic, pre-generated",
+              "parallelism": f"env-sharded x{world} (no data-path collective)"}
+
+    if args.impl == "reference":
+        # the reference's own Ray+MuJoCo path cannot be installed here (mujoco/ray absent, no network):
+        # this arm times the CPU port (oracle/) on all host cores, rank 0 only.
+        if rank != 0:
+            return
+        n_sample = min(args.envs * world, 4096)
+        sps, threads, dt = cpu_reference(n_sample, max(1, min(K, 8)), 1, args.seed)
+        print(json.dumps({"metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+                          "ms_per_step": 1e3 * dt / max(1, min(K, 8)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
+                          "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
+                                           "sample": f"{n_sample} envs x {max(1, min(K, 8))} control steps, OpenMP over envs; "
+                                                     "reference Ray+MuJoCo path not runnable on this box (mujoco/ray not installable)"},
+                          "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from learninghumanoidwalking_b200 import _lib
+    from learninghumanoidwalking_b200.envs import BatchedHumanoidEnv
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    env = BatchedHumanoidEnv(n, precision=args.precision, seed=args.seed, first_env_id=rank * n, device=local_rank)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(args.seed * 1000 + rank)
+    acts = torch.randn(K + W, n, 12, device=dev, generator=g, dtype=env.dtype) * SIGMA
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for k in range(W):
+        env.step(acts[k])
+    launches0 = _lib.lib().lhw_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- value: device resident, per-step CUDA events (L2 flushed before every step, flush not timed)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record()
+        env.step(acts[W + k])
+        ev[k][1].record()
+    barrier()
+    wall = time.perf_counter() - t0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    launches = _lib.lib().lhw_launch_count() - launches0
+    # ---- e2e: pinned host actions in, pinned host obs/reward/done out, every step
+    h_acts = torch.empty(K, n, 12, dtype=env.dtype).pin_memory()
+    h_acts.copy_(acts[W:W + K].cpu())
+    h_obs = torch.empty(n, env.obs_dim, dtype=env.dtype).pin_memory()
+    h_rew = torch.empty(n, dtype=env.dtype).pin_memory()
+    h_done = torch.empty(n, dtype=torch.int32).pin_memory()
+    d_act = torch.empty(n, 12, dtype=env.dtype, device=dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        d_act.copy_(h_acts[k], non_blocking=True)
+        obs, rew, done, _ = env.step(d_act)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_done.copy_(done, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the host consumer needs this step's result before the next action
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    esz = 8 if args.precision == 64 else 4
+    # max over ranks
+    t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    iters = env.solver_iterations().float().mean().item()
+    if rank == 0:
+        value = n * world * K / (total_ms * 1e-3)
+        e2e = n * world * K / (e2e_ms * 1e-3)
+        peak, peak_src = peaks()
+        kernel_ms = statistics.mean(step_ms)   # one launch per step: the event pair brackets exactly the step kernel
+        achieved = n * ALG_BYTES[args.precision] / (kernel_ms * 1e-3) / 1e9
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+               "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
+               "config": dict(config, l2="flushed (256 MiB write) before every timed step; CUDA events bracket the step only",
+                              wall_s_incl_flush=wall, newton_iters_per_env_step=iters),
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * 12 * esz,
+                       "d2h_bytes_per_step": n * (env.obs_dim * esz + esz + 4)},
+               "gpu_launches": int(launches),
+               "clocks": clocks,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_env_step": ALG_BYTES[args.precision],
+                            "note": "the step kernel is ALU/latency bound (25 substeps of O(nv^3) work per ~2 KB of state); "
+                                    "see DESIGN.md for the FP-issue bound reported beside this"}}
+        if not args.no_cpu_baseline and world == 1:
+            sps, threads, dt = cpu_reference(min(n, 2048), 4, 1, args.seed)
+            out["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": f"{min(n, 2048)} envs x 4 control steps ({dt:.1f} s), same action distribution; "
+                                             "oracle/ C port with OpenMP (reference Ray+MuJoCo path not installable here)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

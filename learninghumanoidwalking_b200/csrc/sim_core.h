@@ -123,6 +123,14 @@ template <class real, int NJ> struct Dims {
   static constexpr int NSTATE_R = NQ + NV + NV + 5 * NU + 3 + 1;
 };
 
+// ---------------------------------------------------------------- arrow-packed symmetric matrix
+// ordering [root | chain0 | chain1]; chain0-chain1 coupling is structurally zero and not stored
+template <class real, int NJ> struct Arrow {
+  real r[6][6];      // root block (M: full symmetric; factor: lower triangle)
+  real x[2][6][NJ];  // coupling  x[chain][root dof][chain dof]   (factor: X = B L^-T)
+  real c[2][NJ][NJ]; // chain blocks (M: full symmetric; factor: lower triangle)
+};
+
 // ---------------------------------------------------------------- per-warp working set (shared memory)
 template <class real, int NJ> struct Work {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
@@ -135,21 +143,33 @@ template <class real, int NJ> struct Work {
   // ---- control-step scratch
   real target[NU], ctrl[NU], act_force[NU];
   // ---- kinematics / dynamics
+  real sc[NU][2];
   real o[3], xr[NL][3], xmat[NL][9];
   real S[NV][6];
-  real inert[NL][10], comp[NL][10];
-  real V[NL][6], A[NL][6], F[NL][6];
-  real M[NV][NV], H[NV][NV], hdinv[NV];
+  real V[NL][6];
+  Arrow<real, NJ> M, H;
+  real hdinv[NV];
   real qfs[NV], qacc[NV], Ma[NV], grad[NV], sdir[NV], Ms[NV], vec[NV];
-  // ---- contacts (slot = foot*4 + k) and joint limits
+  // ---- contacts (slot = foot*4 + k), expressed through the foot's spatial motion: J_contact = P(p) S_foot
   int ncon[2];
-  real cpos[NCON][3], cdist[NCON], cD[NCON], cKid[NCON];
-  real Jc[NCON][3][NA], WJ[NCON][3][NA];
-  real cu[NCON][3], cW[NCON][5], cF[NCON][3];
-  real earef[NEDGE], ejar[NEDGE], ejv[NEDGE], ef[NEDGE];
-  int eact[NEDGE];
-  int lside[NU], lact[NU];
-  real laref[NU], lD[NU], ljar[NU], ljv[NU], lf[NU];
+  real cpos[NCON][3], cD[NCON], cKid[NCON];
+  real earef[NEDGE], ejar[NEDGE];
+  int lside[NU];
+  real laref[NU], lD[NU], ljar[NU];
+  // two scratch groups with disjoint lifetimes share storage: rigid-body quantities live from P2 to P8 (the last
+  // reader is qfrc_smooth), the Newton quantities from P9 to P11
+  union {
+    struct {
+      real inert[NL][10], comp[NL][10];
+      real A[NL][6], F[NL][6];
+    };
+    struct {
+      real T[2][NA][6], Af[2][21], Ff[2][6], ya[2][6], ys[2][6];
+      real cF[NCON][3], cW[NCON][5];
+      real ef[NEDGE], ejv[NEDGE], lf[NU], ljv[NU];
+      int eact[NEDGE], lact[NU];
+    };
+  };
   // ---- what mj_step leaves behind (pre-integration state of the last substep)
   real root_vlin[3], foot_vel[2][3], grf[2], cz_min, qacc_lag[3];
   real rew[NREW], obs[NOBS];
@@ -162,6 +182,9 @@ template <class real> LHW_DEV void cross(const real* a, const real* b, real* c) 
   c[0] = x; c[1] = y; c[2] = z;
 }
 template <class real> LHW_DEV real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <class real> LHW_DEV real dot6(const real* a, const real* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
 template <class real> LHW_DEV void mv3(const real* R, const real* v, real* out) {
   real x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
   real y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
@@ -184,142 +207,225 @@ template <class real> LHW_DEV void inert_mul(const real* I, const real* mvv, rea
   out[4] = m * v[1] - hw[1];
   out[5] = m * v[2] - hw[2];
 }
-
-// dof d -> link that carries it ; link i>0 -> its dof
 template <int NJ> LHW_DEV int dof_link(int d) { return d < 6 ? 0 : d - 5; }
-// local (per-foot) jacobian column -> global dof
 template <int NJ> LHW_DEV int loc2dof(int foot, int j) { return j < 6 ? j : 6 + foot * NJ + (j - 6); }
+// fast reciprocal square root (pivot scaling); the product keeps 1/sqrt explicitly, never sqrt then divide
+LHW_DEV float m_rsqrt(float x) {
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+LHW_DEV double m_rsqrt(double x) {
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+// column a of the 3x6 map P(p) from a body's spatial motion [w; v_o] to the contact-frame velocity (n,t1,t2)=(+z,+y,-x)
+// of the body point at p:  u = v_o + w x p
+template <class real> LHW_DEV void pcol(const real* p, int a, real* out) {
+  switch (a) {
+    case 0: out[0] = p[1]; out[1] = -p[2]; out[2] = 0; break;
+    case 1: out[0] = -p[0]; out[1] = 0; out[2] = -p[2]; break;
+    case 2: out[0] = 0; out[1] = p[0]; out[2] = p[1]; break;
+    case 3: out[0] = 0; out[1] = 0; out[2] = -1; break;
+    case 4: out[0] = 0; out[1] = 1; out[2] = 0; break;
+    default: out[0] = 1; out[1] = 0; out[2] = 0; break;
+  }
+}
+// contact-frame velocity of the point p of a body moving with spatial motion y
+template <class real> LHW_DEV void contact_u(const real* p, const real* y, real* u) {
+  u[0] = y[5] + y[0] * p[1] - y[1] * p[0];
+  u[1] = y[4] + y[2] * p[0] - y[0] * p[2];
+  u[2] = -(y[3] + y[1] * p[2] - y[2] * p[1]);
+}
+LHW_DEV int sym6(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+// power-law impedance sigmoid of MuJoCo's getimpedance()
+template <class real> LHW_DEV real impedance(const real* solimp, real dist) {
+  const real d0 = solimp[0], dw = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  const real x = m_abs(dist) / width;
+  if (x >= 1) return dw;
+  if (x <= 0) return d0;
+  real y;
+  if (power < (real)1.0000001) y = x;
+  else if (power == (real)2) {
+    if (x <= mid) { const real t = x / mid; y = t * t * mid; }
+    else { const real t = (1 - x) / (1 - mid); y = 1 - t * t * (1 - mid); }
+  } else if (x <= mid) y = m_pow(x / mid, power) * mid;
+  else y = 1 - m_pow((1 - x) / (1 - mid), power) * (1 - mid);
+  return d0 + y * (dw - d0);
+}
 
-
-// ================================================================= arrow-structured Cholesky of H (in place)
-// ordering [chain0 | chain1 | root]:  H = [[A0,0,B0'],[0,A1,B1'],[B0,B1,C]]  ->  A_c = L_c L_c',  X_c = B_c L_c^-T,
-// C - sum_c X_c X_c' = L_C L_C'.  L_c sits in the lower triangle of H[chain][chain], X_c[r][k] in H[chain k][root r],
-// L_C in the lower triangle of H[root][root]; reciprocal pivots in hdinv (the diagonal of H is left untouched).
-template <class real, int NJ> LHW_DEV void arrow_factor(Work<real, NJ>& w) {
+// ================================================================= H x = b : arrow Cholesky with the forward
+// substitution fused into the factorisation (the right-hand side rides along as one more "row")
+// A_c = L_c L_c',  X_c = B_c L_c^-T,  C - sum_c X_c X_c' = L_C L_C'.  Reciprocal pivots in hdinv; the diagonal of
+// the factor is never stored (nor read).  x (global dof order) is overwritten with the solution.
+template <class real, int NJ> LHW_DEV void arrow_factor_solve(Work<real, NJ>& w, real* x) {
+  Arrow<real, NJ>& H = w.H;
+#pragma unroll
   for (int k = 0; k < NJ; k++) {
     LHW_LANES(l) {
       const int ch = l >> 4, r = l & 15;
-      if (r < NJ + 6 && (r >= NJ || r >= k)) {
-        const int c0 = 6 + ch * NJ, ck = c0 + k;
-        real dk = w.H[ck][ck];
-        for (int mm = 0; mm < k; mm++) dk -= w.H[ck][c0 + mm] * w.H[ck][c0 + mm];
+      if (r < NJ + 7 && (r >= NJ || r >= k)) {
+        const real* pk = H.c[ch][k];
+        real dk = pk[k];
+#pragma unroll
+        for (int mm = 0; mm < k; mm++) dk -= pk[mm] * pk[mm];
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
-        const real inv = (real)1 / m_sqrt(dk);
+        const real inv = m_rsqrt(dk);
         if (r == k) {
-          w.hdinv[ck] = inv;
+          w.hdinv[6 + ch * NJ + k] = inv;
         } else if (r < NJ) {
-          const int ci = c0 + r;
-          real t = w.H[ci][ck];
-          for (int mm = 0; mm < k; mm++) t -= w.H[ci][c0 + mm] * w.H[ck][c0 + mm];
-          w.H[ci][ck] = t * inv;
+          real* pi = H.c[ch][r];
+          real t = pi[k];
+#pragma unroll
+          for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
+          pi[k] = t * inv;
+        } else if (r < NJ + 6) {
+          real* px = H.x[ch][r - NJ];
+          real t = px[k];
+#pragma unroll
+          for (int mm = 0; mm < k; mm++) t -= px[mm] * pk[mm];
+          px[k] = t * inv;
         } else {
-          const int rr = r - NJ;
-          real t = w.H[ck][rr];
-          for (int mm = 0; mm < k; mm++) t -= w.H[c0 + mm][rr] * w.H[ck][c0 + mm];
-          w.H[ck][rr] = t * inv;
+          real* pb = x + 6 + ch * NJ;
+          real t = pb[k];
+#pragma unroll
+          for (int mm = 0; mm < k; mm++) t -= pb[mm] * pk[mm];
+          pb[k] = t * inv;
         }
       }
     }
     LHW_SYNC();
   }
+  // Schur complement of the root block and of the root right-hand side
   LHW_LANES(l) {
     if (l < 21) {
       int r = 0, t = l;
       while (t > r) { t -= r + 1; r++; }
-      const int c = t;  // (r,c), r >= c, root block
-      real acc = w.H[r][c];
-      for (int j = 6; j < 6 + 2 * NJ; j++) acc -= w.H[j][r] * w.H[j][c];
-      w.H[r][c] = acc;
+      const int c = t;
+      real acc = H.r[r][c];
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++)
+#pragma unroll
+        for (int k = 0; k < NJ; k++) acc -= H.x[ch][r][k] * H.x[ch][c][k];
+      H.r[r][c] = acc;
+    } else if (l < 27) {
+      const int r = l - 21;
+      real acc = x[r];
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++)
+#pragma unroll
+        for (int k = 0; k < NJ; k++) acc -= H.x[ch][r][k] * x[6 + ch * NJ + k];
+      x[r] = acc;
     }
   }
   LHW_SYNC();
+#pragma unroll
   for (int k = 0; k < 6; k++) {
     LHW_LANES(l) {
-      if (l < 6 && l >= k) {
-        real dk = w.H[k][k];
-        for (int mm = 0; mm < k; mm++) dk -= w.H[k][mm] * w.H[k][mm];
+      if (l < 7 && l >= k) {
+        const real* pk = H.r[k];
+        real dk = pk[k];
+#pragma unroll
+        for (int mm = 0; mm < k; mm++) dk -= pk[mm] * pk[mm];
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
-        const real inv = (real)1 / m_sqrt(dk);
+        const real inv = m_rsqrt(dk);
         if (l == k) w.hdinv[k] = inv;
-        else {
-          real t = w.H[l][k];
-          for (int mm = 0; mm < k; mm++) t -= w.H[l][mm] * w.H[k][mm];
-          w.H[l][k] = t * inv;
+        else if (l < 6) {
+          real* pi = H.r[l];
+          real t = pi[k];
+#pragma unroll
+          for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
+          pi[k] = t * inv;
+        } else {
+          real t = x[k];
+#pragma unroll
+          for (int mm = 0; mm < k; mm++) t -= x[mm] * pk[mm];
+          x[k] = t * inv;
         }
       }
     }
     LHW_SYNC();
   }
-}
-
-// x <- H^-1 x using the factor above
-template <class real, int NJ> LHW_DEV void arrow_solve(Work<real, NJ>& w, real* x) {
-  LHW_LANES(l) {
-    if (l < 2) {
-      const int c0 = 6 + l * NJ;
-      for (int k = 0; k < NJ; k++) {
-        real t = x[c0 + k];
-        for (int mm = 0; mm < k; mm++) t -= w.H[c0 + k][c0 + mm] * x[c0 + mm];
-        x[c0 + k] = t * w.hdinv[c0 + k];
-      }
-    }
-  }
-  LHW_SYNC();
-  LHW_LANES(l) {
-    if (l < 6) {
-      real t = x[l];
-      for (int j = 6; j < 6 + 2 * NJ; j++) t -= w.H[j][l] * x[j];
-      x[l] = t;
-    }
-  }
-  LHW_SYNC();
+  // back substitution: root (one lane, fully unrolled), coupling, then both chains side by side
   LHW_LANES(l) {
     if (l == 0) {
-      for (int k = 0; k < 6; k++) {
-        real t = x[k];
-        for (int mm = 0; mm < k; mm++) t -= w.H[k][mm] * x[mm];
-        x[k] = t * w.hdinv[k];
-      }
+      real z[6];
+#pragma unroll
       for (int k = 5; k >= 0; k--) {
         real t = x[k];
-        for (int mm = k + 1; mm < 6; mm++) t -= w.H[mm][k] * x[mm];
-        x[k] = t * w.hdinv[k];
+#pragma unroll
+        for (int mm = k + 1; mm < 6; mm++) t -= H.r[mm][k] * z[mm];
+        z[k] = t * w.hdinv[k];
       }
+#pragma unroll
+      for (int k = 0; k < 6; k++) x[k] = z[k];
     }
   }
   LHW_SYNC();
   LHW_LANES(l) {
     const int ch = l >> 4, k = l & 15;
     if (k < NJ) {
-      const int ck = 6 + ch * NJ + k;
-      real t = x[ck];
-      for (int r = 0; r < 6; r++) t -= w.H[ck][r] * x[r];
-      x[ck] = t;
+      real t = x[6 + ch * NJ + k];
+#pragma unroll
+      for (int r = 0; r < 6; r++) t -= H.x[ch][r][k] * x[r];
+      x[6 + ch * NJ + k] = t;
     }
   }
   LHW_SYNC();
   LHW_LANES(l) {
     if (l < 2) {
-      const int c0 = 6 + l * NJ;
+      real z[NJ];
+      real* pb = x + 6 + l * NJ;
+#pragma unroll
       for (int k = NJ - 1; k >= 0; k--) {
-        real t = x[c0 + k];
-        for (int mm = k + 1; mm < NJ; mm++) t -= w.H[c0 + mm][c0 + k] * x[c0 + mm];
-        x[c0 + k] = t * w.hdinv[c0 + k];
+        real t = pb[k];
+#pragma unroll
+        for (int mm = k + 1; mm < NJ; mm++) t -= H.c[l][mm][k] * z[mm];
+        z[k] = t * w.hdinv[6 + l * NJ + k];
       }
+#pragma unroll
+      for (int k = 0; k < NJ; k++) pb[k] = z[k];
     }
   }
   LHW_SYNC();
+}
+
+// y = M x for the arrow-packed symmetric M (lane = dof), result written to out[dof]
+template <class real, int NJ> LHW_DEV real arrow_row_dot(const Arrow<real, NJ>& M, int d, const real* x) {
+  real acc = 0;
+  if (d < 6) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) acc += M.r[d][j] * x[j];
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++)
+#pragma unroll
+      for (int k = 0; k < NJ; k++) acc += M.x[ch][d][k] * x[6 + ch * NJ + k];
+  } else {
+    const int ch = (d - 6) / NJ, k = d - 6 - ch * NJ;
+#pragma unroll
+    for (int j = 0; j < 6; j++) acc += M.x[ch][j][k] * x[j];
+#pragma unroll
+    for (int kk = 0; kk < NJ; kk++) acc += M.c[ch][k][kk] * x[6 + ch * NJ + kk];
+  }
+  return acc;
 }
 
 // ================================================================= one physics substep (mujoco.mj_step)
 template <class real, int NJ>
 LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool last) {
   constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ;
-  // ---------------- P1 forward kinematics: root, then both chains level by level (lane = chain)
+  // ---------------- P1 forward kinematics.  (a) sin/cos of all joints side by side + root rotation
   LHW_LANES(l) {
-    if (l == 0) {
+    if (l < NU) {
+      m_sincos(w.qpos[7 + l], &w.sc[l][0], &w.sc[l][1]);
+    } else if (l == NU) {
       real q0 = w.qpos[3], q1 = w.qpos[4], q2 = w.qpos[5], q3 = w.qpos[6];
-      real n = (real)1 / m_sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+      const real n = m_rsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
       q0 *= n; q1 *= n; q2 *= n; q3 *= n;
       real* R = w.xmat[0];
       R[0] = 1 - 2 * (q2 * q2 + q3 * q3); R[1] = 2 * (q1 * q2 - q0 * q3); R[2] = 2 * (q1 * q3 + q0 * q2);
@@ -330,27 +436,34 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
     }
   }
   LHW_SYNC();
+  // (b) both chains level by level; lane = chain*16 + matrix element (9 elements) ; elements 9..11 do the origin
+#pragma unroll
   for (int k = 0; k < NJ; k++) {
     LHW_LANES(l) {
-      if (l < 2) {
-        const int i = 1 + l * NJ + k, p = k == 0 ? 0 : i - 1;
-        real off[3], R0[9];
-        mv3(w.xmat[p], m.link_pos[i], off);
-        for (int c = 0; c < 3; c++) w.xr[i][c] = w.xr[p][c] + off[c];
-        for (int r = 0; r < 3; r++)
-          for (int c = 0; c < 3; c++)
-            R0[3 * r + c] = w.xmat[p][3 * r] * m.link_rot[i][c] + w.xmat[p][3 * r + 1] * m.link_rot[i][3 + c] +
-                            w.xmat[p][3 * r + 2] * m.link_rot[i][6 + c];
-        const real* a = m.axis[i];
-        real s, c;
-        m_sincos(w.qpos[6 + i], &s, &c);
-        const real t = 1 - c;
-        real Rj[9] = {c + a[0] * a[0] * t,        a[0] * a[1] * t - a[2] * s, a[0] * a[2] * t + a[1] * s,
-                      a[0] * a[1] * t + a[2] * s, c + a[1] * a[1] * t,        a[1] * a[2] * t - a[0] * s,
-                      a[0] * a[2] * t - a[1] * s, a[1] * a[2] * t + a[0] * s, c + a[2] * a[2] * t};
-        for (int r = 0; r < 3; r++)
-          for (int cc = 0; cc < 3; cc++)
-            w.xmat[i][3 * r + cc] = R0[3 * r] * Rj[cc] + R0[3 * r + 1] * Rj[3 + cc] + R0[3 * r + 2] * Rj[6 + cc];
+      const int ch = l >> 4, e = l & 15;
+      if (e < 12) {
+        const int i = 1 + ch * NJ + k, p = k == 0 ? 0 : i - 1;
+        const real* Rp = w.xmat[p];
+        if (e < 9) {
+          const int r = e / 3, c = e - 3 * r;
+          // column c of (link_rot * Rj):  Rj[:,c] = cos e_c + (1-cos) a_c a + sin (a x e_c)
+          const real* a = m.axis[i];
+          const real sn = w.sc[i - 1][0], cs = w.sc[i - 1][1], t = 1 - cs;
+          real col[3] = {t * a[c] * a[0], t * a[c] * a[1], t * a[c] * a[2]};
+          col[c] += cs;
+          const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;  // a x e_c : [c1] -= a[c2]... cyclic
+          col[c1] += sn * a[c2];
+          col[c2] -= sn * a[c1];
+          const real* L0 = m.link_rot[i];
+          const real b0 = L0[0] * col[0] + L0[1] * col[1] + L0[2] * col[2];
+          const real b1 = L0[3] * col[0] + L0[4] * col[1] + L0[5] * col[2];
+          const real b2 = L0[6] * col[0] + L0[7] * col[1] + L0[8] * col[2];
+          w.xmat[i][e] = Rp[3 * r] * b0 + Rp[3 * r + 1] * b1 + Rp[3 * r + 2] * b2;
+        } else {
+          const int r = e - 9;
+          const real* lp = m.link_pos[i];
+          w.xr[i][r] = w.xr[p][r] + Rp[3 * r] * lp[0] + Rp[3 * r + 1] * lp[1] + Rp[3 * r + 2] * lp[2];
+        }
       }
     }
     LHW_SYNC();
@@ -360,6 +473,7 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
     if (l < NV) {
       real* S = w.S[l];
       if (l < 3) {
+#pragma unroll
         for (int c = 0; c < 6; c++) S[c] = 0;
         S[3 + l] = 1;
       } else if (l < 6) {
@@ -377,14 +491,18 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       const real* R = w.xmat[i];
       real c[3];
       mv3(R, m.com[i], c);
+#pragma unroll
       for (int x = 0; x < 3; x++) c[x] += w.xr[i][x];
       const real* Ib = m.inertia[i];
       const real B[9] = {Ib[0], Ib[3], Ib[4], Ib[3], Ib[1], Ib[5], Ib[4], Ib[5], Ib[2]};
       real T[9];
+#pragma unroll
       for (int r = 0; r < 3; r++)
+#pragma unroll
         for (int cc = 0; cc < 3; cc++) T[3 * r + cc] = R[3 * r] * B[cc] + R[3 * r + 1] * B[3 + cc] + R[3 * r + 2] * B[6 + cc];
       real Iw[6];  // xx yy zz xy xz yz
       const int ri[6] = {0, 1, 2, 0, 0, 1}, ci[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
       for (int e = 0; e < 6; e++)
         Iw[e] = T[3 * ri[e]] * R[3 * ci[e]] + T[3 * ri[e] + 1] * R[3 * ci[e] + 1] + T[3 * ri[e] + 2] * R[3 * ci[e] + 2];
       const real ms = m.mass[i], cc2 = dot3(c, c);
@@ -395,48 +513,24 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
     }
   }
   LHW_SYNC();
-  // ---------------- P3 composite inertias: suffix sums along each chain (lane = chain*10 + component), then root
+  // ---------------- P3 composite inertias (suffix sums, lane = chain*10 + component) ; link velocities V
+  // (prefix sums, lanes 20..31 = chain*6 + component) ; velocity-product terms need V first -> next phase
   LHW_LANES(l) {
     if (l < 20) {
       const int ch = l / 10, e = l - ch * 10;
       real acc = 0;
+#pragma unroll
       for (int k = NJ - 1; k >= 0; k--) {
         const int i = 1 + ch * NJ + k;
         acc += w.inert[i][e];
         w.comp[i][e] = acc;
       }
-    }
-  }
-  LHW_SYNC();
-  LHW_LANES(l) {
-    if (l < 10) w.comp[0][l] = w.inert[0][l] + w.comp[1][l] + w.comp[1 + NJ][l];
-  }
-  LHW_SYNC();
-  // ---------------- P4 mass matrix (CRBA), lane = dof; concurrently link velocities V (lanes 20..31: chain x 6 comps)
-  LHW_LANES(l) {
-    if (l < NV) {
-      real f[6];
-      inert_mul(w.comp[dof_link<NJ>(l)], w.S[l], f);
-      int j = l;
-      const int cstart = l < 6 ? 0 : 6 + ((l - 6) / NJ) * NJ;
-      for (; j >= cstart; j--) {
-        const real* Sj = w.S[j];
-        real v = Sj[0] * f[0] + Sj[1] * f[1] + Sj[2] * f[2] + Sj[3] * f[3] + Sj[4] * f[4] + Sj[5] * f[5];
-        if (j == l) v += m.armature[l];
-        w.M[l][j] = v; w.M[j][l] = v;
-      }
-      if (l >= 6)
-        for (j = 5; j >= 0; j--) {
-          const real* Sj = w.S[j];
-          real v = Sj[0] * f[0] + Sj[1] * f[1] + Sj[2] * f[2] + Sj[3] * f[3] + Sj[4] * f[4] + Sj[5] * f[5];
-          w.M[l][j] = v; w.M[j][l] = v;
-        }
-    } else if (l >= 20) {
-      const int ch = (l - 20) / 6, e = (l - 20) % 6;
-      // root spatial velocity component e : [R w_body ; v_lin]
+    } else {
+      const int ch = (l - 20) / 6, e = (l - 20) - ch * 6;
       real acc = e < 3 ? w.xmat[0][3 * e] * w.qvel[3] + w.xmat[0][3 * e + 1] * w.qvel[4] + w.xmat[0][3 * e + 2] * w.qvel[5]
                        : w.qvel[e - 3];
       if (ch == 0) w.V[0][e] = acc;
+#pragma unroll
       for (int k = 0; k < NJ; k++) {
         const int i = 1 + ch * NJ + k;
         acc += w.S[5 + i][e] * w.qvel[5 + i];
@@ -445,35 +539,71 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
     }
   }
   LHW_SYNC();
-  // ---------------- P5 bias accelerations A (lane = chain, serial along the chain), gravity folded in as -g
+  // ---------------- P4 root composite (lanes 0..9) ; per-joint velocity-product acceleration (V x S) qd (lanes 10..)
   LHW_LANES(l) {
-    if (l < 2) {
-      real A[6];
+    if (l < 10) w.comp[0][l] = w.inert[0][l] + w.comp[1][l] + w.comp[1 + NJ][l];
+    else if (l < 10 + NU) {
+      const int i = 1 + (l - 10);
+      const real* Vi = w.V[i];
+      const real* S = w.S[5 + i];
+      const real qd = w.qvel[5 + i];
+      real t1[3], t2[3], t3[3];
+      cross(Vi, S, t1);          // w x w_s
+      cross(Vi, S + 3, t2);      // w x v_s
+      cross(Vi + 3, S, t3);      // v x w_s
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        w.A[i][c] = t1[c] * qd;
+        w.A[i][3 + c] = (t2[c] + t3[c]) * qd;
+      }
+    } else if (l == 31) {
       const real* V0 = w.V[0];
-      A[0] = A[1] = A[2] = 0;
-      cross(V0 + 3, V0, A + 3);  // v_o x w : rotational free-joint axes move with the body
-      for (int c = 0; c < 3; c++) A[3 + c] -= m.grav[c];
-      if (l == 0)
-        for (int c = 0; c < 6; c++) w.A[0][c] = A[c];
+      real t[3];
+      cross(V0 + 3, V0, t);  // v_o x w : the rotational free-joint axes move with the body
+      w.A[0][0] = w.A[0][1] = w.A[0][2] = 0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) w.A[0][3 + c] = t[c] - m.grav[c];  // gravity folded in as base acceleration -g
+    }
+  }
+  LHW_SYNC();
+  // ---------------- P5 mass matrix (CRBA), lane = dof ; bias accelerations A (prefix sums, lanes 20..31)
+  LHW_LANES(l) {
+    if (l < NV) {
+      real f[6];
+      inert_mul(w.comp[dof_link<NJ>(l)], w.S[l], f);
+      if (l < 6) {
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+          if (j <= l) {
+            const real v = dot6(w.S[j], f);
+            w.M.r[l][j] = v; w.M.r[j][l] = v;
+          }
+      } else {
+        const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ;
+#pragma unroll
+        for (int kk = 0; kk < NJ; kk++)
+          if (kk <= k) {
+            real v = dot6(w.S[6 + ch * NJ + kk], f);
+            if (kk == k) v += m.armature[l];
+            w.M.c[ch][k][kk] = v; w.M.c[ch][kk][k] = v;
+          }
+#pragma unroll
+        for (int j = 0; j < 6; j++) w.M.x[ch][j][k] = dot6(w.S[j], f);
+      }
+    } else if (l >= 20) {
+      const int ch = (l - 20) / 6, e = (l - 20) - ch * 6;
+      real acc = w.A[0][e];
+#pragma unroll
       for (int k = 0; k < NJ; k++) {
-        const int i = 1 + l * NJ + k;
-        const real* Vi = w.V[i];
-        const real* S = w.S[5 + i];
-        const real qd = w.qvel[5 + i];
-        real t1[3], t2[3], t3[3];
-        cross(Vi, S, t1);          // w x w_s
-        cross(Vi, S + 3, t2);      // w x v_s
-        cross(Vi + 3, S, t3);      // v x w_s
-        for (int c = 0; c < 3; c++) {
-          A[c] += t1[c] * qd;
-          A[3 + c] += (t2[c] + t3[c]) * qd;
-        }
-        for (int c = 0; c < 6; c++) w.A[i][c] = A[c];
+        const int i = 1 + ch * NJ + k;
+        acc += w.A[i][e];
+        w.A[i][e] = acc;
       }
     }
   }
   LHW_SYNC();
-  // ---------------- P6 link forces f_i = I A + V x* (I V) (lane = link) ; contact detection (lanes 30,31 = feet)
+  // ---------------- P6 link forces f_i = I A + V x* (I V) (lane = link) ; contact detection (lanes 30,31 = feet) ;
+  // joint limits (lanes 14..14+NU)
   LHW_LANES(l) {
     if (l < NL) {
       real IA[6], IV[6], t1[3], t2[3], t3[3];
@@ -483,6 +613,7 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       cross(V, IV, t1);          // w x n
       cross(V + 3, IV + 3, t2);  // v x f
       cross(V, IV + 3, t3);      // w x f
+#pragma unroll
       for (int c = 0; c < 3; c++) {
         w.F[l][c] = IA[c] + t1[c] + t2[c];
         w.F[l][3 + c] = IA[3 + c] + t3[c];
@@ -492,6 +623,7 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       const int f = l - 30, lk = (f + 1) * NJ;
       real ctr[3], v[3], corner[3];
       mv3(w.xmat[lk], m.foot_pos[f], ctr);
+#pragma unroll
       for (int c = 0; c < 3; c++) ctr[c] += w.xr[lk][c];
       const real dist0 = w.o[2] + ctr[2];
       int cnt = 0;
@@ -499,48 +631,23 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
         v[0] = (i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0];
         v[1] = (i & 2) ? m.foot_size[f][1] : -m.foot_size[f][1];
         v[2] = (i & 4) ? m.foot_size[f][2] : -m.foot_size[f][2];
-        mv3(w.xmat[lk], v, corner);
-        const real ld = corner[2];
+        const real ld = w.xmat[lk][6] * v[0] + w.xmat[lk][7] * v[1] + w.xmat[lk][8] * v[2];
         if (dist0 + ld > 0 || ld > 0) continue;
+        mv3(w.xmat[lk], v, corner);
         const int s = f * 4 + cnt;
         const real cd = dist0 + ld;
-        w.cdist[s] = cd;
         w.cpos[s][0] = corner[0] + ctr[0];
         w.cpos[s][1] = corner[1] + ctr[1];
         w.cpos[s][2] = corner[2] + ctr[2] - (real)0.5 * cd;
-        // impedance (getimpedance), regulariser and reference stiffness term
-        const real d0 = m.solimp[0], dw = m.solimp[1], width = m.solimp[2], mid = m.solimp[3], power = m.solimp[4];
-        real x = m_abs(cd) / width, imp;
-        if (x >= 1) imp = dw;
-        else if (x <= 0) imp = d0;
-        else {
-          real y;
-          if (power < (real)1.0000001) y = x;
-          else if (x <= mid) y = m_pow(x / mid, power) * mid;
-          else y = 1 - m_pow((1 - x) / (1 - mid), power) * (1 - mid);
-          imp = d0 + y * (dw - d0);
-        }
+        const real imp = impedance(m.solimp, cd);
         const real Rn = m_max((real)1e-15, (1 - imp) / imp * (m.foot_invw[f] * (1 + m.mu * m.mu)));
         w.cD[s] = (real)1 / (2 * m.mu_reg * m.mu_reg * Rn);
         w.cKid[s] = m.K * imp * cd;
         cnt++;
       }
       w.ncon[f] = cnt;
-    }
-  }
-  LHW_SYNC();
-  // ---------------- P7 subtree forces (suffix sums, lane = chain*6 + comp) ; joint limits (lanes 12..12+NU)
-  LHW_LANES(l) {
-    if (l < 12) {
-      const int ch = l / 6, e = l - ch * 6;
-      real acc = 0;
-      for (int k = NJ - 1; k >= 0; k--) {
-        const int i = 1 + ch * NJ + k;
-        acc += w.F[i][e];
-        w.F[i][e] = acc;
-      }
-    } else if (l < 12 + NU) {
-      const int u = l - 12, d = 6 + u;
+    } else if (l >= 14 && l < 14 + NU) {
+      const int u = l - 14, d = 6 + u;
       const real q = w.qpos[7 + u];
       const real dlo = q - m.range_lo[d], dhi = m.range_hi[d] - q;
       int side = 0;
@@ -549,120 +656,101 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       else if (dhi < 0) { side = -1; dist = dhi; }
       w.lside[u] = side;
       if (side) {
-        const real d0 = m.solimp[0], dw = m.solimp[1], width = m.solimp[2], mid = m.solimp[3], power = m.solimp[4];
-        real x = m_abs(dist) / width, imp;
-        if (x >= 1) imp = dw;
-        else {
-          real y;
-          if (power < (real)1.0000001) y = x;
-          else if (x <= mid) y = m_pow(x / mid, power) * mid;
-          else y = 1 - m_pow((1 - x) / (1 - mid), power) * (1 - mid);
-          imp = d0 + y * (dw - d0);
-        }
+        const real imp = impedance(m.solimp, dist);
         w.lD[u] = (real)1 / m_max((real)1e-15, (1 - imp) / imp * m.dof_invw[d]);
         w.laref[u] = -m.B * (side * w.qvel[d]) - m.K * imp * dist;
       }
     }
   }
   LHW_SYNC();
-  // ---------------- P8 qfrc_smooth (lane = dof) ; contact jacobians in the contact frame (n,t1,t2)=(+z,+y,-x)
+  // ---------------- P7 subtree forces (suffix sums, lane = chain*6 + comp) ; pyramid-edge reference accelerations
+  // (lane = edge; uses the foot link's spatial velocity from P3)
   LHW_LANES(l) {
-    if (l < NV) {
-      const int lk = dof_link<NJ>(l);
-      const real* S = w.S[l];
-      real Ft[6];
-      if (lk == 0)
-        for (int c = 0; c < 6; c++) Ft[c] = w.F[0][c] + w.F[1][c] + w.F[1 + NJ][c];
-      else
-        for (int c = 0; c < 6; c++) Ft[c] = w.F[lk][c];
-      const real bias = S[0] * Ft[0] + S[1] * Ft[1] + S[2] * Ft[2] + S[3] * Ft[3] + S[4] * Ft[4] + S[5] * Ft[5];
-      real q = -m.damping[l] * w.qvel[l] - bias;
-      if (l >= 6) q += w.ctrl[l - 6];
-      w.qfs[l] = q;
-      w.qacc[l] = w.qacc_warm[l];
-    }
-    for (int it = l; it < NCON * NA; it += 32) {
-      const int s = it / NA, j = it - s * NA, f = s >> 2;
+    {
+      const int s = l >> 2, e = l & 3, f = s >> 2;
       if ((s & 3) < w.ncon[f]) {
-        const real* S = w.S[loc2dof<NJ>(f, j)];
         real u[3];
-        cross(S, w.cpos[s], u);
-        w.Jc[s][0][j] = S[5] + u[2];
-        w.Jc[s][1][j] = S[4] + u[1];
-        w.Jc[s][2][j] = -(S[3] + u[0]);
+        contact_u(w.cpos[s], w.V[(f + 1) * NJ], u);
+        const real vel = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)];
+        w.earef[l] = -m.B * vel - w.cKid[s];
+      }
+    }
+    if (l < 12) {
+      const int ch = l / 6, e = l - ch * 6;
+      real acc = 0;
+#pragma unroll
+      for (int k = NJ - 1; k >= 0; k--) {
+        const int i = 1 + ch * NJ + k;
+        acc += w.F[i][e];
+        w.F[i][e] = acc;
       }
     }
   }
   LHW_SYNC();
-  // ---------------- P9 reference accelerations of the 4 pyramid edges of each contact (lane = contact row)
+  // ---------------- P8 qfrc_smooth (lane = dof), warm start
   LHW_LANES(l) {
-    if (l < NCON * 3) {
-      const int s = l / 3, k = l - 3 * s, f = s >> 2;
-      if ((s & 3) < w.ncon[f]) {
-        real acc = 0;
-        for (int j = 0; j < NA; j++) acc += w.Jc[s][k][j] * w.qvel[loc2dof<NJ>(f, j)];
-        w.cu[s][k] = acc;
+    if (l < NV) {
+      const int lk = dof_link<NJ>(l);
+      real Ft[6];
+      if (lk == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) Ft[c] = w.F[0][c] + w.F[1][c] + w.F[1 + NJ][c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 6; c++) Ft[c] = w.F[lk][c];
       }
+      real q = -m.damping[l] * w.qvel[l] - dot6(w.S[l], Ft);
+      if (l >= 6) q += w.ctrl[l - 6];
+      w.qfs[l] = q;
+      w.qacc[l] = w.qacc_warm[l];
+    }
+  }
+  LHW_SYNC();
+  // ---------------- P9 Newton start: Ma = M a (lane = dof) ; foot spatial accelerations ya = S_foot a (lanes 20..31)
+  LHW_LANES(l) {
+    if (l < NV) w.Ma[l] = arrow_row_dot<real, NJ>(w.M, l, w.qacc);
+    else if (l >= 20) {
+      const int f = (l - 20) / 6, e = (l - 20) - f * 6;
+      real acc = 0;
+#pragma unroll
+      for (int j = 0; j < NA; j++) acc += w.S[loc2dof<NJ>(f, j)][e] * w.qacc[loc2dof<NJ>(f, j)];
+      w.ya[f][e] = acc;
     }
   }
   LHW_SYNC();
   LHW_LANES(l) {
     const int s = l >> 2, e = l & 3, f = s >> 2;
+    real jar = 1;
     if ((s & 3) < w.ncon[f]) {
-      const real vel = w.cu[s][0] + ((e & 1) ? -m.mu : m.mu) * w.cu[s][1 + (e >> 1)];
-      w.earef[l] = -m.B * vel - w.cKid[s];
+      real u[3];
+      contact_u(w.cpos[s], w.ya[f], u);
+      jar = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)] - w.earef[l];
     }
+    w.ejar[l] = jar;
+    if (l < NU) w.ljar[l] = w.lside[l] ? w.lside[l] * w.qacc[6 + l] - w.laref[l] : (real)1;
   }
   LHW_SYNC();
 
   // ---------------- P10 primal Newton on  1/2 (a-a_s)' M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
+  // residuals (Ma, ejar, ljar) are carried incrementally: x += alpha * (direction image)
   bool converged = false;
   for (int iter = 0; iter <= m.max_iter && !converged; iter++) {
-    // (a) M a (lanes < NV) ; J_c a per contact row (lanes 8.. reuse all lanes with a strided loop)
+    // (a) edge / limit forces and active sets
     LHW_LANES(l) {
-      if (l < NV) {
-        real acc = 0;
-        if (l < 6) {
-          for (int j = 0; j < NV; j++) acc += w.M[l][j] * w.qacc[j];
-        } else {
-          const int cs = 6 + ((l - 6) / NJ) * NJ;
-          for (int j = 0; j < 6; j++) acc += w.M[l][j] * w.qacc[j];
-          for (int j = cs; j < cs + NJ; j++) acc += w.M[l][j] * w.qacc[j];
-        }
-        w.Ma[l] = acc;
-      }
-      for (int it = l; it < NCON * 3; it += 32) {
-        const int s = it / 3, k = it - 3 * s, f = s >> 2;
-        if ((s & 3) < w.ncon[f]) {
-          real acc = 0;
-          for (int j = 0; j < NA; j++) acc += w.Jc[s][k][j] * w.qacc[loc2dof<NJ>(f, j)];
-          w.cu[s][k] = acc;
-        }
-      }
-    }
-    LHW_SYNC();
-    // (b) edge residuals / forces (lane = edge) and limit rows
-    LHW_LANES(l) {
-      const int s = l >> 2, e = l & 3, f = s >> 2;
-      real fe = 0, jar = 1;
-      if ((s & 3) < w.ncon[f]) {
-        jar = w.cu[s][0] + ((e & 1) ? -m.mu : m.mu) * w.cu[s][1 + (e >> 1)] - w.earef[l];
-        fe = jar < 0 ? -w.cD[s] * jar : (real)0;
-      }
-      w.ejar[l] = jar; w.ef[l] = fe; w.eact[l] = jar < 0;
+      const int s = l >> 2;
+      const real jar = w.ejar[l];
+      w.ef[l] = jar < 0 ? -w.cD[s] * jar : (real)0;   // inactive slots carry jar = 1
+      w.eact[l] = jar < 0;
       if (l < NU) {
-        real fl = 0, jl = 1;
-        if (w.lside[l]) {
-          jl = w.lside[l] * w.qacc[6 + l] - w.laref[l];
-          fl = jl < 0 ? -w.lD[l] * jl : (real)0;
-        }
-        w.ljar[l] = jl; w.lf[l] = fl; w.lact[l] = jl < 0;
+        const real jl = w.ljar[l];
+        w.lf[l] = jl < 0 ? -w.lD[l] * jl : (real)0;
+        w.lact[l] = jl < 0;
       }
     }
     LHW_SYNC();
-    // (c) per contact: force in the contact frame and the 3x3 weight  W = sum_active D w w'
+    // (b) per contact: force in the contact frame and the 3x3 weight  W = sum_active D w w'
     LHW_LANES(l) {
-      if (l < NCON) {
+      if (l < NCON && (l & 3) < w.ncon[l >> 2]) {
         const real* fe = w.ef + 4 * l;
         w.cF[l][0] = fe[0] + fe[1] + fe[2] + fe[3];
         w.cF[l][1] = m.mu * (fe[0] - fe[1]);
@@ -677,106 +765,127 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       }
     }
     LHW_SYNC();
-    // (d) gradient (lane = dof) ; WJ = W Jc
+    // (c) per foot: wrench Ff = sum P' cF  (12 items) and spatial weight Af = sum P' W P (2 x 21 items)
+    LHW_LANES(l) {
+      for (int it = l; it < 12 + 42; it += 32) {
+        if (it < 12) {
+          const int f = it / 6, a = it - f * 6;
+          real acc = 0;
+          for (int k = 0; k < w.ncon[f]; k++) {
+            real ca[3];
+            pcol(w.cpos[f * 4 + k], a, ca);
+            acc += dot3(ca, w.cF[f * 4 + k]);
+          }
+          w.Ff[f][a] = acc;
+        } else {
+          const int f = (it - 12) / 21, t0 = (it - 12) - f * 21;
+          int a = 0, t = t0;
+          while (t > a) { t -= a + 1; a++; }
+          const int b = t;
+          real acc = 0;
+          for (int k = 0; k < w.ncon[f]; k++) {
+            const int s = f * 4 + k;
+            real ca[3], cb[3];
+            pcol(w.cpos[s], a, ca);
+            pcol(w.cpos[s], b, cb);
+            const real* W = w.cW[s];
+            acc += ca[0] * (W[0] * cb[0] + W[1] * cb[1] + W[2] * cb[2]) + ca[1] * (W[1] * cb[0] + W[3] * cb[1]) +
+                   ca[2] * (W[2] * cb[0] + W[4] * cb[2]);
+          }
+          w.Af[f][t0] = acc;
+        }
+      }
+    }
+    LHW_SYNC();
+    // (d) gradient (lane = dof)
     LHW_LANES(l) {
       if (l < NV) {
         real g = w.Ma[l] - w.qfs[l];
-        for (int f = 0; f < 2; f++) {
-          int j = -1;
-          if (l < 6) j = l;
-          else if (l >= 6 + f * NJ && l < 6 + (f + 1) * NJ) j = 6 + (l - 6 - f * NJ);
-          if (j >= 0)
-            for (int k = 0; k < w.ncon[f]; k++) {
-              const int s = f * 4 + k;
-              g -= w.Jc[s][0][j] * w.cF[s][0] + w.Jc[s][1][j] * w.cF[s][1] + w.Jc[s][2][j] * w.cF[s][2];
-            }
+        if (l < 6) g -= dot6(w.S[l], w.Ff[0]) + dot6(w.S[l], w.Ff[1]);
+        else {
+          g -= dot6(w.S[l], w.Ff[(l - 6) / NJ]);
+          if (w.lside[l - 6]) g -= w.lside[l - 6] * w.lf[l - 6];
         }
-        if (l >= 6 && w.lside[l - 6]) g -= w.lside[l - 6] * w.lf[l - 6];
         w.grad[l] = g;
-      }
-      for (int it = l; it < NCON * NA; it += 32) {
-        const int s = it / NA, j = it - s * NA, f = s >> 2;
-        if ((s & 3) < w.ncon[f]) {
-          const real j0 = w.Jc[s][0][j], j1 = w.Jc[s][1][j], j2 = w.Jc[s][2][j];
-          const real* W = w.cW[s];
-          w.WJ[s][0][j] = W[0] * j0 + W[1] * j1 + W[2] * j2;
-          w.WJ[s][1][j] = W[1] * j0 + W[3] * j1;
-          w.WJ[s][2][j] = W[2] * j0 + W[4] * j2;
-        }
+        w.sdir[l] = -g;
       }
     }
     LHW_SYNC();
     const real g2 = warp_sum<real>([&](int l) { return l < NV ? w.grad[l] * w.grad[l] : (real)0; });
     if (g2 < m.tol2 || iter == m.max_iter) { converged = true; break; }
-    // (e) H = M + Jc' W Jc + diag(limit D) on the structurally non-zero lower triangle
+    // (e) T_f = Af S_f (per foot, per ancestor dof, per component)
     LHW_LANES(l) {
-      for (int it = l; it < Model<real, NJ>::NT; it += 32) {
-        const int i = m.h_i[it], j = m.h_j[it];
-        real acc = w.M[i][j];
-        if (i == j && i >= 6 && w.lside[i - 6] && w.lact[i - 6]) acc += w.lD[i - 6];
-        const int f0 = i < 6 ? 0 : (i - 6) / NJ, f1 = i < 6 ? 1 : f0;
-        for (int f = f0; f <= f1; f++) {
-          const int li = i < 6 ? i : 6 + (i - 6 - f * NJ), lj = j < 6 ? j : 6 + (j - 6 - f * NJ);
-          for (int k = 0; k < w.ncon[f]; k++) {
-            const int s = f * 4 + k;
-            acc += w.Jc[s][0][li] * w.WJ[s][0][lj] + w.Jc[s][1][li] * w.WJ[s][1][lj] + w.Jc[s][2][li] * w.WJ[s][2][lj];
-          }
-        }
-        w.H[i][j] = acc;
+      for (int it = l; it < 2 * NA * 6; it += 32) {
+        const int f = it / (NA * 6), r = it - f * (NA * 6), j = r / 6, a = r - j * 6;
+        const real* S = w.S[loc2dof<NJ>(f, j)];
+        const real* Af = w.Af[f];
+        real acc = 0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) acc += Af[sym6(a, b)] * S[b];
+        w.T[f][j][a] = w.ncon[f] ? acc : (real)0;
       }
-      if (l < NV) w.sdir[l] = -w.grad[l];
     }
     LHW_SYNC();
-    arrow_factor<real, NJ>(w);
-    arrow_solve<real, NJ>(w, w.sdir);
-    // (f) exact line search along sdir: phi'(alpha) is continuous, piecewise linear and increasing
+    // (f) H = M + S' Af S + diag(limit D) on the arrow pattern (21 + 2*36 + 2*21 items)
     LHW_LANES(l) {
-      if (l < NV) {
-        real acc = 0;
-        if (l < 6) {
-          for (int j = 0; j < NV; j++) acc += w.M[l][j] * w.sdir[j];
+      for (int it = l; it < 21 + 2 * 6 * NJ + NJ * (NJ + 1); it += 32) {
+        if (it < 21) {
+          int r = 0, t = it;
+          while (t > r) { t -= r + 1; r++; }
+          w.H.r[r][t] = w.M.r[r][t] + dot6(w.S[r], w.T[0][t]) + dot6(w.S[r], w.T[1][t]);
+        } else if (it < 21 + 2 * 6 * NJ) {
+          const int q = it - 21, ch = q / (6 * NJ), rr = q - ch * 6 * NJ, j = rr / NJ, k = rr - j * NJ;
+          w.H.x[ch][j][k] = w.M.x[ch][j][k] + dot6(w.S[6 + ch * NJ + k], w.T[ch][j]);
         } else {
-          const int cs = 6 + ((l - 6) / NJ) * NJ;
-          for (int j = 0; j < 6; j++) acc += w.M[l][j] * w.sdir[j];
-          for (int j = cs; j < cs + NJ; j++) acc += w.M[l][j] * w.sdir[j];
+          const int q = it - 21 - 2 * 6 * NJ, ch = q / (NJ * (NJ + 1) / 2);
+          int k = 0, t = q - ch * (NJ * (NJ + 1) / 2);
+          while (t > k) { t -= k + 1; k++; }
+          real acc = w.M.c[ch][k][t] + dot6(w.S[6 + ch * NJ + k], w.T[ch][6 + t]);
+          if (k == t && w.lside[ch * NJ + k] && w.lact[ch * NJ + k]) acc += w.lD[ch * NJ + k];
+          w.H.c[ch][k][t] = acc;
         }
-        w.Ms[l] = acc;
       }
-      for (int it = l; it < NCON * 3; it += 32) {
-        const int s = it / 3, k = it - 3 * s, f = s >> 2;
-        if ((s & 3) < w.ncon[f]) {
-          real acc = 0;
-          for (int j = 0; j < NA; j++) acc += w.Jc[s][k][j] * w.sdir[loc2dof<NJ>(f, j)];
-          w.cu[s][k] = acc;
-        }
+    }
+    LHW_SYNC();
+    arrow_factor_solve<real, NJ>(w, w.sdir);
+    // (g) images of the search direction: M s, foot spatial accelerations, edge / limit rates
+    LHW_LANES(l) {
+      if (l < NV) w.Ms[l] = arrow_row_dot<real, NJ>(w.M, l, w.sdir);
+      else if (l >= 20) {
+        const int f = (l - 20) / 6, e = (l - 20) - f * 6;
+        real acc = 0;
+#pragma unroll
+        for (int j = 0; j < NA; j++) acc += w.S[loc2dof<NJ>(f, j)][e] * w.sdir[loc2dof<NJ>(f, j)];
+        w.ys[f][e] = acc;
       }
     }
     LHW_SYNC();
     LHW_LANES(l) {
       const int s = l >> 2, e = l & 3, f = s >> 2;
       real jv = 0;
-      if ((s & 3) < w.ncon[f]) jv = w.cu[s][0] + ((e & 1) ? -m.mu : m.mu) * w.cu[s][1 + (e >> 1)];
+      if ((s & 3) < w.ncon[f]) {
+        real u[3];
+        contact_u(w.cpos[s], w.ys[f], u);
+        jv = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)];
+      }
       w.ejv[l] = jv;
       if (l < NU) w.ljv[l] = w.lside[l] ? w.lside[l] * w.sdir[6 + l] : (real)0;
     }
     LHW_SYNC();
     const real sMs = warp_sum<real>([&](int l) { return l < NV ? w.sdir[l] * w.Ms[l] : (real)0; });
     const real sg = warp_sum<real>([&](int l) { return l < NV ? w.sdir[l] * (w.Ma[l] - w.qfs[l]) : (real)0; });
-    // safeguarded 1-D Newton: exact on each linear piece of phi', bracketed by [lo, hi]
+    // (h) exact line search: phi'(alpha) is continuous, piecewise linear, increasing; safeguarded 1-D Newton
     const real LS_TOL = sizeof(real) == 8 ? (real)2e-14 : (real)1e-5;
     real alpha = 1, lo = 0, hi = -1, d_at0 = 0;
     for (int ls = 0; ls < 40; ls++) {
       const real al = ls == 0 ? (real)0 : alpha;
       const real cd = warp_sum<real>([&](int l) {
-        const int s = l >> 2, f = s >> 2;
         real acc = 0;
-        if ((s & 3) < w.ncon[f]) {
-          const real x = w.ejar[l] + al * w.ejv[l];
-          if (x < 0) acc += w.cD[s] * x * w.ejv[l];
-        }
-        if (l < NU && w.lside[l]) {
-          const real x = w.ljar[l] + al * w.ljv[l];
-          if (x < 0) acc += w.lD[l] * x * w.ljv[l];
+        const real x = w.ejar[l] + al * w.ejv[l];   // inactive slots: jar = 1, jv = 0
+        if (x < 0) acc += w.cD[l >> 2] * x * w.ejv[l];
+        if (l < NU) {
+          const real xl = w.ljar[l] + al * w.ljv[l];
+          if (xl < 0) acc += w.lD[l] * xl * w.ljv[l];
         }
         return acc;
       });
@@ -788,10 +897,9 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       }
       if (m_abs(d) <= LS_TOL * m_abs(d_at0)) break;
       const real cdd = warp_sum<real>([&](int l) {
-        const int s = l >> 2, f = s >> 2;
         real acc = 0;
-        if ((s & 3) < w.ncon[f] && w.ejar[l] + al * w.ejv[l] < 0) acc += w.cD[s] * w.ejv[l] * w.ejv[l];
-        if (l < NU && w.lside[l] && w.ljar[l] + al * w.ljv[l] < 0) acc += w.lD[l] * w.ljv[l] * w.ljv[l];
+        if (w.ejar[l] + al * w.ejv[l] < 0) acc += w.cD[l >> 2] * w.ejv[l] * w.ejv[l];
+        if (l < NU && w.ljar[l] + al * w.ljv[l] < 0) acc += w.lD[l] * w.ljv[l] * w.ljv[l];
         return acc;
       });
       if (d < 0) lo = al; else hi = al;
@@ -801,7 +909,12 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       alpha = an;
     }
     LHW_LANES(l) {
-      if (l < NV) w.qacc[l] += alpha * w.sdir[l];
+      if (l < NV) {
+        w.qacc[l] += alpha * w.sdir[l];
+        w.Ma[l] += alpha * w.Ms[l];
+      }
+      w.ejar[l] += alpha * w.ejv[l];
+      if (l < NU) w.ljar[l] += alpha * w.ljv[l];
       if (l == 31) w.iters_total++;
     }
     LHW_SYNC();
@@ -821,14 +934,14 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
         const int f = l - 16, lk = (f + 1) * NJ;
         real t[3];
         cross(w.V[lk], w.xr[lk], t);  // velocity of the link origin: v_o + w x r
-        real g = 0, zmin = 0;
+        real g = 0;
+#pragma unroll
         for (int c = 0; c < 3; c++) w.foot_vel[f][c] = w.V[lk][3 + c] + t[c];
         for (int k = 0; k < w.ncon[f]; k++) {
           const real* cf = w.cF[f * 4 + k];
-          g += m_sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]);
+          g += m_sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]);  // norm of mj_contactForce, friction included
         }
         w.grf[f] = g;
-        (void)zmin;
       }
       if (l == 20) {
         real z = 0;
@@ -849,14 +962,18 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
   // ---------------- P12 mj_Euler: (M + h diag(damping)) a' = qfrc_smooth + qfrc_constraint ; integrate
   if (m.any_damping) {
     LHW_LANES(l) {
-      for (int it = l; it < Model<real, NJ>::NT; it += 32) {
-        const int i = m.h_i[it], j = m.h_j[it];
-        w.H[i][j] = w.M[i][j] + (i == j ? m.h * m.damping[i] : (real)0);
-      }
+      constexpr int NW = (int)(sizeof(Arrow<real, NJ>) / sizeof(real));
+      const real* src = &w.M.r[0][0];
+      real* dst = &w.H.r[0][0];
+      for (int it = l; it < NW; it += 32) dst[it] = src[it];
     }
     LHW_SYNC();
-    arrow_factor<real, NJ>(w);
-    arrow_solve<real, NJ>(w, w.vec);
+    LHW_LANES(l) {
+      if (l < 6) w.H.r[l][l] += m.h * m.damping[l];
+      else if (l < NV) { const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ; w.H.c[ch][k][k] += m.h * m.damping[l]; }
+    }
+    LHW_SYNC();
+    arrow_factor_solve<real, NJ>(w, w.vec);
   } else {
     LHW_LANES(l) {
       if (l < NV) w.vec[l] = w.qacc[l];
@@ -876,7 +993,7 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
     if (l < 3) w.qpos[l] += m.h * w.qvel[l];
     else if (l == 3) {
       real* q = w.qpos + 3;
-      real n = (real)1 / m_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      real n = m_rsqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
       real q0 = q[0] * n, q1 = q[1] * n, q2 = q[2] * n, q3 = q[3] * n;
       const real* wv = w.qvel + 3;
       const real wn = m_sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
@@ -887,7 +1004,7 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
         const real r0 = ca, r1 = wv[0] * sa, r2 = wv[1] * sa, r3 = wv[2] * sa;
         const real o0 = q0 * r0 - q1 * r1 - q2 * r2 - q3 * r3, o1 = q0 * r1 + q1 * r0 + q2 * r3 - q3 * r2;
         const real o2 = q0 * r2 - q1 * r3 + q2 * r0 + q3 * r1, o3 = q0 * r3 + q1 * r2 - q2 * r1 + q3 * r0;
-        n = (real)1 / m_sqrt(o0 * o0 + o1 * o1 + o2 * o2 + o3 * o3);
+        n = m_rsqrt(o0 * o0 + o1 * o1 + o2 * o2 + o3 * o3);
         q0 = o0 * n; q1 = o1 * n; q2 = o2 * n; q3 = o3 * n;
       }
       q[0] = q0; q[1] = q1; q[2] = q2; q[3] = q3;
@@ -897,7 +1014,6 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
   }
   LHW_SYNC();
 }
-
 
 // ================================================================= environment level (one control step)
 // state record I/O: reals [qpos qvel qacc_warm act_len act_vel prev_pred prev_action prev_torque mode_ref ep_rew],
@@ -914,7 +1030,6 @@ LHW_DEV void load_state(Work<real, NJ>& w, const real* sr, const int32_t* si, ui
       w.env_id = env_id;
       w.iters_total = 0;
     }
-    for (int it = l; it < Work<real, NJ>::NV * Work<real, NJ>::NV; it += 32) { (&w.M[0][0])[it] = 0; (&w.H[0][0])[it] = 0; }
   }
   LHW_SYNC();
 }

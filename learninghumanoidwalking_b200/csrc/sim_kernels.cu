@@ -68,8 +68,9 @@ __global__ void __launch_bounds__(128) reset_kernel(real* __restrict__ state_r, 
     for (int it = lane; it < W::NOBS; it += 32) obs_out[(size_t)env * W::NOBS + it] = w.obs[it];
 }
 
+// fp32: 4 warps per block, >= 6 blocks per SM (24 warps, <= 85 regs) ; fp64 is bound by shared memory (13 warps/SM)
 template <class real>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, sizeof(real) == 4 ? 7 : 4)
     step_kernel(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs, uint32_t seed, uint32_t first_id,
                 const real* __restrict__ actions, int max_traj_len, int autoreset, real* __restrict__ obs,
                 real* __restrict__ term_obs, real* __restrict__ reward, real* __restrict__ rew_terms,
@@ -148,7 +149,7 @@ int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision,
   // carve shared memory: as many whole warps per block as fit in ~1/2 .. 1 SM worth, capped at 4
   const char* env_wpb = getenv("LHW_WARPS_PER_BLOCK");
   s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? 2 : 4);
-  if (s->warps_per_block < 1 || s->warps_per_block > 4) s->warps_per_block = 2;
+  if (s->warps_per_block < 1 || s->warps_per_block > 4) s->warps_per_block = precision == 64 ? 2 : 4;
   const size_t smem = s->work_bytes * s->warps_per_block;
   int maxsmem = 0;
   CUDA_OK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));

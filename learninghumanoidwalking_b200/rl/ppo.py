@@ -1,0 +1,244 @@
+"""PPO (clip objective) with the reference's learner API (rl/algos/ppo.py): PPO(env_fn, args, seed),
+.train(env_fn, n_itr), .sample_parallel_with_workers(deterministic) -> BatchData,
+.update_actor_critic(obs, act, ret, adv, mask, mirror_observation, mirror_action) -> 7-tuple,
+.actor_optimizer / .critic_optimizer.
+
+What changes underneath (the hot path of BASELINE.json):
+  * sampling: one DeviceRolloutWorker over a BatchedHumanoidEnv with num_procs environments (no Ray, no host
+    round trip inside a control step);
+  * GAE, advantage normalisation, minibatch gathers and clip+Adam are CUDA launches on device tensors;
+  * multi-GPU: env copies shard by index across ranks; ONE NCCL all-reduce of the flat (actor+critic) gradient
+    per optimiser step, clipping computed on the reduced gradient, advantage statistics all-reduced (2 doubles).
+The loss graph itself stays torch autograd + cuBLAS (north-star: "the small MLP policy left to cuBLAS").
+"""
+from __future__ import annotations
+
+import datetime
+import time
+from copy import deepcopy
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch.nn import functional as F
+
+from .. import _lib
+from .optim import FusedClipAdam
+from .policies import FF_V, Gaussian_FF_Actor
+from .storage import BatchData
+from .workers import DeviceRolloutWorker
+
+
+def get_worker_seed(master_seed: int, worker_id: int, offset: int = 0) -> int:
+    """rl/utils/seeding.py:34-52 (the rank plays the worker's role)."""
+    return (master_seed * 1_000_003 + offset * 10_007 + worker_id) % (2 ** 32 - 1)
+
+
+class PPO:
+    def __init__(self, env_fn, args, seed=None):
+        self.seed = seed
+        self.gamma, self.lam, self.lr, self.eps = args.gamma, args.lam, args.lr, args.eps
+        self.ent_coeff, self.clip = args.entropy_coeff, args.clip
+        self.minibatch_size, self.epochs = args.minibatch_size, args.epochs
+        self.max_traj_len, self.n_proc = args.max_traj_len, args.num_procs
+        self.grad_clip, self.mirror_coeff = args.max_grad_norm, args.mirror_coeff
+        self.eval_freq = getattr(args, "eval_freq", 100)
+        self.imitate_coeff = getattr(args, "imitate_coeff", 0.0)
+        if getattr(args, "recurrent", False):
+            raise NotImplementedError("recurrent policies are outside the accelerated path (SURVEY.md §2 row 5)")
+        self.recurrent = False
+        self.steps_per_env = getattr(args, "steps_per_env", None) or self.max_traj_len
+        self.total_steps, self.iteration_count = 0, 0
+        self.save_path = Path(getattr(args, "logdir", "/tmp/lhw_b200_logs"))
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+
+        if not torch.cuda.is_available():
+            raise _lib.LhwError("PPO needs a CUDA device (no CPU fallback on the hot path)")
+        env = env_fn()
+        self.env = env
+        self.device = env.device
+        obs_dim, action_dim = env.observation_space.shape[0], env.action_space.shape[0]
+        # every rank builds identical initial weights (same seed), like N workers deep-copying one template
+        if seed is not None:
+            torch.manual_seed(seed)
+        policy = Gaussian_FF_Actor(obs_dim, action_dim, init_std=args.std_dev, learn_std=getattr(args, "learn_std", False))
+        critic = FF_V(obs_dim)
+        with torch.no_grad():   # fixed normalisation from the env (rl/algos/ppo.py:94-113)
+            policy.obs_mean = torch.tensor(env.obs_mean, dtype=torch.float32)
+            policy.obs_std = torch.tensor(env.obs_std, dtype=torch.float32)
+            critic.obs_mean, critic.obs_std = policy.obs_mean, policy.obs_std
+        self.obs_rms = None
+        self.policy = policy.to(self.device)
+        self.critic = critic.to(self.device)
+        self.old_policy = deepcopy(self.policy)
+        self.base_policy, self.imitation_projector = None, None
+        self.env_fn = env_fn
+        wseed = get_worker_seed(seed if seed is not None else 0, self.rank)
+        self.workers = [DeviceRolloutWorker(env, self.policy, self.critic, seed=wseed, worker_id=self.rank)]
+        self.batch_size = env.num_envs * self.steps_per_env
+        self.actor_optimizer = self.critic_optimizer = None
+        L = _lib.lib()
+        self._adv_stats = torch.zeros(L.lhw_adv_stats_words(), dtype=torch.float64, device=self.device)
+        self._mb = None
+
+    # ------------------------------------------------------------------ sampling (rl/algos/ppo.py:215-297)
+    def sample_parallel_with_workers(self, deterministic=False) -> BatchData:
+        w = self.workers[0]
+        w.sync_state(iteration_count=self.iteration_count)
+        return w.sample(self.gamma, self.lam, self.steps_per_env, self.max_traj_len, deterministic)
+
+    # ------------------------------------------------------------------ one optimiser step (rl/algos/ppo.py:299-406)
+    def update_actor_critic(self, obs_batch, action_batch, return_batch, advantage_batch, mask,
+                            mirror_observation=None, mirror_action=None):
+        pdf = self.policy.distribution(obs_batch)
+        log_probs = pdf.log_prob(action_batch).sum(-1, keepdim=True)
+        with torch.no_grad():
+            old_log_probs = self.old_policy.distribution(obs_batch).log_prob(action_batch).sum(-1, keepdim=True)
+        ratio = (log_probs - old_log_probs).exp()
+        cpi_loss = ratio * advantage_batch * mask
+        clip_loss = ratio.clamp(1.0 - self.clip, 1.0 + self.clip) * advantage_batch * mask
+        actor_loss = -torch.min(cpi_loss, clip_loss).mean()
+        clip_fraction = torch.mean((torch.abs(ratio.detach() - 1) > self.clip).float())
+        values = self.critic(obs_batch)
+        critic_loss = F.mse_loss(return_batch, values)
+        entropy_penalty = -(pdf.entropy() * mask).mean()
+        deterministic_actions = pdf.mean
+        if mirror_observation is not None and mirror_action is not None:
+            mirror_actions = mirror_action(self.policy(mirror_observation(obs_batch)))
+            mirror_loss = (deterministic_actions - mirror_actions).pow(2).mean()
+        else:
+            mirror_loss = torch.zeros_like(actor_loss)
+        imitation_loss = torch.zeros_like(actor_loss)
+        with torch.no_grad():
+            approx_kl_div = torch.mean((ratio - 1) - (log_probs - old_log_probs))
+        total_loss = (actor_loss + self.mirror_coeff * mirror_loss + self.imitate_coeff * imitation_loss
+                      + self.ent_coeff * entropy_penalty + critic_loss)
+        self.actor_optimizer.zero_grad()
+        self.critic_optimizer.zero_grad()
+        total_loss.backward()
+        if self.world > 1:  # the one exchange step of the path: flat (actor+critic) gradient over NVLink
+            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
+        # clip_grad_norm_ x2 + Adam.step x2 (rl/algos/ppo.py:393-396), norms of the (averaged) global gradient
+        self.actor_optimizer.step()
+        self.critic_optimizer.step()
+        return (actor_loss, entropy_penalty, critic_loss, approx_kl_div, mirror_loss, imitation_loss, clip_fraction)
+
+    def make_optimizers(self):
+        """Adam(lr, eps) for actor and critic (rl/algos/ppo.py:429-430) as fused clip+Adam over one flat buffer."""
+        from .optim import flatten_modules_
+        flat, grad, segs = flatten_modules_([self.policy, self.critic])
+        self._flat_param, self._flat_grad = flat, grad
+        self.actor_optimizer = FusedClipAdam(self.policy, lr=self.lr, eps=self.eps, max_norm=self.grad_clip,
+                                             views=(flat[segs[0][0]:segs[0][1]], grad[segs[0][0]:segs[0][1]]))
+        self.critic_optimizer = FusedClipAdam(self.critic, lr=self.lr, eps=self.eps, max_norm=self.grad_clip,
+                                              views=(flat[segs[1][0]:segs[1][1]], grad[segs[1][0]:segs[1][1]]))
+        self.actor_optimizer.world = self.critic_optimizer.world = self.world
+        # old_policy must not alias the flat buffer
+        self.old_policy = deepcopy(self.policy)
+
+    # ------------------------------------------------------------------ device data path helpers
+    def normalize_advantages(self, returns: torch.Tensor, values: torch.Tensor) -> torch.Tensor:
+        """rl/algos/ppo.py:484-485 on device; statistics are global across ranks."""
+        L, st = _lib.lib(), _lib.current_stream_ptr()
+        n = returns.numel()
+        adv = torch.empty_like(returns)
+        _lib.check(L.lhw_adv_stats(returns.data_ptr(), values.data_ptr(), self._adv_stats.data_ptr(), n, st), "lhw_adv_stats")
+        if self.world > 1:
+            dist.all_reduce(self._adv_stats[0:2], op=dist.ReduceOp.SUM)
+        _lib.check(L.lhw_adv_apply(returns.data_ptr(), values.data_ptr(), adv.data_ptr(), self._adv_stats.data_ptr(), n,
+                                   n * self.world, self.eps, st), "lhw_adv_apply")
+        return adv
+
+    def gather_minibatch(self, obs, act, ret, adv, idx: torch.Tensor):
+        B = idx.numel()
+        if self._mb is None or self._mb[0].shape[0] != B:
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self._mb = (torch.empty(B, obs.shape[1], **f32), torch.empty(B, act.shape[1], **f32),
+                        torch.empty(B, 1, **f32), torch.empty(B, 1, **f32))
+        o, a, r, d = self._mb
+        _lib.check(_lib.lib().lhw_gather_minibatch(obs.data_ptr(), act.data_ptr(), ret.data_ptr(), adv.data_ptr(),
+                                                   idx.data_ptr(), o.data_ptr(), a.data_ptr(), r.data_ptr(), d.data_ptr(), B,
+                                                   obs.shape[1], act.shape[1], _lib.current_stream_ptr()), "lhw_gather_minibatch")
+        return o, a, r, d
+
+    def minibatch_indices(self, num_samples: int, itr: int, epoch: int):
+        """SubsetRandomSampler + BatchSampler(drop_last=True) with the reference's seeding
+        (rl/algos/ppo.py:504-517): generator seeded seed + itr*epochs + epoch, identical on every rank."""
+        g = None
+        if self.seed is not None:
+            g = torch.Generator()
+            g.manual_seed(self.seed + itr * self.epochs + epoch)
+        perm = torch.randperm(num_samples, generator=g)
+        mb = self.minibatch_size or num_samples
+        nb = num_samples // mb
+        return perm[: nb * mb].view(nb, mb).to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ training loop (rl/algos/ppo.py:428-641)
+    def train(self, env_fn, n_itr, verbose=True):
+        if self.actor_optimizer is None:
+            self.make_optimizers()
+        env = self.env
+        obs_mirr = getattr(env, "mirror_clock_observation", None) if self.mirror_coeff else None
+        act_mirr = getattr(env, "mirror_action", None) if self.mirror_coeff else None
+        train_start = time.time()
+        log = []
+        for itr in range(n_itr):
+            if verbose and self.rank == 0:
+                print(f"********** Iteration {itr} ************")
+            self.policy.train()
+            self.critic.train()
+            self.iteration_count = itr
+            t0 = time.time()
+            batch = self.sample_parallel_with_workers()
+            observations, actions = batch.states, batch.actions
+            returns, values = batch.returns.contiguous(), batch.values.contiguous()
+            num_samples = observations.shape[0]
+            torch.cuda.synchronize(self.device)
+            sample_time = time.time() - t0
+            if verbose and self.rank == 0:
+                print(f"Sampling took {sample_time:.2f}s for {num_samples * self.world} steps.")
+            advantages = self.normalize_advantages(returns, values)
+            self.total_steps += num_samples * self.world
+            self.old_policy.load_state_dict(self.policy.state_dict())
+            self.old_policy.obs_mean, self.old_policy.obs_std = self.policy.obs_mean.clone(), self.policy.obs_std.clone()
+            t1 = time.time()
+            stats = torch.zeros(7, device=self.device)
+            n_updates = 0
+            for epoch in range(self.epochs):
+                for idx in self.minibatch_indices(num_samples, itr, epoch):
+                    ob, ab, rb, db = self.gather_minibatch(observations, actions, returns, advantages, idx)
+                    scalars = self.update_actor_critic(ob, ab, rb, db, 1, mirror_observation=obs_mirr, mirror_action=act_mirr)
+                    stats += torch.stack([s.detach().float() for s in scalars])
+                    n_updates += 1
+            stats = (stats / max(1, n_updates)).tolist()   # the only host sync of the optimisation phase
+            optimize_time = time.time() - t1
+            total_time = time.time() - train_start
+            fps = self.total_steps / total_time
+            ep_rew = float(batch.ep_rewards.mean()) if batch.ep_rewards.numel() else float("nan")
+            ep_len = float(batch.ep_lens.float().mean()) if batch.ep_lens.numel() else float("nan")
+            log.append(dict(itr=itr, sample_time=sample_time, optimize_time=optimize_time, fps=fps, ep_rew=ep_rew, ep_len=ep_len,
+                            actor_loss=stats[0], entropy=stats[1], critic_loss=stats[2], kl=stats[3], mirror=stats[4],
+                            clip_frac=stats[6]))
+            if verbose and self.rank == 0:
+                print(f"Optimizer took: {optimize_time:.2f}s")
+                print("-" * 37)
+                for k, v in (("Mean Eprew", ep_rew), ("Mean Eplen", ep_len), ("Actor loss", stats[0]), ("Critic loss", stats[2]),
+                             ("Mirror loss", stats[4]), ("Imitation loss", stats[5]), ("Mean KL Div", stats[3]),
+                             ("Mean Entropy", stats[1]), ("Clip Fraction", stats[6]),
+                             ("Mean noise std", float(torch.as_tensor(self.policy.stds).mean()))):
+                    print(f"| {k:>15} | {v:>15.5g} |")
+                print("-" * 37)
+                eta = round((n_itr - itr) * total_time / (itr + 1))
+                print(f"Total time elapsed: {total_time:.2f}s. Total steps: {self.total_steps} "
+                      f"(fps={fps:.2f}. iter-avg={total_time / (itr + 1):.2f}s. ETA={datetime.timedelta(seconds=eta)})")
+            if self.rank == 0 and (itr == 0 or (itr + 1) % self.eval_freq == 0):
+                self.save(itr)
+        return log
+
+    def save(self, itr):
+        """actor_{itr}.pt / critic_{itr}.pt as whole pickled modules (rl/utils/checkpointer.py:51-83)."""
+        self.save_path.mkdir(parents=True, exist_ok=True)
+        torch.save(self.policy, self.save_path / f"actor_{itr}.pt")
+        torch.save(self.critic, self.save_path / f"critic_{itr}.pt")
