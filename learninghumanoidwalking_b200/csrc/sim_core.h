@@ -164,10 +164,10 @@ template <class real, int NJ> struct Work {
       real A[NL][6], F[NL][6];
     };
     struct {
-      real T[2][NA][6], Af[2][21], Ff[2][6], ya[2][6], ys[2][6];
+      real T[2][NA][6], Af[2][6][6], Ff[2][6], ya[2][6], ys[2][6];
+      real Pm[NCON][3][6];   // contact-frame point map: rows = unit wrenches of (n, t1, t2) applied at the contact
       real cF[NCON][3], cW[NCON][5];
-      real ef[NEDGE], ejv[NEDGE], lf[NU], ljv[NU];
-      int eact[NEDGE], lact[NU];
+      real ejv[NEDGE], ljv[NU];
     };
   };
   // ---- what mj_step leaves behind (pre-integration state of the last substep)
@@ -224,25 +224,12 @@ LHW_DEV double m_rsqrt(double x) {
   return 1.0 / sqrt(x);
 #endif
 }
-// column a of the 3x6 map P(p) from a body's spatial motion [w; v_o] to the contact-frame velocity (n,t1,t2)=(+z,+y,-x)
-// of the body point at p:  u = v_o + w x p
-template <class real> LHW_DEV void pcol(const real* p, int a, real* out) {
-  switch (a) {
-    case 0: out[0] = p[1]; out[1] = -p[2]; out[2] = 0; break;
-    case 1: out[0] = -p[0]; out[1] = 0; out[2] = -p[2]; break;
-    case 2: out[0] = 0; out[1] = p[0]; out[2] = p[1]; break;
-    case 3: out[0] = 0; out[1] = 0; out[2] = -1; break;
-    case 4: out[0] = 0; out[1] = 1; out[2] = 0; break;
-    default: out[0] = 1; out[1] = 0; out[2] = 0; break;
-  }
-}
 // contact-frame velocity of the point p of a body moving with spatial motion y
 template <class real> LHW_DEV void contact_u(const real* p, const real* y, real* u) {
   u[0] = y[5] + y[0] * p[1] - y[1] * p[0];
   u[1] = y[4] + y[2] * p[0] - y[0] * p[2];
   u[2] = -(y[3] + y[1] * p[2] - y[2] * p[1]);
 }
-LHW_DEV int sym6(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 // power-law impedance sigmoid of MuJoCo's getimpedance()
 template <class real> LHW_DEV real impedance(const real* solimp, real dist) {
   const real d0 = solimp[0], dw = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
@@ -716,6 +703,14 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       for (int j = 0; j < NA; j++) acc += w.S[loc2dof<NJ>(f, j)][e] * w.qacc[loc2dof<NJ>(f, j)];
       w.ya[f][e] = acc;
     }
+    if (l < NCON && (l & 3) < w.ncon[l >> 2]) {
+      // rows of P: spatial wrench [p x e ; e] of a unit force along e = n (+z), t1 (+y), t2 (-x) applied at p
+      const real px = w.cpos[l][0], py = w.cpos[l][1], pz = w.cpos[l][2];
+      real* P = &w.Pm[l][0][0];
+      P[0] = py;  P[1] = -px; P[2] = 0;   P[3] = 0;  P[4] = 0; P[5] = 1;
+      P[6] = -pz; P[7] = 0;   P[8] = px;  P[9] = 0;  P[10] = 1; P[11] = 0;
+      P[12] = 0;  P[13] = -pz; P[14] = py; P[15] = -1; P[16] = 0; P[17] = 0;
+    }
   }
   LHW_SYNC();
   LHW_LANES(l) {
@@ -735,64 +730,53 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
   // residuals (Ma, ejar, ljar) are carried incrementally: x += alpha * (direction image)
   bool converged = false;
   for (int iter = 0; iter <= m.max_iter && !converged; iter++) {
-    // (a) edge / limit forces and active sets
-    LHW_LANES(l) {
-      const int s = l >> 2;
-      const real jar = w.ejar[l];
-      w.ef[l] = jar < 0 ? -w.cD[s] * jar : (real)0;   // inactive slots carry jar = 1
-      w.eact[l] = jar < 0;
-      if (l < NU) {
-        const real jl = w.ljar[l];
-        w.lf[l] = jl < 0 ? -w.lD[l] * jl : (real)0;
-        w.lact[l] = jl < 0;
-      }
-    }
-    LHW_SYNC();
-    // (b) per contact: force in the contact frame and the 3x3 weight  W = sum_active D w w'
+    // (a) per contact: force in the contact frame and the 3x3 weight  W = sum_active D w w'  (lane = contact);
+    // active set = sign of the carried residuals (inactive slots carry jar = 1)
     LHW_LANES(l) {
       if (l < NCON && (l & 3) < w.ncon[l >> 2]) {
-        const real* fe = w.ef + 4 * l;
-        w.cF[l][0] = fe[0] + fe[1] + fe[2] + fe[3];
-        w.cF[l][1] = m.mu * (fe[0] - fe[1]);
-        w.cF[l][2] = m.mu * (fe[2] - fe[3]);
-        const int* a = w.eact + 4 * l;
+        const real* jr = w.ejar + 4 * l;
         const real D = w.cD[l], mu = m.mu;
-        w.cW[l][0] = D * (a[0] + a[1] + a[2] + a[3]);
-        w.cW[l][1] = D * mu * (a[0] - a[1]);
-        w.cW[l][2] = D * mu * (a[2] - a[3]);
-        w.cW[l][3] = D * mu * mu * (a[0] + a[1]);
-        w.cW[l][4] = D * mu * mu * (a[2] + a[3]);
+        const int a0 = jr[0] < 0, a1 = jr[1] < 0, a2 = jr[2] < 0, a3 = jr[3] < 0;
+        const real f0 = a0 ? -D * jr[0] : (real)0, f1 = a1 ? -D * jr[1] : (real)0;
+        const real f2 = a2 ? -D * jr[2] : (real)0, f3 = a3 ? -D * jr[3] : (real)0;
+        w.cF[l][0] = f0 + f1 + f2 + f3;
+        w.cF[l][1] = mu * (f0 - f1);
+        w.cF[l][2] = mu * (f2 - f3);
+        w.cW[l][0] = D * (a0 + a1 + a2 + a3);
+        w.cW[l][1] = D * mu * (a0 - a1);
+        w.cW[l][2] = D * mu * (a2 - a3);
+        w.cW[l][3] = D * mu * mu * (a0 + a1);
+        w.cW[l][4] = D * mu * mu * (a2 + a3);
       }
     }
     LHW_SYNC();
-    // (c) per foot: wrench Ff = sum P' cF  (12 items) and spatial weight Af = sum P' W P (2 x 21 items)
+    // (c) per foot: wrench Ff = sum P' cF  (12 items) and spatial weight Af = sum P' W P (2 x 21 items, mirrored)
     LHW_LANES(l) {
       for (int it = l; it < 12 + 42; it += 32) {
         if (it < 12) {
           const int f = it / 6, a = it - f * 6;
           real acc = 0;
           for (int k = 0; k < w.ncon[f]; k++) {
-            real ca[3];
-            pcol(w.cpos[f * 4 + k], a, ca);
-            acc += dot3(ca, w.cF[f * 4 + k]);
+            const real* P = &w.Pm[f * 4 + k][0][0];
+            const real* cf = w.cF[f * 4 + k];
+            acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
           }
           w.Ff[f][a] = acc;
         } else {
-          const int f = (it - 12) / 21, t0 = (it - 12) - f * 21;
-          int a = 0, t = t0;
+          const int f = (it - 12) / 21;
+          int a = 0, t = (it - 12) - f * 21;
           while (t > a) { t -= a + 1; a++; }
           const int b = t;
           real acc = 0;
           for (int k = 0; k < w.ncon[f]; k++) {
             const int s = f * 4 + k;
-            real ca[3], cb[3];
-            pcol(w.cpos[s], a, ca);
-            pcol(w.cpos[s], b, cb);
+            const real* P = &w.Pm[s][0][0];
             const real* W = w.cW[s];
-            acc += ca[0] * (W[0] * cb[0] + W[1] * cb[1] + W[2] * cb[2]) + ca[1] * (W[1] * cb[0] + W[3] * cb[1]) +
-                   ca[2] * (W[2] * cb[0] + W[4] * cb[2]);
+            const real a0 = P[a], a1 = P[6 + a], a2 = P[12 + a], b0 = P[b], b1 = P[6 + b], b2 = P[12 + b];
+            acc += a0 * (W[0] * b0 + W[1] * b1 + W[2] * b2) + a1 * (W[1] * b0 + W[3] * b1) + a2 * (W[2] * b0 + W[4] * b2);
           }
-          w.Af[f][t0] = acc;
+          w.Af[f][a][b] = acc;
+          w.Af[f][b][a] = acc;
         }
       }
     }
@@ -804,7 +788,7 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
         if (l < 6) g -= dot6(w.S[l], w.Ff[0]) + dot6(w.S[l], w.Ff[1]);
         else {
           g -= dot6(w.S[l], w.Ff[(l - 6) / NJ]);
-          if (w.lside[l - 6]) g -= w.lside[l - 6] * w.lf[l - 6];
+          if (w.lside[l - 6] && w.ljar[l - 6] < 0) g -= w.lside[l - 6] * (-w.lD[l - 6] * w.ljar[l - 6]);
         }
         w.grad[l] = g;
         w.sdir[l] = -g;
@@ -818,10 +802,10 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       for (int it = l; it < 2 * NA * 6; it += 32) {
         const int f = it / (NA * 6), r = it - f * (NA * 6), j = r / 6, a = r - j * 6;
         const real* S = w.S[loc2dof<NJ>(f, j)];
-        const real* Af = w.Af[f];
+        const real* Af = w.Af[f][a];
         real acc = 0;
 #pragma unroll
-        for (int b = 0; b < 6; b++) acc += Af[sym6(a, b)] * S[b];
+        for (int b = 0; b < 6; b++) acc += Af[b] * S[b];
         w.T[f][j][a] = w.ncon[f] ? acc : (real)0;
       }
     }
@@ -841,7 +825,7 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
           int k = 0, t = q - ch * (NJ * (NJ + 1) / 2);
           while (t > k) { t -= k + 1; k++; }
           real acc = w.M.c[ch][k][t] + dot6(w.S[6 + ch * NJ + k], w.T[ch][6 + t]);
-          if (k == t && w.lside[ch * NJ + k] && w.lact[ch * NJ + k]) acc += w.lD[ch * NJ + k];
+          if (k == t && w.lside[ch * NJ + k] && w.ljar[ch * NJ + k] < 0) acc += w.lD[ch * NJ + k];
           w.H.c[ch][k][t] = acc;
         }
       }

@@ -41,17 +41,17 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 template <class real>
-__global__ void __launch_bounds__(128) reset_kernel(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs,
+__global__ void __launch_bounds__(32) reset_kernel(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs,
                                                     uint32_t seed, uint32_t first_id, const int32_t* __restrict__ mask,
                                                     int fresh, real* __restrict__ obs_out) {
   constexpr int NJ = NJ_JVRC;
   using W = Work<real, NJ>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int lane = threadIdx.x & 31;
+  const int env = blockIdx.x;
   if (env >= n_envs) return;
   if (mask && !mask[env]) return;
-  W& w = reinterpret_cast<W*>(smem_raw)[warp];
+  W& w = *reinterpret_cast<W*>(smem_raw);
   const Model<real, NJ>& m = cmodel<real>();
   constexpr int NR = Dims<real, NJ>::NSTATE_R;
   real* sr = state_r + (size_t)env * NR;
@@ -68,9 +68,11 @@ __global__ void __launch_bounds__(128) reset_kernel(real* __restrict__ state_r, 
     for (int it = lane; it < W::NOBS; it += 32) obs_out[(size_t)env * W::NOBS + it] = w.obs[it];
 }
 
-// fp32: 4 warps per block, >= 6 blocks per SM (24 warps, <= 85 regs) ; fp64 is bound by shared memory (13 warps/SM)
+// ONE warp per block: the warp's Work struct then sits at a link-time-constant shared-memory address, so every
+// access is [index + immediate] and no base register has to be kept (or rematerialised).  fp32: 28 blocks/SM
+// (the whole 4096-env batch of BASELINE configs[1] is resident at once); fp64: 16 blocks/SM (shared-memory bound).
 template <class real>
-__global__ void __launch_bounds__(128, sizeof(real) == 4 ? 7 : 4)
+__global__ void __launch_bounds__(32, sizeof(real) == 4 ? 28 : 16)
     step_kernel(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs, uint32_t seed, uint32_t first_id,
                 const real* __restrict__ actions, int max_traj_len, int autoreset, real* __restrict__ obs,
                 real* __restrict__ term_obs, real* __restrict__ reward, real* __restrict__ rew_terms,
@@ -79,10 +81,9 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 7 : 4)
   constexpr int NJ = NJ_JVRC;
   using W = Work<real, NJ>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int env = blockIdx.x;
   if (env >= n_envs) return;
-  W& w = reinterpret_cast<W*>(smem_raw)[warp];
+  W& w = *reinterpret_cast<W*>(smem_raw);
   const Model<real, NJ>& m = cmodel<real>();
   constexpr int NR = Dims<real, NJ>::NSTATE_R, NU = 2 * NJ;
   real* sr = state_r + (size_t)env * NR;
@@ -146,10 +147,7 @@ int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision,
     return fail(-4, "malformed model array (fill_model rc " + std::to_string(rc) + ")");
   }
   s->work_bytes = precision == 64 ? sizeof(Work<double, NJ_JVRC>) : sizeof(Work<float, NJ_JVRC>);
-  // carve shared memory: as many whole warps per block as fit in ~1/2 .. 1 SM worth, capped at 4
-  const char* env_wpb = getenv("LHW_WARPS_PER_BLOCK");
-  s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? 2 : 4);
-  if (s->warps_per_block < 1 || s->warps_per_block > 4) s->warps_per_block = precision == 64 ? 2 : 4;
+  s->warps_per_block = 1;
   const size_t smem = s->work_bytes * s->warps_per_block;
   int maxsmem = 0;
   CUDA_OK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));

@@ -1,0 +1,195 @@
+"""GPU tests of the PPO data path through the C-ABI (GAE, advantage normalisation, minibatch gather, clip+Adam)
+against oracle/ppo_oracle.py (pinned to the reference's PPOBuffer by tests/golden/gae.json), and of the
+DeviceRolloutWorker / PPO host classes against the reference's behavioural contract (tests/test_training.py)."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _lib():
+    from learninghumanoidwalking_b200 import _lib
+    return _lib
+
+
+def _gae_gpu(rew, val, ended, boot, last, gamma, lam):
+    L = _lib()
+    T, N = rew.shape
+    d = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device="cuda")
+    r, v, e, b, lv = d(rew), d(val), d(ended, torch.int32), d(boot), d(last)
+    ret = torch.empty_like(r)
+    L.check(L.lib().lhw_gae(r.data_ptr(), v.data_ptr(), e.data_ptr(), b.data_ptr(), lv.data_ptr(), ret.data_ptr(), T, N,
+                            gamma, lam, L.current_stream_ptr()))
+    return ret.cpu().numpy()
+
+
+def test_gae_matches_reference_buffer_golden():
+    for c in json.load(open(os.path.join(GOLD, "gae.json"))):
+        T = len(c["rewards"])
+        ended, boot = np.zeros((T, 1), np.int32), np.zeros((T, 1))
+        for e_, lv in zip(c["path_ends"], c["last_vals"]):
+            ended[e_ - 1, 0], boot[e_ - 1, 0] = 1, lv
+        ret = _gae_gpu(np.array(c["rewards"])[:, None], np.array(c["values"])[:, None], ended, boot, np.zeros(1), c["gamma"], c["lam"])
+        assert np.abs(ret[:, 0] - np.array(c["returns"])).max() < 2e-6 * max(1, np.abs(c["returns"]).max())
+
+
+def test_gae_full_size_against_oracle_and_linearity():
+    from oracle.ppo_oracle import gae_rollout
+    rng = np.random.RandomState(0)
+    T, N = 400, 4096
+    rew, val = rng.uniform(-1, 1, (T, N)).astype(np.float32), rng.uniform(-2, 2, (T, N)).astype(np.float32)
+    ended = (rng.rand(T, N) < 0.02).astype(np.int32)
+    boot = (rng.uniform(-2, 2, (T, N)) * (rng.rand(T, N) < 0.5)).astype(np.float32)
+    last = rng.uniform(-2, 2, N).astype(np.float32)
+    ret = _gae_gpu(rew, val, ended, boot, last, 0.99, 0.95)
+    sub = slice(0, 64)
+    exp = gae_rollout(rew[:, sub].astype(np.float64), val[:, sub].astype(np.float64), ended[:, sub], boot[:, sub].astype(np.float64),
+                      last[sub].astype(np.float64), 0.99, 0.95)
+    assert np.abs(ret[:, sub] - exp).max() < 1e-4
+    # size-independent property: GAE is linear in (rewards, values, boot, last_val)
+    ret2 = _gae_gpu(2 * rew, 2 * val, ended, 2 * boot, 2 * last, 0.99, 0.95)
+    assert np.abs(ret2 - 2 * ret).max() < 1e-4
+
+
+def test_advantage_normalisation():
+    from oracle.ppo_oracle import adv_normalize
+    L = _lib()
+    rng = np.random.RandomState(1)
+    n = 4096 * 400
+    ret, val = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32) * 0.5 + 0.1
+    r, v = torch.as_tensor(ret, device="cuda"), torch.as_tensor(val, device="cuda")
+    stats = torch.zeros(L.lib().lhw_adv_stats_words(), dtype=torch.float64, device="cuda")
+    adv = torch.empty_like(r)
+    st = L.current_stream_ptr()
+    L.check(L.lib().lhw_adv_stats(r.data_ptr(), v.data_ptr(), stats.data_ptr(), n, st))
+    L.check(L.lib().lhw_adv_apply(r.data_ptr(), v.data_ptr(), adv.data_ptr(), stats.data_ptr(), n, n, 1e-5, st))
+    exp = adv_normalize(ret, val, 1e-5)
+    assert np.abs(adv.cpu().numpy() - exp).max() < 1e-5
+    a = adv.double()
+    assert abs(a.mean().item()) < 1e-6 and abs(a.std().item() - 1) < 1e-4
+    # run-to-run deterministic
+    adv2 = torch.empty_like(r)
+    L.check(L.lib().lhw_adv_stats(r.data_ptr(), v.data_ptr(), stats.data_ptr(), n, st))
+    L.check(L.lib().lhw_adv_apply(r.data_ptr(), v.data_ptr(), adv2.data_ptr(), stats.data_ptr(), n, n, 1e-5, st))
+    assert torch.equal(adv, adv2)
+
+
+def test_gather_minibatch_is_exact():
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n, B = 50000, 64
+    obs, act = torch.randn(n, 37, device="cuda", generator=g), torch.randn(n, 12, device="cuda", generator=g)
+    ret, adv = torch.randn(n, 1, device="cuda", generator=g), torch.randn(n, 1, device="cuda", generator=g)
+    idx = torch.randperm(n, device="cuda")[:B]
+    o, a, r, d = (torch.empty(B, 37, device="cuda"), torch.empty(B, 12, device="cuda"), torch.empty(B, 1, device="cuda"), torch.empty(B, 1, device="cuda"))
+    L.check(L.lib().lhw_gather_minibatch(obs.data_ptr(), act.data_ptr(), ret.data_ptr(), adv.data_ptr(), idx.data_ptr(), o.data_ptr(),
+                                         a.data_ptr(), r.data_ptr(), d.data_ptr(), B, 37, 12, L.current_stream_ptr()))
+    assert torch.equal(o, obs[idx]) and torch.equal(a, act[idx]) and torch.equal(r, ret[idx]) and torch.equal(d, adv[idx])
+
+
+def test_fused_clip_adam_matches_torch_clip_grad_norm_and_adam():
+    from learninghumanoidwalking_b200.rl import FusedClipAdam, Gaussian_FF_Actor
+    from oracle.ppo_oracle import clip_adam
+    torch.manual_seed(0)
+    a = Gaussian_FF_Actor(37, 12).cuda()
+    b = Gaussian_FF_Actor(37, 12).cuda()
+    b.load_state_dict(a.state_dict())
+    opt_a = FusedClipAdam(a, lr=3e-4, eps=1e-5, max_norm=0.05)
+    opt_b = torch.optim.Adam(b.parameters(), lr=3e-4, eps=1e-5)
+    p0 = opt_a.flat.double().cpu().numpy().copy()
+    m = v = np.zeros_like(p0)
+    p = p0
+    x = torch.randn(64, 37, device="cuda")
+    for step in range(1, 4):
+        for net, opt in ((a, opt_a), (b, opt_b)):
+            opt.zero_grad()
+            (net(x).pow(2).mean() * 50).backward()
+        g_np = opt_a.grad.double().cpu().numpy().copy()
+        torch.nn.utils.clip_grad_norm_(b.parameters(), 0.05)
+        opt_a.step()
+        opt_b.step()
+        p, m, v, tn = clip_adam(p, g_np, m, v, step, 3e-4, 1e-5, 0.05)
+        assert abs(opt_a.total_norm().item() - tn) < 1e-4 * max(1, tn)
+        flat_b = torch.cat([q.data.reshape(-1) for q in b.parameters()])
+        assert (opt_a.flat - flat_b).abs().max().item() < 2e-6
+        assert np.abs(opt_a.flat.double().cpu().numpy() - p).max() < 2e-6
+
+
+def _args(**kw):
+    d = dict(gamma=0.99, lam=0.95, lr=3e-4, eps=1e-5, entropy_coeff=0.0, clip=0.2, minibatch_size=256, epochs=1,
+             max_traj_len=50, num_procs=64, max_grad_norm=0.05, mirror_coeff=0.4, eval_freq=100, recurrent=False,
+             imitate_coeff=0.0, std_dev=0.223, learn_std=False, logdir="/tmp/lhw_test_logs", steps_per_env=20)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+def _env_fn(n=64, seed=0):
+    from learninghumanoidwalking_b200.envs import BatchedHumanoidEnv
+    from learninghumanoidwalking_b200.rl.symmetric import SymmetricEnv
+    base = lambda: BatchedHumanoidEnv(n, precision=32, seed=seed)
+    probe = base()
+    r = probe.robot
+    probe.close()
+    return lambda: SymmetricEnv(base, mirrored_obs=r.mirrored_obs, mirrored_act=r.mirrored_acts, clock_inds=r.clock_inds)
+
+
+def test_rollout_worker_contract_and_gae_consistency():
+    """tests/test_training.py:79-129 contract + returns == GAE of the stored (rewards, values, boot)."""
+    from learninghumanoidwalking_b200.rl import PPO, BatchData
+    from oracle.ppo_oracle import gae_rollout
+    ppo = PPO(_env_fn(), _args(), seed=0)
+    batch = ppo.sample_parallel_with_workers()
+    assert isinstance(batch, BatchData)
+    n = 64 * 20
+    assert batch.states.shape == (n, 37) and batch.actions.shape == (n, 12)
+    for t in (batch.rewards, batch.values, batch.returns, batch.dones):
+        assert t.shape == (n, 1) and torch.isfinite(t).all()
+    buf = ppo.workers[0]._buf
+    exp = gae_rollout(buf.rewards.double().cpu().numpy(), buf.values.double().cpu().numpy(), buf.ended.cpu().numpy(),
+                      buf.boot.double().cpu().numpy(), buf.last_val.double().cpu().numpy(), 0.99, 0.95)
+    assert np.abs(buf.returns.cpu().numpy() - exp).max() < 1e-4
+    # env-major flattening: sample k of env e sits at e*T + k
+    assert torch.equal(batch.states[3 * 20 + 5], buf.states[5, 3])
+    # episodes persist across calls: traj_len keeps counting
+    tl0 = ppo.env.state_i[:, 2].clone()
+    ppo.sample_parallel_with_workers()
+    assert (ppo.env.state_i[:, 2] != tl0).any()
+    # completed episodes only
+    assert batch.ep_lens.numel() == int(batch.dones.sum().item()) and (batch.ep_lens > 0).all()
+
+
+def test_ppo_update_changes_weights_and_returns_seven_scalars(tmp_path):
+    from learninghumanoidwalking_b200.rl import PPO
+    ppo = PPO(_env_fn(), _args(logdir=str(tmp_path)), seed=1)
+    ppo.make_optimizers()
+    before = ppo._flat_param.clone()
+    batch = ppo.sample_parallel_with_workers()
+    adv = ppo.normalize_advantages(batch.returns.contiguous(), batch.values.contiguous())
+    env = ppo.env
+    out = ppo.update_actor_critic(batch.states[:256], batch.actions[:256], batch.returns[:256], adv[:256], 1,
+                                  mirror_observation=env.mirror_clock_observation, mirror_action=env.mirror_action)
+    assert len(out) == 7 and all(np.isfinite(float(s)) for s in out)
+    assert not torch.equal(before, ppo._flat_param)
+    log = ppo.train(None, 1, verbose=False)
+    assert (tmp_path / "actor_0.pt").exists() and (tmp_path / "critic_0.pt").exists()
+    assert np.isfinite(log[0]["critic_loss"])
+    actor = torch.load(tmp_path / "actor_0.pt", weights_only=False)
+    assert actor(batch.states[:4]).shape == (4, 12)
+
+
+def test_same_seed_gives_bit_identical_weights():
+    """tests/test_determinism.py:79-146: two runs, same seed => torch.equal on the final weights."""
+    from learninghumanoidwalking_b200.rl import PPO
+    finals = []
+    for _ in range(2):
+        ppo = PPO(_env_fn(seed=3), _args(), seed=3)
+        ppo.train(None, 2, verbose=False)
+        finals.append(ppo._flat_param.clone())
+        ppo.env.close()
+    assert torch.equal(finals[0], finals[1])

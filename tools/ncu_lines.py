@@ -48,11 +48,12 @@ for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"{str(key):36s} inst {a[0]:>12d} {100*a[0]/tot:5.1f}%  lanes {a[1]/max(1,a[0]):5.1f}  samples {100*a[2]/max(1,tots):5.1f}%")
 
 # ---- coarse regions of sim_core.h
-REGIONS = [(54, 71, "math wrappers (sqrt/pow/sincos...)"), (72, 84, "warp_sum"), (85, 100, "philox"), (159, 192, "vec helpers (cross/mv3/inert_mul)"),
-           (198, 255, "arrow_factor"), (256, 314, "arrow_solve"), (318, 357, "P1 FK"), (358, 397, "P2 S+inertia"), (398, 414, "P3 composite"),
-           (415, 447, "P4 CRBA+V"), (448, 475, "P5 bias acc"), (476, 531, "P6 link force+contacts"), (532, 567, "P7 subtree+limits"),
-           (568, 596, "P8 qfs+Jc"), (597, 617, "P9 aref"), (618, 729, "P10 newton a-e"), (730, 767, "P10 f linesearch prep"),
-           (768, 810, "P10 linesearch loop"), (811, 848, "P11 lagged"), (849, 904, "P12 euler+integrate"), (905, 1200, "env level")]
+REGIONS = [(54, 71, "math wrappers"), (72, 84, "warp_sum"), (85, 100, "philox"), (179, 265, "vec helpers/pcol/impedance"),
+           (266, 398, "arrow_factor_solve"), (399, 418, "arrow_row_dot"), (422, 470, "P1 FK"), (471, 515, "P2 S+inertia"),
+           (516, 541, "P3 comp+V"), (542, 568, "P4 rootcomp+velprod"), (569, 604, "P5 CRBA+A"), (605, 665, "P6 F+contacts+limits"),
+           (666, 689, "P7 subtree+aref"), (690, 708, "P8 qfs"), (709, 733, "P9 newton init"), (734, 775, "P10 a-b forces"),
+           (776, 812, "P10 c Ff/Af"), (813, 830, "P10 d grad"), (831, 849, "P10 e T"), (850, 879, "P10 f-g H,images"),
+           (880, 923, "P10 h linesearch+update"), (924, 961, "P11 lagged"), (962, 1020, "P12 euler+integrate"), (1021, 1400, "env level")]
 reg = defaultdict(lambda: [0, 0, 0])
 for (f, ln), a in agg.items() if all(k is not None for k in agg) else [(k, v) for k, v in agg.items() if k is not None]:
     name = f if f != "sim_core.h" else next((n for lo, hi, n in REGIONS if lo <= ln <= hi), "other")
