@@ -23,6 +23,13 @@ template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b
     for (int k = 0; k < 3; k++) m.com[i][k] = (real)rd();
     for (int k = 0; k < 6; k++) m.inertia[i][k] = (real)rd();
   }
+  for (int i = 0; i < NL; i++) {
+    m.axis_id[i] = -1;
+    bool ident = true;
+    for (int k = 0; k < 9; k++) ident = ident && (double)m.link_rot[i][k] == ((k % 4 == 0) ? 1.0 : 0.0);
+    for (int a = 0; a < 3 && ident && i > 0; a++)
+      if ((double)m.axis[i][a] == 1.0 && (double)m.axis[i][(a + 1) % 3] == 0.0 && (double)m.axis[i][(a + 2) % 3] == 0.0) m.axis_id[i] = a;
+  }
   m.any_damping = 0;
   for (int d = 0; d < NV; d++) {
     m.armature[d] = (real)rd();
@@ -70,17 +77,6 @@ template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b
   for (int c = 0; c < 4; c++)
     for (int k = 0; k < m.period; k++) m.clock[c][k] = (real)rd();
   if (p != n) return -3;
-  // structurally non-zero lower-triangle entries of the arrow matrix
-  int t_ = 0;
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j <= i; j++) { m.h_i[t_] = (unsigned char)i; m.h_j[t_] = (unsigned char)j; t_++; }
-  for (int c = 0; c < 2; c++)
-    for (int k = 0; k < NJ; k++) {
-      const int i = 6 + c * NJ + k;
-      for (int j = 0; j < 6; j++) { m.h_i[t_] = (unsigned char)i; m.h_j[t_] = (unsigned char)j; t_++; }
-      for (int kk = 0; kk <= k; kk++) { m.h_i[t_] = (unsigned char)i; m.h_j[t_] = (unsigned char)(6 + c * NJ + kk); t_++; }
-    }
-  if (t_ != Model<real, NJ>::NT) return -4;
   return 0;
 }
 

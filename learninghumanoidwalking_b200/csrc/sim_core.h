@@ -64,8 +64,8 @@ LHW_DEV float m_atan2(float y, float x) { return atan2f(y, x); }
 LHW_DEV double m_atan2(double y, double x) { return atan2(y, x); }
 LHW_DEV float m_pow(float x, float y) { return powf(x, y); }
 LHW_DEV double m_pow(double x, double y) { return pow(x, y); }
-LHW_DEV void m_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
-LHW_DEV void m_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+LHW_DEV void m_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+LHW_DEV void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 template <class T> LHW_DEV T m_min(T a, T b) { return a < b ? a : b; }
 template <class T> LHW_DEV T m_max(T a, T b) { return a > b ? a : b; }
 
@@ -113,7 +113,7 @@ template <class real, int NJ> struct Model {
   real head[3], fcap, goal_height;
   real clock[4][MAXPERIOD];  // r_frc r_vel l_frc l_vel
   int max_iter, frame_skip, period, any_damping;
-  unsigned char h_i[NT], h_j[NT];
+  int axis_id[NL];  // 0/1/2: hinge axis is +e_x/+e_y/+e_z of the link frame AND link_rot is the identity (fast FK path); -1: general
 };
 
 template <class real, int NJ> struct Dims {
@@ -162,6 +162,8 @@ template <class real, int NJ> struct Work {
     struct {
       real inert[NL][10], comp[NL][10];
       real A[NL][6], F[NL][6];
+      real ccd[16];   // signed distance of each foot-box corner (8 per foot), > 0: not a contact candidate
+      int cslot[NCON];
     };
     struct {
       real T[2][NA][6], Af[2][6][6], Ff[2][6], ya[2][6], ys[2][6];
@@ -433,19 +435,31 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
         const real* Rp = w.xmat[p];
         if (e < 9) {
           const int r = e / 3, c = e - 3 * r;
-          // column c of (link_rot * Rj):  Rj[:,c] = cos e_c + (1-cos) a_c a + sin (a x e_c)
-          const real* a = m.axis[i];
-          const real sn = w.sc[i - 1][0], cs = w.sc[i - 1][1], t = 1 - cs;
-          real col[3] = {t * a[c] * a[0], t * a[c] * a[1], t * a[c] * a[2]};
-          col[c] += cs;
-          const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;  // a x e_c : [c1] -= a[c2]... cyclic
-          col[c1] += sn * a[c2];
-          col[c2] -= sn * a[c1];
-          const real* L0 = m.link_rot[i];
-          const real b0 = L0[0] * col[0] + L0[1] * col[1] + L0[2] * col[2];
-          const real b1 = L0[3] * col[0] + L0[4] * col[1] + L0[5] * col[2];
-          const real b2 = L0[6] * col[0] + L0[7] * col[1] + L0[8] * col[2];
-          w.xmat[i][e] = Rp[3 * r] * b0 + Rp[3 * r + 1] * b1 + Rp[3 * r + 2] * b2;
+          const real sn = w.sc[i - 1][0], cs = w.sc[i - 1][1];
+          const int ax = m.axis_id[i];
+          if (ax >= 0) {
+            // rotation about a coordinate axis of the parent-aligned frame: column `ax` is kept, the other two
+            // columns rotate in their plane:  col_b' = cs col_b + sn col_c ,  col_c' = cs col_c - sn col_b  (b=ax+1, c=ax+2 cyclic)
+            const int b = ax == 2 ? 0 : ax + 1, cc = ax == 0 ? 2 : ax - 1;
+            real v = Rp[3 * r + c];
+            if (c == b) v = cs * v + sn * Rp[3 * r + cc];
+            else if (c == cc) v = cs * v - sn * Rp[3 * r + b];
+            w.xmat[i][e] = v;
+          } else {
+            // column c of (link_rot * Rj):  Rj[:,c] = cos e_c + (1-cos) a_c a + sin (a x e_c)
+            const real* a = m.axis[i];
+            const real t = 1 - cs;
+            real col[3] = {t * a[c] * a[0], t * a[c] * a[1], t * a[c] * a[2]};
+            col[c] += cs;
+            const int c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
+            col[c1] += sn * a[c2];
+            col[c2] -= sn * a[c1];
+            const real* L0 = m.link_rot[i];
+            const real b0 = L0[0] * col[0] + L0[1] * col[1] + L0[2] * col[2];
+            const real b1 = L0[3] * col[0] + L0[4] * col[1] + L0[5] * col[2];
+            const real b2 = L0[6] * col[0] + L0[7] * col[1] + L0[8] * col[2];
+            w.xmat[i][e] = Rp[3 * r] * b0 + Rp[3 * r + 1] * b1 + Rp[3 * r + 2] * b2;
+          }
         } else {
           const int r = e - 9;
           const real* lp = m.link_pos[i];
@@ -589,8 +603,7 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
     }
   }
   LHW_SYNC();
-  // ---------------- P6 link forces f_i = I A + V x* (I V) (lane = link) ; contact detection (lanes 30,31 = feet) ;
-  // joint limits (lanes 14..14+NU)
+  // ---------------- P6 link forces f_i = I A + V x* (I V) (lane = link) ; foot-box corner candidates (lanes 16..31)
   LHW_LANES(l) {
     if (l < NL) {
       real IA[6], IV[6], t1[3], t2[3], t3[3];
@@ -605,53 +618,63 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
         w.F[l][c] = IA[c] + t1[c] + t2[c];
         w.F[l][3 + c] = IA[3 + c] + t3[c];
       }
-    } else if (l >= 30) {
-      // mjc_PlaneBox against the ground plane z = 0 (normal +z): corners in index order, at most 4
-      const int f = l - 30, lk = (f + 1) * NJ;
-      real ctr[3], v[3], corner[3];
-      mv3(w.xmat[lk], m.foot_pos[f], ctr);
-#pragma unroll
-      for (int c = 0; c < 3; c++) ctr[c] += w.xr[lk][c];
-      const real dist0 = w.o[2] + ctr[2];
-      int cnt = 0;
-      for (int i = 0; i < 8 && cnt < 4; i++) {
-        v[0] = (i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0];
-        v[1] = (i & 2) ? m.foot_size[f][1] : -m.foot_size[f][1];
-        v[2] = (i & 4) ? m.foot_size[f][2] : -m.foot_size[f][2];
-        const real ld = w.xmat[lk][6] * v[0] + w.xmat[lk][7] * v[1] + w.xmat[lk][8] * v[2];
-        if (dist0 + ld > 0 || ld > 0) continue;
-        mv3(w.xmat[lk], v, corner);
-        const int s = f * 4 + cnt;
-        const real cd = dist0 + ld;
-        w.cpos[s][0] = corner[0] + ctr[0];
-        w.cpos[s][1] = corner[1] + ctr[1];
-        w.cpos[s][2] = corner[2] + ctr[2] - (real)0.5 * cd;
-        const real imp = impedance(m.solimp, cd);
-        const real Rn = m_max((real)1e-15, (1 - imp) / imp * (m.foot_invw[f] * (1 + m.mu * m.mu)));
-        w.cD[s] = (real)1 / (2 * m.mu_reg * m.mu_reg * Rn);
-        w.cKid[s] = m.K * imp * cd;
-        cnt++;
-      }
-      w.ncon[f] = cnt;
-    } else if (l >= 14 && l < 14 + NU) {
-      const int u = l - 14, d = 6 + u;
-      const real q = w.qpos[7 + u];
-      const real dlo = q - m.range_lo[d], dhi = m.range_hi[d] - q;
-      int side = 0;
-      real dist = 0;
-      if (dlo < 0) { side = 1; dist = dlo; }
-      else if (dhi < 0) { side = -1; dist = dhi; }
-      w.lside[u] = side;
-      if (side) {
-        const real imp = impedance(m.solimp, dist);
-        w.lD[u] = (real)1 / m_max((real)1e-15, (1 - imp) / imp * m.dof_invw[d]);
-        w.laref[u] = -m.B * (side * w.qvel[d]) - m.K * imp * dist;
-      }
+    } else if (l >= 16) {
+      // mjc_PlaneBox against the ground plane z = 0 (normal +z): one lane per (foot, corner); a corner is a contact
+      // candidate when it is below the plane and on the plane side of the box centre
+      const int f = (l - 16) >> 3, i = (l - 16) & 7, lk = (f + 1) * NJ;
+      const real* R = w.xmat[lk];
+      const real dist0 = w.o[2] + w.xr[lk][2] + R[6] * m.foot_pos[f][0] + R[7] * m.foot_pos[f][1] + R[8] * m.foot_pos[f][2];
+      const real ld = R[6] * ((i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0]) +
+                      R[7] * ((i & 2) ? m.foot_size[f][1] : -m.foot_size[f][1]) +
+                      R[8] * ((i & 4) ? m.foot_size[f][2] : -m.foot_size[f][2]);
+      w.ccd[l - 16] = (dist0 + ld > 0 || ld > 0) ? (real)1 : dist0 + ld;
     }
   }
   LHW_SYNC();
-  // ---------------- P7 subtree forces (suffix sums, lane = chain*6 + comp) ; pyramid-edge reference accelerations
-  // (lane = edge; uses the foot link's spatial velocity from P3)
+  // ---------------- P7 subtree forces (suffix sums, lane = chain*6 + comp) ; contact slots: the first (at most) 4
+  // candidate corners of each foot in corner-index order, as mjc_PlaneBox returns them (lanes 12, 13)
+  LHW_LANES(l) {
+    if (l < 12) {
+      const int ch = l / 6, e = l - ch * 6;
+      real acc = 0;
+#pragma unroll
+      for (int k = NJ - 1; k >= 0; k--) {
+        const int i = 1 + ch * NJ + k;
+        acc += w.F[i][e];
+        w.F[i][e] = acc;
+      }
+    } else if (l < 14) {
+      const int f = l - 12;
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (cnt < 4 && !(w.ccd[f * 8 + i] > 0)) { w.cslot[f * 4 + cnt] = i; cnt++; }
+      w.ncon[f] = cnt;
+    }
+  }
+  LHW_SYNC();
+  // ---------------- P7b per contact slot: position, impedance, regulariser, reference stiffness (lane = slot)
+  LHW_LANES(l) {
+    if (l < NCON && (l & 3) < w.ncon[l >> 2]) {
+      const int f = l >> 2, lk = (f + 1) * NJ, i = w.cslot[l];
+      const real cd = w.ccd[f * 8 + i];
+      real v[3], corner[3];
+      v[0] = ((i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0]) + m.foot_pos[f][0];
+      v[1] = ((i & 2) ? m.foot_size[f][1] : -m.foot_size[f][1]) + m.foot_pos[f][1];
+      v[2] = ((i & 4) ? m.foot_size[f][2] : -m.foot_size[f][2]) + m.foot_pos[f][2];
+      mv3(w.xmat[lk], v, corner);
+      w.cpos[l][0] = corner[0] + w.xr[lk][0];
+      w.cpos[l][1] = corner[1] + w.xr[lk][1];
+      w.cpos[l][2] = corner[2] + w.xr[lk][2] - (real)0.5 * cd;
+      const real imp = impedance(m.solimp, cd);
+      const real Rn = m_max((real)1e-15, (1 - imp) / imp * (m.foot_invw[f] * (1 + m.mu * m.mu)));
+      w.cD[l] = (real)1 / (2 * m.mu_reg * m.mu_reg * Rn);
+      w.cKid[l] = m.K * imp * cd;
+    }
+  }
+  LHW_SYNC();
+  // ---------------- P8 pyramid-edge reference accelerations (lane = edge; foot spatial velocity from P3) ;
+  // qfrc_smooth + warm start (lane = dof) ; joint limits (lanes 18..18+NU)
   LHW_LANES(l) {
     {
       const int s = l >> 2, e = l & 3, f = s >> 2;
@@ -662,20 +685,6 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
         w.earef[l] = -m.B * vel - w.cKid[s];
       }
     }
-    if (l < 12) {
-      const int ch = l / 6, e = l - ch * 6;
-      real acc = 0;
-#pragma unroll
-      for (int k = NJ - 1; k >= 0; k--) {
-        const int i = 1 + ch * NJ + k;
-        acc += w.F[i][e];
-        w.F[i][e] = acc;
-      }
-    }
-  }
-  LHW_SYNC();
-  // ---------------- P8 qfrc_smooth (lane = dof), warm start
-  LHW_LANES(l) {
     if (l < NV) {
       const int lk = dof_link<NJ>(l);
       real Ft[6];
@@ -690,6 +699,20 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       if (l >= 6) q += w.ctrl[l - 6];
       w.qfs[l] = q;
       w.qacc[l] = w.qacc_warm[l];
+    } else if (l < NV + NU) {
+      const int u = l - NV, d = 6 + u;
+      const real q = w.qpos[7 + u];
+      const real dlo = q - m.range_lo[d], dhi = m.range_hi[d] - q;
+      int side = 0;
+      real dist = 0;
+      if (dlo < 0) { side = 1; dist = dlo; }
+      else if (dhi < 0) { side = -1; dist = dhi; }
+      w.lside[u] = side;
+      if (side) {
+        const real imp = impedance(m.solimp, dist);
+        w.lD[u] = (real)1 / m_max((real)1e-15, (1 - imp) / imp * m.dof_invw[d]);
+        w.laref[u] = -m.B * (side * w.qvel[d]) - m.K * imp * dist;
+      }
     }
   }
   LHW_SYNC();
@@ -750,34 +773,17 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
       }
     }
     LHW_SYNC();
-    // (c) per foot: wrench Ff = sum P' cF  (12 items) and spatial weight Af = sum P' W P (2 x 21 items, mirrored)
+    // (c) per foot: wrench Ff = sum P' cF  (lane = foot*6 + component)
     LHW_LANES(l) {
-      for (int it = l; it < 12 + 42; it += 32) {
-        if (it < 12) {
-          const int f = it / 6, a = it - f * 6;
-          real acc = 0;
-          for (int k = 0; k < w.ncon[f]; k++) {
-            const real* P = &w.Pm[f * 4 + k][0][0];
-            const real* cf = w.cF[f * 4 + k];
-            acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
-          }
-          w.Ff[f][a] = acc;
-        } else {
-          const int f = (it - 12) / 21;
-          int a = 0, t = (it - 12) - f * 21;
-          while (t > a) { t -= a + 1; a++; }
-          const int b = t;
-          real acc = 0;
-          for (int k = 0; k < w.ncon[f]; k++) {
-            const int s = f * 4 + k;
-            const real* P = &w.Pm[s][0][0];
-            const real* W = w.cW[s];
-            const real a0 = P[a], a1 = P[6 + a], a2 = P[12 + a], b0 = P[b], b1 = P[6 + b], b2 = P[12 + b];
-            acc += a0 * (W[0] * b0 + W[1] * b1 + W[2] * b2) + a1 * (W[1] * b0 + W[3] * b1) + a2 * (W[2] * b0 + W[4] * b2);
-          }
-          w.Af[f][a][b] = acc;
-          w.Af[f][b][a] = acc;
+      if (l < 12) {
+        const int f = l / 6, a = l - f * 6;
+        real acc = 0;
+        for (int k = 0; k < w.ncon[f]; k++) {
+          const real* P = &w.Pm[f * 4 + k][0][0];
+          const real* cf = w.cF[f * 4 + k];
+          acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
         }
+        w.Ff[f][a] = acc;
       }
     }
     LHW_SYNC();
@@ -797,7 +803,27 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
     LHW_SYNC();
     const real g2 = warp_sum<real>([&](int l) { return l < NV ? w.grad[l] * w.grad[l] : (real)0; });
     if (g2 < m.tol2 || iter == m.max_iter) { converged = true; break; }
-    // (e) T_f = Af S_f (per foot, per ancestor dof, per component)
+    // (e) a Newton step is needed: spatial weight per foot  Af = sum P' W P  (2 x 21 items, mirrored) ...
+    LHW_LANES(l) {
+      for (int it = l; it < 42; it += 32) {
+        const int f = it / 21;
+        int a = 0, t = it - f * 21;
+        while (t > a) { t -= a + 1; a++; }
+        const int b = t;
+        real acc = 0;
+        for (int k = 0; k < w.ncon[f]; k++) {
+          const int s = f * 4 + k;
+          const real* P = &w.Pm[s][0][0];
+          const real* W = w.cW[s];
+          const real a0 = P[a], a1 = P[6 + a], a2 = P[12 + a], b0 = P[b], b1 = P[6 + b], b2 = P[12 + b];
+          acc += a0 * (W[0] * b0 + W[1] * b1 + W[2] * b2) + a1 * (W[1] * b0 + W[3] * b1) + a2 * (W[2] * b0 + W[4] * b2);
+        }
+        w.Af[f][a][b] = acc;
+        w.Af[f][b][a] = acc;
+      }
+    }
+    LHW_SYNC();
+    // ... and T_f = Af S_f (per foot, per ancestor dof, per component)
     LHW_LANES(l) {
       for (int it = l; it < 2 * NA * 6; it += 32) {
         const int f = it / (NA * 6), r = it - f * (NA * 6), j = r / 6, a = r - j * 6;

@@ -34,7 +34,20 @@ class _MLP(nn.Module):
         return self.out(x)
 
 
-class Gaussian_FF_Actor(nn.Module):
+class _NormAttrs(nn.Module):
+    """obs_mean / obs_std / stds are plain tensor attributes in the reference (moved by hand in rl/algos/ppo.py:136-147);
+    here they follow .to()/.cuda()/.cpu() automatically."""
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        for name in ("stds", "obs_mean", "obs_std"):
+            v = getattr(self, name, None)
+            if torch.is_tensor(v) and not isinstance(v, nn.Parameter):
+                setattr(self, name, fn(v))
+        return self
+
+
+class Gaussian_FF_Actor(_NormAttrs):
     def __init__(self, state_dim, action_dim, layers=(256, 256), init_std=0.2, learn_std=False, bounded=False):
         super().__init__()
         self.net = _MLP(state_dim, layers, action_dim, 0.01)
@@ -45,14 +58,6 @@ class Gaussian_FF_Actor(nn.Module):
             self.stds = init_std * torch.ones(action_dim)
         self.state_dim, self.action_dim, self.bounded = state_dim, action_dim, bounded
         self.obs_mean, self.obs_std = 0.0, 1.0
-
-    def _apply(self, fn, *a, **k):
-        super()._apply(fn, *a, **k)
-        for name in ("stds", "obs_mean", "obs_std"):  # plain-tensor attributes follow .to()/.cuda() like the reference moves them by hand
-            v = getattr(self, name)
-            if torch.is_tensor(v) and not isinstance(v, nn.Parameter):
-                setattr(self, name, fn(v))
-        return self
 
     def _get_dist_params(self, state):
         mean = self.net((state - self.obs_mean) / self.obs_std)
@@ -69,13 +74,12 @@ class Gaussian_FF_Actor(nn.Module):
         return torch.distributions.Normal(mu, sd)
 
 
-class FF_V(nn.Module):
+class FF_V(_NormAttrs):
     def __init__(self, state_dim, layers=(256, 256)):
         super().__init__()
         self.net = _MLP(state_dim, layers, 1, 1.0)
         self.obs_mean, self.obs_std = 0.0, 1.0
 
-    _apply = Gaussian_FF_Actor._apply
     stds = None
 
     def forward(self, state):

@@ -1,0 +1,56 @@
+"""Host-side policy / mirror helpers against vectors produced by the reference's own classes
+(tools/gen_golden.py: rl/policies/actor.py, critic.py, rl/envs/wrappers.py)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "policy.json")))
+
+
+def _load(net, sd, hidden_prefix, out_prefix):
+    for i, lin in enumerate(net.hidden):
+        lin.weight.data = torch.tensor(sd[f"{hidden_prefix}.{i}.weight"])
+        lin.bias.data = torch.tensor(sd[f"{hidden_prefix}.{i}.bias"])
+    net.out.weight.data = torch.tensor(sd[f"{out_prefix}.weight"])
+    net.out.bias.data = torch.tensor(sd[f"{out_prefix}.bias"])
+
+
+def test_actor_and_critic_forward_match_reference_modules():
+    from learninghumanoidwalking_b200.rl.policies import FF_V, Gaussian_FF_Actor
+    a, c = Gaussian_FF_Actor(37, 12, layers=(16, 16)), FF_V(37, layers=(16, 16))
+    _load(a.net, G["actor"], "actor_layers", "means")
+    _load(c.net, G["critic"], "critic_layers", "network_out")
+    a.obs_mean = c.obs_mean = torch.tensor(G["obs_mean"])
+    a.obs_std = c.obs_std = torch.tensor(G["obs_std"])
+    x = torch.tensor(G["x"])
+    assert (a(x) - torch.tensor(G["mu"])).abs().max() < 1e-6
+    assert (c(x) - torch.tensor(G["v"])).abs().max() < 1e-6
+
+
+def test_parameter_counts_and_normc_init():
+    from learninghumanoidwalking_b200.rl.policies import FF_V, Gaussian_FF_Actor
+    a, c = Gaussian_FF_Actor(37, 12), FF_V(37)
+    assert sum(p.numel() for p in a.parameters()) == G["n_actor"] == 78604
+    assert sum(p.numel() for p in c.parameters()) == G["n_critic"] == 75777
+    assert abs(float(a.net.out.weight.norm(dim=1).mean()) - G["out_layer_norm"]) < 1e-6   # output layer x 0.01
+    assert torch.allclose(a.net.hidden[0].weight.norm(dim=1), torch.ones(256), atol=1e-5)    # normc rows
+    assert float(a.net.hidden[0].bias.abs().max()) == 0.0
+
+
+def test_mirror_matrices_match_reference():
+    from learninghumanoidwalking_b200.rl.symmetric import symmetry_matrix
+    assert np.array_equal(symmetry_matrix(G["mirrored_obs"]).numpy(), np.array(G["obs_mirror_matrix"], dtype=np.float32))
+    assert np.array_equal(symmetry_matrix(G["mirrored_act"]).numpy(), np.array(G["act_mirror_matrix"], dtype=np.float32))
+
+
+def test_clock_mirror_is_the_reference_formula():
+    """sin(arcsin(c) + pi) == -c on the clock entries (rl/envs/wrappers.py:64-75)."""
+    from learninghumanoidwalking_b200.rl.symmetric import SymmetricEnv
+    env = SymmetricEnv(lambda: object(), mirrored_obs=G["mirrored_obs"], mirrored_act=G["mirrored_act"], clock_inds=[29, 30])
+    obs = torch.rand(6, 37) * 1.6 - 0.8
+    ref = obs @ torch.tensor(G["obs_mirror_matrix"], dtype=torch.float32)
+    for i in (29, 30):
+        ref[:, i] = torch.sin(torch.arcsin(ref[:, i]) + np.pi)
+    assert (env.mirror_clock_observation(obs) - ref).abs().max() < 1e-6
