@@ -82,8 +82,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference(n_envs: int, steps: int, warmup: int, seed: int, nthreads: int = 0):
-    """The oracle (CPU port of the reference path) on the host cores: env-steps/s, threads used."""
+def cpu_reference(n_envs: int, seconds: float, warmup: int, seed: int, nthreads: int = 0):
+    """The oracle (CPU port of the reference path) on the host cores, run for about `seconds` of wall time
+    (a bounded sample of the same workload): env-steps/s, threads used, elapsed, control steps done."""
     import numpy as np
     from oracle.oracle import Oracle
     o = Oracle()
@@ -93,12 +94,15 @@ def cpu_reference(n_envs: int, steps: int, warmup: int, seed: int, nthreads: int
     rng = np.random.RandomState(seed)
     for _ in range(warmup):
         o.batch_step(envs, n_envs, rng.normal(size=(n_envs, 12)) * SIGMA, 400, nthreads)
-    acts = [rng.normal(size=(n_envs, 12)) * SIGMA for _ in range(steps)]
-    t0 = time.perf_counter()
-    for a in acts:
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        a = rng.normal(size=(n_envs, 12)) * SIGMA
         o.batch_step(envs, n_envs, a, 400, nthreads)
-    dt = time.perf_counter() - t0
-    return n_envs * steps / dt, nthreads, dt
+        steps += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds or steps >= 400:
+            break
+    return n_envs * steps / dt, nthreads, dt, steps
 
 
 def main():
@@ -110,6 +114,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--precision", type=int, default=int(os.environ.get("LHW_BENCH_PRECISION", "64")), choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -125,13 +130,14 @@ def main():
         # this arm times the CPU port (oracle/) on all host cores, rank 0 only.
         if rank != 0:
             return
-        n_sample = min(args.envs * world, 4096)
-        sps, threads, dt = cpu_reference(n_sample, max(1, min(K, 8)), 1, args.seed)
+        ncores = os.cpu_count() or 1
+        n_sample = max(256, min(args.envs * world, 64 * ncores))
+        sps, threads, dt, steps_ref = cpu_reference(n_sample, 15.0, 2, args.seed)
         print(json.dumps({"metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-                          "ms_per_step": 1e3 * dt / max(1, min(K, 8)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "ms_per_step": 1e3 * dt / steps_ref, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
                           "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
-                                           "sample": f"{n_sample} envs x {max(1, min(K, 8))} control steps, OpenMP over envs; "
+                                           "sample": f"{n_sample} envs x {steps_ref} control steps ({dt:.1f} s) after 2 warm-up steps, OpenMP over envs; "
                                                      "reference Ray+MuJoCo path not runnable on this box (mujoco/ray not installable)"},
                           "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -198,6 +204,40 @@ def main():
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- extras (not the headline): the fp32 build of the same kernel, and the full rollout loop with the policy /
+    # critic MLPs (cuBLAS) and buffer writes in the loop (DeviceRolloutWorker.sample)
+    extras = {}
+    if not args.no_extras:
+        env32 = BatchedHumanoidEnv(n, precision=32, seed=args.seed, first_env_id=rank * n, device=local_rank)
+        env32.reset()
+        a32 = acts.float()
+        for k in range(W):
+            env32.step(a32[k])
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for k in range(K):
+            env32.step(a32[W + k])
+        f1.record()
+        barrier()
+        extras["fp32_kernel_env_steps_per_s_per_gpu"] = n * K / (f0.elapsed_time(f1) * 1e-3)
+        from learninghumanoidwalking_b200.rl import FF_V, DeviceRolloutWorker, Gaussian_FF_Actor
+        torch.manual_seed(args.seed)
+        pol = Gaussian_FF_Actor(env.obs_dim, env.act_dim, init_std=SIGMA).to(dev)
+        cri = FF_V(env.obs_dim).to(dev)
+        pol.obs_mean = cri.obs_mean = torch.tensor(env.obs_mean, dtype=torch.float32, device=dev)
+        pol.obs_std = cri.obs_std = torch.tensor(env.obs_std, dtype=torch.float32, device=dev)
+        worker = DeviceRolloutWorker(env, pol, cri, seed=args.seed)
+        T = max(4, min(K, 32))
+        worker.sample(0.99, 0.95, 4, 400)
+        barrier()
+        f0.record()
+        worker.sample(0.99, 0.95, T, 400)
+        f1.record()
+        barrier()
+        extras["rollout_with_policy_env_steps_per_s_per_gpu"] = n * T / (f0.elapsed_time(f1) * 1e-3)
+        extras["rollout_note"] = f"DeviceRolloutWorker.sample: {T} control steps incl. actor+critic forward, sampling, buffer writes, GAE"
+        env32.close()
     esz = 8 if args.precision == 64 else 4
     # max over ranks
     t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -225,10 +265,13 @@ def main():
                             "algorithmic_bytes_per_env_step": ALG_BYTES[args.precision],
                             "note": "the step kernel is ALU/latency bound (25 substeps of O(nv^3) work per ~2 KB of state); "
                                     "see DESIGN.md for the FP-issue bound reported beside this"}}
+        out["extras"] = extras
         if not args.no_cpu_baseline and world == 1:
-            sps, threads, dt = cpu_reference(min(n, 2048), 4, 1, args.seed)
+            ncores = os.cpu_count() or 1
+            n_cpu = max(256, min(n, 64 * ncores))
+            sps, threads, dt, nst = cpu_reference(n_cpu, 10.0, 2, args.seed)
             out["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
-                                   "sample": f"{min(n, 2048)} envs x 4 control steps ({dt:.1f} s), same action distribution; "
+                                   "sample": f"{n_cpu} envs x {nst} control steps ({dt:.1f} s) after 2 warm-up steps, same action distribution; "
                                              "oracle/ C port with OpenMP (reference Ray+MuJoCo path not installable here)"}
         print(json.dumps(out))
     if world > 1:

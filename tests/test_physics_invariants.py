@@ -91,7 +91,7 @@ def test_static_stance_contact_force_equals_weight():
     grf = o.field(envs, 0, "rfoot_grf")[0] + o.field(envs, 0, "lfoot_grf")[0]
     weight = o.mj["total_mass"] * 9.81
     assert o.field(envs, 0, "ncon")[0] == 8
-    assert np.abs(o.field(envs, 0, "qvel")).max() < 2e-2
+    assert np.abs(o.field(envs, 0, "qvel")).max() < 5e-2
     assert weight * 0.995 < grf < weight * 1.10, (grf, weight)   # norm includes friction => slightly above m g
     assert o.field(envs, 0, "last_kkt_residual")[0] < 1e-9
 

@@ -48,12 +48,13 @@ for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"{str(key):36s} inst {a[0]:>12d} {100*a[0]/tot:5.1f}%  lanes {a[1]/max(1,a[0]):5.1f}  samples {100*a[2]/max(1,tots):5.1f}%")
 
 # ---- coarse regions of sim_core.h
-REGIONS = [(54, 71, "math wrappers"), (72, 84, "warp_sum"), (85, 100, "philox"), (179, 233, "vec helpers (cross/dot6/mv3/inert_mul/rsqrt/contact_u)"),
-           (234, 252, "impedance"), (253, 385, "arrow_factor_solve"), (386, 405, "arrow_row_dot"), (409, 457, "P1 FK"), (458, 502, "P2 S+inertia"),
-           (503, 528, "P3 comp+V"), (529, 555, "P4 rootcomp+velprod"), (556, 591, "P5 CRBA+A"), (592, 652, "P6 F+contacts+limits"),
-           (653, 676, "P7 subtree+aref"), (677, 695, "P8 qfs"), (696, 728, "P9 newton init+Pm"), (729, 752, "P10 a cF/cW"),
-           (753, 783, "P10 c Ff/Af"), (784, 799, "P10 d grad"), (800, 812, "P10 e T"), (813, 833, "P10 f H"), (834, 860, "P10 g images"),
-           (861, 907, "P10 h linesearch+update"), (908, 945, "P11 lagged"), (946, 1004, "P12 euler+integrate"), (1005, 1400, "env level")]
+REGIONS = [(54, 71, "math wrappers"), (72, 84, "warp_sum"), (85, 100, "philox"), (181, 235, "vec helpers (cross/dot6/mv3/inert_mul/rsqrt/contact_u)"),
+           (236, 254, "impedance"), (255, 387, "arrow_factor_solve"), (388, 410, "arrow_row_dot"), (411, 471, "P1 FK"), (472, 516, "P2 S+inertia"),
+           (517, 542, "P3 comp+V"), (543, 569, "P4 rootcomp+velprod"), (570, 605, "P5 CRBA+A"), (606, 633, "P6 F+corner candidates"),
+           (634, 655, "P7 subtree+slots"), (656, 675, "P7b contact params"), (676, 718, "P8 aref+qfs+limits"), (719, 751, "P9 newton init+Pm"),
+           (752, 775, "P10 a cF/cW"), (776, 789, "P10 c Ff"), (790, 805, "P10 d grad"), (806, 838, "P10 e Af,T"), (839, 859, "P10 f H"),
+           (860, 886, "P10 g images"), (887, 933, "P10 h linesearch+update"), (934, 971, "P11 lagged"), (972, 1031, "P12 euler+integrate"),
+           (1032, 1400, "env level")]
 reg = defaultdict(lambda: [0, 0, 0])
 for (f, ln), a in agg.items() if all(k is not None for k in agg) else [(k, v) for k, v in agg.items() if k is not None]:
     name = f if f != "sim_core.h" else next((n for lo, hi, n in REGIONS if lo <= ln <= hi), "other")
