@@ -76,6 +76,17 @@ template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b
   if (m.period < 1 || m.period > MAXPERIOD) return -2;
   for (int c = 0; c < 4; c++)
     for (int k = 0; k < m.period; k++) m.clock[c][k] = (real)rd();
+  m.ncap = (int)rd();
+  if (m.ncap < 0 || m.ncap > MAXCAP) return -5;
+  for (int c = 0; c < m.ncap; c++) {
+    m.cap_link[c] = (int)rd();
+    for (int k = 0; k < 3; k++) m.cap_p0[c][k] = (real)rd();
+    for (int k = 0; k < 3; k++) m.cap_p1[c][k] = (real)rd();
+    m.cap_r[c] = (real)rd();
+  }
+  m.npair = (int)rd();
+  if (m.npair < 0 || m.npair > MAXPAIR) return -6;
+  for (int c = 0; c < m.npair; c++) { m.pair_a[c] = (unsigned char)rd(); m.pair_b[c] = (unsigned char)rd(); }
   if (p != n) return -3;
   return 0;
 }

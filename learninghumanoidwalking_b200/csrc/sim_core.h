@@ -47,7 +47,9 @@ constexpr int NCON = 8;        // 2 feet x 4 box corners (mjc_PlaneBox returns a
 constexpr int NEDGE = 32;      // pyramidal condim 3: 4 edges per contact
 constexpr int NREW = 10;
 constexpr int MAXPERIOD = 96;
-constexpr int NSTATE_I = 8;    // int32 words per env in the integer state record
+constexpr int NSTATE_I = 8;
+constexpr int MAXCAP = 8;       // self-collision capsule proxies
+constexpr int MAXPAIR = 16;    // int32 words per env in the integer state record
 
 enum { STANDING = 0, INPLACE = 1, FORWARD = 2 };
 
@@ -113,6 +115,9 @@ template <class real, int NJ> struct Model {
   real head[3], fcap, goal_height;
   real clock[4][MAXPERIOD];  // r_frc r_vel l_frc l_vel
   int max_iter, frame_skip, period, any_damping;
+  int ncap, npair, cap_link[MAXCAP];
+  real cap_p0[MAXCAP][3], cap_p1[MAXCAP][3], cap_r[MAXCAP];
+  unsigned char pair_a[MAXPAIR], pair_b[MAXPAIR];
   int axis_id[NL];  // 0/1/2: hinge axis is +e_x/+e_y/+e_z of the link frame AND link_rot is the identity (fast FK path); -1: general
 };
 
@@ -175,7 +180,7 @@ template <class real, int NJ> struct Work {
   // ---- what mj_step leaves behind (pre-integration state of the last substep)
   real root_vlin[3], foot_vel[2][3], grf[2], cz_min, qacc_lag[3];
   real rew[NREW], obs[NOBS];
-  int iters_total;
+  int iters_total, selfcol;
 };
 
 // ---------------------------------------------------------------- small vector helpers
@@ -246,6 +251,33 @@ template <class real> LHW_DEV real impedance(const real* solimp, real dist) {
   } else if (x <= mid) y = m_pow(x / mid, power) * mid;
   else y = 1 - m_pow((1 - x) / (1 - mid), power) * (1 - mid);
   return d0 + y * (dw - d0);
+}
+
+// squared distance between the segments p1-q1 and p2-q2 (closest points by clamping)
+template <class real> LHW_DEV real seg_seg_dist2(const real* p1, const real* q1, const real* p2, const real* q2) {
+  real d1[3], d2[3], r[3];
+#pragma unroll
+  for (int x = 0; x < 3; x++) { d1[x] = q1[x] - p1[x]; d2[x] = q2[x] - p2[x]; r[x] = p1[x] - p2[x]; }
+  const real a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), EPS = (real)1e-12;
+  real s, t;
+  if (a <= EPS && e <= EPS) { s = t = 0; }
+  else if (a <= EPS) { s = 0; t = m_min(m_max(f / e, (real)0), (real)1); }
+  else {
+    const real c = dot3(d1, r);
+    if (e <= EPS) { t = 0; s = m_min(m_max(-c / a, (real)0), (real)1); }
+    else {
+      const real b = dot3(d1, d2), den = a * e - b * b;
+      s = den > EPS ? (b * f - c * e) / den : (real)0;
+      s = m_min(m_max(s, (real)0), (real)1);
+      t = (b * s + f) / e;
+      if (t < 0) { t = 0; s = m_min(m_max(-c / a, (real)0), (real)1); }
+      else if (t > 1) { t = 1; s = m_min(m_max((b - c) / a, (real)0), (real)1); }
+    }
+  }
+  real dd = 0;
+#pragma unroll
+  for (int x = 0; x < 3; x++) { const real w_ = r[x] + d1[x] * s - d2[x] * t; dd += w_ * w_; }
+  return dd;
 }
 
 // ================================================================= H x = b : arrow Cholesky with the forward
@@ -967,8 +999,35 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
     }
     // rhs of the implicit-damping solve: qfrc_smooth + J' f = M a - grad
     if (l < NV) w.vec[l] = w.Ma[l] - w.grad[l];
+    if (last) {
+      // self-collision proxies: capsule end points (rel. o) into the T scratch (dead after the Hessian build)
+      if (l >= 22 && l < 22 + m.ncap) {
+        const int c = l - 22, lk = m.cap_link[c];
+        real* E = &w.T[0][0][0] + 6 * c;
+        real t[3];
+        mv3(w.xmat[lk], m.cap_p0[c], t);
+#pragma unroll
+        for (int x = 0; x < 3; x++) E[x] = w.xr[lk][x] + t[x];
+        mv3(w.xmat[lk], m.cap_p1[c], t);
+#pragma unroll
+        for (int x = 0; x < 3; x++) E[3 + x] = w.xr[lk][x] + t[x];
+      }
+      if (l == 31) w.selfcol = 0;
+    }
   }
   LHW_SYNC();
+  if (last && m.npair > 0) {
+    LHW_LANES(l) {
+      if (l < m.npair) {
+        const int a = m.pair_a[l], b = m.pair_b[l];
+        const real* Ea = &w.T[0][0][0] + 6 * a;
+        const real* Eb = &w.T[0][0][0] + 6 * b;
+        const real rr = m.cap_r[a] + m.cap_r[b];
+        if (seg_seg_dist2(Ea, Ea + 3, Eb, Eb + 3) < rr * rr) w.selfcol = 1;
+      }
+    }
+    LHW_SYNC();
+  }
   // ---------------- P12 mj_Euler: (M + h diag(damping)) a' = qfrc_smooth + qfrc_constraint ; integrate
   if (m.any_damping) {
     LHW_LANES(l) {
@@ -1039,6 +1098,7 @@ LHW_DEV void load_state(Work<real, NJ>& w, const real* sr, const int32_t* si, ui
       w.rng_ctr = (uint32_t)si[4]; w.have_prev = si[5]; w.status = si[6];
       w.env_id = env_id;
       w.iters_total = 0;
+      w.selfcol = 0;
     }
   }
   LHW_SYNC();
@@ -1239,7 +1299,7 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
   env_obs<real, NJ>(w, m);
   real total = 0;
   for (int i = 0; i < NREW; i++) total += w.rew[i];
-  const int done = (w.qpos[2] < (real)0.6) || (w.qpos[2] > (real)1.4) || (w.status != 0);
+  const int done = (w.qpos[2] < (real)0.6) || (w.qpos[2] > (real)1.4) || (w.selfcol != 0) || (w.status != 0);
   const int ended = done || (w.traj_len + 1 >= max_traj_len);
   LHW_SYNC();
   LHW_LANES(l) {

@@ -19,7 +19,8 @@ def load_model(name: str = "jvrc_walk") -> dict:
         return json.load(f)
 
 
-def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = None, kp=None, kd=None) -> np.ndarray:
+def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = None, kp=None, kd=None,
+               self_collision: bool = True) -> np.ndarray:
     links = mj["links"]
     nl = len(links)
     assert (nl - 1) % 2 == 0, "expected a free root + two equal serial chains"
@@ -67,4 +68,14 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
                                       total_duration=t["total_duration"])
     b += [mj["total_mass"], t["goal_height"], period]
     b += list(table.reshape(-1))
+    # self-collision capsule proxies (termination flag; tools/fit_collision_proxies.py)
+    sc = mj.get("self_collision") if self_collision else None
+    caps = sc["capsules"] if sc else []
+    b.append(len(caps))
+    for c in caps:
+        b += [c["link"]] + list(c["p0"]) + list(c["p1"]) + [c["radius"]]
+    pairs = sc["pairs"] if sc else []
+    b.append(len(pairs))
+    for a_, b_ in pairs:
+        b += [a_, b_]
     return np.asarray(b, dtype=np.float64)

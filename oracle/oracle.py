@@ -36,7 +36,8 @@ def load_clocks() -> dict:
     return json.load(open(os.path.join(ROOT, "tests", "golden", "gait_clocks.json")))
 
 
-def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: int = 0, iterations: int | None = None):
+def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: int = 0, iterations: int | None = None,
+               self_collision: bool = True):
     """Flat double layout consumed by orc_model_from_flat (keep in sync with sim_oracle.c)."""
     b: list[float] = []
     links = mj["links"]
@@ -79,6 +80,15 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
     b += [mj["total_mass"], c["task"]["goal_height"], clocks["period"]]
     for k in ("r_frc", "r_vel", "l_frc", "l_vel"):
         b += clocks[k]
+    sc = mj.get("self_collision") if self_collision else None
+    caps = sc["capsules"] if sc else []
+    b.append(len(caps))
+    for c in caps:
+        b += [c["link"]] + c["p0"] + c["p1"] + [c["radius"]]
+    pairs = sc["pairs"] if sc else []
+    b.append(len(pairs))
+    for a_, b_ in pairs:
+        b += [a_, b_]
     return np.array(b, dtype=np.float64)
 
 

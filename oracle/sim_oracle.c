@@ -143,6 +143,17 @@ int orc_model_from_flat(orc_model* m, const double* b, int n) {
   if (m->period > ORC_MAXPERIOD) return -4;
   for (int c = 0; c < 4; c++)
     for (int k = 0; k < m->period; k++) m->clock[c][k] = RD();
+  m->ncap = (int)RD();
+  if (m->ncap > ORC_MAXCAP) return -5;
+  for (int c = 0; c < m->ncap; c++) {
+    m->cap_link[c] = (int)RD();
+    for (int k = 0; k < 3; k++) m->cap_p0[c][k] = RD();
+    for (int k = 0; k < 3; k++) m->cap_p1[c][k] = RD();
+    m->cap_r[c] = RD();
+  }
+  m->npair = (int)RD();
+  if (m->npair > ORC_MAXPAIR) return -6;
+  for (int c = 0; c < m->npair; c++) { m->pair[c][0] = (int)RD(); m->pair[c][1] = (int)RD(); }
 #undef RD
   return p == n ? 0 : -100 - (p > n);
 }
@@ -586,6 +597,49 @@ static int solve_pgs(const orc_model* m, const double* M, const efc_t* e, const 
   return it;
 }
 
+/* squared distance between segments p1-q1 and p2-q2 (closest points by clamping, textbook formulation) */
+static double seg_seg_dist2(const double* p1, const double* q1, const double* p2, const double* q2) {
+  double d1[3], d2[3], r[3];
+  for (int x = 0; x < 3; x++) { d1[x] = q1[x] - p1[x]; d2[x] = q2[x] - p2[x]; r[x] = p1[x] - p2[x]; }
+  double a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), s, t;
+  const double EPS = 1e-12;
+  if (a <= EPS && e <= EPS) { s = t = 0; }
+  else if (a <= EPS) { s = 0; t = f / e; t = t < 0 ? 0 : (t > 1 ? 1 : t); }
+  else {
+    double c = dot3(d1, r);
+    if (e <= EPS) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+    else {
+      double b = dot3(d1, d2), den = a * e - b * b;
+      s = den > EPS ? (b * f - c * e) / den : 0.0;
+      s = s < 0 ? 0 : (s > 1 ? 1 : s);
+      t = (b * s + f) / e;
+      if (t < 0) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+      else if (t > 1) { t = 1; s = (b - c) / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+    }
+  }
+  double dd = 0;
+  for (int x = 0; x < 3; x++) { double w_ = r[x] + d1[x] * s - d2[x] * t; dd += w_ * w_; }
+  return dd;
+}
+
+static int self_collision(const orc_model* m, const kin_t* k) {
+  double e0[ORC_MAXCAP][3], e1[ORC_MAXCAP][3];
+  for (int c = 0; c < m->ncap; c++) {
+    int lk = m->cap_link[c];
+    double t[3];
+    matvec3(k->xmat[lk], m->cap_p0[c], t);
+    for (int x = 0; x < 3; x++) e0[c][x] = k->xpos[lk][x] + t[x];
+    matvec3(k->xmat[lk], m->cap_p1[c], t);
+    for (int x = 0; x < 3; x++) e1[c][x] = k->xpos[lk][x] + t[x];
+  }
+  for (int p = 0; p < m->npair; p++) {
+    int a = m->pair[p][0], b = m->pair[p][1];
+    double rr = m->cap_r[a] + m->cap_r[b];
+    if (seg_seg_dist2(e0[a], e1[a], e0[b], e1[b]) < rr * rr) return 1;
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------ mj_step */
 void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
   int nv = m->nv, nu = m->nu;
@@ -642,7 +696,7 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
   e->ncon_r = e->ncon_l = 0;
   e->ncon = efc.ncon;
   e->contact_z_min = 0;
-  e->self_collision = 0;
+  e->self_collision = self_collision(m, &k);
   int first = 1;
   for (int ci = 0; ci < efc.ncon; ci++) {
     const double* f = force + efc.con_row[ci];

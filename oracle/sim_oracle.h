@@ -34,6 +34,8 @@ extern "C" {
 #define ORC_MAXPERIOD 128
 #define ORC_NOBS 37
 #define ORC_NREW 10
+#define ORC_MAXCAP 8
+#define ORC_MAXPAIR 16
 
 enum { ORC_STANDING = 0, ORC_INPLACE = 1, ORC_FORWARD = 2 };
 enum { ORC_SOLVER_NEWTON = 0, ORC_SOLVER_PGS = 1 };
@@ -69,7 +71,12 @@ typedef struct {
   double head_in_root[3];
   double total_mass, goal_height;
   int period;
-  double clock[4][ORC_MAXPERIOD];  /* r_frc, r_vel, l_frc, l_vel at integer phases */
+  double clock[4][ORC_MAXPERIOD];
+  /* self-collision proxies (capsules on the leg hulls / feet; termination only, robot_interface.py:472-484) */
+  int ncap, npair;
+  int cap_link[ORC_MAXCAP];
+  double cap_p0[ORC_MAXCAP][3], cap_p1[ORC_MAXCAP][3], cap_r[ORC_MAXCAP];
+  int pair[ORC_MAXPAIR][2];  /* r_frc, r_vel, l_frc, l_vel at integer phases */
 } orc_model;
 
 typedef struct {

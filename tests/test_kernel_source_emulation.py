@@ -68,3 +68,33 @@ def test_fp32_kernel_source_stays_close_for_a_short_horizon(oracle_tight):
         eo, _, _, er, ed, een, _, _ = e.step(a)
         assert (ee == een).all()
         assert np.abs(oo - eo).max() < 2e-3 and np.abs(rr - er).max() < 2e-3
+
+
+def test_self_collision_proxies_terminate_when_legs_cross(oracle_tight):
+    """reference row S7 (check_self_collisions): capsule proxies flag leg-leg contact; oracle and kernel agree."""
+    o = oracle_tight
+    mj = load_model()
+    assert len(mj["self_collision"]["capsules"]) == 8 and len(mj["self_collision"]["pairs"]) == 16
+    e = Emu(pack_model(mj, tolerance=1e-14), 64, 1, seed=2)
+    envs = o.make_envs(1, seed=2)
+    o.reset(envs)
+    e.reset()
+    # nominal stance: no self collision, episode continues
+    _, _, d0, _ = o.step(envs, 0, np.zeros(12))
+    out = e.step(np.zeros((1, 12)), autoreset=0)
+    assert not d0 and not out[4][0]
+    # swing the right hip inwards (roll) hard: thighs / shanks cross -> both must terminate on the same step
+    a = np.zeros(12)
+    a[1] = 1.2    # R_HIP_R target +1.2 rad on top of nominal (towards the left leg)
+    a[7] = -1.2   # L_HIP_R mirrored
+    hit = None
+    for k in range(30):
+        _, _, d_o, _ = o.step(envs, 0, a)
+        out = e.step(a[None], autoreset=0)
+        assert bool(out[4][0]) == d_o, k
+        if d_o:
+            hit = k
+            sc = int(o.field(envs, 0, "self_collision")[0])
+            z = o.field(envs, 0, "qpos")[2]
+            break
+    assert hit is not None and sc == 1 and 0.6 < z < 1.4, (hit, sc, z)
