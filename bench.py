@@ -82,13 +82,35 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def effective_cpus() -> int:
+    """Host cores this process may really use: affinity mask capped by the cgroup CPU quota (the GPU boxes expose 128
+    logical CPUs but a container quota of 16)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(round(int(q) / int(per)))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(round(q / per))))
+        except Exception:
+            pass
+    return n
+
+
 def cpu_reference(n_envs: int, seconds: float, warmup: int, seed: int, nthreads: int = 0):
     """The oracle (CPU port of the reference path) on the host cores, run for about `seconds` of wall time
     (a bounded sample of the same workload): env-steps/s, threads used, elapsed, control steps done."""
     import numpy as np
     from oracle.oracle import Oracle
     o = Oracle()
-    nthreads = nthreads or (os.cpu_count() or 1)
+    nthreads = nthreads or effective_cpus()
     envs = o.make_envs(n_envs, seed=seed)
     o.batch_reset(envs, n_envs, nthreads)
     rng = np.random.RandomState(seed)
@@ -130,7 +152,7 @@ def main():
         # this arm times the CPU port (oracle/) on all host cores, rank 0 only.
         if rank != 0:
             return
-        ncores = os.cpu_count() or 1
+        ncores = effective_cpus()
         n_sample = max(256, min(args.envs * world, 64 * ncores))
         sps, threads, dt, steps_ref = cpu_reference(n_sample, 15.0, 2, args.seed)
         print(json.dumps({"metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
@@ -138,6 +160,7 @@ def main():
                           "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
                           "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
                                            "sample": f"{n_sample} envs x {steps_ref} control steps ({dt:.1f} s) after 2 warm-up steps, OpenMP over envs; "
+                                                     f"threads = cgroup CPU quota ({threads} of {os.cpu_count()} logical CPUs); "
                                                      "reference Ray+MuJoCo path not runnable on this box (mujoco/ray not installable)"},
                           "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -267,7 +290,7 @@ def main():
                                     "see DESIGN.md for the FP-issue bound reported beside this"}}
         out["extras"] = extras
         if not args.no_cpu_baseline and world == 1:
-            ncores = os.cpu_count() or 1
+            ncores = effective_cpus()
             n_cpu = max(256, min(n, 64 * ncores))
             sps, threads, dt, nst = cpu_reference(n_cpu, 10.0, 2, args.seed)
             out["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
