@@ -96,6 +96,26 @@ int lhw_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_av
                   long long n, int step, float lr, float beta1, float beta2, float eps, float max_norm,
                   float grad_scale, void* stream);
 
+/* ---- multi-GPU exchange step, fused (csrc/comm_kernels.cu) ------------------------------------------
+ * Replaces, on N > 1 GPUs, the sequence of rl/algos/ppo.py:389-396: (gradient all-reduce) -> clip_grad_norm_(actor),
+ * clip_grad_norm_(critic) -> actor Adam.step, critic Adam.step, by ONE cooperative kernel that reads the peers'
+ * flat gradients over NVLink peer memory (CUDA IPC), sums them in fixed rank order, and applies clip + Adam.
+ * lhw_comm owns a cudaMalloc'ed IPC-exported gradient buffer of n_floats floats (lhw_comm_grad_ptr) — the host
+ * makes the modules' .grad tensors views of it. Handles are exchanged by the host (torch.distributed
+ * all_gather of lhw_comm_handle_size() bytes per rank) and mapped with lhw_comm_import.
+ * n_actor: the first n_actor floats belong to the actor (own norm / clip), the rest to the critic. */
+typedef struct lhw_comm lhw_comm;
+const char* lhw_comm_last_error(void);
+int lhw_comm_handle_size(void);
+int lhw_comm_create(lhw_comm** out, long long n_floats, int rank, int world, int device);
+void* lhw_comm_grad_ptr(lhw_comm* comm);
+int lhw_comm_export(lhw_comm* comm, void* handle_blob_host);
+int lhw_comm_import(lhw_comm* comm, const void* all_handle_blobs_host);
+int lhw_comm_destroy(lhw_comm* comm);
+int lhw_fused_allreduce_clip_adam(lhw_comm* comm, float* param, float* exp_avg, float* exp_avg_sq, long long n_actor,
+                                  long long n_total, int step, float lr, float beta1, float beta2, float eps, float max_norm,
+                                  float* norms_out_host_or_null, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,15 @@ SIGNATURES = {
     "lhw_adv_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_float, c_void_p]),
     "lhw_gather_minibatch": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p]),
     "lhw_grad_sumsq": (c_int, [c_void_p, c_void_p, c_ll, c_float, c_void_p]),
+    "lhw_comm_last_error": (ctypes.c_char_p, []),
+    "lhw_comm_handle_size": (c_int, []),
+    "lhw_comm_create": (c_int, [ctypes.POINTER(c_void_p), c_ll, c_int, c_int, c_int]),
+    "lhw_comm_grad_ptr": (c_void_p, [c_void_p]),
+    "lhw_comm_export": (c_int, [c_void_p, c_void_p]),
+    "lhw_comm_import": (c_int, [c_void_p, c_void_p]),
+    "lhw_comm_destroy": (c_int, [c_void_p]),
+    "lhw_fused_allreduce_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_int, c_float, c_float,
+                                              c_float, c_float, c_float, c_void_p, c_void_p]),
     "lhw_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_float,
                               c_float, c_float, c_float, c_void_p]),
 }

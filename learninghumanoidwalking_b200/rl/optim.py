@@ -28,14 +28,16 @@ def flatten_module_(module: torch.nn.Module):
     return flat, grad
 
 
-def flatten_modules_(modules):
-    """Several modules in ONE pair of flat buffers (one NCCL all-reduce covers all of them).
-    Returns flat, grad, [(start, end) per module]."""
+def flatten_modules_(modules, grad_buffer=None):
+    """Several modules in ONE pair of flat buffers (one all-reduce covers all of them).  `grad_buffer`: use this
+    (e.g. peer-visible IPC) tensor for the gradients.  Returns flat, grad, [(start, end) per module]."""
     params = [[p for p in m.parameters()] for m in modules]
     n = sum(p.numel() for ps in params for p in ps)
     dev = params[0][0].device
     flat = torch.zeros(n, dtype=torch.float32, device=dev)
-    grad = torch.zeros(n, dtype=torch.float32, device=dev)
+    grad = torch.zeros(n, dtype=torch.float32, device=dev) if grad_buffer is None else grad_buffer
+    assert grad.numel() == n and grad.dtype == torch.float32
+    grad.zero_()
     off, segs = 0, []
     for ps in params:
         start = off
@@ -56,9 +58,12 @@ class FusedClipAdam(torch.optim.Optimizer):
         if not params or not params[0].is_cuda:
             raise _lib.LhwError("FusedClipAdam needs CUDA parameters (no CPU fallback)")
         super().__init__(params, dict(lr=lr, eps=eps, betas=betas, max_norm=max_norm))
-        self.flat, self.grad = views if views is not None else flatten_module_(module)
-        self.exp_avg = torch.zeros_like(self.flat)
-        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.flat, self.grad = views[:2] if views is not None else flatten_module_(module)
+        if views is not None and len(views) == 4:
+            self.exp_avg, self.exp_avg_sq = views[2], views[3]
+        else:
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
         self.norm = torch.zeros(1, dtype=torch.float32, device=self.flat.device)
         self.step_count = 0
         self.process_group = process_group

@@ -79,6 +79,7 @@ class PPO:
         self.workers = [DeviceRolloutWorker(env, self.policy, self.critic, seed=wseed, worker_id=self.rank)]
         self.batch_size = env.num_envs * self.steps_per_env
         self.actor_optimizer = self.critic_optimizer = None
+        self._comm = None
         L = _lib.lib()
         self._adv_stats = torch.zeros(L.lhw_adv_stats_words(), dtype=torch.float64, device=self.device)
         self._mb = None
@@ -118,22 +119,43 @@ class PPO:
         self.actor_optimizer.zero_grad()
         self.critic_optimizer.zero_grad()
         total_loss.backward()
-        if self.world > 1:  # the one exchange step of the path: flat (actor+critic) gradient over NVLink
-            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
-        # clip_grad_norm_ x2 + Adam.step x2 (rl/algos/ppo.py:393-396), norms of the (averaged) global gradient
-        self.actor_optimizer.step()
-        self.critic_optimizer.step()
+        a_opt, c_opt = self.actor_optimizer, self.critic_optimizer
+        if self._comm is not None and isinstance(a_opt, FusedClipAdam) and isinstance(c_opt, FusedClipAdam):
+            # the one exchange step of the path, fused: peer-memory all-reduce + 2x clip_grad_norm_ + 2x Adam in ONE launch
+            a_opt.step_count += 1
+            c_opt.step_count += 1
+            g = a_opt.param_groups[0]
+            self._comm.fused_step(self._flat_param, self._flat_m, self._flat_v, self._n_actor, a_opt.step_count, g["lr"],
+                                  g["betas"], g["eps"], g["max_norm"])
+        elif isinstance(a_opt, FusedClipAdam) and isinstance(c_opt, FusedClipAdam):
+            if self.world > 1:  # baseline path: NCCL all-reduce of the flat gradient, then clip+Adam launches
+                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
+            a_opt.step()
+            c_opt.step()
+        else:  # hand-made torch optimisers (tests/test_training.py:140-141): the reference's own sequence
+            torch.nn.utils.clip_grad_norm_(self.policy.parameters(), self.grad_clip)
+            torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.grad_clip)
+            a_opt.step()
+            c_opt.step()
         return (actor_loss, entropy_penalty, critic_loss, approx_kl_div, mirror_loss, imitation_loss, clip_fraction)
 
     def make_optimizers(self):
         """Adam(lr, eps) for actor and critic (rl/algos/ppo.py:429-430) as fused clip+Adam over one flat buffer."""
+        import os
+        from .comm import PeerComm
         from .optim import flatten_modules_
-        flat, grad, segs = flatten_modules_([self.policy, self.critic])
+        n_total = sum(p.numel() for m in (self.policy, self.critic) for p in m.parameters())
+        fused = os.environ.get("LHW_FUSED_EXCHANGE", "1") != "0"
+        self._comm = PeerComm(n_total, self.device) if fused else None
+        flat, grad, segs = flatten_modules_([self.policy, self.critic], None if self._comm is None else self._comm.grad)
         self._flat_param, self._flat_grad = flat, grad
+        self._flat_m, self._flat_v = torch.zeros_like(flat), torch.zeros_like(flat)
+        self._n_actor = segs[0][1]
+        sl = lambda t, k: t[segs[k][0]:segs[k][1]]
         self.actor_optimizer = FusedClipAdam(self.policy, lr=self.lr, eps=self.eps, max_norm=self.grad_clip,
-                                             views=(flat[segs[0][0]:segs[0][1]], grad[segs[0][0]:segs[0][1]]))
+                                             views=(sl(flat, 0), sl(grad, 0), sl(self._flat_m, 0), sl(self._flat_v, 0)))
         self.critic_optimizer = FusedClipAdam(self.critic, lr=self.lr, eps=self.eps, max_norm=self.grad_clip,
-                                              views=(flat[segs[1][0]:segs[1][1]], grad[segs[1][0]:segs[1][1]]))
+                                              views=(sl(flat, 1), sl(grad, 1), sl(self._flat_m, 1), sl(self._flat_v, 1)))
         self.actor_optimizer.world = self.critic_optimizer.world = self.world
         # old_policy must not alias the flat buffer
         self.old_policy = deepcopy(self.policy)

@@ -193,3 +193,26 @@ def test_same_seed_gives_bit_identical_weights():
         finals.append(ppo._flat_param.clone())
         ppo.env.close()
     assert torch.equal(finals[0], finals[1])
+
+
+def test_fused_exchange_kernel_single_rank_matches_oracle_clip_adam():
+    """lhw_fused_allreduce_clip_adam at world = 1: one launch = clip_grad_norm_ x2 + Adam x2 (rl/algos/ppo.py:393-396)."""
+    from learninghumanoidwalking_b200.rl.comm import PeerComm
+    from oracle.ppo_oracle import clip_adam
+    dev = torch.device("cuda", 0)
+    n_a, n = 1000, 1700
+    comm = PeerComm(n, dev)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    p = torch.randn(n, device="cuda", generator=g)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pa, ma, va = p[:n_a].double().cpu().numpy(), np.zeros(n_a), np.zeros(n_a)
+    pc, mc, vc = p[n_a:].double().cpu().numpy(), np.zeros(n - n_a), np.zeros(n - n_a)
+    for step in range(1, 4):
+        comm.grad.copy_(torch.randn(n, device="cuda", generator=g) * (0.3 if step == 2 else 0.001))   # clipped and unclipped cases
+        gnp = comm.grad.double().cpu().numpy()
+        norms = comm.fused_step(p, m, v, n_a, step, 3e-4, (0.9, 0.999), 1e-5, 0.05, want_norms=True)
+        pa, ma, va, na = clip_adam(pa, gnp[:n_a], ma, va, step, 3e-4, 1e-5, 0.05)
+        pc, mc, vc, nc = clip_adam(pc, gnp[n_a:], mc, vc, step, 3e-4, 1e-5, 0.05)
+        assert abs(norms[0] - na) < 1e-5 * max(1, na) and abs(norms[1] - nc) < 1e-5 * max(1, nc)
+        assert np.abs(p[:n_a].double().cpu().numpy() - pa).max() < 2e-6 and np.abs(p[n_a:].double().cpu().numpy() - pc).max() < 2e-6
+    comm.close()

@@ -41,8 +41,10 @@ def main():
     dist.all_gather(obs_all, obs0)
     differ = world == 1 or not torch.equal(obs_all[0], obs_all[-1])
     if rank == 0:
-        print(f"DIST_CHECK world={world} envs/rank={n} identical_weights={same} ranks_simulate_different_envs={differ} "
-              f"critic_loss={log[-1]['critic_loss']:.4f} fps={log[-1]['fps']:.0f}")
+        fused = ppo._comm is not None
+        print(f"DIST_CHECK world={world} envs/rank={n} fused_exchange={fused} identical_weights={same} "
+              f"ranks_simulate_different_envs={differ} critic_loss={log[-1]['critic_loss']:.4f} fps={log[-1]['fps']:.0f} "
+              f"wsum={flat.double().sum().item():.10f} wabs={flat.double().abs().sum().item():.10f}")
     dist.destroy_process_group()
     if not (same and differ):
         sys.exit(1)
