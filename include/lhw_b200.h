@@ -59,6 +59,10 @@ int lhw_sim_step(lhw_sim* sim, void* state_r, int32_t* state_i, int n_envs, uint
                  const void* actions, int max_traj_len, int autoreset, void* obs, void* term_obs, void* reward,
                  void* rew_terms, int32_t* done, int32_t* ended, int32_t* ep_len, void* ep_rew, void* stream);
 
+/* lhw_sim_bind: make `sim`'s model constants the resident ones (they live in one __constant__ bank per precision,
+ * shared by all sims of the process; lhw_sim_step/reset do this implicitly, a replayed CUDA graph cannot). */
+int lhw_sim_bind(lhw_sim* sim, void* stream);
+
 /* number of kernels this library has launched since load (the bench's gpu_launches claim) */
 long long lhw_launch_count(void);
 

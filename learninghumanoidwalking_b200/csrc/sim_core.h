@@ -226,7 +226,10 @@ LHW_DEV float m_rsqrt(float x) {
 }
 LHW_DEV double m_rsqrt(double x) {
 #if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
-  return rsqrt(x);
+  // single-precision seed (MUFU.RSQ) + one Newton step in double: relative error ~1.5 * (6e-8)^2 = 5e-15, a third of
+  // the dependent-instruction chain of the library rsqrt(double); pivots and quaternion norms are far inside float range
+  double y = (double)rsqrtf((float)x);
+  return y * (1.5 - 0.5 * x * y * y);
 #else
   return 1.0 / sqrt(x);
 #endif

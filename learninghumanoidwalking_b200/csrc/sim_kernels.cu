@@ -178,6 +178,11 @@ int lhw_sim_obs_dim(const lhw_sim*) { return Work<double, NJ_JVRC>::NOBS; }
 int lhw_sim_act_dim(const lhw_sim*) { return 2 * NJ_JVRC; }
 int lhw_sim_smem_bytes_per_env(const lhw_sim* s) { return (int)s->work_bytes; }
 
+int lhw_sim_bind(lhw_sim* s, void* stream) {
+  if (!s) return fail(-1, "null argument");
+  return upload_model(s, (cudaStream_t)stream);
+}
+
 int lhw_sim_reset(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint32_t seed, uint32_t first_env_id,
                   const int32_t* mask, int fresh, void* obs, void* stream) {
   if (!s || !state_r || !state_i) return fail(-1, "null argument");

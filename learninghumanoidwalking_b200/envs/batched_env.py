@@ -103,6 +103,12 @@ class BatchedHumanoidEnv:
                        "lhw_sim_step")
         return self.obs, self.reward, self.done, self.ended
 
+    def bind(self):
+        """Upload this env's model constants if another env of the same precision used the constant bank last
+        (needed before replaying CUDA graphs that contain lhw_sim_step launches)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().lhw_sim_bind(self._h, _lib.current_stream_ptr()), "lhw_sim_bind")
+
     # ------------------------------------------------------------------ host API (numpy in / out, copies inside)
     def step_host(self, actions: np.ndarray, autoreset: bool = True):
         """Reference-facing batched call with HOST buffers: H2D actions, one launch, D2H obs/reward/done."""

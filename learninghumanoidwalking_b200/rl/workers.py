@@ -25,6 +25,7 @@ class DeviceRolloutWorker:
         self.gen.manual_seed(0 if seed is None else int(seed))
         self.current_state = None      # [N, obs_dim] float32; None before the first reset
         self._buf = None
+        self._graphs = {}
         self.total_steps = 0
 
     def sync_state(self, policy_state_dict=None, critic_state_dict=None, obs_mean=None, obs_std=None, iteration_count=0):
@@ -40,39 +41,73 @@ class DeviceRolloutWorker:
             self.policy.obs_std = self.critic.obs_std = obs_std
         self.env.robot.iteration_count = iteration_count
 
+    # ------------------------------------------------------------------ one control step of the rollout loop
+    def _step_body(self, buf, state, noise, t_idx, deterministic):
+        """policy -> action -> critic -> env.step -> bootstrap -> buffer writes, all on device tensors; `t_idx` is a
+        1-element device index so the same code can be replayed from a CUDA graph (no host-side loop counter)."""
+        env = self.env
+        mu = self.policy(state, deterministic=True)
+        action = mu if deterministic else mu + self.policy.stds * noise.index_select(0, t_idx)[0]
+        buf.states.index_copy_(0, t_idx, state.unsqueeze(0))
+        buf.actions.index_copy_(0, t_idx, action.unsqueeze(0))
+        buf.values.index_copy_(0, t_idx, self.critic(state).squeeze(-1).unsqueeze(0))
+        obs, reward, done, ended = env.step(action if env.dtype == torch.float32 else action.double())
+        buf.rewards.index_copy_(0, t_idx, reward.float().unsqueeze(0))
+        buf.ended.index_copy_(0, t_idx, ended.unsqueeze(0))
+        buf.ep_len.index_copy_(0, t_idx, env.ep_len.unsqueeze(0))
+        buf.ep_rew.index_copy_(0, t_idx, env.ep_rew.float().unsqueeze(0))
+        # truncation bootstrap: (not done) * critic(pre-reset next_state) where the episode ended
+        v_term = self.critic(env.term_obs.float()).squeeze(-1)
+        buf.boot.index_copy_(0, t_idx, torch.where((ended != 0) & (done == 0), v_term, torch.zeros_like(v_term)).unsqueeze(0))
+        state.copy_(obs.float())
+        t_idx.add_(1)
+
     @torch.no_grad()
     def sample(self, gamma, lam, max_steps, max_traj_len, deterministic=False, env_major=True) -> BatchData:
+        import os
         env = self.env
         N, T = env.num_envs, int(max_steps)
         env.max_traj_len = int(max_traj_len)
         if self._buf is None or self._buf.T != T or self._buf.N != N:
             self._buf = DeviceRolloutBuffer(T, N, env.obs_dim, env.act_dim, self.device, gamma, lam)
+            self._graphs = {}
         buf = self._buf
         buf.gamma, buf.lam = gamma, lam
         if self.current_state is None:
             self.current_state = env.reset().float().clone()
-        state = self.current_state
-        std = self.policy.stds
-        for t in range(T):
-            mu = self.policy(state, deterministic=True)
-            if deterministic:
-                action = mu
-            else:
-                action = mu + std * torch.randn(mu.shape, device=self.device, generator=self.gen)
-            buf.states[t] = state
-            buf.actions[t] = action
-            buf.values[t] = self.critic(state).squeeze(-1)
-            obs, reward, done, ended = env.step(action if env.dtype == torch.float32 else action.double())
-            buf.rewards[t] = reward
-            buf.ended[t] = ended
-            buf.ep_len[t] = env.ep_len
-            buf.ep_rew[t] = env.ep_rew
-            # truncation bootstrap: (not done) * critic(pre-reset next_state) where the episode ended
-            v_term = self.critic(env.term_obs.float()).squeeze(-1)
-            buf.boot[t] = torch.where((ended != 0) & (done == 0), v_term, torch.zeros_like(v_term))
-            state = obs.float().clone()
+            self._t_idx = torch.zeros(1, dtype=torch.long, device=self.device)
+            self._noise = torch.zeros(T, N, env.act_dim, device=self.device)
+        if self._noise.shape[0] != T:
+            self._noise = torch.zeros(T, N, env.act_dim, device=self.device)
+        state, t_idx, noise = self.current_state, self._t_idx, self._noise
+        t_idx.zero_()
+        if not deterministic:
+            noise.copy_(torch.randn(noise.shape, device=self.device, generator=self.gen))
+        use_graph = os.environ.get("LHW_ROLLOUT_GRAPH", "1") != "0"
+        if use_graph:
+            key = (bool(deterministic), env.max_traj_len)
+            g = self._graphs.get(key)
+            first = 0
+            if g is None:
+                # warm-up on a side stream (cuBLAS workspaces, constant-memory upload), then capture ONE control step
+                s = torch.cuda.Stream(device=self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    self._step_body(buf, state, noise, t_idx, deterministic)
+                torch.cuda.current_stream(self.device).wait_stream(s)
+                first = 1
+                if T > 1:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._step_body(buf, state, noise, t_idx, deterministic)
+                    self._graphs[key] = g   # capturing does not execute: warm-up did step 0, replays do the rest
+            env.bind()   # make sure THIS env's model constants are the resident ones before replaying launches
+            for _ in range(first, T):
+                g.replay()
+        else:
+            for _ in range(T):
+                self._step_body(buf, state, noise, t_idx, deterministic)
         buf.last_val.copy_(self.critic(state).squeeze(-1))
         buf.finish()
-        self.current_state = state
         self.total_steps += T * N
         return buf.get_data(env_major=env_major)

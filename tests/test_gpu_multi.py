@@ -18,11 +18,14 @@ def test_two_rank_nccl_ppo_replicas_stay_identical():
     import re
     sums = {}
     for fused in ("1", "0"):
-        env = dict(os.environ, LHW_FUSED_EXCHANGE=fused)
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-        assert "identical_weights=True" in out.stdout and "ranks_simulate_different_envs=True" in out.stdout
-        assert f"fused_exchange={fused == '1'}" in out.stdout
-        sums[fused] = [float(x) for x in re.search(r"wsum=(\S+) wabs=(\S+)", out.stdout).groups()]
-    # the fused NVLink kernel and the NCCL + clip/Adam baseline train to the same weights (2 ranks: a+b is order-free)
-    assert abs(sums["1"][0] - sums["0"][0]) < 1e-3 and abs(sums["1"][1] - sums["0"][1]) < 1e-2 * 1e-2 * sums["0"][1] + 1e-3, sums
+        for one_step in ("0", "1"):
+            env = dict(os.environ, LHW_FUSED_EXCHANGE=fused, LHW_CHECK_ONE_STEP=one_step)
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+            assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+            assert "identical_weights=True" in out.stdout and "ranks_simulate_different_envs=True" in out.stdout
+            assert f"fused_exchange={fused == '1'}" in out.stdout
+            if one_step == "1":
+                sums[fused] = [float(x) for x in re.search(r"wsum=(\S+) wabs=(\S+)", out.stdout).groups()]
+    # after ONE optimiser step on identical data the fused NVLink kernel and the NCCL + clip/Adam baseline agree to rounding
+    # (2 ranks: a + b is order-free; only the norm reductions differ in the last bits)
+    assert abs(sums["1"][0] - sums["0"][0]) < 1e-4 and abs(sums["1"][1] - sums["0"][1]) < 1e-4, sums

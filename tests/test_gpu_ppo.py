@@ -216,3 +216,19 @@ def test_fused_exchange_kernel_single_rank_matches_oracle_clip_adam():
         assert abs(norms[0] - na) < 1e-5 * max(1, na) and abs(norms[1] - nc) < 1e-5 * max(1, nc)
         assert np.abs(p[:n_a].double().cpu().numpy() - pa).max() < 2e-6 and np.abs(p[n_a:].double().cpu().numpy() - pc).max() < 2e-6
     comm.close()
+
+
+def test_graph_replayed_rollout_is_bitwise_equal_to_the_eager_loop(monkeypatch):
+    """DeviceRolloutWorker.sample replays one captured control step (policy + critic + lhw_sim_step + buffer writes);
+    the eager loop must give bit-identical batches."""
+    from learninghumanoidwalking_b200.rl import PPO
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LHW_ROLLOUT_GRAPH", mode)
+        ppo = PPO(_env_fn(seed=4), _args(), seed=4)
+        b1 = ppo.sample_parallel_with_workers()
+        b2 = ppo.sample_parallel_with_workers()            # second call: pure replay path
+        outs[mode] = [t.clone() for b in (b1, b2) for t in (b.states, b.actions, b.rewards, b.values, b.returns, b.dones)]
+        ppo.env.close()
+    for a, b in zip(outs["1"], outs["0"]):
+        assert torch.equal(a, b)

@@ -31,7 +31,16 @@ def main():
                            max_traj_len=50, num_procs=n, max_grad_norm=0.05, mirror_coeff=0.4, eval_freq=1000, recurrent=False,
                            imitate_coeff=0.0, std_dev=0.223, learn_std=False, logdir=f"/tmp/lhw_dist_{rank}", steps_per_env=16)
     ppo = PPO(env_fn, args, seed=0)
-    log = ppo.train(None, 2, verbose=False)
+    if os.environ.get("LHW_CHECK_ONE_STEP") == "1":
+        # exactly one optimiser step on identical data: the two exchange implementations must agree to rounding
+        ppo.make_optimizers()
+        batch = ppo.sample_parallel_with_workers()
+        adv = ppo.normalize_advantages(batch.returns.contiguous(), batch.values.contiguous())
+        ppo.update_actor_critic(batch.states[:128], batch.actions[:128], batch.returns[:128], adv[:128], 1,
+                                mirror_observation=ppo.env.mirror_clock_observation, mirror_action=ppo.env.mirror_action)
+        log = [dict(critic_loss=0.0, fps=0.0)]
+    else:
+        log = ppo.train(None, 2, verbose=False)
     flat = ppo._flat_param
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
