@@ -252,7 +252,7 @@ def main():
         pol.obs_std = cri.obs_std = torch.tensor(env.obs_std, dtype=torch.float32, device=dev)
         worker = DeviceRolloutWorker(env, pol, cri, seed=args.seed)
         T = max(4, min(K, 32))
-        worker.sample(0.99, 0.95, 4, 400)
+        worker.sample(0.99, 0.95, T, 400)   # warm-up with the same horizon: captures the per-step CUDA graph
         barrier()
         f0.record()
         worker.sample(0.99, 0.95, T, 400)

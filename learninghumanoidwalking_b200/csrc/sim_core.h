@@ -287,16 +287,15 @@ template <class real> LHW_DEV real seg_seg_dist2(const real* p1, const real* q1,
 // substitution fused into the factorisation (the right-hand side rides along as one more "row")
 // A_c = L_c L_c',  X_c = B_c L_c^-T,  C - sum_c X_c X_c' = L_C L_C'.  Reciprocal pivots in hdinv; the diagonal of
 // the factor is never stored (nor read).  x (global dof order) is overwritten with the solution.
-template <class real, int NJ> LHW_DEV void arrow_factor_solve(Work<real, NJ>& w, real* x) {
+template <class real, int NJ> LHW_DEVNI void arrow_factor_solve(Work<real, NJ>& w, real* x) {
   Arrow<real, NJ>& H = w.H;
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < NJ; k++) {
     LHW_LANES(l) {
       const int ch = l >> 4, r = l & 15;
       if (r < NJ + 7 && (r >= NJ || r >= k)) {
         const real* pk = H.c[ch][k];
         real dk = pk[k];
-#pragma unroll
         for (int mm = 0; mm < k; mm++) dk -= pk[mm] * pk[mm];
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
         const real inv = m_rsqrt(dk);
@@ -305,19 +304,16 @@ template <class real, int NJ> LHW_DEV void arrow_factor_solve(Work<real, NJ>& w,
         } else if (r < NJ) {
           real* pi = H.c[ch][r];
           real t = pi[k];
-#pragma unroll
           for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
           pi[k] = t * inv;
         } else if (r < NJ + 6) {
           real* px = H.x[ch][r - NJ];
           real t = px[k];
-#pragma unroll
           for (int mm = 0; mm < k; mm++) t -= px[mm] * pk[mm];
           px[k] = t * inv;
         } else {
           real* pb = x + 6 + ch * NJ;
           real t = pb[k];
-#pragma unroll
           for (int mm = 0; mm < k; mm++) t -= pb[mm] * pk[mm];
           pb[k] = t * inv;
         }
@@ -348,13 +344,12 @@ template <class real, int NJ> LHW_DEV void arrow_factor_solve(Work<real, NJ>& w,
     }
   }
   LHW_SYNC();
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 6; k++) {
     LHW_LANES(l) {
       if (l < 7 && l >= k) {
         const real* pk = H.r[k];
         real dk = pk[k];
-#pragma unroll
         for (int mm = 0; mm < k; mm++) dk -= pk[mm] * pk[mm];
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
         const real inv = m_rsqrt(dk);
@@ -362,12 +357,10 @@ template <class real, int NJ> LHW_DEV void arrow_factor_solve(Work<real, NJ>& w,
         else if (l < 6) {
           real* pi = H.r[l];
           real t = pi[k];
-#pragma unroll
           for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
           pi[k] = t * inv;
         } else {
           real t = x[k];
-#pragma unroll
           for (int mm = 0; mm < k; mm++) t -= x[mm] * pk[mm];
           x[k] = t * inv;
         }
@@ -441,7 +434,7 @@ template <class real, int NJ> LHW_DEV real arrow_row_dot(const Arrow<real, NJ>& 
 
 // ================================================================= one physics substep (mujoco.mj_step)
 template <class real, int NJ>
-LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool last) {
+LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool last) {
   constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ;
   // ---------------- P1 forward kinematics.  (a) sin/cos of all joints side by side + root rotation
   LHW_LANES(l) {
@@ -461,7 +454,7 @@ LHW_DEV void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool las
   }
   LHW_SYNC();
   // (b) both chains level by level; lane = chain*16 + matrix element (9 elements) ; elements 9..11 do the origin
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < NJ; k++) {
     LHW_LANES(l) {
       const int ch = l >> 4, e = l & 15;
