@@ -54,20 +54,22 @@ constexpr int MAXPAIR = 16;    // int32 words per env in the integer state recor
 enum { STANDING = 0, INPLACE = 1, FORWARD = 2 };
 
 // ---------------------------------------------------------------- math wrappers
+// the transcendental ones are deliberately NOT inlined on the device: each inlined copy of exp/tan/atan2/pow/sincos
+// is 100-400 SASS instructions and the kernel is instruction-cache bound (see profiles/), one shared copy each
 LHW_DEV float m_sqrt(float x) { return sqrtf(x); }
 LHW_DEV double m_sqrt(double x) { return sqrt(x); }
 LHW_DEV float m_abs(float x) { return fabsf(x); }
 LHW_DEV double m_abs(double x) { return fabs(x); }
-LHW_DEV float m_exp(float x) { return expf(x); }
-LHW_DEV double m_exp(double x) { return exp(x); }
-LHW_DEV float m_tan(float x) { return tanf(x); }
-LHW_DEV double m_tan(double x) { return tan(x); }
-LHW_DEV float m_atan2(float y, float x) { return atan2f(y, x); }
-LHW_DEV double m_atan2(double y, double x) { return atan2(y, x); }
-LHW_DEV float m_pow(float x, float y) { return powf(x, y); }
-LHW_DEV double m_pow(double x, double y) { return pow(x, y); }
-LHW_DEV void m_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
-LHW_DEV void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+LHW_DEVNI float m_exp(float x) { return expf(x); }
+LHW_DEVNI double m_exp(double x) { return exp(x); }
+LHW_DEVNI float m_tan(float x) { return tanf(x); }
+LHW_DEVNI double m_tan(double x) { return tan(x); }
+LHW_DEVNI float m_atan2(float y, float x) { return atan2f(y, x); }
+LHW_DEVNI double m_atan2(double y, double x) { return atan2(y, x); }
+LHW_DEVNI float m_pow(float x, float y) { return powf(x, y); }
+LHW_DEVNI double m_pow(double x, double y) { return pow(x, y); }
+LHW_DEVNI void m_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+LHW_DEVNI void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 template <class T> LHW_DEV T m_min(T a, T b) { return a < b ? a : b; }
 template <class T> LHW_DEV T m_max(T a, T b) { return a > b ? a : b; }
 
@@ -241,7 +243,7 @@ template <class real> LHW_DEV void contact_u(const real* p, const real* y, real*
   u[2] = -(y[3] + y[1] * p[2] - y[2] * p[1]);
 }
 // power-law impedance sigmoid of MuJoCo's getimpedance()
-template <class real> LHW_DEV real impedance(const real* solimp, real dist) {
+template <class real> LHW_DEVNI real impedance(const real* solimp, real dist) {
   const real d0 = solimp[0], dw = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
   const real x = m_abs(dist) / width;
   if (x >= 1) return dw;
@@ -289,13 +291,14 @@ template <class real> LHW_DEV real seg_seg_dist2(const real* p1, const real* q1,
 // the factor is never stored (nor read).  x (global dof order) is overwritten with the solution.
 template <class real, int NJ> LHW_DEVNI void arrow_factor_solve(Work<real, NJ>& w, real* x) {
   Arrow<real, NJ>& H = w.H;
-#pragma unroll 1
+#pragma unroll
   for (int k = 0; k < NJ; k++) {
     LHW_LANES(l) {
       const int ch = l >> 4, r = l & 15;
       if (r < NJ + 7 && (r >= NJ || r >= k)) {
         const real* pk = H.c[ch][k];
         real dk = pk[k];
+#pragma unroll
         for (int mm = 0; mm < k; mm++) dk -= pk[mm] * pk[mm];
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
         const real inv = m_rsqrt(dk);
@@ -304,17 +307,20 @@ template <class real, int NJ> LHW_DEVNI void arrow_factor_solve(Work<real, NJ>& 
         } else if (r < NJ) {
           real* pi = H.c[ch][r];
           real t = pi[k];
-          for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
+  #pragma unroll
+        for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
           pi[k] = t * inv;
         } else if (r < NJ + 6) {
           real* px = H.x[ch][r - NJ];
           real t = px[k];
-          for (int mm = 0; mm < k; mm++) t -= px[mm] * pk[mm];
+  #pragma unroll
+        for (int mm = 0; mm < k; mm++) t -= px[mm] * pk[mm];
           px[k] = t * inv;
         } else {
           real* pb = x + 6 + ch * NJ;
           real t = pb[k];
-          for (int mm = 0; mm < k; mm++) t -= pb[mm] * pk[mm];
+  #pragma unroll
+        for (int mm = 0; mm < k; mm++) t -= pb[mm] * pk[mm];
           pb[k] = t * inv;
         }
       }
@@ -344,12 +350,13 @@ template <class real, int NJ> LHW_DEVNI void arrow_factor_solve(Work<real, NJ>& 
     }
   }
   LHW_SYNC();
-#pragma unroll 1
+#pragma unroll
   for (int k = 0; k < 6; k++) {
     LHW_LANES(l) {
       if (l < 7 && l >= k) {
         const real* pk = H.r[k];
         real dk = pk[k];
+#pragma unroll
         for (int mm = 0; mm < k; mm++) dk -= pk[mm] * pk[mm];
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
         const real inv = m_rsqrt(dk);
@@ -357,11 +364,13 @@ template <class real, int NJ> LHW_DEVNI void arrow_factor_solve(Work<real, NJ>& 
         else if (l < 6) {
           real* pi = H.r[l];
           real t = pi[k];
-          for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
+  #pragma unroll
+        for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
           pi[k] = t * inv;
         } else {
           real t = x[k];
-          for (int mm = 0; mm < k; mm++) t -= x[mm] * pk[mm];
+  #pragma unroll
+        for (int mm = 0; mm < k; mm++) t -= x[mm] * pk[mm];
           x[k] = t * inv;
         }
       }
@@ -430,6 +439,39 @@ template <class real, int NJ> LHW_DEV real arrow_row_dot(const Arrow<real, NJ>& 
     for (int kk = 0; kk < NJ; kk++) acc += M.c[ch][k][kk] * x[6 + ch * NJ + kk];
   }
   return acc;
+}
+
+
+// images of a dof-space vector x: outM = M x (lane = dof), outY[f] = S_foot x (lanes 20..31), then the pyramid-edge
+// rows e_out = J_edge x - e_sub and limit rows l_out = side * x - l_sub (inactive rows get `fill`).  Used for the warm
+// start (x = qacc, sub = aref, fill = 1) and for the search direction (x = s, sub = 0, fill = 0): one shared copy.
+template <class real, int NJ>
+LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m, const real* x, real* outM, real (*outY)[6],
+                                 real* e_out, real* l_out, const real* e_sub, const real* l_sub, real fill) {
+  constexpr int NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ;
+  LHW_LANES(l) {
+    if (l < NV) outM[l] = arrow_row_dot<real, NJ>(w.M, l, x);
+    else if (l >= 20) {
+      const int f = (l - 20) / 6, e = (l - 20) - f * 6;
+      real acc = 0;
+#pragma unroll
+      for (int j = 0; j < NA; j++) acc += w.S[loc2dof<NJ>(f, j)][e] * x[loc2dof<NJ>(f, j)];
+      outY[f][e] = acc;
+    }
+  }
+  LHW_SYNC();
+  LHW_LANES(l) {
+    const int s = l >> 2, e = l & 3, f = s >> 2;
+    real v = fill;
+    if ((s & 3) < w.ncon[f]) {
+      real u[3];
+      contact_u(w.cpos[s], outY[f], u);
+      v = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)] - (e_sub ? e_sub[l] : (real)0);
+    }
+    e_out[l] = v;
+    if (l < NU) l_out[l] = w.lside[l] ? w.lside[l] * x[6 + l] - (l_sub ? l_sub[l] : (real)0) : fill;
+  }
+  LHW_SYNC();
 }
 
 // ================================================================= one physics substep (mujoco.mj_step)
@@ -744,16 +786,8 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool l
     }
   }
   LHW_SYNC();
-  // ---------------- P9 Newton start: Ma = M a (lane = dof) ; foot spatial accelerations ya = S_foot a (lanes 20..31)
+  // ---------------- P9 Newton start: contact point maps Pm, then Ma = M a, ya = S_foot a and the row residuals
   LHW_LANES(l) {
-    if (l < NV) w.Ma[l] = arrow_row_dot<real, NJ>(w.M, l, w.qacc);
-    else if (l >= 20) {
-      const int f = (l - 20) / 6, e = (l - 20) - f * 6;
-      real acc = 0;
-#pragma unroll
-      for (int j = 0; j < NA; j++) acc += w.S[loc2dof<NJ>(f, j)][e] * w.qacc[loc2dof<NJ>(f, j)];
-      w.ya[f][e] = acc;
-    }
     if (l < NCON && (l & 3) < w.ncon[l >> 2]) {
       // rows of P: spatial wrench [p x e ; e] of a unit force along e = n (+z), t1 (+y), t2 (-x) applied at p
       const real px = w.cpos[l][0], py = w.cpos[l][1], pz = w.cpos[l][2];
@@ -763,19 +797,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool l
       P[12] = 0;  P[13] = -pz; P[14] = py; P[15] = -1; P[16] = 0; P[17] = 0;
     }
   }
-  LHW_SYNC();
-  LHW_LANES(l) {
-    const int s = l >> 2, e = l & 3, f = s >> 2;
-    real jar = 1;
-    if ((s & 3) < w.ncon[f]) {
-      real u[3];
-      contact_u(w.cpos[s], w.ya[f], u);
-      jar = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)] - w.earef[l];
-    }
-    w.ejar[l] = jar;
-    if (l < NU) w.ljar[l] = w.lside[l] ? w.lside[l] * w.qacc[6 + l] - w.laref[l] : (real)1;
-  }
-  LHW_SYNC();
+  constraint_images<real, NJ>(w, m, w.qacc, w.Ma, w.ya, w.ejar, w.ljar, w.earef, w.laref, (real)1);
 
   // ---------------- P10 primal Newton on  1/2 (a-a_s)' M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
   // residuals (Ma, ejar, ljar) are carried incrementally: x += alpha * (direction image)
@@ -887,29 +909,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool l
     LHW_SYNC();
     arrow_factor_solve<real, NJ>(w, w.sdir);
     // (g) images of the search direction: M s, foot spatial accelerations, edge / limit rates
-    LHW_LANES(l) {
-      if (l < NV) w.Ms[l] = arrow_row_dot<real, NJ>(w.M, l, w.sdir);
-      else if (l >= 20) {
-        const int f = (l - 20) / 6, e = (l - 20) - f * 6;
-        real acc = 0;
-#pragma unroll
-        for (int j = 0; j < NA; j++) acc += w.S[loc2dof<NJ>(f, j)][e] * w.sdir[loc2dof<NJ>(f, j)];
-        w.ys[f][e] = acc;
-      }
-    }
-    LHW_SYNC();
-    LHW_LANES(l) {
-      const int s = l >> 2, e = l & 3, f = s >> 2;
-      real jv = 0;
-      if ((s & 3) < w.ncon[f]) {
-        real u[3];
-        contact_u(w.cpos[s], w.ys[f], u);
-        jv = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)];
-      }
-      w.ejv[l] = jv;
-      if (l < NU) w.ljv[l] = w.lside[l] ? w.lside[l] * w.sdir[6 + l] : (real)0;
-    }
-    LHW_SYNC();
+    constraint_images<real, NJ>(w, m, w.sdir, w.Ms, w.ys, w.ejv, w.ljv, (const real*)nullptr, (const real*)nullptr, (real)0);
     const real sMs = warp_sum<real>([&](int l) { return l < NV ? w.sdir[l] * w.Ms[l] : (real)0; });
     const real sg = warp_sum<real>([&](int l) { return l < NV ? w.sdir[l] * (w.Ma[l] - w.qfs[l]) : (real)0; });
     // (h) exact line search: phi'(alpha) is continuous, piecewise linear, increasing; safeguarded 1-D Newton
