@@ -41,6 +41,12 @@
 #define LHW_SYNC() ((void)0)
 #endif
 
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+#define LHW_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define LHW_ASSUME_SHARED(p) ((void)0)
+#endif
+
 namespace lhw {
 
 constexpr int NCON = 8;        // 2 feet x 4 box corners (mjc_PlaneBox returns at most 4)
@@ -122,6 +128,16 @@ template <class real, int NJ> struct Model {
   unsigned char pair_a[MAXPAIR], pair_b[MAXPAIR];
   int axis_id[NL];  // 0/1/2: hinge axis is +e_x/+e_y/+e_z of the link frame AND link_rot is the identity (fast FK path); -1: general
 };
+
+// Out-of-line device routines must not read the model through a generic reference (that turns every constant-bank
+// LDC into a generic load): the translation unit that owns the __constant__ object specialises this hook; the default
+// (host emulation) just returns what it was given.
+template <class real, int NJ> struct ModelHome {
+  static LHW_DEV const Model<real, NJ>& get(const Model<real, NJ>& passed) { return passed; }
+};
+template <class real, int NJ> LHW_DEV const Model<real, NJ>& model_ref(const Model<real, NJ>& passed) {
+  return ModelHome<real, NJ>::get(passed);
+}
 
 template <class real, int NJ> struct Dims {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
@@ -290,6 +306,8 @@ template <class real> LHW_DEV real seg_seg_dist2(const real* p1, const real* q1,
 // A_c = L_c L_c',  X_c = B_c L_c^-T,  C - sum_c X_c X_c' = L_C L_C'.  Reciprocal pivots in hdinv; the diagonal of
 // the factor is never stored (nor read).  x (global dof order) is overwritten with the solution.
 template <class real, int NJ> LHW_DEVNI void arrow_factor_solve(Work<real, NJ>& w, real* x) {
+  LHW_ASSUME_SHARED(&w);
+  LHW_ASSUME_SHARED(x);
   Arrow<real, NJ>& H = w.H;
 #pragma unroll
   for (int k = 0; k < NJ; k++) {
@@ -446,9 +464,13 @@ template <class real, int NJ> LHW_DEV real arrow_row_dot(const Arrow<real, NJ>& 
 // rows e_out = J_edge x - e_sub and limit rows l_out = side * x - l_sub (inactive rows get `fill`).  Used for the warm
 // start (x = qacc, sub = aref, fill = 1) and for the search direction (x = s, sub = 0, fill = 0): one shared copy.
 template <class real, int NJ>
-LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m, const real* x, real* outM, real (*outY)[6],
+LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const real* x, real* outM, real (*outY)[6],
                                  real* e_out, real* l_out, const real* e_sub, const real* l_sub, real fill) {
   constexpr int NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ;
+  const Model<real, NJ>& m = model_ref<real, NJ>(m_arg);
+  LHW_ASSUME_SHARED(&w); LHW_ASSUME_SHARED(x); LHW_ASSUME_SHARED(outM); LHW_ASSUME_SHARED(outY);
+  LHW_ASSUME_SHARED(e_out); LHW_ASSUME_SHARED(l_out);
+  if (e_sub) { LHW_ASSUME_SHARED(e_sub); LHW_ASSUME_SHARED(l_sub); }
   LHW_LANES(l) {
     if (l < NV) outM[l] = arrow_row_dot<real, NJ>(w.M, l, x);
     else if (l >= 20) {
@@ -476,8 +498,10 @@ LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m, co
 
 // ================================================================= one physics substep (mujoco.mj_step)
 template <class real, int NJ>
-LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m, const bool last) {
+LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bool last) {
   constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ;
+  LHW_ASSUME_SHARED(&w);
+  const Model<real, NJ>& m = model_ref<real, NJ>(m_arg);  // device: the __constant__ object itself (LDC), not a generic reference
   // ---------------- P1 forward kinematics.  (a) sin/cos of all joints side by side + root rotation
   LHW_LANES(l) {
     if (l < NU) {

@@ -26,6 +26,18 @@ template <class real> __device__ __forceinline__ const Model<real, NJ_JVRC>& cmo
 template <> __device__ __forceinline__ const Model<double, NJ_JVRC>& cmodel<double>() { return c_model_d; }
 template <> __device__ __forceinline__ const Model<float, NJ_JVRC>& cmodel<float>() { return c_model_f; }
 
+}  // namespace
+// tell sim_core.h's out-of-line routines where the model really lives (constant bank -> LDC with immediate offsets)
+namespace lhw {
+template <> struct ModelHome<double, NJ_JVRC> {
+  static __device__ __forceinline__ const Model<double, NJ_JVRC>& get(const Model<double, NJ_JVRC>&) { return c_model_d; }
+};
+template <> struct ModelHome<float, NJ_JVRC> {
+  static __device__ __forceinline__ const Model<float, NJ_JVRC>& get(const Model<float, NJ_JVRC>&) { return c_model_f; }
+};
+}  // namespace lhw
+namespace {
+
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 const void* g_owner[2] = {nullptr, nullptr};  // which sim's model currently sits in constant memory (per precision)
