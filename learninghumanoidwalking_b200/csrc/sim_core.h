@@ -41,6 +41,12 @@
 #define LHW_SYNC() ((void)0)
 #endif
 
+// optional block-level rendez-vous once per substep (multi-warp blocks only): keeps the warps of a block in the same
+// region of the code so they share instruction-cache fills
+#ifndef LHW_BLOCK_SYNC
+#define LHW_BLOCK_SYNC(on) ((void)0)
+#endif
+
 #if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
 #define LHW_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 #else
@@ -498,7 +504,7 @@ LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m_arg
 
 // ================================================================= one physics substep (mujoco.mj_step)
 template <class real, int NJ>
-LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bool last) {
+LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bool last, const int block_sync = 0) {
   constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ;
   LHW_ASSUME_SHARED(&w);
   const Model<real, NJ>& m = model_ref<real, NJ>(m_arg);  // device: the __constant__ object itself (LDC), not a generic reference
@@ -810,6 +816,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
     }
   }
   LHW_SYNC();
+  LHW_BLOCK_SYNC(block_sync & 2);  // optional second rendez-vous of the block's warps, before the solver
   // ---------------- P9 Newton start: contact point maps Pm, then Ma = M a, ya = S_foot a and the row residuals
   LHW_LANES(l) {
     if (l < NCON && (l & 3) < w.ncon[l >> 2]) {
@@ -1218,7 +1225,7 @@ struct StepOut {
 // BaseHumanoidEnv.step + the RolloutWorker's bookkeeping (traj_len truncation, auto-reset, episode stats)
 template <class real, int NJ>
 LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* action, uint32_t seed, int max_traj_len,
-                      int autoreset, real* obs_out, real* term_obs_out, real* reward_out, real* rew_terms_out,
+                      int autoreset, const int block_sync, const int alive, real* obs_out, real* term_obs_out, real* reward_out, real* rew_terms_out,
                       int32_t* done_out, int32_t* ended_out, int32_t* ep_len_out, real* ep_rew_out) {
   constexpr int NU = 2 * NJ, NOBS = Work<real, NJ>::NOBS;
   // action smoothing + nominal offsets (base_humanoid_env.py:209-212, robot_base.py:80-85)
@@ -1235,8 +1242,11 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
       if (l < NU) w.ctrl[l] = m.kp[l] * (w.target[l] - w.act_len[l]) + m.kd[l] * ((real)0 - w.act_vel[l]);
     }
     LHW_SYNC();
-    substep<real, NJ>(w, m, sidx == m.frame_skip - 1);
+    if (alive) substep<real, NJ>(w, m, sidx == m.frame_skip - 1, block_sync);
+    else LHW_BLOCK_SYNC(block_sync & 2);
+    LHW_BLOCK_SYNC(block_sync & 1);
   }
+  if (!alive) return;
   // WalkingTask.step (tasks/walking_task.py:149-179)
   LHW_LANES(l) {
     if (l == 0) {

@@ -12,6 +12,7 @@
 #include <string>
 
 #include "../../include/lhw_b200.h"
+#define LHW_BLOCK_SYNC(on) do { if (on) __syncthreads(); } while (0)
 #include "model_pack.h"
 
 using namespace lhw;
@@ -101,17 +102,46 @@ __global__ void __launch_bounds__(32, sizeof(real) == 4 ? 28 : 16)
   real* sr = state_r + (size_t)env * NR;
   int32_t* si = state_i + (size_t)env * NSTATE_I;
   load_state<real, NJ>(w, sr, si, first_id + env);
-  env_step<real, NJ>(w, m, actions + (size_t)env * NU, seed, max_traj_len, autoreset, obs + (size_t)env * W::NOBS,
+  env_step<real, NJ>(w, m, actions + (size_t)env * NU, seed, max_traj_len, autoreset, 0, 1, obs + (size_t)env * W::NOBS,
                      term_obs ? term_obs + (size_t)env * W::NOBS : nullptr, reward + env,
                      rew_terms ? rew_terms + (size_t)env * NREW : nullptr, done + env, ended + env,
                      ep_len ? ep_len + env : nullptr, ep_rew ? ep_rew + env : nullptr);
   store_state<real, NJ>(w, sr, si);
 }
 
+// experiment / alternative carving: W warps per block (one env each), a __syncthreads() per substep so the warps of an SM
+// share instruction-cache fills (the kernel is instruction-fetch bound, profiles/); selected with LHW_WARPS_PER_BLOCK > 1
+template <class real>
+__global__ void __launch_bounds__(sizeof(real) == 8 ? 512 : 896, 1)
+    step_kernel_mw(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs, uint32_t seed, uint32_t first_id,
+                   const real* __restrict__ actions, int max_traj_len, int autoreset, real* __restrict__ obs,
+                   real* __restrict__ term_obs, real* __restrict__ reward, real* __restrict__ rew_terms,
+                   int32_t* __restrict__ done, int32_t* __restrict__ ended, int32_t* __restrict__ ep_len,
+                   real* __restrict__ ep_rew, int sync_mode) {
+  constexpr int NJ = NJ_JVRC;
+  using W = Work<real, NJ>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int alive = env < n_envs;
+  const int e = alive ? env : n_envs - 1;
+  W& w = reinterpret_cast<W*>(smem_raw)[warp];
+  const Model<real, NJ>& m = cmodel<real>();
+  constexpr int NR = Dims<real, NJ>::NSTATE_R, NU = 2 * NJ;
+  real* sr = state_r + (size_t)e * NR;
+  int32_t* si = state_i + (size_t)e * NSTATE_I;
+  if (alive) load_state<real, NJ>(w, sr, si, first_id + e);
+  env_step<real, NJ>(w, m, actions + (size_t)e * NU, seed, max_traj_len, autoreset, sync_mode, alive, obs + (size_t)e * W::NOBS,
+                     term_obs ? term_obs + (size_t)e * W::NOBS : nullptr, reward + e,
+                     rew_terms ? rew_terms + (size_t)e * NREW : nullptr, done + e, ended + e,
+                     ep_len ? ep_len + e : nullptr, ep_rew ? ep_rew + e : nullptr);
+  if (alive) store_state<real, NJ>(w, sr, si);
+}
+
 }  // namespace
 
 struct lhw_sim {
-  int precision, device, warps_per_block;
+  int precision, device, warps_per_block, sync_mode;
   Model<double, NJ_JVRC> md;
   Model<float, NJ_JVRC> mf;
   size_t work_bytes;
@@ -159,7 +189,12 @@ int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision,
     return fail(-4, "malformed model array (fill_model rc " + std::to_string(rc) + ")");
   }
   s->work_bytes = precision == 64 ? sizeof(Work<double, NJ_JVRC>) : sizeof(Work<float, NJ_JVRC>);
-  s->warps_per_block = 1;
+  const char* env_wpb = getenv("LHW_WARPS_PER_BLOCK");
+  // measured on B200 (profiles/): lock-step blocks of 8 (fp64, 2 blocks/SM) / 14 (fp32, 2 blocks/SM) warps
+  s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? 8 : 14);
+  const char* env_sync = getenv("LHW_BLOCK_SYNC_MODE");
+  s->sync_mode = env_sync ? atoi(env_sync) : 1;
+  if (s->warps_per_block < 1 || s->warps_per_block > (precision == 64 ? 16 : 28)) s->warps_per_block = 1;
   const size_t smem = s->work_bytes * s->warps_per_block;
   int maxsmem = 0;
   CUDA_OK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -168,9 +203,11 @@ int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision,
     return fail(-5, "working set does not fit in shared memory");
   }
   if (precision == 64) {
-    if (prepare_kernel(step_kernel<double>, smem) || prepare_kernel(reset_kernel<double>, smem)) { delete s; return -10; }
+    if (prepare_kernel(step_kernel<double>, s->work_bytes) || prepare_kernel(reset_kernel<double>, s->work_bytes) ||
+        (s->warps_per_block > 1 && prepare_kernel(step_kernel_mw<double>, smem))) { delete s; return -10; }
   } else {
-    if (prepare_kernel(step_kernel<float>, smem) || prepare_kernel(reset_kernel<float>, smem)) { delete s; return -10; }
+    if (prepare_kernel(step_kernel<float>, s->work_bytes) || prepare_kernel(reset_kernel<float>, s->work_bytes) ||
+        (s->warps_per_block > 1 && prepare_kernel(step_kernel_mw<float>, smem))) { delete s; return -10; }
   }
   *out = s;
   return 0;
@@ -201,8 +238,8 @@ int lhw_sim_reset(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint3
   if (n_envs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (upload_model(s, st)) return -10;
-  const int wpb = s->warps_per_block, grid = (n_envs + wpb - 1) / wpb;
-  const size_t smem = s->work_bytes * wpb;
+  const int wpb = 1, grid = n_envs;
+  const size_t smem = s->work_bytes;
   if (s->precision == 64)
     reset_kernel<double><<<grid, wpb * 32, smem, st>>>((double*)state_r, state_i, n_envs, seed, first_env_id, mask, fresh, (double*)obs);
   else
@@ -221,7 +258,18 @@ int lhw_sim_step(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint32
   if (upload_model(s, st)) return -10;
   const int wpb = s->warps_per_block, grid = (n_envs + wpb - 1) / wpb;
   const size_t smem = s->work_bytes * wpb;
-  if (s->precision == 64)
+  if (wpb > 1) {
+    if (s->precision == 64)
+      step_kernel_mw<double><<<grid, wpb * 32, smem, st>>>((double*)state_r, state_i, n_envs, seed, first_env_id,
+                                                           (const double*)actions, max_traj_len, autoreset, (double*)obs,
+                                                           (double*)term_obs, (double*)reward, (double*)rew_terms, done,
+                                                           ended, ep_len, (double*)ep_rew, s->sync_mode);
+    else
+      step_kernel_mw<float><<<grid, wpb * 32, smem, st>>>((float*)state_r, state_i, n_envs, seed, first_env_id,
+                                                          (const float*)actions, max_traj_len, autoreset, (float*)obs,
+                                                          (float*)term_obs, (float*)reward, (float*)rew_terms, done, ended,
+                                                          ep_len, (float*)ep_rew, s->sync_mode);
+  } else if (s->precision == 64)
     step_kernel<double><<<grid, wpb * 32, smem, st>>>((double*)state_r, state_i, n_envs, seed, first_env_id,
                                                       (const double*)actions, max_traj_len, autoreset, (double*)obs,
                                                       (double*)term_obs, (double*)reward, (double*)rew_terms, done,

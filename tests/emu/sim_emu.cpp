@@ -42,7 +42,7 @@ static void step_all(void* h, real* sr, int32_t* si, int n_envs, uint32_t seed, 
   constexpr int NR = Dims<real, NJ>::NSTATE_R, NOBS = Work<real, NJ>::NOBS, NU = 2 * NJ;
   for (int i = 0; i < n_envs; i++) {
     load_state(e->work, sr + (size_t)i * NR, si + (size_t)i * NSTATE_I, first_id + i);
-    env_step(e->work, e->model, actions + (size_t)i * NU, seed, max_traj_len, autoreset, obs + (size_t)i * NOBS,
+    env_step(e->work, e->model, actions + (size_t)i * NU, seed, max_traj_len, autoreset, 0, 1, obs + (size_t)i * NOBS,
              term_obs + (size_t)i * NOBS, reward + i, rew_terms + (size_t)i * NREW, done + i, ended + i, ep_len + i,
              ep_rew + i);
     store_state(e->work, sr + (size_t)i * NR, si + (size_t)i * NSTATE_I);
