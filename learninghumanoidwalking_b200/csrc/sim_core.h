@@ -1244,7 +1244,7 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
     LHW_SYNC();
     if (alive) substep<real, NJ>(w, m, sidx == m.frame_skip - 1, block_sync);
     else LHW_BLOCK_SYNC(block_sync & 2);
-    LHW_BLOCK_SYNC(block_sync & 1);
+    LHW_BLOCK_SYNC((block_sync & 1) && ((sidx + 1) % ((block_sync >> 4) + 1) == 0));   // every (block_sync>>4)+1 substeps
   }
   if (!alive) return;
   // WalkingTask.step (tasks/walking_task.py:149-179)

@@ -48,13 +48,13 @@ for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"{str(key):36s} inst {a[0]:>12d} {100*a[0]/tot:5.1f}%  lanes {a[1]/max(1,a[0]):5.1f}  samples {100*a[2]/max(1,tots):5.1f}%")
 
 # ---- coarse regions of sim_core.h
-REGIONS = [(54, 71, "math wrappers"), (72, 84, "warp_sum"), (85, 100, "philox"), (181, 235, "vec helpers (cross/dot6/mv3/inert_mul/rsqrt/contact_u)"),
-           (236, 254, "impedance"), (255, 387, "arrow_factor_solve"), (388, 410, "arrow_row_dot"), (411, 471, "P1 FK"), (472, 516, "P2 S+inertia"),
-           (517, 542, "P3 comp+V"), (543, 569, "P4 rootcomp+velprod"), (570, 605, "P5 CRBA+A"), (606, 633, "P6 F+corner candidates"),
-           (634, 655, "P7 subtree+slots"), (656, 675, "P7b contact params"), (676, 718, "P8 aref+qfs+limits"), (719, 751, "P9 newton init+Pm"),
-           (752, 775, "P10 a cF/cW"), (776, 789, "P10 c Ff"), (790, 805, "P10 d grad"), (806, 838, "P10 e Af,T"), (839, 859, "P10 f H"),
-           (860, 886, "P10 g images"), (887, 933, "P10 h linesearch+update"), (934, 971, "P11 lagged"), (972, 1031, "P12 euler+integrate"),
-           (1032, 1400, "env level")]
+REGIONS = [(60, 82, "math wrappers (out of line)"), (83, 100, "warp_sum"), (101, 120, "philox"), (210, 267, "vec helpers (cross/dot6/mv3/inert_mul/rsqrt/contact_u)"),
+           (268, 283, "impedance"), (284, 313, "seg_seg_dist2"), (314, 448, "arrow_factor_solve"), (449, 472, "arrow_row_dot"),
+           (473, 510, "constraint_images"), (511, 571, "P1 FK"), (572, 616, "P2 S+inertia"), (617, 642, "P3 comp+V"),
+           (643, 669, "P4 rootcomp+velprod"), (670, 705, "P5 CRBA+A"), (706, 733, "P6 F+corner candidates"), (734, 755, "P7 subtree+slots"),
+           (756, 775, "P7b contact params"), (776, 819, "P8 aref+qfs+limits"), (820, 835, "P9 Pm + newton init"), (836, 856, "P10 a cF/cW"),
+           (857, 870, "P10 c Ff"), (871, 886, "P10 d grad"), (887, 919, "P10 e Af,T"), (920, 940, "P10 f H"), (941, 948, "P10 g images call"),
+           (949, 992, "P10 h linesearch+update"), (993, 1057, "P11 lagged+selfcol"), (1058, 1117, "P12 euler+integrate"), (1118, 1500, "env level")]
 reg = defaultdict(lambda: [0, 0, 0])
 for (f, ln), a in agg.items() if all(k is not None for k in agg) else [(k, v) for k, v in agg.items() if k is not None]:
     name = f if f != "sim_core.h" else next((n for lo, hi, n in REGIONS if lo <= ln <= hi), "other")
