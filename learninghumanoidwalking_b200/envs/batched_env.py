@@ -129,6 +129,11 @@ class BatchedHumanoidEnv:
         """Newton iterations spent in the last launch, per env."""
         return self.state_i[:, 7]
 
+    def status_flags(self) -> torch.Tensor:
+        """Per-env status word of the last launch (1: non-finite / diverging acceleration seen, forced reset — the analogue
+        of MuJoCo's mj_checkAcc auto-reset; 2: a Cholesky pivot had to be clamped)."""
+        return self.state_i[:, 6]
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.lib().lhw_sim_destroy(self._h)
