@@ -15,20 +15,41 @@ namespace {
 
 thread_local std::string g_perr;
 
-// GAE(lambda): one thread per env, reverse scan over time; float64 accumulation like the reference's buffers
-__global__ void gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const int32_t* __restrict__ ended,
-                           const float* __restrict__ boot, const float* __restrict__ last_val, float* __restrict__ ret,
-                           int T, int N, double gamma, double lam) {
+// GAE(lambda): one thread per env, reverse scan over time; float64 accumulation like the reference's buffers.
+// The recurrence is serial in t but its loads are not: GAE_U time steps are fetched ahead of the dependent chain
+// (independent coalesced loads in flight), which is what turns the loop from latency bound into a streaming kernel.
+constexpr int GAE_U = 8;
+__global__ void __launch_bounds__(64) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                                 const int32_t* __restrict__ ended, const float* __restrict__ boot,
+                                                 const float* __restrict__ last_val, float* __restrict__ ret, int T, int N,
+                                                 double gamma, double lam) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   double next_val = (double)last_val[n], gae = 0.0;
   const double gl = gamma * lam;
-  for (int t = T - 1; t >= 0; t--) {
+  int t = T - 1;
+  for (; t >= GAE_U - 1; t -= GAE_U) {
+    float r[GAE_U], v[GAE_U], b[GAE_U];
+    int e[GAE_U];
+#pragma unroll
+    for (int u = 0; u < GAE_U; u++) {
+      const size_t i = (size_t)(t - u) * N + n;
+      r[u] = __ldg(rew + i); v[u] = __ldg(val + i); e[u] = __ldg(ended + i); b[u] = __ldg(boot + i);
+    }
+#pragma unroll
+    for (int u = 0; u < GAE_U; u++) {
+      if (e[u]) { next_val = (double)b[u]; gae = 0.0; }
+      const double vv = (double)v[u];
+      gae = ((double)r[u] + gamma * next_val - vv) + gl * gae;
+      ret[(size_t)(t - u) * N + n] = (float)(gae + vv);
+      next_val = vv;
+    }
+  }
+  for (; t >= 0; t--) {
     const size_t i = (size_t)t * N + n;
     if (ended[i]) { next_val = (double)boot[i]; gae = 0.0; }
     const double v = (double)val[i];
-    const double delta = (double)rew[i] + gamma * next_val - v;
-    gae = delta + gl * gae;
+    gae = ((double)rew[i] + gamma * next_val - v) + gl * gae;
     ret[i] = (float)(gae + v);
     next_val = v;
   }
@@ -150,7 +171,7 @@ extern "C" {
 int lhw_gae(const float* rewards, const float* values, const int32_t* ended, const float* boot, const float* last_val,
             float* returns, int T, int N, float gamma, float lam, void* stream) {
   if (T <= 0 || N <= 0) return 0;
-  gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, values, ended, boot, last_val, returns, T, N,
+  gae_kernel<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(rewards, values, ended, boot, last_val, returns, T, N,
                                                                 (double)gamma, (double)lam);
   KCHECK("gae_kernel");
   return 0;
