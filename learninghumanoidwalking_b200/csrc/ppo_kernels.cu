@@ -15,37 +15,48 @@ namespace {
 
 thread_local std::string g_perr;
 
-// GAE(lambda): one thread per env, reverse scan over time; float64 accumulation like the reference's buffers.
-// The recurrence is serial in t but its loads are not: GAE_U time steps are fetched ahead of the dependent chain
-// (independent coalesced loads in flight), which is what turns the loop from latency bound into a streaming kernel.
-constexpr int GAE_U = 8;
-__global__ void __launch_bounds__(64) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
-                                                 const int32_t* __restrict__ ended, const float* __restrict__ boot,
-                                                 const float* __restrict__ last_val, float* __restrict__ ret, int T, int N,
-                                                 double gamma, double lam) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  double next_val = (double)last_val[n], gae = 0.0;
+// GAE(lambda) as a two-level reverse scan.  A_t = delta_t + c_t A_{t+1} with c_t = gamma*lambda (0 where an episode
+// ended) is an affine recurrence, and V(s_{t+1}) is data (the next row of `val`, or the bootstrap where the path ends),
+// so only the scalar A crosses a segment boundary.  Block = 32 envs x GAE_SEG time segments: (1) every thread scans its
+// segment with A_in = 0 and keeps (A_out, C = prod c_t); (2) the carry into each segment is the fixed-order composition
+// of the later segments' (A, C) through shared memory; (3) the segment is rescanned with the right A_in and written.
+// 2 x 16 B reads + 4 B write per sample, coalesced across the env index, T*N/GAE_LEN threads instead of N.
+// float64 accumulation like the reference's buffers (rl/storage/rollout_storage.py:26-31).
+constexpr int GAE_SEG = 16;
+__global__ void __launch_bounds__(32 * GAE_SEG) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                                           const int32_t* __restrict__ ended, const float* __restrict__ boot,
+                                                           const float* __restrict__ last_val, float* __restrict__ ret, int T,
+                                                           int N, double gamma, double lam) {
+  __shared__ double shA[GAE_SEG][32], shC[GAE_SEG][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const int len = (T + GAE_SEG - 1) / GAE_SEG;
+  const int t_lo = seg * len, t_hi = min(T, t_lo + len) - 1;   // this thread owns t_lo..t_hi (may be empty)
+  const bool live = n < N && t_lo <= t_hi;
   const double gl = gamma * lam;
-  int t = T - 1;
-  for (; t >= GAE_U - 1; t -= GAE_U) {
-    float r[GAE_U], v[GAE_U], b[GAE_U];
-    int e[GAE_U];
-#pragma unroll
-    for (int u = 0; u < GAE_U; u++) {
-      const size_t i = (size_t)(t - u) * N + n;
-      r[u] = __ldg(rew + i); v[u] = __ldg(val + i); e[u] = __ldg(ended + i); b[u] = __ldg(boot + i);
-    }
-#pragma unroll
-    for (int u = 0; u < GAE_U; u++) {
-      if (e[u]) { next_val = (double)b[u]; gae = 0.0; }
-      const double vv = (double)v[u];
-      gae = ((double)r[u] + gamma * next_val - vv) + gl * gae;
-      ret[(size_t)(t - u) * N + n] = (float)(gae + vv);
-      next_val = vv;
+  double A = 0.0, C = 1.0;
+  if (live) {
+    double next_val = t_hi == T - 1 ? (double)last_val[n] : (double)val[(size_t)(t_hi + 1) * N + n];
+    for (int t = t_hi; t >= t_lo; t--) {
+      const size_t i = (size_t)t * N + n;
+      if (ended[i]) { next_val = (double)boot[i]; A = 0.0; C = 0.0; }
+      const double v = (double)val[i];
+      A = ((double)rew[i] + gamma * next_val - v) + gl * A;
+      C *= gl;
+
+      next_val = v;
     }
   }
-  for (; t >= 0; t--) {
+  shA[seg][lane] = A;
+  shC[seg][lane] = live ? C : 1.0;
+  __syncthreads();
+  if (!live) return;
+  // carry into this segment = A of everything later, composed from the last segment backwards (fixed order)
+  double carry = 0.0;
+  for (int s2 = GAE_SEG - 1; s2 > seg; s2--) carry = shA[s2][lane] + shC[s2][lane] * carry;
+  double gae = carry;
+  double next_val = t_hi == T - 1 ? (double)last_val[n] : (double)val[(size_t)(t_hi + 1) * N + n];
+  for (int t = t_hi; t >= t_lo; t--) {
     const size_t i = (size_t)t * N + n;
     if (ended[i]) { next_val = (double)boot[i]; gae = 0.0; }
     const double v = (double)val[i];
@@ -171,7 +182,7 @@ extern "C" {
 int lhw_gae(const float* rewards, const float* values, const int32_t* ended, const float* boot, const float* last_val,
             float* returns, int T, int N, float gamma, float lam, void* stream) {
   if (T <= 0 || N <= 0) return 0;
-  gae_kernel<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(rewards, values, ended, boot, last_val, returns, T, N,
+  gae_kernel<<<(N + 31) / 32, 32 * GAE_SEG, 0, (cudaStream_t)stream>>>(rewards, values, ended, boot, last_val, returns, T, N,
                                                                 (double)gamma, (double)lam);
   KCHECK("gae_kernel");
   return 0;
