@@ -17,7 +17,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "_build", "liboracle.so")
-NOBS, NREW, NU, NV, NQ = 37, 10, 12, 18, 19
+NOBS, NREW, NU, NV, NQ = 37, 10, 12, 18, 19   # jvrc sizes == the C struct capacities (ORC_NU, ORC_NV, ORC_NQ)
+MAXLINK = 16
 
 
 def build(force: bool = False) -> str:
@@ -62,8 +63,8 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
     b.append(len(mj["geoms"]))
     for g in mj["geoms"]:
         b.append(g["link"])
-        b += g["pos"]
-        b += g["size"]
+        b += g.get("pos", [0.0, 0.0, 0.0])
+        b += g.get("size", [0.0, 0.0, 0.0])
     o = mj["opt"]
     b.append(o["timestep"])
     b += o["gravity"]
@@ -76,10 +77,12 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
     b += c["kd"]
     b += c["nominal_qpos"]
     b += [c["frame_skip"], c["action_smoothing"], mj["rfoot_link"], mj["lfoot_link"]]
-    b += mj["head_in_root"]
-    b += [mj["total_mass"], c["task"]["goal_height"], clocks["period"]]
-    for k in ("r_frc", "r_vel", "l_frc", "l_vel"):
-        b += clocks[k]
+    stand = mj["name"] == "h1"
+    b += mj.get("head_in_root", [0.0, 0.0, 0.0])
+    b += [mj["total_mass"], c.get("task", {}).get("goal_height", 0.98), 0 if stand else clocks["period"]]
+    if not stand:
+        for k in ("r_frc", "r_vel", "l_frc", "l_vel"):
+            b += clocks[k]
     sc = mj.get("self_collision") if self_collision else None
     caps = sc["capsules"] if sc else []
     b.append(len(caps))
@@ -89,6 +92,31 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
     b.append(len(pairs))
     for a_, b_ in pairs:
         b += [a_, b_]
+    # task / robot variant tail (envs/h1/configs/base.yaml, tasks/standing_task.py)
+    if stand:
+        ns = c["observation_noise"]
+        sc = ns["scales"]
+        lvl = ns["multiplier"] if ns["enabled"] else 0.0
+        pert, dyn = c["perturbation"], c["dynamics_randomization"]
+        b += [1, 35, 0.9, 1.4]
+        b += [lvl * sc[k] for k in ("root_orient", "root_ang_vel", "motor_pos", "motor_vel", "motor_tau")]
+        b += [int(dyn["interval"] / c["control_dt"]) if dyn["enable"] else 0,
+              int(pert["interval"] / c["control_dt"]) if pert["enable"] else 0,
+              pert["force_magnitude"], pert["torque_magnitude"], c["init_noise_deg"]]
+    else:
+        b += [0, 37, 0.6, 1.4] + [0.0] * 5 + [0, 0, 0.0, 0.0, 0.0]
+    for g in mj["geoms"]:
+        pts = g.get("points", [])
+        b += [1 if g.get("type") == "spheres" else 0, len(pts), g.get("radius", 0.0)]
+        for pt in pts:
+            b += pt
+    rp = mj.get("root_parts")
+    if rp:
+        b += [rp["pelvis"]["mass"]] + rp["pelvis"]["com"] + list(np.array(rp["pelvis"]["Ic"]).reshape(-1))
+        b += [rp["rest"]["mass"]] + rp["rest"]["mc"] + list(np.array(rp["rest"]["Io"]).reshape(-1))
+        b += rp["torso_com"]
+    else:
+        b += [0.0] * 29
     return np.array(b, dtype=np.float64)
 
 
@@ -108,6 +136,10 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"orc_model_from_flat failed: {rc}")
         self.env_size = L.orc_sizeof_env()
+        assert self.env_size == _ENV_SIZE, (self.env_size, _ENV_SIZE)
+        self.nu = len(self.mj["links"]) - 1
+        self.nv, self.nq = 6 + self.nu, 7 + self.nu
+        self.nobs = 35 if name == "h1" else NOBS
 
     # ---- single/batched env management
     def make_envs(self, n: int, seed: int = 0, first_id: int = 0):
@@ -132,7 +164,7 @@ class Oracle:
         raw[off:off + cnt * np.dtype(typ).itemsize] = np.asarray(value, dtype=typ).reshape(cnt).view(np.uint8)
 
     def reset(self, envs, i=0):
-        obs = np.zeros(NOBS)
+        obs = np.zeros(self.nobs)
         self.lib.orc_reset(self._model, self.env_ptr(envs, i), obs.ctypes.data_as(ctypes.c_void_p))
         return obs
 
@@ -142,7 +174,7 @@ class Oracle:
 
     def step(self, envs, i, action):
         action = np.ascontiguousarray(action, dtype=np.float64)
-        obs, terms = np.zeros(NOBS), np.zeros(NREW)
+        obs, terms = np.zeros(self.nobs), np.zeros(NREW)
         rew, done = ctypes.c_double(), ctypes.c_int()
         self.lib.orc_step(self._model, self.env_ptr(envs, i), action.ctypes.data_as(ctypes.c_void_p),
                           obs.ctypes.data_as(ctypes.c_void_p), terms.ctypes.data_as(ctypes.c_void_p),
@@ -150,14 +182,14 @@ class Oracle:
         return obs, rew.value, bool(done.value), terms
 
     def batch_reset(self, envs, n, nthreads=0):
-        obs = np.zeros((n, NOBS))
+        obs = np.zeros((n, self.nobs))
         self.lib.orc_batch_reset(self._model, envs, n, obs.ctypes.data_as(ctypes.c_void_p), nthreads)
         return obs
 
     def batch_step(self, envs, n, actions, max_traj_len=400, nthreads=0):
         actions = np.ascontiguousarray(actions, dtype=np.float64)
-        assert actions.shape == (n, NU)
-        obs, tobs, terms = np.zeros((n, NOBS)), np.zeros((n, NOBS)), np.zeros((n, NREW))
+        assert actions.shape == (n, self.nu)
+        obs, tobs, terms = np.zeros((n, self.nobs)), np.zeros((n, self.nobs)), np.zeros((n, NREW))
         rew = np.zeros(n)
         done, ended = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
@@ -168,14 +200,14 @@ class Oracle:
     # ---- building blocks
     def mass_matrix(self, qpos):
         qpos = np.ascontiguousarray(qpos, dtype=np.float64)
-        M = np.zeros((NV, NV))
+        M = np.zeros((self.nv, self.nv))
         self.lib.orc_mass_matrix(self._model, qpos.ctypes.data_as(ctypes.c_void_p), M.ctypes.data_as(ctypes.c_void_p))
         return M
 
     def bias(self, qpos, qvel):
         qpos = np.ascontiguousarray(qpos, dtype=np.float64)
         qvel = np.ascontiguousarray(qvel, dtype=np.float64)
-        c = np.zeros(NV)
+        c = np.zeros(self.nv)
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         self.lib.orc_bias(self._model, p(qpos), p(qvel), p(c))
         return c
@@ -226,6 +258,10 @@ def _layout():
         ("traj_len", 1, "i4"), ("ep_len", 1, "i4"), ("ep_rew", 1, "f8"),
         ("seed", 1, "u4"), ("env_id", 1, "u4"), ("rng_ctr", 1, "u4"), ("last_solver_iter", 1, "i4"),
         ("last_kkt_residual", 1, "f8"), ("status", 1, "i4"), ("nsubsteps", 1, "i4"),
+        # orc_params P, then xfrc[2][6]
+        ("P_mass", MAXLINK, "f8"), ("P_com", MAXLINK * 3, "f8"), ("P_inertia", MAXLINK * 9, "f8"),
+        ("P_damping", NV, "f8"), ("P_frictionloss", NV, "f8"), ("P_pel_mass", 1, "f8"), ("P_pel_com", 3, "f8"),
+        ("xfrc", 12, "f8"),
     ]
     out, off = {}, 0
     for name, cnt, typ in fields:

@@ -154,6 +154,23 @@ int orc_model_from_flat(orc_model* m, const double* b, int n) {
   m->npair = (int)RD();
   if (m->npair > ORC_MAXPAIR) return -6;
   for (int c = 0; c < m->npair; c++) { m->pair[c][0] = (int)RD(); m->pair[c][1] = (int)RD(); }
+  m->task = (int)RD(); m->nobs = (int)RD(); m->done_lo = RD(); m->done_hi = RD();
+  for (int k = 0; k < 5; k++) m->obs_noise[k] = RD();
+  m->dynrand_interval = (int)RD(); m->perturb_interval = (int)RD();
+  m->perturb_force = RD(); m->perturb_torque = RD(); m->init_noise = RD();
+  for (int g = 0; g < m->ngeom; g++) {
+    m->geom_type[g] = (int)RD(); m->geom_npts[g] = (int)RD(); m->geom_radius[g] = RD();
+    if (m->geom_npts[g] > ORC_MAXPTS) return -7;
+    for (int k = 0; k < m->geom_npts[g]; k++)
+      for (int x = 0; x < 3; x++) m->geom_pts[g][k][x] = RD();
+  }
+  m->pel_mass = RD();
+  for (int k = 0; k < 3; k++) m->pel_com[k] = RD();
+  for (int k = 0; k < 9; k++) m->pel_Ic[k] = RD();
+  m->rest_mass = RD();
+  for (int k = 0; k < 3; k++) m->rest_mc[k] = RD();
+  for (int k = 0; k < 9; k++) m->rest_Io[k] = RD();
+  for (int k = 0; k < 3; k++) m->torso_com[k] = RD();
 #undef RD
   return p == n ? 0 : -100 - (p > n);
 }
@@ -180,12 +197,24 @@ void orc_philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t stream, u
 static inline double u01(uint32_t u) { return (double)(u >> 8) * (1.0 / 16777216.0); } /* 24 bit, exact in f32 too */
 static inline int randint(uint32_t u, int n) { return (int)(((uint64_t)u * (uint64_t)n) >> 32); }
 
+static void params_default(const orc_model* m, orc_params* P) {
+  memset(P, 0, sizeof(*P));
+  for (int i = 0; i < m->nlink; i++) {
+    P->mass[i] = m->mass[i];
+    memcpy(P->com[i], m->com[i], sizeof(P->com[i]));
+    memcpy(P->inertia[i], m->inertia[i], sizeof(P->inertia[i]));
+  }
+  for (int d = 0; d < m->nv; d++) P->damping[d] = m->damping[d];
+  P->pel_mass = m->pel_mass;
+  memcpy(P->pel_com, m->pel_com, sizeof(P->pel_com));
+}
+
 /* ------------------------------------------------------------------ kinematics */
 typedef struct {
   double xpos[L][3], xmat[L][9], xaxis[L][3], xcom[L][3], Iw[L][9];
 } kin_t;
 
-static void fk(const orc_model* m, const double* qpos, kin_t* k) {
+static void fk(const orc_model* m, const orc_params* P, const double* qpos, kin_t* k) {
   double q[4] = {qpos[3], qpos[4], qpos[5], qpos[6]};
   double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   for (int i = 0; i < 4; i++) q[i] /= nrm;
@@ -210,9 +239,9 @@ static void fk(const orc_model* m, const double* qpos, kin_t* k) {
       matvec3(k->xmat[i], a, k->xaxis[i]);
     }
     double sc[3], T[9], Rt[9];
-    matvec3(k->xmat[i], m->com[i], sc);
+    matvec3(k->xmat[i], P->com[i], sc);
     for (int c = 0; c < 3; c++) k->xcom[i][c] = k->xpos[i][c] + sc[c];
-    matmul3(k->xmat[i], m->inertia[i], T);
+    matmul3(k->xmat[i], P->inertia[i], T);
     for (int r = 0; r < 3; r++)
       for (int c = 0; c < 3; c++) Rt[3 * r + c] = k->xmat[i][3 * c + r];
     matmul3(T, Rt, k->Iw[i]);
@@ -248,7 +277,7 @@ static void jac_point(const orc_model* m, const kin_t* k, int link, const double
   }
 }
 
-static void mass_matrix_k(const orc_model* m, const kin_t* k, double* M) {
+static void mass_matrix_k(const orc_model* m, const orc_params* P, const kin_t* k, double* M) {
   int nv = m->nv;
   memset(M, 0, NV * NV * sizeof(double));
   double jp[3 * NV], jr[3 * NV], IJ[3 * NV];
@@ -260,7 +289,7 @@ static void mass_matrix_k(const orc_model* m, const kin_t* k, double* M) {
     for (int a = 0; a < nv; a++)
       for (int b = 0; b < nv; b++) {
         double s = 0;
-        for (int c = 0; c < 3; c++) s += m->mass[i] * jp[c * NV + a] * jp[c * NV + b] + jr[c * NV + a] * IJ[c * NV + b];
+        for (int c = 0; c < 3; c++) s += P->mass[i] * jp[c * NV + a] * jp[c * NV + b] + jr[c * NV + a] * IJ[c * NV + b];
         M[a * NV + b] += s;
       }
   }
@@ -268,15 +297,16 @@ static void mass_matrix_k(const orc_model* m, const kin_t* k, double* M) {
 }
 
 void orc_mass_matrix(const orc_model* m, const double* qpos, double* Mout) {
-  kin_t k; double M[NV * NV];
-  fk(m, qpos, &k);
-  mass_matrix_k(m, &k, M);
+  kin_t k; double M[NV * NV]; orc_params P;
+  params_default(m, &P);
+  fk(m, &P, qpos, &k);
+  mass_matrix_k(m, &P, &k, M);
   for (int a = 0; a < m->nv; a++)
     for (int b = 0; b < m->nv; b++) Mout[a * m->nv + b] = M[a * NV + b];
 }
 
 /* qfrc_bias = C(q,v) v + gravity term, by projecting each link's Newton-Euler equation (qacc = 0) on its Jacobians */
-static void bias_k(const orc_model* m, const kin_t* k, const double* qvel, double* c) {
+static void bias_k(const orc_model* m, const orc_params* P, const kin_t* k, const double* qvel, double* c) {
   int nv = m->nv;
   double w[L][3], al[L][3], ao[L][3];
   memset(c, 0, NV * sizeof(double));
@@ -303,7 +333,7 @@ static void bias_k(const orc_model* m, const kin_t* k, const double* qvel, doubl
     cross3(w[i], s, t2);
     cross3(w[i], t2, t2);
     for (int x = 0; x < 3; x++) ac[x] = ao[i][x] + t[x] + t2[x];
-    for (int x = 0; x < 3; x++) F[x] = m->mass[i] * (ac[x] - m->gravity[x]);
+    for (int x = 0; x < 3; x++) F[x] = P->mass[i] * (ac[x] - m->gravity[x]);
     matvec3(k->Iw[i], w[i], Iw_w);
     matvec3(k->Iw[i], al[i], Iw_al);
     cross3(w[i], Iw_w, t);
@@ -315,20 +345,22 @@ static void bias_k(const orc_model* m, const kin_t* k, const double* qvel, doubl
 }
 
 void orc_bias(const orc_model* m, const double* qpos, const double* qvel, double* c) {
-  kin_t k; double cc[NV];
-  fk(m, qpos, &k);
-  bias_k(m, &k, qvel, cc);
+  kin_t k; double cc[NV]; orc_params P;
+  params_default(m, &P);
+  fk(m, &P, qpos, &k);
+  bias_k(m, &P, &k, qvel, cc);
   memcpy(c, cc, m->nv * sizeof(double));
 }
 
 double orc_energy(const orc_model* m, const double* qpos, const double* qvel, double* kinetic, double* potential) {
-  kin_t k; double M[NV * NV];
-  fk(m, qpos, &k);
-  mass_matrix_k(m, &k, M);
+  kin_t k; double M[NV * NV]; orc_params P;
+  params_default(m, &P);
+  fk(m, &P, qpos, &k);
+  mass_matrix_k(m, &P, &k, M);
   double ke = 0, pe = 0;
   for (int a = 0; a < m->nv; a++)
     for (int b = 0; b < m->nv; b++) ke += 0.5 * qvel[a] * M[a * NV + b] * qvel[b];
-  for (int i = 0; i < m->nlink; i++) pe -= m->mass[i] * dot3(m->gravity, k.xcom[i]);
+  for (int i = 0; i < m->nlink; i++) pe -= P.mass[i] * dot3(m->gravity, k.xcom[i]);
   if (kinetic) *kinetic = ke;
   if (potential) *potential = pe;
   return ke + pe;
@@ -339,6 +371,8 @@ typedef struct {
   int nrow, ncon;
   double J[ORC_MAXROW][NV];
   double pos[ORC_MAXROW], D[ORC_MAXROW], aref[ORC_MAXROW], R[ORC_MAXROW];
+  int type[ORC_MAXROW];      /* 0: unilateral (limit / pyramid edge), 1: dof friction loss */
+  double floss[ORC_MAXROW];
   int con_row[ORC_MAXCON], con_geom[ORC_MAXCON];
   double con_pos[ORC_MAXCON][3], con_dist[ORC_MAXCON];
 } efc_t;
@@ -359,7 +393,22 @@ static double impedance(const double* solimp, double pos) {
   return d0 + y * (dw - d0);
 }
 
-static void make_constraints(const orc_model* m, const kin_t* k, const double* qpos, const double* qvel, efc_t* e) {
+/* constraint force and curvature of one row at residual x = J a - aref (MuJoCo PrimalUpdateConstraint):
+ * unilateral: f = -D x for x < 0 else 0 ; friction loss: f = clamp(-D x, -floss, +floss) (quadratic zone |x| < floss/D) */
+static double row_force(const efc_t* e, int r, double x, double* curv) {
+  if (e->type[r] == 0) {
+    *curv = x < 0 ? e->D[r] : 0.0;
+    return x < 0 ? -e->D[r] * x : 0.0;
+  }
+  double lim = e->floss[r] * e->R[r];
+  if (x <= -lim) { *curv = 0; return e->floss[r]; }
+  if (x >= lim) { *curv = 0; return -e->floss[r]; }
+  *curv = e->D[r];
+  return -e->D[r] * x;
+}
+
+static void make_constraints(const orc_model* m, const orc_params* P, const kin_t* k, const double* qpos, const double* qvel,
+                             efc_t* e) {
   int nv = m->nv;
   e->nrow = 0; e->ncon = 0;
   double tau = m->solref[0], zeta = m->solref[1];
@@ -367,6 +416,20 @@ static void make_constraints(const orc_model* m, const kin_t* k, const double* q
   double dmax = m->solimp[1];
   double K = 1.0 / fmax(MINVAL, dmax * dmax * tau * tau * zeta * zeta);
   double B = 2.0 / fmax(MINVAL, dmax * tau);
+  /* dof friction loss (mj_makeConstraint puts these first): J = e_d, pos = 0 -> imp = solimp[0], aref = -B vel */
+  for (int d = 6; d < nv; d++) {
+    if (!(P->frictionloss[d] > 0)) continue;
+    int r = e->nrow++;
+    memset(e->J[r], 0, sizeof(e->J[r]));
+    e->J[r][d] = 1.0;
+    double imp = impedance(m->solimp, 0.0);
+    e->pos[r] = 0;
+    e->type[r] = 1;
+    e->floss[r] = P->frictionloss[d];
+    e->R[r] = fmax(MINVAL, (1 - imp) / imp * m->dof_invweight0[d]);
+    e->D[r] = 1.0 / e->R[r];
+    e->aref[r] = -B * qvel[d];
+  }
   /* joint limits (rows precede contacts, as in mj_makeConstraint) */
   for (int d = 6; d < nv; d++) {
     if (!m->limited[d]) continue;
@@ -380,15 +443,33 @@ static void make_constraints(const orc_model* m, const kin_t* k, const double* q
         double imp = impedance(m->solimp, dist);
         double vel = e->J[r][d] * qvel[d];
         e->pos[r] = dist;
+        e->type[r] = 0; e->floss[r] = 0;
         e->R[r] = fmax(MINVAL, (1 - imp) / imp * m->dof_invweight0[d]);
         e->D[r] = 1.0 / e->R[r];
         e->aref[r] = -B * vel - K * imp * dist;
       }
     }
   }
-  /* foot box vs ground plane z=0, normal +z (mjc_PlaneBox: at most 4 corners, in corner-index order) */
+  /* feet vs ground plane z=0, normal +z.  box: mjc_PlaneBox (at most 4 corners, in corner-index order);
+   * spheres: the end spheres of the foot capsules, mjc_PlaneCapsule = 2 x mjc_PlaneSphere (dist = z - r,
+   * pos = centre - n (r + dist/2)) */
   for (int g = 0; g < m->ngeom; g++) {
     int lk = m->geom_link[g];
+    if (m->geom_type[g] == ORC_GEOM_SPHERES) {
+      for (int i = 0; i < m->geom_npts[g]; i++) {
+        double c[3];
+        matvec3(k->xmat[lk], m->geom_pts[g][i], c);
+        for (int x = 0; x < 3; x++) c[x] += k->xpos[lk][x];
+        double cd = c[2] - m->geom_radius[g];
+        if (!(cd < 0)) continue;
+        int ci = e->ncon++;
+        e->con_geom[ci] = g;
+        e->con_dist[ci] = cd;
+        e->con_pos[ci][0] = c[0]; e->con_pos[ci][1] = c[1];
+        e->con_pos[ci][2] = c[2] - (m->geom_radius[g] + 0.5 * cd);
+      }
+      continue;
+    }
     double off[3], ctr[3];
     matvec3(k->xmat[lk], m->geom_pos[g], off);
     for (int x = 0; x < 3; x++) ctr[x] = k->xpos[lk][x] + off[x];
@@ -433,6 +514,7 @@ static void make_constraints(const orc_model* m, const kin_t* k, const double* q
       }
       for (int d = nv; d < NV; d++) e->J[r][d] = 0;
       e->pos[r] = e->con_dist[ci];
+      e->type[r] = 0; e->floss[r] = 0;
       e->R[r] = Rpy;
       e->D[r] = 1.0 / Rpy;
       e->aref[r] = -B * vel - K * imp * e->con_dist[ci];
@@ -457,7 +539,8 @@ static int solve_newton(const orc_model* m, const double* M, const efc_t* e, con
       double t = -e->aref[r];
       for (int d = 0; d < nv; d++) t += e->J[r][d] * qacc[d];
       jar[r] = t;
-      force[r] = t < 0 ? -e->D[r] * t : 0.0;
+      double cv;
+      force[r] = row_force(e, r, t, &cv);
     }
     gnorm = 0;
     for (int a = 0; a < nv; a++) {
@@ -471,8 +554,11 @@ static int solve_newton(const orc_model* m, const double* M, const efc_t* e, con
     for (int a = 0; a < nv; a++)
       for (int b = 0; b < nv; b++) {
         double t = M[a * NV + b];
-        for (int r = 0; r < nr; r++)
-          if (jar[r] < 0) t += e->D[r] * e->J[r][a] * e->J[r][b];
+        for (int r = 0; r < nr; r++) {
+          double cv;
+          row_force(e, r, jar[r], &cv);
+          if (cv > 0) t += cv * e->J[r][a] * e->J[r][b];
+        }
         H[a * nv + b] = t;
       }
     if (chol(H, nv)) break;
@@ -492,12 +578,19 @@ static int solve_newton(const orc_model* m, const double* M, const efc_t* e, con
       for (int d = 0; d < nv; d++) t += e->J[r][d] * s[d];
       jv[r] = t;
     }
-    double bp[ORC_MAXROW];
+    double bp[2 * ORC_MAXROW];
     int nbp = 0;
     for (int r = 0; r < nr; r++)
       if (jv[r] != 0) {
-        double a0 = -jar[r] / jv[r];
-        if (a0 > 0) bp[nbp++] = a0;
+        if (e->type[r] == 0) {
+          double a0 = -jar[r] / jv[r];
+          if (a0 > 0) bp[nbp++] = a0;
+        } else {
+          double lim = e->floss[r] * e->R[r];
+          double a0 = (-lim - jar[r]) / jv[r], a1 = (lim - jar[r]) / jv[r];
+          if (a0 > 0) bp[nbp++] = a0;
+          if (a1 > 0) bp[nbp++] = a1;
+        }
       }
     for (int i = 1; i < nbp; i++) { /* insertion sort */
       double v = bp[i]; int j = i - 1;
@@ -508,8 +601,8 @@ static int solve_newton(const orc_model* m, const double* M, const efc_t* e, con
   do {                                                                      \
     double _d = (al) * sMs + sg;                                            \
     for (int r = 0; r < nr; r++) {                                          \
-      double x = jar[r] + (al) * jv[r];                                     \
-      if (x < 0) _d += e->D[r] * x * jv[r];                                 \
+      double _cv, _f = row_force(e, r, jar[r] + (al) * jv[r], &_cv);        \
+      _d -= _f * jv[r];                                                     \
     }                                                                       \
     (out) = _d;                                                             \
   } while (0)
@@ -524,8 +617,11 @@ static int solve_newton(const orc_model* m, const double* M, const efc_t* e, con
     }
     if (alpha < 0) { /* beyond the last breakpoint: slope is constant */
       double slope = sMs, mid = lo + 1.0;
-      for (int r = 0; r < nr; r++)
-        if (jar[r] + mid * jv[r] < 0) slope += e->D[r] * jv[r] * jv[r];
+      for (int r = 0; r < nr; r++) {
+        double cv;
+        row_force(e, r, jar[r] + mid * jv[r], &cv);
+        slope += cv * jv[r] * jv[r];
+      }
       alpha = lo - dlo / slope;
     }
 #undef DPHI
@@ -569,7 +665,8 @@ static int solve_pgs(const orc_model* m, const double* M, const efc_t* e, const 
       double res = b[r];
       for (int c = 0; c < nr; c++) res += A[r][c] * force[c];
       double fn = force[r] - res / A[r][r];
-      if (fn < 0) fn = 0;
+      if (e->type[r] == 0) { if (fn < 0) fn = 0; }
+      else { if (fn > e->floss[r]) fn = e->floss[r]; if (fn < -e->floss[r]) fn = -e->floss[r]; }
       change += fabs(fn - force[r]);
       force[r] = fn;
     }
@@ -588,7 +685,8 @@ static int solve_pgs(const orc_model* m, const double* M, const efc_t* e, const 
       for (int r = 0; r < nr; r++) {
         double jr_ = -e->aref[r];
         for (int d = 0; d < nv; d++) jr_ += e->J[r][d] * qacc[d];
-        t -= e->J[r][a] * (jr_ < 0 ? -e->D[r] * jr_ : 0);
+        double cv_;
+        t -= e->J[r][a] * row_force(e, r, jr_, &cv_);
       }
       g2 += t * t;
     }
@@ -647,12 +745,28 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
   kin_t k;
   efc_t efc;
   double M[NV * NV], bias[NV], qfs[NV], force[ORC_MAXROW], qacc[NV];
-  fk(m, e->qpos, &k);
-  mass_matrix_k(m, &k, M);
-  make_constraints(m, &k, e->qpos, e->qvel, &efc);
-  bias_k(m, &k, e->qvel, bias);
-  for (int d = 0; d < nv; d++) qfs[d] = -m->damping[d] * e->qvel[d] - bias[d];
+  const orc_params* P = &e->P;
+  fk(m, P, e->qpos, &k);
+  mass_matrix_k(m, P, &k, M);
+  make_constraints(m, P, &k, e->qpos, e->qvel, &efc);
+  bias_k(m, P, &k, e->qvel, bias);
+  for (int d = 0; d < nv; d++) qfs[d] = -P->damping[d] * e->qvel[d] - bias[d];
   for (int u = 0; u < nu; u++) qfs[6 + u] += ctrl[u]; /* motors, gear 1 */
+  /* xfrc_applied on the pelvis / torso bodies (both welded into the root link): world force f and torque tau at the
+   * body CoM -> generalised force J_com' [f; tau]; only the root dofs see it */
+  for (int b = 0; b < 2; b++) {
+    const double* f = e->xfrc[b];
+    if (f[0] == 0 && f[1] == 0 && f[2] == 0 && f[3] == 0 && f[4] == 0 && f[5] == 0) continue;
+    double rloc[3], r[3], rxf[3];
+    memcpy(rloc, b == 0 ? P->pel_com : m->torso_com, sizeof(rloc));
+    matvec3(k.xmat[0], rloc, r);
+    cross3(r, f, rxf);
+    for (int x = 0; x < 3; x++) qfs[x] += f[x];
+    for (int kk = 0; kk < 3; kk++) {
+      double ax[3] = {k.xmat[0][kk], k.xmat[0][3 + kk], k.xmat[0][6 + kk]};
+      qfs[3 + kk] += ax[0] * (f[3] + rxf[0]) + ax[1] * (f[4] + rxf[1]) + ax[2] * (f[5] + rxf[2]);
+    }
+  }
   memcpy(qacc, e->qacc_warm, sizeof(qacc));
   double kkt = 0;
   if (efc.nrow == 0) {
@@ -696,7 +810,7 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
   e->ncon_r = e->ncon_l = 0;
   e->ncon = efc.ncon;
   e->contact_z_min = 0;
-  e->self_collision = self_collision(m, &k);
+  e->self_collision = m->npair > 0 ? self_collision(m, &k) : 0;
   int first = 1;
   for (int ci = 0; ci < efc.ncon; ci++) {
     const double* f = force + efc.con_row[ci];
@@ -715,12 +829,12 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
     double t = qfs[d];
     for (int r = 0; r < efc.nrow; r++) t += efc.J[r][d] * force[r];
     rhs[d] = t;
-    if (m->damping[d] > 0) any_damp = 1;
+    if (P->damping[d] > 0) any_damp = 1;
   }
   if (efc.nrow == 0) memset(force, 0, sizeof(force));
   if (any_damp) {
     for (int a = 0; a < nv; a++)
-      for (int c = 0; c < nv; c++) G[a * nv + c] = M[a * NV + c] + (a == c ? h * m->damping[a] : 0);
+      for (int c = 0; c < nv; c++) G[a * nv + c] = M[a * NV + c] + (a == c ? h * P->damping[a] : 0);
     chol(G, nv);
     chol_solve(G, nv, rhs);
   } else {
@@ -783,6 +897,21 @@ static void get_obs(const orc_model* m, const orc_env* e, double* obs) {
   for (int x = 0; x < 3; x++) obs[o++] = e->qvel[3 + x];
   for (int u = 0; u < nu; u++) obs[o++] = e->act_len[u];
   for (int u = 0; u < nu; u++) obs[o++] = e->act_vel[u];
+  if (m->task == ORC_TASK_STAND) {
+    /* H1BaseEnv._get_robot_state (envs/h1/h1_base.py:91-117): + motor torques, then uniform observation noise
+     * (base_humanoid_env.py:311-338) drawn as value i -> philox stream 40 + i/4, lane i%4 */
+    for (int u = 0; u < nu; u++) obs[o++] = e->act_force[u];
+    for (int i = 0; i < o; i++) {
+      double sc = i < 2 ? m->obs_noise[0] : i < 5 ? m->obs_noise[1] : i < 5 + nu ? m->obs_noise[2]
+                  : i < 5 + 2 * nu ? m->obs_noise[3] : m->obs_noise[4];
+      if (sc > 0) {
+        uint32_t w[4];
+        orc_philox(e->seed, e->env_id, e->rng_ctr, 40 + (i >> 2), w);
+        obs[i] += -sc + 2 * sc * u01(w[i & 3]);
+      }
+    }
+    return;
+  }
   obs[o++] = sin(2 * M_PI * e->phase / m->period);
   obs[o++] = cos(2 * M_PI * e->phase / m->period);
   /* WalkModes.encode: STANDING [0,0,1], INPLACE [0,1,0], FORWARD [1,0,0] */
@@ -804,6 +933,7 @@ static void sample_ref(orc_env* e, uint32_t stream) {
 
 static void task_reset(const orc_model* m, orc_env* e) {
   uint32_t u[4];
+  if (m->task == ORC_TASK_STAND) return; /* StandingTask.reset is empty (tasks/standing_task.py:33) */
   orc_philox(e->seed, e->env_id, e->rng_ctr, 3, u);
   double c = u01(u[0]);
   e->mode = c < 0.6 ? ORC_STANDING : (c < 0.8 ? ORC_INPLACE : ORC_FORWARD);
@@ -813,6 +943,7 @@ static void task_reset(const orc_model* m, orc_env* e) {
 
 static void task_step(const orc_model* m, orc_env* e) {
   uint32_t u[4];
+  if (m->task == ORC_TASK_STAND) return;
   e->phase += 1;
   if (e->phase >= m->period) e->phase = 0;
   orc_philox(e->seed, e->env_id, e->rng_ctr, 0, u);
@@ -877,9 +1008,85 @@ static void calc_reward(const orc_model* m, const orc_env* e, const double* acti
   t[9] = 0.025 * exp(-5 * ae / nu);
 }
 
+/* StandingTask.calc_reward (tasks/standing_task.py:49-105); 6 terms in dict order, t[6..9] = 0 */
+static void calc_reward_stand(const orc_model* m, const orc_env* e, double* t) {
+  int nu = m->nu;
+  double vloc[3];
+  mattvec3(e->root_xmat, e->root_vlin, vloc);            /* get_body_vel('pelvis', frame=1)[0][:2] */
+  double v2 = vloc[0] * vloc[0] + vloc[1] * vloc[1];
+  t[0] = 0.3 * exp(-4 * v2);
+  t[1] = 0.3 * exp(-4 * e->qvel[5] * e->qvel[5]);
+  double he = e->root_xpos[2] - 0.98;
+  t[2] = 0.1 * exp(-0.5 * he * he);
+  /* torso_link is welded to the pelvis (waist joint removed, envs/h1/h1_env.py:21) at head_in_root */
+  double ub2 = m->head_in_root[0] * m->head_in_root[0] + m->head_in_root[1] * m->head_in_root[1];
+  t[3] = 0.1 * exp(-40 * ub2);
+  double pe = 0, te = 0;
+  for (int u = 0; u < nu; u++) {
+    double d = e->act_len[u] - m->nominal_qpos[7 + u];
+    pe += d * d;
+    te += e->act_force[u] * e->act_force[u];
+  }
+  t[4] = 0.1 * exp(-5e-5 * te);
+  t[5] = 0.1 * exp(-pe);
+  t[6] = t[7] = t[8] = t[9] = 0;
+}
+
+/* randomize_dynamics (envs/common/domain_randomization.py:29-56).  Draw order restated on counter-based streams:
+ * joint j -> stream 16 + j/2, lanes 2(j%2) (frictionloss) and 2(j%2)+1 (damping); body b (pelvis, then the leg
+ * links in joint order) -> stream 21 + b, lane 0 mass scale, lanes 1..3 ipos offset.  body_inertia is not touched. */
+static void randomize_dynamics(const orc_model* m, orc_env* e) {
+  orc_params* P = &e->P;
+  uint32_t w[4];
+  for (int j = 0; j < m->nu; j++) {
+    if ((j & 1) == 0) orc_philox(e->seed, e->env_id, e->rng_ctr, 16 + (j >> 1), w);
+    P->frictionloss[6 + j] = 2.0 * u01(w[2 * (j & 1)]);
+    P->damping[6 + j] = 0.02 + 1.98 * u01(w[2 * (j & 1) + 1]);
+  }
+  for (int b = 0; b <= m->nu; b++) {
+    orc_philox(e->seed, e->env_id, e->rng_ctr, 21 + b, w);
+    double sc = 0.95 + 0.1 * u01(w[0]);
+    double off[3] = {-0.01 + 0.02 * u01(w[1]), -0.01 + 0.02 * u01(w[2]), -0.01 + 0.02 * u01(w[3])};
+    if (b == 0) {
+      P->pel_mass = m->pel_mass * sc;
+      for (int x = 0; x < 3; x++) P->pel_com[x] = m->pel_com[x] + off[x];
+    } else {
+      P->mass[b] = m->mass[b] * sc;
+      for (int x = 0; x < 3; x++) P->com[b][x] = m->com[b][x] + off[x];
+    }
+  }
+  /* root link = pelvis body (+) welded rest: composite mass, com, inertia about the com */
+  double mp = P->pel_mass, M = mp + m->rest_mass, c[3], Io[9];
+  const double* cp = P->pel_com;
+  for (int x = 0; x < 3; x++) c[x] = (mp * cp[x] + m->rest_mc[x]) / M;
+  double cp2 = dot3(cp, cp), c2 = dot3(c, c);
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) {
+      Io[3 * a + b] = m->pel_Ic[3 * a + b] + mp * ((a == b ? cp2 : 0) - cp[a] * cp[b]) + m->rest_Io[3 * a + b];
+      P->inertia[0][3 * a + b] = Io[3 * a + b] - M * ((a == b ? c2 : 0) - c[a] * c[b]);
+    }
+  P->mass[0] = M;
+  memcpy(P->com[0], c, sizeof(c));
+}
+
+/* apply_perturbation (domain_randomization.py:10-26): per body, force U(-F,F)^3, torque U(-T,T)^3, then a coin that
+ * clears the WHOLE xfrc_applied array.  body b -> streams 32+2b (force, lane 3 = coin) and 33+2b (torque) */
+static void apply_perturbation(const orc_model* m, orc_env* e) {
+  uint32_t wf[4], wt[4];
+  for (int b = 0; b < 2; b++) {
+    orc_philox(e->seed, e->env_id, e->rng_ctr, 32 + 2 * b, wf);
+    orc_philox(e->seed, e->env_id, e->rng_ctr, 33 + 2 * b, wt);
+    for (int x = 0; x < 3; x++) {
+      e->xfrc[b][x] = -m->perturb_force + 2 * m->perturb_force * u01(wf[x]);
+      e->xfrc[b][3 + x] = -m->perturb_torque + 2 * m->perturb_torque * u01(wt[x]);
+    }
+    if (randint(wf[3], 2) == 0) memset(e->xfrc, 0, sizeof(e->xfrc));
+  }
+}
+
 void orc_env_init(const orc_model* m, orc_env* e, uint32_t seed, uint32_t env_id) {
-  (void)m;
   memset(e, 0, sizeof(*e));
+  params_default(m, &e->P);
   e->seed = seed;
   e->env_id = env_id;
   e->qpos[3] = 1.0;
@@ -888,11 +1095,28 @@ void orc_env_init(const orc_model* m, orc_env* e, uint32_t seed, uint32_t env_id
 void orc_reset(const orc_model* m, orc_env* e, double* obs) {
   /* mj_resetData (mujoco_env.py:114): qvel, warmstart, ctrl <- 0 ; then reset_model: nominal pose, 3 zero-ctrl steps */
   double zero[ORC_NU] = {0};
+  e->rng_ctr++;
+  memset(e->xfrc, 0, sizeof(e->xfrc));                       /* mj_resetData clears xfrc_applied */
+  if (m->dynrand_interval > 0) randomize_dynamics(m, e);     /* base_humanoid_env.py:252-253 */
   memcpy(e->qpos, m->nominal_qpos, m->nq * sizeof(double));
+  if (m->init_noise > 0) {
+    /* _apply_init_noise (base_humanoid_env.py:281-309): stream 50 lanes 0..2 = height, roll, pitch;
+     * joint j -> stream 51 + j/4 lane j%4.  euler2quat(r, p, 0) 'sxyz' = (cp cr, cp sr, sp cr, -sp sr) */
+    double c = m->init_noise * M_PI / 180.0;
+    uint32_t w[4];
+    orc_philox(e->seed, e->env_id, e->rng_ctr, 50, w);
+    e->qpos[2] = m->nominal_qpos[2] + 0.02 * u01(w[0]);
+    double r = -c + 2 * c * u01(w[1]), p = -c + 2 * c * u01(w[2]);
+    double cr = cos(0.5 * r), sr = sin(0.5 * r), cp = cos(0.5 * p), sp = sin(0.5 * p);
+    e->qpos[3] = cp * cr; e->qpos[4] = cp * sr; e->qpos[5] = sp * cr; e->qpos[6] = -sp * sr;
+    for (int j = 0; j < m->nu; j++) {
+      if ((j & 3) == 0) orc_philox(e->seed, e->env_id, e->rng_ctr, 51 + (j >> 2), w);
+      e->qpos[7 + j] = m->nominal_qpos[7 + j] + (-c + 2 * c * u01(w[j & 3]));
+    }
+  }
   memset(e->qvel, 0, sizeof(e->qvel));
   memset(e->qacc_warm, 0, sizeof(e->qacc_warm));
   for (int i = 0; i < 3; i++) orc_mj_step(m, e, zero);
-  e->rng_ctr++;
   task_reset(m, e);
   memset(e->prev_prediction, 0, sizeof(e->prev_prediction));
   e->traj_len = 0; e->ep_len = 0; e->ep_rew = 0;
@@ -917,12 +1141,20 @@ void orc_step(const orc_model* m, orc_env* e, const double* action, double* obs,
   }
   e->rng_ctr++;
   task_step(m, e);
-  calc_reward(m, e, target, t);
-  int d = (e->qpos[2] < 0.6) || (e->qpos[2] > 1.4) || e->self_collision || e->status;
+  if (m->task == ORC_TASK_STAND) calc_reward_stand(m, e, t);
+  else calc_reward(m, e, target, t);
+  int d = (e->qpos[2] < m->done_lo) || (e->qpos[2] > m->done_hi) || e->self_collision || e->status;
   memcpy(e->prev_action, target, sizeof(target));
   memcpy(e->prev_torque, e->act_force, sizeof(e->prev_torque));
   if (obs) get_obs(m, e, obs);
   memcpy(e->prev_prediction, action, nu * sizeof(double));
+  /* domain randomisation after the observation (base_humanoid_env.py:228-233); decisions on stream 0 lanes 2, 3 */
+  if (m->dynrand_interval > 0 || m->perturb_interval > 0) {
+    uint32_t w[4];
+    orc_philox(e->seed, e->env_id, e->rng_ctr, 0, w);
+    if (m->dynrand_interval > 0 && randint(w[2], m->dynrand_interval) == 0) randomize_dynamics(m, e);
+    if (m->perturb_interval > 0 && randint(w[3], m->perturb_interval) == 0) apply_perturbation(m, e);
+  }
   double sum = 0;
   for (int i = 0; i < ORC_NREW; i++) sum += t[i];
   if (rew_terms) memcpy(rew_terms, t, sizeof(t));
@@ -937,12 +1169,12 @@ void orc_step_autoreset(const orc_model* m, orc_env* e, const double* action, in
   orc_step(m, e, action, o, rew_terms, &r, &d);
   e->traj_len++; e->ep_len++; e->ep_rew += r;
   int end = d || (e->traj_len >= max_traj_len);
-  if (term_obs) memcpy(term_obs, o, sizeof(o));
+  if (term_obs) memcpy(term_obs, o, m->nobs * sizeof(double));
   if (end) {
     e->status = 0;
     orc_reset(m, e, o);
   }
-  if (obs) memcpy(obs, o, sizeof(o));
+  if (obs) memcpy(obs, o, m->nobs * sizeof(double));
   if (reward) *reward = r;
   if (done) *done = d;
   if (ended) *ended = end;
@@ -952,7 +1184,7 @@ void orc_batch_reset(const orc_model* m, orc_env* envs, int n, double* obs, int 
 #ifdef _OPENMP
 #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : omp_get_max_threads()) schedule(static)
 #endif
-  for (int i = 0; i < n; i++) orc_reset(m, envs + i, obs ? obs + (size_t)i * ORC_NOBS : 0);
+  for (int i = 0; i < n; i++) orc_reset(m, envs + i, obs ? obs + (size_t)i * m->nobs : 0);
   (void)nthreads;
 }
 
@@ -963,8 +1195,8 @@ void orc_batch_step_autoreset(const orc_model* m, orc_env* envs, int n, const do
 #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : omp_get_max_threads()) schedule(dynamic, 4)
 #endif
   for (int i = 0; i < n; i++)
-    orc_step_autoreset(m, envs + i, actions + (size_t)i * m->nu, max_traj_len, obs ? obs + (size_t)i * ORC_NOBS : 0,
-                       term_obs ? term_obs + (size_t)i * ORC_NOBS : 0, rew_terms ? rew_terms + (size_t)i * ORC_NREW : 0,
+    orc_step_autoreset(m, envs + i, actions + (size_t)i * m->nu, max_traj_len, obs ? obs + (size_t)i * m->nobs : 0,
+                       term_obs ? term_obs + (size_t)i * m->nobs : 0, rew_terms ? rew_terms + (size_t)i * ORC_NREW : 0,
                        reward ? reward + i : 0, done ? done + i : 0, ended ? ended + i : 0);
   (void)nthreads;
 }

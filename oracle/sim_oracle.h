@@ -29,16 +29,26 @@ extern "C" {
 #define ORC_NQ 19
 #define ORC_NU 12
 #define ORC_MAXGEOM 4
-#define ORC_MAXCON 8
-#define ORC_MAXROW (ORC_NU + 4 * ORC_MAXCON)
+#define ORC_MAXCON 12
+#define ORC_MAXPTS 8
+#define ORC_MAXROW (2 * ORC_NU + 4 * ORC_MAXCON)
 #define ORC_MAXPERIOD 128
 #define ORC_NOBS 37
 #define ORC_NREW 10
-#define ORC_MAXCAP 8
-#define ORC_MAXPAIR 16
+#define ORC_MAXCAP 16
+#define ORC_MAXPAIR 64
 
 enum { ORC_STANDING = 0, ORC_INPLACE = 1, ORC_FORWARD = 2 };
 enum { ORC_SOLVER_NEWTON = 0, ORC_SOLVER_PGS = 1 };
+enum { ORC_TASK_WALK = 0, ORC_TASK_STAND = 1 };
+enum { ORC_GEOM_BOX = 0, ORC_GEOM_SPHERES = 1 };
+
+/* per-environment model parameters (domain randomisation edits these in place, envs/common/domain_randomization.py:29-56) */
+typedef struct {
+  double mass[ORC_MAXLINK], com[ORC_MAXLINK][3], inertia[ORC_MAXLINK][9];
+  double damping[ORC_NV], frictionloss[ORC_NV];
+  double pel_mass, pel_com[3];     /* the pelvis BODY inside the welded root link (xfrc point, composite rebuild) */
+} orc_params;
 
 typedef struct {
   int nlink, nv, nq, nu;
@@ -76,7 +86,17 @@ typedef struct {
   int ncap, npair;
   int cap_link[ORC_MAXCAP];
   double cap_p0[ORC_MAXCAP][3], cap_p1[ORC_MAXCAP][3], cap_r[ORC_MAXCAP];
-  int pair[ORC_MAXPAIR][2];  /* r_frc, r_vel, l_frc, l_vel at integer phases */
+  int pair[ORC_MAXPAIR][2];
+  /* task / robot variants */
+  int task, nobs;
+  double done_lo, done_hi;
+  double obs_noise[5];              /* root_orient, root_ang_vel, motor_pos, motor_vel, motor_tau (0: off) */
+  int dynrand_interval, perturb_interval;
+  double perturb_force, perturb_torque, init_noise;
+  int geom_type[ORC_MAXGEOM], geom_npts[ORC_MAXGEOM];
+  double geom_pts[ORC_MAXGEOM][ORC_MAXPTS][3], geom_radius[ORC_MAXGEOM];
+  /* root link = randomisable pelvis body + welded rest (H1) */
+  double pel_mass, pel_com[3], pel_Ic[9], rest_mass, rest_mc[3], rest_Io[9], torso_com[3];
 } orc_model;
 
 typedef struct {
@@ -108,6 +128,9 @@ typedef struct {
   double last_kkt_residual;
   int status;                      /* nonzero: NaN / divergence seen (mj_checkAcc analogue) */
   int nsubsteps;
+  /* H1 additions (appended so the jvrc field offsets used by the tests stay put) */
+  orc_params P;
+  double xfrc[2][6];               /* world-frame [force, torque] on the pelvis and torso bodies, applied at their CoM */
 } orc_env;
 
 /* fill a model from a flat double array (layout documented in oracle/oracle.py:pack_model) */

@@ -329,6 +329,136 @@ def add_setconst(model):
     ]
 
 
+
+# ==============================================================================================
+# Unitree H1 (envs/h1/gen_xml.py:64-126, envs/h1/h1_env.py:17-33, envs/h1/h1_base.py:38-70,
+# models/mujoco_menagerie/unitree_h1/h1.xml)
+# ==============================================================================================
+H1_LEG_JOINTS = ["left_hip_yaw", "left_hip_roll", "left_hip_pitch", "left_knee", "left_ankle",
+                 "right_hip_yaw", "right_hip_roll", "right_hip_pitch", "right_knee", "right_ankle"]
+
+
+def compile_h1():
+    """H1Env: torso + arm joints removed (unused_joints), jointlimited=False, ctrllimited=False, minimal XML.
+    Post-compile the reference overrides body masses (pelvis 8.89, torso_link 21.289, h1_base.py:40-41) WITHOUT
+    re-running mj_setConst: inertia tensors and *_invweight0 keep their compile-time values."""
+    xml_dir = os.path.join(REF, "models/mujoco_menagerie/unitree_h1")
+    root = ET.parse(os.path.join(xml_dir, "h1.xml")).getroot()
+    cfg = yaml.safe_load(open(os.path.join(REF, "envs/h1/configs/base.yaml")))
+    dflt = root.find("default").find("default")          # class h1
+    assert dflt.attrib["class"] == "h1"
+    jd = dflt.find("joint").attrib
+    j_damping, j_armature = r5(jd["damping"]), r5(jd["armature"])
+    foot_cls = {}
+    for d in dflt.iter("default"):
+        if d.attrib.get("class", "").startswith("foot") and d.find("geom") is not None and "fromto" in d.find("geom").attrib:
+            foot_cls[d.attrib["class"]] = vec(d.find("geom").attrib["fromto"], 6)
+    foot_radius = r5(0.014)
+    keep = set(H1_LEG_JOINTS)
+    mass_override = {"pelvis": 8.89, "torso_link": 21.289}
+    links: list[Link] = []
+    parts = {}      # xml body name -> dict(link, mass0, mass, com (link frame), Ic (link frame))
+    foot_pts = {}
+
+    def walk(body, link_idx, pos_in_link, rot_in_link):
+        name = body.attrib["name"]
+        jel, fj = body.find("joint"), body.find("freejoint")
+        jointed = fj is not None or (jel is not None and jel.attrib["name"] in keep)
+        if jointed:
+            lk = Link(name, link_idx, pos_in_link, rot_in_link)
+            if fj is not None:
+                lk.joint = dict(type="free", name="root")
+            else:
+                lk.joint = dict(type="hinge", name=jel.attrib["name"], axis=vec(jel.attrib["axis"], 3),
+                                armature=r5(jel.attrib.get("armature", j_armature)), damping=r5(jel.attrib.get("damping", j_damping)),
+                                range=vec(jel.attrib["range"], 2), limited=False)   # jointlimited: false (configs/base.yaml)
+            links.append(lk)
+            link_idx = len(links) - 1
+            pos_in_link, rot_in_link = np.zeros(3), np.eye(3)
+        lk = links[link_idx]
+        lk.members[name] = (pos_in_link.copy(), rot_in_link.copy())
+        ine = body.find("inertial")
+        m0 = r5(ine.attrib["mass"])
+        ipos = vec(ine.attrib.get("pos", "0 0 0"), 3)
+        Ri = rot_in_link @ quat2mat(vec(ine.attrib.get("quat", "1 0 0 0"), 4))
+        Ic = Ri @ np.diag(vec(ine.attrib["diaginertia"], 3)) @ Ri.T
+        parts[name] = dict(link=link_idx, mass0=m0, mass=mass_override.get(name, m0), com=pos_in_link + rot_in_link @ ipos, Ic=Ic)
+        for g in body.findall("geom"):
+            c = g.attrib.get("class", "")
+            if c in foot_cls:
+                ft = foot_cls[c]
+                foot_pts.setdefault(link_idx, []).extend([(pos_in_link + rot_in_link @ ft[0:3]).tolist(),
+                                                          (pos_in_link + rot_in_link @ ft[3:6]).tolist()])
+        for child in body.findall("body"):
+            cpos = vec(child.attrib.get("pos", "0 0 0"), 3)
+            crot = quat2mat(vec(child.attrib["quat"], 4)) if "quat" in child.attrib else np.eye(3)
+            walk(child, link_idx, pos_in_link + rot_in_link @ cpos, rot_in_link @ crot)
+
+    pelvis = root.find("worldbody").find("body")
+    assert pelvis.attrib["name"] == "pelvis"
+    qpos0_root = vec(pelvis.attrib["pos"], 3)
+    walk(pelvis, -1, np.zeros(3), np.eye(3))
+    assert [lk.joint["name"] for lk in links[1:]] == H1_LEG_JOINTS
+
+    def assemble(use_override):
+        for lk in links:
+            lk.mass, lk.mc, lk.Io = 0.0, np.zeros(3), np.zeros((3, 3))
+        for nm, pt in parts.items():
+            links[pt["link"]].add_inertial(pt["mass"] if use_override else pt["mass0"], pt["com"], pt["Ic"])
+        out = []
+        for lk in links:
+            c, Ic = lk.finalize()
+            d = dict(name=lk.name, parent=lk.parent, pos=lk.pos.tolist(), rot=lk.rot.tolist(), mass=lk.mass, com=c.tolist(),
+                     inertia=[Ic[0, 0], Ic[1, 1], Ic[2, 2], Ic[0, 1], Ic[0, 2], Ic[1, 2]], members=sorted(lk.members))
+            j = lk.joint
+            d["joint"] = dict(type="free", name="root") if j["type"] == "free" else dict(
+                type="hinge", name=j["name"], axis=j["axis"].tolist(), armature=j["armature"], damping=j["damping"],
+                range=j["range"].tolist(), limited=False)
+            out.append(d)
+        return out
+
+    model = dict(name="h1")
+    model["opt"] = dict(timestep=float(cfg["sim_dt"]), gravity=[0.0, 0.0, -9.81], solver="Newton", iterations=100, tolerance=1e-8,
+                        cone="pyramidal", impratio=1.0, solref=[0.02, 1.0], solimp=[0.9, 0.95, 0.001, 0.5, 2.0],
+                        friction=[1.0, 0.005, 0.0001])
+    model["qpos0"] = qpos0_root.tolist() + [1.0, 0.0, 0.0, 0.0] + [0.0] * 10
+    model["cfg"] = dict(sim_dt=cfg["sim_dt"], control_dt=cfg["control_dt"], frame_skip=int(round(cfg["control_dt"] / cfg["sim_dt"])),
+                        action_smoothing=cfg["action_smoothing"], obs_history_len=cfg["obs_history_len"], init_noise_deg=cfg["init_noise"])
+    # mj_setConst quantities with the COMPILE-TIME masses (the override happens afterwards and does not refresh them)
+    model["links"] = assemble(False)
+    add_setconst(model)
+    frozen = {k: model[k] for k in ("dof_invweight0", "link_invweight0", "meaninertia")}
+    # runtime model: overridden masses
+    model["links"] = assemble(True)
+    model.update(frozen)
+    gains = cfg["pdgains"]
+    model["cfg"].update(kp=[float(gains[j][0]) for j in H1_LEG_JOINTS], kd=[float(gains[j][1]) for j in H1_LEG_JOINTS],
+                        half_sitting_pose=[float(x) for x in cfg["half_sitting_pose"]],
+                        nominal_qpos=[0.0, 0.0, 0.98, 1.0, 0.0, 0.0, 0.0] + [float(x) for x in cfg["half_sitting_pose"]],
+                        observation_noise=cfg["observation_noise"], perturbation=cfg["perturbation"],
+                        dynamics_randomization=cfg["dynamics_randomization"])
+    li = {lk.name: i for i, lk in enumerate(links)}
+    model["lfoot_link"], model["rfoot_link"] = li["left_ankle_link"], li["right_ankle_link"]
+    model["geoms"] = [dict(name=links[l].name + "-feet", type="spheres", link=l, radius=foot_radius, points=foot_pts[l])
+                      for l in (li["left_ankle_link"], li["right_ankle_link"])]
+    model["total_mass"] = float(sum(lk.mass for lk in links))
+    # the root link is pelvis + torso + arms welded; randomize_dynamics (domain_randomization.py:46-56) only touches the
+    # pelvis BODY (mass x U(.95,1.05), ipos + U(+-.01)) and the leg bodies, so keep the pelvis separable from the rest
+    pel = parts["pelvis"]
+    rest_m = sum(p_["mass"] for n_, p_ in parts.items() if p_["link"] == 0 and n_ != "pelvis")
+    rest_mc = sum(p_["mass"] * p_["com"] for n_, p_ in parts.items() if p_["link"] == 0 and n_ != "pelvis")
+    rest_Io = sum(p_["Ic"] + p_["mass"] * (np.dot(p_["com"], p_["com"]) * np.eye(3) - np.outer(p_["com"], p_["com"]))
+                  for n_, p_ in parts.items() if p_["link"] == 0 and n_ != "pelvis")
+    model["root_parts"] = dict(pelvis=dict(mass=pel["mass"], com=pel["com"].tolist(), Ic=pel["Ic"].tolist()),
+                               rest=dict(mass=float(rest_m), mc=np.asarray(rest_mc).tolist(), Io=np.asarray(rest_Io).tolist()),
+                               torso_com=(parts["torso_link"]["com"]).tolist())
+    model["notes"] = ["dof_invweight0 / link_invweight0 / meaninertia evaluated with the XML masses (pelvis 5.39, torso 17.789); "
+                      "dynamics use the overridden ones (8.89, 21.289) with unchanged inertia tensors (h1_base.py:40-41)",
+                      "ground contacts: the 3 foot capsules per foot (6 end spheres, radius 0.014); other collision primitives "
+                      "(legs, torso, arms) only touch the floor after the 0.9 m termination height and are not modelled"]
+    return model
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..",
@@ -337,12 +467,22 @@ def main():
     os.makedirs(args.out, exist_ok=True)
     m = compile_jvrc()
     path = os.path.join(args.out, "jvrc_walk.json")
+    if os.path.exists(path):   # tools/fit_collision_proxies.py adds this block afterwards; keep it across recompiles
+        old = json.load(open(path))
+        if "self_collision" in old:
+            m["self_collision"] = old["self_collision"]
     with open(path, "w") as f:
         json.dump(m, f, indent=1)
     print("wrote", path, "mass", m["total_mass"], "links", len(m["links"]), "meaninertia", m["meaninertia"])
     for lk in m["links"]:
         print(f"  {lk['name']:14s} parent {lk['parent']:2d} mass {lk['mass']:.4f} com {np.round(lk['com'], 4)}")
     print("foot invweight0", m["link_invweight0"][m["rfoot_link"]], "dof_invweight0", np.round(m["dof_invweight0"], 4))
+    h = compile_h1()
+    json.dump(h, open(os.path.join(args.out, "h1.json"), "w"), indent=1)
+    print("wrote h1.json mass", h["total_mass"], "links", len(h["links"]), "meaninertia", h["meaninertia"])
+    for lk in h["links"]:
+        print(f"  {lk['name']:22s} parent {lk['parent']:2d} mass {lk['mass']:.4f} com {np.round(lk['com'], 4)}")
+    print("  foot points", np.round(h["geoms"][0]["points"], 4).tolist())
 
 
 if __name__ == "__main__":
