@@ -28,18 +28,23 @@ const char* lhw_last_error(void);
 /* ---- environment batch --------------------------------------------------------------------------
  * lhw_sim_create: replaces MujocoEnv.__init__ (envs/common/mujoco_env.py:16-36: MjSpec.compile +
  * MjData) and JvrcBaseEnv._setup_robot (envs/jvrc/jvrc_base.py:38-67): takes the compiled model
- * constants as a flat HOST float64 array (layout: learninghumanoidwalking_b200/model/loader.py). */
+ * constants as a flat HOST float64 array (layout: learninghumanoidwalking_b200/model/loader.py).
+ * The first word selects the robot/task variant: 6 = JVRC-1 + WalkingTask (envs/jvrc/jvrc_walk.py),
+ * 5 = Unitree H1 + StandingTask (envs/h1/h1_env.py, envs/h1/h1_base.py:31-63: mass overrides, PD gains,
+ * StandingTask), whose step also runs the observation noise, dynamics randomisation, random pushes and
+ * initial-pose noise of envs/common/base_humanoid_env.py:228-338 + envs/common/domain_randomization.py inside
+ * the kernel (per-env randomised parameters live at the tail of the state record). */
 int lhw_sim_create(lhw_sim** out, const double* model_flat_host, int n_flat, int precision, int device);
 int lhw_sim_destroy(lhw_sim* sim);
 int lhw_sim_state_reals(const lhw_sim* sim); /* real words per env in the state record */
 int lhw_sim_state_ints(const lhw_sim* sim);  /* int32 words per env in the state record */
-int lhw_sim_obs_dim(const lhw_sim* sim);     /* env.observation_space.shape[0] (37 for jvrc_walk) */
-int lhw_sim_act_dim(const lhw_sim* sim);     /* env.action_space.shape[0] (12) */
+int lhw_sim_obs_dim(const lhw_sim* sim);     /* env.observation_space.shape[0] (37 jvrc_walk, 35 h1) */
+int lhw_sim_act_dim(const lhw_sim* sim);     /* env.action_space.shape[0] (12 jvrc_walk, 10 h1) */
 int lhw_sim_smem_bytes_per_env(const lhw_sim* sim);
 
 /* lhw_sim_reset: MujocoEnv.reset + BaseHumanoidEnv.reset_model + WalkingTask.reset
- * (envs/common/mujoco_env.py:113-116, envs/common/base_humanoid_env.py:247-276,
- * tasks/walking_task.py:194-205) for every env whose mask[i] != 0 (mask == NULL: all).
+ * (envs/common/mujoco_env.py:113-116, envs/common/base_humanoid_env.py:247-309,
+ * tasks/walking_task.py:194-205 / tasks/standing_task.py:33) for every env whose mask[i] != 0 (mask == NULL: all).
  * `fresh` != 0 zero-initialises the record first (a newly constructed env).
  * state_r: [n_envs, state_reals] reals; state_i: [n_envs, state_ints] int32; obs: [n_envs, obs_dim]. */
 int lhw_sim_reset(lhw_sim* sim, void* state_r, int32_t* state_i, int n_envs, uint32_t seed, uint32_t first_env_id,
@@ -48,7 +53,7 @@ int lhw_sim_reset(lhw_sim* sim, void* state_r, int32_t* state_i, int n_envs, uin
 /* lhw_sim_step: BaseHumanoidEnv.step (envs/common/base_humanoid_env.py:199-227) ->
  * RobotBase.step/_do_simulation (robots/robot_base.py:41-98) -> frame_skip x {RobotInterface.step_pd,
  * set_motor_torque, mujoco.mj_step} (envs/common/robot_interface.py:493-546) -> WalkingTask.step /
- * calc_reward / done (tasks/walking_task.py:85-192) -> get_obs (base_humanoid_env.py:177-197), for
+ * calc_reward / done (tasks/walking_task.py:85-192; tasks/standing_task.py:49-131 for h1) -> get_obs (base_humanoid_env.py:177-197), for
  * n_envs environments in one launch.  With autoreset != 0 it also does the RolloutWorker's episode
  * bookkeeping (rl/workers/rollout_worker.py:146-176): ended = done || traj_len >= max_traj_len; an ended env
  * is reset inside the same launch and `obs` is the post-reset observation while `term_obs` keeps the
@@ -59,7 +64,7 @@ int lhw_sim_step(lhw_sim* sim, void* state_r, int32_t* state_i, int n_envs, uint
                  const void* actions, int max_traj_len, int autoreset, void* obs, void* term_obs, void* reward,
                  void* rew_terms, int32_t* done, int32_t* ended, int32_t* ep_len, void* ep_rew, void* stream);
 
-/* lhw_sim_bind: make `sim`'s model constants the resident ones (they live in one __constant__ bank per precision,
+/* lhw_sim_bind: make `sim`'s model constants the resident ones (they live in one __constant__ object per (robot, precision),
  * shared by all sims of the process; lhw_sim_step/reset do this implicitly, a replayed CUDA graph cannot). */
 int lhw_sim_bind(lhw_sim* sim, void* stream);
 

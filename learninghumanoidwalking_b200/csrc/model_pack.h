@@ -73,7 +73,7 @@ template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b
   m.fcap = (real)(total_mass * 9.8 * 0.5);  // tasks/rewards.py:129
   m.goal_height = (real)rd();
   m.period = (int)rd();
-  if (m.period < 1 || m.period > MAXPERIOD) return -2;
+  if (m.period < (Cfg<NJ>::STAND ? 0 : 1) || m.period > MAXPERIOD) return -2;
   for (int c = 0; c < 4; c++)
     for (int k = 0; k < m.period; k++) m.clock[c][k] = (real)rd();
   m.ncap = (int)rd();
@@ -87,6 +87,25 @@ template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b
   m.npair = (int)rd();
   if (m.npair < 0 || m.npair > MAXPAIR) return -6;
   for (int c = 0; c < m.npair; c++) { m.pair_a[c] = (unsigned char)rd(); m.pair_b[c] = (unsigned char)rd(); }
+  // task / robot variant tail
+  m.done_lo = (real)rd(); m.done_hi = (real)rd();
+  for (int k = 0; k < 5; k++) m.obs_noise[k] = (real)rd();
+  m.dynrand_interval = (int)rd(); m.perturb_interval = (int)rd();
+  m.perturb_force = (real)rd(); m.perturb_torque = (real)rd(); m.init_noise = (real)rd();
+  for (int f = 0; f < 2; f++) {
+    const int npts = (int)rd();
+    if (npts != (Cfg<NJ>::SPHERES ? Cfg<NJ>::NPTS : 0)) return -7;
+    m.foot_radius[f] = (real)rd();
+    for (int k = 0; k < npts; k++)
+      for (int x = 0; x < 3; x++) m.foot_pts[f][k][x] = (real)rd();
+  }
+  m.pel_mass = (real)rd();
+  for (int k = 0; k < 3; k++) m.pel_com[k] = (real)rd();
+  for (int k = 0; k < 6; k++) m.pel_Ic[k] = (real)rd();
+  m.rest_mass = (real)rd();
+  for (int k = 0; k < 3; k++) m.rest_mc[k] = (real)rd();
+  for (int k = 0; k < 6; k++) m.rest_Io[k] = (real)rd();
+  for (int k = 0; k < 3; k++) m.torso_com[k] = (real)rd();
   if (p != n) return -3;
   return 0;
 }

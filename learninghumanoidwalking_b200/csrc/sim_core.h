@@ -8,6 +8,8 @@
 //   mujoco.mj_step (external)
 //   tasks/walking_task.py:85-205, tasks/rewards.py:9-174, tasks/observations.py:12-72,
 //   envs/jvrc/jvrc_base.py:133-145, envs/jvrc/jvrc_walk.py:65-67
+//   H1 standing variant (Cfg<5>): envs/h1/h1_base.py:91-117, tasks/standing_task.py:49-131,
+//   envs/common/domain_randomization.py:10-56, base_humanoid_env.py:228-233, :247-338
 //
 // Execution model.  Every phase is a `LHW_LANES(l) { ... }` block: on the GPU each of the 32 lanes of the
 // warp runs the body once with its own lane id and `LHW_SYNC()` is __syncwarp(); all inter-lane traffic goes
@@ -55,13 +57,23 @@
 
 namespace lhw {
 
-constexpr int NCON = 8;        // 2 feet x 4 box corners (mjc_PlaneBox returns at most 4)
-constexpr int NEDGE = 32;      // pyramidal condim 3: 4 edges per contact
 constexpr int NREW = 10;
 constexpr int MAXPERIOD = 96;
-constexpr int NSTATE_I = 8;
-constexpr int MAXCAP = 8;       // self-collision capsule proxies
-constexpr int MAXPAIR = 16;    // int32 words per env in the integer state record
+constexpr int NSTATE_I = 8;    // int32 words per env in the integer state record
+constexpr int MAXCAP = 16;     // self-collision capsules
+constexpr int MAXPAIR = 64;
+
+// robot / task variant, keyed by the chain length NJ.  Everything variant-specific below is `if constexpr` on these
+// flags, so each instantiation only carries its own code.
+template <int NJ> struct Cfg;
+template <> struct Cfg<6> {  // JVRC-1, WalkingTask: box feet (mjc_PlaneBox: at most 4 of the 8 corners per foot)
+  static constexpr int CPF = 4, NPTS = 8;
+  static constexpr bool SPHERES = false, FLOSS = false, PERENV = false, STAND = false;
+};
+template <> struct Cfg<5> {  // Unitree H1, StandingTask: 3 capsules per foot = 6 end spheres; dof friction loss;
+  static constexpr int CPF = 6, NPTS = 6;  // per-env randomised mass / com / damping / frictionloss; xfrc perturbations
+  static constexpr bool SPHERES = true, FLOSS = true, PERENV = true, STAND = true;
+};
 
 enum { STANDING = 0, INPLACE = 1, FORWARD = 2 };
 
@@ -122,6 +134,7 @@ template <class real, int NJ> struct Model {
   real mass[NL], com[NL][3], inertia[NL][6];  // xx yy zz xy xz yz about com, link frame
   real armature[NV], damping[NV], range_lo[NV], range_hi[NV], dof_invw[NV];
   real foot_pos[2][3], foot_size[2][3], foot_invw[2];
+  real foot_pts[2][Cfg<NJ>::NPTS][3], foot_radius[2];  // SPHERES: sphere centres in the foot link frame
   real h, grav[3];
   real K, B, solimp[5], mu, mu_reg;  // mu_reg = mu * sqrt(1/impratio)
   real tol2;                         // (tolerance * meaninertia * nv)^2 : threshold on |grad|^2
@@ -132,6 +145,10 @@ template <class real, int NJ> struct Model {
   int ncap, npair, cap_link[MAXCAP];
   real cap_p0[MAXCAP][3], cap_p1[MAXCAP][3], cap_r[MAXCAP];
   unsigned char pair_a[MAXPAIR], pair_b[MAXPAIR];
+  // task / robot variant constants (zero / unused where the variant has no such feature)
+  real done_lo, done_hi, obs_noise[5], perturb_force, perturb_torque, init_noise;  // init_noise in radians
+  int dynrand_interval, perturb_interval;
+  real pel_mass, pel_com[3], pel_Ic[6], rest_mass, rest_mc[3], rest_Io[6], torso_com[3];  // root link = pelvis body + welded rest
   int axis_id[NL];  // 0/1/2: hinge axis is +e_x/+e_y/+e_z of the link frame AND link_rot is the identity (fast FK path); -1: general
 };
 
@@ -147,9 +164,10 @@ template <class real, int NJ> LHW_DEV const Model<real, NJ>& model_ref(const Mod
 
 template <class real, int NJ> struct Dims {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
-  static constexpr int NOBS = 5 + 2 * NU + 8;
+  static constexpr int NOBS = Cfg<NJ>::STAND ? 5 + 3 * NU : 5 + 2 * NU + 8;
   // real-valued state record per env (HBM, env-major so one warp streams its env's record contiguously)
-  static constexpr int NSTATE_R = NQ + NV + NV + 5 * NU + 3 + 1;
+  static constexpr int NPARAM = Cfg<NJ>::PERENV ? NL + 3 * NL + 6 + 2 * NU + 3 + 12 : 0;
+  static constexpr int NSTATE_R = NQ + NV + NV + 5 * NU + 3 + 1 + NPARAM;
 };
 
 // ---------------------------------------------------------------- arrow-packed symmetric matrix
@@ -161,12 +179,28 @@ template <class real, int NJ> struct Arrow {
 };
 
 // ---------------------------------------------------------------- per-warp working set (shared memory)
-template <class real, int NJ> struct Work {
-  static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
-  static constexpr int NOBS = 5 + 2 * NU + 8;
-  // ---- persistent state (mirrors the HBM record, same order)
+// persistent state (mirrors the HBM record, same order); variants with per-env model parameters append them
+template <class real, int NJ> struct Persist {
+  static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ;
   real qpos[NQ], qvel[NV], qacc_warm[NV], act_len[NU], act_vel[NU], prev_pred[NU], prev_action[NU], prev_torque[NU];
   real mode_ref[3], ep_rew;
+};
+template <class real, int NJ> struct PersistRand : Persist<real, NJ> {
+  static constexpr int NL = 1 + 2 * NJ, NU = 2 * NJ;
+  real p_mass[NL], p_com[NL][3], p_inertia0[6];  // link masses / coms; root inertia about its com (xx yy zz xy xz yz)
+  real p_damping[NU], p_floss[NU];
+  real p_pelcom[3];                              // com of the pelvis BODY (point of application of xfrc[0])
+  real xfrc[2][6];                               // world [force, torque] on the pelvis / torso bodies
+};
+template <bool C, class A, class B> struct Select { typedef A type; };
+template <class A, class B> struct Select<false, A, B> { typedef B type; };
+
+template <class real, int NJ>
+struct Work : Select<Cfg<NJ>::PERENV, PersistRand<real, NJ>, Persist<real, NJ>>::type {
+  static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
+  static constexpr int CPF = Cfg<NJ>::CPF, NCON = 2 * CPF, NEDGE = 4 * NCON, NPTS = Cfg<NJ>::NPTS;
+  static constexpr int NOBS = Dims<real, NJ>::NOBS;
+  static constexpr int NFL = Cfg<NJ>::FLOSS ? NU : 1;
   int phase, mode, traj_len, ep_len, have_prev, status;
   uint32_t rng_ctr, env_id;
   // ---- control-step scratch
@@ -185,21 +219,23 @@ template <class real, int NJ> struct Work {
   real earef[NEDGE], ejar[NEDGE];
   int lside[NU];
   real laref[NU], lD[NU], ljar[NU];
+  real fD[NFL], flim[NFL], faref[NFL], fjar[NFL];  // dof friction-loss rows: 1/R, floss * R (half width of the quadratic zone)
   // two scratch groups with disjoint lifetimes share storage: rigid-body quantities live from P2 to P8 (the last
   // reader is qfrc_smooth), the Newton quantities from P9 to P11
   union {
     struct {
       real inert[NL][10], comp[NL][10];
       real A[NL][6], F[NL][6];
-      real ccd[16];   // signed distance of each foot-box corner (8 per foot), > 0: not a contact candidate
+      real ccd[2 * NPTS];   // signed distance of each candidate point (box corner / sphere), > 0: not a candidate
       int cslot[NCON];
     };
     struct {
       real T[2][NA][6], Af[2][6][6], Ff[2][6], ya[2][6], ys[2][6];
       real Pm[NCON][3][6];   // contact-frame point map: rows = unit wrenches of (n, t1, t2) applied at the contact
       real cF[NCON][3], cW[NCON][5];
-      real ejv[NEDGE], ljv[NU];
+      real ejv[NEDGE], ljv[NU], fjv[NFL];
     };
+    real capE[MAXCAP][6];  // self-collision capsule end points; lives where T was (T is dead after the Hessian build)
   };
   // ---- what mj_step leaves behind (pre-integration state of the last substep)
   real root_vlin[3], foot_vel[2][3], grf[2], cz_min, qacc_lag[3];
@@ -471,8 +507,9 @@ template <class real, int NJ> LHW_DEV real arrow_row_dot(const Arrow<real, NJ>& 
 // start (x = qacc, sub = aref, fill = 1) and for the search direction (x = s, sub = 0, fill = 0): one shared copy.
 template <class real, int NJ>
 LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const real* x, real* outM, real (*outY)[6],
-                                 real* e_out, real* l_out, const real* e_sub, const real* l_sub, real fill) {
-  constexpr int NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ;
+                                 real* e_out, real* l_out, real* f_out, const real* e_sub, const real* l_sub,
+                                 const real* f_sub, real fill) {
+  constexpr int NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ, CPF = Cfg<NJ>::CPF, NEDGE = 8 * CPF;
   const Model<real, NJ>& m = model_ref<real, NJ>(m_arg);
   LHW_ASSUME_SHARED(&w); LHW_ASSUME_SHARED(x); LHW_ASSUME_SHARED(outM); LHW_ASSUME_SHARED(outY);
   LHW_ASSUME_SHARED(e_out); LHW_ASSUME_SHARED(l_out);
@@ -489,23 +526,39 @@ LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m_arg
   }
   LHW_SYNC();
   LHW_LANES(l) {
-    const int s = l >> 2, e = l & 3, f = s >> 2;
-    real v = fill;
-    if ((s & 3) < w.ncon[f]) {
-      real u[3];
-      contact_u(w.cpos[s], outY[f], u);
-      v = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)] - (e_sub ? e_sub[l] : (real)0);
+#pragma unroll
+    for (int ed = l; ed < NEDGE; ed += 32) {
+      const int s = ed >> 2, e = ed & 3, f = s / CPF;
+      real v = fill;
+      if (s - f * CPF < w.ncon[f]) {
+        real u[3];
+        contact_u(w.cpos[s], outY[f], u);
+        v = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)] - (e_sub ? e_sub[ed] : (real)0);
+      }
+      e_out[ed] = v;
     }
-    e_out[l] = v;
-    if (l < NU) l_out[l] = w.lside[l] ? w.lside[l] * x[6 + l] - (l_sub ? l_sub[l] : (real)0) : fill;
+    if (l < NU) {
+      l_out[l] = w.lside[l] ? w.lside[l] * x[6 + l] - (l_sub ? l_sub[l] : (real)0) : fill;
+      if constexpr (Cfg<NJ>::FLOSS) f_out[l] = x[6 + l] - (f_sub ? f_sub[l] : (real)0);
+    }
   }
   LHW_SYNC();
+}
+
+// force of a friction-loss row at residual x (MuJoCo PrimalUpdateConstraint): linear inside |x| < floss R, saturated outside
+template <class real> LHW_DEV real floss_force(real D, real lim, real fl, real x, real* curv) {
+  if (x <= -lim) { *curv = 0; return fl; }
+  if (x >= lim) { *curv = 0; return -fl; }
+  *curv = D;
+  return -D * x;
 }
 
 // ================================================================= one physics substep (mujoco.mj_step)
 template <class real, int NJ>
 LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bool last, const int block_sync = 0) {
   constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ;
+  constexpr int CPF = Cfg<NJ>::CPF, NCON = 2 * CPF, NEDGE = 4 * NCON, NPTS = Cfg<NJ>::NPTS;
+  constexpr bool PERENV = Cfg<NJ>::PERENV, FLOSS = Cfg<NJ>::FLOSS;
   LHW_ASSUME_SHARED(&w);
   const Model<real, NJ>& m = model_ref<real, NJ>(m_arg);  // device: the __constant__ object itself (LDC), not a generic reference
   // ---------------- P1 forward kinematics.  (a) sin/cos of all joints side by side + root rotation
@@ -591,10 +644,18 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       const int i = l - (32 - NL);
       const real* R = w.xmat[i];
       real c[3];
-      mv3(R, m.com[i], c);
+      const real* Ib = m.inertia[i];
+      real ms;
+      if constexpr (PERENV) {
+        mv3(R, w.p_com[i], c);
+        ms = w.p_mass[i];
+        if (i == 0) Ib = w.p_inertia0;
+      } else {
+        mv3(R, m.com[i], c);
+        ms = m.mass[i];
+      }
 #pragma unroll
       for (int x = 0; x < 3; x++) c[x] += w.xr[i][x];
-      const real* Ib = m.inertia[i];
       const real B[9] = {Ib[0], Ib[3], Ib[4], Ib[3], Ib[1], Ib[5], Ib[4], Ib[5], Ib[2]};
       real T[9];
 #pragma unroll
@@ -606,7 +667,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
 #pragma unroll
       for (int e = 0; e < 6; e++)
         Iw[e] = T[3 * ri[e]] * R[3 * ci[e]] + T[3 * ri[e] + 1] * R[3 * ci[e] + 1] + T[3 * ri[e] + 2] * R[3 * ci[e] + 2];
-      const real ms = m.mass[i], cc2 = dot3(c, c);
+      const real cc2 = dot3(c, c);
       real* I = w.inert[i];
       I[0] = ms; I[1] = ms * c[0]; I[2] = ms * c[1]; I[3] = ms * c[2];
       I[4] = Iw[0] + ms * (cc2 - c[0] * c[0]); I[5] = Iw[1] + ms * (cc2 - c[1] * c[1]); I[6] = Iw[2] + ms * (cc2 - c[2] * c[2]);
@@ -718,7 +779,14 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         w.F[l][c] = IA[c] + t1[c] + t2[c];
         w.F[l][3 + c] = IA[3 + c] + t3[c];
       }
-    } else if (l >= 16) {
+    } else if (Cfg<NJ>::SPHERES && l >= 16 && l < 16 + 2 * NPTS) {
+      // mjc_PlaneCapsule = two mjc_PlaneSphere: dist = centre height - radius, contact iff dist < 0
+      const int f = (l - 16) / NPTS, i = (l - 16) - f * NPTS, lk = (f + 1) * NJ;
+      const real* R = w.xmat[lk];
+      const real* pt = m.foot_pts[f][i];
+      const real cd = w.o[2] + w.xr[lk][2] + R[6] * pt[0] + R[7] * pt[1] + R[8] * pt[2] - m.foot_radius[f];
+      w.ccd[l - 16] = cd < 0 ? cd : (real)1;
+    } else if (!Cfg<NJ>::SPHERES && l >= 16) {
       // mjc_PlaneBox against the ground plane z = 0 (normal +z): one lane per (foot, corner); a corner is a contact
       // candidate when it is below the plane and on the plane side of the box centre
       const int f = (l - 16) >> 3, i = (l - 16) & 7, lk = (f + 1) * NJ;
@@ -747,25 +815,30 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       const int f = l - 12;
       int cnt = 0;
 #pragma unroll
-      for (int i = 0; i < 8; i++)
-        if (cnt < 4 && !(w.ccd[f * 8 + i] > 0)) { w.cslot[f * 4 + cnt] = i; cnt++; }
+      for (int i = 0; i < NPTS; i++)
+        if (cnt < CPF && !(w.ccd[f * NPTS + i] > 0)) { w.cslot[f * CPF + cnt] = i; cnt++; }
       w.ncon[f] = cnt;
     }
   }
   LHW_SYNC();
   // ---------------- P7b per contact slot: position, impedance, regulariser, reference stiffness (lane = slot)
   LHW_LANES(l) {
-    if (l < NCON && (l & 3) < w.ncon[l >> 2]) {
-      const int f = l >> 2, lk = (f + 1) * NJ, i = w.cslot[l];
-      const real cd = w.ccd[f * 8 + i];
+    if (l < NCON && l - (l / CPF) * CPF < w.ncon[l / CPF]) {
+      const int f = l / CPF, lk = (f + 1) * NJ, i = w.cslot[l];
+      const real cd = w.ccd[f * NPTS + i];
       real v[3], corner[3];
-      v[0] = ((i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0]) + m.foot_pos[f][0];
-      v[1] = ((i & 2) ? m.foot_size[f][1] : -m.foot_size[f][1]) + m.foot_pos[f][1];
-      v[2] = ((i & 4) ? m.foot_size[f][2] : -m.foot_size[f][2]) + m.foot_pos[f][2];
+      if constexpr (Cfg<NJ>::SPHERES) {
+        v[0] = m.foot_pts[f][i][0]; v[1] = m.foot_pts[f][i][1]; v[2] = m.foot_pts[f][i][2];
+      } else {
+        v[0] = ((i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0]) + m.foot_pos[f][0];
+        v[1] = ((i & 2) ? m.foot_size[f][1] : -m.foot_size[f][1]) + m.foot_pos[f][1];
+        v[2] = ((i & 4) ? m.foot_size[f][2] : -m.foot_size[f][2]) + m.foot_pos[f][2];
+      }
       mv3(w.xmat[lk], v, corner);
       w.cpos[l][0] = corner[0] + w.xr[lk][0];
       w.cpos[l][1] = corner[1] + w.xr[lk][1];
-      w.cpos[l][2] = corner[2] + w.xr[lk][2] - (real)0.5 * cd;
+      // contact point: half way through the penetration (box corner), resp. sphere centre - n (r + dist/2)
+      w.cpos[l][2] = corner[2] + w.xr[lk][2] - (Cfg<NJ>::SPHERES ? m.foot_radius[f] + (real)0.5 * cd : (real)0.5 * cd);
       const real imp = impedance(m.solimp, cd);
       const real Rn = m_max((real)1e-15, (1 - imp) / imp * (m.foot_invw[f] * (1 + m.mu * m.mu)));
       w.cD[l] = (real)1 / (2 * m.mu_reg * m.mu_reg * Rn);
@@ -776,13 +849,14 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
   // ---------------- P8 pyramid-edge reference accelerations (lane = edge; foot spatial velocity from P3) ;
   // qfrc_smooth + warm start (lane = dof) ; joint limits (lanes 18..18+NU)
   LHW_LANES(l) {
-    {
-      const int s = l >> 2, e = l & 3, f = s >> 2;
-      if ((s & 3) < w.ncon[f]) {
+#pragma unroll
+    for (int ed = l; ed < NEDGE; ed += 32) {
+      const int s = ed >> 2, e = ed & 3, f = s / CPF;
+      if (s - f * CPF < w.ncon[f]) {
         real u[3];
         contact_u(w.cpos[s], w.V[(f + 1) * NJ], u);
         const real vel = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)];
-        w.earef[l] = -m.B * vel - w.cKid[s];
+        w.earef[ed] = -m.B * vel - w.cKid[s];
       }
     }
     if (l < NV) {
@@ -795,7 +869,27 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
 #pragma unroll
         for (int c = 0; c < 6; c++) Ft[c] = w.F[lk][c];
       }
-      real q = -m.damping[l] * w.qvel[l] - dot6(w.S[l], Ft);
+      real q;
+      if constexpr (PERENV) {
+        q = -(l >= 6 ? w.p_damping[l - 6] : m.damping[l]) * w.qvel[l] - dot6(w.S[l], Ft);
+        if (l < 6) {
+          // xfrc_applied on the pelvis / torso bodies (both inside the root link): J_com' [f; tau], root dofs only
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            const real* fx = w.xfrc[b];
+            if (l < 3) q += fx[l];
+            else {
+              real r[3], rxf[3];
+              mv3(w.xmat[0], b == 0 ? w.p_pelcom : m.torso_com, r);
+              cross(r, fx, rxf);
+              const int k = l - 3;
+              q += w.xmat[0][k] * (fx[3] + rxf[0]) + w.xmat[0][3 + k] * (fx[4] + rxf[1]) + w.xmat[0][6 + k] * (fx[5] + rxf[2]);
+            }
+          }
+        }
+      } else {
+        q = -m.damping[l] * w.qvel[l] - dot6(w.S[l], Ft);
+      }
       if (l >= 6) q += w.ctrl[l - 6];
       w.qfs[l] = q;
       w.qacc[l] = w.qacc_warm[l];
@@ -813,13 +907,21 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         w.lD[u] = (real)1 / m_max((real)1e-15, (1 - imp) / imp * m.dof_invw[d]);
         w.laref[u] = -m.B * (side * w.qvel[d]) - m.K * imp * dist;
       }
+      if constexpr (FLOSS) {
+        // dof friction loss: J = e_d, pos = 0 -> impedance solimp[0], aref = -B vel
+        const real imp = m.solimp[0];
+        const real Rf = m_max((real)1e-15, (1 - imp) / imp * m.dof_invw[d]);
+        w.fD[u] = (real)1 / Rf;
+        w.flim[u] = w.p_floss[u] * Rf;
+        w.faref[u] = -m.B * w.qvel[d];
+      }
     }
   }
   LHW_SYNC();
   LHW_BLOCK_SYNC(block_sync & 2);  // optional second rendez-vous of the block's warps, before the solver
   // ---------------- P9 Newton start: contact point maps Pm, then Ma = M a, ya = S_foot a and the row residuals
   LHW_LANES(l) {
-    if (l < NCON && (l & 3) < w.ncon[l >> 2]) {
+    if (l < NCON && l - (l / CPF) * CPF < w.ncon[l / CPF]) {
       // rows of P: spatial wrench [p x e ; e] of a unit force along e = n (+z), t1 (+y), t2 (-x) applied at p
       const real px = w.cpos[l][0], py = w.cpos[l][1], pz = w.cpos[l][2];
       real* P = &w.Pm[l][0][0];
@@ -828,7 +930,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       P[12] = 0;  P[13] = -pz; P[14] = py; P[15] = -1; P[16] = 0; P[17] = 0;
     }
   }
-  constraint_images<real, NJ>(w, m, w.qacc, w.Ma, w.ya, w.ejar, w.ljar, w.earef, w.laref, (real)1);
+  constraint_images<real, NJ>(w, m, w.qacc, w.Ma, w.ya, w.ejar, w.ljar, w.fjar, w.earef, w.laref, w.faref, (real)1);
 
   // ---------------- P10 primal Newton on  1/2 (a-a_s)' M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
   // residuals (Ma, ejar, ljar) are carried incrementally: x += alpha * (direction image)
@@ -837,7 +939,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
     // (a) per contact: force in the contact frame and the 3x3 weight  W = sum_active D w w'  (lane = contact);
     // active set = sign of the carried residuals (inactive slots carry jar = 1)
     LHW_LANES(l) {
-      if (l < NCON && (l & 3) < w.ncon[l >> 2]) {
+      if (l < NCON && l - (l / CPF) * CPF < w.ncon[l / CPF]) {
         const real* jr = w.ejar + 4 * l;
         const real D = w.cD[l], mu = m.mu;
         const int a0 = jr[0] < 0, a1 = jr[1] < 0, a2 = jr[2] < 0, a3 = jr[3] < 0;
@@ -860,8 +962,8 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         const int f = l / 6, a = l - f * 6;
         real acc = 0;
         for (int k = 0; k < w.ncon[f]; k++) {
-          const real* P = &w.Pm[f * 4 + k][0][0];
-          const real* cf = w.cF[f * 4 + k];
+          const real* P = &w.Pm[f * CPF + k][0][0];
+          const real* cf = w.cF[f * CPF + k];
           acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
         }
         w.Ff[f][a] = acc;
@@ -876,6 +978,10 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         else {
           g -= dot6(w.S[l], w.Ff[(l - 6) / NJ]);
           if (w.lside[l - 6] && w.ljar[l - 6] < 0) g -= w.lside[l - 6] * (-w.lD[l - 6] * w.ljar[l - 6]);
+          if constexpr (FLOSS) {
+            real cv;
+            g -= floss_force(w.fD[l - 6], w.flim[l - 6], w.p_floss[l - 6], w.fjar[l - 6], &cv);
+          }
         }
         w.grad[l] = g;
         w.sdir[l] = -g;
@@ -893,7 +999,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         const int b = t;
         real acc = 0;
         for (int k = 0; k < w.ncon[f]; k++) {
-          const int s = f * 4 + k;
+          const int s = f * CPF + k;
           const real* P = &w.Pm[s][0][0];
           const real* W = w.cW[s];
           const real a0 = P[a], a1 = P[6 + a], a2 = P[12 + a], b0 = P[b], b1 = P[6 + b], b2 = P[12 + b];
@@ -933,6 +1039,12 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
           while (t > k) { t -= k + 1; k++; }
           real acc = w.M.c[ch][k][t] + dot6(w.S[6 + ch * NJ + k], w.T[ch][6 + t]);
           if (k == t && w.lside[ch * NJ + k] && w.ljar[ch * NJ + k] < 0) acc += w.lD[ch * NJ + k];
+          if constexpr (FLOSS) {
+            if (k == t) {
+              const real xj = w.fjar[ch * NJ + k], lim = w.flim[ch * NJ + k];
+              if (xj > -lim && xj < lim) acc += w.fD[ch * NJ + k];
+            }
+          }
           w.H.c[ch][k][t] = acc;
         }
       }
@@ -940,7 +1052,8 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
     LHW_SYNC();
     arrow_factor_solve<real, NJ>(w, w.sdir);
     // (g) images of the search direction: M s, foot spatial accelerations, edge / limit rates
-    constraint_images<real, NJ>(w, m, w.sdir, w.Ms, w.ys, w.ejv, w.ljv, (const real*)nullptr, (const real*)nullptr, (real)0);
+    constraint_images<real, NJ>(w, m, w.sdir, w.Ms, w.ys, w.ejv, w.ljv, w.fjv, (const real*)nullptr, (const real*)nullptr,
+                                (const real*)nullptr, (real)0);
     const real sMs = warp_sum<real>([&](int l) { return l < NV ? w.sdir[l] * w.Ms[l] : (real)0; });
     const real sg = warp_sum<real>([&](int l) { return l < NV ? w.sdir[l] * (w.Ma[l] - w.qfs[l]) : (real)0; });
     // (h) exact line search: phi'(alpha) is continuous, piecewise linear, increasing; safeguarded 1-D Newton
@@ -950,11 +1063,18 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       const real al = ls == 0 ? (real)0 : alpha;
       const real cd = warp_sum<real>([&](int l) {
         real acc = 0;
-        const real x = w.ejar[l] + al * w.ejv[l];   // inactive slots: jar = 1, jv = 0
-        if (x < 0) acc += w.cD[l >> 2] * x * w.ejv[l];
+#pragma unroll
+        for (int ed = l; ed < NEDGE; ed += 32) {
+          const real x = w.ejar[ed] + al * w.ejv[ed];   // inactive slots: jar = 1, jv = 0
+          if (x < 0) acc += w.cD[ed >> 2] * x * w.ejv[ed];
+        }
         if (l < NU) {
           const real xl = w.ljar[l] + al * w.ljv[l];
           if (xl < 0) acc += w.lD[l] * xl * w.ljv[l];
+          if constexpr (FLOSS) {
+            real cv;
+            acc -= floss_force(w.fD[l], w.flim[l], w.p_floss[l], w.fjar[l] + al * w.fjv[l], &cv) * w.fjv[l];
+          }
         }
         return acc;
       });
@@ -967,8 +1087,17 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       if (m_abs(d) <= LS_TOL * m_abs(d_at0)) break;
       const real cdd = warp_sum<real>([&](int l) {
         real acc = 0;
-        if (w.ejar[l] + al * w.ejv[l] < 0) acc += w.cD[l >> 2] * w.ejv[l] * w.ejv[l];
+#pragma unroll
+        for (int ed = l; ed < NEDGE; ed += 32)
+          if (w.ejar[ed] + al * w.ejv[ed] < 0) acc += w.cD[ed >> 2] * w.ejv[ed] * w.ejv[ed];
         if (l < NU && w.ljar[l] + al * w.ljv[l] < 0) acc += w.lD[l] * w.ljv[l] * w.ljv[l];
+        if constexpr (FLOSS) {
+          if (l < NU) {
+            real cv;
+            floss_force(w.fD[l], w.flim[l], w.p_floss[l], w.fjar[l] + al * w.fjv[l], &cv);
+            acc += cv * w.fjv[l] * w.fjv[l];
+          }
+        }
         return acc;
       });
       if (d < 0) lo = al; else hi = al;
@@ -982,8 +1111,12 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         w.qacc[l] += alpha * w.sdir[l];
         w.Ma[l] += alpha * w.Ms[l];
       }
-      w.ejar[l] += alpha * w.ejv[l];
-      if (l < NU) w.ljar[l] += alpha * w.ljv[l];
+#pragma unroll
+      for (int ed = l; ed < NEDGE; ed += 32) w.ejar[ed] += alpha * w.ejv[ed];
+      if (l < NU) {
+        w.ljar[l] += alpha * w.ljv[l];
+        if constexpr (FLOSS) w.fjar[l] += alpha * w.fjv[l];
+      }
       if (l == 31) w.iters_total++;
     }
     LHW_SYNC();
@@ -1007,7 +1140,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
 #pragma unroll
         for (int c = 0; c < 3; c++) w.foot_vel[f][c] = w.V[lk][3 + c] + t[c];
         for (int k = 0; k < w.ncon[f]; k++) {
-          const real* cf = w.cF[f * 4 + k];
+          const real* cf = w.cF[f * CPF + k];
           g += m_sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]);  // norm of mj_contactForce, friction included
         }
         w.grf[f] = g;
@@ -1016,7 +1149,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         real z = 0;
         bool first = true;
         for (int s = 0; s < NCON; s++)
-          if ((s & 3) < w.ncon[s >> 2]) {
+          if (s - (s / CPF) * CPF < w.ncon[s / CPF]) {
             const real cz = w.o[2] + w.cpos[s][2];
             if (first || cz < z) z = cz;
             first = false;
@@ -1027,10 +1160,12 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
     // rhs of the implicit-damping solve: qfrc_smooth + J' f = M a - grad
     if (l < NV) w.vec[l] = w.Ma[l] - w.grad[l];
     if (last) {
-      // self-collision proxies: capsule end points (rel. o) into the T scratch (dead after the Hessian build)
-      if (l >= 22 && l < 22 + m.ncap) {
-        const int c = l - 22, lk = m.cap_link[c];
-        real* E = &w.T[0][0][0] + 6 * c;
+      // self-collision capsules: end points relative to o
+      // lanes 22..31 take capsules 0..9 (the dof lanes are busy above), lanes 0..5 the rest
+      const int c = l >= 22 ? l - 22 : (l < MAXCAP - 10 ? l + 10 : MAXCAP);
+      if (c < m.ncap) {
+        const int lk = m.cap_link[c];
+        real* E = w.capE[c];
         real t[3];
         mv3(w.xmat[lk], m.cap_p0[c], t);
 #pragma unroll
@@ -1045,10 +1180,10 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
   LHW_SYNC();
   if (last && m.npair > 0) {
     LHW_LANES(l) {
-      if (l < m.npair) {
-        const int a = m.pair_a[l], b = m.pair_b[l];
-        const real* Ea = &w.T[0][0][0] + 6 * a;
-        const real* Eb = &w.T[0][0][0] + 6 * b;
+      for (int pi = l; pi < m.npair; pi += 32) {
+        const int a = m.pair_a[pi], b = m.pair_b[pi];
+        const real* Ea = w.capE[a];
+        const real* Eb = w.capE[b];
         const real rr = m.cap_r[a] + m.cap_r[b];
         if (seg_seg_dist2(Ea, Ea + 3, Eb, Eb + 3) < rr * rr) w.selfcol = 1;
       }
@@ -1056,7 +1191,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
     LHW_SYNC();
   }
   // ---------------- P12 mj_Euler: (M + h diag(damping)) a' = qfrc_smooth + qfrc_constraint ; integrate
-  if (m.any_damping) {
+  if (PERENV || m.any_damping) {
     LHW_LANES(l) {
       constexpr int NW = (int)(sizeof(Arrow<real, NJ>) / sizeof(real));
       const real* src = &w.M.r[0][0];
@@ -1066,7 +1201,11 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
     LHW_SYNC();
     LHW_LANES(l) {
       if (l < 6) w.H.r[l][l] += m.h * m.damping[l];
-      else if (l < NV) { const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ; w.H.c[ch][k][k] += m.h * m.damping[l]; }
+      else if (l < NV) {
+        const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ;
+        if constexpr (PERENV) w.H.c[ch][k][k] += m.h * w.p_damping[l - 6];
+        else w.H.c[ch][k][k] += m.h * m.damping[l];
+      }
     }
     LHW_SYNC();
     arrow_factor_solve<real, NJ>(w, w.vec);
@@ -1157,7 +1296,8 @@ template <class real, int NJ> LHW_DEV void sample_ref(Work<real, NJ>& w, uint32_
 }
 
 // observation (envs/jvrc/jvrc_base.py:133-145 + jvrc_walk.py:65-67): current qpos quat / qvel, LAGGED actuator state
-template <class real, int NJ> LHW_DEV void env_obs(Work<real, NJ>& w, const Model<real, NJ>& m) {
+template <class real, int NJ> LHW_DEV void env_obs(Work<real, NJ>& w, const Model<real, NJ>& m, uint32_t seed) {
+  (void)seed;
   constexpr int NU = 2 * NJ;
   LHW_LANES(l) {
     if (l == 0) {  // transforms3d quat2euler (sxyz) roll, pitch via quat2mat
@@ -1175,46 +1315,179 @@ template <class real, int NJ> LHW_DEV void env_obs(Work<real, NJ>& w, const Mode
       w.obs[1] = m_atan2(-M20, cy);
     } else if (l < 4) {
       w.obs[1 + l] = w.qvel[2 + l];
-    } else if (l == 4) {
+    } else if (!Cfg<NJ>::STAND && l == 4) {
       real sn, cs;
       m_sincos((real)(2 * M_PI) * w.phase / m.period, &sn, &cs);
       w.obs[5 + 2 * NU] = sn; w.obs[6 + 2 * NU] = cs;
-    } else if (l == 5) {
+    } else if (!Cfg<NJ>::STAND && l == 5) {
       real* e = w.obs + 7 + 2 * NU;
       e[0] = w.mode == FORWARD; e[1] = w.mode == INPLACE; e[2] = w.mode == STANDING;
       e[3] = w.mode_ref[0]; e[4] = w.mode_ref[1]; e[5] = w.mode_ref[2];
     } else if (l >= 8 && l < 8 + NU) {
       w.obs[5 + l - 8] = w.act_len[l - 8];
       w.obs[5 + NU + l - 8] = w.act_vel[l - 8];
+      if constexpr (Cfg<NJ>::STAND) w.obs[5 + 2 * NU + l - 8] = w.act_force[l - 8];   // motor torques (h1_base.py:97)
     }
   }
   LHW_SYNC();
+  if constexpr (Cfg<NJ>::STAND) {
+    // uniform observation noise (base_humanoid_env.py:311-338): value i -> philox stream 40 + i/4, lane i%4
+    constexpr int NOBS = Dims<real, NJ>::NOBS;
+    LHW_LANES(l) {
+      for (int i = l; i < NOBS; i += 32) {
+        const real sc = i < 2 ? m.obs_noise[0] : i < 5 ? m.obs_noise[1] : i < 5 + NU ? m.obs_noise[2]
+                        : i < 5 + 2 * NU ? m.obs_noise[3] : m.obs_noise[4];
+        if (sc > 0) {
+          uint32_t u[4];
+          philox(seed, w.env_id, w.rng_ctr, 40 + (i >> 2), u);
+          w.obs[i] += -sc + 2 * sc * u01<real>(u[i & 3]);
+        }
+      }
+    }
+    LHW_SYNC();
+  }
+}
+
+// randomize_dynamics (envs/common/domain_randomization.py:29-56) on counter-based streams: joint j -> stream 16 + j/2,
+// lanes 2(j%2) (frictionloss U(0,2)) and 2(j%2)+1 (damping U(0.02,2)); body b (pelvis, then the leg links) -> stream 21+b,
+// lane 0 mass scale U(0.95,1.05), lanes 1..3 ipos offset U(-0.01,0.01).  body_inertia is left alone, as in the reference.
+template <class real, int NJ> LHW_DEV void env_randomize(Work<real, NJ>& w, const Model<real, NJ>& m, uint32_t seed) {
+  if constexpr (Cfg<NJ>::PERENV) {
+    constexpr int NU = 2 * NJ;
+    LHW_LANES(l) {
+      if (l < NU) {
+        uint32_t u[4];
+        philox(seed, w.env_id, w.rng_ctr, 16 + (l >> 1), u);
+        w.p_floss[l] = (real)2 * u01<real>(u[2 * (l & 1)]);
+        w.p_damping[l] = (real)0.02 + (real)1.98 * u01<real>(u[2 * (l & 1) + 1]);
+      } else if (l >= 16 && l <= 16 + NU) {
+        const int b = l - 16;
+        uint32_t u[4];
+        philox(seed, w.env_id, w.rng_ctr, 21 + b, u);
+        const real sc = (real)0.95 + (real)0.1 * u01<real>(u[0]);
+        if (b == 0) {
+          // root link = pelvis body (+) welded rest: composite mass, com, inertia about the com
+          real cp[3];
+#pragma unroll
+          for (int x = 0; x < 3; x++) { cp[x] = m.pel_com[x] + ((real)-0.01 + (real)0.02 * u01<real>(u[1 + x])); w.p_pelcom[x] = cp[x]; }
+          const real mp = m.pel_mass * sc, M = mp + m.rest_mass;
+          real c[3];
+#pragma unroll
+          for (int x = 0; x < 3; x++) c[x] = (mp * cp[x] + m.rest_mc[x]) / M;
+          const real cp2 = dot3(cp, cp), c2 = dot3(c, c);
+          const int ra[6] = {0, 1, 2, 0, 0, 1}, rb[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+          for (int e = 0; e < 6; e++) {
+            const int a = ra[e], bb = rb[e];
+            const real Io = m.pel_Ic[e] + mp * ((a == bb ? cp2 : (real)0) - cp[a] * cp[bb]) + m.rest_Io[e];
+            w.p_inertia0[e] = Io - M * ((a == bb ? c2 : (real)0) - c[a] * c[bb]);
+          }
+          w.p_mass[0] = M;
+#pragma unroll
+          for (int x = 0; x < 3; x++) w.p_com[0][x] = c[x];
+        } else {
+          w.p_mass[b] = m.mass[b] * sc;
+#pragma unroll
+          for (int x = 0; x < 3; x++) w.p_com[b][x] = m.com[b][x] + ((real)-0.01 + (real)0.02 * u01<real>(u[1 + x]));
+        }
+      }
+    }
+    LHW_SYNC();
+  }
+}
+
+// apply_perturbation (domain_randomization.py:10-26): per body force U(-F,F)^3, torque U(-T,T)^3, then a coin that clears
+// the WHOLE xfrc_applied array.  body b -> streams 32+2b (force, lane 3 = coin) and 33+2b (torque)
+template <class real, int NJ> LHW_DEV void env_perturb(Work<real, NJ>& w, const Model<real, NJ>& m, uint32_t seed) {
+  if constexpr (Cfg<NJ>::PERENV) {
+    LHW_LANES(l) {
+      if (l == 0) {
+#pragma unroll 1
+        for (int b = 0; b < 2; b++) {
+          uint32_t uf[4], ut[4];
+          philox(seed, w.env_id, w.rng_ctr, 32 + 2 * b, uf);
+          philox(seed, w.env_id, w.rng_ctr, 33 + 2 * b, ut);
+          for (int x = 0; x < 3; x++) {
+            w.xfrc[b][x] = -m.perturb_force + 2 * m.perturb_force * u01<real>(uf[x]);
+            w.xfrc[b][3 + x] = -m.perturb_torque + 2 * m.perturb_torque * u01<real>(ut[x]);
+          }
+          if (randint(uf[3], 2) == 0)
+            for (int x = 0; x < 12; x++) (&w.xfrc[0][0])[x] = 0;
+        }
+      }
+    }
+    LHW_SYNC();
+  }
 }
 
 // MujocoEnv.reset + BaseHumanoidEnv.reset_model + WalkingTask.reset
 template <class real, int NJ> LHW_DEV void env_reset(Work<real, NJ>& w, const Model<real, NJ>& m, uint32_t seed) {
   constexpr int NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ;
   LHW_LANES(l) {
+    if (l == 0) w.rng_ctr++;
     if (l < NQ) w.qpos[l] = m.nominal[l];
     if (l < NV) { w.qvel[l] = 0; w.qacc_warm[l] = 0; }
     if (l < NU) { w.ctrl[l] = 0; w.prev_pred[l] = 0; }
+    if constexpr (Cfg<NJ>::PERENV) {
+      if (l >= 20) (&w.xfrc[0][0])[l - 20] = 0;   // mj_resetData clears xfrc_applied
+    }
   }
   LHW_SYNC();
+  if constexpr (Cfg<NJ>::PERENV) {
+    if (m.dynrand_interval > 0) env_randomize<real, NJ>(w, m, seed);   // base_humanoid_env.py:252-253
+    else {
+      // randomisation disabled: the per-env parameter block is just the nominal model
+      LHW_LANES(l) {
+        if (l < 1 + NU) {
+          w.p_mass[l] = m.mass[l];
+          for (int x = 0; x < 3; x++) w.p_com[l][x] = m.com[l][x];
+        }
+        if (l < NU) { w.p_damping[l] = m.damping[6 + l]; w.p_floss[l] = 0; }
+        if (l < 6) w.p_inertia0[l] = m.inertia[0][l];
+        if (l < 3) w.p_pelcom[l] = m.pel_com[l];
+      }
+      LHW_SYNC();
+    }
+    if (m.init_noise > 0) {
+      // _apply_init_noise (base_humanoid_env.py:281-309): stream 50 lanes 0..2 = height, roll, pitch; joint j -> stream
+      // 51 + j/4 lane j%4.  euler2quat(r, p, 0) 'sxyz' = (cp cr, cp sr, sp cr, -sp sr)
+      const real c = m.init_noise;
+      LHW_LANES(l) {
+        if (l == 0) {
+          uint32_t u[4];
+          philox(seed, w.env_id, w.rng_ctr, 50, u);
+          w.qpos[2] = m.nominal[2] + (real)0.02 * u01<real>(u[0]);
+          const real r = -c + 2 * c * u01<real>(u[1]), p = -c + 2 * c * u01<real>(u[2]);
+          real sr, cr, sp, cp;
+          m_sincos((real)0.5 * r, &sr, &cr);
+          m_sincos((real)0.5 * p, &sp, &cp);
+          w.qpos[3] = cp * cr; w.qpos[4] = cp * sr; w.qpos[5] = sp * cr; w.qpos[6] = -sp * sr;
+        } else if (l >= 8 && l < 8 + NU) {
+          const int j = l - 8;
+          uint32_t u[4];
+          philox(seed, w.env_id, w.rng_ctr, 51 + (j >> 2), u);
+          w.qpos[7 + j] = m.nominal[7 + j] + (-c + 2 * c * u01<real>(u[j & 3]));
+        }
+      }
+      LHW_SYNC();
+    }
+  }
   for (int i = 0; i < 3; i++) substep<real, NJ>(w, m, false);
   LHW_LANES(l) {
     if (l == 0) {
-      w.rng_ctr++;
-      uint32_t u[4];
-      philox(seed, w.env_id, w.rng_ctr, 3, u);
-      const real c = u01<real>(u[0]);
-      w.mode = c < (real)0.6 ? STANDING : (c < (real)0.8 ? INPLACE : FORWARD);
-      sample_ref<real, NJ>(w, seed, 4);
-      w.phase = randint(u[1], m.period);
+      if constexpr (!Cfg<NJ>::STAND) {
+        uint32_t u[4];
+        philox(seed, w.env_id, w.rng_ctr, 3, u);
+        const real c = u01<real>(u[0]);
+        w.mode = c < (real)0.6 ? STANDING : (c < (real)0.8 ? INPLACE : FORWARD);
+        sample_ref<real, NJ>(w, seed, 4);
+        w.phase = randint(u[1], m.period);
+      }
       w.traj_len = 0; w.ep_len = 0; w.ep_rew = 0; w.status = 0;
     }
   }
   LHW_SYNC();
-  env_obs<real, NJ>(w, m);
+  env_obs<real, NJ>(w, m, seed);
 }
 
 struct StepOut {
@@ -1252,6 +1525,8 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
     if (l == 0) {
       w.have_prev = 1;
       w.rng_ctr++;
+    }
+    if (!Cfg<NJ>::STAND && l == 0) {
       w.phase += 1;
       if (w.phase >= m.period) w.phase = 0;
       uint32_t u[4];
@@ -1271,6 +1546,36 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
   }
   LHW_SYNC();
   // WalkingTask.calc_reward (tasks/walking_task.py:85-147, tasks/rewards.py), lane = term
+  if constexpr (Cfg<NJ>::STAND) {
+    // StandingTask.calc_reward (tasks/standing_task.py:49-105), lane = term (6 terms, the rest 0)
+    LHW_LANES(l) {
+      if (l < NREW) {
+        real r = 0;
+        if (l == 0) {
+          const real* R = w.xmat[0];
+          const real* v = w.root_vlin;
+          const real vx = R[0] * v[0] + R[3] * v[1] + R[6] * v[2], vy = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+          r = (real)0.3 * m_exp(-4 * (vx * vx + vy * vy));
+        } else if (l == 1) {
+          r = (real)0.3 * m_exp(-4 * w.qvel[5] * w.qvel[5]);
+        } else if (l == 2) {
+          const real he = w.o[2] - (real)0.98;
+          r = (real)0.1 * m_exp((real)-0.5 * he * he);
+        } else if (l == 3) {
+          r = (real)0.1 * m_exp(-40 * (m.head[0] * m.head[0] + m.head[1] * m.head[1]));  // torso welded to the pelvis
+        } else if (l == 4) {
+          real te = 0;
+          for (int u = 0; u < NU; u++) te += w.act_force[u] * w.act_force[u];
+          r = (real)0.1 * m_exp((real)-5e-5 * te);
+        } else if (l == 5) {
+          real pe = 0;
+          for (int u = 0; u < NU; u++) { const real d = w.act_len[u] - m.nominal[7 + u]; pe += d * d; }
+          r = (real)0.1 * m_exp(-pe);
+        }
+        w.rew[l] = r;
+      }
+    }
+  } else
   LHW_LANES(l) {
     if (l < NREW) {
       real rfc = m.clock[0][w.phase], rvc = m.clock[1][w.phase], lfc = m.clock[2][w.phase], lvc = m.clock[3][w.phase];
@@ -1326,10 +1631,10 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
     }
   }
   LHW_SYNC();
-  env_obs<real, NJ>(w, m);
+  env_obs<real, NJ>(w, m, seed);
   real total = 0;
   for (int i = 0; i < NREW; i++) total += w.rew[i];
-  const int done = (w.qpos[2] < (real)0.6) || (w.qpos[2] > (real)1.4) || (w.selfcol != 0) || (w.status != 0);
+  const int done = (w.qpos[2] < m.done_lo) || (w.qpos[2] > m.done_hi) || (w.selfcol != 0) || (w.status != 0);
   const int ended = done || (w.traj_len + 1 >= max_traj_len);
   LHW_SYNC();
   LHW_LANES(l) {
@@ -1349,6 +1654,15 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
       for (int it = l; it < NOBS; it += 32) term_obs_out[it] = w.obs[it];
   }
   LHW_SYNC();
+  if constexpr (Cfg<NJ>::PERENV) {
+    // domain randomisation after the observation (base_humanoid_env.py:228-233); decisions on stream 0 lanes 2, 3
+    if (m.dynrand_interval > 0 || m.perturb_interval > 0) {
+      uint32_t u[4];
+      philox(seed, w.env_id, w.rng_ctr, 0, u);
+      if (m.dynrand_interval > 0 && randint(u[2], m.dynrand_interval) == 0) env_randomize<real, NJ>(w, m, seed);
+      if (m.perturb_interval > 0 && randint(u[3], m.perturb_interval) == 0) env_perturb<real, NJ>(w, m, seed);
+    }
+  }
   if (ended && autoreset) {
     LHW_LANES(l) {
       if (l == 0) {

@@ -19,13 +19,18 @@ using namespace lhw;
 
 namespace {
 
-constexpr int NJ_JVRC = 6;
+// robot variants (sim_core.h Cfg<NJ>): NJ = 6 JVRC-1 walking, NJ = 5 Unitree H1 standing
+constexpr int NJ_JVRC = 6, NJ_H1 = 5;
 __constant__ Model<double, NJ_JVRC> c_model_d;
 __constant__ Model<float, NJ_JVRC> c_model_f;
+__constant__ Model<double, NJ_H1> c_model_d5;
+__constant__ Model<float, NJ_H1> c_model_f5;
 
-template <class real> __device__ __forceinline__ const Model<real, NJ_JVRC>& cmodel();
-template <> __device__ __forceinline__ const Model<double, NJ_JVRC>& cmodel<double>() { return c_model_d; }
-template <> __device__ __forceinline__ const Model<float, NJ_JVRC>& cmodel<float>() { return c_model_f; }
+template <class real, int NJ> __device__ __forceinline__ const Model<real, NJ>& cmodel();
+template <> __device__ __forceinline__ const Model<double, NJ_JVRC>& cmodel<double, NJ_JVRC>() { return c_model_d; }
+template <> __device__ __forceinline__ const Model<float, NJ_JVRC>& cmodel<float, NJ_JVRC>() { return c_model_f; }
+template <> __device__ __forceinline__ const Model<double, NJ_H1>& cmodel<double, NJ_H1>() { return c_model_d5; }
+template <> __device__ __forceinline__ const Model<float, NJ_H1>& cmodel<float, NJ_H1>() { return c_model_f5; }
 
 }  // namespace
 // tell sim_core.h's out-of-line routines where the model really lives (constant bank -> LDC with immediate offsets)
@@ -36,12 +41,18 @@ template <> struct ModelHome<double, NJ_JVRC> {
 template <> struct ModelHome<float, NJ_JVRC> {
   static __device__ __forceinline__ const Model<float, NJ_JVRC>& get(const Model<float, NJ_JVRC>&) { return c_model_f; }
 };
+template <> struct ModelHome<double, NJ_H1> {
+  static __device__ __forceinline__ const Model<double, NJ_H1>& get(const Model<double, NJ_H1>&) { return c_model_d5; }
+};
+template <> struct ModelHome<float, NJ_H1> {
+  static __device__ __forceinline__ const Model<float, NJ_H1>& get(const Model<float, NJ_H1>&) { return c_model_f5; }
+};
 }  // namespace lhw
 namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-const void* g_owner[2] = {nullptr, nullptr};  // which sim's model currently sits in constant memory (per precision)
+const void* g_owner[4] = {nullptr, nullptr, nullptr, nullptr};  // which sim's model sits in each constant-memory slot
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -53,11 +64,10 @@ int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess) return fail(-10, std::string(#call) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
-template <class real>
+template <class real, int NJ>
 __global__ void __launch_bounds__(32) reset_kernel(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs,
                                                     uint32_t seed, uint32_t first_id, const int32_t* __restrict__ mask,
                                                     int fresh, real* __restrict__ obs_out) {
-  constexpr int NJ = NJ_JVRC;
   using W = Work<real, NJ>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -65,7 +75,7 @@ __global__ void __launch_bounds__(32) reset_kernel(real* __restrict__ state_r, i
   if (env >= n_envs) return;
   if (mask && !mask[env]) return;
   W& w = *reinterpret_cast<W*>(smem_raw);
-  const Model<real, NJ>& m = cmodel<real>();
+  const Model<real, NJ>& m = cmodel<real, NJ>();
   constexpr int NR = Dims<real, NJ>::NSTATE_R;
   real* sr = state_r + (size_t)env * NR;
   int32_t* si = state_i + (size_t)env * NSTATE_I;
@@ -84,20 +94,19 @@ __global__ void __launch_bounds__(32) reset_kernel(real* __restrict__ state_r, i
 // ONE warp per block: the warp's Work struct then sits at a link-time-constant shared-memory address, so every
 // access is [index + immediate] and no base register has to be kept (or rematerialised).  fp32: 28 blocks/SM
 // (the whole 4096-env batch of BASELINE configs[1] is resident at once); fp64: 16 blocks/SM (shared-memory bound).
-template <class real>
-__global__ void __launch_bounds__(32, sizeof(real) == 4 ? 28 : 16)
+template <class real, int NJ>
+__global__ void __launch_bounds__(32, sizeof(real) == 4 ? 28 : (NJ == NJ_JVRC ? 16 : 15))
     step_kernel(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs, uint32_t seed, uint32_t first_id,
                 const real* __restrict__ actions, int max_traj_len, int autoreset, real* __restrict__ obs,
                 real* __restrict__ term_obs, real* __restrict__ reward, real* __restrict__ rew_terms,
                 int32_t* __restrict__ done, int32_t* __restrict__ ended, int32_t* __restrict__ ep_len,
                 real* __restrict__ ep_rew) {
-  constexpr int NJ = NJ_JVRC;
   using W = Work<real, NJ>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int env = blockIdx.x;
   if (env >= n_envs) return;
   W& w = *reinterpret_cast<W*>(smem_raw);
-  const Model<real, NJ>& m = cmodel<real>();
+  const Model<real, NJ>& m = cmodel<real, NJ>();
   constexpr int NR = Dims<real, NJ>::NSTATE_R, NU = 2 * NJ;
   real* sr = state_r + (size_t)env * NR;
   int32_t* si = state_i + (size_t)env * NSTATE_I;
@@ -111,14 +120,13 @@ __global__ void __launch_bounds__(32, sizeof(real) == 4 ? 28 : 16)
 
 // experiment / alternative carving: W warps per block (one env each), a __syncthreads() per substep so the warps of an SM
 // share instruction-cache fills (the kernel is instruction-fetch bound, profiles/); selected with LHW_WARPS_PER_BLOCK > 1
-template <class real>
+template <class real, int NJ>
 __global__ void __launch_bounds__(sizeof(real) == 8 ? 512 : 896, 1)
     step_kernel_mw(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs, uint32_t seed, uint32_t first_id,
                    const real* __restrict__ actions, int max_traj_len, int autoreset, real* __restrict__ obs,
                    real* __restrict__ term_obs, real* __restrict__ reward, real* __restrict__ rew_terms,
                    int32_t* __restrict__ done, int32_t* __restrict__ ended, int32_t* __restrict__ ep_len,
                    real* __restrict__ ep_rew, int sync_mode) {
-  constexpr int NJ = NJ_JVRC;
   using W = Work<real, NJ>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(sizeof(real) == 8 ? 512 : 896, 1)
   const int alive = env < n_envs;
   const int e = alive ? env : n_envs - 1;
   W& w = reinterpret_cast<W*>(smem_raw)[warp];
-  const Model<real, NJ>& m = cmodel<real>();
+  const Model<real, NJ>& m = cmodel<real, NJ>();
   constexpr int NR = Dims<real, NJ>::NSTATE_R, NU = 2 * NJ;
   real* sr = state_r + (size_t)e * NR;
   int32_t* si = state_i + (size_t)e * NSTATE_I;
@@ -141,19 +149,27 @@ __global__ void __launch_bounds__(sizeof(real) == 8 ? 512 : 896, 1)
 }  // namespace
 
 struct lhw_sim {
-  int precision, device, warps_per_block, sync_mode;
+  int precision, device, warps_per_block, sync_mode, nj;
   Model<double, NJ_JVRC> md;
   Model<float, NJ_JVRC> mf;
+  Model<double, NJ_H1> md5;
+  Model<float, NJ_H1> mf5;
   size_t work_bytes;
+  int state_reals, obs_dim;
 };
 
 namespace {
 
 int upload_model(lhw_sim* s, cudaStream_t st) {
-  const int slot = s->precision == 64 ? 0 : 1;
+  const int slot = (s->nj == NJ_JVRC ? 0 : 2) + (s->precision == 64 ? 0 : 1);
   if (g_owner[slot] == s) return 0;
-  if (s->precision == 64) CUDA_OK(cudaMemcpyToSymbolAsync(c_model_d, &s->md, sizeof(s->md), 0, cudaMemcpyHostToDevice, st));
-  else CUDA_OK(cudaMemcpyToSymbolAsync(c_model_f, &s->mf, sizeof(s->mf), 0, cudaMemcpyHostToDevice, st));
+  if (s->nj == NJ_JVRC) {
+    if (s->precision == 64) CUDA_OK(cudaMemcpyToSymbolAsync(c_model_d, &s->md, sizeof(s->md), 0, cudaMemcpyHostToDevice, st));
+    else CUDA_OK(cudaMemcpyToSymbolAsync(c_model_f, &s->mf, sizeof(s->mf), 0, cudaMemcpyHostToDevice, st));
+  } else {
+    if (s->precision == 64) CUDA_OK(cudaMemcpyToSymbolAsync(c_model_d5, &s->md5, sizeof(s->md5), 0, cudaMemcpyHostToDevice, st));
+    else CUDA_OK(cudaMemcpyToSymbolAsync(c_model_f5, &s->mf5, sizeof(s->mf5), 0, cudaMemcpyHostToDevice, st));
+  }
   g_owner[slot] = s;
   return 0;
 }
@@ -163,68 +179,106 @@ template <class K> int prepare_kernel(K kernel, size_t smem) {
   return 0;
 }
 
+template <class real, int NJ> int prepare_variant(lhw_sim* s) {
+  s->work_bytes = sizeof(Work<real, NJ>);
+  s->state_reals = Dims<real, NJ>::NSTATE_R;
+  s->obs_dim = Dims<real, NJ>::NOBS;
+  int maxsmem = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+  // lock-step blocks: as many warps as the launch bound and the shared memory of one SM allow, two blocks per SM
+  const int cap_threads = (sizeof(real) == 8 ? 512 : 896) / 32;
+  if (s->warps_per_block > cap_threads) s->warps_per_block = cap_threads;
+  while (s->warps_per_block > 1 && s->work_bytes * s->warps_per_block > (size_t)maxsmem) s->warps_per_block--;
+  if (s->warps_per_block < 1) s->warps_per_block = 1;
+  if ((int)s->work_bytes > maxsmem) return fail(-5, "working set does not fit in shared memory");
+  if (prepare_kernel(step_kernel<real, NJ>, s->work_bytes) || prepare_kernel(reset_kernel<real, NJ>, s->work_bytes)) return -10;
+  if (s->warps_per_block > 1 && prepare_kernel(step_kernel_mw<real, NJ>, s->work_bytes * s->warps_per_block)) return -10;
+  return 0;
+}
+
+template <class real, int NJ>
+int launch_reset(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint32_t seed, uint32_t first_env_id,
+                 const int32_t* mask, int fresh, void* obs, cudaStream_t st) {
+  reset_kernel<real, NJ><<<n_envs, 32, s->work_bytes, st>>>((real*)state_r, state_i, n_envs, seed, first_env_id, mask, fresh,
+                                                           (real*)obs);
+  return 0;
+}
+
+template <class real, int NJ>
+int launch_step(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint32_t seed, uint32_t first_env_id,
+                const void* actions, int max_traj_len, int autoreset, void* obs, void* term_obs, void* reward,
+                void* rew_terms, int32_t* done, int32_t* ended, int32_t* ep_len, void* ep_rew, cudaStream_t st) {
+  const int wpb = s->warps_per_block, grid = (n_envs + wpb - 1) / wpb;
+  const size_t smem = s->work_bytes * wpb;
+  if (wpb > 1)
+    step_kernel_mw<real, NJ><<<grid, wpb * 32, smem, st>>>((real*)state_r, state_i, n_envs, seed, first_env_id,
+                                                          (const real*)actions, max_traj_len, autoreset, (real*)obs,
+                                                          (real*)term_obs, (real*)reward, (real*)rew_terms, done, ended,
+                                                          ep_len, (real*)ep_rew, s->sync_mode);
+  else
+    step_kernel<real, NJ><<<grid, 32, smem, st>>>((real*)state_r, state_i, n_envs, seed, first_env_id,
+                                                 (const real*)actions, max_traj_len, autoreset, (real*)obs, (real*)term_obs,
+                                                 (real*)reward, (real*)rew_terms, done, ended, ep_len, (real*)ep_rew);
+  return 0;
+}
+
+// (precision, NJ) dispatch
+#define LHW_DISPATCH(s, FN, ...)                                                              \
+  ((s)->nj == NJ_JVRC ? ((s)->precision == 64 ? FN<double, NJ_JVRC>(__VA_ARGS__) : FN<float, NJ_JVRC>(__VA_ARGS__)) \
+                      : ((s)->precision == 64 ? FN<double, NJ_H1>(__VA_ARGS__) : FN<float, NJ_H1>(__VA_ARGS__)))
+
 }  // namespace
 
 extern "C" {
 
-int lhw_version(void) { return 1; }
+int lhw_version(void) { return 2; }
 const char* lhw_last_error(void) { return g_err.c_str(); }
 long long lhw_launch_count(void) { return g_launches.load(); }
 void lhw_count_launch(void) { g_launches++; }
 
 int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision, int device) {
-  if (!out || !flat) return fail(-1, "null argument");
+  if (!out || !flat || n_flat < 1) return fail(-1, "null argument");
   if (precision != 64 && precision != 32) return fail(-2, "precision must be 32 or 64");
   int ndev = 0;
   CUDA_OK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device");
   CUDA_OK(cudaSetDevice(device));
+  const int nj = (int)flat[0];
+  if (nj != NJ_JVRC && nj != NJ_H1) return fail(-4, "unsupported robot: chains of " + std::to_string(nj) + " joints");
   lhw_sim* s = new lhw_sim();
   s->precision = precision;
   s->device = device;
-  int rc = fill_model(s->md, flat, n_flat);
-  if (rc == 0) rc = fill_model(s->mf, flat, n_flat);
+  s->nj = nj;
+  int rc = nj == NJ_JVRC ? fill_model(s->md, flat, n_flat) : fill_model(s->md5, flat, n_flat);
+  if (rc == 0) rc = nj == NJ_JVRC ? fill_model(s->mf, flat, n_flat) : fill_model(s->mf5, flat, n_flat);
   if (rc != 0) {
     delete s;
     return fail(-4, "malformed model array (fill_model rc " + std::to_string(rc) + ")");
   }
-  s->work_bytes = precision == 64 ? sizeof(Work<double, NJ_JVRC>) : sizeof(Work<float, NJ_JVRC>);
   const char* env_wpb = getenv("LHW_WARPS_PER_BLOCK");
   // measured on B200 (profiles/): lock-step blocks of 8 (fp64, 2 blocks/SM) / 14 (fp32, 2 blocks/SM) warps
-  s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? 8 : 14);
+  s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? (nj == NJ_JVRC ? 8 : 7) : 14);
   const char* env_sync = getenv("LHW_BLOCK_SYNC_MODE");
   s->sync_mode = env_sync ? atoi(env_sync) : 1;
-  if (s->warps_per_block < 1 || s->warps_per_block > (precision == 64 ? 16 : 28)) s->warps_per_block = 1;
-  const size_t smem = s->work_bytes * s->warps_per_block;
-  int maxsmem = 0;
-  CUDA_OK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  if ((int)smem > maxsmem) {
-    delete s;
-    return fail(-5, "working set does not fit in shared memory");
-  }
-  if (precision == 64) {
-    if (prepare_kernel(step_kernel<double>, s->work_bytes) || prepare_kernel(reset_kernel<double>, s->work_bytes) ||
-        (s->warps_per_block > 1 && prepare_kernel(step_kernel_mw<double>, smem))) { delete s; return -10; }
-  } else {
-    if (prepare_kernel(step_kernel<float>, s->work_bytes) || prepare_kernel(reset_kernel<float>, s->work_bytes) ||
-        (s->warps_per_block > 1 && prepare_kernel(step_kernel_mw<float>, smem))) { delete s; return -10; }
-  }
+  if (s->warps_per_block < 1) s->warps_per_block = 1;
+  rc = LHW_DISPATCH(s, prepare_variant, s);
+  if (rc != 0) { delete s; return rc; }
   *out = s;
   return 0;
 }
 
 int lhw_sim_destroy(lhw_sim* s) {
   if (!s) return 0;
-  for (int k = 0; k < 2; k++)
+  for (int k = 0; k < 4; k++)
     if (g_owner[k] == s) g_owner[k] = nullptr;
   delete s;
   return 0;
 }
 
-int lhw_sim_state_reals(const lhw_sim*) { return Dims<double, NJ_JVRC>::NSTATE_R; }
+int lhw_sim_state_reals(const lhw_sim* s) { return s ? s->state_reals : Dims<double, NJ_JVRC>::NSTATE_R; }
 int lhw_sim_state_ints(const lhw_sim*) { return NSTATE_I; }
-int lhw_sim_obs_dim(const lhw_sim*) { return Work<double, NJ_JVRC>::NOBS; }
-int lhw_sim_act_dim(const lhw_sim*) { return 2 * NJ_JVRC; }
+int lhw_sim_obs_dim(const lhw_sim* s) { return s ? s->obs_dim : Dims<double, NJ_JVRC>::NOBS; }
+int lhw_sim_act_dim(const lhw_sim* s) { return 2 * (s ? s->nj : NJ_JVRC); }
 int lhw_sim_smem_bytes_per_env(const lhw_sim* s) { return (int)s->work_bytes; }
 
 int lhw_sim_bind(lhw_sim* s, void* stream) {
@@ -238,12 +292,7 @@ int lhw_sim_reset(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint3
   if (n_envs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (upload_model(s, st)) return -10;
-  const int wpb = 1, grid = n_envs;
-  const size_t smem = s->work_bytes;
-  if (s->precision == 64)
-    reset_kernel<double><<<grid, wpb * 32, smem, st>>>((double*)state_r, state_i, n_envs, seed, first_env_id, mask, fresh, (double*)obs);
-  else
-    reset_kernel<float><<<grid, wpb * 32, smem, st>>>((float*)state_r, state_i, n_envs, seed, first_env_id, mask, fresh, (float*)obs);
+  LHW_DISPATCH(s, launch_reset, s, state_r, state_i, n_envs, seed, first_env_id, mask, fresh, obs, st);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -256,29 +305,8 @@ int lhw_sim_step(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint32
   if (n_envs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (upload_model(s, st)) return -10;
-  const int wpb = s->warps_per_block, grid = (n_envs + wpb - 1) / wpb;
-  const size_t smem = s->work_bytes * wpb;
-  if (wpb > 1) {
-    if (s->precision == 64)
-      step_kernel_mw<double><<<grid, wpb * 32, smem, st>>>((double*)state_r, state_i, n_envs, seed, first_env_id,
-                                                           (const double*)actions, max_traj_len, autoreset, (double*)obs,
-                                                           (double*)term_obs, (double*)reward, (double*)rew_terms, done,
-                                                           ended, ep_len, (double*)ep_rew, s->sync_mode);
-    else
-      step_kernel_mw<float><<<grid, wpb * 32, smem, st>>>((float*)state_r, state_i, n_envs, seed, first_env_id,
-                                                          (const float*)actions, max_traj_len, autoreset, (float*)obs,
-                                                          (float*)term_obs, (float*)reward, (float*)rew_terms, done, ended,
-                                                          ep_len, (float*)ep_rew, s->sync_mode);
-  } else if (s->precision == 64)
-    step_kernel<double><<<grid, wpb * 32, smem, st>>>((double*)state_r, state_i, n_envs, seed, first_env_id,
-                                                      (const double*)actions, max_traj_len, autoreset, (double*)obs,
-                                                      (double*)term_obs, (double*)reward, (double*)rew_terms, done,
-                                                      ended, ep_len, (double*)ep_rew);
-  else
-    step_kernel<float><<<grid, wpb * 32, smem, st>>>((float*)state_r, state_i, n_envs, seed, first_env_id,
-                                                     (const float*)actions, max_traj_len, autoreset, (float*)obs,
-                                                     (float*)term_obs, (float*)reward, (float*)rew_terms, done, ended,
-                                                     ep_len, (float*)ep_rew);
+  LHW_DISPATCH(s, launch_step, s, state_r, state_i, n_envs, seed, first_env_id, actions, max_traj_len, autoreset, obs,
+               term_obs, reward, rew_terms, done, ended, ep_len, ep_rew, st);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

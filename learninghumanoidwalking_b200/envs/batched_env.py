@@ -19,12 +19,16 @@ from ..model import load_model, pack_model
 
 REWARD_NAMES = ("foot_frc_score", "foot_vel_score", "root_accel", "height_error", "com_vel_error", "yaw_vel_error",
                 "upper_body_reward", "posture_error", "torque_penalty", "action_penalty")  # tasks/walking_task.py:131-146
+STAND_REWARD_NAMES = ("com_vel_error", "yaw_vel_error", "height", "upperbody", "joint_torque_reward",
+                      "posture")                                                          # tasks/standing_task.py:97-104
+N_REWARD_SLOTS = 10   # width of the kernel's reward-term record (csrc/sim_core.h NREW); unused slots are 0
 
 
 class BatchedHumanoidEnv:
     def __init__(self, num_envs: int, model: str = "jvrc_walk", precision: int = 32, seed: int = 0,
                  first_env_id: int = 0, device: int | torch.device | None = None, max_traj_len: int = 400,
-                 tolerance: float | None = None, max_iter: int | None = None):
+                 tolerance: float | None = None, max_iter: int | None = None, observation_noise: bool = True,
+                 domain_randomization: bool = True, init_noise: bool = True):
         if not torch.cuda.is_available():
             raise _lib.LhwError("BatchedHumanoidEnv needs a CUDA device (no CPU fallback on the rollout path)")
         if device is None:
@@ -37,7 +41,8 @@ class BatchedHumanoidEnv:
         self.mj = load_model(model)
         if tolerance is None and precision == 32:
             tolerance = 1e-6  # fp32 cannot reach the reference's 1e-10; gradient floor is ~1e-6 of the force scale
-        flat = pack_model(self.mj, tolerance=tolerance, max_iter=max_iter)
+        flat = pack_model(self.mj, tolerance=tolerance, max_iter=max_iter, observation_noise=observation_noise,
+                          domain_randomization=domain_randomization, init_noise=init_noise)
         L = _lib.lib()
         h = ctypes.c_void_p()
         _lib.check(L.lhw_sim_create(ctypes.byref(h), flat.ctypes.data_as(ctypes.c_void_p), len(flat), self.precision,
@@ -50,7 +55,7 @@ class BatchedHumanoidEnv:
         self.obs = torch.zeros(n, self.obs_dim, dtype=self.dtype, device=dev)
         self.term_obs = torch.zeros(n, self.obs_dim, dtype=self.dtype, device=dev)
         self.reward = torch.zeros(n, dtype=self.dtype, device=dev)
-        self.rew_terms = torch.zeros(n, len(REWARD_NAMES), dtype=self.dtype, device=dev)
+        self.rew_terms = torch.zeros(n, N_REWARD_SLOTS, dtype=self.dtype, device=dev)
         self.done = torch.zeros(n, dtype=torch.int32, device=dev)
         self.ended = torch.zeros(n, dtype=torch.int32, device=dev)
         self.ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -63,6 +68,16 @@ class BatchedHumanoidEnv:
         self.dt = cfg["control_dt"]
         self.action_space = np.zeros(self.act_dim)
         self.observation_space = np.zeros(self.obs_dim * self.history_len)
+        self.nq, self.nv = 7 + self.act_dim, 6 + self.act_dim
+        if model == "h1":
+            # envs/h1/h1_env.py:37-55 (normalisation), envs/h1/h1_base.py:66-76 ; no mirror lists on the H1 robot
+            self.reward_names = STAND_REWARD_NAMES
+            half = np.asarray(cfg["half_sitting_pose"], dtype=float)
+            self.obs_mean = np.concatenate((np.zeros(5), half, np.zeros(10), np.zeros(10)))
+            self.obs_std = np.concatenate(([0.2, 0.2, 1, 1, 1], 0.5 * np.ones(10), 4 * np.ones(10), 100 * np.ones(10)))
+            self.robot = SimpleNamespace(iteration_count=np.inf)
+            return
+        self.reward_names = REWARD_NAMES
         half = np.deg2rad(cfg["half_sitting_pose_deg"])
         self.obs_mean = np.concatenate((np.zeros(5), half, np.zeros(12), [0, 0, 0.5, 0.5, 0.5, 0, 0, 0]))
         self.obs_std = np.concatenate(([0.2, 0.2, 1, 1, 1], 0.5 * np.ones(12), 4 * np.ones(12), [1, 1, 1, 1, 1, 0.5, 0.5, 0.5]))
@@ -119,11 +134,11 @@ class BatchedHumanoidEnv:
     # ------------------------------------------------------------------ state access (tests / checkpointing)
     @property
     def qpos(self) -> torch.Tensor:
-        return self.state_r[:, 0:19]
+        return self.state_r[:, 0:self.nq]
 
     @property
     def qvel(self) -> torch.Tensor:
-        return self.state_r[:, 19:37]
+        return self.state_r[:, self.nq:self.nq + self.nv]
 
     def solver_iterations(self) -> torch.Tensor:
         """Newton iterations spent in the last launch, per env."""

@@ -6,14 +6,18 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .batched_env import REWARD_NAMES, BatchedHumanoidEnv
+from .batched_env import BatchedHumanoidEnv
 
 
 class JvrcWalkEnv:
-    def __init__(self, path_to_yaml: str | None = None, precision: int = 64, seed: int = 0, env_id: int = 0, device=None):
+    MODEL = "jvrc_walk"
+
+    def __init__(self, path_to_yaml: str | None = None, precision: int = 64, seed: int = 0, env_id: int = 0, device=None,
+                 **env_kwargs):
         if path_to_yaml is not None:
             raise NotImplementedError("custom YAML: recompile the model with tools/compile_model.py")
-        self._b = BatchedHumanoidEnv(1, "jvrc_walk", precision=precision, seed=seed, first_env_id=env_id, device=device)
+        self._b = BatchedHumanoidEnv(1, self.MODEL, precision=precision, seed=seed, first_env_id=env_id, device=device,
+                                     **env_kwargs)
         for k in ("observation_space", "action_space", "obs_mean", "obs_std", "robot", "history_len", "base_obs_len", "dt"):
             setattr(self, k, getattr(self._b, k))
 
@@ -27,7 +31,7 @@ class JvrcWalkEnv:
         a = torch.as_tensor(np.copy(action), dtype=self._b.dtype).reshape(1, -1)
         obs, rew, done, _ = self._b.step(a, autoreset=False)
         terms = self._b.rew_terms[0].double().cpu().numpy()
-        info = {k: float(v) for k, v in zip(REWARD_NAMES, terms)}
+        info = {k: float(v) for k, v in zip(self._b.reward_names, terms)}
         return obs[0].double().cpu().numpy(), float(sum(info.values())), bool(done[0].item()), info
 
     def close(self):

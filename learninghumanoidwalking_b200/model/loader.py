@@ -20,7 +20,8 @@ def load_model(name: str = "jvrc_walk") -> dict:
 
 
 def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = None, kp=None, kd=None,
-               self_collision: bool = True) -> np.ndarray:
+               self_collision: bool = True, observation_noise: bool = True, domain_randomization: bool = True,
+               init_noise: bool = True) -> np.ndarray:
     links = mj["links"]
     nl = len(links)
     assert (nl - 1) % 2 == 0, "expected a free root + two equal serial chains"
@@ -29,7 +30,8 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
         for k in range(nj):
             i = 1 + c * nj + k
             assert links[i]["parent"] == (0 if k == 0 else i - 1), "links must be ordered root, chain0, chain1"
-    assert mj["rfoot_link"] == nj and mj["lfoot_link"] == 2 * nj
+    assert {mj["rfoot_link"], mj["lfoot_link"]} == {nj, 2 * nj}
+    stand = mj["name"] == "h1"          # Unitree H1 + StandingTask (csrc/sim_core.h Cfg<5>)
     b: list[float] = [nj]
     for lk in links:
         b += lk["pos"]
@@ -44,11 +46,13 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
             b += [0.0, 0.0, 0.0, 0.0, mj["dof_invweight0"][d]]
         else:
             j = links[d - 5]["joint"]
-            b += [j["armature"], j["damping"], j["range"][0], j["range"][1], mj["dof_invweight0"][d]]
+            lo, hi = j["range"] if j.get("limited", True) else (-1e30, 1e30)
+            b += [j["armature"], j["damping"], lo, hi, mj["dof_invweight0"][d]]
+    assert [g["link"] for g in mj["geoms"]] == [nj, 2 * nj], "one ground-contact geom set per foot, chain order"
     for g in mj["geoms"]:
-        assert g["type"] == "box"
-        b += g["pos"]
-        b += g["size"]
+        assert g["type"] == ("spheres" if stand else "box")
+        b += g.get("pos", [0.0, 0.0, 0.0])
+        b += g.get("size", [0.0, 0.0, 0.0])
         b.append(mj["link_invweight0"][g["link"]][0])
     o = mj["opt"]
     b.append(o["timestep"])
@@ -62,12 +66,15 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
     b += list(c["kd"] if kd is None else kd)
     b += c["nominal_qpos"]
     b += [c["action_smoothing"], c["frame_skip"]]
-    b += mj["head_in_root"]
-    t = c["task"]
-    period, table = phase_clock_table(t["swing_duration"], t["stance_duration"], 0.1, "grounded", 1.0 / c["control_dt"],
-                                      total_duration=t["total_duration"])
-    b += [mj["total_mass"], t["goal_height"], period]
-    b += list(table.reshape(-1))
+    b += mj.get("head_in_root", [0.0, 0.0, 0.0])
+    if stand:
+        b += [mj["total_mass"], 0.98, 0]       # no gait clock (tasks/standing_task.py)
+    else:
+        t = c["task"]
+        period, table = phase_clock_table(t["swing_duration"], t["stance_duration"], 0.1, "grounded",
+                                          1.0 / c["control_dt"], total_duration=t["total_duration"])
+        b += [mj["total_mass"], t["goal_height"], period]
+        b += list(table.reshape(-1))
     # self-collision capsule proxies (termination flag; tools/fit_collision_proxies.py)
     sc = mj.get("self_collision") if self_collision else None
     caps = sc["capsules"] if sc else []
@@ -78,4 +85,31 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
     b.append(len(pairs))
     for a_, b_ in pairs:
         b += [a_, b_]
+    # task / robot variant tail
+    if stand:
+        ns = c["observation_noise"] if observation_noise else {"enabled": False}
+        lvl = ns["multiplier"] if ns["enabled"] else 0.0
+        scales = [lvl * ns["scales"][k] for k in ("root_orient", "root_ang_vel", "motor_pos", "motor_vel", "motor_tau")] \
+            if ns["enabled"] else [0.0] * 5
+        pert, dyn = c["perturbation"], c["dynamics_randomization"]
+        b += [0.9, 1.4] + scales            # tasks/standing_task.py:124-125
+        b += [int(dyn["interval"] / c["control_dt"]) if dyn["enable"] and domain_randomization else 0,
+              int(pert["interval"] / c["control_dt"]) if pert["enable"] and domain_randomization else 0,
+              pert["force_magnitude"], pert["torque_magnitude"],
+              c["init_noise_deg"] * np.pi / 180 if init_noise else 0.0]
+    else:
+        b += [0.6, 1.4] + [0.0] * 5 + [0, 0, 0.0, 0.0, 0.0]   # tasks/walking_task.py:192-193
+    for g in mj["geoms"]:
+        pts = g.get("points", [])
+        b += [len(pts), g.get("radius", 0.0)]
+        for pt in pts:
+            b += pt
+    rp = mj.get("root_parts")
+    if rp:
+        sym = lambda A: [A[0][0], A[1][1], A[2][2], A[0][1], A[0][2], A[1][2]]
+        b += [rp["pelvis"]["mass"]] + rp["pelvis"]["com"] + sym(rp["pelvis"]["Ic"])
+        b += [rp["rest"]["mass"]] + rp["rest"]["mc"] + sym(rp["rest"]["Io"])
+        b += rp["torso_com"]
+    else:
+        b += [0.0] * 23
     return np.asarray(b, dtype=np.float64)

@@ -59,7 +59,8 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
             b += [0.0, 0.0, 0.0, 0.0, 0.0, mj["dof_invweight0"][d]]
         else:
             j = links[d - 5]["joint"]
-            b += [j["armature"], j["damping"], j["range"][0], j["range"][1], 1.0, mj["dof_invweight0"][d]]
+            b += [j["armature"], j["damping"], j["range"][0], j["range"][1], 1.0 if j.get("limited", True) else 0.0,
+                  mj["dof_invweight0"][d]]
     b.append(len(mj["geoms"]))
     for g in mj["geoms"]:
         b.append(g["link"])

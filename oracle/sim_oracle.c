@@ -1084,6 +1084,22 @@ static void apply_perturbation(const orc_model* m, orc_env* e) {
   }
 }
 
+/* _apply_init_noise (base_humanoid_env.py:281-309) on e->qpos (already the nominal pose): stream 50 lanes 0..2 = height,
+ * roll, pitch; joint j -> stream 51 + j/4 lane j%4.  euler2quat(r, p, 0) 'sxyz' = (cp cr, cp sr, sp cr, -sp sr) */
+static void init_pose_noise(const orc_model* m, orc_env* e) {
+  double c = m->init_noise * M_PI / 180.0;
+  uint32_t w[4];
+  orc_philox(e->seed, e->env_id, e->rng_ctr, 50, w);
+  e->qpos[2] = m->nominal_qpos[2] + 0.02 * u01(w[0]);
+  double r = -c + 2 * c * u01(w[1]), p = -c + 2 * c * u01(w[2]);
+  double cr = cos(0.5 * r), sr = sin(0.5 * r), cp = cos(0.5 * p), sp = sin(0.5 * p);
+  e->qpos[3] = cp * cr; e->qpos[4] = cp * sr; e->qpos[5] = sp * cr; e->qpos[6] = -sp * sr;
+  for (int j = 0; j < m->nu; j++) {
+    if ((j & 3) == 0) orc_philox(e->seed, e->env_id, e->rng_ctr, 51 + (j >> 2), w);
+    e->qpos[7 + j] = m->nominal_qpos[7 + j] + (-c + 2 * c * u01(w[j & 3]));
+  }
+}
+
 void orc_env_init(const orc_model* m, orc_env* e, uint32_t seed, uint32_t env_id) {
   memset(e, 0, sizeof(*e));
   params_default(m, &e->P);
@@ -1099,21 +1115,7 @@ void orc_reset(const orc_model* m, orc_env* e, double* obs) {
   memset(e->xfrc, 0, sizeof(e->xfrc));                       /* mj_resetData clears xfrc_applied */
   if (m->dynrand_interval > 0) randomize_dynamics(m, e);     /* base_humanoid_env.py:252-253 */
   memcpy(e->qpos, m->nominal_qpos, m->nq * sizeof(double));
-  if (m->init_noise > 0) {
-    /* _apply_init_noise (base_humanoid_env.py:281-309): stream 50 lanes 0..2 = height, roll, pitch;
-     * joint j -> stream 51 + j/4 lane j%4.  euler2quat(r, p, 0) 'sxyz' = (cp cr, cp sr, sp cr, -sp sr) */
-    double c = m->init_noise * M_PI / 180.0;
-    uint32_t w[4];
-    orc_philox(e->seed, e->env_id, e->rng_ctr, 50, w);
-    e->qpos[2] = m->nominal_qpos[2] + 0.02 * u01(w[0]);
-    double r = -c + 2 * c * u01(w[1]), p = -c + 2 * c * u01(w[2]);
-    double cr = cos(0.5 * r), sr = sin(0.5 * r), cp = cos(0.5 * p), sp = sin(0.5 * p);
-    e->qpos[3] = cp * cr; e->qpos[4] = cp * sr; e->qpos[5] = sp * cr; e->qpos[6] = -sp * sr;
-    for (int j = 0; j < m->nu; j++) {
-      if ((j & 3) == 0) orc_philox(e->seed, e->env_id, e->rng_ctr, 51 + (j >> 2), w);
-      e->qpos[7 + j] = m->nominal_qpos[7 + j] + (-c + 2 * c * u01(w[j & 3]));
-    }
-  }
+  if (m->init_noise > 0) init_pose_noise(m, e);
   memset(e->qvel, 0, sizeof(e->qvel));
   memset(e->qacc_warm, 0, sizeof(e->qacc_warm));
   for (int i = 0; i < 3; i++) orc_mj_step(m, e, zero);
@@ -1203,5 +1205,15 @@ void orc_batch_step_autoreset(const orc_model* m, orc_env* envs, int n, const do
 
 /* test hook: reward terms for the current env fields (lets tests/ pin calc_reward to the golden vectors) */
 void orc_calc_reward(const orc_model* m, const orc_env* e, const double* target, double* terms) {
-  calc_reward(m, e, target, terms);
+  if (m->task == ORC_TASK_STAND) calc_reward_stand(m, e, terms);
+  else calc_reward(m, e, target, terms);
+}
+/* test hooks for the H1 pieces pinned by tests/golden/h1_*.json (each uses the env's current rng_ctr) */
+void orc_test_randomize_dynamics(const orc_model* m, orc_env* e) { randomize_dynamics(m, e); }
+void orc_test_apply_perturbation(const orc_model* m, orc_env* e) { apply_perturbation(m, e); }
+void orc_test_get_obs(const orc_model* m, const orc_env* e, double* obs) { get_obs(m, e, obs); }
+/* the noisy initial pose alone (reset_model before set_state), without the settling steps */
+void orc_test_init_pose(const orc_model* m, orc_env* e) {
+  memcpy(e->qpos, m->nominal_qpos, m->nq * sizeof(double));
+  init_pose_noise(m, e);
 }

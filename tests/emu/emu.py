@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "_build", "libsim_emu.so")
-NOBS, NREW, NU, NSTATE_I = 37, 10, 12, 8
+NREW, NSTATE_I = 10, 8
 
 
 def build():
@@ -29,7 +29,10 @@ class Emu:
         assert self.h.value, "emu_create failed"
         self.prec, self.n, self.seed, self.first_id = precision, n, seed, first_id
         self.dt = np.float64 if precision == 64 else np.float32
-        self.nr = self.lib.emu_state_words(precision)
+        self.nr = self.lib.emu_state_words(self.h)
+        self.nobs = self.lib.emu_obs_dim(self.h)
+        self.nu = 2 * int(flat[0])
+        self.nq, self.nv = 7 + self.nu, 6 + self.nu
         self.sr = np.zeros((n, self.nr), dtype=self.dt)
         self.si = np.zeros((n, NSTATE_I), dtype=np.int32)
 
@@ -37,15 +40,15 @@ class Emu:
         return a.ctypes.data_as(ctypes.c_void_p)
 
     def reset(self):
-        obs = np.zeros((self.n, NOBS), dtype=self.dt)
+        obs = np.zeros((self.n, self.nobs), dtype=self.dt)
         self.lib.emu_reset(self.h, self.prec, self._p(self.sr), self._p(self.si), self.n, ctypes.c_uint32(self.seed),
                            ctypes.c_uint32(self.first_id), self._p(obs))
         return obs
 
     def step(self, actions, max_traj_len=400, autoreset=1):
-        a = np.ascontiguousarray(actions, dtype=self.dt).reshape(self.n, NU)
+        a = np.ascontiguousarray(actions, dtype=self.dt).reshape(self.n, self.nu)
         n = self.n
-        obs, tobs = np.zeros((n, NOBS), self.dt), np.zeros((n, NOBS), self.dt)
+        obs, tobs = np.zeros((n, self.nobs), self.dt), np.zeros((n, self.nobs), self.dt)
         rew, terms, eprew = np.zeros(n, self.dt), np.zeros((n, NREW), self.dt), np.zeros(n, self.dt)
         done, ended, eplen = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
         self.lib.emu_step(self.h, self.prec, self._p(self.sr), self._p(self.si), n, ctypes.c_uint32(self.seed),
@@ -61,8 +64,8 @@ class Emu:
 
     @property
     def qpos(self):
-        return self.sr[:, 0:19]
+        return self.sr[:, 0:self.nq]
 
     @property
     def qvel(self):
-        return self.sr[:, 19:37]
+        return self.sr[:, self.nq:self.nq + self.nv]

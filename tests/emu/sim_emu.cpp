@@ -49,33 +49,59 @@ static void step_all(void* h, real* sr, int32_t* si, int n_envs, uint32_t seed, 
   }
 }
 
+// physics substeps on a raw state record with explicit ctrl (for mj_step-level parity)
+template <int NJ> static void substeps64(void* p, double* sr, int32_t* si, const double* ctrl, int nsteps) {
+  auto* e = (Emu<double, NJ>*)p;
+  load_state(e->work, sr, si, 0);
+  for (int k = 0; k < 2 * NJ; k++) e->work.ctrl[k] = ctrl[k];
+  for (int s = 0; s < nsteps; s++) substep<double, NJ>(e->work, e->model, true);
+  store_state(e->work, sr, si);
+}
+
+// dispatch on (precision, NJ): NJ = 6 JVRC-1 walking, NJ = 5 Unitree H1 standing
+struct Handle { int nj; void* p; };
+#define DISPATCH(h, prec, CALL)                                         \
+  do {                                                                  \
+    if ((h)->nj == 6) { if ((prec) == 64) { CALL(double, 6); } else { CALL(float, 6); } } \
+    else { if ((prec) == 64) { CALL(double, 5); } else { CALL(float, 5); } }              \
+  } while (0)
+
 extern "C" {
 void* emu_create(const double* flat, int n, int precision) {
-  return precision == 64 ? create<double, 6>(flat, n) : create<float, 6>(flat, n);
+  const int nj = (int)flat[0];
+  if (nj != 6 && nj != 5) return nullptr;
+  void* p = nullptr;
+  if (nj == 6) p = precision == 64 ? create<double, 6>(flat, n) : create<float, 6>(flat, n);
+  else p = precision == 64 ? create<double, 5>(flat, n) : create<float, 5>(flat, n);
+  if (!p) return nullptr;
+  return new Handle{nj, p};
 }
-int emu_state_words(int precision) { (void)precision; return Dims<double, 6>::NSTATE_R; }
-void emu_reset(void* h, int precision, void* sr, int32_t* si, int n, uint32_t seed, uint32_t first_id, void* obs) {
-  if (precision == 64) reset_all<double, 6>(h, (double*)sr, si, n, seed, first_id, (double*)obs);
-  else reset_all<float, 6>(h, (float*)sr, si, n, seed, first_id, (float*)obs);
+int emu_state_words(void* hv) { return ((Handle*)hv)->nj == 6 ? Dims<double, 6>::NSTATE_R : Dims<double, 5>::NSTATE_R; }
+int emu_obs_dim(void* hv) { return ((Handle*)hv)->nj == 6 ? Dims<double, 6>::NOBS : Dims<double, 5>::NOBS; }
+int emu_work_bytes(void* hv, int precision) {
+  Handle* h = (Handle*)hv;
+  if (h->nj == 6) return precision == 64 ? (int)sizeof(Work<double, 6>) : (int)sizeof(Work<float, 6>);
+  return precision == 64 ? (int)sizeof(Work<double, 5>) : (int)sizeof(Work<float, 5>);
 }
-void emu_step(void* h, int precision, void* sr, int32_t* si, int n, uint32_t seed, uint32_t first_id,
+void emu_reset(void* hv, int precision, void* sr, int32_t* si, int n, uint32_t seed, uint32_t first_id, void* obs) {
+  Handle* h = (Handle*)hv;
+#define CALL(R, J) reset_all<R, J>(h->p, (R*)sr, si, n, seed, first_id, (R*)obs)
+  DISPATCH(h, precision, CALL);
+#undef CALL
+}
+void emu_step(void* hv, int precision, void* sr, int32_t* si, int n, uint32_t seed, uint32_t first_id,
               const void* actions, int max_traj_len, int autoreset, void* obs, void* term_obs, void* reward,
               void* rew_terms, int32_t* done, int32_t* ended, int32_t* ep_len, void* ep_rew) {
-  if (precision == 64)
-    step_all<double, 6>(h, (double*)sr, si, n, seed, first_id, (const double*)actions, max_traj_len, autoreset,
-                        (double*)obs, (double*)term_obs, (double*)reward, (double*)rew_terms, done, ended, ep_len,
-                        (double*)ep_rew);
-  else
-    step_all<float, 6>(h, (float*)sr, si, n, seed, first_id, (const float*)actions, max_traj_len, autoreset,
-                       (float*)obs, (float*)term_obs, (float*)reward, (float*)rew_terms, done, ended, ep_len,
-                       (float*)ep_rew);
+  Handle* h = (Handle*)hv;
+#define CALL(R, J)                                                                                             \
+  step_all<R, J>(h->p, (R*)sr, si, n, seed, first_id, (const R*)actions, max_traj_len, autoreset, (R*)obs,       \
+                 (R*)term_obs, (R*)reward, (R*)rew_terms, done, ended, ep_len, (R*)ep_rew)
+  DISPATCH(h, precision, CALL);
+#undef CALL
 }
-// single physics substep on a raw state record with explicit ctrl (for mj_step-level parity)
-void emu_substep64(void* h, double* sr, int32_t* si, const double* ctrl, int nsteps) {
-  auto* e = (Emu<double, 6>*)h;
-  load_state(e->work, sr, si, 0);
-  for (int k = 0; k < 12; k++) e->work.ctrl[k] = ctrl[k];
-  for (int s = 0; s < nsteps; s++) substep<double, 6>(e->work, e->model, true);
-  store_state(e->work, sr, si);
+void emu_substep64(void* hv, double* sr, int32_t* si, const double* ctrl, int nsteps) {
+  Handle* h = (Handle*)hv;
+  if (h->nj == 6) substeps64<6>(h->p, sr, si, ctrl, nsteps);
+  else substeps64<5>(h->p, sr, si, ctrl, nsteps);
 }
 }
