@@ -55,6 +55,10 @@
 #define LHW_ASSUME_SHARED(p) ((void)0)
 #endif
 
+// lane-strided loop over N items with a COMPILE-TIME trip count (the item guard vanishes when N is a multiple of 32)
+#define LHW_STRIDED(it, l, N) \
+  _Pragma("unroll") for (int _k = 0, it = (l); _k < ((N) + 31) / 32; _k++, it += 32) if ((N) % 32 == 0 || it < (N))
+
 namespace lhw {
 
 constexpr int NREW = 10;
@@ -172,7 +176,8 @@ template <class real, int NJ> struct Dims {
 
 // ---------------------------------------------------------------- arrow-packed symmetric matrix
 // ordering [root | chain0 | chain1]; chain0-chain1 coupling is structurally zero and not stored
-template <class real, int NJ> struct Arrow {
+// 16-byte aligned (as is Work): lets the compiler fuse neighbouring shared-memory accesses into LDS.64 / LDS.128
+template <class real, int NJ> struct alignas(16) Arrow {
   real r[6][6];      // root block (M: full symmetric; factor: lower triangle)
   real x[2][6][NJ];  // coupling  x[chain][root dof][chain dof]   (factor: X = B L^-T)
   real c[2][NJ][NJ]; // chain blocks (M: full symmetric; factor: lower triangle)
@@ -196,7 +201,7 @@ template <bool C, class A, class B> struct Select { typedef A type; };
 template <class A, class B> struct Select<false, A, B> { typedef B type; };
 
 template <class real, int NJ>
-struct Work : Select<Cfg<NJ>::PERENV, PersistRand<real, NJ>, Persist<real, NJ>>::type {
+struct alignas(16) Work : Select<Cfg<NJ>::PERENV, PersistRand<real, NJ>, Persist<real, NJ>>::type {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
   static constexpr int CPF = Cfg<NJ>::CPF, NCON = 2 * CPF, NEDGE = 4 * NCON, NPTS = Cfg<NJ>::NPTS;
   static constexpr int NOBS = Dims<real, NJ>::NOBS;
@@ -526,8 +531,7 @@ LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m_arg
   }
   LHW_SYNC();
   LHW_LANES(l) {
-#pragma unroll
-    for (int ed = l; ed < NEDGE; ed += 32) {
+    LHW_STRIDED(ed, l, NEDGE) {
       const int s = ed >> 2, e = ed & 3, f = s / CPF;
       real v = fill;
       if (s - f * CPF < w.ncon[f]) {
@@ -849,8 +853,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
   // ---------------- P8 pyramid-edge reference accelerations (lane = edge; foot spatial velocity from P3) ;
   // qfrc_smooth + warm start (lane = dof) ; joint limits (lanes 18..18+NU)
   LHW_LANES(l) {
-#pragma unroll
-    for (int ed = l; ed < NEDGE; ed += 32) {
+    LHW_STRIDED(ed, l, NEDGE) {
       const int s = ed >> 2, e = ed & 3, f = s / CPF;
       if (s - f * CPF < w.ncon[f]) {
         real u[3];
@@ -1063,8 +1066,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       const real al = ls == 0 ? (real)0 : alpha;
       const real cd = warp_sum<real>([&](int l) {
         real acc = 0;
-#pragma unroll
-        for (int ed = l; ed < NEDGE; ed += 32) {
+        LHW_STRIDED(ed, l, NEDGE) {
           const real x = w.ejar[ed] + al * w.ejv[ed];   // inactive slots: jar = 1, jv = 0
           if (x < 0) acc += w.cD[ed >> 2] * x * w.ejv[ed];
         }
@@ -1087,8 +1089,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       if (m_abs(d) <= LS_TOL * m_abs(d_at0)) break;
       const real cdd = warp_sum<real>([&](int l) {
         real acc = 0;
-#pragma unroll
-        for (int ed = l; ed < NEDGE; ed += 32)
+        LHW_STRIDED(ed, l, NEDGE)
           if (w.ejar[ed] + al * w.ejv[ed] < 0) acc += w.cD[ed >> 2] * w.ejv[ed] * w.ejv[ed];
         if (l < NU && w.ljar[l] + al * w.ljv[l] < 0) acc += w.lD[l] * w.ljv[l] * w.ljv[l];
         if constexpr (FLOSS) {
@@ -1111,8 +1112,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         w.qacc[l] += alpha * w.sdir[l];
         w.Ma[l] += alpha * w.Ms[l];
       }
-#pragma unroll
-      for (int ed = l; ed < NEDGE; ed += 32) w.ejar[ed] += alpha * w.ejv[ed];
+      LHW_STRIDED(ed, l, NEDGE) w.ejar[ed] += alpha * w.ejv[ed];
       if (l < NU) {
         w.ljar[l] += alpha * w.ljv[l];
         if constexpr (FLOSS) w.fjar[l] += alpha * w.fjv[l];
