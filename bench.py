@@ -104,21 +104,30 @@ def effective_cpus() -> int:
     return n
 
 
-def cpu_reference(n_envs: int, seconds: float, warmup: int, seed: int, nthreads: int = 0):
+WORKLOADS = {
+    "jvrc_walk": dict(model="jvrc_walk", metric="env-steps/sec jvrc_walk",
+                      desc="jvrc_walk {n} envs/GPU (BASELINE configs[1]), JVRC-1 sim_dt=0.001 control_dt=0.025 flat terrain"),
+    "h1": dict(model="h1", metric="env-steps/sec h1 standing",
+               desc="h1 standing task {n} envs/GPU (BASELINE configs[3]), Unitree H1 sim_dt=0.001 control_dt=0.025, observation "
+                    "noise + dynamics randomisation (damping, frictionloss, mass, CoM) + random pushes in the kernel"),
+}
+
+
+def cpu_reference(n_envs: int, seconds: float, warmup: int, seed: int, nthreads: int = 0, model: str = "jvrc_walk"):
     """The oracle (CPU port of the reference path) on the host cores, run for about `seconds` of wall time
     (a bounded sample of the same workload): env-steps/s, threads used, elapsed, control steps done."""
     import numpy as np
     from oracle.oracle import Oracle
-    o = Oracle()
+    o = Oracle(model)
     nthreads = nthreads or effective_cpus()
     envs = o.make_envs(n_envs, seed=seed)
     o.batch_reset(envs, n_envs, nthreads)
     rng = np.random.RandomState(seed)
     for _ in range(warmup):
-        o.batch_step(envs, n_envs, rng.normal(size=(n_envs, 12)) * SIGMA, 400, nthreads)
+        o.batch_step(envs, n_envs, rng.normal(size=(n_envs, o.nu)) * SIGMA, 400, nthreads)
     steps, t0 = 0, time.perf_counter()
     while True:
-        a = rng.normal(size=(n_envs, 12)) * SIGMA
+        a = rng.normal(size=(n_envs, o.nu)) * SIGMA
         o.batch_step(envs, n_envs, a, 400, nthreads)
         steps += 1
         dt = time.perf_counter() - t0
@@ -138,12 +147,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--workload", default="jvrc_walk", choices=sorted(WORKLOADS),
+                    help="jvrc_walk: the configuration BASELINE.json's metric is quoted on (default); h1: configs[3]")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K, W = args.steps, max(3, args.warmup)
-    config = {"workload": f"jvrc_walk {args.envs} envs/GPU (BASELINE configs[1]), JVRC-1 sim_dt=0.001 control_dt=0.025 flat terrain",
+    wl = WORKLOADS[args.workload]
+    metric = wl["metric"]
+    config = {"workload": wl["desc"].format(n=args.envs),
               "envs_per_gpu": args.envs, "global_envs": args.envs * world, "actions": f"N(0,{SIGMA}^2) synthetic, pre-generated",
               "parallelism": f"env-sharded x{world} (no data-path collective)"}
 
@@ -154,8 +167,8 @@ def main():
             return
         ncores = effective_cpus()
         n_sample = max(256, min(args.envs * world, 64 * ncores))
-        sps, threads, dt, steps_ref = cpu_reference(n_sample, 15.0, 2, args.seed)
-        print(json.dumps({"metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        sps, threads, dt, steps_ref = cpu_reference(n_sample, 15.0, 2, args.seed, model=wl["model"])
+        print(json.dumps({"metric": metric, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
                           "ms_per_step": 1e3 * dt / steps_ref, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
                           "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
@@ -175,10 +188,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs
-    env = BatchedHumanoidEnv(n, precision=args.precision, seed=args.seed, first_env_id=rank * n, device=local_rank)
+    env = BatchedHumanoidEnv(n, model=wl["model"], precision=args.precision, seed=args.seed, first_env_id=rank * n,
+                             device=local_rank)
     env.reset()
+    A = env.act_dim
     g = torch.Generator(device=dev).manual_seed(args.seed * 1000 + rank)
-    acts = torch.randn(K + W, n, 12, device=dev, generator=g, dtype=env.dtype) * SIGMA
+    acts = torch.randn(K + W, n, A, device=dev, generator=g, dtype=env.dtype) * SIGMA
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -207,12 +222,12 @@ def main():
     total_ms = sum(step_ms)
     launches = _lib.lib().lhw_launch_count() - launches0
     # ---- e2e: pinned host actions in, pinned host obs/reward/done out, every step
-    h_acts = torch.empty(K, n, 12, dtype=env.dtype).pin_memory()
+    h_acts = torch.empty(K, n, A, dtype=env.dtype).pin_memory()
     h_acts.copy_(acts[W:W + K].cpu())
     h_obs = torch.empty(n, env.obs_dim, dtype=env.dtype).pin_memory()
     h_rew = torch.empty(n, dtype=env.dtype).pin_memory()
     h_done = torch.empty(n, dtype=torch.int32).pin_memory()
-    d_act = torch.empty(n, 12, dtype=env.dtype, device=dev)
+    d_act = torch.empty(n, A, dtype=env.dtype, device=dev)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -231,7 +246,7 @@ def main():
     # critic MLPs (cuBLAS) and buffer writes in the loop (DeviceRolloutWorker.sample)
     extras = {}
     if not args.no_extras:
-        env32 = BatchedHumanoidEnv(n, precision=32, seed=args.seed, first_env_id=rank * n, device=local_rank)
+        env32 = BatchedHumanoidEnv(n, model=wl["model"], precision=32, seed=args.seed, first_env_id=rank * n, device=local_rank)
         env32.reset()
         a32 = acts.float()
         for k in range(W):
@@ -273,26 +288,30 @@ def main():
         e2e = n * world * K / (e2e_ms * 1e-3)
         peak, peak_src = peaks()
         kernel_ms = statistics.mean(step_ms)   # one launch per step: the event pair brackets exactly the step kernel
-        achieved = n * ALG_BYTES[args.precision] / (kernel_ms * 1e-3) / 1e9
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        esz_ = 8 if args.precision == 64 else 4
+        # algorithmic bytes per env-step: state record read + written, actions in, obs / reward / flags out
+        alg_bytes = ALG_BYTES[args.precision] if args.workload == "jvrc_walk" else \
+            (2 * env.state_r.shape[1] + A + env.obs_dim + 2) * esz_ + 2 * 8 * 4 + 2 * 4
+        achieved = n * alg_bytes / (kernel_ms * 1e-3) / 1e9
+        out = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
                "config": dict(config, l2="flushed (256 MiB write) before every timed step; CUDA events bracket the step only",
                               wall_s_incl_flush=wall, newton_iters_per_env_step=iters),
-               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * 12 * esz,
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * A * esz,
                        "d2h_bytes_per_step": n * (env.obs_dim * esz + esz + 4)},
                "gpu_launches": int(launches),
                "clocks": clocks,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": None, "peak_source": peak_src,
-                            "algorithmic_bytes_per_env_step": ALG_BYTES[args.precision],
+                            "algorithmic_bytes_per_env_step": alg_bytes,
                             "note": "the step kernel is ALU/latency bound (25 substeps of O(nv^3) work per ~2 KB of state); "
                                     "see DESIGN.md for the FP-issue bound reported beside this"}}
         out["extras"] = extras
         if not args.no_cpu_baseline and world == 1:
             ncores = effective_cpus()
             n_cpu = max(256, min(n, 64 * ncores))
-            sps, threads, dt, nst = cpu_reference(n_cpu, 10.0, 2, args.seed)
+            sps, threads, dt, nst = cpu_reference(n_cpu, 10.0, 2, args.seed, model=wl["model"])
             out["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": f"{n_cpu} envs x {nst} control steps ({dt:.1f} s) after 2 warm-up steps, same action distribution; "
                                              "oracle/ C port with OpenMP (reference Ray+MuJoCo path not installable here)"}

@@ -79,8 +79,8 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
     sc = mj.get("self_collision") if self_collision else None
     caps = sc["capsules"] if sc else []
     b.append(len(caps))
-    for c in caps:
-        b += [c["link"]] + list(c["p0"]) + list(c["p1"]) + [c["radius"]]
+    for cap in caps:
+        b += [cap["link"]] + list(cap["p0"]) + list(cap["p1"]) + [cap["radius"]]
     pairs = sc["pairs"] if sc else []
     b.append(len(pairs))
     for a_, b_ in pairs:

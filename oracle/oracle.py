@@ -87,8 +87,8 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
     sc = mj.get("self_collision") if self_collision else None
     caps = sc["capsules"] if sc else []
     b.append(len(caps))
-    for c in caps:
-        b += [c["link"]] + c["p0"] + c["p1"] + [c["radius"]]
+    for cap in caps:
+        b += [cap["link"]] + cap["p0"] + cap["p1"] + [cap["radius"]]
     pairs = sc["pairs"] if sc else []
     b.append(len(pairs))
     for a_, b_ in pairs:

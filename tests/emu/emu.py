@@ -42,8 +42,15 @@ class Emu:
     def reset(self):
         obs = np.zeros((self.n, self.nobs), dtype=self.dt)
         self.lib.emu_reset(self.h, self.prec, self._p(self.sr), self._p(self.si), self.n, ctypes.c_uint32(self.seed),
-                           ctypes.c_uint32(self.first_id), self._p(obs))
+                           ctypes.c_uint32(self.first_id), self._p(obs), 1)
         return obs
+
+    def reset_one(self, i):
+        """Reset env i only (what the RolloutWorker does after a terminal step when autoreset is off)."""
+        obs = np.zeros((1, self.nobs), dtype=self.dt)
+        self.lib.emu_reset(self.h, self.prec, self._p(self.sr[i]), self._p(self.si[i]), 1, ctypes.c_uint32(self.seed),
+                           ctypes.c_uint32(self.first_id + i), self._p(obs), 0)
+        return obs[0]
 
     def step(self, actions, max_traj_len=400, autoreset=1):
         a = np.ascontiguousarray(actions, dtype=self.dt).reshape(self.n, self.nu)

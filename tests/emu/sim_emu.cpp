@@ -21,12 +21,14 @@ template <class real, int NJ> static void* create(const double* flat, int n) {
 }
 
 template <class real, int NJ>
-static void reset_all(void* h, real* sr, int32_t* si, int n_envs, uint32_t seed, uint32_t first_id, real* obs) {
+static void reset_all(void* h, real* sr, int32_t* si, int n_envs, uint32_t seed, uint32_t first_id, real* obs, int fresh) {
   auto* e = (Emu<real, NJ>*)h;
   constexpr int NR = Dims<real, NJ>::NSTATE_R, NOBS = Work<real, NJ>::NOBS;
   for (int i = 0; i < n_envs; i++) {
-    for (int k = 0; k < NR; k++) sr[(size_t)i * NR + k] = 0;
-    for (int k = 0; k < NSTATE_I; k++) si[(size_t)i * NSTATE_I + k] = 0;
+    if (fresh) {
+      for (int k = 0; k < NR; k++) sr[(size_t)i * NR + k] = 0;
+      for (int k = 0; k < NSTATE_I; k++) si[(size_t)i * NSTATE_I + k] = 0;
+    }
     load_state(e->work, sr + (size_t)i * NR, si + (size_t)i * NSTATE_I, first_id + i);
     env_reset(e->work, e->model, seed);
     store_state(e->work, sr + (size_t)i * NR, si + (size_t)i * NSTATE_I);
@@ -83,9 +85,9 @@ int emu_work_bytes(void* hv, int precision) {
   if (h->nj == 6) return precision == 64 ? (int)sizeof(Work<double, 6>) : (int)sizeof(Work<float, 6>);
   return precision == 64 ? (int)sizeof(Work<double, 5>) : (int)sizeof(Work<float, 5>);
 }
-void emu_reset(void* hv, int precision, void* sr, int32_t* si, int n, uint32_t seed, uint32_t first_id, void* obs) {
+void emu_reset(void* hv, int precision, void* sr, int32_t* si, int n, uint32_t seed, uint32_t first_id, void* obs, int fresh) {
   Handle* h = (Handle*)hv;
-#define CALL(R, J) reset_all<R, J>(h->p, (R*)sr, si, n, seed, first_id, (R*)obs)
+#define CALL(R, J) reset_all<R, J>(h->p, (R*)sr, si, n, seed, first_id, (R*)obs, fresh)
   DISPATCH(h, precision, CALL);
 #undef CALL
 }

@@ -18,7 +18,8 @@ def h1_oracle():
     return Oracle("h1", tolerance=1e-14)
 
 
-def test_h1_fp64_closed_loop_with_randomisation_and_resets(h1_oracle):
+@pytest.mark.parametrize("sigma,steps,min_ends", [(0.3, 300, 40), (1.0, 120, 60)])   # sigma 1.0: legs cross -> self-collision flag
+def test_h1_fp64_closed_loop_with_randomisation_and_resets(h1_oracle, sigma, steps, min_ends):
     from learninghumanoidwalking_b200.envs import BatchedHumanoidEnv
     o, n = h1_oracle, 16
     env = BatchedHumanoidEnv(n, model="h1", precision=64, seed=21, first_env_id=7, max_traj_len=60, tolerance=1e-14)
@@ -27,8 +28,8 @@ def test_h1_fp64_closed_loop_with_randomisation_and_resets(h1_oracle):
     assert _rel(env.reset().cpu().numpy(), o.batch_reset(envs, n)) < 1e-9
     rng = np.random.RandomState(0)
     n_end, pushed, worst = 0, False, 0.0
-    for k in range(300):
-        a = rng.normal(size=(n, 10)) * 0.3
+    for k in range(steps):
+        a = rng.normal(size=(n, 10)) * sigma
         o_obs, o_tobs, o_terms, o_rew, o_done, o_end = o.batch_step(envs, n, a, max_traj_len=60)
         g_obs, g_rew, g_done, g_end = env.step(torch.as_tensor(a, device="cuda", dtype=env.dtype))
         assert (g_done.cpu().numpy() == o_done).all() and (g_end.cpu().numpy() == o_end).all(), f"step {k}"
@@ -44,7 +45,7 @@ def test_h1_fp64_closed_loop_with_randomisation_and_resets(h1_oracle):
         if m.any():
             assert _rel(env.term_obs.cpu().numpy()[m], o_tobs[m]) < 1e-7
             n_end += int(m.sum())
-    assert n_end > 40 and pushed
+    assert n_end > min_ends and (pushed or steps < 200)
     assert worst < 1e-7, worst
     fl = np.stack([o.field(envs, i, "P_frictionloss")[6:16] for i in range(n)])
     assert np.abs(env.state_r[:, 163:173].cpu().numpy() - fl).max() < 1e-14

@@ -244,6 +244,35 @@ def test_kernel_source_matches_oracle_h1_fp64(h1):
         assert np.abs(o.field(envs, i, "P_frictionloss")[6:16] - e.sr[i, 163:173]).max() < 1e-15
 
 
+def test_kernel_source_h1_self_collision_flag(h1):
+    """Large actions make the legs cross: the leg-vs-leg capsule test must fire in the kernel source exactly when it
+    does in the oracle (stepping without auto-reset so the terminal state can be inspected)."""
+    from emu import Emu
+    from learninghumanoidwalking_b200.model import load_model, pack_model
+    o, N = h1, 8
+    e = Emu(pack_model(load_model("h1"), tolerance=1e-14), 64, N, seed=2, first_id=0)
+    envs = o.make_envs(N, seed=2, first_id=0)
+    o.batch_reset(envs, N)
+    e.reset()
+    rng = np.random.RandomState(5)
+    n_self = n_done = 0
+    for t in range(140):
+        a = rng.normal(size=(N, 10))
+        eo, _, _, er, ed, *_ = e.step(a, autoreset=0)
+        for i in range(N):
+            ob, r, d, _ = o.step(envs, i, a[i])
+            assert bool(ed[i]) == d
+            assert np.abs(ob - eo[i]).max() < 1e-8
+            if d:
+                n_done += 1
+                z = o.field(envs, i, "qpos")[2]
+                sc = int(o.field(envs, i, "self_collision")[0])
+                n_self += sc
+                assert sc or z < 0.9 or z > 1.4
+                assert np.abs(o.reset(envs, i) - e.reset_one(i)).max() < 1e-12
+    assert n_done > 30 and n_self >= 2, (n_done, n_self)
+
+
 def test_kernel_source_h1_fp32_stays_close(h1):
     from emu import Emu
     from learninghumanoidwalking_b200.model import load_model, pack_model

@@ -338,6 +338,11 @@ H1_LEG_JOINTS = ["left_hip_yaw", "left_hip_roll", "left_hip_pitch", "left_knee",
                  "right_hip_yaw", "right_hip_roll", "right_hip_pitch", "right_knee", "right_ankle"]
 
 
+def r5v(v):
+    """%.5g export rounding (mjcf.export_with_assets(precision=5)) of a vector."""
+    return [r5(x) for x in np.asarray(v, dtype=float)]
+
+
 def compile_h1():
     """H1Env: torso + arm joints removed (unused_joints), jointlimited=False, ctrllimited=False, minimal XML.
     Post-compile the reference overrides body masses (pelvis 8.89, torso_link 21.289, h1_base.py:40-41) WITHOUT
@@ -359,6 +364,7 @@ def compile_h1():
     links: list[Link] = []
     parts = {}      # xml body name -> dict(link, mass0, mass, com (link frame), Ic (link frame))
     foot_pts = {}
+    leg_caps = []   # exact capsule / sphere collision primitives of the leg links (self-collision termination flag)
 
     def walk(body, link_idx, pos_in_link, rot_in_link):
         name = body.attrib["name"]
@@ -389,6 +395,15 @@ def compile_h1():
                 ft = foot_cls[c]
                 foot_pts.setdefault(link_idx, []).extend([(pos_in_link + rot_in_link @ ft[0:3]).tolist(),
                                                           (pos_in_link + rot_in_link @ ft[3:6]).tolist()])
+                leg_caps.append(dict(link=link_idx, p0=r5v(pos_in_link + rot_in_link @ ft[0:3]),
+                                     p1=r5v(pos_in_link + rot_in_link @ ft[3:6]), radius=foot_radius, name=name + ":" + c))
+            elif c == "collision" and link_idx > 0 and g.attrib.get("type") == "capsule":
+                ft = vec(g.attrib["fromto"], 6)
+                leg_caps.append(dict(link=link_idx, p0=r5v(pos_in_link + rot_in_link @ ft[0:3]),
+                                     p1=r5v(pos_in_link + rot_in_link @ ft[3:6]), radius=r5(g.attrib["size"]), name=name + ":capsule"))
+            elif c == "collision" and link_idx > 0 and g.attrib.get("type") == "sphere":
+                ctr = r5v(pos_in_link + rot_in_link @ vec(g.attrib["pos"], 3))
+                leg_caps.append(dict(link=link_idx, p0=ctr, p1=ctr, radius=r5(g.attrib["size"]), name=name + ":sphere"))
         for child in body.findall("body"):
             cpos = vec(child.attrib.get("pos", "0 0 0"), 3)
             crot = quat2mat(vec(child.attrib["quat"], 4)) if "quat" in child.attrib else np.eye(3)
@@ -442,6 +457,16 @@ def compile_h1():
     model["geoms"] = [dict(name=links[l].name + "-feet", type="spheres", link=l, radius=foot_radius, points=foot_pts[l])
                       for l in (li["left_ankle_link"], li["right_ankle_link"])]
     model["total_mass"] = float(sum(lk.mass for lk in links))
+    # self-collision (StandingTask.done -> check_self_collisions, robot_interface.py:472-484): MuJoCo collides every pair of
+    # collision geoms on different, non-adjacent (weld-aware) bodies.  Modelled exactly: all capsule / sphere primitives of one
+    # leg against those of the other leg (thigh x2, shin, knee sphere, 3 foot capsules = 7 per leg, 49 pairs).  Not modelled:
+    # the hip cylinders, the torso box and the welded upper body (head, arms) against the legs.
+    nj = len(H1_LEG_JOINTS) // 2
+    left = [i for i, c_ in enumerate(leg_caps) if c_["link"] <= nj]
+    right = [i for i, c_ in enumerate(leg_caps) if c_["link"] > nj]
+    assert len(left) == len(right) == 7, (len(left), len(right))
+    model["self_collision"] = dict(capsules=leg_caps, pairs=[[a, b] for a in left for b in right],
+                                   source="exact primitives from unitree_h1/h1.xml (capsule and sphere geoms of the leg bodies)")
     # the root link is pelvis + torso + arms welded; randomize_dynamics (domain_randomization.py:46-56) only touches the
     # pelvis BODY (mass x U(.95,1.05), ipos + U(+-.01)) and the leg bodies, so keep the pelvis separable from the rest
     pel = parts["pelvis"]
@@ -455,7 +480,9 @@ def compile_h1():
     model["notes"] = ["dof_invweight0 / link_invweight0 / meaninertia evaluated with the XML masses (pelvis 5.39, torso 17.789); "
                       "dynamics use the overridden ones (8.89, 21.289) with unchanged inertia tensors (h1_base.py:40-41)",
                       "ground contacts: the 3 foot capsules per foot (6 end spheres, radius 0.014); other collision primitives "
-                      "(legs, torso, arms) only touch the floor after the 0.9 m termination height and are not modelled"]
+                      "(legs, torso, arms) only touch the floor after the 0.9 m termination height and are not modelled",
+                      "self-collision flag: leg-vs-leg capsule / sphere primitives (exact); hip cylinders, torso box and the welded "
+                      "upper body are not modelled"]
     return model
 
 
