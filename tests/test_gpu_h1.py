@@ -118,3 +118,27 @@ def test_h1_switches_turn_the_randomisation_off():
         obs, *_ = env.step(torch.zeros(4, 10, device="cuda", dtype=torch.float64))
     assert torch.equal(obs[0], obs[2])
     env.close()
+
+
+def test_ppo_trains_on_the_h1_environment(tmp_path):
+    """The PPO data path (device rollout worker, GAE / adv-norm / gather / fused clip+Adam kernels) on the H1 standing
+    env: obs 35, act 10, no mirror lists on the robot (envs/h1/h1_env.py has none) -> mirror loss is 0."""
+    from types import SimpleNamespace
+    from learninghumanoidwalking_b200.envs import BatchedHumanoidEnv
+    from learninghumanoidwalking_b200.rl import PPO
+    args = SimpleNamespace(gamma=0.99, lam=0.95, lr=3e-4, eps=1e-5, entropy_coeff=0.0, clip=0.2, minibatch_size=256,
+                           epochs=1, max_traj_len=50, num_procs=64, max_grad_norm=0.05, mirror_coeff=0.4, eval_freq=100,
+                           recurrent=False, imitate_coeff=0.0, std_dev=0.223, learn_std=False, logdir=str(tmp_path),
+                           steps_per_env=20)
+    finals = []
+    for _ in range(2):
+        ppo = PPO(lambda: BatchedHumanoidEnv(64, model="h1", precision=32, seed=2), args, seed=2)
+        log = ppo.train(None, 2, verbose=False)
+        assert np.isfinite(log[-1]["critic_loss"]) and float(log[-1]["mirror"]) == 0.0
+        finals.append(ppo._flat_param.clone())
+        batch = ppo.sample_parallel_with_workers()
+        assert batch.states.shape == (64 * 20, 35) and batch.actions.shape == (64 * 20, 10)
+        ppo.env.close()
+    assert torch.equal(finals[0], finals[1])     # same seed, bit-identical weights
+    actor = torch.load(tmp_path / "actor_1.pt", weights_only=False)
+    assert actor(batch.states[:4]).shape == (4, 10)
