@@ -527,7 +527,7 @@ static int solve_newton(const orc_model* m, const double* M, const efc_t* e, con
                         double* force, double* kkt) {
   int nv = m->nv, nr = e->nrow, it;
   double scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
-  double Ma[NV], jar[ORC_MAXROW], grad[NV], H[NV * NV], s[NV], jv[ORC_MAXROW], Ms[NV];
+  double Ma[NV], jar[ORC_MAXROW], curv[ORC_MAXROW], grad[NV], H[NV * NV], s[NV], jv[ORC_MAXROW], Ms[NV];
   double gnorm = 0;
   for (it = 0; it <= m->iterations; it++) {
     for (int a = 0; a < nv; a++) {
@@ -539,8 +539,7 @@ static int solve_newton(const orc_model* m, const double* M, const efc_t* e, con
       double t = -e->aref[r];
       for (int d = 0; d < nv; d++) t += e->J[r][d] * qacc[d];
       jar[r] = t;
-      double cv;
-      force[r] = row_force(e, r, t, &cv);
+      force[r] = row_force(e, r, t, &curv[r]);
     }
     gnorm = 0;
     for (int a = 0; a < nv; a++) {
@@ -554,11 +553,8 @@ static int solve_newton(const orc_model* m, const double* M, const efc_t* e, con
     for (int a = 0; a < nv; a++)
       for (int b = 0; b < nv; b++) {
         double t = M[a * NV + b];
-        for (int r = 0; r < nr; r++) {
-          double cv;
-          row_force(e, r, jar[r], &cv);
-          if (cv > 0) t += cv * e->J[r][a] * e->J[r][b];
-        }
+        for (int r = 0; r < nr; r++)
+          if (curv[r] > 0) t += curv[r] * e->J[r][a] * e->J[r][b];
         H[a * nv + b] = t;
       }
     if (chol(H, nv)) break;

@@ -140,5 +140,5 @@ def test_ppo_trains_on_the_h1_environment(tmp_path):
         assert batch.states.shape == (64 * 20, 35) and batch.actions.shape == (64 * 20, 10)
         ppo.env.close()
     assert torch.equal(finals[0], finals[1])     # same seed, bit-identical weights
-    actor = torch.load(tmp_path / "actor_1.pt", weights_only=False)
+    actor = torch.load(tmp_path / "actor_0.pt", weights_only=False)   # saved at eval_freq boundaries (itr 0)
     assert actor(batch.states[:4]).shape == (4, 10)

@@ -47,14 +47,31 @@ print(f"total warp-instr {tot}  samples {tots}")
 for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"{str(key):36s} inst {a[0]:>12d} {100*a[0]/tot:5.1f}%  lanes {a[1]/max(1,a[0]):5.1f}  samples {100*a[2]/max(1,tots):5.1f}%")
 
-# ---- coarse regions of sim_core.h
-REGIONS = [(60, 82, "math wrappers (out of line)"), (83, 100, "warp_sum"), (101, 120, "philox"), (210, 267, "vec helpers (cross/dot6/mv3/inert_mul/rsqrt/contact_u)"),
-           (268, 283, "impedance"), (284, 313, "seg_seg_dist2"), (314, 448, "arrow_factor_solve"), (449, 472, "arrow_row_dot"),
-           (473, 510, "constraint_images"), (511, 571, "P1 FK"), (572, 616, "P2 S+inertia"), (617, 642, "P3 comp+V"),
-           (643, 669, "P4 rootcomp+velprod"), (670, 705, "P5 CRBA+A"), (706, 733, "P6 F+corner candidates"), (734, 755, "P7 subtree+slots"),
-           (756, 775, "P7b contact params"), (776, 819, "P8 aref+qfs+limits"), (820, 835, "P9 Pm + newton init"), (836, 856, "P10 a cF/cW"),
-           (857, 870, "P10 c Ff"), (871, 886, "P10 d grad"), (887, 919, "P10 e Af,T"), (920, 940, "P10 f H"), (941, 948, "P10 g images call"),
-           (949, 992, "P10 h linesearch+update"), (993, 1057, "P11 lagged+selfcol"), (1058, 1117, "P12 euler+integrate"), (1118, 1500, "env level")]
+# ---- coarse regions of sim_core.h, derived from anchor text in the header itself (no hand-kept line numbers)
+import os
+ANCHORS = [("LHW_DEV float m_sqrt", "math wrappers (out of line)"), ("LHW_DEV real warp_sum", "warp_sum"), ("LHW_DEV void philox", "philox"),
+           ("struct Model {", "struct definitions"), ("LHW_DEV void cross(", "vec helpers (cross/dot6/mv3/inert_mul/rsqrt/contact_u)"),
+           ("LHW_DEVNI real impedance(", "impedance"), ("LHW_DEV real seg_seg_dist2(", "seg_seg_dist2"),
+           ("LHW_DEVNI void arrow_factor_solve(", "arrow_factor_solve"), ("LHW_DEV real arrow_row_dot(", "arrow_row_dot"),
+           ("LHW_DEVNI void constraint_images(", "constraint_images"), ("LHW_DEV real floss_force(", "floss_force"),
+           ("LHW_DEVNI void substep(", "substep prologue"), ("// ---------------- P1 ", "P1 FK"), ("// ---------------- P2 ", "P2 S+inertia"),
+           ("// ---------------- P3 ", "P3 comp+V"), ("// ---------------- P4 ", "P4 rootcomp+velprod"), ("// ---------------- P5 ", "P5 CRBA+A"),
+           ("// ---------------- P6 ", "P6 F+contact candidates"), ("// ---------------- P7 ", "P7 subtree+slots"),
+           ("// ---------------- P7b ", "P7b contact params"), ("// ---------------- P8 ", "P8 aref+qfs+limits+floss"),
+           ("// ---------------- P9 ", "P9 Pm + newton init"), ("// ---------------- P10 ", "P10 loop head"), ("    // (a) per contact", "P10 a cF/cW"),
+           ("    // (c) per foot", "P10 c Ff"), ("    // (d) gradient", "P10 d grad"), ("    // (e) a Newton step", "P10 e Af,T"),
+           ("    // (f) H = ", "P10 f H"), ("    // (g) images", "P10 g images call"), ("    // (h) exact line search", "P10 h linesearch+update"),
+           ("// ---------------- P11 ", "P11 lagged+selfcol"), ("// ---------------- P12 ", "P12 euler+integrate"),
+           ("LHW_DEV void load_state(", "env level")]
+hdr_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "learninghumanoidwalking_b200", "csrc", "sim_core.h")
+src_lines = open(hdr_path).read().splitlines()
+marks = []
+for text, name in ANCHORS:
+    ln = next((k + 1 for k, l in enumerate(src_lines) if text in l), None)
+    if ln is not None:
+        marks.append((ln, name))
+marks.sort()
+REGIONS = [(lo, (marks[k + 1][0] - 1) if k + 1 < len(marks) else 10 ** 6, name) for k, (lo, name) in enumerate(marks)]
 reg = defaultdict(lambda: [0, 0, 0])
 for (f, ln), a in agg.items() if all(k is not None for k in agg) else [(k, v) for k, v in agg.items() if k is not None]:
     name = f if f != "sim_core.h" else next((n for lo, hi, n in REGIONS if lo <= ln <= hi), "other")
