@@ -106,6 +106,7 @@ template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b
   for (int k = 0; k < 3; k++) m.rest_mc[k] = (real)rd();
   for (int k = 0; k < 6; k++) m.rest_Io[k] = (real)rd();
   for (int k = 0; k < 3; k++) m.torso_com[k] = (real)rd();
+  m.pdrand_k = (real)rd();
   if (p != n) return -3;
   return 0;
 }

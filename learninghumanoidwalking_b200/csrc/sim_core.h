@@ -152,6 +152,7 @@ template <class real, int NJ> struct Model {
   // task / robot variant constants (zero / unused where the variant has no such feature)
   real done_lo, done_hi, obs_noise[5], perturb_force, perturb_torque, init_noise;  // init_noise in radians
   int dynrand_interval, perturb_interval;
+  real pdrand_k;   // RobotBase(pdrand_k): PD gains ~ U((1-k) g, (1+k) g) once per control step; 0 = off (reference default)
   real pel_mass, pel_com[3], pel_Ic[6], rest_mass, rest_mc[3], rest_Io[6], torso_com[3];  // root link = pelvis body + welded rest
   int axis_id[NL];  // 0/1/2: hinge axis is +e_x/+e_y/+e_z of the link frame AND link_rot is the identity (fast FK path); -1: general
 };
@@ -209,7 +210,7 @@ struct alignas(16) Work : Select<Cfg<NJ>::PERENV, PersistRand<real, NJ>, Persist
   int phase, mode, traj_len, ep_len, have_prev, status;
   uint32_t rng_ctr, env_id;
   // ---- control-step scratch
-  real target[NU], ctrl[NU], act_force[NU];
+  real target[NU], ctrl[NU], act_force[NU], kp_step[NU], kd_step[NU];
   // ---- kinematics / dynamics
   real sc[NU][2];
   real o[3], xr[NL][3], xmat[NL][9];
@@ -1502,17 +1503,30 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
                       int32_t* done_out, int32_t* ended_out, int32_t* ep_len_out, real* ep_rew_out) {
   constexpr int NU = 2 * NJ, NOBS = Work<real, NJ>::NOBS;
   // action smoothing + nominal offsets (base_humanoid_env.py:209-212, robot_base.py:80-85)
+  // one event counter per control step: every draw of this step is keyed by rng_ctr + 1 (stored below)
   LHW_LANES(l) {
     if (l < NU) {
       const real t = m.smoothing * action[l] + (1 - m.smoothing) * w.prev_pred[l] + m.nominal[7 + l];
       w.target[l] = t;
       if (!w.have_prev) { w.prev_action[l] = t; w.prev_torque[l] = 0; }
+      real kp = m.kp[l], kd = m.kd[l];
+      if (m.pdrand_k > 0) {
+        // RobotBase._do_simulation (robots/robot_base.py:41-47): joint u -> stream 8 + u/4 (kp) / 11 + u/4 (kd), lane u%4
+        uint32_t u[4];
+        philox(seed, w.env_id, w.rng_ctr + 1, 8 + (l >> 2), u);
+        real lo = (1 - m.pdrand_k) * kp, hi = (1 + m.pdrand_k) * kp;
+        kp = lo + (hi - lo) * u01<real>(u[l & 3]);
+        philox(seed, w.env_id, w.rng_ctr + 1, 11 + (l >> 2), u);
+        lo = (1 - m.pdrand_k) * kd; hi = (1 + m.pdrand_k) * kd;
+        kd = lo + (hi - lo) * u01<real>(u[l & 3]);
+      }
+      w.kp_step[l] = kp; w.kd_step[l] = kd;
     }
   }
   LHW_SYNC();
   for (int sidx = 0; sidx < m.frame_skip; sidx++) {
     LHW_LANES(l) {
-      if (l < NU) w.ctrl[l] = m.kp[l] * (w.target[l] - w.act_len[l]) + m.kd[l] * ((real)0 - w.act_vel[l]);
+      if (l < NU) w.ctrl[l] = w.kp_step[l] * (w.target[l] - w.act_len[l]) + w.kd_step[l] * ((real)0 - w.act_vel[l]);
     }
     LHW_SYNC();
     if (alive) substep<real, NJ>(w, m, sidx == m.frame_skip - 1, block_sync);

@@ -28,7 +28,7 @@ class BatchedHumanoidEnv:
     def __init__(self, num_envs: int, model: str = "jvrc_walk", precision: int = 32, seed: int = 0,
                  first_env_id: int = 0, device: int | torch.device | None = None, max_traj_len: int = 400,
                  tolerance: float | None = None, max_iter: int | None = None, observation_noise: bool = True,
-                 domain_randomization: bool = True, init_noise: bool = True):
+                 domain_randomization: bool = True, init_noise: bool = True, pd_gain_randomization: float = 0.0):
         if not torch.cuda.is_available():
             raise _lib.LhwError("BatchedHumanoidEnv needs a CUDA device (no CPU fallback on the rollout path)")
         if device is None:
@@ -42,7 +42,8 @@ class BatchedHumanoidEnv:
         if tolerance is None and precision == 32:
             tolerance = 1e-6  # fp32 cannot reach the reference's 1e-10; gradient floor is ~1e-6 of the force scale
         flat = pack_model(self.mj, tolerance=tolerance, max_iter=max_iter, observation_noise=observation_noise,
-                          domain_randomization=domain_randomization, init_noise=init_noise)
+                          domain_randomization=domain_randomization, init_noise=init_noise,
+                          pd_gain_randomization=pd_gain_randomization)
         L = _lib.lib()
         h = ctypes.c_void_p()
         _lib.check(L.lhw_sim_create(ctypes.byref(h), flat.ctypes.data_as(ctypes.c_void_p), len(flat), self.precision,

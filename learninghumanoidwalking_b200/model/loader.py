@@ -21,7 +21,7 @@ def load_model(name: str = "jvrc_walk") -> dict:
 
 def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = None, kp=None, kd=None,
                self_collision: bool = True, observation_noise: bool = True, domain_randomization: bool = True,
-               init_noise: bool = True) -> np.ndarray:
+               init_noise: bool = True, pd_gain_randomization: float = 0.0) -> np.ndarray:
     links = mj["links"]
     nl = len(links)
     assert (nl - 1) % 2 == 0, "expected a free root + two equal serial chains"
@@ -112,4 +112,5 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
         b += rp["torso_com"]
     else:
         b += [0.0] * 23
+    b.append(float(pd_gain_randomization))     # RobotBase(pdrand_k) (robots/robot_base.py:5,43-47); 0 = off
     return np.asarray(b, dtype=np.float64)

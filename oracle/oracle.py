@@ -38,7 +38,7 @@ def load_clocks() -> dict:
 
 
 def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: int = 0, iterations: int | None = None,
-               self_collision: bool = True):
+               self_collision: bool = True, pdrand_k: float = 0.0):
     """Flat double layout consumed by orc_model_from_flat (keep in sync with sim_oracle.c)."""
     b: list[float] = []
     links = mj["links"]
@@ -118,6 +118,7 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
         b += rp["torso_com"]
     else:
         b += [0.0] * 29
+    b.append(float(pdrand_k))
     return np.array(b, dtype=np.float64)
 
 
@@ -125,13 +126,13 @@ class Oracle:
     """One compiled model + helpers to own N environments."""
 
     def __init__(self, name: str = "jvrc_walk", tolerance: float | None = None, solver: int = 0,
-                 iterations: int | None = None):
+                 iterations: int | None = None, pdrand_k: float = 0.0):
         self.lib = ctypes.CDLL(build())
         L = self.lib
         L.orc_energy.restype = ctypes.c_double
         self.mj = load_model_json(name)
         self.clocks = load_clocks()
-        flat = pack_model(self.mj, self.clocks, tolerance, solver, iterations)
+        flat = pack_model(self.mj, self.clocks, tolerance, solver, iterations, pdrand_k=pdrand_k)
         self._model = ctypes.create_string_buffer(L.orc_sizeof_model())
         rc = L.orc_model_from_flat(self._model, flat.ctypes.data_as(ctypes.c_void_p), len(flat))
         if rc != 0:

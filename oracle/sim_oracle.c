@@ -171,6 +171,7 @@ int orc_model_from_flat(orc_model* m, const double* b, int n) {
   for (int k = 0; k < 3; k++) m->rest_mc[k] = RD();
   for (int k = 0; k < 9; k++) m->rest_Io[k] = RD();
   for (int k = 0; k < 3; k++) m->torso_com[k] = RD();
+  m->pdrand_k = RD();
 #undef RD
   return p == n ? 0 : -100 - (p > n);
 }
@@ -1133,11 +1134,29 @@ void orc_step(const orc_model* m, orc_env* e, const double* action, double* obs,
     memcpy(e->prev_torque, e->act_force, sizeof(e->prev_torque));
     e->have_prev = 1;
   }
+  e->rng_ctr++;   /* one event counter per control step; every draw of this step is keyed by it */
+  double kp[ORC_NU], kd[ORC_NU];
+  memcpy(kp, m->kp, sizeof(kp));
+  memcpy(kd, m->kd, sizeof(kd));
+  if (m->pdrand_k > 0) {
+    /* RobotBase._do_simulation (robots/robot_base.py:41-47): kp ~ U((1-k) kp, (1+k) kp), then kd likewise, once per
+     * control step.  joint u -> stream 8 + u/4 (kp) / 11 + u/4 (kd), lane u%4 */
+    uint32_t w[4];
+    for (int u = 0; u < nu; u++) {
+      if ((u & 3) == 0) orc_philox(e->seed, e->env_id, e->rng_ctr, 8 + (u >> 2), w);
+      double lo = (1 - m->pdrand_k) * m->kp[u], hi = (1 + m->pdrand_k) * m->kp[u];
+      kp[u] = lo + (hi - lo) * u01(w[u & 3]);
+    }
+    for (int u = 0; u < nu; u++) {
+      if ((u & 3) == 0) orc_philox(e->seed, e->env_id, e->rng_ctr, 11 + (u >> 2), w);
+      double lo = (1 - m->pdrand_k) * m->kd[u], hi = (1 + m->pdrand_k) * m->kd[u];
+      kd[u] = lo + (hi - lo) * u01(w[u & 3]);
+    }
+  }
   for (int s = 0; s < m->frame_skip; s++) {
-    for (int u = 0; u < nu; u++) ctrl[u] = m->kp[u] * (target[u] - e->act_len[u]) + m->kd[u] * (0.0 - e->act_vel[u]);
+    for (int u = 0; u < nu; u++) ctrl[u] = kp[u] * (target[u] - e->act_len[u]) + kd[u] * (0.0 - e->act_vel[u]);
     orc_mj_step(m, e, ctrl);
   }
-  e->rng_ctr++;
   task_step(m, e);
   if (m->task == ORC_TASK_STAND) calc_reward_stand(m, e, t);
   else calc_reward(m, e, target, t);
@@ -1205,6 +1224,20 @@ void orc_calc_reward(const orc_model* m, const orc_env* e, const double* target,
   else calc_reward(m, e, target, terms);
 }
 /* test hooks for the H1 pieces pinned by tests/golden/h1_*.json (each uses the env's current rng_ctr) */
+/* the PD gains a control step with event counter rng_ctr would use */
+void orc_test_pd_gains(const orc_model* m, const orc_env* e, double* kp, double* kd) {
+  uint32_t w[4];
+  for (int u = 0; u < m->nu; u++) {
+    if ((u & 3) == 0) orc_philox(e->seed, e->env_id, e->rng_ctr, 8 + (u >> 2), w);
+    double lo = (1 - m->pdrand_k) * m->kp[u], hi = (1 + m->pdrand_k) * m->kp[u];
+    kp[u] = lo + (hi - lo) * u01(w[u & 3]);
+  }
+  for (int u = 0; u < m->nu; u++) {
+    if ((u & 3) == 0) orc_philox(e->seed, e->env_id, e->rng_ctr, 11 + (u >> 2), w);
+    double lo = (1 - m->pdrand_k) * m->kd[u], hi = (1 + m->pdrand_k) * m->kd[u];
+    kd[u] = lo + (hi - lo) * u01(w[u & 3]);
+  }
+}
 void orc_test_randomize_dynamics(const orc_model* m, orc_env* e) { randomize_dynamics(m, e); }
 void orc_test_apply_perturbation(const orc_model* m, orc_env* e) { apply_perturbation(m, e); }
 void orc_test_get_obs(const orc_model* m, const orc_env* e, double* obs) { get_obs(m, e, obs); }

@@ -97,6 +97,7 @@ typedef struct {
   double geom_pts[ORC_MAXGEOM][ORC_MAXPTS][3], geom_radius[ORC_MAXGEOM];
   /* root link = randomisable pelvis body + welded rest (H1) */
   double pel_mass, pel_com[3], pel_Ic[9], rest_mass, rest_mc[3], rest_Io[9], torso_com[3];
+  double pdrand_k;                  /* RobotBase(pdrand_k): per-step PD gain randomisation, 0 = off (the reference's default) */
 } orc_model;
 
 typedef struct {

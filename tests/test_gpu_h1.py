@@ -142,3 +142,23 @@ def test_ppo_trains_on_the_h1_environment(tmp_path):
     assert torch.equal(finals[0], finals[1])     # same seed, bit-identical weights
     actor = torch.load(tmp_path / "actor_0.pt", weights_only=False)   # saved at eval_freq boundaries (itr 0)
     assert actor(batch.states[:4]).shape == (4, 10)
+
+
+def test_h1_pd_gain_randomisation_matches_oracle():
+    """BASELINE configs[3] names domain-randomised PD gains: RobotBase(pdrand_k) (robots/robot_base.py:41-47, off in every
+    reference env) is available as pd_gain_randomization=k; CUDA path vs oracle with k = 0.3."""
+    from learninghumanoidwalking_b200.envs import BatchedHumanoidEnv
+    from oracle.oracle import Oracle
+    o, n = Oracle("h1", tolerance=1e-14, pdrand_k=0.3), 8
+    env = BatchedHumanoidEnv(n, model="h1", precision=64, seed=4, first_env_id=1, max_traj_len=50, tolerance=1e-14,
+                             pd_gain_randomization=0.3)
+    envs = o.make_envs(n, seed=4, first_id=1)
+    assert _rel(env.reset().cpu().numpy(), o.batch_reset(envs, n)) < 1e-9
+    rng = np.random.RandomState(0)
+    for k in range(60):
+        a = rng.normal(size=(n, 10)) * 0.3
+        o_obs, _, _, o_rew, o_done, o_end = o.batch_step(envs, n, a, max_traj_len=50)
+        g_obs, g_rew, g_done, g_end = env.step(torch.as_tensor(a, device="cuda", dtype=env.dtype))
+        assert (g_done.cpu().numpy() == o_done).all() and (g_end.cpu().numpy() == o_end).all()
+        assert _rel(g_obs.cpu().numpy(), o_obs) < 1e-7 and _rel(g_rew.cpu().numpy(), o_rew) < 1e-7
+    env.close()

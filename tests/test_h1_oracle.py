@@ -290,3 +290,40 @@ def test_kernel_source_h1_fp32_stays_close(h1):
         # torque observations (scale 100) dominate the absolute error; compare in normalised units
         std = np.concatenate(([0.2, 0.2, 1, 1, 1], 0.5 * np.ones(10), 4 * np.ones(10), 100 * np.ones(10)))
         assert (np.abs(oo - eo) / std).max() < 5e-2 and np.abs(rr - er).max() < 5e-3
+
+
+# ---------------------------------------------------------------------------------- PD-gain randomisation (RobotBase pdrand_k)
+def test_pd_gain_randomisation_matches_reference_robot_base():
+    """robots/robot_base.py:41-47 fed with the oracle's Philox words must give the oracle's gains."""
+    for c in gold("h1_pd_gain_randomization.json"):
+        o = O.Oracle("h1", pdrand_k=c["k"])
+        envs = o.make_envs(1, seed=c["seed"], first_id=c["env_id"])
+        o.set_field(envs, 0, "rng_ctr", [c["ctr"]])
+        kp, kd = np.zeros(12), np.zeros(12)
+        o.lib.orc_test_pd_gains(o._model, o.env_ptr(envs, 0), _p(kp), _p(kd))
+        assert np.abs(kp[:10] - c["kp"]).max() < 1e-12 and np.abs(kd[:10] - c["kd"]).max() < 1e-13
+
+
+@pytest.mark.parametrize("name,nu", [("h1", 10), ("jvrc_walk", 12)])
+def test_kernel_source_matches_oracle_with_pd_gain_randomisation(name, nu):
+    from emu import Emu
+    from learninghumanoidwalking_b200.model import load_model, pack_model
+    o = O.Oracle(name, tolerance=1e-14, pdrand_k=0.3)
+    N = 3
+    e = Emu(pack_model(load_model(name), tolerance=1e-14, pd_gain_randomization=0.3), 64, N, seed=6, first_id=2)
+    envs = o.make_envs(N, seed=6, first_id=2)
+    assert np.abs(o.batch_reset(envs, N) - e.reset()).max() < 1e-12
+    rng = np.random.RandomState(1)
+    o0 = O.Oracle(name, tolerance=1e-14)            # same seeds, gains not randomised: must diverge from the above
+    envs0 = o0.make_envs(N, seed=6, first_id=2)
+    o0.batch_reset(envs0, N)
+    differs = False
+    for t in range(40):
+        a = rng.normal(size=(N, nu)) * 0.3
+        oo, _, tt, rr, dd, ee = o.batch_step(envs, N, a, max_traj_len=30)
+        eo, _, etm, er, ed, een, *_ = e.step(a, max_traj_len=30)
+        assert (dd == ed).all() and (ee == een).all()
+        assert np.abs(oo - eo).max() < 1e-8 and np.abs(rr - er).max() < 1e-10
+        if t < 5:
+            differs |= np.abs(o0.batch_step(envs0, N, a, max_traj_len=30)[0] - oo).max() > 1e-6
+    assert differs

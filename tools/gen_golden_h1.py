@@ -51,10 +51,11 @@ class WordFeed:
         return w
 
     def uniform(self, lo, hi, size=None):
-        n = 1 if size is None else int(size)
+        vec = size is not None or np.ndim(lo) > 0
+        n = int(size) if size is not None else (len(lo) if np.ndim(lo) > 0 else 1)
         u = np.array([(self._u() >> 8) * (1.0 / 16777216.0) for _ in range(n)])
         out = lo + (hi - lo) * u
-        return float(out[0]) if size is None else out
+        return out if vec else float(out[0])
 
     def randint(self, n):
         return (self._u() * n) >> 32
@@ -236,6 +237,46 @@ def main():
     finally:
         np.random.uniform, np.random.randint = real_uniform, real_randint
     json.dump(dict(init_noise=init, observation_noise=obsn), open(os.path.join(OUT, "h1_noise.json"), "w"))
+
+    # ------------------------------------------------------------------ RobotBase PD-gain randomisation (pdrand_k)
+    rb = load_by_path("ref_robot_base", "robots/robot_base.py")
+
+    class PDClient:
+        def __init__(self):
+            self.gains = []
+
+        def nu(self): return 10
+        def sim_dt(self): return 0.001
+        def set_pd_gains(self, kp, kd): self.gains.append((np.array(kp, dtype=float), np.array(kd, dtype=float)))
+        def step_pd(self, p, v): return np.zeros(10)
+        def get_act_joint_velocities(self): return np.zeros(10)
+        def get_gear_ratios(self): return np.ones(10)
+        def set_motor_torque(self, tau, motor_dyn=False): pass
+        def step(self): pass
+
+    pd = []
+    try:
+        for case in range(6):
+            seed, env_id, ctr = int(rng.randint(1 << 30)), int(rng.randint(1 << 20)), int(rng.randint(1, 1 << 20))
+            k = float(rng.choice([0.1, 0.2, 0.3]))
+            words = []
+            for s_ in (8, 9, 10):
+                words += o.philox(seed, env_id, ctr, s_)
+            words = words[:10]
+            w2 = []
+            for s_ in (11, 12, 13):
+                w2 += o.philox(seed, env_id, ctr, s_)
+            words += w2[:10]
+            client = PDClient()
+            robot = rb.RobotBase(np.array([cfg["kp"], cfg["kd"]]), cfg["control_dt"], client, None, pdrand_k=k)
+            feed = WordFeed(words)
+            np.random.uniform, np.random.randint = feed.uniform, feed.randint
+            robot._do_simulation(np.zeros(10), 2)
+            kp, kd = client.gains[-1]
+            pd.append(dict(seed=seed, env_id=env_id, ctr=ctr, k=k, kp=kp.tolist(), kd=kd.tolist()))
+    finally:
+        np.random.uniform, np.random.randint = real_uniform, real_randint
+    json.dump(pd, open(os.path.join(OUT, "h1_pd_gain_randomization.json"), "w"))
     print("H1 golden vectors written to", os.path.abspath(OUT))
 
 
