@@ -107,6 +107,10 @@ def effective_cpus() -> int:
 WORKLOADS = {
     "jvrc_walk": dict(model="jvrc_walk", metric="env-steps/sec jvrc_walk",
                       desc="jvrc_walk {n} envs/GPU (BASELINE configs[1]), JVRC-1 sim_dt=0.001 control_dt=0.025 flat terrain"),
+    "jvrc_step": dict(model="jvrc_step", metric="env-steps/sec jvrc_step",
+                      desc="jvrc_step footstep-plan task {n} envs/GPU (BASELINE configs[2]), JVRC-1 sim_dt=0.001 control_dt=0.025, "
+                           "20 stepping-stone slabs per env (footstep sequences, floor dropped in FORWARD mode, 0.1 m stairs: "
+                           "iteration_count = inf) in the kernel"),
     "h1": dict(model="h1", metric="env-steps/sec h1 standing",
                desc="h1 standing task {n} envs/GPU (BASELINE configs[3]), Unitree H1 sim_dt=0.001 control_dt=0.025, observation "
                     "noise + dynamics randomisation (damping, frictionloss, mass, CoM) + random pushes in the kernel"),
@@ -148,7 +152,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--workload", default="jvrc_walk", choices=sorted(WORKLOADS),
-                    help="jvrc_walk: the configuration BASELINE.json's metric is quoted on (default); h1: configs[3]")
+                    help="jvrc_walk: the configuration BASELINE.json's metric is quoted on (default); jvrc_step: configs[2]; h1: configs[3]")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -29,7 +29,9 @@ const char* lhw_last_error(void);
  * lhw_sim_create: replaces MujocoEnv.__init__ (envs/common/mujoco_env.py:16-36: MjSpec.compile +
  * MjData) and JvrcBaseEnv._setup_robot (envs/jvrc/jvrc_base.py:38-67): takes the compiled model
  * constants as a flat HOST float64 array (layout: learninghumanoidwalking_b200/model/loader.py).
- * The first word selects the robot/task variant: 6 = JVRC-1 + WalkingTask (envs/jvrc/jvrc_walk.py),
+ * The first word selects the robot/task variant: 106 = JVRC-1 + SteppingTask (envs/jvrc/jvrc_step.py,
+ * tasks/stepping_task.py: footstep sequences, 20 per-env stepping-stone slabs, floor dropped in FORWARD mode),
+ * 6 = JVRC-1 + WalkingTask (envs/jvrc/jvrc_walk.py),
  * 5 = Unitree H1 + StandingTask (envs/h1/h1_env.py, envs/h1/h1_base.py:31-63: mass overrides, PD gains,
  * StandingTask), whose step also runs the observation noise, dynamics randomisation, random pushes and
  * initial-pose noise of envs/common/base_humanoid_env.py:228-338 + envs/common/domain_randomization.py inside
@@ -38,7 +40,7 @@ int lhw_sim_create(lhw_sim** out, const double* model_flat_host, int n_flat, int
 int lhw_sim_destroy(lhw_sim* sim);
 int lhw_sim_state_reals(const lhw_sim* sim); /* real words per env in the state record */
 int lhw_sim_state_ints(const lhw_sim* sim);  /* int32 words per env in the state record */
-int lhw_sim_obs_dim(const lhw_sim* sim);     /* env.observation_space.shape[0] (37 jvrc_walk, 35 h1) */
+int lhw_sim_obs_dim(const lhw_sim* sim);     /* env.observation_space.shape[0] (37 jvrc_walk, 39 jvrc_step, 35 h1) */
 int lhw_sim_act_dim(const lhw_sim* sim);     /* env.action_space.shape[0] (12 jvrc_walk, 10 h1) */
 int lhw_sim_smem_bytes_per_env(const lhw_sim* sim);
 
@@ -67,6 +69,11 @@ int lhw_sim_step(lhw_sim* sim, void* state_r, int32_t* state_i, int n_envs, uint
 /* lhw_sim_bind: make `sim`'s model constants the resident ones (they live in one __constant__ object per (robot, precision),
  * shared by all sims of the process; lhw_sim_step/reset do this implicitly, a replayed CUDA graph cannot). */
 int lhw_sim_bind(lhw_sim* sim, void* stream);
+
+/* lhw_sim_set_step_height: SteppingTask curriculum (tasks/stepping_task.py:312): the host computes
+ * h = clip((iteration_count - 3000) / 8000, 0, 1) * 0.1 from `env.robot.iteration_count` (rl/workers/rollout_worker.py:95)
+ * and passes it here; it takes effect at the next task reset.  No-op for the other variants. */
+int lhw_sim_set_step_height(lhw_sim* sim, double h);
 
 /* number of kernels this library has launched since load (the bench's gpu_launches claim) */
 long long lhw_launch_count(void);

@@ -25,6 +25,7 @@ SIGNATURES = {
     "lhw_sim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lhw_sim_bind": (c_int, [c_void_p, c_void_p]),
+    "lhw_sim_set_step_height": (c_int, [c_void_p, ctypes.c_double]),
     "lhw_launch_count": (c_ll, []),
     "lhw_gae": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
     "lhw_adv_stats_words": (c_int, []),

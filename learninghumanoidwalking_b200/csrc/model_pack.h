@@ -9,12 +9,14 @@
 namespace lhw {
 
 // returns 0 on success, negative on malformed input
-template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b, int n) {
+// the first word is NJ + 100 * TK (6: jvrc_walk, 5: h1, 106: jvrc_step).  `plan_table` (STEP only): caller-owned buffer of
+// MAXPLAN * PLAN_STRIDE reals that receives the footstep plans; the caller points m.plans at its device copy.
+template <class real, int NJ, int TK> int fill_model(Model<real, NJ, TK>& m, const double* b, int n, real* plan_table = nullptr) {
   constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ;
   int p = 0;
   auto rd = [&]() -> double { return p < n ? b[p++] : (p++, 0.0); };
   memset(&m, 0, sizeof(m));
-  if ((int)rd() != NJ) return -1;
+  if ((int)rd() != NJ + 100 * TK) return -1;
   for (int i = 0; i < NL; i++) {
     for (int k = 0; k < 3; k++) m.link_pos[i][k] = (real)rd();
     for (int k = 0; k < 9; k++) m.link_rot[i][k] = (real)rd();
@@ -73,7 +75,7 @@ template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b
   m.fcap = (real)(total_mass * 9.8 * 0.5);  // tasks/rewards.py:129
   m.goal_height = (real)rd();
   m.period = (int)rd();
-  if (m.period < (Cfg<NJ>::STAND ? 0 : 1) || m.period > MAXPERIOD) return -2;
+  if (m.period < (Cfg<NJ, TK>::STAND ? 0 : 1) || m.period > MAXPERIOD) return -2;
   for (int c = 0; c < 4; c++)
     for (int k = 0; k < m.period; k++) m.clock[c][k] = (real)rd();
   m.ncap = (int)rd();
@@ -94,7 +96,7 @@ template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b
   m.perturb_force = (real)rd(); m.perturb_torque = (real)rd(); m.init_noise = (real)rd();
   for (int f = 0; f < 2; f++) {
     const int npts = (int)rd();
-    if (npts != (Cfg<NJ>::SPHERES ? Cfg<NJ>::NPTS : 0)) return -7;
+    if (npts != (Cfg<NJ, TK>::SPHERES ? Cfg<NJ, TK>::NPTS : 0)) return -7;
     m.foot_radius[f] = (real)rd();
     for (int k = 0; k < npts; k++)
       for (int x = 0; x < 3; x++) m.foot_pts[f][k][x] = (real)rd();
@@ -107,6 +109,22 @@ template <class real, int NJ> int fill_model(Model<real, NJ>& m, const double* b
   for (int k = 0; k < 6; k++) m.rest_Io[k] = (real)rd();
   for (int k = 0; k < 3; k++) m.torso_com[k] = (real)rd();
   m.pdrand_k = (real)rd();
+  if constexpr (Cfg<NJ, TK>::STEP) {
+    for (int f = 0; f < 2; f++)
+      for (int k = 0; k < 3; k++) m.foot_site[f][k] = (real)rd();
+    for (int k = 0; k < 3; k++) m.slab_half[k] = (real)rd();
+    m.target_radius = (real)rd(); m.side_tol = (real)rd(); m.delay_frames = (int)rd(); m.step_height = (real)rd();
+    m.nplan = (int)rd();
+    if (m.nplan < 1 || m.nplan > MAXPLAN || !plan_table) return -8;
+    for (int i = 0; i < m.nplan; i++) {
+      const int len = (int)rd();
+      if (len < 1 || len > NSLAB) return -9;
+      real* row = plan_table + (size_t)i * PLAN_STRIDE;
+      row[0] = (real)len;
+      for (int k = 0; k < 3 * len; k++) row[1 + k] = (real)rd();
+    }
+    m.plans = plan_table;
+  }
   if (p != n) return -3;
   return 0;
 }

@@ -55,6 +55,20 @@
 #define LHW_ASSUME_SHARED(p) ((void)0)
 #endif
 
+// exclusive prefix count over the lanes of a warp of (a + b), a and b in {0, 1}; `run` is a warp-uniform running total.
+// In the CPU emulation the lanes run in order, so a plain running counter declared outside LHW_LANES does the same.
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+#define LHW_PREFIX2(a, b, run, pos)                                                                              \
+  do {                                                                                                           \
+    const unsigned _ma = __ballot_sync(0xffffffffu, (a)), _mb = __ballot_sync(0xffffffffu, (b));                 \
+    const unsigned _lt = (1u << (threadIdx.x & 31)) - 1u;                                                        \
+    (pos) = (run) + __popc(_ma & _lt) + __popc(_mb & _lt);                                                       \
+    (run) += __popc(_ma) + __popc(_mb);                                                                          \
+  } while (0)
+#else
+#define LHW_PREFIX2(a, b, run, pos) do { (pos) = (run); (run) += ((a) ? 1 : 0) + ((b) ? 1 : 0); } while (0)
+#endif
+
 // lane-strided loop over N items with a COMPILE-TIME trip count (the item guard vanishes when N is a multiple of 32)
 #define LHW_STRIDED(it, l, N) \
   _Pragma("unroll") for (int _k = 0, it = (l); _k < ((N) + 31) / 32; _k++, it += 32) if ((N) % 32 == 0 || it < (N))
@@ -69,15 +83,23 @@ constexpr int MAXPAIR = 64;
 
 // robot / task variant, keyed by the chain length NJ.  Everything variant-specific below is `if constexpr` on these
 // flags, so each instantiation only carries its own code.
-template <int NJ> struct Cfg;
-template <> struct Cfg<6> {  // JVRC-1, WalkingTask: box feet (mjc_PlaneBox: at most 4 of the 8 corners per foot)
+template <int NJ, int TK> struct Cfg;
+template <> struct Cfg<6, 0> {  // JVRC-1, WalkingTask: box feet (mjc_PlaneBox: at most 4 of the 8 corners per foot)
   static constexpr int CPF = 4, NPTS = 8;
-  static constexpr bool SPHERES = false, FLOSS = false, PERENV = false, STAND = false;
+  static constexpr bool SPHERES = false, FLOSS = false, PERENV = false, STAND = false, STEP = false;
 };
-template <> struct Cfg<5> {  // Unitree H1, StandingTask: 3 capsules per foot = 6 end spheres; dof friction loss;
+template <> struct Cfg<5, 0> {  // Unitree H1, StandingTask: 3 capsules per foot = 6 end spheres; dof friction loss;
   static constexpr int CPF = 6, NPTS = 6;  // per-env randomised mass / com / damping / frictionloss; xfrc perturbations
-  static constexpr bool SPHERES = true, FLOSS = true, PERENV = true, STAND = true;
+  static constexpr bool SPHERES = true, FLOSS = true, PERENV = true, STAND = true, STEP = false;
 };
+template <> struct Cfg<6, 1> {  // JVRC-1, SteppingTask: box feet on the floor + 20 per-env stepping-stone slabs;
+  static constexpr int CPF = 8, NPTS = 8;  // per foot 4 corner slots (with multiplicity) + 4 sole-edge x slab-boundary slots
+  static constexpr bool SPHERES = false, FLOSS = false, PERENV = false, STAND = false, STEP = true;
+};
+constexpr int NSLAB = 20;          // stepping stones per env (envs/jvrc/gen_xml.py:147-153)
+constexpr int NCORNER = 4;         // corner slots per foot (mjc_PlaneBox keeps at most 4)
+constexpr int MAXPLAN = 128, PLAN_STRIDE = 1 + 3 * NSLAB;   // footstep plan table: [len, (x y theta) * len]
+enum { ST_CURVED = 0, ST_STANDING = 1, ST_BACKWARD = 2, ST_LATERAL = 3, ST_FORWARD = 4 };  // tasks/stepping_task.py:268-271
 
 enum { STANDING = 0, INPLACE = 1, FORWARD = 2 };
 
@@ -131,14 +153,14 @@ template <class real> LHW_DEV real u01(uint32_t u) { return (real)(u >> 8) * (re
 LHW_DEV int randint(uint32_t u, int n) { return (int)(((uint64_t)u * (uint64_t)n) >> 32); }
 
 // ---------------------------------------------------------------- model constants (one per robot/task)
-template <class real, int NJ> struct Model {
+template <class real, int NJ, int TK> struct Model {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
   static constexpr int NT = 21 + NJ * (NJ + 1) + 12 * NJ;  // structurally non-zero lower-triangle entries of H
   real link_pos[NL][3], link_rot[NL][9], axis[NL][3];
   real mass[NL], com[NL][3], inertia[NL][6];  // xx yy zz xy xz yz about com, link frame
   real armature[NV], damping[NV], range_lo[NV], range_hi[NV], dof_invw[NV];
   real foot_pos[2][3], foot_size[2][3], foot_invw[2];
-  real foot_pts[2][Cfg<NJ>::NPTS][3], foot_radius[2];  // SPHERES: sphere centres in the foot link frame
+  real foot_pts[2][Cfg<NJ, TK>::NPTS][3], foot_radius[2];  // SPHERES: sphere centres in the foot link frame
   real h, grav[3];
   real K, B, solimp[5], mu, mu_reg;  // mu_reg = mu * sqrt(1/impratio)
   real tol2;                         // (tolerance * meaninertia * nv)^2 : threshold on |grad|^2
@@ -155,30 +177,34 @@ template <class real, int NJ> struct Model {
   real pdrand_k;   // RobotBase(pdrand_k): PD gains ~ U((1-k) g, (1+k) g) once per control step; 0 = off (reference default)
   real pel_mass, pel_com[3], pel_Ic[6], rest_mass, rest_mc[3], rest_Io[6], torso_com[3];  // root link = pelvis body + welded rest
   int axis_id[NL];  // 0/1/2: hinge axis is +e_x/+e_y/+e_z of the link frame AND link_rot is the identity (fast FK path); -1: general
+  // SteppingTask (Cfg::STEP): force-sensor sites, slab half sizes, target logic, curriculum step height, footstep plans
+  real foot_site[2][3], slab_half[3], target_radius, side_tol, step_height;
+  int delay_frames, nplan;
+  const real* plans;   // [nplan][PLAN_STRIDE] in global memory (host memory in the CPU emulation)
 };
 
 // Out-of-line device routines must not read the model through a generic reference (that turns every constant-bank
 // LDC into a generic load): the translation unit that owns the __constant__ object specialises this hook; the default
 // (host emulation) just returns what it was given.
-template <class real, int NJ> struct ModelHome {
-  static LHW_DEV const Model<real, NJ>& get(const Model<real, NJ>& passed) { return passed; }
+template <class real, int NJ, int TK> struct ModelHome {
+  static LHW_DEV const Model<real, NJ, TK>& get(const Model<real, NJ, TK>& passed) { return passed; }
 };
-template <class real, int NJ> LHW_DEV const Model<real, NJ>& model_ref(const Model<real, NJ>& passed) {
-  return ModelHome<real, NJ>::get(passed);
+template <class real, int NJ, int TK> LHW_DEV const Model<real, NJ, TK>& model_ref(const Model<real, NJ, TK>& passed) {
+  return ModelHome<real, NJ, TK>::get(passed);
 }
 
-template <class real, int NJ> struct Dims {
+template <class real, int NJ, int TK> struct Dims {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
-  static constexpr int NOBS = Cfg<NJ>::STAND ? 5 + 3 * NU : 5 + 2 * NU + 8;
+  static constexpr int NOBS = Cfg<NJ, TK>::STAND ? 5 + 3 * NU : (Cfg<NJ, TK>::STEP ? 5 + 2 * NU + 10 : 5 + 2 * NU + 8);
   // real-valued state record per env (HBM, env-major so one warp streams its env's record contiguously)
-  static constexpr int NPARAM = Cfg<NJ>::PERENV ? NL + 3 * NL + 6 + 2 * NU + 3 + 12 : 0;
+  static constexpr int NPARAM = Cfg<NJ, TK>::PERENV ? NL + 3 * NL + 6 + 2 * NU + 3 + 12 : (Cfg<NJ, TK>::STEP ? 4 * NSLAB + 5 : 0);
   static constexpr int NSTATE_R = NQ + NV + NV + 5 * NU + 3 + 1 + NPARAM;
 };
 
 // ---------------------------------------------------------------- arrow-packed symmetric matrix
 // ordering [root | chain0 | chain1]; chain0-chain1 coupling is structurally zero and not stored
 // 16-byte aligned (as is Work): lets the compiler fuse neighbouring shared-memory accesses into LDS.64 / LDS.128
-template <class real, int NJ> struct alignas(16) Arrow {
+template <class real, int NJ, int TK> struct alignas(16) Arrow {
   real r[6][6];      // root block (M: full symmetric; factor: lower triangle)
   real x[2][6][NJ];  // coupling  x[chain][root dof][chain dof]   (factor: X = B L^-T)
   real c[2][NJ][NJ]; // chain blocks (M: full symmetric; factor: lower triangle)
@@ -186,27 +212,34 @@ template <class real, int NJ> struct alignas(16) Arrow {
 
 // ---------------------------------------------------------------- per-warp working set (shared memory)
 // persistent state (mirrors the HBM record, same order); variants with per-env model parameters append them
-template <class real, int NJ> struct Persist {
+template <class real, int NJ, int TK> struct Persist {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ;
   real qpos[NQ], qvel[NV], qacc_warm[NV], act_len[NU], act_vel[NU], prev_pred[NU], prev_action[NU], prev_torque[NU];
   real mode_ref[3], ep_rew;
 };
-template <class real, int NJ> struct PersistRand : Persist<real, NJ> {
+template <class real, int NJ, int TK> struct PersistRand : Persist<real, NJ, TK> {
   static constexpr int NL = 1 + 2 * NJ, NU = 2 * NJ;
   real p_mass[NL], p_com[NL][3], p_inertia0[6];  // link masses / coms; root inertia about its com (xx yy zz xy xz yz)
   real p_damping[NU], p_floss[NU];
   real p_pelcom[3];                              // com of the pelvis BODY (point of application of xfrc[0])
   real xfrc[2][6];                               // world [force, torque] on the pelvis / torso bodies
 };
+// SteppingTask: the footstep sequence (= the slab poses: slab k's top face passes through seq[k]) and the task counters
+template <class real, int NJ, int TK> struct PersistStep : Persist<real, NJ, TK> {
+  real seq[NSLAB][4];   // x y z theta, world
+  real tk[5];           // seq_len, t1, t2, target_reached, target_reached_frames (small integers, held exactly)
+};
 template <bool C, class A, class B> struct Select { typedef A type; };
 template <class A, class B> struct Select<false, A, B> { typedef B type; };
 
-template <class real, int NJ>
-struct alignas(16) Work : Select<Cfg<NJ>::PERENV, PersistRand<real, NJ>, Persist<real, NJ>>::type {
+template <class real, int NJ, int TK>
+struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
+                                 typename Select<Cfg<NJ, TK>::STEP, PersistStep<real, NJ, TK>, Persist<real, NJ, TK>>::type>::type {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
-  static constexpr int CPF = Cfg<NJ>::CPF, NCON = 2 * CPF, NEDGE = 4 * NCON, NPTS = Cfg<NJ>::NPTS;
-  static constexpr int NOBS = Dims<real, NJ>::NOBS;
-  static constexpr int NFL = Cfg<NJ>::FLOSS ? NU : 1;
+  static constexpr int CPF = Cfg<NJ, TK>::CPF, NCON = 2 * CPF, NEDGE = 4 * NCON, NPTS = Cfg<NJ, TK>::NPTS;
+  static constexpr int NOBS = Dims<real, NJ, TK>::NOBS;
+  static constexpr int NFL = Cfg<NJ, TK>::FLOSS ? NU : 1;
+  static constexpr int NSL = Cfg<NJ, TK>::STEP ? NSLAB : 1, NST = Cfg<NJ, TK>::STEP ? 1 : 0;
   int phase, mode, traj_len, ep_len, have_prev, status;
   uint32_t rng_ctr, env_id;
   // ---- control-step scratch
@@ -216,11 +249,15 @@ struct alignas(16) Work : Select<Cfg<NJ>::PERENV, PersistRand<real, NJ>, Persist
   real o[3], xr[NL][3], xmat[NL][9];
   real S[NV][6];
   real V[NL][6];
-  Arrow<real, NJ> M, H;
+  Arrow<real, NJ, TK> M, H;
   real hdinv[NV];
   real qfs[NV], qacc[NV], Ma[NV], grad[NV], sdir[NV], Ms[NV], vec[NV];
   // ---- contacts (slot = foot*4 + k), expressed through the foot's spatial motion: J_contact = P(p) S_foot
   int ncon[2];
+  // stepping stones: cos/sin of the slab yaws, per-corner multiplicity, crossing-slot distances
+  real slab_cs[NSL][2], cmul[NST * 16 + 1], xcd[NST * NCON + 1];
+  int ncorner[2];
+  real site[2][3], rquat[4], goal[8];   // lagged site_xpos / root xquat ; _goal_steps_{x,y,z,theta}
   real cpos[NCON][3], cD[NCON], cKid[NCON];
   real earef[NEDGE], ejar[NEDGE];
   int lside[NU];
@@ -234,6 +271,7 @@ struct alignas(16) Work : Select<Cfg<NJ>::PERENV, PersistRand<real, NJ>, Persist
       real A[NL][6], F[NL][6];
       real ccd[2 * NPTS];   // signed distance of each candidate point (box corner / sphere), > 0: not a candidate
       int cslot[NCON];
+      real cwp[NST * 16 + 1][3];   // STEP: foot-box corners relative to o
     };
     struct {
       real T[2][NA][6], Af[2][6][6], Ff[2][6], ya[2][6], ys[2][6];
@@ -353,10 +391,10 @@ template <class real> LHW_DEV real seg_seg_dist2(const real* p1, const real* q1,
 // substitution fused into the factorisation (the right-hand side rides along as one more "row")
 // A_c = L_c L_c',  X_c = B_c L_c^-T,  C - sum_c X_c X_c' = L_C L_C'.  Reciprocal pivots in hdinv; the diagonal of
 // the factor is never stored (nor read).  x (global dof order) is overwritten with the solution.
-template <class real, int NJ> LHW_DEVNI void arrow_factor_solve(Work<real, NJ>& w, real* x) {
+template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<real, NJ, TK>& w, real* x) {
   LHW_ASSUME_SHARED(&w);
   LHW_ASSUME_SHARED(x);
-  Arrow<real, NJ>& H = w.H;
+  Arrow<real, NJ, TK>& H = w.H;
 #pragma unroll
   for (int k = 0; k < NJ; k++) {
     LHW_LANES(l) {
@@ -488,7 +526,7 @@ template <class real, int NJ> LHW_DEVNI void arrow_factor_solve(Work<real, NJ>& 
 }
 
 // y = M x for the arrow-packed symmetric M (lane = dof), result written to out[dof]
-template <class real, int NJ> LHW_DEV real arrow_row_dot(const Arrow<real, NJ>& M, int d, const real* x) {
+template <class real, int NJ, int TK> LHW_DEV real arrow_row_dot(const Arrow<real, NJ, TK>& M, int d, const real* x) {
   real acc = 0;
   if (d < 6) {
 #pragma unroll
@@ -511,17 +549,17 @@ template <class real, int NJ> LHW_DEV real arrow_row_dot(const Arrow<real, NJ>& 
 // images of a dof-space vector x: outM = M x (lane = dof), outY[f] = S_foot x (lanes 20..31), then the pyramid-edge
 // rows e_out = J_edge x - e_sub and limit rows l_out = side * x - l_sub (inactive rows get `fill`).  Used for the warm
 // start (x = qacc, sub = aref, fill = 1) and for the search direction (x = s, sub = 0, fill = 0): one shared copy.
-template <class real, int NJ>
-LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const real* x, real* outM, real (*outY)[6],
+template <class real, int NJ, int TK>
+LHW_DEVNI void constraint_images(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, const real* x, real* outM, real (*outY)[6],
                                  real* e_out, real* l_out, real* f_out, const real* e_sub, const real* l_sub,
                                  const real* f_sub, real fill) {
-  constexpr int NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ, CPF = Cfg<NJ>::CPF, NEDGE = 8 * CPF;
-  const Model<real, NJ>& m = model_ref<real, NJ>(m_arg);
+  constexpr int NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ, CPF = Cfg<NJ, TK>::CPF, NEDGE = 8 * CPF;
+  const Model<real, NJ, TK>& m = model_ref<real, NJ, TK>(m_arg);
   LHW_ASSUME_SHARED(&w); LHW_ASSUME_SHARED(x); LHW_ASSUME_SHARED(outM); LHW_ASSUME_SHARED(outY);
   LHW_ASSUME_SHARED(e_out); LHW_ASSUME_SHARED(l_out);
   if (e_sub) { LHW_ASSUME_SHARED(e_sub); LHW_ASSUME_SHARED(l_sub); }
   LHW_LANES(l) {
-    if (l < NV) outM[l] = arrow_row_dot<real, NJ>(w.M, l, x);
+    if (l < NV) outM[l] = arrow_row_dot<real, NJ, TK>(w.M, l, x);
     else if (l >= 20) {
       const int f = (l - 20) / 6, e = (l - 20) - f * 6;
       real acc = 0;
@@ -544,7 +582,7 @@ LHW_DEVNI void constraint_images(Work<real, NJ>& w, const Model<real, NJ>& m_arg
     }
     if (l < NU) {
       l_out[l] = w.lside[l] ? w.lside[l] * x[6 + l] - (l_sub ? l_sub[l] : (real)0) : fill;
-      if constexpr (Cfg<NJ>::FLOSS) f_out[l] = x[6 + l] - (f_sub ? f_sub[l] : (real)0);
+      if constexpr (Cfg<NJ, TK>::FLOSS) f_out[l] = x[6 + l] - (f_sub ? f_sub[l] : (real)0);
     }
   }
   LHW_SYNC();
@@ -559,13 +597,13 @@ template <class real> LHW_DEV real floss_force(real D, real lim, real fl, real x
 }
 
 // ================================================================= one physics substep (mujoco.mj_step)
-template <class real, int NJ>
-LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bool last, const int block_sync = 0) {
+template <class real, int NJ, int TK>
+LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, const bool last, const int block_sync = 0) {
   constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NU = 2 * NJ, NA = 6 + NJ;
-  constexpr int CPF = Cfg<NJ>::CPF, NCON = 2 * CPF, NEDGE = 4 * NCON, NPTS = Cfg<NJ>::NPTS;
-  constexpr bool PERENV = Cfg<NJ>::PERENV, FLOSS = Cfg<NJ>::FLOSS;
+  constexpr int CPF = Cfg<NJ, TK>::CPF, NCON = 2 * CPF, NEDGE = 4 * NCON, NPTS = Cfg<NJ, TK>::NPTS;
+  constexpr bool PERENV = Cfg<NJ, TK>::PERENV, FLOSS = Cfg<NJ, TK>::FLOSS;
   LHW_ASSUME_SHARED(&w);
-  const Model<real, NJ>& m = model_ref<real, NJ>(m_arg);  // device: the __constant__ object itself (LDC), not a generic reference
+  const Model<real, NJ, TK>& m = model_ref<real, NJ, TK>(m_arg);  // device: the __constant__ object itself (LDC), not a generic reference
   // ---------------- P1 forward kinematics.  (a) sin/cos of all joints side by side + root rotation
   LHW_LANES(l) {
     if (l < NU) {
@@ -580,6 +618,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       R[6] = 2 * (q1 * q3 - q0 * q2); R[7] = 2 * (q2 * q3 + q0 * q1); R[8] = 1 - 2 * (q1 * q1 + q2 * q2);
       w.o[0] = w.qpos[0]; w.o[1] = w.qpos[1]; w.o[2] = w.qpos[2];
       w.xr[0][0] = w.xr[0][1] = w.xr[0][2] = 0;
+      if constexpr (Cfg<NJ, TK>::STEP) { w.rquat[0] = q0; w.rquat[1] = q1; w.rquat[2] = q2; w.rquat[3] = q3; }
     }
   }
   LHW_SYNC();
@@ -784,23 +823,56 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         w.F[l][c] = IA[c] + t1[c] + t2[c];
         w.F[l][3 + c] = IA[3 + c] + t3[c];
       }
-    } else if (Cfg<NJ>::SPHERES && l >= 16 && l < 16 + 2 * NPTS) {
+    } else if (Cfg<NJ, TK>::SPHERES && l >= 16 && l < 16 + 2 * NPTS) {
       // mjc_PlaneCapsule = two mjc_PlaneSphere: dist = centre height - radius, contact iff dist < 0
       const int f = (l - 16) / NPTS, i = (l - 16) - f * NPTS, lk = (f + 1) * NJ;
       const real* R = w.xmat[lk];
       const real* pt = m.foot_pts[f][i];
       const real cd = w.o[2] + w.xr[lk][2] + R[6] * pt[0] + R[7] * pt[1] + R[8] * pt[2] - m.foot_radius[f];
       w.ccd[l - 16] = cd < 0 ? cd : (real)1;
-    } else if (!Cfg<NJ>::SPHERES && l >= 16) {
+    } else if (!Cfg<NJ, TK>::SPHERES && l >= 16) {
       // mjc_PlaneBox against the ground plane z = 0 (normal +z): one lane per (foot, corner); a corner is a contact
       // candidate when it is below the plane and on the plane side of the box centre
       const int f = (l - 16) >> 3, i = (l - 16) & 7, lk = (f + 1) * NJ;
       const real* R = w.xmat[lk];
-      const real dist0 = w.o[2] + w.xr[lk][2] + R[6] * m.foot_pos[f][0] + R[7] * m.foot_pos[f][1] + R[8] * m.foot_pos[f][2];
       const real ld = R[6] * ((i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0]) +
                       R[7] * ((i & 2) ? m.foot_size[f][1] : -m.foot_size[f][1]) +
                       R[8] * ((i & 4) ? m.foot_size[f][2] : -m.foot_size[f][2]);
+      if constexpr (Cfg<NJ, TK>::STEP) {
+        // stepping stones: the corner rests on the HIGHEST surface under it (floor plane, or the top face of a slab whose
+        // footprint contains it); surfaces at exactly that height each contribute an identical contact -> multiplicity
+        real v[3], cr[3];
+        v[0] = ((i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0]) + m.foot_pos[f][0];
+        v[1] = ((i & 2) ? m.foot_size[f][1] : -m.foot_size[f][1]) + m.foot_pos[f][1];
+        v[2] = ((i & 4) ? m.foot_size[f][2] : -m.foot_size[f][2]) + m.foot_pos[f][2];
+        mv3(R, v, cr);
+#pragma unroll
+        for (int x = 0; x < 3; x++) { cr[x] += w.xr[lk][x]; w.cwp[l - 16][x] = cr[x]; }
+        const real ax = w.o[0] + cr[0], ay = w.o[1] + cr[1], az = w.o[2] + cr[2];
+        const real floor_z = w.mode == ST_FORWARD ? (real)-2 : (real)0;   // stepping_task.py:332-334
+        real best = 0;
+        int have = 0, mult = 0;
+        if (az - floor_z < 0) { best = floor_z; have = 1; mult = 1; }
+#pragma unroll 1
+        for (int sidx = 0; sidx < NSLAB; sidx++) {
+          const real* sl = w.seq[sidx];
+          const real d = az - sl[2];
+          if (!(d < 0) || -d >= 2 * m.slab_half[2]) continue;
+          const real c = w.slab_cs[sidx][0], sn = w.slab_cs[sidx][1];
+          const real dx = ax - sl[0], dy = ay - sl[1];
+          const real ix = m.slab_half[0] - m_abs(c * dx + sn * dy), iy = m.slab_half[1] - m_abs(-sn * dx + c * dy);
+          if (ix < 0 || iy < 0) continue;
+          const real inset = ix < iy ? ix : iy;
+          if (-d > m.side_tol && -d > inset) continue;
+          if (!have || sl[2] > best) { best = sl[2]; have = 1; mult = 1; }
+          else if (sl[2] == best) mult++;
+        }
+        w.ccd[l - 16] = (have && !(ld > 0)) ? az - best : (real)1;
+        w.cmul[l - 16] = (real)mult;
+      } else {
+      const real dist0 = w.o[2] + w.xr[lk][2] + R[6] * m.foot_pos[f][0] + R[7] * m.foot_pos[f][1] + R[8] * m.foot_pos[f][2];
       w.ccd[l - 16] = (dist0 + ld > 0 || ld > 0) ? (real)1 : dist0 + ld;
+      }
     }
   }
   LHW_SYNC();
@@ -821,18 +893,101 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       int cnt = 0;
 #pragma unroll
       for (int i = 0; i < NPTS; i++)
-        if (cnt < CPF && !(w.ccd[f * NPTS + i] > 0)) { w.cslot[f * CPF + cnt] = i; cnt++; }
+        if (cnt < (Cfg<NJ, TK>::STEP ? NCORNER : CPF) && !(w.ccd[f * NPTS + i] > 0)) { w.cslot[f * CPF + cnt] = i; cnt++; }
       w.ncon[f] = cnt;
+      w.ncorner[f] = cnt;
     }
   }
   LHW_SYNC();
+  if constexpr (Cfg<NJ, TK>::STEP) {
+    // ---------------- P7x sole-edge x slab-boundary crossings: the remaining vertices of (sole rectangle) clipped against
+    // (slab footprint) -- the face-face manifold of a box-box test with the slab's top face as reference face.  One lane
+    // per (slab, sole edge): Liang-Barsky clip of the edge against the footprint; an entry / exit parameter strictly
+    // inside (0,1) is a polygon vertex.  Kept: the first CPF - NCORNER per foot in (slab, edge, entry-then-exit) order.
+#pragma unroll 1
+    for (int f = 0; f < 2; f++) {
+      int run = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < (4 * NSLAB + 31) / 32; pass++) {
+        LHW_LANES(l) {
+          const int t = pass * 32 + l;
+          int he = 0, hx = 0;
+          real pe[4], px[4];   // x, y, z relative to o, signed distance
+          if (t < 4 * NSLAB) {
+            const int sidx = t >> 2, ed = t & 3;
+            const int ia = ed == 0 ? 0 : ed == 1 ? 1 : ed == 2 ? 3 : 2, ib = ed == 0 ? 1 : ed == 1 ? 3 : ed == 2 ? 2 : 0;
+            const real* A = w.cwp[f * 8 + ia];
+            const real* B = w.cwp[f * 8 + ib];
+            const real* sl = w.seq[sidx];
+            const real c = w.slab_cs[sidx][0], sn = w.slab_cs[sidx][1];
+            const real Ax = w.o[0] + A[0] - sl[0], Ay = w.o[1] + A[1] - sl[1], Bx = w.o[0] + B[0] - sl[0], By = w.o[1] + B[1] - sl[1];
+            const real ax = c * Ax + sn * Ay, ay = -sn * Ax + c * Ay, bx = c * Bx + sn * By, by = -sn * Bx + c * By;
+            const real dx = bx - ax, dy = by - ay;
+            real t0 = 0, t1 = 1;
+            bool ok = true;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+              const real pp = b == 0 ? -dx : b == 1 ? dx : b == 2 ? -dy : dy;
+              const real qq = b == 0 ? ax + m.slab_half[0] : b == 1 ? m.slab_half[0] - ax : b == 2 ? ay + m.slab_half[1] : m.slab_half[1] - ay;
+              if (pp == 0) { if (qq < 0) ok = false; }
+              else {
+                const real r = qq / pp;
+                if (pp < 0) { if (r > t1) ok = false; else if (r > t0) t0 = r; }
+                else { if (r < t0) ok = false; else if (r < t1) t1 = r; }
+              }
+            }
+            if (ok) {
+#pragma unroll
+              for (int side = 0; side < 2; side++) {
+                const real tt = side == 0 ? t0 : t1;
+                if (side == 0 ? !(t0 > 0) : !(t1 < 1)) continue;
+                const real zr = A[2] + tt * (B[2] - A[2]);
+                const real cd = (w.o[2] + zr) - sl[2];
+                if (!(cd < 0) || -cd > m.side_tol) continue;
+                real* o4 = side == 0 ? pe : px;
+                o4[0] = A[0] + tt * (B[0] - A[0]); o4[1] = A[1] + tt * (B[1] - A[1]); o4[2] = zr - (real)0.5 * cd; o4[3] = cd;
+                if (side == 0) he = 1; else hx = 1;
+              }
+            }
+          }
+          int pos;
+          LHW_PREFIX2(he, hx, run, pos);
+          if (he && pos < CPF - NCORNER) {
+            const int sl_ = f * CPF + w.ncorner[f] + pos;
+            w.cpos[sl_][0] = pe[0]; w.cpos[sl_][1] = pe[1]; w.cpos[sl_][2] = pe[2]; w.xcd[sl_] = pe[3];
+          }
+          if (hx && pos + he < CPF - NCORNER) {
+            const int sl_ = f * CPF + w.ncorner[f] + pos + he;
+            w.cpos[sl_][0] = px[0]; w.cpos[sl_][1] = px[1]; w.cpos[sl_][2] = px[2]; w.xcd[sl_] = px[3];
+          }
+        }
+      }
+      LHW_LANES(l) {
+        if (l == 0) w.ncon[f] = w.ncorner[f] + (run < CPF - NCORNER ? run : CPF - NCORNER);
+      }
+    }
+    LHW_SYNC();
+  }
   // ---------------- P7b per contact slot: position, impedance, regulariser, reference stiffness (lane = slot)
   LHW_LANES(l) {
     if (l < NCON && l - (l / CPF) * CPF < w.ncon[l / CPF]) {
-      const int f = l / CPF, lk = (f + 1) * NJ, i = w.cslot[l];
-      const real cd = w.ccd[f * NPTS + i];
+      const int f = l / CPF, lk = (f + 1) * NJ;
+      real cd, mult = 1;
+      if constexpr (Cfg<NJ, TK>::STEP) {
+        if (l - f * CPF < w.ncorner[f]) {
+          const int i = w.cslot[l];
+          cd = w.ccd[f * NPTS + i];
+          mult = w.cmul[f * NPTS + i];
+          w.cpos[l][0] = w.cwp[f * 8 + i][0]; w.cpos[l][1] = w.cwp[f * 8 + i][1];
+          w.cpos[l][2] = w.cwp[f * 8 + i][2] - (real)0.5 * cd;
+        } else {
+          cd = w.xcd[l];   // crossing slot: position already written by P7x
+        }
+      } else {
+      const int i = w.cslot[l];
+      cd = w.ccd[f * NPTS + i];
       real v[3], corner[3];
-      if constexpr (Cfg<NJ>::SPHERES) {
+      if constexpr (Cfg<NJ, TK>::SPHERES) {
         v[0] = m.foot_pts[f][i][0]; v[1] = m.foot_pts[f][i][1]; v[2] = m.foot_pts[f][i][2];
       } else {
         v[0] = ((i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0]) + m.foot_pos[f][0];
@@ -843,10 +998,11 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       w.cpos[l][0] = corner[0] + w.xr[lk][0];
       w.cpos[l][1] = corner[1] + w.xr[lk][1];
       // contact point: half way through the penetration (box corner), resp. sphere centre - n (r + dist/2)
-      w.cpos[l][2] = corner[2] + w.xr[lk][2] - (Cfg<NJ>::SPHERES ? m.foot_radius[f] + (real)0.5 * cd : (real)0.5 * cd);
+      w.cpos[l][2] = corner[2] + w.xr[lk][2] - (Cfg<NJ, TK>::SPHERES ? m.foot_radius[f] + (real)0.5 * cd : (real)0.5 * cd);
+      }
       const real imp = impedance(m.solimp, cd);
       const real Rn = m_max((real)1e-15, (1 - imp) / imp * (m.foot_invw[f] * (1 + m.mu * m.mu)));
-      w.cD[l] = (real)1 / (2 * m.mu_reg * m.mu_reg * Rn);
+      w.cD[l] = mult / (2 * m.mu_reg * m.mu_reg * Rn);
       w.cKid[l] = m.K * imp * cd;
     }
   }
@@ -934,7 +1090,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       P[12] = 0;  P[13] = -pz; P[14] = py; P[15] = -1; P[16] = 0; P[17] = 0;
     }
   }
-  constraint_images<real, NJ>(w, m, w.qacc, w.Ma, w.ya, w.ejar, w.ljar, w.fjar, w.earef, w.laref, w.faref, (real)1);
+  constraint_images<real, NJ, TK>(w, m, w.qacc, w.Ma, w.ya, w.ejar, w.ljar, w.fjar, w.earef, w.laref, w.faref, (real)1);
 
   // ---------------- P10 primal Newton on  1/2 (a-a_s)' M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
   // residuals (Ma, ejar, ljar) are carried incrementally: x += alpha * (direction image)
@@ -1054,9 +1210,9 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       }
     }
     LHW_SYNC();
-    arrow_factor_solve<real, NJ>(w, w.sdir);
+    arrow_factor_solve<real, NJ, TK>(w, w.sdir);
     // (g) images of the search direction: M s, foot spatial accelerations, edge / limit rates
-    constraint_images<real, NJ>(w, m, w.sdir, w.Ms, w.ys, w.ejv, w.ljv, w.fjv, (const real*)nullptr, (const real*)nullptr,
+    constraint_images<real, NJ, TK>(w, m, w.sdir, w.Ms, w.ys, w.ejv, w.ljv, w.fjv, (const real*)nullptr, (const real*)nullptr,
                                 (const real*)nullptr, (real)0);
     const real sMs = warp_sum<real>([&](int l) { return l < NV ? w.sdir[l] * w.Ms[l] : (real)0; });
     const real sg = warp_sum<real>([&](int l) { return l < NV ? w.sdir[l] * (w.Ma[l] - w.qfs[l]) : (real)0; });
@@ -1140,6 +1296,12 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
         real g = 0;
 #pragma unroll
         for (int c = 0; c < 3; c++) w.foot_vel[f][c] = w.V[lk][3 + c] + t[c];
+        if constexpr (Cfg<NJ, TK>::STEP) {
+          real st[3];
+          mv3(w.xmat[lk], m.foot_site[f], st);
+#pragma unroll
+          for (int c = 0; c < 3; c++) w.site[f][c] = w.o[c] + w.xr[lk][c] + st[c];
+        }
         for (int k = 0; k < w.ncon[f]; k++) {
           const real* cf = w.cF[f * CPF + k];
           g += m_sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]);  // norm of mj_contactForce, friction included
@@ -1194,7 +1356,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
   // ---------------- P12 mj_Euler: (M + h diag(damping)) a' = qfrc_smooth + qfrc_constraint ; integrate
   if (PERENV || m.any_damping) {
     LHW_LANES(l) {
-      constexpr int NW = (int)(sizeof(Arrow<real, NJ>) / sizeof(real));
+      constexpr int NW = (int)(sizeof(Arrow<real, NJ, TK>) / sizeof(real));
       const real* src = &w.M.r[0][0];
       real* dst = &w.H.r[0][0];
       for (int it = l; it < NW; it += 32) dst[it] = src[it];
@@ -1209,7 +1371,7 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
       }
     }
     LHW_SYNC();
-    arrow_factor_solve<real, NJ>(w, w.vec);
+    arrow_factor_solve<real, NJ, TK>(w, w.vec);
   } else {
     LHW_LANES(l) {
       if (l < NV) w.vec[l] = w.qacc[l];
@@ -1251,12 +1413,22 @@ LHW_DEVNI void substep(Work<real, NJ>& w, const Model<real, NJ>& m_arg, const bo
   LHW_SYNC();
 }
 
+// cos / sin of the slab yaws (stepping stones), once per launch and after every task reset
+template <class real, int NJ, int TK> LHW_DEV void slab_frames(Work<real, NJ, TK>& w) {
+  if constexpr (Cfg<NJ, TK>::STEP) {
+    LHW_LANES(l) {
+      if (l < NSLAB) m_sincos(w.seq[l][3], &w.slab_cs[l][1], &w.slab_cs[l][0]);
+    }
+    LHW_SYNC();
+  }
+}
+
 // ================================================================= environment level (one control step)
 // state record I/O: reals [qpos qvel qacc_warm act_len act_vel prev_pred prev_action prev_torque mode_ref ep_rew],
 // ints [phase mode traj_len ep_len rng_ctr have_prev status pad]; env-major, one coalesced stream per warp
-template <class real, int NJ>
-LHW_DEV void load_state(Work<real, NJ>& w, const real* sr, const int32_t* si, uint32_t env_id) {
-  constexpr int NR = Dims<real, NJ>::NSTATE_R;
+template <class real, int NJ, int TK>
+LHW_DEV void load_state(Work<real, NJ, TK>& w, const real* sr, const int32_t* si, uint32_t env_id) {
+  constexpr int NR = Dims<real, NJ, TK>::NSTATE_R;
   real* dst = w.qpos;  // persistent block is contiguous in Work, same order as the record
   LHW_LANES(l) {
     for (int it = l; it < NR; it += 32) dst[it] = sr[it];
@@ -1269,9 +1441,10 @@ LHW_DEV void load_state(Work<real, NJ>& w, const real* sr, const int32_t* si, ui
     }
   }
   LHW_SYNC();
+  slab_frames<real, NJ, TK>(w);
 }
-template <class real, int NJ> LHW_DEV void store_state(const Work<real, NJ>& w, real* sr, int32_t* si) {
-  constexpr int NR = Dims<real, NJ>::NSTATE_R;
+template <class real, int NJ, int TK> LHW_DEV void store_state(const Work<real, NJ, TK>& w, real* sr, int32_t* si) {
+  constexpr int NR = Dims<real, NJ, TK>::NSTATE_R;
   const real* src = w.qpos;
   LHW_LANES(l) {
     for (int it = l; it < NR; it += 32) sr[it] = src[it];
@@ -1284,7 +1457,7 @@ template <class real, int NJ> LHW_DEV void store_state(const Work<real, NJ>& w, 
 }
 
 // WalkModes.sample_ref (tasks/walking_task.py:33-40)
-template <class real, int NJ> LHW_DEV void sample_ref(Work<real, NJ>& w, uint32_t seed, uint32_t stream) {
+template <class real, int NJ, int TK> LHW_DEV void sample_ref(Work<real, NJ, TK>& w, uint32_t seed, uint32_t stream) {
   uint32_t u[4];
   philox(seed, w.env_id, w.rng_ctr, stream, u);
   if (w.mode == STANDING) {
@@ -1297,7 +1470,7 @@ template <class real, int NJ> LHW_DEV void sample_ref(Work<real, NJ>& w, uint32_
 }
 
 // observation (envs/jvrc/jvrc_base.py:133-145 + jvrc_walk.py:65-67): current qpos quat / qvel, LAGGED actuator state
-template <class real, int NJ> LHW_DEV void env_obs(Work<real, NJ>& w, const Model<real, NJ>& m, uint32_t seed) {
+template <class real, int NJ, int TK> LHW_DEV void env_obs(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, uint32_t seed) {
   (void)seed;
   constexpr int NU = 2 * NJ;
   LHW_LANES(l) {
@@ -1316,24 +1489,28 @@ template <class real, int NJ> LHW_DEV void env_obs(Work<real, NJ>& w, const Mode
       w.obs[1] = m_atan2(-M20, cy);
     } else if (l < 4) {
       w.obs[1 + l] = w.qvel[2 + l];
-    } else if (!Cfg<NJ>::STAND && l == 4) {
+    } else if (!Cfg<NJ, TK>::STAND && l == 4) {
       real sn, cs;
       m_sincos((real)(2 * M_PI) * w.phase / m.period, &sn, &cs);
       w.obs[5 + 2 * NU] = sn; w.obs[6 + 2 * NU] = cs;
-    } else if (!Cfg<NJ>::STAND && l == 5) {
+    } else if (Cfg<NJ, TK>::STEP && l == 5) {
+      real* e = w.obs + 7 + 2 * NU;   // envs/jvrc/jvrc_step.py:67-76: goal steps x[2] y[2] z[2] theta[2]
+#pragma unroll
+      for (int i = 0; i < 8; i++) e[i] = w.goal[i];
+    } else if (!Cfg<NJ, TK>::STAND && !Cfg<NJ, TK>::STEP && l == 5) {
       real* e = w.obs + 7 + 2 * NU;
       e[0] = w.mode == FORWARD; e[1] = w.mode == INPLACE; e[2] = w.mode == STANDING;
       e[3] = w.mode_ref[0]; e[4] = w.mode_ref[1]; e[5] = w.mode_ref[2];
     } else if (l >= 8 && l < 8 + NU) {
       w.obs[5 + l - 8] = w.act_len[l - 8];
       w.obs[5 + NU + l - 8] = w.act_vel[l - 8];
-      if constexpr (Cfg<NJ>::STAND) w.obs[5 + 2 * NU + l - 8] = w.act_force[l - 8];   // motor torques (h1_base.py:97)
+      if constexpr (Cfg<NJ, TK>::STAND) w.obs[5 + 2 * NU + l - 8] = w.act_force[l - 8];   // motor torques (h1_base.py:97)
     }
   }
   LHW_SYNC();
-  if constexpr (Cfg<NJ>::STAND) {
+  if constexpr (Cfg<NJ, TK>::STAND) {
     // uniform observation noise (base_humanoid_env.py:311-338): value i -> philox stream 40 + i/4, lane i%4
-    constexpr int NOBS = Dims<real, NJ>::NOBS;
+    constexpr int NOBS = Dims<real, NJ, TK>::NOBS;
     LHW_LANES(l) {
       for (int i = l; i < NOBS; i += 32) {
         const real sc = i < 2 ? m.obs_noise[0] : i < 5 ? m.obs_noise[1] : i < 5 + NU ? m.obs_noise[2]
@@ -1352,8 +1529,8 @@ template <class real, int NJ> LHW_DEV void env_obs(Work<real, NJ>& w, const Mode
 // randomize_dynamics (envs/common/domain_randomization.py:29-56) on counter-based streams: joint j -> stream 16 + j/2,
 // lanes 2(j%2) (frictionloss U(0,2)) and 2(j%2)+1 (damping U(0.02,2)); body b (pelvis, then the leg links) -> stream 21+b,
 // lane 0 mass scale U(0.95,1.05), lanes 1..3 ipos offset U(-0.01,0.01).  body_inertia is left alone, as in the reference.
-template <class real, int NJ> LHW_DEV void env_randomize(Work<real, NJ>& w, const Model<real, NJ>& m, uint32_t seed) {
-  if constexpr (Cfg<NJ>::PERENV) {
+template <class real, int NJ, int TK> LHW_DEV void env_randomize(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, uint32_t seed) {
+  if constexpr (Cfg<NJ, TK>::PERENV) {
     constexpr int NU = 2 * NJ;
     LHW_LANES(l) {
       if (l < NU) {
@@ -1399,8 +1576,8 @@ template <class real, int NJ> LHW_DEV void env_randomize(Work<real, NJ>& w, cons
 
 // apply_perturbation (domain_randomization.py:10-26): per body force U(-F,F)^3, torque U(-T,T)^3, then a coin that clears
 // the WHOLE xfrc_applied array.  body b -> streams 32+2b (force, lane 3 = coin) and 33+2b (torque)
-template <class real, int NJ> LHW_DEV void env_perturb(Work<real, NJ>& w, const Model<real, NJ>& m, uint32_t seed) {
-  if constexpr (Cfg<NJ>::PERENV) {
+template <class real, int NJ, int TK> LHW_DEV void env_perturb(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, uint32_t seed) {
+  if constexpr (Cfg<NJ, TK>::PERENV) {
     LHW_LANES(l) {
       if (l == 0) {
 #pragma unroll 1
@@ -1421,21 +1598,123 @@ template <class real, int NJ> LHW_DEV void env_perturb(Work<real, NJ>& w, const 
   }
 }
 
+// ---------------- SteppingTask (tasks/stepping_task.py), run by lane 0
+// update_target_steps (:207-213)
+template <class real, int NJ, int TK> LHW_DEV void step_update_targets(Work<real, NJ, TK>& w) {
+  w.tk[1] = w.tk[2];
+  w.tk[2] += 1;
+  if (w.tk[2] == w.tk[0]) w.tk[2] = w.tk[0] - 1;
+}
+// update_goal_steps (:188-205): targets t1, t2 in the root frame, R' (p - root_pos) and the yaw of R' Rz(theta)
+template <class real, int NJ, int TK> LHW_DEV void step_update_goals(Work<real, NJ, TK>& w) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) w.goal[i] = 0;
+  if (w.mode == ST_STANDING) return;
+  const real* R = w.xmat[0];
+#pragma unroll 1
+  for (int idx = 0; idx < 2; idx++) {
+    const int t = (int)w.tk[1 + idx];
+    const real* sq = w.seq[t];
+    const real d0 = sq[0] - w.o[0], d1 = sq[1] - w.o[1], d2 = sq[2] - w.o[2];
+    w.goal[0 + idx] = R[0] * d0 + R[3] * d1 + R[6] * d2;
+    w.goal[2 + idx] = R[1] * d0 + R[4] * d1 + R[7] * d2;
+    w.goal[4 + idx] = R[2] * d0 + R[5] * d1 + R[8] * d2;
+    const real c = w.slab_cs[t][0], sn = w.slab_cs[t][1];
+    const real r00 = R[0] * c + R[3] * sn, r10 = R[1] * c + R[4] * sn;
+    const real cy = m_sqrt(r00 * r00 + r10 * r10);
+    w.goal[6 + idx] = cy > (real)(4 * 2.220446049250313e-16) ? m_atan2(r10, r00) : (real)0;
+  }
+}
+// SteppingTask.reset (:243-334); draws: stream 3 lane 0 mode, lane 1 phase, lane 2 first-step offset / plan index / lateral
+// sign, lane 3 randint(2,4); stream 4 lane 0 sign of the step height
+template <class real, int NJ, int TK>
+LHW_DEV void step_task_reset(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, uint32_t seed) {
+  uint32_t u[4], v[4];
+  philox(seed, w.env_id, w.rng_ctr, 3, u);
+  philox(seed, w.env_id, w.rng_ctr, 4, v);
+  w.tk[3] = 0; w.tk[4] = 0; w.tk[1] = 0; w.tk[2] = 0;
+  w.phase = randint(u[1], 2) == 0 ? 0 : m.period / 2;
+  const real cm = u01<real>(u[0]);
+  w.mode = cm < (real)0.15 ? ST_CURVED : cm < (real)(0.15 + 0.05) ? ST_STANDING : cm < (real)(0.15 + 0.05 + 0.2) ? ST_BACKWARD
+           : cm < (real)(0.15 + 0.05 + 0.2 + 0.3) ? ST_LATERAL : ST_FORWARD;
+  real step_size = (real)0.3, step_height = 0;
+  const real step_gap = (real)0.15;
+  int num_steps = NSLAB;
+  if (w.mode == ST_STANDING) num_steps = 1;
+  else if (w.mode == ST_BACKWARD) step_size = (real)-0.1;
+  else if (w.mode == ST_LATERAL) step_size = (real)0.4;
+  else if (w.mode == ST_FORWARD) step_height = randint(v[0], 2) == 0 ? -m.step_height : m.step_height;
+  // transform_sequence (:123-136): about the mid-point of the foot bodies, yawed with the root
+  const real* R = w.xmat[0];
+  const real cyn = m_sqrt(R[0] * R[0] + R[3] * R[3]);
+  const real yaw = cyn > (real)(4 * 2.220446049250313e-16) ? m_atan2(R[3], R[0]) : (real)0;
+  real sy, cyw;
+  m_sincos(yaw, &sy, &cyw);
+  const real mid0 = w.o[0] + (w.xr[2 * NJ][0] + w.xr[NJ][0]) / 2, mid1 = w.o[1] + (w.xr[2 * NJ][1] + w.xr[NJ][1]) / 2;
+  int n = 0;
+  auto put = [&](real x, real y, real z, real th) {
+    w.seq[n][0] = mid0 + x * cyw - y * sy;
+    w.seq[n][1] = mid1 + x * sy + y * cyw;
+    w.seq[n][2] = z;
+    w.seq[n][3] = yaw + th;
+    n++;
+  };
+  if (w.mode == ST_CURVED) {
+    const real* plan = m.plans + (size_t)randint(u[2], m.nplan) * PLAN_STRIDE;
+    const int len = (int)plan[0];
+#pragma unroll 1
+    for (int i = 0; i < len; i++) put(plan[1 + 3 * i], plan[2 + 3 * i], 0, plan[3 + 3 * i]);
+  } else if (w.mode == ST_LATERAL) {
+    real y = 0;
+    const real c = randint(u[2], 2) == 0 ? (real)-1 : (real)1;
+#pragma unroll 1
+    for (int i = 1; i < num_steps; i++) {
+      if (i % 2) y += step_size; else y -= (real)(2.0 / 3.0) * step_size;
+      put(0, c * y, 0, 0);
+    }
+  } else {
+    const real first = (real)0.095 + (real)(0.105 - 0.095) * u01<real>(u[2]);
+    real y;
+    if (w.phase == m.period / 2 && 2 * (m.period / 2) == m.period) { put(0, -first, 0, 0); y = -step_gap; }
+    else { put(0, first, 0, 0); y = step_gap; }
+    real x = 0, z = 0;
+    const int c = 2 + randint(u[3], 2);
+#pragma unroll 1
+    for (int i = 1; i < num_steps - 1; i++) {
+      x += step_size;
+      y *= -1;
+      if (i > c) z += step_height;
+      put(x, y, z, 0);
+    }
+    put(x + step_size, -y, z, 0);
+  }
+  w.tk[0] = (real)n;
+  for (int i = n; i < NSLAB; i++) { w.seq[i][0] = 0; w.seq[i][1] = 0; w.seq[i][2] = -1; w.seq[i][3] = 0; }   // unused boxes (:322)
+  step_update_targets<real, NJ, TK>(w);
+#pragma unroll
+  for (int i = 0; i < 8; i++) w.goal[i] = 0;
+}
+
 // MujocoEnv.reset + BaseHumanoidEnv.reset_model + WalkingTask.reset
-template <class real, int NJ> LHW_DEV void env_reset(Work<real, NJ>& w, const Model<real, NJ>& m, uint32_t seed) {
+template <class real, int NJ, int TK> LHW_DEV void env_reset(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, uint32_t seed) {
   constexpr int NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ;
   LHW_LANES(l) {
     if (l == 0) w.rng_ctr++;
     if (l < NQ) w.qpos[l] = m.nominal[l];
     if (l < NV) { w.qvel[l] = 0; w.qacc_warm[l] = 0; }
     if (l < NU) { w.ctrl[l] = 0; w.prev_pred[l] = 0; }
-    if constexpr (Cfg<NJ>::PERENV) {
+    if constexpr (Cfg<NJ, TK>::PERENV) {
       if (l >= 20) (&w.xfrc[0][0])[l - 20] = 0;   // mj_resetData clears xfrc_applied
+    }
+    if constexpr (Cfg<NJ, TK>::STEP) {
+      // the settling steps below still see the PREVIOUS episode's slabs and floor (the reference edits the model in
+      // task.reset, after them); a freshly built env has its boxes below the floor (gen_xml.py:149)
+      if (l < NSLAB && w.tk[0] == 0) w.seq[l][2] = -1;
     }
   }
   LHW_SYNC();
-  if constexpr (Cfg<NJ>::PERENV) {
-    if (m.dynrand_interval > 0) env_randomize<real, NJ>(w, m, seed);   // base_humanoid_env.py:252-253
+  if constexpr (Cfg<NJ, TK>::PERENV) {
+    if (m.dynrand_interval > 0) env_randomize<real, NJ, TK>(w, m, seed);   // base_humanoid_env.py:252-253
     else {
       // randomisation disabled: the per-env parameter block is just the nominal model
       LHW_LANES(l) {
@@ -1473,22 +1752,25 @@ template <class real, int NJ> LHW_DEV void env_reset(Work<real, NJ>& w, const Mo
       LHW_SYNC();
     }
   }
-  for (int i = 0; i < 3; i++) substep<real, NJ>(w, m, false);
+  for (int i = 0; i < 3; i++) substep<real, NJ, TK>(w, m, false);
   LHW_LANES(l) {
     if (l == 0) {
-      if constexpr (!Cfg<NJ>::STAND) {
+      if constexpr (Cfg<NJ, TK>::STEP) {
+        step_task_reset<real, NJ, TK>(w, m, seed);
+      } else if constexpr (!Cfg<NJ, TK>::STAND) {
         uint32_t u[4];
         philox(seed, w.env_id, w.rng_ctr, 3, u);
         const real c = u01<real>(u[0]);
         w.mode = c < (real)0.6 ? STANDING : (c < (real)0.8 ? INPLACE : FORWARD);
-        sample_ref<real, NJ>(w, seed, 4);
+        sample_ref<real, NJ, TK>(w, seed, 4);
         w.phase = randint(u[1], m.period);
       }
       w.traj_len = 0; w.ep_len = 0; w.ep_rew = 0; w.status = 0;
     }
   }
   LHW_SYNC();
-  env_obs<real, NJ>(w, m, seed);
+  slab_frames<real, NJ, TK>(w);
+  env_obs<real, NJ, TK>(w, m, seed);
 }
 
 struct StepOut {
@@ -1497,11 +1779,11 @@ struct StepOut {
 };
 
 // BaseHumanoidEnv.step + the RolloutWorker's bookkeeping (traj_len truncation, auto-reset, episode stats)
-template <class real, int NJ>
-LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* action, uint32_t seed, int max_traj_len,
+template <class real, int NJ, int TK>
+LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const real* action, uint32_t seed, int max_traj_len,
                       int autoreset, const int block_sync, const int alive, real* obs_out, real* term_obs_out, real* reward_out, real* rew_terms_out,
                       int32_t* done_out, int32_t* ended_out, int32_t* ep_len_out, real* ep_rew_out) {
-  constexpr int NU = 2 * NJ, NOBS = Work<real, NJ>::NOBS;
+  constexpr int NU = 2 * NJ, NOBS = Work<real, NJ, TK>::NOBS;
   // action smoothing + nominal offsets (base_humanoid_env.py:209-212, robot_base.py:80-85)
   // one event counter per control step: every draw of this step is keyed by rng_ctr + 1 (stored below)
   LHW_LANES(l) {
@@ -1529,7 +1811,7 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
       if (l < NU) w.ctrl[l] = w.kp_step[l] * (w.target[l] - w.act_len[l]) + w.kd_step[l] * ((real)0 - w.act_vel[l]);
     }
     LHW_SYNC();
-    if (alive) substep<real, NJ>(w, m, sidx == m.frame_skip - 1, block_sync);
+    if (alive) substep<real, NJ, TK>(w, m, sidx == m.frame_skip - 1, block_sync);
     else LHW_BLOCK_SYNC(block_sync & 2);
     LHW_BLOCK_SYNC((block_sync & 1) && ((sidx + 1) % ((block_sync >> 4) + 1) == 0));   // every (block_sync>>4)+1 substeps
   }
@@ -1540,7 +1822,27 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
       w.have_prev = 1;
       w.rng_ctr++;
     }
-    if (!Cfg<NJ>::STAND && l == 0) {
+    if (Cfg<NJ, TK>::STEP && l == 0) {
+      if constexpr (Cfg<NJ, TK>::STEP) {
+        // SteppingTask.step (tasks/stepping_task.py:215-243)
+        w.phase += 1;
+        if (w.phase >= m.period) w.phase = 0;
+        const real* tp = w.seq[(int)w.tk[1]];
+        bool in = false;
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+          const real d0 = w.site[f][0] - tp[0], d1 = w.site[f][1] - tp[1], d2 = w.site[f][2] - tp[2];
+          if (m_sqrt(d0 * d0 + d1 * d1 + d2 * d2) < m.target_radius) in = true;
+        }
+        if (in) { w.tk[3] = 1; w.tk[4] += 1; } else { w.tk[3] = 0; w.tk[4] = 0; }
+        if (w.tk[3] != 0 && w.tk[4] >= (real)m.delay_frames) {
+          step_update_targets<real, NJ, TK>(w);
+          w.tk[3] = 0; w.tk[4] = 0;
+        }
+        step_update_goals<real, NJ, TK>(w);
+      }
+    }
+    if (!Cfg<NJ, TK>::STAND && !Cfg<NJ, TK>::STEP && l == 0) {
       w.phase += 1;
       if (w.phase >= m.period) w.phase = 0;
       uint32_t u[4];
@@ -1549,18 +1851,64 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
       if (randint(u[0], 100) == 0 && dbl) {
         if (w.mode == INPLACE) w.mode = STANDING;
         else if (w.mode == STANDING) w.mode = INPLACE;
-        sample_ref<real, NJ>(w, seed, 1);
+        sample_ref<real, NJ, TK>(w, seed, 1);
       }
       if (randint(u[1], 200) == 0 && w.mode != STANDING) {
         if (w.mode == FORWARD) w.mode = INPLACE;
         else if (w.mode == INPLACE) w.mode = FORWARD;
-        sample_ref<real, NJ>(w, seed, 2);
+        sample_ref<real, NJ, TK>(w, seed, 2);
       }
     }
   }
   LHW_SYNC();
   // WalkingTask.calc_reward (tasks/walking_task.py:85-147, tasks/rewards.py), lane = term
-  if constexpr (Cfg<NJ>::STAND) {
+  if constexpr (Cfg<NJ, TK>::STEP) {
+    // SteppingTask.calc_reward (tasks/stepping_task.py:66-121), lane = term (6 terms, the rest 0)
+    LHW_LANES(l) {
+      if (l < NREW) {
+        real rfc = m.clock[0][w.phase], rvc = m.clock[1][w.phase], lfc = m.clock[2][w.phase], lvc = m.clock[3][w.phase];
+        if (w.mode == ST_STANDING) { rfc = lfc = 1; rvc = lvc = -1; }
+        const real PI4 = (real)(M_PI / 4);
+        const real* sq = w.seq[(int)w.tk[1]];
+        real r = 0;
+        if (l == 0) {
+          const real nl = m_min(w.grf[1], m.fcap) / m.fcap * 2 - 1, nr = m_min(w.grf[0], m.fcap) / m.fcap * 2 - 1;
+          r = (real)0.150 * ((m_tan(PI4 * lfc * nl) + m_tan(PI4 * rfc * nr)) / 2);
+        } else if (l == 1) {
+          const real lv = m_sqrt(dot3(w.foot_vel[1], w.foot_vel[1])), rv = m_sqrt(dot3(w.foot_vel[0], w.foot_vel[0]));
+          const real vl = m_min(lv, (real)0.2) / (real)0.2 * 2 - 1, vr = m_min(rv, (real)0.2) / (real)0.2 * 2 - 1;
+          r = (real)0.150 * ((m_tan(PI4 * lvc * vl) + m_tan(PI4 * rvc * vr)) / 2);
+        } else if (l == 2) {
+          real sh, ch;
+          m_sincos((real)0.5 * sq[3], &sh, &ch);   // euler2quat(0, 0, th) = (cos th/2, 0, 0, sin th/2)
+          const real inner = ch * w.rquat[0] + sh * w.rquat[3];
+          r = (real)0.050 * m_exp(-10 * (1 - inner * inner));
+        } else if (l == 3) {
+          const real cz = (w.ncon[0] + w.ncon[1]) > 0 ? w.cz_min : (real)0;
+          real herr = m_abs(w.o[2] - cz - m.goal_height);
+          if (herr < (real)0.01) herr = 0;
+          r = (real)0.050 * m_exp(-40 * herr * herr);
+        } else if (l == 4) {
+          real dmin = (real)1e30;
+#pragma unroll
+          for (int f = 0; f < 2; f++) {
+            const real d0 = w.site[f][0] - sq[0], d1 = w.site[f][1] - sq[1], d2 = w.site[f][2] - sq[2];
+            dmin = m_min(dmin, m_sqrt(d0 * d0 + d1 * d1 + d2 * d2));
+          }
+          const real hit = w.tk[3] != 0 ? m_exp(-dmin / (real)0.25) : (real)0;
+          const real* s2 = w.seq[(int)w.tk[2]];
+          const real mx = (sq[0] + s2[0]) / 2 - w.o[0], my = (sq[1] + s2[1]) / 2 - w.o[1];
+          const real progress = m_exp(-m_sqrt(mx * mx + my * my) / 2);
+          r = (real)0.450 * ((real)0.8 * hit + (real)0.2 * progress);
+        } else if (l == 5) {
+          real hp[3];
+          mv3(w.xmat[0], m.head, hp);
+          r = (real)0.050 * m_exp(-10 * (hp[0] * hp[0] + hp[1] * hp[1]));
+        }
+        w.rew[l] = r;
+      }
+    }
+  } else if constexpr (Cfg<NJ, TK>::STAND) {
     // StandingTask.calc_reward (tasks/standing_task.py:49-105), lane = term (6 terms, the rest 0)
     LHW_LANES(l) {
       if (l < NREW) {
@@ -1645,10 +1993,14 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
     }
   }
   LHW_SYNC();
-  env_obs<real, NJ>(w, m, seed);
+  env_obs<real, NJ, TK>(w, m, seed);
   real total = 0;
   for (int i = 0; i < NREW; i++) total += w.rew[i];
-  const int done = (w.qpos[2] < m.done_lo) || (w.qpos[2] > m.done_hi) || (w.selfcol != 0) || (w.status != 0);
+  // WalkingTask / StandingTask.done: current root height; SteppingTask.done (stepping_task.py:248-260): lagged root
+  // height above the lower foot site
+  const int done = Cfg<NJ, TK>::STEP
+      ? ((w.o[2] - m_min(w.site[0][2], w.site[1][2]) < m.done_lo) || (w.selfcol != 0) || (w.status != 0))
+      : ((w.qpos[2] < m.done_lo) || (w.qpos[2] > m.done_hi) || (w.selfcol != 0) || (w.status != 0));
   const int ended = done || (w.traj_len + 1 >= max_traj_len);
   LHW_SYNC();
   LHW_LANES(l) {
@@ -1668,13 +2020,13 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
       for (int it = l; it < NOBS; it += 32) term_obs_out[it] = w.obs[it];
   }
   LHW_SYNC();
-  if constexpr (Cfg<NJ>::PERENV) {
+  if constexpr (Cfg<NJ, TK>::PERENV) {
     // domain randomisation after the observation (base_humanoid_env.py:228-233); decisions on stream 0 lanes 2, 3
     if (m.dynrand_interval > 0 || m.perturb_interval > 0) {
       uint32_t u[4];
       philox(seed, w.env_id, w.rng_ctr, 0, u);
-      if (m.dynrand_interval > 0 && randint(u[2], m.dynrand_interval) == 0) env_randomize<real, NJ>(w, m, seed);
-      if (m.perturb_interval > 0 && randint(u[3], m.perturb_interval) == 0) env_perturb<real, NJ>(w, m, seed);
+      if (m.dynrand_interval > 0 && randint(u[2], m.dynrand_interval) == 0) env_randomize<real, NJ, TK>(w, m, seed);
+      if (m.perturb_interval > 0 && randint(u[3], m.perturb_interval) == 0) env_perturb<real, NJ, TK>(w, m, seed);
     }
   }
   if (ended && autoreset) {
@@ -1685,7 +2037,7 @@ LHW_DEV void env_step(Work<real, NJ>& w, const Model<real, NJ>& m, const real* a
       }
     }
     LHW_SYNC();
-    env_reset<real, NJ>(w, m, seed);
+    env_reset<real, NJ, TK>(w, m, seed);
   }
   LHW_LANES(l) {
     for (int it = l; it < NOBS; it += 32) obs_out[it] = w.obs[it];

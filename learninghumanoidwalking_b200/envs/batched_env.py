@@ -16,19 +16,33 @@ import torch
 
 from .. import _lib
 from ..model import load_model, pack_model
+from ..model.loader import curriculum_height
 
 REWARD_NAMES = ("foot_frc_score", "foot_vel_score", "root_accel", "height_error", "com_vel_error", "yaw_vel_error",
                 "upper_body_reward", "posture_error", "torque_penalty", "action_penalty")  # tasks/walking_task.py:131-146
 STAND_REWARD_NAMES = ("com_vel_error", "yaw_vel_error", "height", "upperbody", "joint_torque_reward",
                       "posture")                                                          # tasks/standing_task.py:97-104
+STEP_REWARD_NAMES = ("foot_frc_score", "foot_vel_score", "orient_cost", "height_error", "step_reward",
+                     "upper_body_reward")                                                 # tasks/stepping_task.py:107-120
 N_REWARD_SLOTS = 10   # width of the kernel's reward-term record (csrc/sim_core.h NREW); unused slots are 0
+
+
+class _Robot(SimpleNamespace):
+    """The attributes the trainer reads / writes on `env.robot` (robots/robot_base.py:35, run_experiment.py:123-125).
+    Writing `iteration_count` (rl/workers/rollout_worker.py:95) drives the SteppingTask's height curriculum."""
+
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name == "iteration_count" and getattr(self, "_on_iteration", None) is not None:
+            self._on_iteration(value)
 
 
 class BatchedHumanoidEnv:
     def __init__(self, num_envs: int, model: str = "jvrc_walk", precision: int = 32, seed: int = 0,
                  first_env_id: int = 0, device: int | torch.device | None = None, max_traj_len: int = 400,
                  tolerance: float | None = None, max_iter: int | None = None, observation_noise: bool = True,
-                 domain_randomization: bool = True, init_noise: bool = True, pd_gain_randomization: float = 0.0):
+                 domain_randomization: bool = True, init_noise: bool = True, pd_gain_randomization: float = 0.0,
+                 iteration_count: float = float("inf")):
         if not torch.cuda.is_available():
             raise _lib.LhwError("BatchedHumanoidEnv needs a CUDA device (no CPU fallback on the rollout path)")
         if device is None:
@@ -39,11 +53,12 @@ class BatchedHumanoidEnv:
         self.dtype = torch.float64 if precision == 64 else torch.float32
         self.model_name = model
         self.mj = load_model(model)
+        self._iteration_count = float(iteration_count)
         if tolerance is None and precision == 32:
             tolerance = 1e-6  # fp32 cannot reach the reference's 1e-10; gradient floor is ~1e-6 of the force scale
         flat = pack_model(self.mj, tolerance=tolerance, max_iter=max_iter, observation_noise=observation_noise,
                           domain_randomization=domain_randomization, init_noise=init_noise,
-                          pd_gain_randomization=pd_gain_randomization)
+                          pd_gain_randomization=pd_gain_randomization, iteration_count=iteration_count)
         L = _lib.lib()
         h = ctypes.c_void_p()
         _lib.check(L.lhw_sim_create(ctypes.byref(h), flat.ctypes.data_as(ctypes.c_void_p), len(flat), self.precision,
@@ -85,9 +100,23 @@ class BatchedHumanoidEnv:
         base_mir_obs = [-0.1, 1, -2, 3, -4, 11, -12, -13, 14, -15, 16, 5, -6, -7, 8, -9, 10,
                         23, -24, -25, 26, -27, 28, 17, -18, -19, 20, -21, 22]
         append_obs = [len(base_mir_obs) + i for i in range(8)]
-        self.robot = SimpleNamespace(mirrored_obs=base_mir_obs + append_obs,
-                                     mirrored_acts=[6, -7, -8, 9, -10, 11, 0.1, -1, -2, 3, -4, 5],
-                                     clock_inds=append_obs[0:2], iteration_count=np.inf)
+        if model == "jvrc_step":
+            # envs/jvrc/jvrc_step.py:41-63: clock(2) + goal steps x(2) y(2) z(2) theta(2)
+            self.reward_names = STEP_REWARD_NAMES
+            self.obs_mean = np.concatenate((np.zeros(5), half, np.zeros(12), [0.5, 0.5], np.zeros(8)))
+            self.obs_std = np.concatenate(([0.2, 0.2, 1, 1, 1], 0.5 * np.ones(12), 4 * np.ones(12), [1, 1], np.ones(8)))
+            append_obs = [len(base_mir_obs) + i for i in range(10)]
+        self.robot = _Robot(mirrored_obs=base_mir_obs + append_obs,
+                            mirrored_acts=[6, -7, -8, 9, -10, 11, 0.1, -1, -2, 3, -4, 5],
+                            clock_inds=append_obs[0:2], iteration_count=self._iteration_count, _on_iteration=None)
+        if model == "jvrc_step":
+            self.robot._on_iteration = self._set_iteration_count
+
+    def _set_iteration_count(self, iteration_count: float) -> None:
+        """SteppingTask.reset(iter_count) (tasks/stepping_task.py:262-264, 312): the curriculum's step height for the
+        episodes that start from now on."""
+        _lib.check(_lib.lib().lhw_sim_set_step_height(self._h, float(curriculum_height(iteration_count))),
+                   "lhw_sim_set_step_height")
 
     # ------------------------------------------------------------------ device API (torch tensors in / out)
     def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:

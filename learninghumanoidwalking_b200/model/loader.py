@@ -21,7 +21,8 @@ def load_model(name: str = "jvrc_walk") -> dict:
 
 def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = None, kp=None, kd=None,
                self_collision: bool = True, observation_noise: bool = True, domain_randomization: bool = True,
-               init_noise: bool = True, pd_gain_randomization: float = 0.0) -> np.ndarray:
+               init_noise: bool = True, pd_gain_randomization: float = 0.0,
+               iteration_count: float = float("inf")) -> np.ndarray:
     links = mj["links"]
     nl = len(links)
     assert (nl - 1) % 2 == 0, "expected a free root + two equal serial chains"
@@ -31,8 +32,9 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
             i = 1 + c * nj + k
             assert links[i]["parent"] == (0 if k == 0 else i - 1), "links must be ordered root, chain0, chain1"
     assert {mj["rfoot_link"], mj["lfoot_link"]} == {nj, 2 * nj}
-    stand = mj["name"] == "h1"          # Unitree H1 + StandingTask (csrc/sim_core.h Cfg<5>)
-    b: list[float] = [nj]
+    stand = mj["name"] == "h1"          # Unitree H1 + StandingTask (csrc/sim_core.h Cfg<5, 0>)
+    step = mj["name"] == "jvrc_step"    # JVRC-1 + SteppingTask (csrc/sim_core.h Cfg<6, 1>)
+    b: list[float] = [nj + (100 if step else 0)]
     for lk in links:
         b += lk["pos"]
         b += list(np.asarray(lk["rot"], dtype=float).reshape(-1))
@@ -97,6 +99,8 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
               int(pert["interval"] / c["control_dt"]) if pert["enable"] and domain_randomization else 0,
               pert["force_magnitude"], pert["torque_magnitude"],
               c["init_noise_deg"] * np.pi / 180 if init_noise else 0.0]
+    elif step:
+        b += [0.6, 1e30] + [0.0] * 5 + [0, 0, 0.0, 0.0, 0.0]  # tasks/stepping_task.py:254-257 (relative height, no upper bound)
     else:
         b += [0.6, 1.4] + [0.0] * 5 + [0, 0, 0.0, 0.0, 0.0]   # tasks/walking_task.py:192-193
     for g in mj["geoms"]:
@@ -113,4 +117,21 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
     else:
         b += [0.0] * 23
     b.append(float(pd_gain_randomization))     # RobotBase(pdrand_k) (robots/robot_base.py:5,43-47); 0 = off
+    if step:
+        st = mj["stepping"]
+        for site in mj["foot_sites"]:
+            b += site
+        b += st["slab_half"]
+        b += [st["target_radius"], st["side_tol"], st["delay_frames"], curriculum_height(iteration_count)]
+        b.append(len(st["plans"]))
+        for plan in st["plans"]:
+            b.append(len(plan))
+            for row in plan:
+                b += row
     return np.asarray(b, dtype=np.float64)
+
+
+def curriculum_height(iteration_count: float) -> float:
+    """SteppingTask.reset (tasks/stepping_task.py:312): h = clip((iteration_count - 3000) / 8000, 0, 1) * 0.1.
+    `env.robot.iteration_count` is inf unless the trainer sets it (robots/robot_base.py:35, rl/workers/rollout_worker.py:95)."""
+    return float(np.clip((iteration_count - 3000) / 8000, 0, 1) * 0.1)

@@ -38,7 +38,7 @@ def load_clocks() -> dict:
 
 
 def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: int = 0, iterations: int | None = None,
-               self_collision: bool = True, pdrand_k: float = 0.0):
+               self_collision: bool = True, pdrand_k: float = 0.0, iteration_count: float = float("inf")):
     """Flat double layout consumed by orc_model_from_flat (keep in sync with sim_oracle.c)."""
     b: list[float] = []
     links = mj["links"]
@@ -104,6 +104,8 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
         b += [int(dyn["interval"] / c["control_dt"]) if dyn["enable"] else 0,
               int(pert["interval"] / c["control_dt"]) if pert["enable"] else 0,
               pert["force_magnitude"], pert["torque_magnitude"], c["init_noise_deg"]]
+    elif mj["name"] == "jvrc_step":
+        b += [2, 39, 0.6, 1e30] + [0.0] * 5 + [0, 0, 0.0, 0.0, 0.0]     # tasks/stepping_task.py:256 (no upper height bound)
     else:
         b += [0, 37, 0.6, 1.4] + [0.0] * 5 + [0, 0, 0.0, 0.0, 0.0]
     for g in mj["geoms"]:
@@ -119,20 +121,38 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
     else:
         b += [0.0] * 29
     b.append(float(pdrand_k))
+    if mj["name"] == "jvrc_step":
+        st = mj["stepping"]
+        for site in mj["foot_sites"]:
+            b += site
+        b += st["slab_half"]
+        b += [st["target_radius"], st["side_tol"], st["delay_frames"], curriculum_height(iteration_count)]
+        b.append(len(st["plans"]))
+        for plan in st["plans"]:
+            b.append(len(plan))
+            for row in plan:
+                b += row
     return np.array(b, dtype=np.float64)
+
+
+def curriculum_height(iteration_count: float) -> float:
+    """tasks/stepping_task.py:312: h = clip((iteration_count - 3000) / 8000, 0, 1) * 0.1 (iteration_count = inf by default,
+    robots/robot_base.py:35)."""
+    return float(np.clip((iteration_count - 3000) / 8000, 0, 1) * 0.1)
 
 
 class Oracle:
     """One compiled model + helpers to own N environments."""
 
     def __init__(self, name: str = "jvrc_walk", tolerance: float | None = None, solver: int = 0,
-                 iterations: int | None = None, pdrand_k: float = 0.0):
+                 iterations: int | None = None, pdrand_k: float = 0.0, iteration_count: float = float("inf")):
         self.lib = ctypes.CDLL(build())
         L = self.lib
         L.orc_energy.restype = ctypes.c_double
         self.mj = load_model_json(name)
         self.clocks = load_clocks()
-        flat = pack_model(self.mj, self.clocks, tolerance, solver, iterations, pdrand_k=pdrand_k)
+        flat = pack_model(self.mj, self.clocks, tolerance, solver, iterations, pdrand_k=pdrand_k,
+                          iteration_count=iteration_count)
         self._model = ctypes.create_string_buffer(L.orc_sizeof_model())
         rc = L.orc_model_from_flat(self._model, flat.ctypes.data_as(ctypes.c_void_p), len(flat))
         if rc != 0:
@@ -141,7 +161,17 @@ class Oracle:
         assert self.env_size == _ENV_SIZE, (self.env_size, _ENV_SIZE)
         self.nu = len(self.mj["links"]) - 1
         self.nv, self.nq = 6 + self.nu, 7 + self.nu
-        self.nobs = 35 if name == "h1" else NOBS
+        self.nobs = {"h1": 35, "jvrc_step": 39}.get(name, NOBS)
+
+    def set_iteration_count(self, iteration_count: float):
+        """env.robot.iteration_count = itr (rl/workers/rollout_worker.py:95) -> the curriculum's step height."""
+        self.lib.orc_set_step_height(self._model, ctypes.c_double(curriculum_height(iteration_count)))
+
+    def task_reset(self, envs, i=0):
+        self.lib.orc_test_task_reset(self._model, self.env_ptr(envs, i))
+
+    def task_step(self, envs, i=0):
+        self.lib.orc_test_task_step(self._model, self.env_ptr(envs, i))
 
     # ---- single/batched env management
     def make_envs(self, n: int, seed: int = 0, first_id: int = 0):
@@ -264,6 +294,10 @@ def _layout():
         ("P_mass", MAXLINK, "f8"), ("P_com", MAXLINK * 3, "f8"), ("P_inertia", MAXLINK * 9, "f8"),
         ("P_damping", NV, "f8"), ("P_frictionloss", NV, "f8"), ("P_pel_mass", 1, "f8"), ("P_pel_com", 3, "f8"),
         ("xfrc", 12, "f8"),
+        # SteppingTask state
+        ("seq", 80, "f8"), ("goal_steps", 8, "f8"), ("site_pos", 6, "f8"), ("foot_xpos", 6, "f8"), ("root_quat", 4, "f8"),
+        ("seq_len", 1, "i4"), ("t1", 1, "i4"), ("t2", 1, "i4"), ("target_reached", 1, "i4"),
+        ("target_reached_frames", 1, "i4"), ("con_overflow", 1, "i4"),
     ]
     out, off = {}, 0
     for name, cnt, typ in fields:

@@ -26,6 +26,7 @@
 #define L ORC_MAXLINK
 #define NV ORC_NV
 #define MINVAL 1e-15
+#define ORC_PGS_MAXROW 160   /* the dual solver is a test cross-check for small row counts only */
 
 /* ------------------------------------------------------------------ small linear algebra */
 static void cross3(const double* a, const double* b, double* c) {
@@ -172,6 +173,20 @@ int orc_model_from_flat(orc_model* m, const double* b, int n) {
   for (int k = 0; k < 9; k++) m->rest_Io[k] = RD();
   for (int k = 0; k < 3; k++) m->torso_com[k] = RD();
   m->pdrand_k = RD();
+  if (m->task == ORC_TASK_STEP) {
+    for (int f = 0; f < 2; f++)
+      for (int k = 0; k < 3; k++) m->foot_site[f][k] = RD();
+    for (int k = 0; k < 3; k++) m->slab_half[k] = RD();
+    m->target_radius = RD(); m->side_tol = RD(); m->delay_frames = (int)RD(); m->step_height = RD();
+    m->nplan = (int)RD();
+    if (m->nplan > ORC_MAXPLAN) return -8;
+    for (int i = 0; i < m->nplan; i++) {
+      m->plan_len[i] = (int)RD();
+      if (m->plan_len[i] > ORC_MAXPLANLEN) return -9;
+      for (int k = 0; k < m->plan_len[i]; k++)
+        for (int x = 0; x < 3; x++) m->plans[i][k][x] = RD();
+    }
+  }
 #undef RD
   return p == n ? 0 : -100 - (p > n);
 }
@@ -408,8 +423,28 @@ static double row_force(const efc_t* e, int r, double x, double* curv) {
   return -e->D[r] * x;
 }
 
+/* ---- stepping stones (tasks/stepping_task.py:318-334): slab k is a box of half sizes slab_half, yawed by seq[k][3], whose
+ * TOP face passes through seq[k][0:3].  MuJoCo collides the foot boxes with them through mjc_BoxBox (not available here,
+ * "parity unpinned"); this restates the face-face case of that routine with the slab's top face as the reference face:
+ * the contact points are the vertices of the foot's sole rectangle clipped against the slab footprint, i.e. (A) sole
+ * corners inside the footprint and (B) sole-edge x footprint-boundary crossings, normal +z, dist = z - top.  A point is
+ * supported by the top face only while it is inside the slab's thickness and not deeper than its inset from the slab's
+ * side faces (beyond that the minimum-penetration axis of a box-box test is a side face, which is not modelled). */
+static int slab_supports(const orc_model* m, const double* sl, const double* p, double* dist) {
+  double c = cos(sl[3]), sn = sin(sl[3]);
+  double dx = p[0] - sl[0], dy = p[1] - sl[1];
+  double xs = c * dx + sn * dy, ys = -sn * dx + c * dy;
+  double ix = m->slab_half[0] - fabs(xs), iy = m->slab_half[1] - fabs(ys);
+  if (ix < 0 || iy < 0) return 0;
+  double d = p[2] - sl[2], inset = ix < iy ? ix : iy;
+  if (!(d < 0) || -d >= 2 * m->slab_half[2]) return 0;
+  if (-d > m->side_tol && -d > inset) return 0;
+  *dist = d;
+  return 1;
+}
+
 static void make_constraints(const orc_model* m, const orc_params* P, const kin_t* k, const double* qpos, const double* qvel,
-                             efc_t* e) {
+                             const orc_env* env, efc_t* e) {
   int nv = m->nv;
   e->nrow = 0; e->ncon = 0;
   double tau = m->solref[0], zeta = m->solref[1];
@@ -474,6 +509,85 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
     double off[3], ctr[3];
     matvec3(k->xmat[lk], m->geom_pos[g], off);
     for (int x = 0; x < 3; x++) ctr[x] = k->xpos[lk][x] + off[x];
+    if (m->task == ORC_TASK_STEP) {
+      /* floor body moved to z = -2 in FORWARD mode (stepping_task.py:332-334) */
+      double floor_z = env->mode == ORC_STEP_FORWARD ? -2.0 : 0.0;
+      double cw[8][3];
+      int cnt = 0;
+      for (int i = 0; i < 8; i++) {
+        double v[3] = {(i & 1 ? 1 : -1) * m->geom_size[g][0], (i & 2 ? 1 : -1) * m->geom_size[g][1],
+                       (i & 4 ? 1 : -1) * m->geom_size[g][2]};
+        double corner[3];
+        matvec3(k->xmat[lk], v, corner);
+        for (int x = 0; x < 3; x++) cw[i][x] = corner[x] + ctr[x];
+        if (cnt >= 4 || corner[2] > 0) continue;       /* mjc_PlaneBox keeps corners on the plane side of the centre, 4 at most */
+        /* (A) the highest supporting surface under this corner; every surface at that height is its own contact */
+        double best = 0, dsl[ORC_NSLAB];
+        int have = 0, sup[ORC_NSLAB];
+        if (cw[i][2] - floor_z < 0) { best = floor_z; have = 1; }
+        for (int sidx = 0; sidx < ORC_NSLAB; sidx++) {
+          sup[sidx] = slab_supports(m, env->seq[sidx], cw[i], &dsl[sidx]);
+          if (sup[sidx] && (!have || env->seq[sidx][2] > best)) { best = env->seq[sidx][2]; have = 1; }
+        }
+        if (!have) continue;
+        cnt++;
+        for (int sidx = -1; sidx < ORC_NSLAB; sidx++) {
+          double h = sidx < 0 ? floor_z : env->seq[sidx][2];
+          if (sidx < 0 ? !(cw[i][2] - floor_z < 0) : !sup[sidx]) continue;
+          if (h != best) continue;
+          if (e->ncon >= ORC_MAXCON) { ((orc_env*)env)->con_overflow++; continue; }
+          double cd = cw[i][2] - h;
+          int ci = e->ncon++;
+          e->con_geom[ci] = g;
+          e->con_dist[ci] = cd;
+          e->con_pos[ci][0] = cw[i][0]; e->con_pos[ci][1] = cw[i][1];
+          e->con_pos[ci][2] = cw[i][2] - 0.5 * cd;
+        }
+      }
+      /* (B) crossings of the sole edges (corner loop 0-1-3-2 of the local -z face) with each slab's footprint boundary:
+       * Liang-Barsky clip of the edge against the rectangle; an entry / exit parameter strictly inside (0,1) is a new
+       * polygon vertex.  At most ORC_MAXCROSS per foot, in (slab, edge, entry-then-exit) order. */
+      static const int ea[4] = {0, 1, 3, 2}, eb[4] = {1, 3, 2, 0};
+      int ncross = 0;
+      for (int sidx = 0; sidx < ORC_NSLAB; sidx++) {
+        const double* sl = env->seq[sidx];
+        double c = cos(sl[3]), sn = sin(sl[3]);
+        for (int ed = 0; ed < 4; ed++) {
+          const double* A = cw[ea[ed]];
+          const double* Bp = cw[eb[ed]];
+          double ax = c * (A[0] - sl[0]) + sn * (A[1] - sl[1]), ay = -sn * (A[0] - sl[0]) + c * (A[1] - sl[1]);
+          double bx = c * (Bp[0] - sl[0]) + sn * (Bp[1] - sl[1]), by = -sn * (Bp[0] - sl[0]) + c * (Bp[1] - sl[1]);
+          double dx = bx - ax, dy = by - ay, t0 = 0, t1 = 1;
+          double pp[4] = {-dx, dx, -dy, dy};
+          double qq[4] = {ax + m->slab_half[0], m->slab_half[0] - ax, ay + m->slab_half[1], m->slab_half[1] - ay};
+          int ok = 1;
+          for (int b = 0; b < 4 && ok; b++) {
+            if (pp[b] == 0) { if (qq[b] < 0) ok = 0; continue; }
+            double r = qq[b] / pp[b];
+            if (pp[b] < 0) { if (r > t1) ok = 0; else if (r > t0) t0 = r; }
+            else { if (r < t0) ok = 0; else if (r < t1) t1 = r; }
+          }
+          if (!ok) continue;
+          for (int side = 0; side < 2; side++) {
+            double t = side == 0 ? t0 : t1;
+            if (side == 0 ? !(t0 > 0) : !(t1 < 1)) continue;
+            double z = A[2] + t * (Bp[2] - A[2]);
+            double cd = z - sl[2];
+            if (!(cd < 0) || -cd > m->side_tol) continue;
+            if (ncross >= ORC_MAXCROSS) { continue; }
+            if (e->ncon >= ORC_MAXCON) { ((orc_env*)env)->con_overflow++; continue; }
+            ncross++;
+            int ci = e->ncon++;
+            e->con_geom[ci] = g;
+            e->con_dist[ci] = cd;
+            e->con_pos[ci][0] = A[0] + t * (Bp[0] - A[0]);
+            e->con_pos[ci][1] = A[1] + t * (Bp[1] - A[1]);
+            e->con_pos[ci][2] = z - 0.5 * cd;
+          }
+        }
+      }
+      continue;
+    }
     double dist0 = ctr[2];
     int cnt = 0;
     for (int i = 0; i < 8 && cnt < 4; i++) {
@@ -633,7 +747,7 @@ static int solve_pgs(const orc_model* m, const double* M, const efc_t* e, const 
                      double* force, double* kkt) {
   int nv = m->nv, nr = e->nrow;
   double G[NV * NV], as[NV], MinvJt[ORC_MAXROW][NV];
-  static __thread double A[ORC_MAXROW][ORC_MAXROW];
+  static __thread double A[ORC_PGS_MAXROW][ORC_PGS_MAXROW];
   double b[ORC_MAXROW];
   for (int a = 0; a < nv; a++)
     for (int c = 0; c < nv; c++) G[a * nv + c] = M[a * NV + c];
@@ -745,7 +859,7 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
   const orc_params* P = &e->P;
   fk(m, P, e->qpos, &k);
   mass_matrix_k(m, P, &k, M);
-  make_constraints(m, P, &k, e->qpos, e->qvel, &efc);
+  make_constraints(m, P, &k, e->qpos, e->qvel, e, &efc);
   bias_k(m, P, &k, e->qvel, bias);
   for (int d = 0; d < nv; d++) qfs[d] = -P->damping[d] * e->qvel[d] - bias[d];
   for (int u = 0; u < nu; u++) qfs[6 + u] += ctrl[u]; /* motors, gear 1 */
@@ -774,7 +888,7 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
     memcpy(qacc, qfs, nv * sizeof(double));
     chol_solve(G, nv, qacc);
     e->last_solver_iter = 0;
-  } else if (m->solver == ORC_SOLVER_PGS) {
+  } else if (m->solver == ORC_SOLVER_PGS && efc.nrow <= ORC_PGS_MAXROW) {
     e->last_solver_iter = solve_pgs(m, M, &efc, qfs, qacc, force, &kkt);
   } else {
     e->last_solver_iter = solve_newton(m, M, &efc, qfs, qacc, force, &kkt);
@@ -802,6 +916,17 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
     for (int x = 0; x < 3; x++)
       for (int d = 0; d < nv; d++) v[x] += jp[x * NV + d] * e->qvel[d];
     memcpy(f == 0 ? e->rfoot_vel : e->lfoot_vel, v, sizeof(v));
+  }
+  for (int f = 0; f < 2; f++) {
+    int lk = f == 0 ? m->rfoot_link : m->lfoot_link;
+    double t[3];
+    matvec3(k.xmat[lk], m->foot_site[f], t);
+    for (int x = 0; x < 3; x++) { e->site_pos[f][x] = k.xpos[lk][x] + t[x]; e->foot_xpos[f][x] = k.xpos[lk][x]; }
+  }
+  {
+    const double* q = e->qpos + 3;   /* mj_kinematics normalises the free-joint quaternion */
+    double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; i++) e->root_quat[i] = q[i] / nq;
   }
   e->rfoot_grf = e->lfoot_grf = 0;
   e->ncon_r = e->ncon_l = 0;
@@ -911,6 +1036,10 @@ static void get_obs(const orc_model* m, const orc_env* e, double* obs) {
   }
   obs[o++] = sin(2 * M_PI * e->phase / m->period);
   obs[o++] = cos(2 * M_PI * e->phase / m->period);
+  if (m->task == ORC_TASK_STEP) {   /* envs/jvrc/jvrc_step.py:67-76 */
+    for (int i = 0; i < 8; i++) obs[o++] = e->goal_steps[i];
+    return;
+  }
   /* WalkModes.encode: STANDING [0,0,1], INPLACE [0,1,0], FORWARD [1,0,0] */
   obs[o++] = e->mode == ORC_FORWARD; obs[o++] = e->mode == ORC_INPLACE; obs[o++] = e->mode == ORC_STANDING;
   for (int x = 0; x < 3; x++) obs[o++] = e->mode_ref[x];
@@ -928,8 +1057,166 @@ static void sample_ref(orc_env* e, uint32_t stream) {
   }
 }
 
+/* ---------------- SteppingTask (tasks/stepping_task.py) */
+/* transforms3d mat2euler(R, 'sxyz')[2] */
+static double mat_yaw(const double* R) {
+  double cy = sqrt(R[0] * R[0] + R[3] * R[3]);
+  return cy > 4 * 2.220446049250313e-16 ? atan2(R[3], R[0]) : 0.0;
+}
+
+/* update_target_steps (stepping_task.py:207-213) */
+static void step_update_targets(orc_env* e) {
+  e->t1 = e->t2;
+  e->t2 += 1;
+  if (e->t2 == e->seq_len) e->t2 = e->seq_len - 1;
+}
+
+/* update_goal_steps (stepping_task.py:188-205): targets t1, t2 expressed in the root frame (4x4 inverse of a rigid
+ * transform = R' (p - root_pos), R' Rz(theta)); zeros in STANDING mode */
+static void step_update_goals(orc_env* e) {
+  memset(e->goal_steps, 0, sizeof(e->goal_steps));
+  if (e->mode == ORC_STEP_STANDING) return;
+  for (int idx = 0; idx < 2; idx++) {
+    const double* sq = e->seq[idx == 0 ? e->t1 : e->t2];
+    double d[3] = {sq[0] - e->root_xpos[0], sq[1] - e->root_xpos[1], sq[2] - e->root_xpos[2]}, rel[3];
+    mattvec3(e->root_xmat, d, rel);
+    double c = cos(sq[3]), sn = sin(sq[3]);
+    double Rz[9] = {c, -sn, 0, sn, c, 0, 0, 0, 1}, Rt[9], Rr[9];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) Rt[3 * a + b] = e->root_xmat[3 * b + a];
+    matmul3(Rt, Rz, Rr);
+    e->goal_steps[0 + idx] = rel[0];
+    e->goal_steps[2 + idx] = rel[1];
+    e->goal_steps[4 + idx] = rel[2];
+    e->goal_steps[6 + idx] = mat_yaw(Rr);
+  }
+}
+
+/* SteppingTask.reset (stepping_task.py:243-334).  Draws (event counter = the reset's): stream 3 lane 0 mode, lane 1 phase,
+ * lane 2 first-step offset / plan index / lateral sign, lane 3 the randint(2,4); stream 4 lane 0 the sign of the step height */
+static void task_reset_step(const orc_model* m, orc_env* e) {
+  uint32_t u[4], v[4];
+  orc_philox(e->seed, e->env_id, e->rng_ctr, 3, u);
+  orc_philox(e->seed, e->env_id, e->rng_ctr, 4, v);
+  memset(e->goal_steps, 0, sizeof(e->goal_steps));
+  e->target_reached = 0; e->target_reached_frames = 0;
+  e->t1 = e->t2 = 0;
+  e->phase = randint(u[1], 2) == 0 ? 0 : m->period / 2;
+  double cm = u01(u[0]);
+  e->mode = cm < 0.15 ? ORC_STEP_CURVED : cm < 0.15 + 0.05 ? ORC_STEP_STANDING : cm < 0.15 + 0.05 + 0.2 ? ORC_STEP_BACKWARD
+            : cm < 0.15 + 0.05 + 0.2 + 0.3 ? ORC_STEP_LATERAL : ORC_STEP_FORWARD;
+  double step_size = 0.3, step_gap = 0.15, step_height = 0;
+  int num_steps = 20;
+  if (e->mode == ORC_STEP_STANDING) num_steps = 1;
+  else if (e->mode == ORC_STEP_BACKWARD) step_size = -0.1;
+  else if (e->mode == ORC_STEP_LATERAL) step_size = 0.4;
+  else if (e->mode == ORC_STEP_FORWARD) step_height = randint(v[0], 2) == 0 ? -m->step_height : m->step_height;
+  double rel[ORC_NSLAB][4];
+  int n = 0;
+  if (e->mode == ORC_STEP_CURVED) {
+    int pi = randint(u[2], m->nplan);
+    for (int i = 0; i < m->plan_len[pi]; i++, n++) {
+      rel[n][0] = m->plans[pi][i][0]; rel[n][1] = m->plans[pi][i][1]; rel[n][2] = 0; rel[n][3] = m->plans[pi][i][2];
+    }
+  } else if (e->mode == ORC_STEP_LATERAL) {
+    double y = 0, c = randint(u[2], 2) == 0 ? -1 : 1;
+    for (int i = 1; i < num_steps; i++, n++) {
+      if (i % 2) y += step_size; else y -= (2.0 / 3.0) * step_size;
+      rel[n][0] = 0; rel[n][1] = c * y; rel[n][2] = 0; rel[n][3] = 0;
+    }
+  } else {
+    double first = 0.095 + (0.105 - 0.095) * u01(u[2]), y;
+    if (e->phase == m->period / 2 && 2 * (m->period / 2) == m->period) { rel[0][1] = -1 * first; y = -step_gap; }
+    else { rel[0][1] = 1 * first; y = step_gap; }
+    rel[0][0] = 0; rel[0][2] = 0; rel[0][3] = 0;
+    n = 1;
+    double x = 0, z = 0;
+    int c = 2 + randint(u[3], 2);
+    for (int i = 1; i < num_steps - 1; i++, n++) {
+      x += step_size;
+      y *= -1;
+      if (i > c) z += step_height;
+      rel[n][0] = x; rel[n][1] = y; rel[n][2] = z; rel[n][3] = 0;
+    }
+    rel[n][0] = x + step_size; rel[n][1] = -y; rel[n][2] = z; rel[n][3] = 0;
+    n++;
+  }
+  /* transform_sequence (stepping_task.py:123-136): about the mid-point of the foot bodies, yawed with the root */
+  double yaw = mat_yaw(e->root_xmat);
+  double mid[2] = {(e->foot_xpos[1][0] + e->foot_xpos[0][0]) / 2, (e->foot_xpos[1][1] + e->foot_xpos[0][1]) / 2};
+  e->seq_len = n;
+  for (int i = 0; i < ORC_NSLAB; i++) {
+    if (i < n) {
+      e->seq[i][0] = mid[0] + rel[i][0] * cos(yaw) - rel[i][1] * sin(yaw);
+      e->seq[i][1] = mid[1] + rel[i][0] * sin(yaw) + rel[i][1] * cos(yaw);
+      e->seq[i][2] = rel[i][2];
+      e->seq[i][3] = yaw + rel[i][3];
+    } else {
+      e->seq[i][0] = 0; e->seq[i][1] = 0; e->seq[i][2] = -1; e->seq[i][3] = 0;   /* unused boxes (stepping_task.py:322) */
+    }
+  }
+  step_update_targets(e);
+}
+
+/* SteppingTask.step (stepping_task.py:215-243) */
+static void task_step_step(const orc_model* m, orc_env* e) {
+  e->phase += 1;
+  if (e->phase >= m->period) e->phase = 0;
+  const double* tp = e->seq[e->t1];
+  int in = 0;
+  for (int f = 0; f < 2; f++) {
+    double d[3] = {e->site_pos[f][0] - tp[0], e->site_pos[f][1] - tp[1], e->site_pos[f][2] - tp[2]};
+    if (sqrt(dot3(d, d)) < m->target_radius) in = 1;
+  }
+  if (in) { e->target_reached = 1; e->target_reached_frames += 1; }
+  else { e->target_reached = 0; e->target_reached_frames = 0; }
+  if (e->target_reached && e->target_reached_frames >= m->delay_frames) {
+    step_update_targets(e);
+    e->target_reached = 0;
+    e->target_reached_frames = 0;
+  }
+  step_update_goals(e);
+}
+
+/* SteppingTask.calc_reward (stepping_task.py:66-121); 6 terms in dict order, t[6..9] = 0 */
+static void calc_reward_step(const orc_model* m, const orc_env* e, double* t) {
+  double rfc = m->clock[0][e->phase], rvc = m->clock[1][e->phase], lfc = m->clock[2][e->phase],
+         lvc = m->clock[3][e->phase];
+  if (e->mode == ORC_STEP_STANDING) { rfc = lfc = 1; rvc = lvc = -1; }
+  double fcap = m->total_mass * 9.8 * 0.5;
+  double nl = fmin(e->lfoot_grf, fcap) / fcap * 2 - 1, nr = fmin(e->rfoot_grf, fcap) / fcap * 2 - 1;
+  t[0] = 0.150 * ((tan(M_PI / 4 * lfc * nl) + tan(M_PI / 4 * rfc * nr)) / 2);
+  double lv = sqrt(dot3(e->lfoot_vel, e->lfoot_vel)), rv = sqrt(dot3(e->rfoot_vel, e->rfoot_vel));
+  double vl = fmin(lv, 0.2) / 0.2 * 2 - 1, vr = fmin(rv, 0.2) / 0.2 * 2 - 1;
+  t[1] = 0.150 * ((tan(M_PI / 4 * lvc * vl) + tan(M_PI / 4 * rvc * vr)) / 2);
+  /* orientation vs the yaw of target t1 (rewards.py:177-193): euler2quat(0, 0, th) = (cos th/2, 0, 0, sin th/2) */
+  const double* sq = e->seq[e->t1];
+  double inner = cos(0.5 * sq[3]) * e->root_quat[0] + sin(0.5 * sq[3]) * e->root_quat[3];
+  t[2] = 0.050 * exp(-10 * (1 - inner * inner));
+  double cz = (e->ncon_r + e->ncon_l) > 0 ? e->contact_z_min : 0.0;
+  double herr = fabs(e->root_xpos[2] - cz - m->goal_height);
+  if (herr < 0.01) herr = 0;                                       /* goal_speed_ref = 0 */
+  t[3] = 0.050 * exp(-40 * herr * herr);
+  /* step_reward (stepping_task.py:52-64) */
+  double dmin = 1e300;
+  for (int f = 0; f < 2; f++) {
+    double d[3] = {e->site_pos[f][0] - sq[0], e->site_pos[f][1] - sq[1], e->site_pos[f][2] - sq[2]};
+    double n = sqrt(dot3(d, d));
+    if (n < dmin) dmin = n;
+  }
+  double hit = e->target_reached ? exp(-dmin / 0.25) : 0.0;
+  const double* s2 = e->seq[e->t2];
+  double mx = (sq[0] + s2[0]) / 2 - e->root_xpos[0], my = (sq[1] + s2[1]) / 2 - e->root_xpos[1];
+  double progress = exp(-sqrt(mx * mx + my * my) / 2);
+  t[4] = 0.450 * (0.8 * hit + 0.2 * progress);
+  double hx = e->head_xpos[0] - e->root_xpos[0], hy = e->head_xpos[1] - e->root_xpos[1];
+  t[5] = 0.050 * exp(-10 * (hx * hx + hy * hy));
+  t[6] = t[7] = t[8] = t[9] = 0;
+}
+
 static void task_reset(const orc_model* m, orc_env* e) {
   uint32_t u[4];
+  if (m->task == ORC_TASK_STEP) { task_reset_step(m, e); return; }
   if (m->task == ORC_TASK_STAND) return; /* StandingTask.reset is empty (tasks/standing_task.py:33) */
   orc_philox(e->seed, e->env_id, e->rng_ctr, 3, u);
   double c = u01(u[0]);
@@ -940,6 +1227,7 @@ static void task_reset(const orc_model* m, orc_env* e) {
 
 static void task_step(const orc_model* m, orc_env* e) {
   uint32_t u[4];
+  if (m->task == ORC_TASK_STEP) { task_step_step(m, e); return; }
   if (m->task == ORC_TASK_STAND) return;
   e->phase += 1;
   if (e->phase >= m->period) e->phase = 0;
@@ -1103,7 +1391,14 @@ void orc_env_init(const orc_model* m, orc_env* e, uint32_t seed, uint32_t env_id
   e->seed = seed;
   e->env_id = env_id;
   e->qpos[3] = 1.0;
+  /* a freshly compiled jvrc_step model has its 20 boxes below the floor (gen_xml.py:149: pos 0 0 -0.2): no contact */
+  for (int i = 0; i < ORC_NSLAB; i++) e->seq[i][2] = -1;
+  e->mode = m->task == ORC_TASK_STEP ? ORC_STEP_STANDING : 0;
 }
+/* test hooks for the SteppingTask pieces pinned by tests/golden/step_*.json */
+void orc_test_task_reset(const orc_model* m, orc_env* e) { task_reset(m, e); }
+void orc_test_task_step(const orc_model* m, orc_env* e) { task_step(m, e); }
+void orc_set_step_height(orc_model* m, double h) { m->step_height = h; }
 
 void orc_reset(const orc_model* m, orc_env* e, double* obs) {
   /* mj_resetData (mujoco_env.py:114): qvel, warmstart, ctrl <- 0 ; then reset_model: nominal pose, 3 zero-ctrl steps */
@@ -1159,8 +1454,13 @@ void orc_step(const orc_model* m, orc_env* e, const double* action, double* obs,
   }
   task_step(m, e);
   if (m->task == ORC_TASK_STAND) calc_reward_stand(m, e, t);
+  else if (m->task == ORC_TASK_STEP) calc_reward_step(m, e, t);
   else calc_reward(m, e, target, t);
   int d = (e->qpos[2] < m->done_lo) || (e->qpos[2] > m->done_hi) || e->self_collision || e->status;
+  if (m->task == ORC_TASK_STEP) {   /* SteppingTask.done (stepping_task.py:248-260): root height above the lower foot site */
+    double fz = e->site_pos[0][2] < e->site_pos[1][2] ? e->site_pos[0][2] : e->site_pos[1][2];
+    d = (e->root_xpos[2] - fz < m->done_lo) || e->self_collision || e->status;
+  }
   memcpy(e->prev_action, target, sizeof(target));
   memcpy(e->prev_torque, e->act_force, sizeof(e->prev_torque));
   if (obs) get_obs(m, e, obs);
@@ -1220,7 +1520,8 @@ void orc_batch_step_autoreset(const orc_model* m, orc_env* envs, int n, const do
 
 /* test hook: reward terms for the current env fields (lets tests/ pin calc_reward to the golden vectors) */
 void orc_calc_reward(const orc_model* m, const orc_env* e, const double* target, double* terms) {
-  if (m->task == ORC_TASK_STAND) calc_reward_stand(m, e, terms);
+  if (m->task == ORC_TASK_STEP) calc_reward_step(m, e, terms);
+  else if (m->task == ORC_TASK_STAND) calc_reward_stand(m, e, terms);
   else calc_reward(m, e, target, terms);
 }
 /* test hooks for the H1 pieces pinned by tests/golden/h1_*.json (each uses the env's current rng_ctr) */

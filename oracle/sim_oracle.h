@@ -29,18 +29,24 @@ extern "C" {
 #define ORC_NQ 19
 #define ORC_NU 12
 #define ORC_MAXGEOM 4
-#define ORC_MAXCON 12
+#define ORC_MAXCON 128
 #define ORC_MAXPTS 8
 #define ORC_MAXROW (2 * ORC_NU + 4 * ORC_MAXCON)
 #define ORC_MAXPERIOD 128
-#define ORC_NOBS 37
+#define ORC_NOBS 39
 #define ORC_NREW 10
 #define ORC_MAXCAP 16
 #define ORC_MAXPAIR 64
+#define ORC_NSLAB 20        /* stepping stones per env (envs/jvrc/gen_xml.py:147-153) */
+#define ORC_MAXPLAN 128
+#define ORC_MAXPLANLEN 20
+#define ORC_MAXCROSS 4     /* sole-edge x slab-boundary contacts kept per foot */
 
 enum { ORC_STANDING = 0, ORC_INPLACE = 1, ORC_FORWARD = 2 };
 enum { ORC_SOLVER_NEWTON = 0, ORC_SOLVER_PGS = 1 };
-enum { ORC_TASK_WALK = 0, ORC_TASK_STAND = 1 };
+enum { ORC_TASK_WALK = 0, ORC_TASK_STAND = 1, ORC_TASK_STEP = 2 };
+/* SteppingTask walk modes in the order of the np.random.choice list (tasks/stepping_task.py:268-271) */
+enum { ORC_STEP_CURVED = 0, ORC_STEP_STANDING = 1, ORC_STEP_BACKWARD = 2, ORC_STEP_LATERAL = 3, ORC_STEP_FORWARD = 4 };
 enum { ORC_GEOM_BOX = 0, ORC_GEOM_SPHERES = 1 };
 
 /* per-environment model parameters (domain randomisation edits these in place, envs/common/domain_randomization.py:29-56) */
@@ -98,6 +104,13 @@ typedef struct {
   /* root link = randomisable pelvis body + welded rest (H1) */
   double pel_mass, pel_com[3], pel_Ic[9], rest_mass, rest_mc[3], rest_Io[9], torso_com[3];
   double pdrand_k;                  /* RobotBase(pdrand_k): per-step PD gain randomisation, 0 = off (the reference's default) */
+  /* jvrc_step (envs/jvrc/jvrc_step.py, tasks/stepping_task.py): force-sensor sites, stepping-stone slabs, footstep plans */
+  double foot_site[2][3];           /* rf_force / lf_force site in the foot link frame (gen_xml.py:143-144) */
+  double slab_half[3];              /* half sizes of a slab: 0.15 x 1 x box_h (stepping_task.py:327) */
+  double target_radius, side_tol, step_height;   /* step_height: the curriculum's h for the current iteration_count */
+  int delay_frames, nplan;
+  int plan_len[ORC_MAXPLAN];
+  double plans[ORC_MAXPLAN][ORC_MAXPLANLEN][3];  /* utils/footstep_plans.txt: x, y, theta */
 } orc_model;
 
 typedef struct {
@@ -132,6 +145,13 @@ typedef struct {
   /* H1 additions (appended so the jvrc field offsets used by the tests stay put) */
   orc_params P;
   double xfrc[2][6];               /* world-frame [force, torque] on the pelvis and torso bodies, applied at their CoM */
+  /* SteppingTask state (tasks/stepping_task.py) */
+  double seq[ORC_NSLAB][4];        /* footstep sequence x, y, z, theta (world); slab k's top face sits at seq[k] */
+  double goal_steps[8];            /* _goal_steps_x[2], _y[2], _z[2], _theta[2] */
+  double site_pos[2][3];           /* rf_force / lf_force site_xpos (lagged, like every mjData quantity) */
+  double foot_xpos[2][3];          /* foot body xpos (lagged) */
+  double root_quat[4];             /* data.xquat of the root body (lagged, normalised) */
+  int seq_len, t1, t2, target_reached, target_reached_frames, con_overflow;
 } orc_env;
 
 /* fill a model from a flat double array (layout documented in oracle/oracle.py:pack_model) */

@@ -31,7 +31,7 @@ class Emu:
         self.dt = np.float64 if precision == 64 else np.float32
         self.nr = self.lib.emu_state_words(self.h)
         self.nobs = self.lib.emu_obs_dim(self.h)
-        self.nu = 2 * int(flat[0])
+        self.nu = 2 * (int(flat[0]) % 100)
         self.nq, self.nv = 7 + self.nu, 6 + self.nu
         self.sr = np.zeros((n, self.nr), dtype=self.dt)
         self.si = np.zeros((n, NSTATE_I), dtype=np.int32)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/lhw_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
-    assert L.lhw_version() == 2   # 2: lhw_sim_create also accepts the Unitree H1 standing model
+    assert L.lhw_version() == 3   # 2: + Unitree H1 standing model; 3: + JVRC-1 stepping model, lhw_sim_set_step_height
 
 
 def test_product_fails_loudly_without_cuda():

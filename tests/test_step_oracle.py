@@ -1,0 +1,185 @@
+"""jvrc_step (BASELINE configs[2]): the oracle's SteppingTask restatement against vectors produced by
+running the reference's tasks/stepping_task.py (tools/gen_golden_step.py), the stepping-stone contact model against
+physical invariants, and the product's kernel source (CPU emulation, tests/emu) against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from emu import Emu
+from learninghumanoidwalking_b200.model import load_model, pack_model
+from oracle.oracle import Oracle
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = ["foot_frc_score", "foot_vel_score", "orient_cost", "height_error", "step_reward", "upper_body_reward"]
+
+
+def quat2mat(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle("jvrc_step", tolerance=1e-14)
+
+
+def test_stepping_task_matches_the_reference_class(orc):
+    """SteppingTask.reset / step / calc_reward / done run from the reference's own file on recorded inputs."""
+    o = orc
+    cases = json.load(open(os.path.join(G, "step_task.json")))
+    assert {c["mode"] for c in cases} == {0, 1, 2, 3, 4}
+    n_adv = n_done = 0
+    for c in cases:
+        assert c["names"] == NAMES and c["period"] == 88 and c["delay_frames"] == 30
+        assert c["box_size"] == [0.15, 1.0, 0.1]
+        envs = o.make_envs(1, seed=c["seed"], first_id=c["env_id"])
+        o.set_iteration_count(np.inf if c["iteration_count"] is None else c["iteration_count"])
+        o.set_field(envs, 0, "rng_ctr", c["rng_ctr"])
+        o.set_field(envs, 0, "root_xpos", c["root_xpos"])
+        o.set_field(envs, 0, "root_xmat", c["root_xmat"])
+        o.set_field(envs, 0, "foot_xpos", c["rfoot_xpos"] + c["lfoot_xpos"])
+        o.task_reset(envs, 0)
+        n = len(c["seq"])
+        assert int(o.field(envs, 0, "mode")[0]) == c["mode"] and int(o.field(envs, 0, "phase")[0]) == c["phase"]
+        assert int(o.field(envs, 0, "seq_len")[0]) == n
+        assert (int(o.field(envs, 0, "t1")[0]), int(o.field(envs, 0, "t2")[0])) == (c["t1"], c["t2"])
+        seq = o.field(envs, 0, "seq").reshape(20, 4)
+        assert np.abs(seq[:n] - np.array(c["seq"])).max() < 1e-13
+        # the boxes the reference re-poses (stepping_task.py:318-334): top face through the step, yawed with it; the rest parked
+        bp, by = np.array(c["box_pos"]), np.array(c["box_yaw"])
+        assert np.abs(seq[:, :2] - bp[:, :2]).max() < 1e-13 and np.abs(seq[:, 2] - (bp[:, 2] + 0.1)).max() < 1e-13
+        assert np.abs(np.angle(np.exp(1j * (seq[:, 3] - by)))).max() < 1e-12
+        assert (c["floor_z"] == -2.0) == (c["mode"] == 4)
+        for s in c["steps"]:
+            o.set_field(envs, 0, "root_xpos", s["root_xpos"])
+            o.set_field(envs, 0, "root_xmat", quat2mat(s["root_quat"]).reshape(-1))
+            o.set_field(envs, 0, "root_quat", s["root_quat"])
+            o.set_field(envs, 0, "head_xpos", s["head_xpos"])
+            o.set_field(envs, 0, "site_pos", s["rsite"] + s["lsite"])
+            o.set_field(envs, 0, "rfoot_vel", s["rvel"]); o.set_field(envs, 0, "lfoot_vel", s["lvel"])
+            o.set_field(envs, 0, "rfoot_grf", s["rgrf"]); o.set_field(envs, 0, "lfoot_grf", s["lgrf"])
+            o.set_field(envs, 0, "ncon_r", s["ncon_r"]); o.set_field(envs, 0, "ncon_l", s["ncon_l"])
+            o.set_field(envs, 0, "contact_z_min", s["contact_z_min"])
+            o.task_step(envs, 0)
+            assert int(o.field(envs, 0, "phase")[0]) == s["phase"]
+            assert (int(o.field(envs, 0, "t1")[0]), int(o.field(envs, 0, "t2")[0])) == (s["t1"], s["t2"])
+            assert bool(o.field(envs, 0, "target_reached")[0]) == s["target_reached"]
+            assert int(o.field(envs, 0, "target_reached_frames")[0]) == s["frames"]
+            assert np.abs(o.field(envs, 0, "goal_steps") - np.array(s["goal_steps"])).max() < 1e-12
+            t = o.calc_reward(envs, 0, np.zeros(12))
+            assert np.abs(t[:6] - np.array(s["terms"])).max() < 1e-13 and (t[6:] == 0).all()
+            fz = min(s["rsite"][2], s["lsite"][2])
+            assert (s["root_xpos"][2] - fz < 0.6) == s["done"]      # SteppingTask.done with no self collision
+            n_done += s["done"]
+        n_adv += c["steps"][-1]["t1"] > 0
+    assert n_adv >= 6 and n_done >= 6
+
+
+def _stand_on(o, envs, seq_rows, mode):
+    """Nominal pose, zero velocity, given slab layout."""
+    q = np.array(o.mj["cfg"]["nominal_qpos"])
+    o.set_field(envs, 0, "qpos", q)
+    o.set_field(envs, 0, "qvel", np.zeros(18))
+    seq = np.tile([0.0, 0.0, -1.0, 0.0], (20, 1))
+    if len(seq_rows):
+        seq[:len(seq_rows)] = seq_rows
+    o.set_field(envs, 0, "seq", seq.reshape(-1))
+    o.set_field(envs, 0, "mode", mode)
+
+
+def test_slab_contacts_equal_floor_contacts_and_stack_as_multiplicity(orc):
+    """A slab whose top face is the plane z = 0 must act on a foot inside its footprint exactly like the floor; floor and
+    k coplanar slabs together are k + 1 identical contacts per corner (MuJoCo would list them all), which stiffens the
+    support but leaves the static force balance sum(GRF) = m g intact."""
+    o = orc
+    mg = o.mj["total_mass"] * 9.81
+    res = {}
+    for name, rows, mode in (("floor", [], 1), ("slab", [[0.12, 0, 0, 0.05]], 4), ("floor+slab", [[0.12, 0, 0, 0.05]], 1),
+                             ("floor+3", [[0.12, 0, 0, 0.05], [0.12, 0.2, 0, -0.05], [0.13, -0.1, 0, 0.0]], 1)):
+        envs = o.make_envs(1)
+        _stand_on(o, envs, rows, mode)
+        kp, kd = np.array(o.mj["cfg"]["kp"]), np.array(o.mj["cfg"]["kd"])
+        nom = np.array(o.mj["cfg"]["nominal_qpos"])[7:]
+        for _ in range(600):   # PD-held nominal stance settles within ~0.5 s
+            ctrl = kp * (nom - o.field(envs, 0, "qpos")[7:]) - kd * o.field(envs, 0, "qvel")[6:]
+            o.mj_step(envs, 0, ctrl)
+        res[name] = (o.field(envs, 0, "qpos").copy(), int(o.field(envs, 0, "ncon")[0]),
+                     float(o.field(envs, 0, "rfoot_grf")[0] + o.field(envs, 0, "lfoot_grf")[0]))
+    assert res["floor"][1] == res["slab"][1] and np.abs(res["floor"][0] - res["slab"][0]).max() < 1e-12
+    assert res["floor+slab"][1] == 2 * res["floor"][1] and res["floor+3"][1] == 4 * res["floor"][1]
+    z = [res[k][0][2] for k in ("floor", "floor+slab", "floor+3")]
+    assert z[0] < z[1] < z[2] and z[2] - z[0] < 2e-3          # stiffer support, less static penetration
+    for k in res:   # quasi-static (the PD-held stance sways slowly): sum of contact-force norms ~ m g in every layout
+        assert 0.95 * mg < res[k][2] < 1.05 * mg, (k, res[k][2], mg)
+    assert abs(res["floor+3"][2] - res["floor"][2]) < 0.01 * mg
+
+
+def test_foot_overhanging_a_slab_edge_is_held_by_edge_contacts(orc):
+    """FORWARD mode (no floor): with the slab ending under the middle of the feet, the sole-edge x slab-boundary crossing
+    vertices carry the load at the slab edge (without them the two inner corners alone would let the feet pitch over it)."""
+    o = orc
+    envs = o.make_envs(1)
+    # feet span x in [0.022, 0.222] at the nominal pose; slab covers x <= 0.15
+    _stand_on(o, envs, [[0.0, 0, 0, 0.0]], 4)
+    o.mj_step(envs, 0, np.zeros(12))
+    q0 = o.field(envs, 0, "qpos").copy()
+    kp, kd = np.array(o.mj["cfg"]["kp"]), np.array(o.mj["cfg"]["kd"])
+    nom = np.array(o.mj["cfg"]["nominal_qpos"])[7:]
+    ncon = set()
+    for _ in range(150):
+        ctrl = kp * (nom - o.field(envs, 0, "qpos")[7:]) - kd * o.field(envs, 0, "qvel")[6:]
+        o.mj_step(envs, 0, ctrl)
+        ncon.add(int(o.field(envs, 0, "ncon")[0]))
+    assert 8 in ncon                                  # 2 corners + 2 crossings per foot
+    assert o.field(envs, 0, "qpos")[2] > 0.775         # rests at the floor-supported stance height (0.787), did not tip over the edge
+
+
+def test_kernel_source_matches_oracle_on_stepping_stones():
+    """csrc/sim_core.h (Cfg<6,1>) emulated on the CPU vs the oracle: closed loop, falls, truncations, auto-resets, all five
+    walk modes, stairs (iteration_count = inf -> 0.1 m steps), contact counts up to 100+ in the oracle (one contact per
+    surface) against the kernel's merged multiplicities."""
+    o = Oracle("jvrc_step", tolerance=1e-14)
+    N = 10
+    e = Emu(pack_model(load_model("jvrc_step"), tolerance=1e-14), 64, N, seed=5, first_id=10)
+    assert e.nobs == 39 and e.nr == 204
+    envs = o.make_envs(N, seed=5, first_id=10)
+    assert np.abs(o.batch_reset(envs, N) - e.reset()).max() < 1e-12
+    rng = np.random.RandomState(2)
+    n_end, modes, ncons = 0, set(), set()
+    for _ in range(120):
+        a = rng.normal(size=(N, 12)) * 0.25
+        oo, to, tt, rr, dd, ee = o.batch_step(envs, N, a, max_traj_len=50)
+        eo, et, etm, er, ed, een, eplen, eprew = e.step(a, max_traj_len=50)
+        assert (dd == ed).all() and (ee == een).all()
+        assert np.abs(oo - eo).max() < 1e-9 and np.abs(rr - er).max() < 1e-10 and np.abs(tt - etm).max() < 1e-10
+        m = ee.astype(bool)
+        if m.any():
+            assert np.abs(to[m] - et[m]).max() < 1e-9
+            n_end += int(m.sum())
+        for i in range(N):
+            modes.add(int(o.field(envs, i, "mode")[0]))
+            ncons.add(int(o.field(envs, i, "ncon")[0]))
+    assert n_end >= 15 and modes == {0, 1, 2, 3, 4} and max(ncons) > 40
+    base = 19 + 18 + 18 + 5 * 12 + 3 + 1
+    seq_o = np.stack([o.field(envs, i, "seq") for i in range(N)])
+    assert np.abs(e.sr[:, base:base + 80] - seq_o).max() < 1e-12
+    assert (e.si[:, 1] == [int(o.field(envs, i, "mode")[0]) for i in range(N)]).all()
+    assert all(int(o.field(envs, i, "con_overflow")[0]) == 0 for i in range(N))
+
+
+def test_height_curriculum_follows_iteration_count():
+    """robot.iteration_count -> h = clip((it - 3000) / 8000, 0, 1) * 0.1 (stepping_task.py:312): flat below 3000."""
+    mj = load_model("jvrc_step")
+    for it, h in ((0, 0.0), (3000, 0.0), (7000, 0.05), (20000, 0.1), (np.inf, 0.1)):
+        o = Oracle("jvrc_step", iteration_count=it)
+        e = Emu(pack_model(mj, iteration_count=it), 64, 24, seed=11)
+        envs = o.make_envs(24, seed=11)
+        assert np.abs(o.batch_reset(envs, 24) - e.reset()).max() < 1e-12
+        zs = np.stack([o.field(envs, i, "seq").reshape(20, 4)[:, 2] for i in range(24)])
+        fwd = np.array([int(o.field(envs, i, "mode")[0]) == 4 for i in range(24)])
+        assert fwd.any() and np.abs(np.abs(zs[fwd]).max(axis=1) - h * 15).max() < 1e-12 + h * 1.01   # 16 or 15 raised steps
+        assert (zs[~fwd][zs[~fwd] > -1] == 0).all()

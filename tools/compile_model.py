@@ -226,6 +226,29 @@ def compile_jvrc(boxes: bool = False):
         nominal_qpos=[0.0, 0.0, 0.81, 1.0, 0.0, 0.0, 0.0] + np.deg2rad(cfg["half_sitting_pose"]).tolist(),
         task=dict(cfg["task"]),
     )
+    if boxes:
+        # envs/jvrc/jvrc_step.py + tasks/stepping_task.py: force-sensor sites (gen_xml.py:143-144), 20 stepping-stone slabs
+        # (gen_xml.py:147-153; re-sized to 0.15 x 1 x box_h at every task reset, stepping_task.py:322-329), footstep plans
+        site = [r5(0.03), 0.0, r5(-0.1)]
+        model["foot_sites"] = [site, site]          # rf_force, lf_force in the foot link frame
+        plans, seq = [], []
+        for line in open(os.path.join(REF, "utils/footstep_plans.txt")):
+            line = line.strip()
+            if line == "---":                       # stepping_task.py:57-64 (a trailing block without '---' is dropped)
+                if seq:
+                    plans.append(seq)
+                seq = []
+            else:
+                seq.append([float(v) for v in line.split(",")])
+        t = cfg["task"]
+        model["stepping"] = dict(
+            nboxes=20, slab_half=[0.15, 1.0, r5(0.1)], target_radius=0.20,
+            delay_frames=int(np.floor(t["swing_duration"] / cfg["control_dt"])),
+            # not in the reference: penetration depth up to which a slab's top face always supports a point (beyond it the
+            # point must be at least as far from the slab's side faces), see oracle/sim_oracle.c:slab_supports
+            side_tol=0.02,
+            mode_probs=[0.15, 0.05, 0.2, 0.3, 0.3],  # CURVED, STANDING, BACKWARD, LATERAL, FORWARD
+            plans=plans)
     add_setconst(model)
     return model
 
@@ -504,6 +527,11 @@ def main():
     for lk in m["links"]:
         print(f"  {lk['name']:14s} parent {lk['parent']:2d} mass {lk['mass']:.4f} com {np.round(lk['com'], 4)}")
     print("foot invweight0", m["link_invweight0"][m["rfoot_link"]], "dof_invweight0", np.round(m["dof_invweight0"], 4))
+    st = compile_jvrc(boxes=True)
+    if "self_collision" in m:
+        st["self_collision"] = m["self_collision"]
+    json.dump(st, open(os.path.join(args.out, "jvrc_step.json"), "w"), indent=1)
+    print("wrote jvrc_step.json plans", len(st["stepping"]["plans"]), "delay_frames", st["stepping"]["delay_frames"])
     h = compile_h1()
     json.dump(h, open(os.path.join(args.out, "h1.json"), "w"), indent=1)
     print("wrote h1.json mass", h["total_mass"], "links", len(h["links"]), "meaninertia", h["meaninertia"])
