@@ -124,6 +124,9 @@ template <class real, int NJ, int TK> int fill_model(Model<real, NJ, TK>& m, con
       for (int k = 0; k < 3 * len; k++) row[1 + k] = (real)rd();
     }
     m.plans = plan_table;
+    for (int f = 0; f < 2; f++)
+      m.foot_rad[f] = (real)(sqrt((double)m.foot_size[f][0] * m.foot_size[f][0] + (double)m.foot_size[f][1] * m.foot_size[f][1] +
+                                  (double)m.foot_size[f][2] * m.foot_size[f][2]) * 1.0001 + 1e-6);
   }
   if (p != n) return -3;
   return 0;

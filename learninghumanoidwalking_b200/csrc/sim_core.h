@@ -136,6 +136,41 @@ template <class real, class F> LHW_DEV real warp_sum(F f) {
 #endif
 }
 
+// warp ballot of a per-lane predicate; bit helpers (the CPU emulation evaluates the predicate lane by lane)
+template <class F> LHW_DEV unsigned warp_ballot(F f) {
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+  return __ballot_sync(0xffffffffu, f((int)(threadIdx.x & 31)));
+#else
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m |= f(l) ? (1u << l) : 0u;
+  return m;
+#endif
+}
+LHW_DEV int bit_count(unsigned m) {
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+  return __popc(m);
+#else
+  return __builtin_popcount(m);
+#endif
+}
+LHW_DEV int lowest_bit(unsigned m) {   // index of the lowest set bit (m != 0)
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+  return __ffs(m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
+LHW_DEV int nth_bit(unsigned m, int n) {   // index of the n-th (0-based) set bit, 32 if there is none
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+  const unsigned r = __fns(m, 0, n + 1);
+  return r == 0xffffffffu ? 32 : (int)r;
+#else
+  for (int i = 0; i < 32; i++)
+    if (m & (1u << i)) { if (n == 0) return i; n--; }
+  return 32;
+#endif
+}
+
 // ---------------------------------------------------------------- rng: philox4x32-10, counter (event, stream, env)
 LHW_DEV void philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t stream, uint32_t out[4]) {
   uint32_t c0 = ctr, c1 = stream, c2 = env_id, c3 = 0x4c485742u;
@@ -178,7 +213,7 @@ template <class real, int NJ, int TK> struct Model {
   real pel_mass, pel_com[3], pel_Ic[6], rest_mass, rest_mc[3], rest_Io[6], torso_com[3];  // root link = pelvis body + welded rest
   int axis_id[NL];  // 0/1/2: hinge axis is +e_x/+e_y/+e_z of the link frame AND link_rot is the identity (fast FK path); -1: general
   // SteppingTask (Cfg::STEP): force-sensor sites, slab half sizes, target logic, curriculum step height, footstep plans
-  real foot_site[2][3], slab_half[3], target_radius, side_tol, step_height;
+  real foot_site[2][3], slab_half[3], target_radius, side_tol, step_height, foot_rad[2];   // foot_rad: box circumradius (+1e-6)
   int delay_frames, nplan;
   const real* plans;   // [nplan][PLAN_STRIDE] in global memory (host memory in the CPU emulation)
 };
@@ -808,6 +843,30 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
   }
   LHW_SYNC();
+  // stepping stones, broad phase: per foot the set of slabs whose footprint (grown by the foot box's circumradius) holds
+  // the box centre and whose top face is within vertical reach; a superset of the slabs any corner / sole edge can touch,
+  // so the narrow phases below give exactly what an exhaustive test over the 20 slabs gives
+  unsigned near_slabs[2] = {0u, 0u};
+  if constexpr (Cfg<NJ, TK>::STEP) {
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      near_slabs[f] = warp_ballot([&](int l) -> bool {
+        if (l >= NSLAB) return false;
+        const int lk = (f + 1) * NJ;
+        const real* R = w.xmat[lk];
+        const real* fp = m.foot_pos[f];
+        const real cx = w.o[0] + w.xr[lk][0] + R[0] * fp[0] + R[1] * fp[1] + R[2] * fp[2];
+        const real cy = w.o[1] + w.xr[lk][1] + R[3] * fp[0] + R[4] * fp[1] + R[5] * fp[2];
+        const real cz = w.o[2] + w.xr[lk][2] + R[6] * fp[0] + R[7] * fp[1] + R[8] * fp[2];
+        const real rad = m.foot_rad[f];
+        const real* sl = w.seq[l];
+        if (!(cz - rad < sl[2]) || !(cz + rad > sl[2] - 2 * m.slab_half[2])) return false;
+        const real c = w.slab_cs[l][0], sn = w.slab_cs[l][1];
+        const real dx = cx - sl[0], dy = cy - sl[1];
+        return m_abs(c * dx + sn * dy) <= m.slab_half[0] + rad && m_abs(-sn * dx + c * dy) <= m.slab_half[1] + rad;
+      });
+    }
+  }
   // ---------------- P6 link forces f_i = I A + V x* (I V) (lane = link) ; foot-box corner candidates (lanes 16..31)
   LHW_LANES(l) {
     if (l < NL) {
@@ -854,7 +913,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         int have = 0, mult = 0;
         if (az - floor_z < 0) { best = floor_z; have = 1; mult = 1; }
 #pragma unroll 1
-        for (int sidx = 0; sidx < NSLAB; sidx++) {
+        for (unsigned mk = near_slabs[f]; mk; mk &= mk - 1) {
+          const int sidx = lowest_bit(mk);
           const real* sl = w.seq[sidx];
           const real d = az - sl[2];
           if (!(d < 0) || -d >= 2 * m.slab_half[2]) continue;
@@ -907,14 +967,15 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
 #pragma unroll 1
     for (int f = 0; f < 2; f++) {
       int run = 0;
+      const int ntask = 4 * bit_count(near_slabs[f]);
 #pragma unroll 1
-      for (int pass = 0; pass < (4 * NSLAB + 31) / 32; pass++) {
+      for (int pass = 0; pass * 32 < ntask; pass++) {
         LHW_LANES(l) {
           const int t = pass * 32 + l;
           int he = 0, hx = 0;
           real pe[4], px[4];   // x, y, z relative to o, signed distance
-          if (t < 4 * NSLAB) {
-            const int sidx = t >> 2, ed = t & 3;
+          if (t < ntask) {
+            const int sidx = nth_bit(near_slabs[f], t >> 2), ed = t & 3;
             const int ia = ed == 0 ? 0 : ed == 1 ? 1 : ed == 2 ? 3 : 2, ib = ed == 0 ? 1 : ed == 1 ? 3 : ed == 2 ? 2 : 0;
             const real* A = w.cwp[f * 8 + ia];
             const real* B = w.cwp[f * 8 + ib];

@@ -1,0 +1,218 @@
+#!/usr/bin/env python3
+"""run_experiment.py — the reference's entry point (run_experiment.py:105-330) on the B200 path.
+
+    python run_experiment.py train --env jvrc_walk --logdir /tmp/logs --num-procs 4096 --n-itr 100 --seed 0
+    python -m torch.distributed.run --nproc-per-node 8 run_experiment.py train --env jvrc_step --num-procs 8192 ...
+    python run_experiment.py eval --logdir /tmp/logs [--ep-len 10]
+
+Same sub-commands and flags as the reference.  What differs underneath: `--num-procs` is the number of parallel environment
+copies (device resident, sharded by index across the ranks of a torchrun launch) instead of Ray worker processes; there is
+no Ray, no MuJoCo and no viewer — `eval` rolls the saved actor out deterministically on one device environment and prints
+the per-term reward means (the reference's EvaluateEnv renders a video with MuJoCo's GL context, out of scope here).
+Artefacts keep the reference's names and format: `<logdir>/<timestamp>_<env>/experiment.pkl`, `actor_<itr>.pt`,
+`critic_<itr>.pt` (whole pickled modules, rl/utils/checkpointer.py:51-83).
+"""
+import argparse
+import os
+import pickle
+import platform
+import re
+import sys
+from datetime import datetime
+from functools import partial
+from pathlib import Path
+
+import torch
+
+ENVS = ("jvrc_walk", "jvrc_step", "h1")
+
+
+def print_system_info(args, training=True):
+    print("=" * 60)
+    print("System Information")
+    print("=" * 60)
+    print(f"PyTorch version: {torch.__version__}")
+    print(f"Platform: {platform.system()} {platform.release()}")
+    print(f"CUDA devices: {torch.cuda.device_count()}"
+          + (f" ({torch.cuda.get_device_name(0)})" if torch.cuda.is_available() else ""))
+    if training:
+        print("-" * 60)
+        print("Training Configuration")
+        print("-" * 60)
+        for k, v in (("Environment", args.env), ("Log directory", args.logdir), ("Parallel envs", args.num_procs),
+                     ("Learning rate", args.lr), ("Max trajectory length", args.max_traj_len), ("Iterations", args.n_itr),
+                     ("Seed", args.seed)):
+            print(f"{k}: {v}")
+    print("=" * 60)
+
+
+def get_latest_run_dir(logdir):
+    logdir = Path(logdir)
+    subdirs = [d for d in logdir.iterdir() if d.is_dir()] if logdir.exists() else []
+    return max(subdirs, key=lambda d: d.stat().st_mtime) if subdirs else None
+
+
+def get_latest_actor(run_dir):
+    files = list(Path(run_dir).glob("actor_*.pt"))
+    if not files:
+        return Path(run_dir) / "actor.pt"
+    return max(files, key=lambda f: int(m.group(1)) if (m := re.search(r"actor_(\d+)\.pt$", f.name)) else -1)
+
+
+def import_env(env_name_str):
+    """run_experiment.py:87-101: env name -> factory of a device-resident batch of that environment."""
+    if env_name_str not in ENVS:
+        raise Exception("Check env name! (this build has: " + ", ".join(ENVS) + ")")
+    from learninghumanoidwalking_b200.envs import BatchedHumanoidEnv
+    return partial(BatchedHumanoidEnv, model=env_name_str)
+
+
+def _dist_setup():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return dist.get_rank(), world, local
+    return 0, 1, 0
+
+
+def run_experiment(args):
+    from learninghumanoidwalking_b200.rl import PPO
+    from learninghumanoidwalking_b200.rl.dist_utils import env_shard
+    from learninghumanoidwalking_b200.rl.symmetric import SymmetricEnv
+    rank, world, local = _dist_setup()
+    timestamp = datetime.now().strftime("%y-%m-%d-%H-%M-%S-%f")[:-3]
+    args.logdir = Path(args.logdir) / f"{timestamp}_{args.env}"
+    if rank == 0:
+        print_system_info(args)
+    if args.yaml is not None:
+        raise NotImplementedError("custom YAML: recompile the model constants with tools/compile_model.py")
+    if args.recurrent or args.imitate:
+        raise NotImplementedError("--recurrent / --imitate are outside the accelerated path (SURVEY.md §2)")
+    Env = import_env(args.env)
+    first, n_local = env_shard(rank, world, args.num_procs)
+    seed = args.seed if args.seed is not None else 0
+    env_fn = partial(Env, n_local, precision=args.precision, seed=seed, first_env_id=first, device=local,
+                     max_traj_len=args.max_traj_len)
+    _env = env_fn()
+    if not args.no_mirror:
+        try:
+            r = _env.robot
+            env_fn = partial(SymmetricEnv, env_fn, mirrored_obs=r.mirrored_obs, mirrored_act=r.mirrored_acts,
+                             clock_inds=r.clock_inds)
+            if rank == 0:
+                print("Wrapping in SymmetricEnv.")
+        except AttributeError as e:
+            print("Warning! Cannot use SymmetricEnv.", e)
+    _env.close()
+    if rank == 0:
+        Path.mkdir(args.logdir, parents=True, exist_ok=True)
+        with open(Path(args.logdir, "experiment.pkl"), "wb") as f:
+            pickle.dump(args, f)
+    algo = PPO(env_fn, args, seed=args.seed)
+    if args.continued is not None:
+        actor = torch.load(args.continued, weights_only=False)
+        critic = torch.load(Path(args.continued.parent, "critic" + str(args.continued).split("actor")[1]), weights_only=False)
+        algo.policy.load_state_dict(actor.state_dict())
+        algo.critic.load_state_dict(critic.state_dict())
+    algo.train(env_fn, args.n_itr, verbose=rank == 0)
+
+
+def evaluate(args):
+    """Deterministic roll-out of a saved actor on one device environment (the numbers EvaluateEnv would overlay)."""
+    if args.path is not None:
+        if args.path.is_file() and args.path.suffix == ".pt":
+            path_to_actor = args.path
+        elif args.path.is_dir():
+            path_to_actor = get_latest_actor(args.path)
+        else:
+            raise Exception("Invalid path to actor module: ", args.path)
+    elif args.logdir is not None:
+        latest = get_latest_run_dir(args.logdir)
+        if latest is None:
+            raise Exception(f"No run directories found under: {args.logdir}")
+        path_to_actor = get_latest_actor(latest)
+    else:
+        raise Exception("Must provide either --path or --logdir")
+    print(f"Loading model: {path_to_actor}")
+    with open(Path(path_to_actor.parent, "experiment.pkl"), "rb") as f:
+        run_args = pickle.load(f)
+    policy = torch.load(path_to_actor, weights_only=False).cuda().eval()
+    print_system_info(args, training=False)
+    env = import_env(run_args.env)(1, precision=64, seed=args.seed or 0)
+    obs = env.reset().float()
+    n_steps = int(args.ep_len / env.dt)
+    totals, ep_ret, ep_len, episodes = torch.zeros(10, dtype=env.dtype, device=env.device), 0.0, 0, []
+    with torch.no_grad():
+        for _ in range(n_steps):
+            obs, rew, done, _ = env.step(policy(obs, deterministic=True).to(env.dtype), autoreset=False)
+            totals += env.rew_terms[0]
+            ep_ret, ep_len = ep_ret + float(rew[0]), ep_len + 1
+            if bool(done[0]):
+                episodes.append((ep_len, ep_ret))
+                ep_ret, ep_len = 0.0, 0
+                obs = env.reset()
+            obs = obs.float()
+    episodes.append((ep_len, ep_ret))
+    print(f"{len(episodes)} episode(s) in {n_steps} control steps: " + ", ".join(f"len {l} return {r:.2f}" for l, r in episodes))
+    for name, v in zip(env.reward_names, (totals / n_steps).tolist()):
+        print(f"  mean {name:>20s} {v:.4f}")
+    env.close()
+    return episodes
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    parser = argparse.ArgumentParser()
+    if argv and argv[0] == "train":
+        parser.add_argument("--env", required=True, type=str)
+        parser.add_argument("--logdir", default=Path("/tmp/logs"), type=Path, help="Path to save weights and logs")
+        parser.add_argument("--input-norm-steps", type=int, default=100000)
+        parser.add_argument("--n-itr", type=int, default=20000, help="Number of iterations of the learning algorithm")
+        parser.add_argument("--lr", type=float, default=3e-4, help="Adam learning rate")
+        parser.add_argument("--eps", type=float, default=1e-5, help="Adam epsilon (for numerical stability)")
+        parser.add_argument("--gamma", type=float, default=0.99, help="MDP discount")
+        parser.add_argument("--lam", type=float, default=0.95, help="GAE lambda (1.0 = MC returns, 0.0 = TD(0))")
+        parser.add_argument("--std-dev", type=float, default=0.223, help="Action noise for exploration")
+        parser.add_argument("--learn-std", action="store_true", help="Exploration noise will be learned")
+        parser.add_argument("--entropy-coeff", type=float, default=0.0, help="Coefficient for entropy regularization")
+        parser.add_argument("--clip", type=float, default=0.2, help="Clipping parameter for PPO surrogate loss")
+        parser.add_argument("--minibatch-size", type=int, default=64, help="Batch size for PPO updates")
+        parser.add_argument("--epochs", type=int, default=3, help="Number of optimization epochs per PPO update")
+        parser.add_argument("--num-procs", type=int, default=4096, help="Number of parallel environment copies (all ranks)")
+        parser.add_argument("--max-grad-norm", type=float, default=0.5, help="Value to clip gradients at")
+        parser.add_argument("--max-traj-len", type=int, default=400, help="Max episode horizon")
+        parser.add_argument("--no-mirror", required=False, action="store_true", help="to use SymmetricEnv")
+        parser.add_argument("--mirror-coeff", required=False, default=0.4, type=float, help="weight for mirror loss")
+        parser.add_argument("--eval-freq", required=False, default=100, type=int, help="Frequency of saving checkpoints")
+        parser.add_argument("--continued", required=False, type=Path, help="path to pretrained weights")
+        parser.add_argument("--recurrent", required=False, action="store_true", help="use LSTM instead of FF")
+        parser.add_argument("--imitate", required=False, type=str, default=None, help="Policy to imitate")
+        parser.add_argument("--imitate-coeff", required=False, type=float, default=0.0)
+        parser.add_argument("--yaml", required=False, type=str, default=None, help="Path to config file passed to Env class")
+        parser.add_argument("--device", required=False, type=str, default="cuda", choices=["auto", "cuda"])
+        parser.add_argument("--seed", type=int, default=None, help="Random seed for reproducibility.")
+        parser.add_argument("--precision", type=int, default=32, choices=[32, 64],
+                            help="arithmetic of the device simulator (64 = the reference's float64)")
+        parser.add_argument("--steps-per-env", type=int, default=None, help="transitions per env per iteration (default: max-traj-len)")
+        args = parser.parse_args(argv[1:])
+        if args.seed is not None:
+            torch.manual_seed(args.seed)
+            print(f"Deterministic mode enabled with seed: {args.seed}")
+        return run_experiment(args)
+    elif argv and argv[0] == "eval":
+        parser.add_argument("--path", required=False, type=Path, default=None)
+        parser.add_argument("--logdir", required=False, type=Path, default=None)
+        parser.add_argument("--out-dir", required=False, type=Path, default=None, help="(videos are not produced by this build)")
+        parser.add_argument("--ep-len", required=False, type=int, default=10, help="Episode length to play (in seconds)")
+        parser.add_argument("--seed", type=int, default=None)
+        args = parser.parse_args(argv[1:])
+        return evaluate(args)
+    else:
+        parser.error("usage: run_experiment.py {train,eval} ...")
+
+
+if __name__ == "__main__":
+    main()

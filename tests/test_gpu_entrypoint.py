@@ -1,0 +1,37 @@
+"""run_experiment.py (the reference's entry point, run_experiment.py:105-330) on the device path: `train` writes the
+reference's artefacts, `eval` finds and rolls out the latest actor."""
+import pickle
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("env_name,obs_dim,act_dim", [("jvrc_walk", 37, 12), ("jvrc_step", 39, 12), ("h1", 35, 10)])
+def test_train_then_eval(tmp_path, env_name, obs_dim, act_dim, capsys):
+    import run_experiment as rx
+    rx.main(["train", "--env", env_name, "--logdir", str(tmp_path), "--num-procs", "64", "--n-itr", "2", "--max-traj-len", "40",
+             "--minibatch-size", "256", "--epochs", "1", "--seed", "3", "--eval-freq", "2"])
+    runs = list(tmp_path.iterdir())
+    assert len(runs) == 1 and runs[0].name.endswith("_" + env_name)
+    names = sorted(p.name for p in runs[0].iterdir())
+    assert names == ["actor_0.pt", "actor_1.pt", "critic_0.pt", "critic_1.pt", "experiment.pkl"]
+    args = pickle.load(open(runs[0] / "experiment.pkl", "rb"))
+    assert args.env == env_name and args.num_procs == 64
+    actor = torch.load(runs[0] / "actor_1.pt", weights_only=False)
+    assert actor(torch.zeros(3, obs_dim, device="cuda")).shape == (3, act_dim)
+    assert rx.get_latest_actor(runs[0]).name == "actor_1.pt"
+    capsys.readouterr()
+    episodes = rx.main(["eval", "--logdir", str(tmp_path), "--ep-len", "2"]) or []
+    out = capsys.readouterr().out
+    assert "episode(s) in 80 control steps" in out and "mean" in out
+
+
+def test_unknown_env_and_unsupported_flags(tmp_path):
+    import run_experiment as rx
+    with pytest.raises(Exception, match="Check env name"):
+        rx.main(["train", "--env", "cartpole", "--logdir", str(tmp_path), "--n-itr", "1"])
+    with pytest.raises(NotImplementedError):
+        rx.main(["train", "--env", "jvrc_walk", "--logdir", str(tmp_path), "--n-itr", "1", "--recurrent"])
