@@ -111,6 +111,9 @@ WORKLOADS = {
                       desc="jvrc_step footstep-plan task {n} envs/GPU (BASELINE configs[2]), JVRC-1 sim_dt=0.001 control_dt=0.025, "
                            "20 stepping-stone slabs per env (footstep sequences, floor dropped in FORWARD mode, 0.1 m stairs: "
                            "iteration_count = inf) in the kernel"),
+    "jvrc_walk_terrain": dict(model="jvrc_walk_terrain", metric="env-steps/sec jvrc_walk uneven/compliant terrain",
+                              desc="jvrc_walk on uneven / compliant terrain {n} envs/GPU (BASELINE configs[4]; an EXTENSION — the reference "
+                                   "has only the unused manip_hfield hook): 20 terraces re-posed with the hook's ranges, contact solref 0.04 s"),
     "h1": dict(model="h1", metric="env-steps/sec h1 standing",
                desc="h1 standing task {n} envs/GPU (BASELINE configs[3]), Unitree H1 sim_dt=0.001 control_dt=0.025, observation "
                     "noise + dynamics randomisation (damping, frictionloss, mass, CoM) + random pushes in the kernel"),
@@ -152,7 +155,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--workload", default="jvrc_walk", choices=sorted(WORKLOADS),
-                    help="jvrc_walk: the configuration BASELINE.json's metric is quoted on (default); jvrc_step: configs[2]; h1: configs[3]")
+                    help="jvrc_walk: the configuration BASELINE.json's metric is quoted on (default); jvrc_step: configs[2]; h1: configs[3]; jvrc_walk_terrain: configs[4] (extension)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -31,6 +31,8 @@ const char* lhw_last_error(void);
  * constants as a flat HOST float64 array (layout: learninghumanoidwalking_b200/model/loader.py).
  * The first word selects the robot/task variant: 106 = JVRC-1 + SteppingTask (envs/jvrc/jvrc_step.py,
  * tasks/stepping_task.py: footstep sequences, 20 per-env stepping-stone slabs, floor dropped in FORWARD mode),
+ * 206 = JVRC-1 + WalkingTask on uneven / compliant terrain (an EXTENSION: the reference only has the unused
+ * WalkingTask(manip_hfield) hook, tasks/walking_task.py:57,172-179; 20 terraces re-posed with that hook's ranges),
  * 6 = JVRC-1 + WalkingTask (envs/jvrc/jvrc_walk.py),
  * 5 = Unitree H1 + StandingTask (envs/h1/h1_env.py, envs/h1/h1_base.py:31-63: mass overrides, PD gains,
  * StandingTask), whose step also runs the observation noise, dynamics randomisation, random pushes and

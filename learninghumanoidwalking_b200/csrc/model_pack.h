@@ -60,6 +60,7 @@ template <class real, int NJ, int TK> int fill_model(Model<real, NJ, TK>& m, con
   const double dmax = solimp[1];
   m.K = (real)(1.0 / fmax(1e-15, dmax * dmax * tau * tau * zeta * zeta));
   m.B = (real)(2.0 / fmax(1e-15, dmax * tau));
+  m.Kc = m.K; m.Bc = m.B;
   for (int k = 0; k < 5; k++) m.solimp[k] = (real)solimp[k];
   m.mu = (real)mu;
   m.mu_reg = (real)(mu * sqrt(1.0 / fmax(1e-15, impratio)));
@@ -109,6 +110,23 @@ template <class real, int NJ, int TK> int fill_model(Model<real, NJ, TK>& m, con
   for (int k = 0; k < 6; k++) m.rest_Io[k] = (real)rd();
   for (int k = 0; k < 3; k++) m.torso_com[k] = (real)rd();
   m.pdrand_k = (real)rd();
+  if constexpr (Cfg<NJ, TK>::TERRAIN) {
+    for (int k = 0; k < 3; k++) m.slab_half[k] = (real)rd();
+    m.side_tol = (real)rd(); m.terrain_pitch = (real)rd(); m.terrain_bump = (real)rd(); m.terrain_zlo = (real)rd();
+    m.terrain_zhi = (real)rd(); m.terrain_xy = (real)rd(); m.terrain_interval = (int)rd();
+    const double tc0 = rd(), zc = rd();
+    if (m.terrain_interval < 1) return -10;
+    if (tc0 > 0) {   // the foot-ground contact pairs carry their own solref (mj_makeImpedance with refsafe)
+      const double tc = tc0 < 2 * h ? 2 * h : tc0;
+      m.Kc = (real)(1.0 / fmax(1e-15, dmax * dmax * tc * tc * zc * zc));
+      m.Bc = (real)(2.0 / fmax(1e-15, dmax * tc));
+    }
+  }
+  if constexpr (Cfg<NJ, TK>::SLABS) {
+    for (int f = 0; f < 2; f++)
+      m.foot_rad[f] = (real)(sqrt((double)m.foot_size[f][0] * m.foot_size[f][0] + (double)m.foot_size[f][1] * m.foot_size[f][1] +
+                                  (double)m.foot_size[f][2] * m.foot_size[f][2]) * 1.0001 + 1e-6);
+  }
   if constexpr (Cfg<NJ, TK>::STEP) {
     for (int f = 0; f < 2; f++)
       for (int k = 0; k < 3; k++) m.foot_site[f][k] = (real)rd();
@@ -124,9 +142,6 @@ template <class real, int NJ, int TK> int fill_model(Model<real, NJ, TK>& m, con
       for (int k = 0; k < 3 * len; k++) row[1 + k] = (real)rd();
     }
     m.plans = plan_table;
-    for (int f = 0; f < 2; f++)
-      m.foot_rad[f] = (real)(sqrt((double)m.foot_size[f][0] * m.foot_size[f][0] + (double)m.foot_size[f][1] * m.foot_size[f][1] +
-                                  (double)m.foot_size[f][2] * m.foot_size[f][2]) * 1.0001 + 1e-6);
   }
   if (p != n) return -3;
   return 0;

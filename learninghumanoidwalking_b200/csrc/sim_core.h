@@ -86,15 +86,19 @@ constexpr int MAXPAIR = 64;
 template <int NJ, int TK> struct Cfg;
 template <> struct Cfg<6, 0> {  // JVRC-1, WalkingTask: box feet (mjc_PlaneBox: at most 4 of the 8 corners per foot)
   static constexpr int CPF = 4, NPTS = 8;
-  static constexpr bool SPHERES = false, FLOSS = false, PERENV = false, STAND = false, STEP = false;
+  static constexpr bool SPHERES = false, FLOSS = false, PERENV = false, STAND = false, STEP = false, SLABS = false, TERRAIN = false;
 };
 template <> struct Cfg<5, 0> {  // Unitree H1, StandingTask: 3 capsules per foot = 6 end spheres; dof friction loss;
   static constexpr int CPF = 6, NPTS = 6;  // per-env randomised mass / com / damping / frictionloss; xfrc perturbations
-  static constexpr bool SPHERES = true, FLOSS = true, PERENV = true, STAND = true, STEP = false;
+  static constexpr bool SPHERES = true, FLOSS = true, PERENV = true, STAND = true, STEP = false, SLABS = false, TERRAIN = false;
 };
 template <> struct Cfg<6, 1> {  // JVRC-1, SteppingTask: box feet on the floor + 20 per-env stepping-stone slabs;
   static constexpr int CPF = 8, NPTS = 8;  // per foot 4 corner slots (with multiplicity) + 4 sole-edge x slab-boundary slots
-  static constexpr bool SPHERES = false, FLOSS = false, PERENV = false, STAND = false, STEP = true;
+  static constexpr bool SPHERES = false, FLOSS = false, PERENV = false, STAND = false, STEP = true, SLABS = true, TERRAIN = false;
+};
+template <> struct Cfg<6, 2> {  // JVRC-1, WalkingTask on uneven / compliant terrain (extension, BASELINE configs[4]): 20 terraces
+  static constexpr int CPF = 8, NPTS = 8;  // = the slabs of the stepping stones, re-posed like the reference's manip_hfield hook
+  static constexpr bool SPHERES = false, FLOSS = false, PERENV = false, STAND = false, STEP = false, SLABS = true, TERRAIN = true;
 };
 constexpr int NSLAB = 20;          // stepping stones per env (envs/jvrc/gen_xml.py:147-153)
 constexpr int NCORNER = 4;         // corner slots per foot (mjc_PlaneBox keeps at most 4)
@@ -197,7 +201,7 @@ template <class real, int NJ, int TK> struct Model {
   real foot_pos[2][3], foot_size[2][3], foot_invw[2];
   real foot_pts[2][Cfg<NJ, TK>::NPTS][3], foot_radius[2];  // SPHERES: sphere centres in the foot link frame
   real h, grav[3];
-  real K, B, solimp[5], mu, mu_reg;  // mu_reg = mu * sqrt(1/impratio)
+  real K, B, Kc, Bc, solimp[5], mu, mu_reg;  // mu_reg = mu * sqrt(1/impratio); Kc, Bc: foot-ground contacts (= K, B by default)
   real tol2;                         // (tolerance * meaninertia * nv)^2 : threshold on |grad|^2
   real kp[NU], kd[NU], nominal[NQ], smoothing;
   real head[3], fcap, goal_height;
@@ -214,6 +218,9 @@ template <class real, int NJ, int TK> struct Model {
   int axis_id[NL];  // 0/1/2: hinge axis is +e_x/+e_y/+e_z of the link frame AND link_rot is the identity (fast FK path); -1: general
   // SteppingTask (Cfg::STEP): force-sensor sites, slab half sizes, target logic, curriculum step height, footstep plans
   real foot_site[2][3], slab_half[3], target_radius, side_tol, step_height, foot_rad[2];   // foot_rad: box circumradius (+1e-6)
+  // terrain extension (Cfg::TERRAIN): terrace pitch, bump range, pose ranges of the manip_hfield hook, re-pose interval
+  real terrain_pitch, terrain_bump, terrain_zlo, terrain_zhi, terrain_xy;
+  int terrain_interval;
   int delay_frames, nplan;
   const real* plans;   // [nplan][PLAN_STRIDE] in global memory (host memory in the CPU emulation)
 };
@@ -232,7 +239,7 @@ template <class real, int NJ, int TK> struct Dims {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
   static constexpr int NOBS = Cfg<NJ, TK>::STAND ? 5 + 3 * NU : (Cfg<NJ, TK>::STEP ? 5 + 2 * NU + 10 : 5 + 2 * NU + 8);
   // real-valued state record per env (HBM, env-major so one warp streams its env's record contiguously)
-  static constexpr int NPARAM = Cfg<NJ, TK>::PERENV ? NL + 3 * NL + 6 + 2 * NU + 3 + 12 : (Cfg<NJ, TK>::STEP ? 4 * NSLAB + 5 : 0);
+  static constexpr int NPARAM = Cfg<NJ, TK>::PERENV ? NL + 3 * NL + 6 + 2 * NU + 3 + 12 : (Cfg<NJ, TK>::SLABS ? 4 * NSLAB + 5 : 0);
   static constexpr int NSTATE_R = NQ + NV + NV + 5 * NU + 3 + 1 + NPARAM;
 };
 
@@ -269,12 +276,12 @@ template <class A, class B> struct Select<false, A, B> { typedef B type; };
 
 template <class real, int NJ, int TK>
 struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
-                                 typename Select<Cfg<NJ, TK>::STEP, PersistStep<real, NJ, TK>, Persist<real, NJ, TK>>::type>::type {
+                                 typename Select<Cfg<NJ, TK>::SLABS, PersistStep<real, NJ, TK>, Persist<real, NJ, TK>>::type>::type {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ, NA = 6 + NJ;
   static constexpr int CPF = Cfg<NJ, TK>::CPF, NCON = 2 * CPF, NEDGE = 4 * NCON, NPTS = Cfg<NJ, TK>::NPTS;
   static constexpr int NOBS = Dims<real, NJ, TK>::NOBS;
   static constexpr int NFL = Cfg<NJ, TK>::FLOSS ? NU : 1;
-  static constexpr int NSL = Cfg<NJ, TK>::STEP ? NSLAB : 1, NST = Cfg<NJ, TK>::STEP ? 1 : 0;
+  static constexpr int NSL = Cfg<NJ, TK>::SLABS ? NSLAB : 1, NST = Cfg<NJ, TK>::SLABS ? 1 : 0;
   int phase, mode, traj_len, ep_len, have_prev, status;
   uint32_t rng_ctr, env_id;
   // ---- control-step scratch
@@ -310,7 +317,9 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
     };
     struct {
       real T[2][NA][6], Af[2][6][6], Ff[2][6], ya[2][6], ys[2][6];
-      real Pm[NCON][3][6];   // contact-frame point map: rows = unit wrenches of (n, t1, t2) applied at the contact
+      // contact-frame point map: rows = unit wrenches of (n, t1, t2) applied at the contact.  The slab variants (16 slots)
+      // rebuild the entries from cpos instead (pmap3): dropping the table is what lets 14 fp64 environments share an SM
+      real Pm[Cfg<NJ, TK>::SLABS ? 1 : NCON][3][6];
       real cF[NCON][3], cW[NCON][5];
       real ejv[NEDGE], ljv[NU], fjv[NFL];
     };
@@ -378,6 +387,13 @@ template <class real> LHW_DEV void contact_u(const real* p, const real* y, real*
   u[0] = y[5] + y[0] * p[1] - y[1] * p[0];
   u[1] = y[4] + y[2] * p[0] - y[0] * p[2];
   u[2] = -(y[3] + y[1] * p[2] - y[2] * p[1]);
+}
+// column a of the contact point map P(p) (see P9): the three entries P[0][a], P[1][a], P[2][a] for a contact at p
+template <class real> LHW_DEV void pmap3(const real* cp, int a, real& p0, real& p1, real& p2) {
+  const real px = cp[0], py = cp[1], pz = cp[2];
+  p0 = a == 0 ? py : a == 1 ? -px : a == 5 ? (real)1 : (real)0;
+  p1 = a == 0 ? -pz : a == 2 ? px : a == 4 ? (real)1 : (real)0;
+  p2 = a == 1 ? -pz : a == 2 ? py : a == 3 ? (real)-1 : (real)0;
 }
 // power-law impedance sigmoid of MuJoCo's getimpedance()
 template <class real> LHW_DEVNI real impedance(const real* solimp, real dist) {
@@ -847,7 +863,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
   // the box centre and whose top face is within vertical reach; a superset of the slabs any corner / sole edge can touch,
   // so the narrow phases below give exactly what an exhaustive test over the 20 slabs gives
   unsigned near_slabs[2] = {0u, 0u};
-  if constexpr (Cfg<NJ, TK>::STEP) {
+  if constexpr (Cfg<NJ, TK>::SLABS) {
 #pragma unroll
     for (int f = 0; f < 2; f++) {
       near_slabs[f] = warp_ballot([&](int l) -> bool {
@@ -897,7 +913,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       const real ld = R[6] * ((i & 1) ? m.foot_size[f][0] : -m.foot_size[f][0]) +
                       R[7] * ((i & 2) ? m.foot_size[f][1] : -m.foot_size[f][1]) +
                       R[8] * ((i & 4) ? m.foot_size[f][2] : -m.foot_size[f][2]);
-      if constexpr (Cfg<NJ, TK>::STEP) {
+      if constexpr (Cfg<NJ, TK>::SLABS) {
         // stepping stones: the corner rests on the HIGHEST surface under it (floor plane, or the top face of a slab whose
         // footprint contains it); surfaces at exactly that height each contribute an identical contact -> multiplicity
         real v[3], cr[3];
@@ -908,7 +924,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
 #pragma unroll
         for (int x = 0; x < 3; x++) { cr[x] += w.xr[lk][x]; w.cwp[l - 16][x] = cr[x]; }
         const real ax = w.o[0] + cr[0], ay = w.o[1] + cr[1], az = w.o[2] + cr[2];
-        const real floor_z = w.mode == ST_FORWARD ? (real)-2 : (real)0;   // stepping_task.py:332-334
+        const real floor_z = (Cfg<NJ, TK>::STEP && w.mode == ST_FORWARD) ? (real)-2 : (real)0;   // stepping_task.py:332-334
         real best = 0;
         int have = 0, mult = 0;
         if (az - floor_z < 0) { best = floor_z; have = 1; mult = 1; }
@@ -953,13 +969,13 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       int cnt = 0;
 #pragma unroll
       for (int i = 0; i < NPTS; i++)
-        if (cnt < (Cfg<NJ, TK>::STEP ? NCORNER : CPF) && !(w.ccd[f * NPTS + i] > 0)) { w.cslot[f * CPF + cnt] = i; cnt++; }
+        if (cnt < (Cfg<NJ, TK>::SLABS ? NCORNER : CPF) && !(w.ccd[f * NPTS + i] > 0)) { w.cslot[f * CPF + cnt] = i; cnt++; }
       w.ncon[f] = cnt;
       w.ncorner[f] = cnt;
     }
   }
   LHW_SYNC();
-  if constexpr (Cfg<NJ, TK>::STEP) {
+  if constexpr (Cfg<NJ, TK>::SLABS) {
     // ---------------- P7x sole-edge x slab-boundary crossings: the remaining vertices of (sole rectangle) clipped against
     // (slab footprint) -- the face-face manifold of a box-box test with the slab's top face as reference face.  One lane
     // per (slab, sole edge): Liang-Barsky clip of the edge against the footprint; an entry / exit parameter strictly
@@ -1034,7 +1050,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     if (l < NCON && l - (l / CPF) * CPF < w.ncon[l / CPF]) {
       const int f = l / CPF, lk = (f + 1) * NJ;
       real cd, mult = 1;
-      if constexpr (Cfg<NJ, TK>::STEP) {
+      if constexpr (Cfg<NJ, TK>::SLABS) {
         if (l - f * CPF < w.ncorner[f]) {
           const int i = w.cslot[l];
           cd = w.ccd[f * NPTS + i];
@@ -1064,7 +1080,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       const real imp = impedance(m.solimp, cd);
       const real Rn = m_max((real)1e-15, (1 - imp) / imp * (m.foot_invw[f] * (1 + m.mu * m.mu)));
       w.cD[l] = mult / (2 * m.mu_reg * m.mu_reg * Rn);
-      w.cKid[l] = m.K * imp * cd;
+      w.cKid[l] = m.Kc * imp * cd;
     }
   }
   LHW_SYNC();
@@ -1077,7 +1093,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         real u[3];
         contact_u(w.cpos[s], w.V[(f + 1) * NJ], u);
         const real vel = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)];
-        w.earef[ed] = -m.B * vel - w.cKid[s];
+        w.earef[ed] = -m.Bc * vel - w.cKid[s];
       }
     }
     if (l < NV) {
@@ -1141,6 +1157,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
   LHW_SYNC();
   LHW_BLOCK_SYNC(block_sync & 2);  // optional second rendez-vous of the block's warps, before the solver
   // ---------------- P9 Newton start: contact point maps Pm, then Ma = M a, ya = S_foot a and the row residuals
+  if constexpr (!Cfg<NJ, TK>::SLABS)
   LHW_LANES(l) {
     if (l < NCON && l - (l / CPF) * CPF < w.ncon[l / CPF]) {
       // rows of P: spatial wrench [p x e ; e] of a unit force along e = n (+z), t1 (+y), t2 (-x) applied at p
@@ -1183,9 +1200,15 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         const int f = l / 6, a = l - f * 6;
         real acc = 0;
         for (int k = 0; k < w.ncon[f]; k++) {
-          const real* P = &w.Pm[f * CPF + k][0][0];
           const real* cf = w.cF[f * CPF + k];
-          acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
+          if constexpr (Cfg<NJ, TK>::SLABS) {
+            real p0, p1, p2;
+            pmap3(w.cpos[f * CPF + k], a, p0, p1, p2);
+            acc += p0 * cf[0] + p1 * cf[1] + p2 * cf[2];
+          } else {
+            const real* P = &w.Pm[f * CPF + k][0][0];
+            acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
+          }
         }
         w.Ff[f][a] = acc;
       }
@@ -1221,9 +1244,15 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         real acc = 0;
         for (int k = 0; k < w.ncon[f]; k++) {
           const int s = f * CPF + k;
-          const real* P = &w.Pm[s][0][0];
           const real* W = w.cW[s];
-          const real a0 = P[a], a1 = P[6 + a], a2 = P[12 + a], b0 = P[b], b1 = P[6 + b], b2 = P[12 + b];
+          real a0, a1, a2, b0, b1, b2;
+          if constexpr (Cfg<NJ, TK>::SLABS) {
+            pmap3(w.cpos[s], a, a0, a1, a2);
+            pmap3(w.cpos[s], b, b0, b1, b2);
+          } else {
+            const real* P = &w.Pm[s][0][0];
+            a0 = P[a]; a1 = P[6 + a]; a2 = P[12 + a]; b0 = P[b]; b1 = P[6 + b]; b2 = P[12 + b];
+          }
           acc += a0 * (W[0] * b0 + W[1] * b1 + W[2] * b2) + a1 * (W[1] * b0 + W[3] * b1) + a2 * (W[2] * b0 + W[4] * b2);
         }
         w.Af[f][a][b] = acc;
@@ -1476,7 +1505,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
 
 // cos / sin of the slab yaws (stepping stones), once per launch and after every task reset
 template <class real, int NJ, int TK> LHW_DEV void slab_frames(Work<real, NJ, TK>& w) {
-  if constexpr (Cfg<NJ, TK>::STEP) {
+  if constexpr (Cfg<NJ, TK>::SLABS) {
     LHW_LANES(l) {
       if (l < NSLAB) m_sincos(w.seq[l][3], &w.slab_cs[l][1], &w.slab_cs[l][0]);
     }
@@ -1756,6 +1785,28 @@ LHW_DEV void step_task_reset(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m
   for (int i = 0; i < 8; i++) w.goal[i] = 0;
 }
 
+// terrain extension: re-pose the 20 terraces with the ranges of WalkingTask's manip_hfield hook (tasks/walking_task.py:
+// 172-179).  Draws at the current event counter: stream 5 lanes 0..2 = x, y ~ U(-xy, xy), z offset ~ U(zlo, zhi); terrace k's
+// bump ~ U(0, bump) = stream 60 + k/4 lane k%4.  Terrace k: centre (px + (k - 4) pitch, py), yaw 0, top at bump_k + zoff.
+template <class real, int NJ, int TK>
+LHW_DEV void terrain_repose(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, uint32_t seed) {
+  if constexpr (Cfg<NJ, TK>::TERRAIN) {
+    uint32_t u[4], v[4];
+    philox(seed, w.env_id, w.rng_ctr, 5, u);
+    const real px = -m.terrain_xy + 2 * m.terrain_xy * u01<real>(u[0]), py = -m.terrain_xy + 2 * m.terrain_xy * u01<real>(u[1]);
+    const real zo = m.terrain_zlo + (m.terrain_zhi - m.terrain_zlo) * u01<real>(u[2]);
+#pragma unroll 1
+    for (int k = 0; k < NSLAB; k++) {
+      if ((k & 3) == 0) philox(seed, w.env_id, w.rng_ctr, 60 + (k >> 2), v);
+      w.seq[k][0] = px + (k - 4) * m.terrain_pitch;
+      w.seq[k][1] = py;
+      w.seq[k][2] = m.terrain_bump * u01<real>(v[k & 3]) + zo;
+      w.seq[k][3] = 0;
+    }
+    w.tk[0] = (real)NSLAB;
+  }
+}
+
 // MujocoEnv.reset + BaseHumanoidEnv.reset_model + WalkingTask.reset
 template <class real, int NJ, int TK> LHW_DEV void env_reset(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, uint32_t seed) {
   constexpr int NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ;
@@ -1767,7 +1818,7 @@ template <class real, int NJ, int TK> LHW_DEV void env_reset(Work<real, NJ, TK>&
     if constexpr (Cfg<NJ, TK>::PERENV) {
       if (l >= 20) (&w.xfrc[0][0])[l - 20] = 0;   // mj_resetData clears xfrc_applied
     }
-    if constexpr (Cfg<NJ, TK>::STEP) {
+    if constexpr (Cfg<NJ, TK>::SLABS) {
       // the settling steps below still see the PREVIOUS episode's slabs and floor (the reference edits the model in
       // task.reset, after them); a freshly built env has its boxes below the floor (gen_xml.py:149)
       if (l < NSLAB && w.tk[0] == 0) w.seq[l][2] = -1;
@@ -1825,6 +1876,9 @@ template <class real, int NJ, int TK> LHW_DEV void env_reset(Work<real, NJ, TK>&
         w.mode = c < (real)0.6 ? STANDING : (c < (real)0.8 ? INPLACE : FORWARD);
         sample_ref<real, NJ, TK>(w, seed, 4);
         w.phase = randint(u[1], m.period);
+        if constexpr (Cfg<NJ, TK>::TERRAIN) {
+          if (w.tk[0] == 0) terrain_repose<real, NJ, TK>(w, m, seed);   // first reset of a new env: the terrain's initial pose
+        }
       }
       w.traj_len = 0; w.ep_len = 0; w.ep_rew = 0; w.status = 0;
     }
@@ -1919,9 +1973,13 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
         else if (w.mode == INPLACE) w.mode = FORWARD;
         sample_ref<real, NJ, TK>(w, seed, 2);
       }
+      if constexpr (Cfg<NJ, TK>::TERRAIN) {
+        if (randint(u[2], m.terrain_interval) == 0 && w.mode != STANDING) terrain_repose<real, NJ, TK>(w, m, seed);
+      }
     }
   }
   LHW_SYNC();
+  if constexpr (Cfg<NJ, TK>::TERRAIN) slab_frames<real, NJ, TK>(w);
   // WalkingTask.calc_reward (tasks/walking_task.py:85-147, tasks/rewards.py), lane = term
   if constexpr (Cfg<NJ, TK>::STEP) {
     // SteppingTask.calc_reward (tasks/stepping_task.py:66-121), lane = term (6 terms, the rest 0)

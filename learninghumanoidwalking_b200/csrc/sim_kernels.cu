@@ -28,6 +28,8 @@ __constant__ Model<double, NJ_H1, 0> c_model_d5;
 __constant__ Model<float, NJ_H1, 0> c_model_f5;
 __constant__ Model<double, NJ_JVRC, 1> c_model_ds;
 __constant__ Model<float, NJ_JVRC, 1> c_model_fs;
+__constant__ Model<double, NJ_JVRC, 2> c_model_dt;
+__constant__ Model<float, NJ_JVRC, 2> c_model_ft;
 
 template <class real, int NJ, int TK> __device__ __forceinline__ const Model<real, NJ, TK>& cmodel();
 template <> __device__ __forceinline__ const Model<double, NJ_JVRC, 0>& cmodel<double, NJ_JVRC, 0>() { return c_model_d; }
@@ -36,6 +38,8 @@ template <> __device__ __forceinline__ const Model<double, NJ_H1, 0>& cmodel<dou
 template <> __device__ __forceinline__ const Model<float, NJ_H1, 0>& cmodel<float, NJ_H1, 0>() { return c_model_f5; }
 template <> __device__ __forceinline__ const Model<double, NJ_JVRC, 1>& cmodel<double, NJ_JVRC, 1>() { return c_model_ds; }
 template <> __device__ __forceinline__ const Model<float, NJ_JVRC, 1>& cmodel<float, NJ_JVRC, 1>() { return c_model_fs; }
+template <> __device__ __forceinline__ const Model<double, NJ_JVRC, 2>& cmodel<double, NJ_JVRC, 2>() { return c_model_dt; }
+template <> __device__ __forceinline__ const Model<float, NJ_JVRC, 2>& cmodel<float, NJ_JVRC, 2>() { return c_model_ft; }
 
 }  // namespace
 // tell sim_core.h's out-of-line routines where the model really lives (constant bank -> LDC with immediate offsets)
@@ -50,13 +54,15 @@ LHW_MODEL_HOME(double, NJ_H1, 0, c_model_d5)
 LHW_MODEL_HOME(float, NJ_H1, 0, c_model_f5)
 LHW_MODEL_HOME(double, NJ_JVRC, 1, c_model_ds)
 LHW_MODEL_HOME(float, NJ_JVRC, 1, c_model_fs)
+LHW_MODEL_HOME(double, NJ_JVRC, 2, c_model_dt)
+LHW_MODEL_HOME(float, NJ_JVRC, 2, c_model_ft)
 #undef LHW_MODEL_HOME
 }  // namespace lhw
 namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-const void* g_owner[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // which sim's model sits in each constant-memory slot
+const void* g_owner[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // which sim's model sits in each constant-memory slot
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -160,6 +166,8 @@ struct lhw_sim {
   Model<float, NJ_H1, 0> mf5;
   Model<double, NJ_JVRC, 1> mds;
   Model<float, NJ_JVRC, 1> mfs;
+  Model<double, NJ_JVRC, 2> mdt;
+  Model<float, NJ_JVRC, 2> mft;
   void* d_plans = nullptr;   // SteppingTask footstep plans in HBM ([MAXPLAN][PLAN_STRIDE] reals of the sim's precision)
   size_t work_bytes;
   int state_reals, obs_dim;
@@ -168,9 +176,12 @@ struct lhw_sim {
 namespace {
 
 int upload_model(lhw_sim* s, cudaStream_t st) {
-  const int slot = (s->tk ? 4 : (s->nj == NJ_JVRC ? 0 : 2)) + (s->precision == 64 ? 0 : 1);
+  const int slot = (s->tk == 2 ? 6 : s->tk ? 4 : (s->nj == NJ_JVRC ? 0 : 2)) + (s->precision == 64 ? 0 : 1);
   if (g_owner[slot] == s) return 0;
-  if (s->tk) {
+  if (s->tk == 2) {
+    if (s->precision == 64) CUDA_OK(cudaMemcpyToSymbolAsync(c_model_dt, &s->mdt, sizeof(s->mdt), 0, cudaMemcpyHostToDevice, st));
+    else CUDA_OK(cudaMemcpyToSymbolAsync(c_model_ft, &s->mft, sizeof(s->mft), 0, cudaMemcpyHostToDevice, st));
+  } else if (s->tk) {
     if (s->precision == 64) CUDA_OK(cudaMemcpyToSymbolAsync(c_model_ds, &s->mds, sizeof(s->mds), 0, cudaMemcpyHostToDevice, st));
     else CUDA_OK(cudaMemcpyToSymbolAsync(c_model_fs, &s->mfs, sizeof(s->mfs), 0, cudaMemcpyHostToDevice, st));
   } else if (s->nj == NJ_JVRC) {
@@ -234,7 +245,8 @@ int launch_step(lhw_sim* s, void* state_r, int32_t* state_i, int n_envs, uint32_
 
 // (precision, NJ) dispatch
 #define LHW_DISPATCH(s, FN, ...)                                                                                          \
-  ((s)->tk ? ((s)->precision == 64 ? FN<double, NJ_JVRC, 1>(__VA_ARGS__) : FN<float, NJ_JVRC, 1>(__VA_ARGS__))               \
+  ((s)->tk == 2 ? ((s)->precision == 64 ? FN<double, NJ_JVRC, 2>(__VA_ARGS__) : FN<float, NJ_JVRC, 2>(__VA_ARGS__))          \
+   : (s)->tk ? ((s)->precision == 64 ? FN<double, NJ_JVRC, 1>(__VA_ARGS__) : FN<float, NJ_JVRC, 1>(__VA_ARGS__))             \
    : (s)->nj == NJ_JVRC ? ((s)->precision == 64 ? FN<double, NJ_JVRC, 0>(__VA_ARGS__) : FN<float, NJ_JVRC, 0>(__VA_ARGS__)) \
                         : ((s)->precision == 64 ? FN<double, NJ_H1, 0>(__VA_ARGS__) : FN<float, NJ_H1, 0>(__VA_ARGS__)))
 
@@ -255,7 +267,7 @@ int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision,
   if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device");
   CUDA_OK(cudaSetDevice(device));
   const int var = (int)flat[0], nj = var % 100, tk = var / 100;
-  if (var != NJ_JVRC && var != NJ_H1 && var != 100 + NJ_JVRC)
+  if (var != NJ_JVRC && var != NJ_H1 && var != 100 + NJ_JVRC && var != 200 + NJ_JVRC)
     return fail(-4, "unsupported robot / task variant " + std::to_string(var));
   lhw_sim* s = new lhw_sim();
   s->precision = precision;
@@ -263,7 +275,10 @@ int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision,
   s->nj = nj;
   s->tk = tk;
   int rc = 0;
-  if (tk) {
+  if (tk == 2) {
+    rc = fill_model(s->mdt, flat, n_flat);
+    if (rc == 0) rc = fill_model(s->mft, flat, n_flat);
+  } else if (tk) {
     // SteppingTask: the footstep plans go to HBM in the sim's precision; the model constants hold the device pointer
     const size_t words = (size_t)MAXPLAN * PLAN_STRIDE;
     std::vector<double> pd(words, 0.0);
@@ -288,7 +303,7 @@ int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision,
   }
   const char* env_wpb = getenv("LHW_WARPS_PER_BLOCK");
   // measured on B200 (profiles/): lock-step blocks of 8 (fp64, 2 blocks/SM) / 14 (fp32, 2 blocks/SM) warps
-  s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? (tk ? 6 : nj == NJ_JVRC ? 8 : 7) : (tk ? 12 : 14));
+  s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? (nj == NJ_JVRC && !tk ? 8 : 7) : (tk ? 13 : 14));
   const char* env_sync = getenv("LHW_BLOCK_SYNC_MODE");
   s->sync_mode = env_sync ? atoi(env_sync) : 1;
   if (s->warps_per_block < 1) s->warps_per_block = 1;
@@ -300,7 +315,7 @@ int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision,
 
 int lhw_sim_destroy(lhw_sim* s) {
   if (!s) return 0;
-  for (int k = 0; k < 6; k++)
+  for (int k = 0; k < 8; k++)
     if (g_owner[k] == s) g_owner[k] = nullptr;
   if (s->d_plans) cudaFree(s->d_plans);
   delete s;
@@ -309,7 +324,7 @@ int lhw_sim_destroy(lhw_sim* s) {
 
 int lhw_sim_set_step_height(lhw_sim* s, double h) {
   if (!s) return fail(-1, "null argument");
-  if (!s->tk) return 0;   // only the SteppingTask has a curriculum
+  if (s->tk != 1) return 0;   // only the SteppingTask has a curriculum
   s->mds.step_height = h;
   s->mfs.step_height = (float)h;
   for (int k = 4; k < 6; k++)

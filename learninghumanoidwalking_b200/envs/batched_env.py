@@ -100,6 +100,8 @@ class BatchedHumanoidEnv:
         base_mir_obs = [-0.1, 1, -2, 3, -4, 11, -12, -13, 14, -15, 16, 5, -6, -7, 8, -9, 10,
                         23, -24, -25, 26, -27, 28, 17, -18, -19, 20, -21, 22]
         append_obs = [len(base_mir_obs) + i for i in range(8)]
+        if model not in ("jvrc_walk", "jvrc_walk_terrain", "jvrc_step"):
+            raise ValueError(f"unknown model {model!r}")
         if model == "jvrc_step":
             # envs/jvrc/jvrc_step.py:41-63: clock(2) + goal steps x(2) y(2) z(2) theta(2)
             self.reward_names = STEP_REWARD_NAMES

@@ -34,7 +34,8 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
     assert {mj["rfoot_link"], mj["lfoot_link"]} == {nj, 2 * nj}
     stand = mj["name"] == "h1"          # Unitree H1 + StandingTask (csrc/sim_core.h Cfg<5, 0>)
     step = mj["name"] == "jvrc_step"    # JVRC-1 + SteppingTask (csrc/sim_core.h Cfg<6, 1>)
-    b: list[float] = [nj + (100 if step else 0)]
+    terrain = mj.get("terrain")         # JVRC-1 + WalkingTask on terraces (extension; csrc/sim_core.h Cfg<6, 2>)
+    b: list[float] = [nj + (100 if step else 200 if terrain else 0)]
     for lk in links:
         b += lk["pos"]
         b += list(np.asarray(lk["rot"], dtype=float).reshape(-1))
@@ -117,6 +118,9 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
     else:
         b += [0.0] * 23
     b.append(float(pd_gain_randomization))     # RobotBase(pdrand_k) (robots/robot_base.py:5,43-47); 0 = off
+    if terrain:
+        b += terrain["strip_half"] + [terrain["side_tol"], terrain["pitch"], terrain["bump"], terrain["z_lo"], terrain["z_hi"],
+                                      terrain["xy"], terrain["interval"]] + terrain["contact_solref"]
     if step:
         st = mj["stepping"]
         for site in mj["foot_sites"]:

@@ -121,6 +121,11 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
     else:
         b += [0.0] * 29
     b.append(float(pdrand_k))
+    tr = mj.get("terrain")
+    b.append(1 if tr else 0)
+    if tr:
+        b += tr["strip_half"] + [tr["side_tol"], tr["pitch"], tr["bump"], tr["z_lo"], tr["z_hi"], tr["xy"], tr["interval"]]
+        b += tr["contact_solref"]
     if mj["name"] == "jvrc_step":
         st = mj["stepping"]
         for site in mj["foot_sites"]:

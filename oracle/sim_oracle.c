@@ -173,6 +173,13 @@ int orc_model_from_flat(orc_model* m, const double* b, int n) {
   for (int k = 0; k < 9; k++) m->rest_Io[k] = RD();
   for (int k = 0; k < 3; k++) m->torso_com[k] = RD();
   m->pdrand_k = RD();
+  m->terrain = (int)RD();
+  if (m->terrain) {
+    for (int k = 0; k < 3; k++) m->slab_half[k] = RD();
+    m->side_tol = RD(); m->terrain_pitch = RD(); m->terrain_bump = RD(); m->terrain_zlo = RD(); m->terrain_zhi = RD();
+    m->terrain_xy = RD(); m->terrain_interval = (int)RD();
+    for (int k = 0; k < 2; k++) m->contact_solref[k] = RD();
+  }
   if (m->task == ORC_TASK_STEP) {
     for (int f = 0; f < 2; f++)
       for (int k = 0; k < 3; k++) m->foot_site[f][k] = RD();
@@ -509,9 +516,9 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
     double off[3], ctr[3];
     matvec3(k->xmat[lk], m->geom_pos[g], off);
     for (int x = 0; x < 3; x++) ctr[x] = k->xpos[lk][x] + off[x];
-    if (m->task == ORC_TASK_STEP) {
+    if (m->task == ORC_TASK_STEP || m->terrain) {
       /* floor body moved to z = -2 in FORWARD mode (stepping_task.py:332-334) */
-      double floor_z = env->mode == ORC_STEP_FORWARD ? -2.0 : 0.0;
+      double floor_z = (m->task == ORC_TASK_STEP && env->mode == ORC_STEP_FORWARD) ? -2.0 : 0.0;
       double cw[8][3];
       int cnt = 0;
       for (int i = 0; i < 8; i++) {
@@ -609,6 +616,11 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
   }
   /* pyramidal rows: frame (n,t1,t2) = (+z, +y, -x) from mju_makeFrame on n = (0,0,1) */
   double mu = m->mu * sqrt(1.0 / fmax(MINVAL, m->impratio));
+  if (m->contact_solref[0] > 0) {   /* compliant-terrain extension: the contact pairs carry their own solref */
+    double tc = m->contact_solref[0] < 2 * m->timestep ? 2 * m->timestep : m->contact_solref[0], zc = m->contact_solref[1];
+    K = 1.0 / fmax(MINVAL, dmax * dmax * tc * tc * zc * zc);
+    B = 2.0 / fmax(MINVAL, dmax * tc);
+  }
   for (int ci = 0; ci < e->ncon; ci++) {
     int lk = m->geom_link[e->con_geom[ci]];
     double jp[3 * NV];
@@ -1214,6 +1226,7 @@ static void calc_reward_step(const orc_model* m, const orc_env* e, double* t) {
   t[6] = t[7] = t[8] = t[9] = 0;
 }
 
+static void terrain_repose(const orc_model* m, orc_env* e);
 static void task_reset(const orc_model* m, orc_env* e) {
   uint32_t u[4];
   if (m->task == ORC_TASK_STEP) { task_reset_step(m, e); return; }
@@ -1223,6 +1236,25 @@ static void task_reset(const orc_model* m, orc_env* e) {
   e->mode = c < 0.6 ? ORC_STANDING : (c < 0.8 ? ORC_INPLACE : ORC_FORWARD);
   sample_ref(e, 4);
   e->phase = randint(u[1], m->period);
+  if (m->terrain && e->seq_len == 0) terrain_repose(m, e);   /* first reset of a new env: the terrain's initial pose */
+}
+
+/* terrain extension: re-pose the 20 terraces.  Draws at the current event counter: stream 5 lanes 0..2 = x, y offset
+ * U(-xy, xy) and z offset U(zlo, zhi) (the ranges of the reference's manip_hfield hook, walking_task.py:172-179); terrace k's
+ * bump height U(0, bump) = stream 60 + k/4 lane k%4.  Terrace k: centre (px + (k - 4) pitch, py), top at bump_k + zoff. */
+static void terrain_repose(const orc_model* m, orc_env* e) {
+  uint32_t u[4], w[4];
+  orc_philox(e->seed, e->env_id, e->rng_ctr, 5, u);
+  double px = -m->terrain_xy + 2 * m->terrain_xy * u01(u[0]), py = -m->terrain_xy + 2 * m->terrain_xy * u01(u[1]);
+  double zo = m->terrain_zlo + (m->terrain_zhi - m->terrain_zlo) * u01(u[2]);
+  for (int k = 0; k < ORC_NSLAB; k++) {
+    if ((k & 3) == 0) orc_philox(e->seed, e->env_id, e->rng_ctr, 60 + (k >> 2), w);
+    e->seq[k][0] = px + (k - 4) * m->terrain_pitch;
+    e->seq[k][1] = py;
+    e->seq[k][2] = m->terrain_bump * u01(w[k & 3]) + zo;
+    e->seq[k][3] = 0;
+  }
+  e->seq_len = ORC_NSLAB;
 }
 
 static void task_step(const orc_model* m, orc_env* e) {
@@ -1243,6 +1275,7 @@ static void task_step(const orc_model* m, orc_env* e) {
     else if (e->mode == ORC_INPLACE) e->mode = ORC_FORWARD;
     sample_ref(e, 2);
   }
+  if (m->terrain && randint(u[2], m->terrain_interval) == 0 && e->mode != ORC_STANDING) terrain_repose(m, e);
 }
 
 /* WalkingTask.calc_reward (tasks/walking_task.py:85-147); t[10] in the dict's insertion order */

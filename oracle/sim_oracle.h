@@ -111,6 +111,12 @@ typedef struct {
   int delay_frames, nplan;
   int plan_len[ORC_MAXPLAN];
   double plans[ORC_MAXPLAN][ORC_MAXPLANLEN][3];  /* utils/footstep_plans.txt: x, y, theta */
+  /* uneven / compliant terrain EXTENSION (BASELINE configs[4]; the reference only has the unused WalkingTask(manip_hfield)
+   * hook, tasks/walking_task.py:172-179, and no height-field asset — SURVEY F7): WalkingTask on 20 terraces (the slabs of
+   * the stepping stones, yaw 0, tiling x), re-posed like the hook re-poses its "hfield" geom; softer contact solref */
+  int terrain, terrain_interval;
+  double terrain_pitch, terrain_bump, terrain_zlo, terrain_zhi, terrain_xy;
+  double contact_solref[2];         /* solref of the foot-ground contacts ({0,0}: the model default) */
 } orc_model;
 
 typedef struct {

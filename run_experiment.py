@@ -24,7 +24,7 @@ from pathlib import Path
 
 import torch
 
-ENVS = ("jvrc_walk", "jvrc_step", "h1")
+ENVS = ("jvrc_walk", "jvrc_step", "h1", "jvrc_walk_terrain")   # the last one is an extension (BASELINE configs[4])
 
 
 def print_system_info(args, training=True):

@@ -67,13 +67,14 @@ struct Handle { int var; void* p; };
   do {                                                                                                \
     if ((h)->var == 6) { if ((prec) == 64) { CALL(double, 6, 0); } else { CALL(float, 6, 0); } }      \
     else if ((h)->var == 106) { if ((prec) == 64) { CALL(double, 6, 1); } else { CALL(float, 6, 1); } } \
+    else if ((h)->var == 206) { if ((prec) == 64) { CALL(double, 6, 2); } else { CALL(float, 6, 2); } } \
     else { if ((prec) == 64) { CALL(double, 5, 0); } else { CALL(float, 5, 0); } }                    \
   } while (0)
 
 extern "C" {
 void* emu_create(const double* flat, int n, int precision) {
   const int var = (int)flat[0];
-  if (var != 6 && var != 5 && var != 106) return nullptr;
+  if (var != 6 && var != 5 && var != 106 && var != 206) return nullptr;
   Handle tmp{var, nullptr};
   void* p = nullptr;
 #define CALL(R, J, T) p = create<R, J, T>(flat, n)
@@ -84,11 +85,11 @@ void* emu_create(const double* flat, int n, int precision) {
 }
 int emu_state_words(void* hv) {
   const int v = ((Handle*)hv)->var;
-  return v == 6 ? Dims<double, 6, 0>::NSTATE_R : v == 106 ? Dims<double, 6, 1>::NSTATE_R : Dims<double, 5, 0>::NSTATE_R;
+  return v == 6 ? Dims<double, 6, 0>::NSTATE_R : v == 106 ? Dims<double, 6, 1>::NSTATE_R : v == 206 ? Dims<double, 6, 2>::NSTATE_R : Dims<double, 5, 0>::NSTATE_R;
 }
 int emu_obs_dim(void* hv) {
   const int v = ((Handle*)hv)->var;
-  return v == 6 ? Dims<double, 6, 0>::NOBS : v == 106 ? Dims<double, 6, 1>::NOBS : Dims<double, 5, 0>::NOBS;
+  return v == 6 ? Dims<double, 6, 0>::NOBS : v == 106 ? Dims<double, 6, 1>::NOBS : v == 206 ? Dims<double, 6, 2>::NOBS : Dims<double, 5, 0>::NOBS;
 }
 int emu_work_bytes(void* hv, int precision) {
   Handle* h = (Handle*)hv;
@@ -118,6 +119,7 @@ void emu_substep64(void* hv, double* sr, int32_t* si, const double* ctrl, int ns
   Handle* h = (Handle*)hv;
   if (h->var == 6) substeps64<6, 0>(h->p, sr, si, ctrl, nsteps);
   else if (h->var == 106) substeps64<6, 1>(h->p, sr, si, ctrl, nsteps);
+  else if (h->var == 206) substeps64<6, 2>(h->p, sr, si, ctrl, nsteps);
   else substeps64<5, 0>(h->p, sr, si, ctrl, nsteps);
 }
 void emu_set_step_height(void* hv, int precision, double h_) {

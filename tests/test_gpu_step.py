@@ -143,3 +143,38 @@ def test_ppo_trains_on_the_stepping_environment_with_mirror_loss(tmp_path):
         assert ppo.env.robot.iteration_count == 1      # rl/workers/rollout_worker.py:95
         ppo.env.close()
     assert torch.equal(finals[0], finals[1])     # same seed, bit-identical weights
+
+
+def test_terrain_extension_fp64_closed_loop_against_oracle():
+    """BASELINE configs[4] (uneven / compliant terrain; an extension): CUDA path vs oracle, with re-poses."""
+    from learninghumanoidwalking_b200.envs import BatchedHumanoidEnv
+    from oracle.oracle import Oracle
+    o, n = Oracle("jvrc_walk_terrain", tolerance=1e-14), 32
+    env = BatchedHumanoidEnv(n, model="jvrc_walk_terrain", precision=64, seed=9, first_env_id=3, max_traj_len=80, tolerance=1e-14)
+    assert env.obs_dim == 37 and env.act_dim == 12 and env.state_r.shape[1] == 204
+    envs = o.make_envs(n, seed=9, first_id=3)
+    assert _rel(env.reset().cpu().numpy(), o.batch_reset(envs, n)) < 1e-9
+    rng = np.random.RandomState(0)
+    n_end, worst, reposed = 0, 0.0, 0
+    prev = env.state_r[:, 119:199].clone()
+    for k in range(300):
+        a = rng.normal(size=(n, 12)) * 0.2
+        o_obs, o_tobs, o_terms, o_rew, o_done, o_end = o.batch_step(envs, n, a, max_traj_len=80)
+        g_obs, g_rew, g_done, g_end = env.step(torch.as_tensor(a, device="cuda", dtype=env.dtype))
+        assert (g_done.cpu().numpy() == o_done).all() and (g_end.cpu().numpy() == o_end).all(), f"step {k}"
+        worst = max(worst, _rel(g_obs.cpu().numpy(), o_obs), _rel(g_rew.cpu().numpy(), o_rew),
+                    _rel(env.rew_terms.cpu().numpy(), o_terms))
+        n_end += int(o_end.sum())
+        cur = env.state_r[:, 119:199]
+        reposed += int(((cur - prev).abs().amax(dim=1) > 0).sum().item())
+        prev = cur.clone()
+    assert n_end > 40 and reposed >= 5 and worst < 1e-7, (n_end, reposed, worst)
+    seq_o = np.stack([o.field(envs, i, "seq") for i in range(n)])
+    assert np.abs(env.state_r[:, 119:199].cpu().numpy() - seq_o).max() == 0
+    env.close()
+    env32 = BatchedHumanoidEnv(256, model="jvrc_walk_terrain", precision=32, seed=1)
+    env32.reset()
+    for _ in range(20):
+        obs, rew, done, ended = env32.step(torch.randn(256, 12, device="cuda") * 0.2)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and (env32.status_flags() == 0).all()
+    env32.close()

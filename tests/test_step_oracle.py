@@ -183,3 +183,60 @@ def test_height_curriculum_follows_iteration_count():
         fwd = np.array([int(o.field(envs, i, "mode")[0]) == 4 for i in range(24)])
         assert fwd.any() and np.abs(np.abs(zs[fwd]).max(axis=1) - h * 15).max() < 1e-12 + h * 1.01   # 16 or 15 raised steps
         assert (zs[~fwd][zs[~fwd] > -1] == 0).all()
+
+
+# ---------------------------------------------------------------- uneven / compliant terrain extension (BASELINE configs[4])
+def test_terrain_extension_kernel_source_matches_oracle_and_reduces_to_flat_walk():
+    """jvrc_walk_terrain = WalkingTask on 20 terraces re-posed with the ranges of the reference's (unused) manip_hfield hook
+    (tasks/walking_task.py:172-179) + softer foot-ground contacts.  Not a parity target of the reference; checked:
+    (i) kernel source == oracle in closed loop incl. re-poses, (ii) with the terraces sunk below the floor and the default
+    contact solref the environment IS jvrc_walk (to roundoff: the slab code path sums the contact point differently), (iii) compliance: the softer contact sinks deeper at rest."""
+    import copy
+    from oracle import oracle as orc
+    mj = load_model("jvrc_walk_terrain")
+    assert mj["terrain"]["interval"] == 200 and mj["terrain"]["z_lo"] == -0.035 and mj["terrain"]["z_hi"] == -0.015
+    o = Oracle("jvrc_walk_terrain", tolerance=1e-14)
+    N = 8
+    e = Emu(pack_model(mj, tolerance=1e-14), 64, N, seed=5, first_id=10)
+    assert e.nobs == 37 and e.nr == 204
+    envs = o.make_envs(N, seed=5, first_id=10)
+    assert np.abs(o.batch_reset(envs, N) - e.reset()).max() < 1e-12
+    rng = np.random.RandomState(2)
+    n_end, reposed = 0, 0
+    prev = np.stack([o.field(envs, i, "seq") for i in range(N)])
+    assert (prev.reshape(N, 20, 4)[:, :, 2].max(axis=1) > 0).any()          # some terraces stick out of the floor
+    for _ in range(220):
+        a = rng.normal(size=(N, 12)) * 0.2
+        oo, to, tt, rr, dd, ee = o.batch_step(envs, N, a, max_traj_len=80)
+        eo, et, etm, er, ed, een, _, _ = e.step(a, max_traj_len=80)
+        assert (dd == ed).all() and (ee == een).all()
+        assert np.abs(oo - eo).max() < 1e-9 and np.abs(rr - er).max() < 1e-10 and np.abs(tt - etm).max() < 1e-10
+        n_end += int(ee.sum())
+        cur = np.stack([o.field(envs, i, "seq") for i in range(N)])
+        reposed += int((np.abs(cur - prev).max(axis=1) > 0).sum())
+        prev = cur
+    assert n_end >= 10 and reposed >= 2
+    assert np.abs(e.sr[:, 119:199] - prev).max() == 0
+
+    # (ii) terraces out of reach + default solref == plain jvrc_walk
+    flat = copy.deepcopy(mj)
+    flat["terrain"].update(bump=0.0, z_lo=-0.3, z_hi=-0.3, contact_solref=[0.02, 1.0])
+    ow = Oracle("jvrc_walk", tolerance=1e-14)
+    ef = Emu(pack_model(flat, tolerance=1e-14), 64, 2, seed=9)
+    ew = Emu(pack_model(load_model("jvrc_walk"), tolerance=1e-14), 64, 2, seed=9)
+    assert np.array_equal(ef.reset(), ew.reset())
+    for _ in range(30):
+        a = rng.normal(size=(2, 12)) * 0.2
+        rf, rw = ef.step(a), ew.step(a)
+        assert np.abs(rf[0] - rw[0]).max() < 1e-10 and np.abs(rf[3] - rw[3]).max() < 1e-11 and (rf[5] == rw[5]).all()
+    # (iii) compliance: PD-held stance on the floor, default vs soft contact
+    z = {}
+    for name, sr in (("default", [0.02, 1.0]), ("soft", [0.04, 1.0])):
+        m2 = copy.deepcopy(flat)
+        m2["terrain"]["contact_solref"] = sr
+        em = Emu(pack_model(m2, tolerance=1e-14), 64, 1, seed=1)
+        em.reset()
+        for _ in range(12):
+            em.step(np.zeros((1, 12)), autoreset=0)
+        z[name] = em.qpos[0, 2]
+    assert 1e-4 < z["default"] - z["soft"] < 5e-3

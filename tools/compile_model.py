@@ -532,6 +532,15 @@ def main():
         st["self_collision"] = m["self_collision"]
     json.dump(st, open(os.path.join(args.out, "jvrc_step.json"), "w"), indent=1)
     print("wrote jvrc_step.json plans", len(st["stepping"]["plans"]), "delay_frames", st["stepping"]["delay_frames"])
+    # uneven / compliant terrain EXTENSION (BASELINE configs[4]; SURVEY F7: the reference has only the unused
+    # WalkingTask(manip_hfield) hook and no height-field asset).  jvrc_walk on 20 terraces re-posed with the hook's ranges
+    # (tasks/walking_task.py:172-179: x, y ~ U(-0.5, 0.5), z ~ U(-0.035, -0.015), w.p. 1/200 per control step outside
+    # STANDING); terrace tops bump ~ U(0, 0.05) above that offset; softer foot-ground contacts (solref timeconst 0.04 s)
+    tm = dict(m)
+    tm["name"] = "jvrc_walk_terrain"
+    tm["terrain"] = dict(strip_half=[0.15, 1.0, 0.1], side_tol=0.02, pitch=0.3, bump=0.05, z_lo=-0.035, z_hi=-0.015, xy=0.5,
+                         interval=200, contact_solref=[0.04, 1.0])
+    json.dump(tm, open(os.path.join(args.out, "jvrc_walk_terrain.json"), "w"), indent=1)
     h = compile_h1()
     json.dump(h, open(os.path.join(args.out, "h1.json"), "w"), indent=1)
     print("wrote h1.json mass", h["total_mass"], "links", len(h["links"]), "meaninertia", h["meaninertia"])
