@@ -206,6 +206,7 @@ class PPO:
         act_mirr = getattr(env, "mirror_action", None) if self.mirror_coeff else None
         train_start = time.time()
         log = []
+        writer = self._tensorboard_writer() if self.rank == 0 else None
         for itr in range(n_itr):
             if verbose and self.rank == 0:
                 print(f"********** Iteration {itr} ************")
@@ -255,9 +256,32 @@ class PPO:
                 eta = round((n_itr - itr) * total_time / (itr + 1))
                 print(f"Total time elapsed: {total_time:.2f}s. Total steps: {self.total_steps} "
                       f"(fps={fps:.2f}. iter-avg={total_time / (itr + 1):.2f}s. ETA={datetime.timedelta(seconds=eta)})")
+            if writer is not None:   # the reference's TensorBoard tags (rl/utils/logger.py:71-115)
+                for tag, v in (("Loss/actor", stats[0]), ("Loss/critic", stats[2]), ("Loss/mirror", stats[4]),
+                               ("Loss/imitation", stats[5]), ("Train/mean_reward", ep_rew), ("Train/mean_episode_length", ep_len),
+                               ("Train/mean_noise_std", float(torch.as_tensor(self.policy.stds).mean())), ("Time/fps", fps),
+                               ("Time/sample_time", sample_time), ("Time/optimize_time", optimize_time),
+                               ("Time/total_elapsed", total_time)):
+                    writer.add_scalar(tag, v, itr)
             if self.rank == 0 and (itr == 0 or (itr + 1) % self.eval_freq == 0):
                 self.save(itr)
+        if writer is not None:
+            writer.flush()
+            writer.close()
         return log
+
+    def _tensorboard_writer(self):
+        """TrainingLogger (rl/utils/logger.py:24-45): a SummaryWriter on the run directory; None if tensorboard is absent
+        or LHW_TENSORBOARD=0."""
+        import os
+        if os.environ.get("LHW_TENSORBOARD", "1") == "0":
+            return None
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+        except Exception:
+            return None
+        self.save_path.mkdir(parents=True, exist_ok=True)
+        return SummaryWriter(str(self.save_path), flush_secs=10)
 
     def save(self, itr):
         """actor_{itr}.pt / critic_{itr}.pt as whole pickled modules (rl/utils/checkpointer.py:51-83)."""

@@ -17,7 +17,16 @@ def test_train_then_eval(tmp_path, env_name, obs_dim, act_dim, capsys):
     runs = list(tmp_path.iterdir())
     assert len(runs) == 1 and runs[0].name.endswith("_" + env_name)
     names = sorted(p.name for p in runs[0].iterdir())
-    assert names == ["actor_0.pt", "actor_1.pt", "critic_0.pt", "critic_1.pt", "experiment.pkl"]
+    assert [n for n in names if not n.startswith("events.out.tfevents")] == ["actor_0.pt", "actor_1.pt", "critic_0.pt",
+                                                                              "critic_1.pt", "experiment.pkl"]
+    ev = [n for n in names if n.startswith("events.out.tfevents")]
+    assert len(ev) == 1                      # TensorBoard log with the reference's tags (rl/utils/logger.py:71-115)
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    acc = EventAccumulator(str(runs[0]))
+    acc.Reload()
+    assert {"Loss/actor", "Loss/critic", "Loss/mirror", "Loss/imitation", "Train/mean_reward", "Train/mean_episode_length",
+            "Train/mean_noise_std", "Time/fps", "Time/sample_time", "Time/optimize_time", "Time/total_elapsed"} <= set(
+        acc.Tags()["scalars"])
     args = pickle.load(open(runs[0] / "experiment.pkl", "rb"))
     assert args.env == env_name and args.num_procs == 64
     actor = torch.load(runs[0] / "actor_1.pt", weights_only=False)
