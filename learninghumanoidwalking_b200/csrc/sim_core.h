@@ -297,10 +297,10 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   // ---- contacts (slot = foot*4 + k), expressed through the foot's spatial motion: J_contact = P(p) S_foot
   int ncon[2];
   // stepping stones: cos/sin of the slab yaws, per-corner multiplicity, crossing-slot distances
-  real slab_cs[NSL][2], cmul[NST * 16 + 1], xcd[NST * NCON + 1];
+  real slab_cs[NSL][2], cmul[NST ? 16 : 1], xcd[NST ? NCON : 1];
   int ncorner[2];
   real site[2][3], rquat[4], goal[8];   // lagged site_xpos / root xquat ; _goal_steps_{x,y,z,theta}
-  real cpos[NCON][3], cD[NCON], cKid[NCON];
+  real cpos[NCON][Cfg<NJ, TK>::SLABS ? 5 : 3], cD[NCON], cKid[NCON];   // SLABS: (px, py, pz, 1, 0), see pmap_sel
   real earef[NEDGE], ejar[NEDGE];
   int lside[NU];
   real laref[NU], lD[NU], ljar[NU];
@@ -313,7 +313,7 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
       real A[NL][6], F[NL][6];
       real ccd[2 * NPTS];   // signed distance of each candidate point (box corner / sphere), > 0: not a candidate
       int cslot[NCON];
-      real cwp[NST * 16 + 1][3];   // STEP: foot-box corners relative to o
+      real cwp[NST ? 16 : 1][3];   // SLABS: foot-box corners relative to o
     };
     struct {
       real T[2][NA][6], Af[2][6][6], Ff[2][6], ya[2][6], ys[2][6];
@@ -324,10 +324,11 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
       real ejv[NEDGE], ljv[NU], fjv[NFL];
     };
     real capE[MAXCAP][6];  // self-collision capsule end points; lives where T was (T is dead after the Hessian build)
+    real obs[NOBS];        // the observation is packed at env level, when both scratch groups are dead
   };
   // ---- what mj_step leaves behind (pre-integration state of the last substep)
   real root_vlin[3], foot_vel[2][3], grf[2], cz_min, qacc_lag[3];
-  real rew[NREW], obs[NOBS];
+  real rew[NREW];
   int iters_total, selfcol;
 };
 
@@ -388,12 +389,12 @@ template <class real> LHW_DEV void contact_u(const real* p, const real* y, real*
   u[1] = y[4] + y[2] * p[0] - y[0] * p[2];
   u[2] = -(y[3] + y[1] * p[2] - y[2] * p[1]);
 }
-// column a of the contact point map P(p) (see P9): the three entries P[0][a], P[1][a], P[2][a] for a contact at p
-template <class real> LHW_DEV void pmap3(const real* cp, int a, real& p0, real& p1, real& p2) {
-  const real px = cp[0], py = cp[1], pz = cp[2];
-  p0 = a == 0 ? py : a == 1 ? -px : a == 5 ? (real)1 : (real)0;
-  p1 = a == 0 ? -pz : a == 2 ? px : a == 4 ? (real)1 : (real)0;
-  p2 = a == 1 ? -pz : a == 2 ? py : a == 3 ? (real)-1 : (real)0;
+// column a of the contact point map P(p) (see P9) without the table: with the contact record cp = (px, py, pz, 1, 0) the
+// entries are P[r][a] = sgn[r] * cp[idx[r]]; idx / sgn depend on the lane's column only and are hoisted out of the contact loops
+template <class real> LHW_DEV void pmap_sel(int a, int idx[3], real sgn[3]) {
+  idx[0] = a == 0 ? 1 : a == 1 ? 0 : a == 5 ? 3 : 4;  sgn[0] = a == 1 ? (real)-1 : (real)1;
+  idx[1] = a == 0 ? 2 : a == 2 ? 0 : a == 4 ? 3 : 4;  sgn[1] = a == 0 ? (real)-1 : (real)1;
+  idx[2] = a == 1 ? 2 : a == 2 ? 1 : a == 3 ? 3 : 4;  sgn[2] = (a == 1 || a == 3) ? (real)-1 : (real)1;
 }
 // power-law impedance sigmoid of MuJoCo's getimpedance()
 template <class real> LHW_DEVNI real impedance(const real* solimp, real dist) {
@@ -1060,6 +1061,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         } else {
           cd = w.xcd[l];   // crossing slot: position already written by P7x
         }
+        w.cpos[l][3] = 1; w.cpos[l][4] = 0;
       } else {
       const int i = w.cslot[l];
       cd = w.ccd[f * NPTS + i];
@@ -1199,12 +1201,14 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       if (l < 12) {
         const int f = l / 6, a = l - f * 6;
         real acc = 0;
+        int ia[3];
+        real sa[3];
+        pmap_sel(a, ia, sa);
         for (int k = 0; k < w.ncon[f]; k++) {
           const real* cf = w.cF[f * CPF + k];
           if constexpr (Cfg<NJ, TK>::SLABS) {
-            real p0, p1, p2;
-            pmap3(w.cpos[f * CPF + k], a, p0, p1, p2);
-            acc += p0 * cf[0] + p1 * cf[1] + p2 * cf[2];
+            const real* cp = w.cpos[f * CPF + k];
+            acc += sa[0] * cp[ia[0]] * cf[0] + sa[1] * cp[ia[1]] * cf[1] + sa[2] * cp[ia[2]] * cf[2];
           } else {
             const real* P = &w.Pm[f * CPF + k][0][0];
             acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
@@ -1242,13 +1246,18 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         while (t > a) { t -= a + 1; a++; }
         const int b = t;
         real acc = 0;
+        int ia[3], ib[3];
+        real sa[3], sb[3];
+        pmap_sel(a, ia, sa);
+        pmap_sel(b, ib, sb);
         for (int k = 0; k < w.ncon[f]; k++) {
           const int s = f * CPF + k;
           const real* W = w.cW[s];
           real a0, a1, a2, b0, b1, b2;
           if constexpr (Cfg<NJ, TK>::SLABS) {
-            pmap3(w.cpos[s], a, a0, a1, a2);
-            pmap3(w.cpos[s], b, b0, b1, b2);
+            const real* cp = w.cpos[s];
+            a0 = sa[0] * cp[ia[0]]; a1 = sa[1] * cp[ia[1]]; a2 = sa[2] * cp[ia[2]];
+            b0 = sb[0] * cp[ib[0]]; b1 = sb[1] * cp[ib[1]]; b2 = sb[2] * cp[ib[2]];
           } else {
             const real* P = &w.Pm[s][0][0];
             a0 = P[a]; a1 = P[6 + a]; a2 = P[12 + a]; b0 = P[b]; b1 = P[6 + b]; b2 = P[12 + b];

@@ -303,7 +303,7 @@ int lhw_sim_create(lhw_sim** out, const double* flat, int n_flat, int precision,
   }
   const char* env_wpb = getenv("LHW_WARPS_PER_BLOCK");
   // measured on B200 (profiles/): lock-step blocks of 8 (fp64, 2 blocks/SM) / 14 (fp32, 2 blocks/SM) warps
-  s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? (nj == NJ_JVRC && !tk ? 8 : 7) : (tk ? 13 : 14));
+  s->warps_per_block = env_wpb ? atoi(env_wpb) : (precision == 64 ? (nj == NJ_JVRC && !tk ? 8 : 7) : 14);
   const char* env_sync = getenv("LHW_BLOCK_SYNC_MODE");
   s->sync_mode = env_sync ? atoi(env_sync) : 1;
   if (s->warps_per_block < 1) s->warps_per_block = 1;
