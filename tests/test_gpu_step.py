@@ -170,7 +170,7 @@ def test_terrain_extension_fp64_closed_loop_against_oracle():
         prev = cur.clone()
     assert n_end > 40 and reposed >= 5 and worst < 1e-7, (n_end, reposed, worst)
     seq_o = np.stack([o.field(envs, i, "seq") for i in range(n)])
-    assert np.abs(env.state_r[:, 119:199].cpu().numpy() - seq_o).max() == 0
+    assert np.abs(env.state_r[:, 119:199].cpu().numpy() - seq_o).max() < 1e-12      # same terrain poses (FMA-level differences)
     env.close()
     env32 = BatchedHumanoidEnv(256, model="jvrc_walk_terrain", precision=32, seed=1)
     env32.reset()
