@@ -391,10 +391,25 @@ template <class real> LHW_DEV void contact_u(const real* p, const real* y, real*
 }
 // column a of the contact point map P(p) (see P9) without the table: with the contact record cp = (px, py, pz, 1, 0) the
 // entries are P[r][a] = sgn[r] * cp[idx[r]]; idx / sgn depend on the lane's column only and are hoisted out of the contact loops
-template <class real> LHW_DEV void pmap_sel(int a, int idx[3], real sgn[3]) {
-  idx[0] = a == 0 ? 1 : a == 1 ? 0 : a == 5 ? 3 : 4;  sgn[0] = a == 1 ? (real)-1 : (real)1;
-  idx[1] = a == 0 ? 2 : a == 2 ? 0 : a == 4 ? 3 : 4;  sgn[1] = a == 0 ? (real)-1 : (real)1;
-  idx[2] = a == 1 ? 2 : a == 2 ? 1 : a == 3 ? 3 : 4;  sgn[2] = (a == 1 || a == 3) ? (real)-1 : (real)1;
+// sgn[r] is a sign-bit mask (0 or 0x80000000) applied with one integer XOR (sflip), not a multiply on the fp64 pipe
+LHW_DEV void pmap_sel(int a, int idx[3], unsigned sgn[3]) {
+  idx[0] = a == 0 ? 1 : a == 1 ? 0 : a == 5 ? 3 : 4;  sgn[0] = a == 1 ? 0x80000000u : 0u;
+  idx[1] = a == 0 ? 2 : a == 2 ? 0 : a == 4 ? 3 : 4;  sgn[1] = a == 0 ? 0x80000000u : 0u;
+  idx[2] = a == 1 ? 2 : a == 2 ? 1 : a == 3 ? 3 : 4;  sgn[2] = (a == 1 || a == 3) ? 0x80000000u : 0u;
+}
+LHW_DEV double sflip(double x, unsigned m) {
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+  return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x));
+#else
+  return m ? -x : x;
+#endif
+}
+LHW_DEV float sflip(float x, unsigned m) {
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+  return __int_as_float(__float_as_int(x) ^ (int)m);
+#else
+  return m ? -x : x;
+#endif
 }
 // power-law impedance sigmoid of MuJoCo's getimpedance()
 template <class real> LHW_DEVNI real impedance(const real* solimp, real dist) {
@@ -1202,13 +1217,13 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         const int f = l / 6, a = l - f * 6;
         real acc = 0;
         int ia[3];
-        real sa[3];
+        unsigned sa[3];
         pmap_sel(a, ia, sa);
         for (int k = 0; k < w.ncon[f]; k++) {
           const real* cf = w.cF[f * CPF + k];
           if constexpr (Cfg<NJ, TK>::SLABS) {
             const real* cp = w.cpos[f * CPF + k];
-            acc += sa[0] * cp[ia[0]] * cf[0] + sa[1] * cp[ia[1]] * cf[1] + sa[2] * cp[ia[2]] * cf[2];
+            acc += sflip(cp[ia[0]], sa[0]) * cf[0] + sflip(cp[ia[1]], sa[1]) * cf[1] + sflip(cp[ia[2]], sa[2]) * cf[2];
           } else {
             const real* P = &w.Pm[f * CPF + k][0][0];
             acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
@@ -1247,7 +1262,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         const int b = t;
         real acc = 0;
         int ia[3], ib[3];
-        real sa[3], sb[3];
+        unsigned sa[3], sb[3];
         pmap_sel(a, ia, sa);
         pmap_sel(b, ib, sb);
         for (int k = 0; k < w.ncon[f]; k++) {
@@ -1256,8 +1271,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           real a0, a1, a2, b0, b1, b2;
           if constexpr (Cfg<NJ, TK>::SLABS) {
             const real* cp = w.cpos[s];
-            a0 = sa[0] * cp[ia[0]]; a1 = sa[1] * cp[ia[1]]; a2 = sa[2] * cp[ia[2]];
-            b0 = sb[0] * cp[ib[0]]; b1 = sb[1] * cp[ib[1]]; b2 = sb[2] * cp[ib[2]];
+            a0 = sflip(cp[ia[0]], sa[0]); a1 = sflip(cp[ia[1]], sa[1]); a2 = sflip(cp[ia[2]], sa[2]);
+            b0 = sflip(cp[ib[0]], sb[0]); b1 = sflip(cp[ib[1]], sb[1]); b2 = sflip(cp[ib[2]], sb[2]);
           } else {
             const real* P = &w.Pm[s][0][0];
             a0 = P[a]; a1 = P[6 + a]; a2 = P[12 + a]; b0 = P[b]; b1 = P[6 + b]; b2 = P[12 + b];

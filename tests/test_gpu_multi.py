@@ -26,6 +26,12 @@ def test_two_rank_nccl_ppo_replicas_stay_identical():
             assert f"fused_exchange={fused == '1'}" in out.stdout
             if one_step == "1":
                 sums[fused] = [float(x) for x in re.search(r"wsum=(\S+) wabs=(\S+)", out.stdout).groups()]
+    # BASELINE configs[2]: the stepping-stone task sharded over the ranks, fused NVLink exchange
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, LHW_FUSED_EXCHANGE="1", LHW_CHECK_ONE_STEP="0", LHW_MODEL="jvrc_step"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "model=jvrc_step" in out.stdout and "identical_weights=True" in out.stdout
+    assert "ranks_simulate_different_envs=True" in out.stdout
     # after ONE optimiser step on identical data the fused NVLink kernel and the NCCL + clip/Adam baseline agree to rounding
     # (2 ranks: a + b is order-free; only the norm reductions differ in the last bits)
     assert abs(sums["1"][0] - sums["0"][0]) < 1e-4 and abs(sums["1"][1] - sums["0"][1]) < 1e-4, sums

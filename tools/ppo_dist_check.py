@@ -22,7 +22,8 @@ def main():
     from learninghumanoidwalking_b200.rl.symmetric import SymmetricEnv
     n_global = int(os.environ.get("LHW_ENVS", "256"))
     first, n = env_shard(rank, world, n_global)
-    base = lambda: BatchedHumanoidEnv(n, precision=32, seed=0, first_env_id=first, device=local)
+    model = os.environ.get("LHW_MODEL", "jvrc_walk")     # jvrc_step: BASELINE configs[2] (env-sharded, gradient exchange)
+    base = lambda: BatchedHumanoidEnv(n, model=model, precision=32, seed=0, first_env_id=first, device=local)
     probe = base()
     r = probe.robot
     probe.close()
@@ -51,7 +52,7 @@ def main():
     differ = world == 1 or not torch.equal(obs_all[0], obs_all[-1])
     if rank == 0:
         fused = ppo._comm is not None
-        print(f"DIST_CHECK world={world} envs/rank={n} fused_exchange={fused} identical_weights={same} "
+        print(f"DIST_CHECK model={model} world={world} envs/rank={n} fused_exchange={fused} identical_weights={same} "
               f"ranks_simulate_different_envs={differ} critic_loss={log[-1]['critic_loss']:.4f} fps={log[-1]['fps']:.0f} "
               f"wsum={flat.double().sum().item():.10f} wabs={flat.double().abs().sum().item():.10f}")
     dist.destroy_process_group()
