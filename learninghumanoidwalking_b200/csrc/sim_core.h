@@ -8,8 +8,11 @@
 //   mujoco.mj_step (external)
 //   tasks/walking_task.py:85-205, tasks/rewards.py:9-174, tasks/observations.py:12-72,
 //   envs/jvrc/jvrc_base.py:133-145, envs/jvrc/jvrc_walk.py:65-67
-//   H1 standing variant (Cfg<5>): envs/h1/h1_base.py:91-117, tasks/standing_task.py:49-131,
+//   H1 standing variant (Cfg<5,0>): envs/h1/h1_base.py:91-117, tasks/standing_task.py:49-131,
 //   envs/common/domain_randomization.py:10-56, base_humanoid_env.py:228-233, :247-338
+//   JVRC stepping variant (Cfg<6,1>): envs/jvrc/jvrc_step.py:41-76, tasks/stepping_task.py:52-334 (footstep sequences,
+//   stepping-stone slabs, target tracking, goal-step observation), utils/footstep_plans.txt
+//   terrain extension (Cfg<6,2>): WalkingTask on re-posed terraces, ranges of tasks/walking_task.py:172-179 (not a reference env)
 //
 // Execution model.  Every phase is a `LHW_LANES(l) { ... }` block: on the GPU each of the 32 lanes of the
 // warp runs the body once with its own lane id and `LHW_SYNC()` is __syncwarp(); all inter-lane traffic goes

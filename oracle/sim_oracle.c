@@ -14,6 +14,9 @@
  *   tasks/rewards.py:9-174                    reward terms
  *   envs/jvrc/jvrc_base.py:133-145, envs/jvrc/jvrc_walk.py:65-67, tasks/observations.py:12-72  obs
  *   mujoco.mj_step (external)                                  -> orc_mj_step
+ *   tasks/stepping_task.py:52-334, envs/jvrc/jvrc_step.py:41-76 (jvrc_step)          -> task_reset_step / task_step_step /
+ *       calc_reward_step / slab contacts in make_constraints (mjc_BoxBox is inside the un-vendored library: face-face case restated)
+ *   tasks/standing_task.py, envs/h1/*, envs/common/domain_randomization.py (h1)      -> calc_reward_stand / randomize_dynamics / ...
  */
 #include "sim_oracle.h"
 
