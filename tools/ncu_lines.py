@@ -49,8 +49,11 @@ for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
 
 # ---- coarse regions of sim_core.h, derived from anchor text in the header itself (no hand-kept line numbers)
 import os
-ANCHORS = [("LHW_DEV float m_sqrt", "math wrappers (out of line)"), ("LHW_DEV real warp_sum", "warp_sum"), ("LHW_DEV void philox", "philox"),
+ANCHORS = [("LHW_DEV float m_sqrt", "math wrappers (out of line)"), ("LHW_DEV real warp_sum", "warp_sum"),
+           ("LHW_DEV unsigned warp_ballot", "ballot / bit helpers"), ("LHW_DEV void philox", "philox"),
            ("struct Model {", "struct definitions"), ("LHW_DEV void cross(", "vec helpers (cross/dot6/mv3/inert_mul/rsqrt/contact_u)"),
+           ("LHW_DEV void pmap_sel(", "pmap_sel / sflip"), ("// stepping stones, broad phase", "slab broad phase"),
+           ("// ---------------- P7x ", "P7x slab-edge crossings"), ("LHW_DEV void slab_frames(", "env level"),
            ("LHW_DEVNI real impedance(", "impedance"), ("LHW_DEV real seg_seg_dist2(", "seg_seg_dist2"),
            ("LHW_DEVNI void arrow_factor_solve(", "arrow_factor_solve"), ("LHW_DEV real arrow_row_dot(", "arrow_row_dot"),
            ("LHW_DEVNI void constraint_images(", "constraint_images"), ("LHW_DEV real floss_force(", "floss_force"),
