@@ -193,7 +193,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on the process's stdout (fd 1) when NCCL_DEBUG=VERSION is set in the environment;
+        # stdout carries exactly ONE JSON line, so fd 1 points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     n = args.envs
     env = BatchedHumanoidEnv(n, model=wl["model"], precision=args.precision, seed=args.seed, first_env_id=rank * n,
                              device=local_rank)
