@@ -13,7 +13,8 @@ std_dev 0.223), synthetic, generated up front.
           observation / reward / done read back to pinned host memory (D2H every step).
   roofline  the step kernel: algorithmic HBM bytes per env-step x envs / CUDA-event time of
           the launches, against the measured HBM peak (MEASURED_PEAKS.json).  The kernel is ALU/latency bound;
-          the honest secondary bound is reported beside it.
+          the honest secondary bound is reported beside it as roofline.issue (warp-instruction issue rate, instruction
+          count per env-step from the committed ncu capture); roofline.traffic = DRAM bytes of that capture.
   cpu_baseline / --impl reference   the CPU restatement (oracle/, "port": the reference's own MuJoCo path is
           not installable here) on the box's host cores, same workload, bounded sample.
 """
@@ -34,6 +35,12 @@ sys.path.insert(0, ROOT)
 METRIC = "env-steps/sec jvrc_walk"
 UNIT = "env-steps/s"
 SIGMA = 0.223
+# per-launch numbers of the committed ncu captures (profiles/r01_step_kernel_*.md; 4096 envs, the bench's action distribution):
+# (DRAM bytes read + written, warp instructions executed).  Under ncu the state record is L2 resident when the launch starts
+# (no flush between replays), so the DRAM traffic is BELOW the algorithmic bytes; nothing is re-read.
+NCU_PER_LAUNCH_4096 = {("jvrc_walk", 64): (4.708608e6 + 0.109824e6, 828537893), ("jvrc_walk", 32): (2.456576e6 + 0.022528e6, 818458105),
+                       ("h1", 64): (6.823168e6 + 0.372992e6, 919081053), ("jvrc_step", 64): (7.490816e6 + 0.552192e6, 1317958630),
+                       ("jvrc_walk_terrain", 64): (7.512576e6 + 0.578816e6, 1024153088)}
 ALG_BYTES = {32: 1220, 64: 2288}   # state read+write, action read, obs/reward/done write
 
 
@@ -312,6 +319,19 @@ def main():
         alg_bytes = ALG_BYTES[args.precision] if args.workload == "jvrc_walk" else \
             (2 * env.state_r.shape[1] + A + env.obs_dim + 2) * esz_ + 2 * 8 * 4 + 2 * 4
         achieved = n * alg_bytes / (kernel_ms * 1e-3) / 1e9
+        # secondary, honest bound: warp-instruction issue rate (instructions per env-step from the ncu capture of this
+        # workload / precision) against 148 SMs x 4 schedulers x 1 warp-instruction per clock at the sampled SM clock
+        cap = NCU_PER_LAUNCH_4096.get((args.workload, args.precision))
+        traffic, issue = None, None
+        if cap is not None:
+            traffic = cap[0] * n / 4096.0
+            inst_per_env_step = cap[1] / 4096.0
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            issue_peak = 148 * 4 * sm_mhz * 1e6
+            issue_ach = n * inst_per_env_step / (kernel_ms * 1e-3)
+            issue = {"bound": "warp-issue", "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
+                     "frac": issue_ach / issue_peak, "warp_inst_per_env_step": inst_per_env_step,
+                     "source": "smsp__inst_executed.sum of the committed ncu capture (profiles/)"}
         out = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
@@ -322,10 +342,13 @@ def main():
                "gpu_launches": int(launches),
                "clocks": clocks,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "peak_source": peak_src,
+                            "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_env_step": alg_bytes,
                             "note": "the step kernel is ALU/latency bound (25 substeps of O(nv^3) work per ~2 KB of state); "
-                                    "see DESIGN.md for the FP-issue bound reported beside this"}}
+                                    "traffic = dram bytes of one 4096-env launch in the committed ncu capture (state L2 resident "
+                                    "under ncu, hence below the algorithmic bytes), scaled to this batch; `issue` is the bound that "
+                                    "actually applies",
+                            "issue": issue}}
         out["extras"] = extras
         if not args.no_cpu_baseline and world == 1:
             ncores = effective_cpus()
