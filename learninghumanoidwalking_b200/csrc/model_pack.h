@@ -132,6 +132,7 @@ template <class real, int NJ, int TK> int fill_model(Model<real, NJ, TK>& m, con
       for (int k = 0; k < 3; k++) m.foot_site[f][k] = (real)rd();
     for (int k = 0; k < 3; k++) m.slab_half[k] = (real)rd();
     m.target_radius = (real)rd(); m.side_tol = (real)rd(); m.delay_frames = (int)rd(); m.step_height = (real)rd();
+    m.slab_contacts_are_floor = (int)rd();
     m.nplan = (int)rd();
     if (m.nplan < 1 || m.nplan > MAXPLAN || !plan_table) return -8;
     for (int i = 0; i < m.nplan; i++) {

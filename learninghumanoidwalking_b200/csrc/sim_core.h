@@ -225,6 +225,7 @@ template <class real, int NJ, int TK> struct Model {
   real terrain_pitch, terrain_bump, terrain_zlo, terrain_zhi, terrain_xy;
   int terrain_interval;
   int delay_frames, nplan;
+  int slab_contacts_are_floor;   // 0: reference behaviour (SURVEY C-2), foot-stone contacts invisible to GRF / contact z
   const real* plans;   // [nplan][PLAN_STRIDE] in global memory (host memory in the CPU emulation)
 };
 
@@ -332,7 +333,7 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   // ---- what mj_step leaves behind (pre-integration state of the last substep)
   real root_vlin[3], foot_vel[2][3], grf[2], cz_min, qacc_lag[3];
   real rew[NREW];
-  int iters_total, selfcol;
+  int iters_total, selfcol, nfloor;   // nfloor: contacts the task's floor-contact queries see (last substep)
 };
 
 // ---------------------------------------------------------------- small vector helpers
@@ -945,8 +946,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         const real ax = w.o[0] + cr[0], ay = w.o[1] + cr[1], az = w.o[2] + cr[2];
         const real floor_z = (Cfg<NJ, TK>::STEP && w.mode == ST_FORWARD) ? (real)-2 : (real)0;   // stepping_task.py:332-334
         real best = 0;
-        int have = 0, mult = 0;
-        if (az - floor_z < 0) { best = floor_z; have = 1; mult = 1; }
+        int have = 0, mult = 0, with_floor = 0;
+        if (az - floor_z < 0) { best = floor_z; have = 1; mult = 1; with_floor = 1; }
 #pragma unroll 1
         for (unsigned mk = near_slabs[f]; mk; mk &= mk - 1) {
           const int sidx = lowest_bit(mk);
@@ -959,11 +960,11 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           if (ix < 0 || iy < 0) continue;
           const real inset = ix < iy ? ix : iy;
           if (-d > m.side_tol && -d > inset) continue;
-          if (!have || sl[2] > best) { best = sl[2]; have = 1; mult = 1; }
+          if (!have || sl[2] > best) { best = sl[2]; have = 1; mult = 1; with_floor = 0; }
           else if (sl[2] == best) mult++;
         }
         w.ccd[l - 16] = (have && !(ld > 0)) ? az - best : (real)1;
-        w.cmul[l - 16] = (real)mult;
+        w.cmul[l - 16] = with_floor ? (real)mult : (real)-mult;   // sign: the floor plane is one of the `mult` supports
       } else {
       const real dist0 = w.o[2] + w.xr[lk][2] + R[6] * m.foot_pos[f][0] + R[7] * m.foot_pos[f][1] + R[8] * m.foot_pos[f][2];
       w.ccd[l - 16] = (dist0 + ld > 0 || ld > 0) ? (real)1 : dist0 + ld;
@@ -1073,11 +1074,14 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         if (l - f * CPF < w.ncorner[f]) {
           const int i = w.cslot[l];
           cd = w.ccd[f * NPTS + i];
-          mult = w.cmul[f * NPTS + i];
+          mult = m_abs(w.cmul[f * NPTS + i]);
           w.cpos[l][0] = w.cwp[f * 8 + i][0]; w.cpos[l][1] = w.cwp[f * 8 + i][1];
           w.cpos[l][2] = w.cwp[f * 8 + i][2] - (real)0.5 * cd;
+          // share of this slot's force that the task's floor-contact queries see (xcd is free for corner slots)
+          w.xcd[l] = (!Cfg<NJ, TK>::STEP || m.slab_contacts_are_floor) ? (real)1 : (w.cmul[f * NPTS + i] > 0 ? (real)1 / mult : (real)0);
         } else {
           cd = w.xcd[l];   // crossing slot: position already written by P7x
+          w.xcd[l] = (!Cfg<NJ, TK>::STEP || m.slab_contacts_are_floor) ? (real)1 : (real)0;
         }
         w.cpos[l][3] = 1; w.cpos[l][4] = 0;
       } else {
@@ -1421,20 +1425,28 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         }
         for (int k = 0; k < w.ncon[f]; k++) {
           const real* cf = w.cF[f * CPF + k];
-          g += m_sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]);  // norm of mj_contactForce, friction included
+          real nrm = m_sqrt(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]);  // norm of mj_contactForce, friction included
+          // get_*_floor_contacts (robot_interface.py:252-301) skips foot-on-stone contacts (the foot box is
+          // geom1 there): only the floor plane's share of a merged corner slot is visible to the task
+          if constexpr (Cfg<NJ, TK>::SLABS) nrm *= w.xcd[f * CPF + k];
+          g += nrm;
         }
         w.grf[f] = g;
       }
       if (l == 20) {
         real z = 0;
         bool first = true;
+        int nfl = 0;
         for (int s = 0; s < NCON; s++)
           if (s - (s / CPF) * CPF < w.ncon[s / CPF]) {
+            if constexpr (Cfg<NJ, TK>::SLABS) { if (!(w.xcd[s] > 0)) continue; }
             const real cz = w.o[2] + w.cpos[s][2];
             if (first || cz < z) z = cz;
             first = false;
+            nfl++;
           }
         w.cz_min = z;
+        w.nfloor = nfl;
       }
     }
     // rhs of the implicit-damping solve: qfrc_smooth + J' f = M a - grad
@@ -2030,7 +2042,7 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
           const real inner = ch * w.rquat[0] + sh * w.rquat[3];
           r = (real)0.050 * m_exp(-10 * (1 - inner * inner));
         } else if (l == 3) {
-          const real cz = (w.ncon[0] + w.ncon[1]) > 0 ? w.cz_min : (real)0;
+          const real cz = w.nfloor > 0 ? w.cz_min : (real)0;
           real herr = m_abs(w.o[2] - cz - m.goal_height);
           if (herr < (real)0.01) herr = 0;
           r = (real)0.050 * m_exp(-40 * herr * herr);
@@ -2106,7 +2118,7 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
         for (int x = 0; x < 3; x++) err += m_abs(w.qacc_lag[x]);
         r = (real)0.05 * m_exp((real)-0.25 * err);
       } else if (l == 3) {
-        const real cz = (w.ncon[0] + w.ncon[1]) > 0 ? w.cz_min : (real)0;
+        const real cz = w.nfloor > 0 ? w.cz_min : (real)0;
         real herr = m_abs(w.o[2] - cz - m.goal_height);
         if (herr < (real)0.01 + (real)0.05 * m_sqrt(vx * vx + vy * vy)) herr = 0;
         r = (real)0.05 * m_exp(-40 * herr * herr);

@@ -76,7 +76,8 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
         t = c["task"]
         period, table = phase_clock_table(t["swing_duration"], t["stance_duration"], 0.1, "grounded",
                                           1.0 / c["control_dt"], total_duration=t["total_duration"])
-        b += [mj["total_mass"], t["goal_height"], period]
+        # get_robot_mass() = mj_getTotalmass: in jvrc_step it also counts the 20 static boxes
+        b += [mj.get("stepping", {}).get("task_mass", mj["total_mass"]), t["goal_height"], period]
         b += list(table.reshape(-1))
     # self-collision capsule proxies (termination flag; tools/fit_collision_proxies.py)
     sc = mj.get("self_collision") if self_collision else None
@@ -126,7 +127,8 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
         for site in mj["foot_sites"]:
             b += site
         b += st["slab_half"]
-        b += [st["target_radius"], st["side_tol"], st["delay_frames"], curriculum_height(iteration_count)]
+        b += [st["target_radius"], st["side_tol"], st["delay_frames"], curriculum_height(iteration_count),
+              1 if st.get("slab_contacts_are_floor") else 0]
         b.append(len(st["plans"]))
         for plan in st["plans"]:
             b.append(len(plan))

@@ -80,7 +80,10 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
     b += [c["frame_skip"], c["action_smoothing"], mj["rfoot_link"], mj["lfoot_link"]]
     stand = mj["name"] == "h1"
     b += mj.get("head_in_root", [0.0, 0.0, 0.0])
-    b += [mj["total_mass"], c.get("task", {}).get("goal_height", 0.98), 0 if stand else clocks["period"]]
+    # the mass the task normalises ground reaction forces with: RobotInterface.get_robot_mass() = mj_getTotalmass, which in
+    # jvrc_step also counts the 20 static boxes
+    task_mass = mj.get("stepping", {}).get("task_mass", mj["total_mass"])
+    b += [task_mass, c.get("task", {}).get("goal_height", 0.98), 0 if stand else clocks["period"]]
     if not stand:
         for k in ("r_frc", "r_vel", "l_frc", "l_vel"):
             b += clocks[k]
@@ -131,7 +134,8 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
         for site in mj["foot_sites"]:
             b += site
         b += st["slab_half"]
-        b += [st["target_radius"], st["side_tol"], st["delay_frames"], curriculum_height(iteration_count)]
+        b += [st["target_radius"], st["side_tol"], st["delay_frames"], curriculum_height(iteration_count),
+              1 if st.get("slab_contacts_are_floor") else 0]
         b.append(len(st["plans"]))
         for plan in st["plans"]:
             b.append(len(plan))
@@ -150,11 +154,12 @@ class Oracle:
     """One compiled model + helpers to own N environments."""
 
     def __init__(self, name: str = "jvrc_walk", tolerance: float | None = None, solver: int = 0,
-                 iterations: int | None = None, pdrand_k: float = 0.0, iteration_count: float = float("inf")):
+                 iterations: int | None = None, pdrand_k: float = 0.0, iteration_count: float = float("inf"),
+                 model_dict: dict | None = None):
         self.lib = ctypes.CDLL(build())
         L = self.lib
         L.orc_energy.restype = ctypes.c_double
-        self.mj = load_model_json(name)
+        self.mj = model_dict if model_dict is not None else load_model_json(name)
         self.clocks = load_clocks()
         flat = pack_model(self.mj, self.clocks, tolerance, solver, iterations, pdrand_k=pdrand_k,
                           iteration_count=iteration_count)

@@ -188,6 +188,7 @@ int orc_model_from_flat(orc_model* m, const double* b, int n) {
       for (int k = 0; k < 3; k++) m->foot_site[f][k] = RD();
     for (int k = 0; k < 3; k++) m->slab_half[k] = RD();
     m->target_radius = RD(); m->side_tol = RD(); m->delay_frames = (int)RD(); m->step_height = RD();
+    m->slab_contacts_are_floor = (int)RD();
     m->nplan = (int)RD();
     if (m->nplan > ORC_MAXPLAN) return -8;
     for (int i = 0; i < m->nplan; i++) {
@@ -399,7 +400,7 @@ typedef struct {
   double pos[ORC_MAXROW], D[ORC_MAXROW], aref[ORC_MAXROW], R[ORC_MAXROW];
   int type[ORC_MAXROW];      /* 0: unilateral (limit / pyramid edge), 1: dof friction loss */
   double floss[ORC_MAXROW];
-  int con_row[ORC_MAXCON], con_geom[ORC_MAXCON];
+  int con_row[ORC_MAXCON], con_geom[ORC_MAXCON], con_slab[ORC_MAXCON];   /* con_slab: 1 = against a stepping stone, 0 = floor plane */
   double con_pos[ORC_MAXCON][3], con_dist[ORC_MAXCON];
 } efc_t;
 
@@ -509,6 +510,7 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
         double cd = c[2] - m->geom_radius[g];
         if (!(cd < 0)) continue;
         int ci = e->ncon++;
+        e->con_slab[ci] = 0;
         e->con_geom[ci] = g;
         e->con_dist[ci] = cd;
         e->con_pos[ci][0] = c[0]; e->con_pos[ci][1] = c[1];
@@ -548,6 +550,7 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
           if (e->ncon >= ORC_MAXCON) { ((orc_env*)env)->con_overflow++; continue; }
           double cd = cw[i][2] - h;
           int ci = e->ncon++;
+          e->con_slab[ci] = sidx >= 0;
           e->con_geom[ci] = g;
           e->con_dist[ci] = cd;
           e->con_pos[ci][0] = cw[i][0]; e->con_pos[ci][1] = cw[i][1];
@@ -588,6 +591,7 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
             if (e->ncon >= ORC_MAXCON) { ((orc_env*)env)->con_overflow++; continue; }
             ncross++;
             int ci = e->ncon++;
+            e->con_slab[ci] = 1;
             e->con_geom[ci] = g;
             e->con_dist[ci] = cd;
             e->con_pos[ci][0] = A[0] + t * (Bp[0] - A[0]);
@@ -609,6 +613,7 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
       if (dist0 + ldist > 0 || ldist > 0) continue;
       double cd = dist0 + ldist;
       int ci = e->ncon++;
+      e->con_slab[ci] = 0;
       e->con_geom[ci] = g;
       e->con_dist[ci] = cd;
       e->con_pos[ci][0] = corner[0] + ctr[0];
@@ -954,6 +959,13 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
     double fn = f[0] + f[1] + f[2] + f[3], f1 = m->mu * (f[0] - f[1]), f2 = m->mu * (f[2] - f[3]);
     double nrm = sqrt(fn * fn + f1 * f1 + f2 * f2); /* robot_interface.py:310-312 norm of mj_contactForce */
     int lk = m->geom_link[efc.con_geom[ci]];
+    /* RobotInterface.get_*_floor_contacts (envs/common/robot_interface.py:252-301) keeps a contact only if
+     * its geom1 is a non-robot geom and its geom2 the foot.  MuJoCo orders the geoms of a contact by type, then by id: plane <
+     * box, so the floor plane is geom1 of a foot contact, but a foot box (low id, robot tree first) precedes a stepping-stone
+     * box, so foot-on-stone contacts have the FOOT as geom1 and are skipped: in jvrc_step they carry load but are invisible
+     * to the task's GRF, contact_point_z and floor-collision checks.  slab_contacts_are_floor = 1 switches to the
+     * physically meant behaviour. */
+    if (m->task == ORC_TASK_STEP && efc.con_slab[ci] && !m->slab_contacts_are_floor) continue;
     if (lk == m->rfoot_link) { e->rfoot_grf += nrm; e->ncon_r++; }
     else if (lk == m->lfoot_link) { e->lfoot_grf += nrm; e->ncon_l++; }
     if (first || efc.con_pos[ci][2] < e->contact_z_min) e->contact_z_min = efc.con_pos[ci][2];

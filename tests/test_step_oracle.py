@@ -94,8 +94,12 @@ def _stand_on(o, envs, seq_rows, mode):
 def test_slab_contacts_equal_floor_contacts_and_stack_as_multiplicity(orc):
     """A slab whose top face is the plane z = 0 must act on a foot inside its footprint exactly like the floor; floor and
     k coplanar slabs together are k + 1 identical contacts per corner (MuJoCo would list them all), which stiffens the
-    support but leaves the static force balance sum(GRF) = m g intact."""
-    o = orc
+    support but leaves the static force balance sum(GRF) = m g intact.  (Run with slab_contacts_are_floor=True so that the
+    recorded GRF covers every contact; the reference's own floor-contact query is checked in the quirks test below.)"""
+    import copy
+    m2 = copy.deepcopy(load_model("jvrc_step"))
+    m2["stepping"]["slab_contacts_are_floor"] = True
+    o = Oracle("jvrc_step", tolerance=1e-14, model_dict=m2)
     mg = o.mj["total_mass"] * 9.81
     res = {}
     for name, rows, mode in (("floor", [], 1), ("slab", [[0.12, 0, 0, 0.05]], 4), ("floor+slab", [[0.12, 0, 0, 0.05]], 1),
@@ -116,6 +120,46 @@ def test_slab_contacts_equal_floor_contacts_and_stack_as_multiplicity(orc):
     for k in res:   # quasi-static (the PD-held stance sways slowly): sum of contact-force norms ~ m g in every layout
         assert 0.95 * mg < res[k][2] < 1.05 * mg, (k, res[k][2], mg)
     assert abs(res["floor+3"][2] - res["floor"][2]) < 0.01 * mg
+
+
+def test_reference_quirks_of_the_stepping_env_are_reproduced_and_switchable(orc):
+    """SURVEY Appendix C-2 / C-3.  (C-3) SteppingTask normalises foot forces with get_robot_mass() = mj_getTotalmass, which
+    also sums the 20 static 800 kg boxes: 16062.4 kg, not 62.4.  (C-2) get_*_floor_contacts drops contacts whose geom1 is a
+    robot geom, i.e. every foot-on-stone contact: the stones carry the robot but the task sees no GRF / contact height from
+    them.  `slab_contacts_are_floor` switches the second one off; kernel source and oracle agree in both settings."""
+    import copy
+    mj = load_model("jvrc_step")
+    assert mj["stepping"]["task_mass"] == pytest.approx(62.4 + 20 * 800.0) and mj["stepping"]["slab_contacts_are_floor"] is False
+    mg = mj["total_mass"] * 9.81
+    seen = {}
+    for flag in (False, True):
+        m2 = copy.deepcopy(mj)
+        m2["stepping"]["slab_contacts_are_floor"] = flag
+        o = Oracle("jvrc_step", tolerance=1e-14, model_dict=m2)
+        envs = o.make_envs(1)
+        kp, kd = np.array(mj["cfg"]["kp"]), np.array(mj["cfg"]["kd"])
+        nom = np.array(mj["cfg"]["nominal_qpos"])[7:]
+        for mode in (4, 1):   # FORWARD: stones only (floor at -2); STANDING: floor + one coplanar stone
+            _stand_on(o, envs, [[0.12, 0, 0, 0.0]], mode)
+            for _ in range(300):
+                ctrl = kp * (nom - o.field(envs, 0, "qpos")[7:]) - kd * o.field(envs, 0, "qvel")[6:]
+                o.mj_step(envs, 0, ctrl)
+            seen[(flag, mode)] = (float(o.field(envs, 0, "rfoot_grf")[0] + o.field(envs, 0, "lfoot_grf")[0]),
+                                  int(o.field(envs, 0, "ncon_r")[0] + o.field(envs, 0, "ncon_l")[0]), int(o.field(envs, 0, "ncon")[0]))
+        # kernel source == oracle under this flag (closed loop, rewards include the GRF / contact-height terms)
+        e = Emu(pack_model(m2, tolerance=1e-14), 64, 4, seed=3)
+        envs = o.make_envs(4, seed=3)
+        assert np.abs(o.batch_reset(envs, 4) - e.reset()).max() < 1e-12
+        rng = np.random.RandomState(5)
+        for _ in range(40):
+            a = rng.normal(size=(4, 12)) * 0.2
+            oo, _, tt, rr, dd, ee = o.batch_step(envs, 4, a, max_traj_len=30)
+            eo, _, etm, er, ed, een, _, _ = e.step(a, max_traj_len=30)
+            assert (dd == ed).all() and np.abs(tt - etm).max() < 1e-10 and np.abs(oo - eo).max() < 1e-9
+    assert seen[(False, 4)][:2] == (0.0, 0) and seen[(False, 4)][2] == 8          # carried by 8 stone contacts, task sees none
+    assert 0.9 * mg < seen[(True, 4)][0] < 1.1 * mg and seen[(True, 4)][1] == 8
+    assert 0.45 * mg < seen[(False, 1)][0] < 0.55 * mg and seen[(False, 1)][1:] == (8, 16)   # the floor's half of the load
+    assert 0.9 * mg < seen[(True, 1)][0] < 1.1 * mg and seen[(True, 1)][1] == 16
 
 
 def test_foot_overhanging_a_slab_edge_is_held_by_edge_contacts(orc):

@@ -247,6 +247,14 @@ def compile_jvrc(boxes: bool = False):
             # not in the reference: penetration depth up to which a slab's top face always supports a point (beyond it the
             # point must be at least as far from the slab's side faces), see oracle/sim_oracle.c:slab_supports
             side_tol=0.02,
+            # SteppingTask normalises the foot forces with RobotInterface.get_robot_mass() = mj_getTotalmass,
+            # which sums EVERY body: the 20 static boxes are compiled from `size="1 1 0.1"` (gen_xml.py:151) at the default
+            # density 1000 kg/m^3 = 800 kg each, and later geom_size edits do not touch body_mass
+            task_mass=float(sum(lk.mass for lk in links)) + 20 * (2 * 1.0) * (2 * 1.0) * (2 * r5(0.1)) * 1000.0,
+            # get_*_floor_contacts skips contacts whose geom1 is a robot geom; a foot box precedes a stone box
+            # in MuJoCo's (type, id) pair ordering, so stone contacts are invisible to the task (GRF, contact_point_z).
+            # True = count them as floor (the physically meant behaviour), False = the reference's behaviour
+            slab_contacts_are_floor=False,
             mode_probs=[0.15, 0.05, 0.2, 0.3, 0.3],  # CURVED, STANDING, BACKWARD, LATERAL, FORWARD
             plans=plans)
     add_setconst(model)

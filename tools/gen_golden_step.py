@@ -28,6 +28,7 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 OUT = os.path.join(ROOT, "tests", "golden")
 sys.path.insert(0, ROOT)
 EPS4 = 4 * np.finfo(float).eps
+TASK_MASS = None
 
 
 # ---------------------------------------------------------------- transforms3d stand-in ('sxyz' = static x, y, z)
@@ -130,7 +131,7 @@ class Client:
         self.contacts_r, self.contacts_l = [], []
         self.selfcol = False
 
-    def get_robot_mass(self): return 62.4
+    def get_robot_mass(self): return TASK_MASS      # mj_getTotalmass incl. the 20 static boxes
     def get_object_xpos_by_name(self, name, typ): return self.pose[name][0].copy()
     def get_object_xquat_by_name(self, name, typ): return self.pose[name][1].copy()
     def get_lfoot_body_pos(self): return self.pose["lfoot"][0].copy()
@@ -164,6 +165,8 @@ def main():
              stm.WalkModes.FORWARD: 4}
 
     o = Oracle("jvrc_step")
+    global TASK_MASS
+    TASK_MASS = o.mj["stepping"]["task_mass"]
     rng = np.random.RandomState(20260923)
     cases = []
     for case in range(12):
