@@ -113,6 +113,11 @@ int lhw_grad_sumsq(const float* grad, float* norm_scratch, long long n, float gr
 int lhw_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* norm_scratch,
                   long long n, int step, float lr, float beta1, float beta2, float eps, float max_norm,
                   float grad_scale, void* stream);
+/* same update, Adam step number kept in DEVICE memory (step_dev[0] = completed steps, incremented by the call): the whole
+ * optimiser step of rl/algos/ppo.py:389-396 can then be replayed from a CUDA graph */
+int lhw_clip_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* norm_scratch,
+                      long long n, int* step_dev, float lr, float beta1, float beta2, float eps, float max_norm,
+                      float grad_scale, void* stream);
 
 /* ---- multi-GPU exchange step, fused (csrc/comm_kernels.cu) ------------------------------------------
  * Replaces, on N > 1 GPUs, the sequence of rl/algos/ppo.py:389-396: (gradient all-reduce) -> clip_grad_norm_(actor),

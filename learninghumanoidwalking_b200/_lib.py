@@ -42,6 +42,8 @@ SIGNATURES = {
     "lhw_comm_destroy": (c_int, [c_void_p]),
     "lhw_fused_allreduce_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_int, c_float, c_float,
                                               c_float, c_float, c_float, c_void_p, c_void_p]),
+    "lhw_clip_adam_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_float, c_float, c_float,
+                                  c_float, c_float, c_float, c_void_p]),
     "lhw_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_float,
                               c_float, c_float, c_float, c_void_p]),
 }

@@ -164,6 +164,29 @@ __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 
+// the same update with the Adam step number read from device memory: lets the whole optimiser step live inside a CUDA graph
+// (a by-value step would be frozen at capture time); step_dev[0] holds the number of completed steps
+__global__ void clip_adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                     float* __restrict__ v, const float* __restrict__ sumsq, long long n,
+                                     const int* __restrict__ step_dev, float lr, float b1, float b2, float eps, float max_norm,
+                                     float scale) {
+  const float t = (float)(step_dev[0] + 1);
+  const float bc1 = 1.0f - powf(b1, t), bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+  const float total_norm = sqrtf(sumsq[0]);
+  float coef = max_norm / (total_norm + 1e-6f);
+  coef = coef > 1.0f ? 1.0f : coef;
+  const float gs = scale * coef, step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float mi = m[i] + (1.0f - b1) * (gi - m[i]);
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+__global__ void step_inc_kernel(int* step_dev) { step_dev[0] += 1; }
+
 int perr(int code, const char* what, cudaError_t e) {
   g_perr = std::string(what) + ": " + cudaGetErrorString(e);
   return code;
@@ -238,6 +261,20 @@ int lhw_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_av
   clip_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, norm_scratch, n, lr, beta1,
                                                            beta2, eps, max_norm, grad_scale, bc1, bc2_sqrt);
   KCHECK("clip_adam_kernel");
+  return 0;
+}
+
+int lhw_clip_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* norm_scratch,
+                      long long n, int* step_dev, float lr, float beta1, float beta2, float eps, float max_norm,
+                      float grad_scale, void* stream) {
+  if (n <= 0 || !step_dev) return 0;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 4) grid = 148 * 4;
+  clip_adam_dev_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, norm_scratch, n, step_dev, lr,
+                                                               beta1, beta2, eps, max_norm, grad_scale);
+  KCHECK("clip_adam_dev_kernel");
+  step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  KCHECK("step_inc_kernel");
   return 0;
 }
 

@@ -65,6 +65,7 @@ class FusedClipAdam(torch.optim.Optimizer):
             self.exp_avg = torch.zeros_like(self.flat)
             self.exp_avg_sq = torch.zeros_like(self.flat)
         self.norm = torch.zeros(1, dtype=torch.float32, device=self.flat.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.flat.device)   # completed Adam steps, device side
         self.step_count = 0
         self.process_group = process_group
         self.world = 1
@@ -80,9 +81,11 @@ class FusedClipAdam(torch.optim.Optimizer):
         scale = 1.0 / self.world
         n = self.flat.numel()
         _lib.check(L.lhw_grad_sumsq(self.grad.data_ptr(), self.norm.data_ptr(), n, scale, st), "lhw_grad_sumsq")
-        _lib.check(L.lhw_clip_adam(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                   self.exp_avg_sq.data_ptr(), self.norm.data_ptr(), n, self.step_count, g["lr"],
-                                   g["betas"][0], g["betas"][1], g["eps"], g["max_norm"], scale, st), "lhw_clip_adam")
+        # the step number lives on the device (bias corrections computed in the kernel), so that an eager step and a step
+        # replayed from a CUDA graph (PPO._update_graphed) are the same launches with the same arguments
+        _lib.check(L.lhw_clip_adam_dev(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), self.norm.data_ptr(), n, self.step_dev.data_ptr(), g["lr"],
+                                       g["betas"][0], g["betas"][1], g["eps"], g["max_norm"], scale, st), "lhw_clip_adam_dev")
 
     def total_norm(self) -> torch.Tensor:
         return self.norm.sqrt()

@@ -83,6 +83,7 @@ class PPO:
         L = _lib.lib()
         self._adv_stats = torch.zeros(L.lhw_adv_stats_words(), dtype=torch.float64, device=self.device)
         self._mb = None
+        self._ug, self._ug_calls = None, 0      # CUDA graph of one optimiser step (see _update_step)
 
     # ------------------------------------------------------------------ sampling (rl/algos/ppo.py:215-297)
     def sample_parallel_with_workers(self, deterministic=False) -> BatchData:
@@ -138,6 +139,47 @@ class PPO:
             a_opt.step()
             c_opt.step()
         return (actor_loss, entropy_penalty, critic_loss, approx_kl_div, mirror_loss, imitation_loss, clip_fraction)
+
+    # ------------------------------------------------------------------ one minibatch update, replayed from a CUDA graph
+    def _update_step(self, ob, ab, rb, db, obs_mirr, act_mirr) -> torch.Tensor:
+        """update_actor_critic on the static minibatch buffers; returns the 7 scalars as one device vector.
+        An update is ~600 small launches (three MLP forwards, autograd backward, clip + Adam); at the reference's minibatch
+        sizes it is launch bound (2.5 ms of host time for 1.9 ms of kernels at 4096 samples, far worse at the default 64).
+        After a few eager steps (cuBLAS / autograd warm-up — they are real updates) the whole step — losses, backward,
+        gradient norms, clip + Adam with the step counter in device memory — is captured once and replayed.
+        Single rank only (the fused NVLink exchange is a cooperative launch); LHW_UPDATE_GRAPH=0 keeps the eager loop."""
+        import os
+        eager = (self.world > 1 or os.environ.get("LHW_UPDATE_GRAPH", "1") == "0" or self._mb is None or ob is not self._mb[0]
+                 or not isinstance(self.actor_optimizer, FusedClipAdam) or not isinstance(self.critic_optimizer, FusedClipAdam))
+        if not eager and self._ug is not None and self._ug[2] == ob.data_ptr():
+            self._ug[0].replay()
+            self.actor_optimizer.step_count += 1
+            self.critic_optimizer.step_count += 1
+            return self._ug[1]
+        if eager:
+            scalars = self.update_actor_critic(ob, ab, rb, db, 1, mirror_observation=obs_mirr, mirror_action=act_mirr)
+            return torch.stack([s.detach().float() for s in scalars])
+        if self._ug_calls < 3:
+            # warm-up on a side stream, as graph capture will run on one (cuBLAS workspaces, autograd buffers)
+            self._ug_calls += 1
+            cur, side = torch.cuda.current_stream(self.device), torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                scalars = self.update_actor_critic(ob, ab, rb, db, 1, mirror_observation=obs_mirr, mirror_action=act_mirr)
+                out = torch.stack([s.detach().float() for s in scalars])
+            cur.wait_stream(side)
+            out.record_stream(cur)
+            return out
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            scalars = self.update_actor_critic(ob, ab, rb, db, 1, mirror_observation=obs_mirr, mirror_action=act_mirr)
+            out = torch.stack([s.detach().float() for s in scalars])
+        # capture does not execute, and the host-side counters it bumped belong to the replay below
+        self.actor_optimizer.step_count -= 1
+        self.critic_optimizer.step_count -= 1
+        self._ug = (g, out, ob.data_ptr())
+        return self._update_step(ob, ab, rb, db, obs_mirr, act_mirr)
 
     def make_optimizers(self):
         """Adam(lr, eps) for actor and critic (rl/algos/ppo.py:429-430) as fused clip+Adam over one flat buffer."""
@@ -225,15 +267,16 @@ class PPO:
             advantages = self.normalize_advantages(returns, values)
             self.total_steps += num_samples * self.world
             self.old_policy.load_state_dict(self.policy.state_dict())
-            self.old_policy.obs_mean, self.old_policy.obs_std = self.policy.obs_mean.clone(), self.policy.obs_std.clone()
+            # in place: a captured update graph holds the addresses of these tensors
+            self.old_policy.obs_mean.copy_(self.policy.obs_mean)
+            self.old_policy.obs_std.copy_(self.policy.obs_std)
             t1 = time.time()
             stats = torch.zeros(7, device=self.device)
             n_updates = 0
             for epoch in range(self.epochs):
                 for idx in self.minibatch_indices(num_samples, itr, epoch):
                     ob, ab, rb, db = self.gather_minibatch(observations, actions, returns, advantages, idx)
-                    scalars = self.update_actor_critic(ob, ab, rb, db, 1, mirror_observation=obs_mirr, mirror_action=act_mirr)
-                    stats += torch.stack([s.detach().float() for s in scalars])
+                    stats += self._update_step(ob, ab, rb, db, obs_mirr, act_mirr)
                     n_updates += 1
             stats = (stats / max(1, n_updates)).tolist()   # the only host sync of the optimisation phase
             optimize_time = time.time() - t1

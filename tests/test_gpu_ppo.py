@@ -232,3 +232,23 @@ def test_graph_replayed_rollout_is_bitwise_equal_to_the_eager_loop(monkeypatch):
         ppo.env.close()
     for a, b in zip(outs["1"], outs["0"]):
         assert torch.equal(a, b)
+
+
+def test_graph_replayed_update_matches_the_eager_update(monkeypatch):
+    """PPO._update_step: after three eager warm-up updates the optimiser step (losses, backward, clip + Adam with the step
+    counter in device memory) is captured once and replayed; same seed, same data => the same weights as the eager loop."""
+    from learninghumanoidwalking_b200.rl import PPO
+    finals, logs = {}, {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LHW_UPDATE_GRAPH", mode)
+        ppo = PPO(_env_fn(seed=4), _args(epochs=2), seed=4)
+        logs[mode] = ppo.train(None, 2, verbose=False)
+        finals[mode] = ppo._flat_param.clone()
+        if mode == "1":
+            assert ppo._ug is not None                              # the graph was really captured and used
+            assert ppo.actor_optimizer.step_count == int(ppo.actor_optimizer.step_dev.item()) == 20
+        else:
+            assert ppo._ug is None
+        ppo.env.close()
+    assert (finals["0"] - finals["1"]).abs().max().item() < 1e-6
+    assert abs(logs["0"][-1]["critic_loss"] - logs["1"][-1]["critic_loss"]) < 1e-5
