@@ -71,7 +71,9 @@ class Gaussian_FF_Actor(_NormAttrs):
 
     def distribution(self, inputs):
         mu, sd = self._get_dist_params(inputs)
-        return torch.distributions.Normal(mu, sd)
+        # validate_args would test the parameters with a host-synchronising `.all()` (not capturable in a CUDA graph);
+        # mu is finite by construction of the update (checked by the trainer's loss statistics) and sd is a constant
+        return torch.distributions.Normal(mu, sd, validate_args=False)
 
 
 class FF_V(_NormAttrs):

@@ -38,4 +38,14 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 ev = prof.key_averages()
 cuda_us = sum(getattr(e, "self_device_time_total", getattr(e, "self_cuda_time_total", 0)) for e in ev)
 nk = sum(e.count for e in ev if getattr(e, "self_device_time_total", getattr(e, "self_cuda_time_total", 0)) > 0)
+def one_g():
+    ob, ab, rb, db = ppo.gather_minibatch(batch.states, batch.actions, batch.returns.contiguous(), adv, idx)
+    return ppo._update_step(ob, ab, rb, db, env.mirror_clock_observation, env.mirror_action)
+for _ in range(6): one_g()
+torch.cuda.synchronize()
+t0 = time.time()
+for _ in range(N): one_g()
+torch.cuda.synchronize()
+wall_g = (time.time() - t0) / N
+print(f"minibatch {mb}: graph-replayed update {wall_g*1e3:.3f} ms/update (captured: {ppo._ug is not None})")
 print(f"minibatch {mb}: wall {wall*1e3:.3f} ms/update, summed CUDA kernel time {cuda_us/N/1e3:.3f} ms/update, ~{nk/N:.0f} kernels/update")
