@@ -138,7 +138,10 @@ class PPO:
             torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.grad_clip)
             a_opt.step()
             c_opt.step()
-        return (actor_loss, entropy_penalty, critic_loss, approx_kl_div, mirror_loss, imitation_loss, clip_fraction)
+        # detached: a caller holding on to the losses must not keep this step's autograd graph (and its AccumulateGrad nodes)
+        # alive into the next one, which may be captured into a CUDA graph
+        return tuple(t.detach() for t in (actor_loss, entropy_penalty, critic_loss, approx_kl_div, mirror_loss, imitation_loss,
+                                          clip_fraction))
 
     # ------------------------------------------------------------------ one minibatch update, replayed from a CUDA graph
     def _update_step(self, ob, ab, rb, db, obs_mirr, act_mirr) -> torch.Tensor:
