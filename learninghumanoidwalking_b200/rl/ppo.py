@@ -45,6 +45,10 @@ class PPO:
         self.grad_clip, self.mirror_coeff = args.max_grad_norm, args.mirror_coeff
         self.eval_freq = getattr(args, "eval_freq", 100)
         self.imitate_coeff = getattr(args, "imitate_coeff", 0.0)
+        # opt-in: TF32 tensor-core GEMMs for the MLPs (the reference trains in fp32 with torch's default allow_tf32 = False, and
+        # so does this build unless asked otherwise; at minibatches >= 32k the update is GEMM bound)
+        if getattr(args, "tf32", False):
+            torch.backends.cuda.matmul.allow_tf32 = True
         if getattr(args, "recurrent", False):
             raise NotImplementedError("recurrent policies are outside the accelerated path (SURVEY.md §2 row 5)")
         self.recurrent = False

@@ -196,6 +196,8 @@ def main(argv=None):
         parser.add_argument("--seed", type=int, default=None, help="Random seed for reproducibility.")
         parser.add_argument("--precision", type=int, default=32, choices=[32, 64],
                             help="arithmetic of the device simulator (64 = the reference's float64)")
+        parser.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core GEMMs in the policy / critic MLPs "
+                            "(off: fp32 like the reference)")
         parser.add_argument("--steps-per-env", type=int, default=None, help="transitions per env per iteration (default: max-traj-len)")
         args = parser.parse_args(argv[1:])
         if args.seed is not None:
