@@ -194,7 +194,9 @@ class PPO:
         from .comm import PeerComm
         from .optim import flatten_modules_
         n_total = sum(p.numel() for m in (self.policy, self.critic) for p in m.parameters())
-        fused = os.environ.get("LHW_FUSED_EXCHANGE", "1") != "0"
+        # the fused NVLink exchange kernel (peer all-reduce + clip + Adam) is the N > 1 path; a single rank uses the two
+        # clip+Adam launches whose step counter lives on the device, so that the step can be replayed from a CUDA graph
+        fused = os.environ.get("LHW_FUSED_EXCHANGE", "1") != "0" and self.world > 1
         self._comm = PeerComm(n_total, self.device) if fused else None
         flat, grad, segs = flatten_modules_([self.policy, self.critic], None if self._comm is None else self._comm.grad)
         self._flat_param, self._flat_grad = flat, grad
