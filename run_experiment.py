@@ -24,6 +24,32 @@ from pathlib import Path
 
 import torch
 
+_F, _I, _P, _S = float, int, Path, str
+# the reference's command line (run_experiment.py:152-260), flag for flag, as data: (flag, argparse keywords)
+TRAIN_FLAGS = [
+    ("--env", dict(required=True, type=_S)), ("--logdir", dict(default=Path("/tmp/logs"), type=_P, help="run directory root")),
+    ("--input-norm-steps", dict(type=_I, default=100000)), ("--n-itr", dict(type=_I, default=20000, help="PPO iterations")),
+    ("--lr", dict(type=_F, default=3e-4)), ("--eps", dict(type=_F, default=1e-5, help="Adam epsilon")),
+    ("--gamma", dict(type=_F, default=0.99)), ("--lam", dict(type=_F, default=0.95, help="GAE lambda")),
+    ("--std-dev", dict(type=_F, default=0.223, help="exploration noise")), ("--learn-std", dict(action="store_true")),
+    ("--entropy-coeff", dict(type=_F, default=0.0)), ("--clip", dict(type=_F, default=0.2, help="PPO clip range")),
+    ("--minibatch-size", dict(type=_I, default=64)), ("--epochs", dict(type=_I, default=3)),
+    ("--num-procs", dict(type=_I, default=4096, help="parallel environment copies over all ranks (the reference: Ray workers)")),
+    ("--max-grad-norm", dict(type=_F, default=0.5)), ("--max-traj-len", dict(type=_I, default=400, help="episode horizon")),
+    ("--no-mirror", dict(action="store_true", help="train without the SymmetricEnv mirror loss")),
+    ("--mirror-coeff", dict(default=0.4, type=_F)), ("--eval-freq", dict(default=100, type=_I, help="checkpoint every N iterations")),
+    ("--continued", dict(type=_P, help="actor checkpoint to continue from")), ("--recurrent", dict(action="store_true")),
+    ("--imitate", dict(type=_S, default=None)), ("--imitate-coeff", dict(type=_F, default=0.0)),
+    ("--yaml", dict(type=_S, default=None)), ("--device", dict(type=_S, default="cuda", choices=["auto", "cuda"])),
+    ("--seed", dict(type=_I, default=None)),
+    # additions of this build
+    ("--precision", dict(type=_I, default=32, choices=[32, 64], help="simulator arithmetic (64 = the reference's float64)")),
+    ("--tf32", dict(action="store_true", help="TF32 tensor-core GEMMs in the MLPs (off: fp32 like the reference)")),
+    ("--steps-per-env", dict(type=_I, default=None, help="transitions per env per iteration (default: max-traj-len)")),
+]
+EVAL_FLAGS = [("--path", dict(type=_P, default=None)), ("--logdir", dict(type=_P, default=None)),
+              ("--out-dir", dict(type=_P, default=None, help="(videos are not produced by this build)")),
+              ("--ep-len", dict(type=_I, default=10, help="seconds to play")), ("--seed", dict(type=_I, default=None))]
 ENVS = ("jvrc_walk", "jvrc_step", "h1", "jvrc_walk_terrain")   # the last one is an extension (BASELINE configs[4])
 
 
@@ -167,49 +193,16 @@ def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     parser = argparse.ArgumentParser()
     if argv and argv[0] == "train":
-        parser.add_argument("--env", required=True, type=str)
-        parser.add_argument("--logdir", default=Path("/tmp/logs"), type=Path, help="Path to save weights and logs")
-        parser.add_argument("--input-norm-steps", type=int, default=100000)
-        parser.add_argument("--n-itr", type=int, default=20000, help="Number of iterations of the learning algorithm")
-        parser.add_argument("--lr", type=float, default=3e-4, help="Adam learning rate")
-        parser.add_argument("--eps", type=float, default=1e-5, help="Adam epsilon (for numerical stability)")
-        parser.add_argument("--gamma", type=float, default=0.99, help="MDP discount")
-        parser.add_argument("--lam", type=float, default=0.95, help="GAE lambda (1.0 = MC returns, 0.0 = TD(0))")
-        parser.add_argument("--std-dev", type=float, default=0.223, help="Action noise for exploration")
-        parser.add_argument("--learn-std", action="store_true", help="Exploration noise will be learned")
-        parser.add_argument("--entropy-coeff", type=float, default=0.0, help="Coefficient for entropy regularization")
-        parser.add_argument("--clip", type=float, default=0.2, help="Clipping parameter for PPO surrogate loss")
-        parser.add_argument("--minibatch-size", type=int, default=64, help="Batch size for PPO updates")
-        parser.add_argument("--epochs", type=int, default=3, help="Number of optimization epochs per PPO update")
-        parser.add_argument("--num-procs", type=int, default=4096, help="Number of parallel environment copies (all ranks)")
-        parser.add_argument("--max-grad-norm", type=float, default=0.5, help="Value to clip gradients at")
-        parser.add_argument("--max-traj-len", type=int, default=400, help="Max episode horizon")
-        parser.add_argument("--no-mirror", required=False, action="store_true", help="to use SymmetricEnv")
-        parser.add_argument("--mirror-coeff", required=False, default=0.4, type=float, help="weight for mirror loss")
-        parser.add_argument("--eval-freq", required=False, default=100, type=int, help="Frequency of saving checkpoints")
-        parser.add_argument("--continued", required=False, type=Path, help="path to pretrained weights")
-        parser.add_argument("--recurrent", required=False, action="store_true", help="use LSTM instead of FF")
-        parser.add_argument("--imitate", required=False, type=str, default=None, help="Policy to imitate")
-        parser.add_argument("--imitate-coeff", required=False, type=float, default=0.0)
-        parser.add_argument("--yaml", required=False, type=str, default=None, help="Path to config file passed to Env class")
-        parser.add_argument("--device", required=False, type=str, default="cuda", choices=["auto", "cuda"])
-        parser.add_argument("--seed", type=int, default=None, help="Random seed for reproducibility.")
-        parser.add_argument("--precision", type=int, default=32, choices=[32, 64],
-                            help="arithmetic of the device simulator (64 = the reference's float64)")
-        parser.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core GEMMs in the policy / critic MLPs "
-                            "(off: fp32 like the reference)")
-        parser.add_argument("--steps-per-env", type=int, default=None, help="transitions per env per iteration (default: max-traj-len)")
+        for flag, kw in TRAIN_FLAGS:
+            parser.add_argument(flag, **kw)
         args = parser.parse_args(argv[1:])
         if args.seed is not None:
             torch.manual_seed(args.seed)
             print(f"Deterministic mode enabled with seed: {args.seed}")
         return run_experiment(args)
     elif argv and argv[0] == "eval":
-        parser.add_argument("--path", required=False, type=Path, default=None)
-        parser.add_argument("--logdir", required=False, type=Path, default=None)
-        parser.add_argument("--out-dir", required=False, type=Path, default=None, help="(videos are not produced by this build)")
-        parser.add_argument("--ep-len", required=False, type=int, default=10, help="Episode length to play (in seconds)")
-        parser.add_argument("--seed", type=int, default=None)
+        for flag, kw in EVAL_FLAGS:
+            parser.add_argument(flag, **kw)
         args = parser.parse_args(argv[1:])
         return evaluate(args)
     else:

@@ -53,7 +53,7 @@ def test_run_experiment_keeps_the_reference_flags():
     list below was read off the reference; where the reference checkout is present (this container, not the GPU box) it is
     re-derived from the file itself."""
     src = open(os.path.join(ROOT, "run_experiment.py")).read()
-    ours = set(re.findall(r"add_argument\(\s*\"(--[a-z-]+)\"", src))
+    ours = set(re.findall(r"\(\"(--[a-z-]+)\",", src))
     ref_flags = {"--env", "--logdir", "--input-norm-steps", "--n-itr", "--lr", "--eps", "--gamma", "--lam", "--std-dev",
                  "--learn-std", "--entropy-coeff", "--clip", "--minibatch-size", "--epochs", "--num-procs", "--max-grad-norm",
                  "--max-traj-len", "--no-mirror", "--mirror-coeff", "--eval-freq", "--continued", "--recurrent", "--imitate",
