@@ -177,6 +177,14 @@ class Oracle:
         """env.robot.iteration_count = itr (rl/workers/rollout_worker.py:95) -> the curriculum's step height."""
         self.lib.orc_set_step_height(self._model, ctypes.c_double(curriculum_height(iteration_count)))
 
+    def contacts(self, envs, i=0):
+        """(pos [n,3], dist [n], foot [n], slab [n]) of the contacts at env i's current qpos."""
+        pos, dist = np.zeros((128, 3)), np.zeros(128)
+        foot, slab = np.zeros(128, dtype=np.int32), np.zeros(128, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        n = self.lib.orc_test_contacts(self._model, self.env_ptr(envs, i), p(pos), p(dist), p(foot), p(slab))
+        return pos[:n], dist[:n], foot[:n], slab[:n]
+
     def task_reset(self, envs, i=0):
         self.lib.orc_test_task_reset(self._model, self.env_ptr(envs, i))
 

@@ -1443,6 +1443,21 @@ void orc_env_init(const orc_model* m, orc_env* e, uint32_t seed, uint32_t env_id
   for (int i = 0; i < ORC_NSLAB; i++) e->seq[i][2] = -1;
   e->mode = m->task == ORC_TASK_STEP ? ORC_STEP_STANDING : 0;
 }
+/* test hook: the contact list mj_collision would produce at the env's current qpos (position, signed distance, foot 0/1,
+ * 1 = against a stepping stone / 0 = floor); returns the number of contacts */
+int orc_test_contacts(const orc_model* m, const orc_env* e, double* pos /* [ORC_MAXCON][3] */, double* dist, int* foot, int* slab) {
+  kin_t k;
+  static __thread efc_t efc;
+  fk(m, &e->P, e->qpos, &k);
+  make_constraints(m, &e->P, &k, e->qpos, e->qvel, e, &efc);
+  for (int ci = 0; ci < efc.ncon; ci++) {
+    for (int x = 0; x < 3; x++) pos[3 * ci + x] = efc.con_pos[ci][x];
+    dist[ci] = efc.con_dist[ci];
+    foot[ci] = efc.con_geom[ci];
+    slab[ci] = efc.con_slab[ci];
+  }
+  return efc.ncon;
+}
 /* test hooks for the SteppingTask pieces pinned by tests/golden/step_*.json */
 void orc_test_task_reset(const orc_model* m, orc_env* e) { task_reset(m, e); }
 void orc_test_task_step(const orc_model* m, orc_env* e) { task_step(m, e); }

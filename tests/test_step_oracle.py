@@ -284,3 +284,83 @@ def test_terrain_extension_kernel_source_matches_oracle_and_reduces_to_flat_walk
             em.step(np.zeros((1, 12)), autoreset=0)
         z[name] = em.qpos[0, 2]
     assert 1e-4 < z["default"] - z["soft"] < 5e-3
+
+
+def test_slab_contact_set_against_an_independent_polygon_clip(orc):
+    """The contact generation of the stepping stones (oracle: corners + Liang-Barsky edge crossings) against an independent
+    formulation: Sutherland-Hodgman clipping of the sole quadrilateral by the slab's four half-planes (numpy, below).  The
+    polygon's vertices with z below the top face must be exactly the oracle's slab contacts for that (foot, slab) pair."""
+    o = orc
+    mj = o.mj
+    hx, hy, hz = mj["stepping"]["slab_half"]
+    size, gpos = np.array(mj["geoms"][0]["size"]), np.array(mj["geoms"][0]["pos"])
+    rng = np.random.RandomState(7)
+
+    def clip_poly(poly, a, b, c):          # keep a*x + b*y <= c ; poly: list of (x, y, z)
+        out = []
+        for i in range(len(poly)):
+            p, q = poly[i], poly[(i + 1) % len(poly)]
+            fp, fq = a * p[0] + b * p[1] - c, a * q[0] + b * q[1] - c
+            if fp <= 0:
+                out.append(p)
+            if (fp < 0 < fq) or (fq < 0 < fp):
+                t = fp / (fp - fq)
+                out.append(p + t * (q - p))
+        return out
+
+    from tools.compile_model import kinematics
+    n_cross = n_corner = 0
+    for trial in range(120):
+        envs = o.make_envs(1)
+        q = np.array(mj["cfg"]["nominal_qpos"])
+        q[0:2] = rng.uniform(-0.1, 0.1, 2)
+        q[2] = 0.806 + rng.uniform(-0.012, 0.003)      # sole between ~1.5 cm inside the slab and just above it
+        ang = rng.normal(size=3) * np.array([0.03, 0.03, 0.5])
+        q[3:7] = [np.cos(np.linalg.norm(ang) / 2), *(np.sin(np.linalg.norm(ang) / 2) * ang / np.linalg.norm(ang))]
+        q[7:] += rng.uniform(-0.08, 0.08, 12)
+        slab = np.array([rng.uniform(-0.1, 0.35), rng.uniform(-0.3, 0.3), rng.uniform(-0.004, 0.004), rng.uniform(-0.8, 0.8)])
+        seq = np.tile([0.0, 0.0, -1.0, 0.0], (20, 1))
+        seq[3] = slab
+        o.set_field(envs, 0, "qpos", q); o.set_field(envs, 0, "seq", seq.reshape(-1)); o.set_field(envs, 0, "mode", 4)   # no floor
+        pos, dist, foot, is_slab = o.contacts(envs, 0)
+        assert is_slab.all()
+        xpos, xmat = kinematics(mj, q)
+        c, s = np.cos(slab[3]), np.sin(slab[3])
+        for f, lk in enumerate((mj["rfoot_link"], mj["lfoot_link"])):
+            R, p0 = np.array(xmat[lk]).reshape(3, 3), np.array(xpos[lk])
+            # sole rectangle in the order the kernel walks it (corner ids 0, 1, 3, 2), world coordinates
+            sole = [p0 + R @ (gpos + np.array([sx * size[0], sy * size[1], -size[2]])) for sx, sy in ((-1, -1), (1, -1), (1, 1), (-1, 1))]
+            to_slab = lambda p: np.array([c * (p[0] - slab[0]) + s * (p[1] - slab[1]), -s * (p[0] - slab[0]) + c * (p[1] - slab[1]), p[2]])
+            poly = [to_slab(p) for p in sole]
+            for a_, b_, c_ in ((1, 0, hx), (-1, 0, hx), (0, 1, hy), (0, -1, hy)):
+                poly = clip_poly(poly, a_, b_, c_)
+            tol = mj["stepping"]["side_tol"]      # the model's side-face rule (DESIGN.md §4.3): deeper than tol only if as far from the sides
+            keep = lambda v: -2 * hz < v[2] - slab[2] < 0 and (slab[2] - v[2] <= tol or slab[2] - v[2] <= min(hx - abs(v[0]), hy - abs(v[1])) + 1e-15)
+            is_corner = lambda v: any(np.abs(v - to_slab(p)).max() < 1e-13 for p in sole)
+            crossings = [v for v in poly if keep(v) and not is_corner(v)]
+            if len(crossings) > 4:
+                continue                               # the per-foot crossing cap is order dependent; not this test's subject
+            # corners: mjc_PlaneBox's rule over all 8 box corners in index order (x sign = bit 0, y = bit 1, z = bit 2), 4 at
+            # most: below the box centre, inside the footprint, supported by the top face (a tilted foot can offer a corner
+            # of its TOP face as well, exactly as it would to the floor plane)
+            ctr = p0 + R @ gpos
+            corners = []
+            for i in range(8):
+                pt = p0 + R @ (gpos + np.array([(1 if i & 1 else -1) * size[0], (1 if i & 2 else -1) * size[1], (1 if i & 4 else -1) * size[2]]))
+                v = to_slab(pt)
+                if len(corners) < 4 and pt[2] - ctr[2] <= 0 and abs(v[0]) <= hx and abs(v[1]) <= hy and keep(v):
+                    corners.append(v)
+            exp = corners + crossings
+            got = pos[foot == f]
+            got_d = dist[foot == f]
+            # the oracle caps crossings at 4 per foot and corners at 4: sizes here never exceed that (one slab)
+            assert len(got) == len(exp), (trial, f, len(got), len(exp))
+            for v in exp:
+                w = np.array([slab[0] + c * v[0] - s * v[1], slab[1] + s * v[0] + c * v[1]])
+                d = v[2] - slab[2]
+                j = np.argmin(np.abs(got[:, 0] - w[0]) + np.abs(got[:, 1] - w[1]))
+                assert np.abs(got[j, :2] - w).max() < 1e-12 and abs(got_d[j] - d) < 1e-12 and abs(got[j, 2] - (v[2] - 0.5 * d)) < 1e-12
+            inside = [abs(to_slab(p)[0]) <= hx and abs(to_slab(p)[1]) <= hy for p in sole]
+            n_corner += sum(inside)
+            n_cross += len(crossings)
+    assert n_cross > 40 and n_corner > 100      # both kinds of vertices were exercised
