@@ -466,38 +466,27 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
   LHW_ASSUME_SHARED(&w);
   LHW_ASSUME_SHARED(x);
   Arrow<real, NJ, TK>& H = w.H;
+  // column steps of both chains side by side.  lane = chain * 16 + row; rows 0..NJ-1: the chain block, NJ..NJ+5: the coupling
+  // rows (X = B L^-T), NJ+6: the right-hand side (forward substitution).  All three kinds of row do the SAME arithmetic on
+  // their own row pointer, so the step is one branch-free instruction stream (a per-kind if/else would run three times)
 #pragma unroll
   for (int k = 0; k < NJ; k++) {
     LHW_LANES(l) {
       const int ch = l >> 4, r = l & 15;
       if (r < NJ + 7 && (r >= NJ || r >= k)) {
+        real* pr = r < NJ ? H.c[ch][r] : (r < NJ + 6 ? H.x[ch][r - NJ] : x + 6 + ch * NJ);
         const real* pk = H.c[ch][k];
-        real dk = pk[k];
+        real dk = pk[k], t = pr[k];
 #pragma unroll
-        for (int mm = 0; mm < k; mm++) dk -= pk[mm] * pk[mm];
+        for (int mm = 0; mm < k; mm++) {
+          const real pkm = pk[mm];
+          dk -= pkm * pkm;
+          t -= pr[mm] * pkm;
+        }
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
         const real inv = m_rsqrt(dk);
-        if (r == k) {
-          w.hdinv[6 + ch * NJ + k] = inv;
-        } else if (r < NJ) {
-          real* pi = H.c[ch][r];
-          real t = pi[k];
-  #pragma unroll
-        for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
-          pi[k] = t * inv;
-        } else if (r < NJ + 6) {
-          real* px = H.x[ch][r - NJ];
-          real t = px[k];
-  #pragma unroll
-        for (int mm = 0; mm < k; mm++) t -= px[mm] * pk[mm];
-          px[k] = t * inv;
-        } else {
-          real* pb = x + 6 + ch * NJ;
-          real t = pb[k];
-  #pragma unroll
-        for (int mm = 0; mm < k; mm++) t -= pb[mm] * pk[mm];
-          pb[k] = t * inv;
-        }
+        if (r == k) w.hdinv[6 + ch * NJ + k] = inv;
+        else pr[k] = t * inv;
       }
     }
     LHW_SYNC();
@@ -528,26 +517,20 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
 #pragma unroll
   for (int k = 0; k < 6; k++) {
     LHW_LANES(l) {
-      if (l < 7 && l >= k) {
+      if (l < 7 && l >= k) {   // rows 0..5 of the Schur complement, row 6 = the root right-hand side: same arithmetic
+        real* pr = l < 6 ? H.r[l] : x;
         const real* pk = H.r[k];
-        real dk = pk[k];
+        real dk = pk[k], t = pr[k];
 #pragma unroll
-        for (int mm = 0; mm < k; mm++) dk -= pk[mm] * pk[mm];
+        for (int mm = 0; mm < k; mm++) {
+          const real pkm = pk[mm];
+          dk -= pkm * pkm;
+          t -= pr[mm] * pkm;
+        }
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
         const real inv = m_rsqrt(dk);
         if (l == k) w.hdinv[k] = inv;
-        else if (l < 6) {
-          real* pi = H.r[l];
-          real t = pi[k];
-  #pragma unroll
-        for (int mm = 0; mm < k; mm++) t -= pi[mm] * pk[mm];
-          pi[k] = t * inv;
-        } else {
-          real t = x[k];
-  #pragma unroll
-        for (int mm = 0; mm < k; mm++) t -= x[mm] * pk[mm];
-          x[k] = t * inv;
-        }
+        else pr[k] = t * inv;
       }
     }
     LHW_SYNC();
