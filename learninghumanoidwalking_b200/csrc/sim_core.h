@@ -367,6 +367,8 @@ template <class real> LHW_DEV void inert_mul(const real* I, const real* mvv, rea
   out[4] = m * v[1] - hw[1];
   out[5] = m * v[2] - hw[2];
 }
+// row of the it-th entry (row-major) of a lower triangle with at most 6 rows: 0,1,1,2,2,2,... packed 3 bits per entry
+LHW_DEV int tri_row(int it) { return (int)((0x5B6DB2491B6D2448ull >> (3 * it)) & 7ull); }
 template <int NJ> LHW_DEV int dof_link(int d) { return d < 6 ? 0 : d - 5; }
 template <int NJ> LHW_DEV int loc2dof(int foot, int j) { return j < 6 ? j : 6 + foot * NJ + (j - 6); }
 // fast reciprocal square root (pivot scaling); the product keeps 1/sqrt explicitly, never sqrt then divide
@@ -494,9 +496,7 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
   // Schur complement of the root block and of the root right-hand side
   LHW_LANES(l) {
     if (l < 21) {
-      int r = 0, t = l;
-      while (t > r) { t -= r + 1; r++; }
-      const int c = t;
+      const int r = tri_row(l), c = l - r * (r + 1) / 2;
       real acc = H.r[r][c];
 #pragma unroll
       for (int ch = 0; ch < 2; ch++)
@@ -612,14 +612,30 @@ LHW_DEVNI void constraint_images(Work<real, NJ, TK>& w, const Model<real, NJ, TK
   LHW_ASSUME_SHARED(&w); LHW_ASSUME_SHARED(x); LHW_ASSUME_SHARED(outM); LHW_ASSUME_SHARED(outY);
   LHW_ASSUME_SHARED(e_out); LHW_ASSUME_SHARED(l_out);
   if (e_sub) { LHW_ASSUME_SHARED(e_sub); LHW_ASSUME_SHARED(l_sub); }
+  // M x (lanes 0..NV-1) and S_foot x (lanes 20..31) are the same shape of sum -- six root terms, then NJ terms of one chain
+  // (root rows: of both chains) -- so they run as ONE instruction stream on per-lane coefficient pointers / strides; the three
+  // lane roles as separate branches would be executed one after the other (same summation order as arrow_row_dot)
   LHW_LANES(l) {
-    if (l < NV) outM[l] = arrow_row_dot<real, NJ, TK>(w.M, l, x);
-    else if (l >= 20) {
-      const int f = (l - 20) / 6, e = (l - 20) - f * 6;
+    if (l < NV || l >= 20) {
+      const int ch = l < NV ? (l < 6 ? 0 : (l - 6) / NJ) : (l - 20) / 6;           // chain (dof lanes) / foot (S_foot lanes)
+      const int k = l < NV ? l - 6 - ch * NJ : (l - 20) - ch * 6;                    // chain dof / spatial component
+      const real* pa = l < 6 ? &w.M.r[l][0] : (l < NV ? &w.M.x[ch][0][k] : &w.S[0][k]);
+      const int sa = l < 6 ? 1 : (l < NV ? NJ : 6);
+      const real* pb = l < 6 ? &w.M.x[0][l][0] : (l < NV ? &w.M.c[ch][k][0] : &w.S[6 + ch * NJ][k]);
+      const int sb = l < NV ? 1 : 6;
+      const real* xb = x + 6 + ch * NJ;
       real acc = 0;
 #pragma unroll
-      for (int j = 0; j < NA; j++) acc += w.S[loc2dof<NJ>(f, j)][e] * x[loc2dof<NJ>(f, j)];
-      outY[f][e] = acc;
+      for (int j = 0; j < 6; j++) acc += pa[j * sa] * x[j];
+#pragma unroll
+      for (int kk = 0; kk < NJ; kk++) acc += pb[kk * sb] * xb[kk];
+      if (l < 6) {
+        const real* pc = &w.M.x[1][l][0];
+#pragma unroll
+        for (int kk = 0; kk < NJ; kk++) acc += pc[kk] * x[6 + NJ + kk];
+      }
+      real* dst = l < NV ? outM + l : &outY[ch][k];
+      *dst = acc;
     }
   }
   LHW_SYNC();
@@ -831,15 +847,15 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     if (l < NV) {
       real f[6];
       inert_mul(w.comp[dof_link<NJ>(l)], w.S[l], f);
-      if (l < 6) {
+      const int ch = l < 6 ? 0 : (l - 6) / NJ, k = l - 6 - ch * NJ;
+      // column of the root motion vectors: one stream for root rows (symmetric root block) and chain rows (coupling block)
 #pragma unroll
-        for (int j = 0; j < 6; j++)
-          if (j <= l) {
-            const real v = dot6(w.S[j], f);
-            w.M.r[l][j] = v; w.M.r[j][l] = v;
-          }
-      } else {
-        const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ;
+      for (int j = 0; j < 6; j++) {
+        const real v = dot6(w.S[j], f);
+        if (l >= 6) w.M.x[ch][j][k] = v;
+        else if (j <= l) { w.M.r[l][j] = v; w.M.r[j][l] = v; }
+      }
+      if (l >= 6) {
 #pragma unroll
         for (int kk = 0; kk < NJ; kk++)
           if (kk <= k) {
@@ -847,8 +863,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
             if (kk == k) v += m.armature[l];
             w.M.c[ch][k][kk] = v; w.M.c[ch][kk][k] = v;
           }
-#pragma unroll
-        for (int j = 0; j < 6; j++) w.M.x[ch][j][k] = dot6(w.S[j], f);
       }
     } else if (l >= 20) {
       const int ch = (l - 20) / 6, e = (l - 20) - ch * 6;
@@ -1247,9 +1261,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     LHW_LANES(l) {
       for (int it = l; it < 42; it += 32) {
         const int f = it / 21;
-        int a = 0, t = it - f * 21;
-        while (t > a) { t -= a + 1; a++; }
-        const int b = t;
+        const int a = tri_row(it - f * 21), b = it - f * 21 - a * (a + 1) / 2;
         real acc = 0;
         int ia[3], ib[3];
         unsigned sa[3], sb[3];
@@ -1288,29 +1300,32 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
     LHW_SYNC();
     // (f) H = M + S' Af S + diag(limit D) on the arrow pattern (21 + 2*36 + 2*21 items)
+    // every entry is  M_entry + S_row . T_col  (root entries: both feet's T), so the three kinds of entry share ONE instruction
+    // stream on per-item pointers; kind-specific extras (second foot, limit / friction-loss curvature) are small tails
     LHW_LANES(l) {
       for (int it = l; it < 21 + 2 * 6 * NJ + NJ * (NJ + 1); it += 32) {
-        if (it < 21) {
-          int r = 0, t = it;
-          while (t > r) { t -= r + 1; r++; }
-          w.H.r[r][t] = w.M.r[r][t] + dot6(w.S[r], w.T[0][t]) + dot6(w.S[r], w.T[1][t]);
-        } else if (it < 21 + 2 * 6 * NJ) {
-          const int q = it - 21, ch = q / (6 * NJ), rr = q - ch * 6 * NJ, j = rr / NJ, k = rr - j * NJ;
-          w.H.x[ch][j][k] = w.M.x[ch][j][k] + dot6(w.S[6 + ch * NJ + k], w.T[ch][j]);
-        } else {
-          const int q = it - 21 - 2 * 6 * NJ, ch = q / (NJ * (NJ + 1) / 2);
-          int k = 0, t = q - ch * (NJ * (NJ + 1) / 2);
-          while (t > k) { t -= k + 1; k++; }
-          real acc = w.M.c[ch][k][t] + dot6(w.S[6 + ch * NJ + k], w.T[ch][6 + t]);
-          if (k == t && w.lside[ch * NJ + k] && w.ljar[ch * NJ + k] < 0) acc += w.lD[ch * NJ + k];
+        constexpr int NTRI = NJ * (NJ + 1) / 2;
+        const bool root = it < 21, coup = !root && it < 21 + 2 * 6 * NJ;
+        const int q = root ? it : (coup ? it - 21 : it - 21 - 2 * 6 * NJ);
+        const int ch = root ? 0 : (coup ? q / (6 * NJ) : q / NTRI);
+        const int rr = coup ? q - ch * 6 * NJ : q - ch * NTRI;
+        const int row = coup ? rr / NJ : tri_row(rr);                      // root: r ; coupling: root dof j ; chain: k
+        const int col = coup ? rr - row * NJ : rr - row * (row + 1) / 2;    // root: t ; coupling: chain dof k ; chain: t
+        const real* msrc = root ? &w.M.r[row][col] : (coup ? &w.M.x[ch][row][col] : &w.M.c[ch][row][col]);
+        real* dst = root ? &w.H.r[row][col] : (coup ? &w.H.x[ch][row][col] : &w.H.c[ch][row][col]);
+        const real* sp = root ? w.S[row] : w.S[6 + ch * NJ + (coup ? col : row)];
+        const real* tp = root ? w.T[0][col] : w.T[ch][coup ? row : 6 + col];
+        real acc = *msrc + dot6(sp, tp);
+        if (root) acc += dot6(sp, w.T[1][col]);
+        else if (!coup && row == col) {
+          const int u = ch * NJ + row;
+          if (w.lside[u] && w.ljar[u] < 0) acc += w.lD[u];
           if constexpr (FLOSS) {
-            if (k == t) {
-              const real xj = w.fjar[ch * NJ + k], lim = w.flim[ch * NJ + k];
-              if (xj > -lim && xj < lim) acc += w.fD[ch * NJ + k];
-            }
+            const real xj = w.fjar[u], lim = w.flim[u];
+            if (xj > -lim && xj < lim) acc += w.fD[u];
           }
-          w.H.c[ch][k][t] = acc;
         }
+        *dst = acc;
       }
     }
     LHW_SYNC();
