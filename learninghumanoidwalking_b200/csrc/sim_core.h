@@ -494,23 +494,19 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
     LHW_SYNC();
   }
   // Schur complement of the root block and of the root right-hand side
+  // (21 entries of the root block + its 6 right-hand sides: the same 2 NJ-term sum against a different second operand)
   LHW_LANES(l) {
-    if (l < 21) {
-      const int r = tri_row(l), c = l - r * (r + 1) / 2;
-      real acc = H.r[r][c];
+    if (l < 27) {
+      const int r = l < 21 ? tri_row(l) : l - 21, c = l - r * (r + 1) / 2;
+      real* dst = l < 21 ? &H.r[r][c] : x + r;
+      const real* q = l < 21 ? &H.x[0][c][0] : x + 6;     // second operand and its stride from chain 0 to chain 1
+      const int qs = l < 21 ? 6 * NJ : NJ;
+      real acc = *dst;
 #pragma unroll
       for (int ch = 0; ch < 2; ch++)
 #pragma unroll
-        for (int k = 0; k < NJ; k++) acc -= H.x[ch][r][k] * H.x[ch][c][k];
-      H.r[r][c] = acc;
-    } else if (l < 27) {
-      const int r = l - 21;
-      real acc = x[r];
-#pragma unroll
-      for (int ch = 0; ch < 2; ch++)
-#pragma unroll
-        for (int k = 0; k < NJ; k++) acc -= H.x[ch][r][k] * x[6 + ch * NJ + k];
-      x[r] = acc;
+        for (int k = 0; k < NJ; k++) acc -= H.x[ch][r][k] * q[ch * qs + k];
+      *dst = acc;
     }
   }
   LHW_SYNC();
@@ -1241,9 +1237,10 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     LHW_LANES(l) {
       if (l < NV) {
         real g = w.Ma[l] - w.qfs[l];
-        if (l < 6) g -= dot6(w.S[l], w.Ff[0]) + dot6(w.S[l], w.Ff[1]);
+        const real gf = dot6(w.S[l], w.Ff[l < 6 ? 0 : (l - 6) / NJ]);    // one stream for root and chain dofs
+        if (l < 6) g -= gf + dot6(w.S[l], w.Ff[1]);
         else {
-          g -= dot6(w.S[l], w.Ff[(l - 6) / NJ]);
+          g -= gf;
           if (w.lside[l - 6] && w.ljar[l - 6] < 0) g -= w.lside[l - 6] * (-w.lD[l - 6] * w.ljar[l - 6]);
           if constexpr (FLOSS) {
             real cv;
