@@ -38,9 +38,8 @@ SIGMA = 0.223
 # per-launch numbers of the committed ncu captures (profiles/r01_step_kernel_*.md; 4096 envs, the bench's action distribution):
 # (DRAM bytes read + written, warp instructions executed).  Under ncu the state record is L2 resident when the launch starts
 # (no flush between replays), so the DRAM traffic is BELOW the algorithmic bytes; nothing is re-read.
-NCU_PER_LAUNCH_4096 = {("jvrc_walk", 64): (4.708608e6 + 0.109824e6, 828537893), ("jvrc_walk", 32): (2.456576e6 + 0.022528e6, 818458105),
-                       ("h1", 64): (6.823168e6 + 0.372992e6, 919081053), ("jvrc_step", 64): (7.490816e6 + 0.552192e6, 1317958630),
-                       ("jvrc_walk_terrain", 64): (7.512576e6 + 0.578816e6, 1024153088)}
+NCU_PER_LAUNCH_4096 = {("jvrc_walk", 64): (4.712192e6 + 0.103424e6, 761598198), ("jvrc_walk", 32): (2.526976e6 + 0.082432e6, 709974877),
+                       ("jvrc_step", 64): (7.463424e6 + 0.455168e6, 1238509046)}   # end-of-round captures (profiles/*_end_of_round.md)
 ALG_BYTES = {32: 1220, 64: 2288}   # state read+write, action read, obs/reward/done write
 
 

@@ -843,15 +843,15 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     if (l < NV) {
       real f[6];
       inert_mul(w.comp[dof_link<NJ>(l)], w.S[l], f);
-      const int ch = l < 6 ? 0 : (l - 6) / NJ, k = l - 6 - ch * NJ;
-      // column of the root motion vectors: one stream for root rows (symmetric root block) and chain rows (coupling block)
+      if (l < 6) {
 #pragma unroll
-      for (int j = 0; j < 6; j++) {
-        const real v = dot6(w.S[j], f);
-        if (l >= 6) w.M.x[ch][j][k] = v;
-        else if (j <= l) { w.M.r[l][j] = v; w.M.r[j][l] = v; }
-      }
-      if (l >= 6) {
+        for (int j = 0; j < 6; j++)
+          if (j <= l) {
+            const real v = dot6(w.S[j], f);
+            w.M.r[l][j] = v; w.M.r[j][l] = v;
+          }
+      } else {
+        const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ;
 #pragma unroll
         for (int kk = 0; kk < NJ; kk++)
           if (kk <= k) {
@@ -859,6 +859,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
             if (kk == k) v += m.armature[l];
             w.M.c[ch][k][kk] = v; w.M.c[ch][kk][k] = v;
           }
+#pragma unroll
+        for (int j = 0; j < 6; j++) w.M.x[ch][j][k] = dot6(w.S[j], f);
       }
     } else if (l >= 20) {
       const int ch = (l - 20) / 6, e = (l - 20) - ch * 6;
@@ -1297,32 +1299,29 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
     LHW_SYNC();
     // (f) H = M + S' Af S + diag(limit D) on the arrow pattern (21 + 2*36 + 2*21 items)
-    // every entry is  M_entry + S_row . T_col  (root entries: both feet's T), so the three kinds of entry share ONE instruction
-    // stream on per-item pointers; kind-specific extras (second foot, limit / friction-loss curvature) are small tails
+    // (21 root + 2 x 6 NJ coupling + 2 x NJ(NJ+1)/2 chain items; a pass of 32 lanes is almost always of ONE kind, so per-kind
+    // branches cost nothing here -- a single stream on per-item pointers was measured 12 % MORE instructions for this phase)
     LHW_LANES(l) {
       for (int it = l; it < 21 + 2 * 6 * NJ + NJ * (NJ + 1); it += 32) {
-        constexpr int NTRI = NJ * (NJ + 1) / 2;
-        const bool root = it < 21, coup = !root && it < 21 + 2 * 6 * NJ;
-        const int q = root ? it : (coup ? it - 21 : it - 21 - 2 * 6 * NJ);
-        const int ch = root ? 0 : (coup ? q / (6 * NJ) : q / NTRI);
-        const int rr = coup ? q - ch * 6 * NJ : q - ch * NTRI;
-        const int row = coup ? rr / NJ : tri_row(rr);                      // root: r ; coupling: root dof j ; chain: k
-        const int col = coup ? rr - row * NJ : rr - row * (row + 1) / 2;    // root: t ; coupling: chain dof k ; chain: t
-        const real* msrc = root ? &w.M.r[row][col] : (coup ? &w.M.x[ch][row][col] : &w.M.c[ch][row][col]);
-        real* dst = root ? &w.H.r[row][col] : (coup ? &w.H.x[ch][row][col] : &w.H.c[ch][row][col]);
-        const real* sp = root ? w.S[row] : w.S[6 + ch * NJ + (coup ? col : row)];
-        const real* tp = root ? w.T[0][col] : w.T[ch][coup ? row : 6 + col];
-        real acc = *msrc + dot6(sp, tp);
-        if (root) acc += dot6(sp, w.T[1][col]);
-        else if (!coup && row == col) {
-          const int u = ch * NJ + row;
-          if (w.lside[u] && w.ljar[u] < 0) acc += w.lD[u];
+        if (it < 21) {
+          const int r = tri_row(it), t = it - r * (r + 1) / 2;
+          w.H.r[r][t] = w.M.r[r][t] + dot6(w.S[r], w.T[0][t]) + dot6(w.S[r], w.T[1][t]);
+        } else if (it < 21 + 2 * 6 * NJ) {
+          const int q = it - 21, ch = q / (6 * NJ), rr = q - ch * 6 * NJ, j = rr / NJ, k = rr - j * NJ;
+          w.H.x[ch][j][k] = w.M.x[ch][j][k] + dot6(w.S[6 + ch * NJ + k], w.T[ch][j]);
+        } else {
+          const int q = it - 21 - 2 * 6 * NJ, ch = q / (NJ * (NJ + 1) / 2), rr = q - ch * (NJ * (NJ + 1) / 2);
+          const int k = tri_row(rr), t = rr - k * (k + 1) / 2;
+          real acc = w.M.c[ch][k][t] + dot6(w.S[6 + ch * NJ + k], w.T[ch][6 + t]);
+          if (k == t && w.lside[ch * NJ + k] && w.ljar[ch * NJ + k] < 0) acc += w.lD[ch * NJ + k];
           if constexpr (FLOSS) {
-            const real xj = w.fjar[u], lim = w.flim[u];
-            if (xj > -lim && xj < lim) acc += w.fD[u];
+            if (k == t) {
+              const real xj = w.fjar[ch * NJ + k], lim = w.flim[ch * NJ + k];
+              if (xj > -lim && xj < lim) acc += w.fD[ch * NJ + k];
+            }
           }
+          w.H.c[ch][k][t] = acc;
         }
-        *dst = acc;
       }
     }
     LHW_SYNC();
