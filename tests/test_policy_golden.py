@@ -54,3 +54,26 @@ def test_clock_mirror_is_the_reference_formula():
     for i in (29, 30):
         ref[:, i] = torch.sin(torch.arcsin(ref[:, i]) + np.pi)
     assert (env.mirror_clock_observation(obs) - ref).abs().max() < 1e-6
+
+
+def test_folded_clock_mirror_matrix_is_bit_identical_to_matmul_then_negate():
+    """SymmetricEnv folds the clock negation into the mirror matrix (one GEMM, no index kernels, capturable in a CUDA graph):
+    every column of P has a single +-1, so obs @ (P diag(s)) equals (obs @ P) with the clock columns negated, bit for bit."""
+    from learninghumanoidwalking_b200.rl.symmetric import SymmetricEnv
+    env = SymmetricEnv(lambda: object(), mirrored_obs=G["mirrored_obs"], mirrored_act=G["mirrored_act"], clock_inds=[29, 30])
+    obs = torch.randn(64, 37)
+    ref = obs @ env.obs_mirror_matrix
+    ref[:, [29, 30]] = -ref[:, [29, 30]]
+    assert torch.equal(env.mirror_clock_observation(obs), ref)
+    assert torch.equal(env.mirror_observation(obs), obs @ env.obs_mirror_matrix)
+    a = torch.randn(5, 12)
+    assert torch.equal(env.mirror_action(env.mirror_action(a)), a)            # an involution
+    assert env._on("obs_mirror_matrix", "cpu") is env._on("obs_mirror_matrix", "cpu")   # uploaded once, then cached
+
+
+def test_height_curriculum_formula():
+    """tasks/stepping_task.py:312: h = clip((iteration_count - 3000) / 8000, 0, 1) * 0.1, iteration_count = inf by default."""
+    from learninghumanoidwalking_b200.model.loader import curriculum_height
+    for it, h in ((0, 0.0), (3000, 0.0), (3800, 0.01), (7000, 0.05), (11000, 0.1), (10 ** 9, 0.1), (float("inf"), 0.1)):
+        assert abs(curriculum_height(it) - h) < 1e-15
+        assert curriculum_height(it) == float(np.clip((it - 3000) / 8000, 0, 1) * 0.1)
