@@ -364,3 +364,51 @@ def test_slab_contact_set_against_an_independent_polygon_clip(orc):
             n_corner += sum(inside)
             n_cross += len(crossings)
     assert n_cross > 40 and n_corner > 100      # both kinds of vertices were exercised
+
+
+def test_newton_and_dual_pgs_agree_on_stepping_stone_contacts():
+    """The stepping-stone rows (corner contacts on a slab, sole-edge crossings at its boundary, stacked coplanar supports) go
+    through the oracle's two independent solvers — primal Newton with exact line search and dual projected Gauss-Seidel on
+    J M^-1 J' + R — and give the same constrained acceleration: the rows are well-posed constraints, not solver artefacts."""
+    newton = Oracle("jvrc_step", tolerance=1e-14, solver=0)
+    pgs = Oracle("jvrc_step", tolerance=1e-14, solver=1, iterations=100)
+    rng = np.random.RandomState(11)
+    seen_rows = set()
+    for layout, mode in (([[0.12, 0, 0, 0.05]], 4),                               # fully on one slab, no floor
+                         ([[0.0, 0, 0, 0.0]], 4),                                 # slab ends under the feet: crossings
+                         ([[0.12, 0, 0, 0.05], [0.12, 0.2, 0, -0.05]], 1)):       # floor + two coplanar slabs: multiplicity 3
+        q = np.array(newton.mj["cfg"]["nominal_qpos"])
+        q[2] = 0.797                         # every sole corner a few mm inside the supporting surface
+        q[3:7] += rng.normal(size=4) * 0.003
+        q[3:7] /= np.linalg.norm(q[3:7])
+        q[7:] += rng.uniform(-0.01, 0.01, 12)
+        v = rng.normal(size=18) * 0.2
+        accs = []
+        for o in (newton, pgs):
+            envs = o.make_envs(1)
+            o.set_field(envs, 0, "qpos", q); o.set_field(envs, 0, "qvel", v)
+            seq = np.tile([0.0, 0.0, -1.0, 0.0], (20, 1)); seq[:len(layout)] = layout
+            o.set_field(envs, 0, "seq", seq.reshape(-1)); o.set_field(envs, 0, "mode", mode)
+            o.mj_step(envs, 0, np.zeros(12))
+            n = int(o.field(envs, 0, "ncon")[0])
+            assert 0 < n <= 34                       # <= 160 rows: inside the dual solver's table
+            assert o.field(envs, 0, "last_kkt_residual")[0] < 1e-6
+            accs.append(o.field(envs, 0, "qacc"))
+            seen_rows.add(n)
+        assert np.abs(accs[0] - accs[1]).max() < 1e-6 * max(1.0, np.abs(accs[0]).max())
+    assert len(seen_rows) >= 3 and max(seen_rows) >= 20, seen_rows
+
+
+def test_fp32_kernel_source_tracks_oracle_on_stepping_stones_for_a_short_horizon():
+    o = Oracle("jvrc_step", tolerance=1e-14)
+    N = 4
+    e = Emu(pack_model(load_model("jvrc_step"), tolerance=1e-6), 32, N, seed=1)
+    envs = o.make_envs(N, seed=1)
+    assert np.abs(o.batch_reset(envs, N) - e.reset()).max() < 1e-5
+    std = np.concatenate(([0.2, 0.2, 1, 1, 1], 0.5 * np.ones(12), 4 * np.ones(12), [1, 1], np.ones(8)))
+    for _ in range(8):
+        a = np.zeros((N, 12))
+        oo, _, _, rr, dd, ee = o.batch_step(envs, N, a)
+        eo, _, _, er, ed, een, _, _ = e.step(a)
+        assert (ee == een).all()
+        assert (np.abs(oo - eo) / std).max() < 5e-3 and np.abs(rr - er).max() < 5e-3
