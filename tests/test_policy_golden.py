@@ -77,3 +77,13 @@ def test_height_curriculum_formula():
     for it, h in ((0, 0.0), (3000, 0.0), (3800, 0.01), (7000, 0.05), (11000, 0.1), (10 ** 9, 0.1), (float("inf"), 0.1)):
         assert abs(curriculum_height(it) - h) < 1e-15
         assert curriculum_height(it) == float(np.clip((it - 3000) / 8000, 0, 1) * 0.1)
+
+
+def test_worker_seed_formula_matches_reference():
+    """rl/utils/seeding.py:34-52 run from the reference's file (tests/golden/seeding.json)."""
+    from learninghumanoidwalking_b200.rl.ppo import get_worker_seed
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "seeding.json")))
+    assert len(cases) == 72
+    for c in cases:
+        assert get_worker_seed(c["master_seed"], c["worker_id"], c["offset"]) == c["seed"]
+    assert len({c["seed"] for c in cases if c["master_seed"] == 12345}) == 12     # collision-free on the grid

@@ -141,5 +141,15 @@ def main():
     print("golden vectors written to", os.path.abspath(OUT))
 
 
+def seeding_vectors():
+    """rl/utils/seeding.py:get_worker_seed (the rank plays the worker's role in this build) on a grid of arguments."""
+    seeding = load_by_path("ref_seeding", "rl/utils/seeding.py")
+    grid = [(m, w, o) for m in (0, 1, 7, 12345, 2 ** 31 - 1, 4294967295) for w in (0, 1, 7, 255) for o in (0, 1, 3)]
+    out = [dict(master_seed=m, worker_id=w, offset=o, seed=int(seeding.get_worker_seed(m, w, o))) for m, w, o in grid]
+    json.dump(out, open(os.path.join(OUT, "seeding.json"), "w"))
+    return out
+
+
 if __name__ == "__main__":
     main()
+    seeding_vectors()
