@@ -70,3 +70,18 @@ def test_update_actor_critic_matches_the_reference_method():
             assert abs(float(p.double().sum()) - d["sum"]) < 1e-4 * max(1.0, d["abs"] * 1e-2)
             assert abs(float(p.double().abs().sum()) - d["abs"]) < 1e-5 * max(1.0, d["abs"])
             assert np.abs(p.detach().reshape(-1)[:8].double().numpy() - np.array(d["head"])).max() < 2e-6
+
+
+def test_minibatch_indices_are_the_reference_sampler():
+    """rl/algos/ppo.py:504-517: SubsetRandomSampler(range(n), generator seeded seed + itr * epochs + epoch) under
+    BatchSampler(drop_last=True).  PPO.minibatch_indices draws the same permutation in one call."""
+    from torch.utils.data.sampler import BatchSampler, SubsetRandomSampler
+    from learninghumanoidwalking_b200.rl.ppo import PPO
+    ppo = PPO.__new__(PPO)
+    ppo.__dict__.update(seed=11, epochs=3, minibatch_size=64, device=torch.device("cpu"))
+    for itr, epoch, n in ((0, 0, 1000), (5, 2, 777), (40, 1, 64), (3, 0, 63)):
+        g = torch.Generator()
+        g.manual_seed(11 + itr * 3 + epoch)
+        ref = [list(b) for b in BatchSampler(SubsetRandomSampler(range(n), generator=g), 64, drop_last=True)]
+        got = ppo.minibatch_indices(n, itr, epoch)
+        assert got.shape == (n // 64, 64) and got.tolist() == ref
