@@ -122,3 +122,36 @@ def test_compiled_model_is_reproducible_from_reference():
     for a, b in zip(fresh["links"], stored["links"]):
         assert a["name"] == b["name"] and np.allclose(a["inertia"], b["inertia"]) and np.allclose(a["com"], b["com"])
     assert np.allclose(fresh["dof_invweight0"], stored["dof_invweight0"])
+
+
+def test_rollout_bootstrap_semantics_match_the_reference_worker():
+    """tests/golden/rollout_worker.json = the reference's RolloutWorker.sample run on a scripted env for three consecutive
+    calls (tools/gen_golden_rollout.py).  The oracle's time-major GAE (ppo_oracle.gae_rollout: what the CUDA GAE kernel and the
+    device rollout worker are tested against) must give the reference's returns from the same per-step rewards / values /
+    episode-end flags with boot = (not done) * critic(pre-reset next state) and the open tail closed by critic(current state)."""
+    import torch
+    from oracle.ppo_oracle import gae_rollout
+    Gr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rollout_worker.json")))
+    W, b = torch.tensor(Gr["critic_w"], dtype=torch.float32), Gr["critic_b"]
+    V = lambda s: float((torch.tensor(s, dtype=torch.float32) @ W + b).reshape(-1)[0])
+    T, carried = Gr["T"], 0
+    for call in Gr["calls"]:
+        ended = np.array(call["dones"]).astype(bool)
+        done = np.array(call["env_done"])
+        assert (ended >= done).all()                                  # every true termination ends the episode ...
+        boot = np.array([(0.0 if done[t] else V(call["next_obs"][t])) if ended[t] else 0.0 for t in range(T)])
+        last_val = V(call["open_state"]) if call["open_state"] is not None else 0.0
+        assert (call["open_state"] is None) == bool(ended[-1])
+        ret = gae_rollout(np.array(call["rewards"])[:, None], np.array(call["values"])[:, None], ended[:, None], boot[:, None],
+                          np.array([last_val]), Gr["gamma"], Gr["lam"])[:, 0]
+        assert np.abs(ret - np.array(call["returns"])).max() < 1e-6
+        # ... and truncation at max_traj_len does too; episode lengths carry over between calls; only completed episodes report
+        lens, run = [], carried
+        for t in range(T):
+            run += 1
+            if ended[t]:
+                assert done[t] or run == Gr["max_traj_len"]
+                lens.append(run)
+                run = 0
+        carried = run
+        assert lens == call["ep_lens"] and len(call["ep_rewards"]) == len(lens)
