@@ -32,7 +32,13 @@ def test_train_then_eval(tmp_path, env_name, obs_dim, act_dim, capsys):
     actor = torch.load(runs[0] / "actor_1.pt", weights_only=False)
     assert actor(torch.zeros(3, obs_dim, device="cuda")).shape == (3, act_dim)
     assert rx.get_latest_actor(runs[0]).name == "actor_1.pt"
-    capsys.readouterr()
+    train_out = capsys.readouterr().out
+    # the stdout lines scripts/benchmark_training.py:75-79 parses ARE the reference's metric definition
+    import re
+    for pat in (r"\*+ Iteration (\d+) \*+", r"Sampling took ([\d.]+)s for (\d+) steps", r"\|\s+Mean Eprew\s+\|\s+([\d.e+-]+)\s+\|",
+                r"\|\s+Mean Eplen\s+\|\s+([\d.e+-]+)\s+\|", r"Total time elapsed: ([\d.]+)s.*fps=([\d.]+)"):
+        assert re.search(pat, train_out), pat
+    assert re.search(r"Sampling took [\d.]+s for (\d+) steps", train_out).group(1) == str(64 * 40)
     episodes = rx.main(["eval", "--logdir", str(tmp_path), "--ep-len", "2"]) or []
     out = capsys.readouterr().out
     assert "episode(s) in 80 control steps" in out and "mean" in out
