@@ -85,6 +85,11 @@ class BatchedHumanoidEnv:
         self.action_space = np.zeros(self.act_dim)
         self.observation_space = np.zeros(self.obs_dim * self.history_len)
         self.nq, self.nv = 7 + self.act_dim, 6 + self.act_dim
+        self._setup_reference_attributes(model, cfg)
+
+    def _setup_reference_attributes(self, model: str, cfg: dict) -> None:
+        """obs_mean / obs_std, reward names and the robot's mirror lists exactly as the reference env classes set them
+        (pure numpy; pinned to the reference's own method bodies by tests/golden/env_attributes.json)."""
         if model == "h1":
             # envs/h1/h1_env.py:37-55 (normalisation), envs/h1/h1_base.py:66-76 ; no mirror lists on the H1 robot
             self.reward_names = STAND_REWARD_NAMES

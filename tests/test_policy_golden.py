@@ -87,3 +87,24 @@ def test_worker_seed_formula_matches_reference():
     for c in cases:
         assert get_worker_seed(c["master_seed"], c["worker_id"], c["offset"]) == c["seed"]
     assert len({c["seed"] for c in cases if c["master_seed"] == 12345}) == 12     # collision-free on the grid
+
+
+def test_env_attributes_match_the_reference_env_classes():
+    """obs_mean / obs_std and the mirror index lists of BatchedHumanoidEnv against the reference's own method bodies, lifted out of
+    envs/jvrc/jvrc_walk.py, jvrc_step.py, jvrc_base.py and envs/h1/h1_env.py and executed (tools/gen_golden_env_attrs.py)."""
+    from learninghumanoidwalking_b200.envs.batched_env import BatchedHumanoidEnv
+    from learninghumanoidwalking_b200.model import load_model
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "env_attributes.json")))
+    for model, key in (("jvrc_walk", "jvrc_walk"), ("jvrc_step", "jvrc_step"), ("h1", "h1"), ("jvrc_walk_terrain", "jvrc_walk")):
+        env = BatchedHumanoidEnv.__new__(BatchedHumanoidEnv)      # attribute setup only: no CUDA, no library handle
+        env._iteration_count = float("inf")
+        env._setup_reference_attributes(model, load_model(model)["cfg"])
+        r = ref[key]
+        assert np.array_equal(env.obs_mean, np.array(r["obs_mean"])) and np.array_equal(env.obs_std, np.array(r["obs_std"]))
+        if key != "h1":
+            assert [float(x) for x in env.robot.mirrored_obs] == r["mirrored_obs"]
+            assert [float(x) for x in env.robot.mirrored_acts] == r["mirrored_acts"]
+            assert list(env.robot.clock_inds) == r["clock_inds"]
+            assert env.robot.iteration_count == float("inf")                 # robots/robot_base.py:35
+        else:
+            assert not hasattr(env.robot, "mirrored_obs")
