@@ -155,3 +155,68 @@ def test_rollout_bootstrap_semantics_match_the_reference_worker():
                 run = 0
         carried = run
         assert lens == call["ep_lens"] and len(call["ep_rewards"]) == len(lens)
+
+
+def test_walking_task_matches_the_reference_class():
+    """WalkingTask.reset / step / calc_reward / done (tasks/walking_task.py:85-205) run from the reference's own file on recorded
+    inputs (tools/gen_golden_walk_task.py), its numpy RNG fed with the Philox words the oracle draws for the same event key.  The
+    terrain extension's re-pose event is checked against the reference's manip_hfield hook (:172-179) the same way: same third
+    `randint(200)` decision, same three uniforms in the same order (the shipped terrain model lists the z range sorted; the hook's
+    call has it as (-0.015, -0.035), which is what this test passes so that the same uniform maps to the same offset)."""
+    import copy
+    from oracle.oracle import Oracle, load_model_json
+    cases = gold("walk_task.json")
+    o = Oracle("jvrc_walk", tolerance=1e-14)
+    tm = copy.deepcopy(load_model_json("jvrc_walk_terrain"))
+    assert sorted((tm["terrain"]["z_lo"], tm["terrain"]["z_hi"])) == [-0.035, -0.015] and tm["terrain"]["xy"] == 0.5
+    assert tm["terrain"]["interval"] == 200
+    tm["terrain"].update(z_lo=-0.015, z_hi=-0.035, bump=0.0)
+    ot = Oracle(model_dict=tm, tolerance=1e-14)
+    cfg = o.mj["cfg"]
+    assert cases[0]["names"] == ["foot_frc_score", "foot_vel_score", "root_accel", "height_error", "com_vel_error", "yaw_vel_error",
+                                 "upper_body_reward", "posture_error", "torque_penalty", "action_penalty"]
+    seen_modes, n_switch, n_hook, n_done = set(), 0, 0, 0
+    for c in cases:
+        envs, envt = o.make_envs(1, seed=c["seed"], first_id=c["env_id"]), ot.make_envs(1, seed=c["seed"], first_id=c["env_id"])
+        for oo, ee in ((o, envs), (ot, envt)):
+            oo.set_field(ee, 0, "rng_ctr", c["reset_ctr"])
+            oo.task_reset(ee, 0)
+            assert int(oo.field(ee, 0, "mode")[0]) == c["mode"] and int(oo.field(ee, 0, "phase")[0]) == c["phase"]
+            assert np.abs(oo.field(ee, 0, "mode_ref") - np.array(c["mode_ref"])).max() < 1e-15
+        assert c["period"] == round(2 * cfg["task"]["total_duration"] / cfg["control_dt"])
+        seen_modes.add(c["mode"])
+        for s in c["steps"]:
+            seq_before = ot.field(envt, 0, "seq").reshape(20, 4).copy()
+            for oo, ee in ((o, envs), (ot, envt)):
+                oo.set_field(ee, 0, "mode", s["pre"]["mode"]); oo.set_field(ee, 0, "mode_ref", s["pre"]["mode_ref"])
+                oo.set_field(ee, 0, "phase", s["pre"]["phase"]); oo.set_field(ee, 0, "rng_ctr", s["ctr"])
+                oo.task_step(ee, 0)
+                assert int(oo.field(ee, 0, "mode")[0]) == s["mode"] and int(oo.field(ee, 0, "phase")[0]) == s["phase"], s["kind"]
+                assert np.abs(oo.field(ee, 0, "mode_ref") - np.array(s["mode_ref"])).max() < 1e-15
+            n_switch += s["mode"] != s["pre"]["mode"]
+            seq = ot.field(envt, 0, "seq").reshape(20, 4)
+            if s["kind"] == "hook":
+                hp = np.array(s["hfield_pos"])
+                assert np.abs(seq[:, 0] - (hp[0] + (np.arange(20) - 4) * tm["terrain"]["pitch"])).max() < 1e-15
+                assert np.abs(seq[:, 1] - hp[1]).max() < 1e-15 and np.abs(seq[:, 2] - hp[2]).max() < 1e-15
+                assert -0.5 <= hp[0] <= 0.5 and -0.035 <= hp[2] <= -0.015
+                n_hook += 1
+            else:
+                assert (seq == seq_before).all()
+            st = s["state"]
+            o.set_field(envs, 0, "root_xmat", np.eye(3).reshape(-1))    # get_body_vel(root, frame=1) is already root-local
+            o.set_field(envs, 0, "root_vlin", st["root_vloc"])
+            o.set_field(envs, 0, "root_xpos", st["root"]); o.set_field(envs, 0, "head_xpos", st["head"])
+            o.set_field(envs, 0, "qvel", st["qvel"]); o.set_field(envs, 0, "qacc", st["qacc"])
+            o.set_field(envs, 0, "lfoot_grf", st["lgrf"]); o.set_field(envs, 0, "rfoot_grf", st["rgrf"])
+            o.set_field(envs, 0, "lfoot_vel", st["lvel"]); o.set_field(envs, 0, "rfoot_vel", st["rvel"])
+            o.set_field(envs, 0, "ncon_r", s["ncon_r"]); o.set_field(envs, 0, "ncon_l", s["ncon_l"])
+            o.set_field(envs, 0, "contact_z_min", s["contact_z_min"])
+            o.set_field(envs, 0, "act_len", st["pose"]); o.set_field(envs, 0, "act_force", st["torque"])
+            o.set_field(envs, 0, "prev_torque", s["prev_torque"]); o.set_field(envs, 0, "prev_action", s["prev_action"])
+            t = o.calc_reward(envs, 0, s["action"])
+            assert np.abs(t - np.array(s["terms"])).max() < 1e-13, (s["kind"], t - np.array(s["terms"]))
+            z = st["qpos"][2]
+            assert ((z < 0.6) or (z > 1.4) or st["selfcol"]) == s["done"]    # the bounds oracle.pack_model / model.loader pack
+            n_done += s["done"]
+    assert seen_modes == {0, 1, 2} and n_switch >= 30 and n_hook >= 15 and 5 <= n_done < 80
