@@ -18,7 +18,6 @@ import time
 from copy import deepcopy
 from pathlib import Path
 
-import numpy as np
 import torch
 import torch.distributed as dist
 from torch.nn import functional as F

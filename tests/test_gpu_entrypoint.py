@@ -1,7 +1,6 @@
 """run_experiment.py (the reference's entry point, run_experiment.py:105-330) on the device path: `train` writes the
 reference's artefacts, `eval` finds and rolls out the latest actor."""
 import pickle
-import sys
 
 import pytest
 import torch

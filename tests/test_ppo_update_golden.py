@@ -6,7 +6,6 @@ CUDA-only in this build (fused clip+Adam, the graph replay) is compared with THI
 import json
 import os
 from copy import deepcopy
-from types import SimpleNamespace
 
 import numpy as np
 import torch

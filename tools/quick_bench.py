@@ -2,7 +2,6 @@
 """Quick device-resident step-kernel timing sweep (development tool; bench.py is the contract)."""
 import os
 import sys
-import time
 
 import torch
 
