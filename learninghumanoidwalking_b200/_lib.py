@@ -6,7 +6,9 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "liblhw_b200.so")
+# LHW_B200_LIB points the binding at another build of the same library (tools/ab_variants.py times candidate kernels that way);
+# it is still a CUDA build of include/lhw_b200.h and still mandatory
+LIB_PATH = os.environ.get("LHW_B200_LIB") or os.path.join(_PKG, "liblhw_b200.so")
 
 c_void_p, c_int, c_uint32, c_float, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_float, ctypes.c_longlong
 

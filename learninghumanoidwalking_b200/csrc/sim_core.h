@@ -30,6 +30,13 @@
 #include <math.h>
 #include <stdint.h>
 
+// Candidate rewrites that have passed the CPU tier (kernel-source emulation vs oracle) but have not been timed on a B200 yet
+// are compiled in with -DLHW_X_<name>=1 (tools/ab_variants.py builds and times one library per flag); default = the measured
+// kernel.  LHW_X_CF: lane-role operand selection by integer offsets and deferred pivot checks instead of branches.
+#ifndef LHW_X_CF
+#define LHW_X_CF 0
+#endif
+
 #if defined(__CUDACC__) && !defined(LHW_CPU_EMU)
 #define LHW_DEV __device__ __forceinline__
 #define LHW_DEVNI __device__ __noinline__
@@ -471,12 +478,24 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
   // column steps of both chains side by side.  lane = chain * 16 + row; rows 0..NJ-1: the chain block, NJ..NJ+5: the coupling
   // rows (X = B L^-T), NJ+6: the right-hand side (forward substitution).  All three kinds of row do the SAME arithmetic on
   // their own row pointer, so the step is one branch-free instruction stream (a per-kind if/else would run three times)
+#if LHW_X_CF
+  // the three kinds of row live at three places of the same Work record: the lane's row is a word offset from &H.c[0][0][0],
+  // chosen with integer selects (the pointer-valued ?: compiled to a jump table per column step), and a failed pivot is
+  // only replaced here; it is reported once, from the stored reciprocal pivots, after the factorisation
+  real* const hc0 = &H.c[0][0][0];
+  const int ox = (int)(&H.x[0][0][0] - hc0), ob = (int)(x - hc0);
+#endif
 #pragma unroll
   for (int k = 0; k < NJ; k++) {
     LHW_LANES(l) {
       const int ch = l >> 4, r = l & 15;
       if (r < NJ + 7 && (r >= NJ || r >= k)) {
+#if LHW_X_CF
+        const int o_c = (ch * NJ + r) * NJ, o_x = ox + (ch * 6 + r - NJ) * NJ, o_b = ob + 6 + ch * NJ;
+        real* pr = hc0 + (r < NJ ? o_c : (r < NJ + 6 ? o_x : o_b));
+#else
         real* pr = r < NJ ? H.c[ch][r] : (r < NJ + 6 ? H.x[ch][r - NJ] : x + 6 + ch * NJ);
+#endif
         const real* pk = H.c[ch][k];
         real dk = pk[k], t = pr[k];
 #pragma unroll
@@ -485,7 +504,11 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
           dk -= pkm * pkm;
           t -= pr[mm] * pkm;
         }
+#if LHW_X_CF
+        dk = dk > 0 ? dk : (real)1e-30;
+#else
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
+#endif
         const real inv = m_rsqrt(dk);
         if (r == k) w.hdinv[6 + ch * NJ + k] = inv;
         else pr[k] = t * inv;
@@ -514,7 +537,11 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
   for (int k = 0; k < 6; k++) {
     LHW_LANES(l) {
       if (l < 7 && l >= k) {   // rows 0..5 of the Schur complement, row 6 = the root right-hand side: same arithmetic
+#if LHW_X_CF
+        real* pr = hc0 + (l < 6 ? (int)(&H.r[0][0] - hc0) + 6 * l : ob);
+#else
         real* pr = l < 6 ? H.r[l] : x;
+#endif
         const real* pk = H.r[k];
         real dk = pk[k], t = pr[k];
 #pragma unroll
@@ -523,7 +550,11 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
           dk -= pkm * pkm;
           t -= pr[mm] * pkm;
         }
+#if LHW_X_CF
+        dk = dk > 0 ? dk : (real)1e-30;
+#else
         if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
+#endif
         const real inv = m_rsqrt(dk);
         if (l == k) w.hdinv[k] = inv;
         else pr[k] = t * inv;
@@ -555,6 +586,9 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
       for (int r = 0; r < 6; r++) t -= H.x[ch][r][k] * x[r];
       x[6 + ch * NJ + k] = t;
     }
+#if LHW_X_CF
+    if (l < 6 + 2 * NJ && w.hdinv[l] >= m_rsqrt((real)1e-30)) w.status |= 2;   // a pivot was not positive (or NaN)
+#endif
   }
   LHW_SYNC();
   LHW_LANES(l) {

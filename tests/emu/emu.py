@@ -7,7 +7,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LIB = os.path.join(HERE, "_build", "libsim_emu.so")
+# LHW_EMU_DEFINES="LHW_X_CF=1 ..." builds (and loads) the emulation of a candidate kernel variant instead (see sim_core.h)
+DEFINES = os.environ.get("LHW_EMU_DEFINES", "").split()
+LIB = os.path.join(HERE, "_build", "libsim_emu" + "".join("." + d.replace("=", "_") for d in DEFINES) + ".so")
 NREW, NSTATE_I = 10, 8
 
 
@@ -16,7 +18,7 @@ def build():
             os.path.join(ROOT, "learninghumanoidwalking_b200", "csrc", "model_pack.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", LIB, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17"] + ["-D" + d for d in DEFINES] + ["-o", LIB, srcs[0]])
     return LIB
 
 

@@ -2,6 +2,7 @@
 sequentially (tests/emu/, test harness only) against the oracle: the same arithmetic the GPU executes,
 checked on the CPU tier.  The GPU tier (test_gpu_parity.py) repeats this through the C-ABI on the device."""
 import numpy as np
+import pytest
 
 from emu import Emu
 from learninghumanoidwalking_b200.model import load_model, pack_model
@@ -98,3 +99,45 @@ def test_self_collision_proxies_terminate_when_legs_cross(oracle_tight):
             z = o.field(envs, 0, "qpos")[2]
             break
     assert hit is not None and sc == 1 and 0.6 < z < 1.4, (hit, sc, z)
+
+
+@pytest.mark.parametrize("poison", ["nan", "nan_pose", "runaway"])
+def test_diverged_environment_is_flagged_terminated_and_reset_without_touching_its_neighbours(oracle_tight, poison):
+    """The build's counterpart of MuJoCo's mj_checkAcc auto-reset (SURVEY §8b, C-ABI row): an environment whose state has gone
+    non-finite (a NaN velocity -> the factorisation sees a non-positive pivot) or runaway (|qacc| > 1e10) gets a status word,
+    terminates on that control step and comes back from the auto-reset with a finite observation; oracle and kernel source
+    agree on which step that is, and the other environments of the batch are bit-identical to an unpoisoned run."""
+    o = oracle_tight
+    N, BAD = 3, 1
+    flat = pack_model(load_model(), tolerance=1e-14)
+    e, clean = Emu(flat, 64, N, seed=9, first_id=4), Emu(flat, 64, N, seed=9, first_id=4)
+    envs = o.make_envs(N, seed=9, first_id=4)
+    o.batch_reset(envs, N); e.reset(); clean.reset()
+    rng = np.random.RandomState(3)
+    for _ in range(3):
+        a = rng.normal(size=(N, 12)) * 0.2
+        o.batch_step(envs, N, a); e.step(a); clean.step(a)
+    qp, qv = o.field(envs, BAD, "qpos"), o.field(envs, BAD, "qvel")
+    if poison == "nan":
+        qv[7] = np.nan
+    elif poison == "nan_pose":
+        qp[9] = np.nan                                           # a NaN joint angle: the mass matrix itself is NaN (pivot check)
+    else:
+        qv[6:] = 1e13
+    o.set_field(envs, BAD, "qpos", qp); o.set_field(envs, BAD, "qvel", qv)
+    e.sr[BAD, :19], e.sr[BAD, 19:19 + 18] = qp, qv               # record layout: [qpos 19 | qvel 18 | ...]
+    a = rng.normal(size=(N, 12)) * 0.2
+    oo, to, tt, rr, dd, ee = o.batch_step(envs, N, a)
+    eo, et, etm, er, ed, een, eplen, eprew = e.step(a)
+    co = clean.step(a)
+    assert dd[BAD] == 1 and ee[BAD] == 1 and ed[BAD] == 1 and een[BAD] == 1
+    assert np.isfinite(eo).all() and np.isfinite(oo).all()        # the observation returned is the fresh episode's
+    assert np.abs(eo[BAD] - oo[BAD]).max() < 1e-12
+    assert e.si[BAD, 6] == 0 and e.si[BAD, 2] == 0                # status cleared, traj_len restarted
+    keep = [i for i in range(N) if i != BAD]
+    assert (eo[keep] == co[0][keep]).all() and (er[keep] == co[3][keep]).all() and (e.sr[keep] == clean.sr[keep]).all()
+    for _ in range(3):                                           # and the batch carries on in step with the oracle
+        a = rng.normal(size=(N, 12)) * 0.2
+        oo, _, _, rr, dd, ee = o.batch_step(envs, N, a)
+        eo, _, _, er, ed, een, _, _ = e.step(a)
+        assert (dd == ed).all() and (ee == een).all() and np.abs(oo - eo).max() < 1e-9
