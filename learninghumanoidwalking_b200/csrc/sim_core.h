@@ -36,6 +36,10 @@
 #ifndef LHW_X_CF
 #define LHW_X_CF 0
 #endif
+// LHW_X_RSQ: the single-precision seed of the fp64 reciprocal square root as the bare MUFU instruction.
+#ifndef LHW_X_RSQ
+#define LHW_X_RSQ 0
+#endif
 
 #if defined(__CUDACC__) && !defined(LHW_CPU_EMU)
 #define LHW_DEV __device__ __forceinline__
@@ -390,7 +394,13 @@ LHW_DEV double m_rsqrt(double x) {
 #if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
   // single-precision seed (MUFU.RSQ) + one Newton step in double: relative error ~1.5 * (6e-8)^2 = 5e-15, a third of
   // the dependent-instruction chain of the library rsqrt(double); pivots and quaternion norms are far inside float range
+#if LHW_X_RSQ
+  float y0;   // the bare MUFU.RSQ: rsqrtf() wraps it in a denormal-input rescale that these operands never need
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)x));
+  const double y = (double)y0;
+#else
   double y = (double)rsqrtf((float)x);
+#endif
   return y * (1.5 - 0.5 * x * y * y);
 #else
   return 1.0 / sqrt(x);

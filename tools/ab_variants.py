@@ -22,11 +22,15 @@ VDIR = os.path.join(PKG, "build", "variants")
 BUILDS = {
     "base": [],
     "cf": ["-DLHW_X_CF=1"],
+    "rsq": ["-DLHW_X_RSQ=1"],
+    "cfrsq": ["-DLHW_X_CF=1", "-DLHW_X_RSQ=1"],
 }
 # (build, env knobs) timed on (model, precision, n_envs)
 RUNS = [
     ("base", {}),
     ("cf", {}),
+    ("rsq", {}),
+    ("cfrsq", {}),
     ("base", {"LHW_WARPS_PER_BLOCK": "4"}),
     ("base", {"LHW_WARPS_PER_BLOCK": "5"}),
     ("cf", {"LHW_WARPS_PER_BLOCK": "4"}),
@@ -86,7 +90,8 @@ def run(quick):
                                env=dict(os.environ, LHW_B200_LIB=lib_path(name)), capture_output=True, text=True)
             parity_done[name] = r.returncode == 0
             print(f"[{name}] parity subset: {'passed' if parity_done[name] else 'FAILED'}  {r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''}", flush=True)
-        for model, prec, n in (WORKLOADS[:1] if quick else WORKLOADS):
+        loads = WORKLOADS[:1] if quick else [w for w in WORKLOADS if not knobs or (w[0] == "jvrc_walk" and w[1] == 64)]
+        for model, prec, n in loads:
             r = subprocess.run([sys.executable, "-c", TIMER % ROOT, model, str(prec), str(n)], cwd=ROOT, env=env, capture_output=True, text=True)
             val = next((float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("RESULT")), None)
             rec = dict(build=name, knobs=knobs, model=model, precision=prec, n_envs=n, env_steps_per_s=val, parity=parity_done[name])
