@@ -40,6 +40,17 @@
 #ifndef LHW_X_RSQ
 #define LHW_X_RSQ 0
 #endif
+// LHW_X_GMODEL: model tables that are indexed by the LANE (per-link / per-dof constants of the per-substep phases) are read from
+// a global-memory twin of the model (LDG through L1) instead of the constant bank, which serialises a warp's distinct addresses
+// (~1 % of the instructions but ~4 % of the stall samples sit behind those LDCs in the end-of-round-1 capture).
+#ifndef LHW_X_GMODEL
+#define LHW_X_GMODEL 0
+#endif
+#if LHW_X_GMODEL && defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+#define LHW_GLD(m, field) __ldg(&(m).gm->field)
+#else
+#define LHW_GLD(m, field) ((m).field)
+#endif
 
 #if defined(__CUDACC__) && !defined(LHW_CPU_EMU)
 #define LHW_DEV __device__ __forceinline__
@@ -238,6 +249,9 @@ template <class real, int NJ, int TK> struct Model {
   int delay_frames, nplan;
   int slab_contacts_are_floor;   // 0: reference behaviour (SURVEY C-2), foot-stone contacts invisible to GRF / contact z
   const real* plans;   // [nplan][PLAN_STRIDE] in global memory (host memory in the CPU emulation)
+#if LHW_X_GMODEL
+  const Model* gm;     // the same record in global memory (device builds; unused by the CPU emulation)
+#endif
 };
 
 // Out-of-line device routines must not read the model through a generic reference (that turns every constant-bank
@@ -743,7 +757,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         if (e < 9) {
           const int r = e / 3, c = e - 3 * r;
           const real sn = w.sc[i - 1][0], cs = w.sc[i - 1][1];
-          const int ax = m.axis_id[i];
+          const int ax = LHW_GLD(m, axis_id[i]);
           if (ax >= 0) {
             // rotation about a coordinate axis of the parent-aligned frame: column `ax` is kept, the other two
             // columns rotate in their plane:  col_b' = cs col_b + sn col_c ,  col_c' = cs col_c - sn col_b  (b=ax+1, c=ax+2 cyclic)
@@ -769,7 +783,11 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           }
         } else {
           const int r = e - 9;
+#if LHW_X_GMODEL
+          const real lp[3] = {LHW_GLD(m, link_pos[i][0]), LHW_GLD(m, link_pos[i][1]), LHW_GLD(m, link_pos[i][2])};
+#else
           const real* lp = m.link_pos[i];
+#endif
           w.xr[i][r] = w.xr[p][r] + Rp[3 * r] * lp[0] + Rp[3 * r + 1] * lp[1] + Rp[3 * r + 2] * lp[2];
         }
       }
@@ -790,7 +808,12 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         S[3] = S[4] = S[5] = 0;
       } else {
         const int i = l - 5;
+#if LHW_X_GMODEL
+        const real ax3[3] = {LHW_GLD(m, axis[i][0]), LHW_GLD(m, axis[i][1]), LHW_GLD(m, axis[i][2])};
+        mv3(w.xmat[i], ax3, S);
+#else
         mv3(w.xmat[i], m.axis[i], S);
+#endif
         cross(w.xr[i], S, S + 3);  // velocity at o of a rotation about the axis through xr: w x (o - p) = p x w
       }
     }
@@ -798,6 +821,24 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       const int i = l - (32 - NL);
       const real* R = w.xmat[i];
       real c[3];
+#if LHW_X_GMODEL
+      real Ib[6];
+#pragma unroll
+      for (int x = 0; x < 6; x++) Ib[x] = LHW_GLD(m, inertia[i][x]);
+      real ms;
+      if constexpr (PERENV) {
+        mv3(R, w.p_com[i], c);
+        ms = w.p_mass[i];
+        if (i == 0) {
+#pragma unroll
+          for (int x = 0; x < 6; x++) Ib[x] = w.p_inertia0[x];
+        }
+      } else {
+        const real cm[3] = {LHW_GLD(m, com[i][0]), LHW_GLD(m, com[i][1]), LHW_GLD(m, com[i][2])};
+        mv3(R, cm, c);
+        ms = LHW_GLD(m, mass[i]);
+      }
+#else
       const real* Ib = m.inertia[i];
       real ms;
       if constexpr (PERENV) {
@@ -808,6 +849,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         mv3(R, m.com[i], c);
         ms = m.mass[i];
       }
+#endif
 #pragma unroll
       for (int x = 0; x < 3; x++) c[x] += w.xr[i][x];
       const real B[9] = {Ib[0], Ib[3], Ib[4], Ib[3], Ib[1], Ib[5], Ib[4], Ib[5], Ib[2]};
@@ -900,7 +942,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         for (int kk = 0; kk < NJ; kk++)
           if (kk <= k) {
             real v = dot6(w.S[6 + ch * NJ + kk], f);
-            if (kk == k) v += m.armature[l];
+            if (kk == k) v += LHW_GLD(m, armature[l]);
             w.M.c[ch][k][kk] = v; w.M.c[ch][kk][k] = v;
           }
 #pragma unroll
@@ -1188,7 +1230,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           }
         }
       } else {
-        q = -m.damping[l] * w.qvel[l] - dot6(w.S[l], Ft);
+        q = -LHW_GLD(m, damping[l]) * w.qvel[l] - dot6(w.S[l], Ft);
       }
       if (l >= 6) q += w.ctrl[l - 6];
       w.qfs[l] = q;
@@ -1196,7 +1238,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     } else if (l < NV + NU) {
       const int u = l - NV, d = 6 + u;
       const real q = w.qpos[7 + u];
-      const real dlo = q - m.range_lo[d], dhi = m.range_hi[d] - q;
+      const real dlo = q - LHW_GLD(m, range_lo[d]), dhi = LHW_GLD(m, range_hi[d]) - q;
       int side = 0;
       real dist = 0;
       if (dlo < 0) { side = 1; dist = dlo; }
@@ -1530,11 +1572,11 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
     LHW_SYNC();
     LHW_LANES(l) {
-      if (l < 6) w.H.r[l][l] += m.h * m.damping[l];
+      if (l < 6) w.H.r[l][l] += m.h * LHW_GLD(m, damping[l]);
       else if (l < NV) {
         const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ;
         if constexpr (PERENV) w.H.c[ch][k][k] += m.h * w.p_damping[l - 6];
-        else w.H.c[ch][k][k] += m.h * m.damping[l];
+        else w.H.c[ch][k][k] += m.h * LHW_GLD(m, damping[l]);
       }
     }
     LHW_SYNC();

@@ -169,15 +169,36 @@ struct lhw_sim {
   Model<double, NJ_JVRC, 2> mdt;
   Model<float, NJ_JVRC, 2> mft;
   void* d_plans = nullptr;   // SteppingTask footstep plans in HBM ([MAXPLAN][PLAN_STRIDE] reals of the sim's precision)
+  void* d_twin = nullptr;    // LHW_X_GMODEL builds: the active model record once more, in global memory
   size_t work_bytes;
   int state_reals, obs_dim;
 };
 
 namespace {
 
+// LHW_X_GMODEL: copy the model to global memory as well and leave its address in the record that goes to the constant bank
+template <class M> int upload_twin(lhw_sim* s, M& host, cudaStream_t st) {
+#if LHW_X_GMODEL
+  if (!s->d_twin) CUDA_OK(cudaMalloc(&s->d_twin, sizeof(M)));
+  host.gm = (const M*)s->d_twin;
+  CUDA_OK(cudaMemcpyAsync(s->d_twin, &host, sizeof(M), cudaMemcpyHostToDevice, st));
+#else
+  (void)s; (void)host; (void)st;
+#endif
+  return 0;
+}
+
 int upload_model(lhw_sim* s, cudaStream_t st) {
   const int slot = (s->tk == 2 ? 6 : s->tk ? 4 : (s->nj == NJ_JVRC ? 0 : 2)) + (s->precision == 64 ? 0 : 1);
   if (g_owner[slot] == s) return 0;
+  {
+    int rc = 0;
+    if (s->tk == 2) rc = s->precision == 64 ? upload_twin(s, s->mdt, st) : upload_twin(s, s->mft, st);
+    else if (s->tk) rc = s->precision == 64 ? upload_twin(s, s->mds, st) : upload_twin(s, s->mfs, st);
+    else if (s->nj == NJ_JVRC) rc = s->precision == 64 ? upload_twin(s, s->md, st) : upload_twin(s, s->mf, st);
+    else rc = s->precision == 64 ? upload_twin(s, s->md5, st) : upload_twin(s, s->mf5, st);
+    if (rc != 0) return rc;
+  }
   if (s->tk == 2) {
     if (s->precision == 64) CUDA_OK(cudaMemcpyToSymbolAsync(c_model_dt, &s->mdt, sizeof(s->mdt), 0, cudaMemcpyHostToDevice, st));
     else CUDA_OK(cudaMemcpyToSymbolAsync(c_model_ft, &s->mft, sizeof(s->mft), 0, cudaMemcpyHostToDevice, st));
@@ -318,6 +339,7 @@ int lhw_sim_destroy(lhw_sim* s) {
   for (int k = 0; k < 8; k++)
     if (g_owner[k] == s) g_owner[k] = nullptr;
   if (s->d_plans) cudaFree(s->d_plans);
+  if (s->d_twin) cudaFree(s->d_twin);
   delete s;
   return 0;
 }

@@ -23,18 +23,20 @@ BUILDS = {
     "base": [],
     "cf": ["-DLHW_X_CF=1"],
     "rsq": ["-DLHW_X_RSQ=1"],
-    "cfrsq": ["-DLHW_X_CF=1", "-DLHW_X_RSQ=1"],
+    "gm": ["-DLHW_X_GMODEL=1"],
+    "all": ["-DLHW_X_CF=1", "-DLHW_X_RSQ=1", "-DLHW_X_GMODEL=1"],
 }
-# (build, env knobs) timed on (model, precision, n_envs)
+# (build, env knobs) timed on (model, precision, n_envs); runs with knobs only time the headline workload
 RUNS = [
     ("base", {}),
     ("cf", {}),
     ("rsq", {}),
-    ("cfrsq", {}),
+    ("gm", {}),
+    ("all", {}),
     ("base", {"LHW_WARPS_PER_BLOCK": "4"}),
     ("base", {"LHW_WARPS_PER_BLOCK": "5"}),
-    ("cf", {"LHW_WARPS_PER_BLOCK": "4"}),
-    ("cf", {"LHW_WARPS_PER_BLOCK": "5"}),
+    ("all", {"LHW_WARPS_PER_BLOCK": "4"}),
+    ("all", {"LHW_WARPS_PER_BLOCK": "5"}),
 ]
 WORKLOADS = [("jvrc_walk", 64, 4096), ("jvrc_walk", 64, 32768), ("jvrc_walk", 32, 4096), ("h1", 64, 4096), ("jvrc_step", 64, 4096)]
 PARITY = ["tests/test_gpu_parity.py", "tests/test_gpu_h1.py::test_h1_fp64_closed_loop_with_randomisation_and_resets",
