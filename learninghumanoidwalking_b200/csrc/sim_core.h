@@ -73,6 +73,18 @@
 #ifndef LHW_BLOCK_SYNC
 #define LHW_BLOCK_SYNC(on) ((void)0)
 #endif
+// LHW_X_SPLITBAR (candidate): the rendez-vous as a split barrier.  A warp ARRIVES when its substep is done and only WAITS, just
+// before the solver of the next substep, for the others to have finished the previous one -- by then they normally have (the
+// pre-solver phases last longer than the spread of the solver), so the wait that costs 23 % of the warp time in lock step is only
+// paid when a warp would get more than about half a substep ahead, and the warps still stay within that window of code.
+// Selected at run time with LHW_BLOCK_SYNC_MODE=4 in a build that defines the two hooks (sim_kernels.cu).
+#ifndef LHW_X_SPLITBAR
+#define LHW_X_SPLITBAR 0
+#endif
+#ifndef LHW_BLOCK_ARRIVE
+#define LHW_BLOCK_ARRIVE(on) ((void)0)
+#define LHW_BLOCK_WAIT(on, parity) ((void)0)
+#endif
 
 #if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
 #define LHW_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
@@ -1261,6 +1273,9 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
   }
   LHW_SYNC();
   LHW_BLOCK_SYNC(block_sync & 2);  // optional second rendez-vous of the block's warps, before the solver
+#if LHW_X_SPLITBAR
+  LHW_BLOCK_WAIT((block_sync & 4) && (block_sync >> 16) > 0, ((block_sync >> 16) - 1) & 1);   // bits 16..: the substep index
+#endif
   // ---------------- P9 Newton start: contact point maps Pm, then Ma = M a, ya = S_foot a and the row residuals
   if constexpr (!Cfg<NJ, TK>::SLABS)
   LHW_LANES(l) {
@@ -2045,9 +2060,16 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
       if (l < NU) w.ctrl[l] = w.kp_step[l] * (w.target[l] - w.act_len[l]) + w.kd_step[l] * ((real)0 - w.act_vel[l]);
     }
     LHW_SYNC();
+#if LHW_X_SPLITBAR
+    if (alive) substep<real, NJ, TK>(w, m, sidx == m.frame_skip - 1, (block_sync & 0xffff) | (sidx << 16));
+    else { LHW_BLOCK_SYNC(block_sync & 2); LHW_BLOCK_WAIT((block_sync & 4) && sidx > 0, (sidx - 1) & 1); }
+    LHW_BLOCK_SYNC((block_sync & 1) && ((sidx + 1) % (((block_sync >> 4) & 0xfff) + 1) == 0));
+    LHW_BLOCK_ARRIVE(block_sync & 4);
+#else
     if (alive) substep<real, NJ, TK>(w, m, sidx == m.frame_skip - 1, block_sync);
     else LHW_BLOCK_SYNC(block_sync & 2);
     LHW_BLOCK_SYNC((block_sync & 1) && ((sidx + 1) % ((block_sync >> 4) + 1) == 0));   // every (block_sync>>4)+1 substeps
+#endif
   }
   if (!alive) return;
   // WalkingTask.step (tasks/walking_task.py:149-179)

@@ -14,6 +14,30 @@
 
 #include "../../include/lhw_b200.h"
 #define LHW_BLOCK_SYNC(on) do { if (on) __syncthreads(); } while (0)
+#if LHW_X_SPLITBAR
+// split rendez-vous of a lock-step block (sim_core.h): one mbarrier per block, one arrival per warp and phase (= substep)
+__shared__ unsigned long long lhw_block_mbar;
+__device__ __forceinline__ void lhw_block_arrive() {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&lhw_block_mbar)) : "memory");
+}
+__device__ __forceinline__ void lhw_block_wait(int parity) {
+  if ((threadIdx.x & 31) == 0)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LHW_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LHW_DONE;\n"
+        "bra LHW_WAIT;\n"
+        "LHW_DONE:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(&lhw_block_mbar)), "r"(parity) : "memory");
+  __syncwarp();
+}
+#define LHW_BLOCK_ARRIVE(on) do { if (on) lhw_block_arrive(); } while (0)
+#define LHW_BLOCK_WAIT(on, parity) do { if (on) lhw_block_wait(parity); } while (0)
+#endif
 #include "model_pack.h"
 
 using namespace lhw;
@@ -142,6 +166,13 @@ __global__ void __launch_bounds__(sizeof(real) == 8 ? 512 : 896, 1)
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * (blockDim.x >> 5) + warp;
   const int alive = env < n_envs;
+#if LHW_X_SPLITBAR
+  if (sync_mode & 4) {
+    if (threadIdx.x == 0)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&lhw_block_mbar)), "r"((int)(blockDim.x >> 5)) : "memory");
+    __syncthreads();
+  }
+#endif
   const int e = alive ? env : n_envs - 1;
   W& w = reinterpret_cast<W*>(smem_raw)[warp];
   const Model<real, NJ, TK>& m = cmodel<real, NJ, TK>();

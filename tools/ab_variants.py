@@ -25,6 +25,8 @@ BUILDS = {
     "rsq": ["-DLHW_X_RSQ=1"],
     "gm": ["-DLHW_X_GMODEL=1"],
     "all": ["-DLHW_X_CF=1", "-DLHW_X_RSQ=1", "-DLHW_X_GMODEL=1"],
+    "sb": ["-DLHW_X_SPLITBAR=1"],
+    "allsb": ["-DLHW_X_CF=1", "-DLHW_X_RSQ=1", "-DLHW_X_GMODEL=1", "-DLHW_X_SPLITBAR=1"],
 }
 # (build, env knobs) timed on (model, precision, n_envs); runs with knobs only time the headline workload
 RUNS = [
@@ -37,6 +39,8 @@ RUNS = [
     ("base", {"LHW_WARPS_PER_BLOCK": "5"}),
     ("all", {"LHW_WARPS_PER_BLOCK": "4"}),
     ("all", {"LHW_WARPS_PER_BLOCK": "5"}),
+    ("sb", {"LHW_BLOCK_SYNC_MODE": "4"}),          # split barrier: arrive after the substep, wait before the next solver
+    ("allsb", {"LHW_BLOCK_SYNC_MODE": "4"}),
 ]
 WORKLOADS = [("jvrc_walk", 64, 4096), ("jvrc_walk", 64, 32768), ("jvrc_walk", 32, 4096), ("h1", 64, 4096), ("jvrc_step", 64, 4096)]
 PARITY = ["tests/test_gpu_parity.py", "tests/test_gpu_h1.py::test_h1_fp64_closed_loop_with_randomisation_and_resets",
@@ -88,13 +92,22 @@ def run(quick):
     for name, knobs in RUNS:
         env = dict(os.environ, LHW_B200_LIB=lib_path(name), **knobs)
         if name not in parity_done:     # the variant's arithmetic against the oracle, through the C-ABI, before any timing of it
-            r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu"] + PARITY, cwd=ROOT,
-                               env=dict(os.environ, LHW_B200_LIB=lib_path(name)), capture_output=True, text=True)
+            try:    # a candidate that hangs must cost its own time-out, not the GPU box
+                r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu"] + PARITY, cwd=ROOT, timeout=900,
+                                   env=dict(os.environ, LHW_B200_LIB=lib_path(name), **knobs), capture_output=True, text=True)
+            except subprocess.TimeoutExpired:
+                r = subprocess.CompletedProcess([], 124, "timed out", "")
             parity_done[name] = r.returncode == 0
             print(f"[{name}] parity subset: {'passed' if parity_done[name] else 'FAILED'}  {r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''}", flush=True)
         loads = WORKLOADS[:1] if quick else [w for w in WORKLOADS if not knobs or (w[0] == "jvrc_walk" and w[1] == 64)]
         for model, prec, n in loads:
-            r = subprocess.run([sys.executable, "-c", TIMER % ROOT, model, str(prec), str(n)], cwd=ROOT, env=env, capture_output=True, text=True)
+            if not parity_done[name]:
+                continue
+            try:
+                r = subprocess.run([sys.executable, "-c", TIMER % ROOT, model, str(prec), str(n)], cwd=ROOT, env=env, capture_output=True,
+                                   text=True, timeout=300)
+            except subprocess.TimeoutExpired:
+                r = subprocess.CompletedProcess([], 124, "", "timed out")
             val = next((float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("RESULT")), None)
             rec = dict(build=name, knobs=knobs, model=model, precision=prec, n_envs=n, env_steps_per_s=val, parity=parity_done[name])
             if val is None:
