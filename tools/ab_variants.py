@@ -72,7 +72,10 @@ def build():
         if p.wait() != 0:
             raise SystemExit(f"nvcc failed on variant {name}")
         subprocess.check_call([nvcc, "-shared", "-o", lib_path(name), obj] + shared + ["-lcudart"])
+        os.remove(obj)      # only the libraries travel to the GPU box
         print("built", lib_path(name))
+    for obj in shared:
+        os.remove(obj)
 
 
 TIMER = r"""
