@@ -43,6 +43,7 @@ class PPO:
         self.max_traj_len, self.n_proc = args.max_traj_len, args.num_procs
         self.grad_clip, self.mirror_coeff = args.max_grad_norm, args.mirror_coeff
         self.eval_freq = getattr(args, "eval_freq", 100)
+        self.eval_batches = getattr(args, "eval_batches", 5)     # evaluate(num_batches=5) in the reference
         self.imitate_coeff = getattr(args, "imitate_coeff", 0.0)
         # opt-in: TF32 tensor-core GEMMs for the MLPs (the reference trains in fp32 with torch's default allow_tf32 = False, and
         # so does this build unless asked otherwise; at minibatches >= 32k the update is GEMM bound)
@@ -87,6 +88,7 @@ class PPO:
         self._adv_stats = torch.zeros(L.lhw_adv_stats_words(), dtype=torch.float64, device=self.device)
         self._mb = None
         self._ug, self._ug_calls = None, 0      # CUDA graph of one optimiser step (see _update_step)
+        self._best_eval = float("-inf")         # ModelCheckpointer._best_metric (rl/utils/checkpointer.py:33)
 
     # ------------------------------------------------------------------ sampling (rl/algos/ppo.py:215-297)
     def sample_parallel_with_workers(self, deterministic=False) -> BatchData:
@@ -247,6 +249,33 @@ class PPO:
         nb = num_samples // mb
         return perm[: nb * mb].view(nb, mb).to(self.device, non_blocking=True)
 
+    # ------------------------------------------------------------------ evaluation + checkpoints (rl/algos/ppo.py:408-426)
+    def evaluate(self, env_fn, nets, itr, num_batches=5):
+        """num_batches deterministic batches from the persistent workers (episodes carry on from the training batch, as in the
+        reference); the mean reward / length of the episodes that completed, over all ranks; `actor_{itr}.pt` / `critic_{itr}.pt`
+        always, the un-suffixed `actor.pt` / `critic.pt` when the mean reward improved (ModelCheckpointer.save_if_best,
+        rl/utils/checkpointer.py:54-83).  Returns (eval_batches, mean_reward, mean_length); no completed episode -> nan, which
+        never counts as an improvement."""
+        for net in nets.values():
+            net.eval()
+        eval_batches = [self.sample_parallel_with_workers(deterministic=True) for _ in range(num_batches)]
+        tot = torch.zeros(3, dtype=torch.float64, device=self.device)
+        for b in eval_batches:
+            tot[0] += b.ep_rewards.double().sum()
+            tot[1] += b.ep_lens.double().sum()
+            tot[2] += b.ep_rewards.numel()
+        if self.world > 1:
+            dist.all_reduce(tot)
+        rew_sum, len_sum, n_ep = tot.tolist()
+        mean_rew = rew_sum / n_ep if n_ep else float("nan")
+        mean_len = len_sum / n_ep if n_ep else float("nan")
+        if self.rank == 0:
+            self.save(itr)
+            if mean_rew > self._best_eval:
+                self._best_eval = mean_rew
+                self.save(None)
+        return eval_batches, mean_rew, mean_len
+
     # ------------------------------------------------------------------ training loop (rl/algos/ppo.py:428-641)
     def train(self, env_fn, n_itr, verbose=True):
         if self.actor_optimizer is None:
@@ -314,8 +343,17 @@ class PPO:
                                ("Time/sample_time", sample_time), ("Time/optimize_time", optimize_time),
                                ("Time/total_elapsed", total_time)):
                     writer.add_scalar(tag, v, itr)
-            if self.rank == 0 and (itr == 0 or (itr + 1) % self.eval_freq == 0):
-                self.save(itr)
+            if itr == 0 or (itr + 1) % self.eval_freq == 0:     # rl/algos/ppo.py:597-615
+                t2 = time.time()
+                _, eval_rew, eval_len = self.evaluate(env_fn, {"actor": self.policy, "critic": self.critic}, itr,
+                                                      num_batches=self.eval_batches)
+                log[-1].update(eval_rew=eval_rew, eval_len=eval_len)
+                if verbose and self.rank == 0:
+                    print("====EVALUATE EPISODE====")
+                    print(f"(Episode length:{eval_len:.3f}. Reward:{eval_rew:.3f}. Time taken:{time.time() - t2:.2f}s)")
+                if writer is not None:
+                    writer.add_scalar("Eval/mean_reward", eval_rew, itr)
+                    writer.add_scalar("Eval/mean_episode_length", eval_len, itr)
         if writer is not None:
             writer.flush()
             writer.close()
@@ -335,7 +373,9 @@ class PPO:
         return SummaryWriter(str(self.save_path), flush_secs=10)
 
     def save(self, itr):
-        """actor_{itr}.pt / critic_{itr}.pt as whole pickled modules (rl/utils/checkpointer.py:51-83)."""
+        """actor_{itr}.pt / critic_{itr}.pt as whole pickled modules; itr None = the un-suffixed "best" pair
+        (rl/utils/checkpointer.py:36-83)."""
         self.save_path.mkdir(parents=True, exist_ok=True)
-        torch.save(self.policy, self.save_path / f"actor_{itr}.pt")
-        torch.save(self.critic, self.save_path / f"critic_{itr}.pt")
+        suffix = "" if itr is None else f"_{itr}"
+        torch.save(self.policy, self.save_path / f"actor{suffix}.pt")
+        torch.save(self.critic, self.save_path / f"critic{suffix}.pt")

@@ -16,15 +16,17 @@ def test_train_then_eval(tmp_path, env_name, obs_dim, act_dim, capsys):
     runs = list(tmp_path.iterdir())
     assert len(runs) == 1 and runs[0].name.endswith("_" + env_name)
     names = sorted(p.name for p in runs[0].iterdir())
-    assert [n for n in names if not n.startswith("events.out.tfevents")] == ["actor_0.pt", "actor_1.pt", "critic_0.pt",
-                                                                              "critic_1.pt", "experiment.pkl"]
+    # suffixed checkpoints at iteration 0 and every --eval-freq, the un-suffixed pair = the best evaluation so far
+    assert [n for n in names if not n.startswith("events.out.tfevents")] == ["actor.pt", "actor_0.pt", "actor_1.pt", "critic.pt",
+                                                                              "critic_0.pt", "critic_1.pt", "experiment.pkl"]
     ev = [n for n in names if n.startswith("events.out.tfevents")]
     assert len(ev) == 1                      # TensorBoard log with the reference's tags (rl/utils/logger.py:71-115)
     from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
     acc = EventAccumulator(str(runs[0]))
     acc.Reload()
     assert {"Loss/actor", "Loss/critic", "Loss/mirror", "Loss/imitation", "Train/mean_reward", "Train/mean_episode_length",
-            "Train/mean_noise_std", "Time/fps", "Time/sample_time", "Time/optimize_time", "Time/total_elapsed"} <= set(
+            "Train/mean_noise_std", "Time/fps", "Time/sample_time", "Time/optimize_time", "Time/total_elapsed",
+            "Eval/mean_reward", "Eval/mean_episode_length"} <= set(
         acc.Tags()["scalars"])
     args = pickle.load(open(runs[0] / "experiment.pkl", "rb"))
     assert args.env == env_name and args.num_procs == 64
@@ -35,7 +37,8 @@ def test_train_then_eval(tmp_path, env_name, obs_dim, act_dim, capsys):
     # the stdout lines scripts/benchmark_training.py:75-79 parses ARE the reference's metric definition
     import re
     for pat in (r"\*+ Iteration (\d+) \*+", r"Sampling took ([\d.]+)s for (\d+) steps", r"\|\s+Mean Eprew\s+\|\s+([\d.e+-]+)\s+\|",
-                r"\|\s+Mean Eplen\s+\|\s+([\d.e+-]+)\s+\|", r"Total time elapsed: ([\d.]+)s.*fps=([\d.]+)"):
+                r"\|\s+Mean Eplen\s+\|\s+([\d.e+-]+)\s+\|", r"Total time elapsed: ([\d.]+)s.*fps=([\d.]+)",
+                r"====EVALUATE EPISODE====\n\(Episode length:([\d.]+)\. Reward:([\d.e+-]+)\. Time taken:([\d.]+)s\)"):
         assert re.search(pat, train_out), pat
     assert re.search(r"Sampling took [\d.]+s for (\d+) steps", train_out).group(1) == str(64 * 40)
     episodes = rx.main(["eval", "--logdir", str(tmp_path), "--ep-len", "2"]) or []
