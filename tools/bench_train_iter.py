@@ -24,7 +24,8 @@ probe = base(); r = probe.robot; probe.close()
 env_fn = lambda: SymmetricEnv(base, mirrored_obs=r.mirrored_obs, mirrored_act=r.mirrored_acts, clock_inds=r.clock_inds)
 args = SimpleNamespace(gamma=0.99, lam=0.95, lr=3e-4, eps=1e-5, entropy_coeff=0.0, clip=0.2, minibatch_size=mb, epochs=3,
                        max_traj_len=400, num_procs=n, max_grad_norm=0.05, mirror_coeff=0.4, eval_freq=10**9, recurrent=False,
-                       imitate_coeff=0.0, std_dev=0.223, learn_std=False, logdir="/tmp/lhw_bench_train", steps_per_env=T)
+                       imitate_coeff=0.0, std_dev=0.223, learn_std=False, logdir="/tmp/lhw_bench_train", steps_per_env=T,
+                       eval_batches=0)     # time sampling + optimisation only: the evaluation pass of iteration 0 is five more batches
 ppo = PPO(env_fn, args, seed=0)
 ppo.train(None, 1, verbose=False)          # warm-up iteration (graph capture, cuBLAS heuristics)
 torch.cuda.synchronize()
