@@ -103,7 +103,9 @@ def run(quick):
                 r = subprocess.CompletedProcess([], 124, "timed out", "")
             parity_done[name] = r.returncode == 0
             print(f"[{name}] parity subset: {'passed' if parity_done[name] else 'FAILED'}  {r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''}", flush=True)
-        loads = WORKLOADS[:1] if quick else [w for w in WORKLOADS if not knobs or (w[0] == "jvrc_walk" and w[1] == 64)]
+        # block-size knobs are sized for the fp64 headline kernel; the split barrier is timed on its fp32 twin too
+        loads = WORKLOADS[:1] if quick else [w for w in WORKLOADS if not knobs or (
+            w[0] == "jvrc_walk" and (w[1] == 64 or "LHW_WARPS_PER_BLOCK" not in knobs))]
         for model, prec, n in loads:
             if not parity_done[name]:
                 continue
