@@ -121,6 +121,13 @@ def run(quick):
             out.append(rec)
             print(f"{name:6s} {json.dumps(knobs):34s} {model:10s} fp{prec} N={n:<6d} {val / 1e6 if val else float('nan'):.3f} M env-steps/s", flush=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "ab_variants.json"), "w"), indent=1)
+    # summary: every run against the unflagged build with default knobs on the same workload
+    base = {(r["model"], r["precision"], r["n_envs"]): r["env_steps_per_s"] for r in out if r["build"] == "base" and not r["knobs"]}
+    print("\n--- relative to base (same workload) ---")
+    for r in out:
+        b = base.get((r["model"], r["precision"], r["n_envs"]))
+        if b and r["env_steps_per_s"] and (r["build"] != "base" or r["knobs"]):
+            print(f"{r['build']:6s} {json.dumps(r['knobs']):62s} {r['model']:10s} fp{r['precision']} N={r['n_envs']:<6d} x{r['env_steps_per_s'] / b:.3f}")
 
 
 if __name__ == "__main__":
