@@ -101,7 +101,8 @@ def run(quick):
                                    env=dict(os.environ, LHW_B200_LIB=lib_path(name), **knobs), capture_output=True, text=True)
             except subprocess.TimeoutExpired:
                 r = subprocess.CompletedProcess([], 124, "timed out", "")
-            parity_done[name] = r.returncode == 0
+            last = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
+            parity_done[name] = r.returncode == 0 and " passed" in last and "skipped" not in last    # skipped = no GPU = not checked
             print(f"[{name}] parity subset: {'passed' if parity_done[name] else 'FAILED'}  {r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ''}", flush=True)
         # block-size knobs are sized for the fp64 headline kernel; the split barrier is timed on its fp32 twin too
         loads = WORKLOADS[:1] if quick else [w for w in WORKLOADS if not knobs or (
