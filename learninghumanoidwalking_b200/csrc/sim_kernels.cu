@@ -3,8 +3,10 @@
 // One environment per warp.  A warp streams its env's state record (env-major, contiguous -> coalesced
 // 128 B lines) from HBM into its private slice of shared memory, runs frame_skip physics substeps + reward /
 // observation / termination / auto-reset entirely on chip, and streams the record back: one HBM round trip
-// per control step (1220 B algorithmic per env-step in fp32).  Only __syncwarp() is used, so
-// warps of a block never wait on each other; the block size only sets how the shared memory is carved.
+// per control step (1220 B algorithmic per env-step in fp32).  Inside an environment only __syncwarp()
+// is used.  The shipped launch puts 8 (fp64) / 14 (fp32) environments in a block that meets at one __syncthreads() per
+// physics substep: the warps then run the same region of a kernel that is far larger than the instruction cache
+// (findings 2 and 6); LHW_WARPS_PER_BLOCK=1 gives the original one-warp blocks that never wait.
 #include <cuda_runtime.h>
 #include <stdio.h>
 
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(32, sizeof(real) == 4 ? (TK ? 24 : 28) : (TK ?
   store_state<real, NJ, TK>(w, sr, si);
 }
 
-// experiment / alternative carving: W warps per block (one env each), a __syncthreads() per substep so the warps of an SM
-// share instruction-cache fills (the kernel is instruction-fetch bound, profiles/); selected with LHW_WARPS_PER_BLOCK > 1
+// the shipped carving: W warps per block (one env each), a __syncthreads() per substep so the warps of an SM share
+// instruction-cache fills (profiles/: stall_no_inst 24 % -> 3 %); W from LHW_WARPS_PER_BLOCK or the measured defaults below
 template <class real, int NJ, int TK>
 __global__ void __launch_bounds__(sizeof(real) == 8 ? 512 : 896, 1)
     step_kernel_mw(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs, uint32_t seed, uint32_t first_id,
