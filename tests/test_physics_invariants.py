@@ -141,3 +141,51 @@ def test_joint_limit_pushes_back(oracle_tight):
 def test_philox_stream_is_counter_based(oracle_tight):
     a = oracle_tight.philox(1, 2, 3, 4)
     assert a == oracle_tight.philox(1, 2, 3, 4) and a != oracle_tight.philox(1, 2, 4, 4) and a != oracle_tight.philox(2, 2, 3, 4)
+
+
+def _momenta(o, q, v):
+    """Total linear momentum P (world) and angular momentum about the centre of mass L_C (world) from the generalised momentum
+    p = M(q) v alone: p[0:3] = P; R p[3:6] = angular momentum about the root origin O (the free joint's angular velocity is
+    body-frame); M[0:3,3:6] = -m R [c]x gives the centre of mass c relative to O; L_C = L_O - (R c) x P."""
+    M = o.mass_matrix(q)
+    p = M @ v
+    w_, x, y, z = q[3:7]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w_ * z), 2 * (x * z + w_ * y)],
+                  [2 * (x * y + w_ * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w_ * x)],
+                  [2 * (x * z - w_ * y), 2 * (y * z + w_ * x), 1 - 2 * (x * x + y * y)]])
+    m = M[0, 0]
+    S = -R.T @ M[0:3, 3:6] / m
+    assert np.abs(S + S.T).max() < 1e-12                     # a cross-product matrix, as the derivation says
+    c = np.array([S[2, 1], S[0, 2], S[1, 0]])
+    return m, p[0:3], R @ p[3:6] - np.cross(R @ c, p[0:3]), q[0:3] + R @ c
+
+
+def test_momentum_balance_in_free_flight_under_internal_torques_and_damping():
+    """Joint torques and joint damping are internal: in free flight the total linear momentum changes at exactly m g and the
+    angular momentum about the centre of mass not at all, whatever the legs do.  Semi-implicit Euler keeps both to O(h): the
+    error must halve with the time step (an inconsistent Coriolis / mass-matrix pair leaves an h-independent residue), and the
+    centre of mass recovered from the mass matrix must be the one the potential energy sees."""
+    errs = []
+    for h in (1e-3, 5e-4, 2.5e-4):
+        o = _oracle_with(lambda mj, h=h: mj["opt"].__setitem__("timestep", h))
+        assert any(lk["joint"]["damping"] > 0 for lk in o.mj["links"][1:])
+        envs = o.make_envs(1)
+        rng = np.random.RandomState(11)
+        q, v = _random_state(o.mj, rng)
+        v[6:] *= 3.0
+        o.set_field(envs, 0, "qpos", q)
+        o.set_field(envs, 0, "qvel", v)
+        m, P0, L0, C0 = _momenta(o, q, v)
+        assert abs(m - o.mj["total_mass"]) < 1e-9
+        ke, pe = o.energy(q, v)
+        assert abs(pe - m * 9.81 * C0[2]) < 1e-8 * abs(pe)     # same centre of mass as the gravity term
+        T = 0.1
+        for k in range(int(round(T / h))):
+            o.mj_step(envs, 0, 40.0 * np.sin(0.05 * k * h / 1e-3 + np.arange(12)))   # strong, time-varying internal torques
+        q1, v1 = o.field(envs, 0, "qpos"), o.field(envs, 0, "qvel")
+        _, P1, L1, _ = _momenta(o, q1, v1)
+        errs.append((np.linalg.norm(P1 - P0 - m * T * np.array([0, 0, -9.81])), np.linalg.norm(L1 - L0), np.linalg.norm(L0)))
+    (p0, l0, scale), (p1, l1, _), (p2, l2, _) = errs
+    assert scale > 5.0 and l0 < 0.02 * scale and p0 < 0.02 * m, errs          # small at the reference's time step already
+    assert abs(l0 / l1 - 2) < 0.15 and abs(l1 / l2 - 2) < 0.15, errs           # and first order in h
+    assert abs(p0 / p1 - 2) < 0.15 and abs(p1 / p2 - 2) < 0.15, errs
