@@ -77,7 +77,8 @@
 // before the solver of the next substep, for the others to have finished the previous one -- by then they normally have (the
 // pre-solver phases last longer than the spread of the solver), so the wait that costs 23 % of the warp time in lock step is only
 // paid when a warp would get more than about half a substep ahead, and the warps still stay within that window of code.
-// Selected at run time with LHW_BLOCK_SYNC_MODE=4 in a build that defines the two hooks (sim_kernels.cu).
+// Selected at run time with LHW_BLOCK_SYNC_MODE=4 in a build that defines the two hooks (sim_kernels.cu); mode 8 puts the wait
+// after the solver instead (more slack, the warps spread further: tools/barrier_model.py).
 #ifndef LHW_X_SPLITBAR
 #define LHW_X_SPLITBAR 0
 #endif
@@ -1496,6 +1497,9 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     if (alpha == 0) converged = true;
   }
 
+#if LHW_X_SPLITBAR
+  LHW_BLOCK_WAIT((block_sync & 8) && (block_sync >> 16) > 0, ((block_sync >> 16) - 1) & 1);   // mode 8: the wait after the solver
+#endif
   // ---------------- P11 what mjData keeps after mj_step (evaluated at the pre-integration state)
   LHW_LANES(l) {
     if (l < NU) {
@@ -2062,9 +2066,9 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
     LHW_SYNC();
 #if LHW_X_SPLITBAR
     if (alive) substep<real, NJ, TK>(w, m, sidx == m.frame_skip - 1, (block_sync & 0xffff) | (sidx << 16));
-    else { LHW_BLOCK_SYNC(block_sync & 2); LHW_BLOCK_WAIT((block_sync & 4) && sidx > 0, (sidx - 1) & 1); }
+    else { LHW_BLOCK_SYNC(block_sync & 2); LHW_BLOCK_WAIT((block_sync & 12) && sidx > 0, (sidx - 1) & 1); }
     LHW_BLOCK_SYNC((block_sync & 1) && ((sidx + 1) % (((block_sync >> 4) & 0xfff) + 1) == 0));
-    LHW_BLOCK_ARRIVE(block_sync & 4);
+    LHW_BLOCK_ARRIVE(block_sync & 12);
 #else
     if (alive) substep<real, NJ, TK>(w, m, sidx == m.frame_skip - 1, block_sync);
     else LHW_BLOCK_SYNC(block_sync & 2);

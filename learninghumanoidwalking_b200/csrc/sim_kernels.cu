@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(sizeof(real) == 8 ? 512 : 896, 1)
   const int env = blockIdx.x * (blockDim.x >> 5) + warp;
   const int alive = env < n_envs;
 #if LHW_X_SPLITBAR
-  if (sync_mode & 4) {
+  if (sync_mode & 12) {
     if (threadIdx.x == 0)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&lhw_block_mbar)), "r"((int)(blockDim.x >> 5)) : "memory");
     __syncthreads();

@@ -42,6 +42,7 @@ RUNS = [
     ("sb", {"LHW_BLOCK_SYNC_MODE": "4"}),          # split barrier: arrive after the substep, wait before the next solver
     ("allsb", {"LHW_BLOCK_SYNC_MODE": "4"}),
     ("sb", {"LHW_BLOCK_SYNC_MODE": "4", "LHW_WARPS_PER_BLOCK": "4"}),
+    ("sb", {"LHW_BLOCK_SYNC_MODE": "8"}),          # ... wait after the solver instead
 ]
 WORKLOADS = [("jvrc_walk", 64, 4096), ("jvrc_walk", 64, 32768), ("jvrc_walk", 32, 4096), ("h1", 64, 4096), ("jvrc_step", 64, 4096)]
 PARITY = ["tests/test_gpu_parity.py", "tests/test_gpu_h1.py::test_h1_fp64_closed_loop_with_randomisation_and_resets",
