@@ -62,9 +62,17 @@
 
 #if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
 #define LHW_LANES(l) for (int l = (int)(threadIdx.x & 31), _o = 1; _o; _o = 0)
+#define LHW_LANES_ORDERED(l) LHW_LANES(l)
 #define LHW_SYNC() __syncwarp()
+#elif defined(LHW_EMU_REVERSE)
+// host emulation with the lanes of a phase run in descending order: a phase whose lanes only touch their own data (or data
+// finished before the preceding LHW_SYNC) gives bit-identical results in either order, so forward vs reverse is a race check
+#define LHW_LANES(l) for (int l = 31; l >= 0; --l)
+#define LHW_LANES_ORDERED(l) for (int l = 0; l < 32; ++l)   // phases whose emulation of a warp-wide prefix needs ascending lanes
+#define LHW_SYNC() ((void)0)
 #else
 #define LHW_LANES(l) for (int l = 0; l < 32; ++l)
+#define LHW_LANES_ORDERED(l) LHW_LANES(l)
 #define LHW_SYNC() ((void)0)
 #endif
 
@@ -1100,7 +1108,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       const int ntask = 4 * bit_count(near_slabs[f]);
 #pragma unroll 1
       for (int pass = 0; pass * 32 < ntask; pass++) {
-        LHW_LANES(l) {
+        LHW_LANES_ORDERED(l) {   // LHW_PREFIX2 below
           const int t = pass * 32 + l;
           int he = 0, hx = 0;
           real pe[4], px[4];   // x, y, z relative to o, signed distance

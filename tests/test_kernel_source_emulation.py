@@ -154,3 +154,47 @@ def test_flagged_candidate_rewrites_still_match_the_oracle():
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.join(here, "test_kernel_source_emulation.py"), "-k",
                         "env_level_parity or diverged or substep_parity"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+
+
+_LANE_ORDER_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path[:0] = [sys.argv[2], sys.argv[2] + "/tests/emu"]
+from emu import Emu
+from learninghumanoidwalking_b200.model import load_model, pack_model
+out = {}
+for name in ("jvrc_walk", "h1", "jvrc_step", "jvrc_walk_terrain"):
+    for prec in (64, 32):
+        e = Emu(pack_model(load_model(name), tolerance=1e-10 if prec == 64 else 1e-6), prec, 3, seed=3, first_id=7)
+        e.reset()
+        rng, acc = np.random.RandomState(5), []
+        for k in range(40):
+            r = e.step(rng.normal(size=(3, e.nu)) * 0.4, max_traj_len=20)
+            acc.append(np.concatenate([np.asarray(x, dtype=np.float64).ravel() for x in (r[0], r[2], r[3], r[4], r[5])] + [e.sr.astype(np.float64).ravel()]))
+        out[f"{name}_{prec}"] = np.stack(acc)
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_no_phase_depends_on_the_order_its_lanes_run_in(tmp_path):
+    """Race check of the kernel source on the CPU tier.  The emulation runs the 32 lanes of a phase one after the other; a phase in
+    which a lane reads what another lane of the SAME phase writes (a missing LHW_SYNC) gives different results when the lanes run
+    in descending instead of ascending order.  Every variant and both precisions, closed loop with contacts, falls, truncations,
+    resets and (H1) randomisation: observations, reward terms, flags and the whole state record must be bit-identical.  (The one
+    phase that emulates a warp-wide prefix count keeps ascending lanes in both builds: LHW_LANES_ORDERED.)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runs = {}
+    for tag, defs in (("fwd", ""), ("rev", "LHW_EMU_REVERSE=1")):
+        out = str(tmp_path / f"{tag}.npz")
+        r = subprocess.run([sys.executable, "-c", _LANE_ORDER_SCRIPT, out, root], env=dict(os.environ, LHW_EMU_DEFINES=defs),
+                           capture_output=True, text=True, timeout=1200)
+        assert r.returncode == 0, r.stderr[-1500:]
+        runs[tag] = np.load(out)
+    assert len(runs["fwd"].files) == 8
+    for k in runs["fwd"].files:
+        a, b = runs["fwd"][k], runs["rev"][k]
+        assert a.shape == b.shape and np.isfinite(a).all()
+        assert (a == b).all(), (k, np.argwhere(a != b)[:3])
