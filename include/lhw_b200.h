@@ -120,13 +120,17 @@ int lhw_clip_adam_dev(float* param, const float* grad, float* exp_avg, float* ex
                       float grad_scale, void* stream);
 
 /* ---- multi-GPU exchange step, fused (csrc/comm_kernels.cu) ------------------------------------------
- * Replaces, on N > 1 GPUs, the sequence of rl/algos/ppo.py:389-396: (gradient all-reduce) -> clip_grad_norm_(actor),
- * clip_grad_norm_(critic) -> actor Adam.step, critic Adam.step, by ONE cooperative kernel that reads the peers'
- * flat gradients over NVLink peer memory (CUDA IPC), sums them in fixed rank order, and applies clip + Adam.
+ * Replaces, on N >= 1 GPUs, the sequence of rl/algos/ppo.py:389-396: (gradient all-reduce) -> clip_grad_norm_(actor),
+ * clip_grad_norm_(critic) -> actor Adam.step, critic Adam.step, by three ordinary (CUDA-graph capturable) launches that
+ * read the peers' flat gradients over NVLink peer memory (CUDA IPC, 16-byte loads), sum them in fixed rank order, and
+ * apply clip + Adam; the Adam step number and the peer-barrier epoch live in device memory.
  * lhw_comm owns a cudaMalloc'ed IPC-exported gradient buffer of n_floats floats (lhw_comm_grad_ptr) — the host
  * makes the modules' .grad tensors views of it. Handles are exchanged by the host (torch.distributed
  * all_gather of lhw_comm_handle_size() bytes per rank) and mapped with lhw_comm_import.
- * n_actor: the first n_actor floats belong to the actor (own norm / clip), the rest to the critic. */
+ * n_actor: the first n_actor floats belong to the actor (own norm / clip), the rest to the critic.
+ * lhw_comm_status: error word of the peer barrier (non-zero: a peer did not arrive within the spin limit; returns -20),
+ * completed Adam steps, the two gradient norms of the last step; synchronises `stream`.
+ * lhw_comm_set_step: set the device-side Adam step number (resume). */
 typedef struct lhw_comm lhw_comm;
 const char* lhw_comm_last_error(void);
 int lhw_comm_handle_size(void);
@@ -136,8 +140,10 @@ int lhw_comm_export(lhw_comm* comm, void* handle_blob_host);
 int lhw_comm_import(lhw_comm* comm, const void* all_handle_blobs_host);
 int lhw_comm_destroy(lhw_comm* comm);
 int lhw_fused_allreduce_clip_adam(lhw_comm* comm, float* param, float* exp_avg, float* exp_avg_sq, long long n_actor,
-                                  long long n_total, int step, float lr, float beta1, float beta2, float eps, float max_norm,
-                                  float* norms_out_host_or_null, void* stream);
+                                  long long n_total, float lr, float beta1, float beta2, float eps, float max_norm,
+                                  void* stream);
+int lhw_comm_status(lhw_comm* comm, int* error_word, int* adam_steps, float* norms2, void* stream);
+int lhw_comm_set_step(lhw_comm* comm, int adam_steps, void* stream);
 
 #ifdef __cplusplus
 }

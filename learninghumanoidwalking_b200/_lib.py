@@ -42,8 +42,10 @@ SIGNATURES = {
     "lhw_comm_export": (c_int, [c_void_p, c_void_p]),
     "lhw_comm_import": (c_int, [c_void_p, c_void_p]),
     "lhw_comm_destroy": (c_int, [c_void_p]),
-    "lhw_fused_allreduce_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_int, c_float, c_float,
-                                              c_float, c_float, c_float, c_void_p, c_void_p]),
+    "lhw_fused_allreduce_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_float, c_float,
+                                              c_float, c_float, c_float, c_void_p]),
+    "lhw_comm_status": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lhw_comm_set_step": (c_int, [c_void_p, c_int, c_void_p]),
     "lhw_clip_adam_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_float, c_float, c_float,
                                   c_float, c_float, c_float, c_void_p]),
     "lhw_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_float,

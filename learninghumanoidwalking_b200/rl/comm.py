@@ -3,7 +3,7 @@
 Owns the IPC-exported flat gradient buffer of this rank, exchanges the CUDA IPC handles through torch.distributed
 (the only thing the process group is used for here) and maps the peers' buffers.  The modules' .grad tensors are
 views of `grad` so autograd writes straight into peer-visible memory; lhw_fused_allreduce_clip_adam then does
-all-reduce + clip + Adam for actor and critic in one cooperative launch.
+all-reduce + clip + Adam for actor and critic in three graph-capturable launches.
 """
 from __future__ import annotations
 
@@ -49,15 +49,29 @@ class PeerComm:
                 raise _lib.LhwError(f"lhw_comm_import failed: {L.lhw_comm_last_error().decode()}")
             dist.barrier()
 
-    def fused_step(self, param, exp_avg, exp_avg_sq, n_actor, step, lr, betas, eps, max_norm, want_norms=False):
+    def fused_step(self, param, exp_avg, exp_avg_sq, n_actor, lr, betas, eps, max_norm):
+        """All-reduce (peer memory) + clip x2 + Adam x2: three plain launches on the current stream, capturable into a CUDA graph
+        (the Adam step number and the barrier epoch live in device memory)."""
         L = _lib.lib()
-        norms = (ctypes.c_float * 2)() if want_norms else None
         rc = L.lhw_fused_allreduce_clip_adam(self._h, param.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(n_actor),
-                                             self.n, int(step), lr, betas[0], betas[1], eps, max_norm, norms,
-                                             _lib.current_stream_ptr())
+                                             self.n, lr, betas[0], betas[1], eps, max_norm, _lib.current_stream_ptr())
         if rc:
             raise _lib.LhwError(f"lhw_fused_allreduce_clip_adam failed: {L.lhw_comm_last_error().decode()}")
-        return (norms[0], norms[1]) if want_norms else None
+
+    def status(self):
+        """(completed Adam steps, (actor grad norm, critic grad norm) of the last step); raises if a peer did not arrive at the
+        gradient exchange within the spin limit (the kernels carry on with partial sums rather than hang the GPU).
+        Synchronises the current stream: call once per iteration, not per step."""
+        L = _lib.lib()
+        err, steps, norms = ctypes.c_int(0), ctypes.c_int(0), (ctypes.c_float * 2)()
+        rc = L.lhw_comm_status(self._h, ctypes.byref(err), ctypes.byref(steps), norms, _lib.current_stream_ptr())
+        if rc:
+            raise _lib.LhwError(f"gradient exchange failed on rank {self.rank}: {L.lhw_comm_last_error().decode()}")
+        return steps.value, (norms[0], norms[1])
+
+    def set_step(self, adam_steps: int):
+        if _lib.lib().lhw_comm_set_step(self._h, int(adam_steps), _lib.current_stream_ptr()):
+            raise _lib.LhwError(f"lhw_comm_set_step failed: {_lib.lib().lhw_comm_last_error().decode()}")
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

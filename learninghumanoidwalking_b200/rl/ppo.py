@@ -82,6 +82,20 @@ class PPO:
         wseed = get_worker_seed(seed if seed is not None else 0, self.rank)
         self.workers = [DeviceRolloutWorker(env, self.policy, self.critic, seed=wseed, worker_id=self.rank)]
         self.batch_size = env.num_envs * self.steps_per_env
+        # `minibatch_size` counts this rank's samples.  minibatch_scale="auto" (run_experiment.py's default) keeps the
+        # reference's number of optimiser steps per iteration instead of its absolute minibatch: the reference's default
+        # geometry is 12 workers x 400 steps = 4800 samples in minibatches of 64 (225 updates per iteration over 3 epochs,
+        # run_experiment.py:159-172); with N device environments the batch is N x steps_per_env, and 64-sample minibatches
+        # would mean tens of thousands of launch-bound updates per iteration.  The minibatch grows with the batch.
+        if getattr(args, "minibatch_scale", "off") == "auto" and self.batch_size > 12 * 400:
+            self.minibatch_size = max(self.minibatch_size, int(round(self.minibatch_size * self.batch_size / (12 * 400))))
+        if self.world > 1:
+            # every rank must issue the same number of gradient exchanges per iteration: equal shards only
+            cnt = torch.tensor([env.num_envs, -env.num_envs], device=self.device)
+            dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+            if int(cnt[0]) != -int(cnt[1]):
+                raise ValueError(f"ranks hold different numbers of environments ({-int(cnt[1])}..{int(cnt[0])}): "
+                                 "num_procs must be a multiple of the world size")
         self.actor_optimizer = self.critic_optimizer = None
         self._comm = None
         L = _lib.lib()
@@ -89,6 +103,25 @@ class PPO:
         self._mb = None
         self._ug, self._ug_calls = None, 0      # CUDA graph of one optimiser step (see _update_step)
         self._best_eval = float("-inf")         # ModelCheckpointer._best_metric (rl/utils/checkpointer.py:33)
+
+    def load_pretrained(self, actor, critic):
+        """`--continued` (rl/algos/ppo.py:69-82): take the weights and the embedded observation normalisation of a saved
+        actor / critic pair (this build's or a reference checkout's — same state-dict keys); like the reference, the action
+        noise `stds` is NOT restored but re-initialised from `--std-dev`, and neither optimiser state nor the iteration
+        counter come back.  In place: captured graphs and the flat parameter buffer keep their addresses."""
+        with torch.no_grad():
+            for mine, theirs in ((self.policy, actor), (self.critic, critic)):
+                sd = {k: v for k, v in theirs.state_dict().items() if k != "stds"}
+                missing, unexpected = mine.load_state_dict(sd, strict=False)
+                if unexpected or [k for k in missing if k != "stds"]:
+                    raise ValueError(f"checkpoint does not fit the network: missing {missing}, unexpected {unexpected}")
+                for name in ("obs_mean", "obs_std"):
+                    v = getattr(theirs, name, None)
+                    if torch.is_tensor(v):
+                        getattr(mine, name).copy_(v.to(self.device, torch.float32))
+            self.old_policy.load_state_dict(self.policy.state_dict())
+            self.old_policy.obs_mean.copy_(self.policy.obs_mean)
+            self.old_policy.obs_std.copy_(self.policy.obs_std)
 
     # ------------------------------------------------------------------ sampling (rl/algos/ppo.py:215-297)
     def sample_parallel_with_workers(self, deterministic=False) -> BatchData:
@@ -127,12 +160,13 @@ class PPO:
         total_loss.backward()
         a_opt, c_opt = self.actor_optimizer, self.critic_optimizer
         if self._comm is not None and isinstance(a_opt, FusedClipAdam) and isinstance(c_opt, FusedClipAdam):
-            # the one exchange step of the path, fused: peer-memory all-reduce + 2x clip_grad_norm_ + 2x Adam in ONE launch
+            # the one exchange step of the path, fused: peer-memory all-reduce + 2x clip_grad_norm_ + 2x Adam in three
+            # graph-capturable launches (csrc/comm_kernels.cu); at world 1 the same launches without the flag traffic
             a_opt.step_count += 1
             c_opt.step_count += 1
             g = a_opt.param_groups[0]
-            self._comm.fused_step(self._flat_param, self._flat_m, self._flat_v, self._n_actor, a_opt.step_count, g["lr"],
-                                  g["betas"], g["eps"], g["max_norm"])
+            self._comm.fused_step(self._flat_param, self._flat_m, self._flat_v, self._n_actor, g["lr"], g["betas"], g["eps"],
+                                  g["max_norm"])
         elif isinstance(a_opt, FusedClipAdam) and isinstance(c_opt, FusedClipAdam):
             if self.world > 1:  # baseline path: NCCL all-reduce of the flat gradient, then clip+Adam launches
                 dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
@@ -155,9 +189,11 @@ class PPO:
         sizes it is launch bound (2.5 ms of host time for 1.9 ms of kernels at 4096 samples, far worse at the default 64).
         After a few eager steps (cuBLAS / autograd warm-up — they are real updates) the whole step — losses, backward,
         gradient norms, clip + Adam with the step counter in device memory — is captured once and replayed.
-        Single rank only (the fused NVLink exchange is a cooperative launch); LHW_UPDATE_GRAPH=0 keeps the eager loop."""
+        Every rank captures and replays the same step: the fused exchange (peer-memory all-reduce + clip + Adam) is three
+        ordinary launches whose epoch / step counters live in device memory, and the NCCL baseline (LHW_FUSED_EXCHANGE=0) is
+        capturable as well.  LHW_UPDATE_GRAPH=0 keeps the eager loop."""
         import os
-        eager = (self.world > 1 or os.environ.get("LHW_UPDATE_GRAPH", "1") == "0" or self._mb is None or ob is not self._mb[0]
+        eager = (os.environ.get("LHW_UPDATE_GRAPH", "1") == "0" or self._mb is None or ob is not self._mb[0]
                  or not isinstance(self.actor_optimizer, FusedClipAdam) or not isinstance(self.critic_optimizer, FusedClipAdam))
         if not eager and self._ug is not None and self._ug[2] == ob.data_ptr():
             self._ug[0].replay()
@@ -195,9 +231,11 @@ class PPO:
         from .comm import PeerComm
         from .optim import flatten_modules_
         n_total = sum(p.numel() for m in (self.policy, self.critic) for p in m.parameters())
-        # the fused NVLink exchange kernel (peer all-reduce + clip + Adam) is the N > 1 path; a single rank uses the two
-        # clip+Adam launches whose step counter lives on the device, so that the step can be replayed from a CUDA graph
-        fused = os.environ.get("LHW_FUSED_EXCHANGE", "1") != "0" and self.world > 1
+        # the fused exchange (peer all-reduce + clip + Adam, three launches) is the path at every world size;
+        # LHW_FUSED_EXCHANGE=0 selects the baseline: NCCL all-reduce + lhw_grad_sumsq / lhw_clip_adam_dev per network
+        fused = os.environ.get("LHW_FUSED_EXCHANGE", "1") != "0"
+        if self._comm is not None:
+            self._comm.close()
         self._comm = PeerComm(n_total, self.device) if fused else None
         flat, grad, segs = flatten_modules_([self.policy, self.critic], None if self._comm is None else self._comm.grad)
         self._flat_param, self._flat_grad = flat, grad
@@ -209,8 +247,16 @@ class PPO:
         self.critic_optimizer = FusedClipAdam(self.critic, lr=self.lr, eps=self.eps, max_norm=self.grad_clip,
                                               views=(sl(flat, 1), sl(grad, 1), sl(self._flat_m, 1), sl(self._flat_v, 1)))
         self.actor_optimizer.world = self.critic_optimizer.world = self.world
+        if self.world > 1:
+            # replicas start from rank 0's weights whatever the seeding of the ranks was
+            dist.broadcast(self._flat_param, src=0)
         # old_policy must not alias the flat buffer
         self.old_policy = deepcopy(self.policy)
+        # the parameters have just been re-homed into the flat buffer: every captured graph (rollout step, optimiser step)
+        # still holds the OLD parameter addresses -> drop them, they are re-captured on next use
+        for w in self.workers:
+            w.invalidate_graphs()
+        self._ug, self._ug_calls = None, 0
 
     # ------------------------------------------------------------------ device data path helpers
     def normalize_advantages(self, returns: torch.Tensor, values: torch.Tensor) -> torch.Tensor:
@@ -221,6 +267,7 @@ class PPO:
         _lib.check(L.lhw_adv_stats(returns.data_ptr(), values.data_ptr(), self._adv_stats.data_ptr(), n, st), "lhw_adv_stats")
         if self.world > 1:
             dist.all_reduce(self._adv_stats[0:2], op=dist.ReduceOp.SUM)
+        # equal shards are enforced in __init__, so the global count is n * world
         _lib.check(L.lhw_adv_apply(returns.data_ptr(), values.data_ptr(), adv.data_ptr(), self._adv_stats.data_ptr(), n,
                                    n * self.world, self.eps, st), "lhw_adv_apply")
         return adv
@@ -316,6 +363,8 @@ class PPO:
                     stats += self._update_step(ob, ab, rb, db, obs_mirr, act_mirr)
                     n_updates += 1
             stats = (stats / max(1, n_updates)).tolist()   # the only host sync of the optimisation phase
+            if getattr(self, "_comm", None) is not None:
+                self._comm.status()    # raises if a peer missed a gradient exchange (bounded spin in the kernels)
             optimize_time = time.time() - t1
             total_time = time.time() - train_start
             fps = self.total_steps / total_time
@@ -377,5 +426,8 @@ class PPO:
         (rl/utils/checkpointer.py:36-83)."""
         self.save_path.mkdir(parents=True, exist_ok=True)
         suffix = "" if itr is None else f"_{itr}"
-        torch.save(self.policy, self.save_path / f"actor{suffix}.pt")
-        torch.save(self.critic, self.save_path / f"critic{suffix}.pt")
+        from .policies import export_module
+        # self-contained CPU copies under the reference's class path (rl.policies.actor.Gaussian_FF_Actor / rl.policies.critic.FF_V):
+        # loadable by a reference checkout's `run_experiment.py eval` / `--continued` (rl/policies/__init__.py)
+        torch.save(export_module(self.policy), self.save_path / f"actor{suffix}.pt")
+        torch.save(export_module(self.critic), self.save_path / f"critic{suffix}.pt")

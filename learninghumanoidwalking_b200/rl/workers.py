@@ -28,6 +28,11 @@ class DeviceRolloutWorker:
         self._graphs = {}
         self.total_steps = 0
 
+    def invalidate_graphs(self):
+        """Drop the captured control-step graphs (they hold the addresses of the policy / critic parameters and of the
+        rollout buffers): call after anything that re-homes those tensors, e.g. PPO.make_optimizers()."""
+        self._graphs = {}
+
     def sync_state(self, policy_state_dict=None, critic_state_dict=None, obs_mean=None, obs_std=None, iteration_count=0):
         """The learner and the sampler share the same modules on the same device: nothing to ship.  Kept so the
         call site of rl/algos/ppo.py:238-242 works unchanged; state dicts are loaded if given."""
@@ -67,7 +72,9 @@ class DeviceRolloutWorker:
         import os
         env = self.env
         N, T = env.num_envs, int(max_steps)
-        env.max_traj_len = int(max_traj_len)
+        # the truncation length lives on the batched env itself, not on a SymmetricEnv wrapper around it
+        inner = env.__dict__.get("env", None)
+        (inner if inner is not None else env).max_traj_len = int(max_traj_len)
         if self._buf is None or self._buf.T != T or self._buf.N != N:
             self._buf = DeviceRolloutBuffer(T, N, env.obs_dim, env.act_dim, self.device, gamma, lam)
             self._graphs = {}

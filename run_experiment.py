@@ -46,6 +46,9 @@ TRAIN_FLAGS = [
     ("--precision", dict(type=_I, default=32, choices=[32, 64], help="simulator arithmetic (64 = the reference's float64)")),
     ("--tf32", dict(action="store_true", help="TF32 tensor-core GEMMs in the MLPs (off: fp32 like the reference)")),
     ("--steps-per-env", dict(type=_I, default=None, help="transitions per env per iteration (default: max-traj-len)")),
+    ("--minibatch-scale", dict(type=_S, default="auto", choices=["auto", "off"],
+                               help="auto: --minibatch-size is scaled by (this rank's batch / 4800) so that an iteration keeps the reference's "
+                                    "225 optimiser steps at its default flags; off: --minibatch-size samples per rank, literally")),
 ]
 EVAL_FLAGS = [("--path", dict(type=_P, default=None)), ("--logdir", dict(type=_P, default=None)),
               ("--out-dir", dict(type=_P, default=None, help="(videos are not produced by this build)")),
@@ -118,6 +121,9 @@ def run_experiment(args):
     if args.recurrent or args.imitate:
         raise NotImplementedError("--recurrent / --imitate are outside the accelerated path (SURVEY.md §2)")
     Env = import_env(args.env)
+    if args.num_procs % world:
+        raise SystemExit(f"--num-procs {args.num_procs} is not a multiple of the {world} ranks: every rank must hold the same number "
+                         "of environments (each optimiser step is one gradient exchange on every rank)")
     first, n_local = env_shard(rank, world, args.num_procs)
     seed = args.seed if args.seed is not None else 0
     env_fn = partial(Env, n_local, precision=args.precision, seed=seed, first_env_id=first, device=local,
@@ -141,8 +147,9 @@ def run_experiment(args):
     if args.continued is not None:
         actor = torch.load(args.continued, weights_only=False)
         critic = torch.load(Path(args.continued.parent, "critic" + str(args.continued).split("actor")[1]), weights_only=False)
-        algo.policy.load_state_dict(actor.state_dict())
-        algo.critic.load_state_dict(critic.state_dict())
+        algo.load_pretrained(actor, critic)
+        if rank == 0:
+            print("Loaded (pre-trained) actor from: ", args.continued)
     algo.train(env_fn, args.n_itr, verbose=rank == 0)
 
 

@@ -202,11 +202,12 @@ def test_same_seed_gives_bit_identical_weights():
 
 
 def test_fused_exchange_kernel_single_rank_matches_oracle_clip_adam():
-    """lhw_fused_allreduce_clip_adam at world = 1: one launch = clip_grad_norm_ x2 + Adam x2 (rl/algos/ppo.py:393-396)."""
+    """lhw_fused_allreduce_clip_adam at world = 1: three launches = clip_grad_norm_ x2 + Adam x2 (rl/algos/ppo.py:393-396),
+    the Adam step number kept in device memory; an odd length exercises the scalar tail after the 16-byte loads."""
     from learninghumanoidwalking_b200.rl.comm import PeerComm
     from oracle.ppo_oracle import clip_adam
     dev = torch.device("cuda", 0)
-    n_a, n = 1000, 1700
+    n_a, n = 1001, 1703
     comm = PeerComm(n, dev)
     g = torch.Generator(device="cuda").manual_seed(0)
     p = torch.randn(n, device="cuda", generator=g)
@@ -216,12 +217,30 @@ def test_fused_exchange_kernel_single_rank_matches_oracle_clip_adam():
     for step in range(1, 4):
         comm.grad.copy_(torch.randn(n, device="cuda", generator=g) * (0.3 if step == 2 else 0.001))   # clipped and unclipped cases
         gnp = comm.grad.double().cpu().numpy()
-        norms = comm.fused_step(p, m, v, n_a, step, 3e-4, (0.9, 0.999), 1e-5, 0.05, want_norms=True)
+        comm.fused_step(p, m, v, n_a, 3e-4, (0.9, 0.999), 1e-5, 0.05)
+        done, norms = comm.status()
+        assert done == step
         pa, ma, va, na = clip_adam(pa, gnp[:n_a], ma, va, step, 3e-4, 1e-5, 0.05)
         pc, mc, vc, nc = clip_adam(pc, gnp[n_a:], mc, vc, step, 3e-4, 1e-5, 0.05)
         assert abs(norms[0] - na) < 1e-5 * max(1, na) and abs(norms[1] - nc) < 1e-5 * max(1, nc)
         assert np.abs(p[:n_a].double().cpu().numpy() - pa).max() < 2e-6 and np.abs(p[n_a:].double().cpu().numpy() - pc).max() < 2e-6
     comm.close()
+
+
+def test_rollout_graph_follows_the_weights_after_make_optimizers():
+    """The public sequence PPO(...); sample_parallel_with_workers(); train() (the reference's tests use it): the rollout
+    graph captured by the first call holds the parameter addresses of BEFORE make_optimizers() re-homes them into the flat
+    buffer.  It must be dropped then, otherwise the sampler keeps acting on weights the learner never touches."""
+    from learninghumanoidwalking_b200.rl import PPO
+    ppo = PPO(_env_fn(seed=6), _args(), seed=6)
+    b0 = ppo.sample_parallel_with_workers(deterministic=True)
+    assert b0.actions.abs().max().item() > 0
+    ppo.make_optimizers()
+    with torch.no_grad():
+        ppo._flat_param.zero_()            # all-zero weights and biases: the deterministic action is exactly 0
+    b1 = ppo.sample_parallel_with_workers(deterministic=True)
+    assert b1.actions.abs().max().item() == 0 and b1.values.abs().max().item() == 0
+    ppo.env.close()
 
 
 def test_graph_replayed_rollout_is_bitwise_equal_to_the_eager_loop(monkeypatch):
@@ -254,7 +273,7 @@ def test_graph_replayed_update_matches_the_eager_update(monkeypatch):
         finals[mode] = ppo._flat_param.clone()
         if mode == "1":
             assert ppo._ug is not None                              # the graph was really captured and used
-            assert ppo.actor_optimizer.step_count == int(ppo.actor_optimizer.step_dev.item()) == 20
+            assert ppo.actor_optimizer.step_count == ppo._comm.status()[0] == 20
         else:
             assert ppo._ug is None
         ppo.env.close()

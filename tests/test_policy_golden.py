@@ -9,19 +9,17 @@ import torch
 G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "policy.json")))
 
 
-def _load(net, sd, hidden_prefix, out_prefix):
-    for i, lin in enumerate(net.hidden):
-        lin.weight.data = torch.tensor(sd[f"{hidden_prefix}.{i}.weight"])
-        lin.bias.data = torch.tensor(sd[f"{hidden_prefix}.{i}.bias"])
-    net.out.weight.data = torch.tensor(sd[f"{out_prefix}.weight"])
-    net.out.bias.data = torch.tensor(sd[f"{out_prefix}.bias"])
+def _load(net, sd):
+    """the golden file holds the reference modules' state dicts: the keys must be ours, one to one"""
+    assert set(sd) == set(net.state_dict())
+    net.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
 
 
 def test_actor_and_critic_forward_match_reference_modules():
     from learninghumanoidwalking_b200.rl.policies import FF_V, Gaussian_FF_Actor
     a, c = Gaussian_FF_Actor(37, 12, layers=(16, 16)), FF_V(37, layers=(16, 16))
-    _load(a.net, G["actor"], "actor_layers", "means")
-    _load(c.net, G["critic"], "critic_layers", "network_out")
+    _load(a, G["actor"])
+    _load(c, G["critic"])
     a.obs_mean = c.obs_mean = torch.tensor(G["obs_mean"])
     a.obs_std = c.obs_std = torch.tensor(G["obs_std"])
     x = torch.tensor(G["x"])
@@ -34,9 +32,9 @@ def test_parameter_counts_and_normc_init():
     a, c = Gaussian_FF_Actor(37, 12), FF_V(37)
     assert sum(p.numel() for p in a.parameters()) == G["n_actor"] == 78604
     assert sum(p.numel() for p in c.parameters()) == G["n_critic"] == 75777
-    assert abs(float(a.net.out.weight.norm(dim=1).mean()) - G["out_layer_norm"]) < 1e-6   # output layer x 0.01
-    assert torch.allclose(a.net.hidden[0].weight.norm(dim=1), torch.ones(256), atol=1e-5)    # normc rows
-    assert float(a.net.hidden[0].bias.abs().max()) == 0.0
+    assert abs(float(a.means.weight.norm(dim=1).mean()) - G["out_layer_norm"]) < 1e-6   # output layer x 0.01
+    assert torch.allclose(a.actor_layers[0].weight.norm(dim=1), torch.ones(256), atol=1e-5)    # normc rows
+    assert float(a.actor_layers[0].bias.abs().max()) == 0.0
 
 
 def test_mirror_matrices_match_reference():

@@ -85,7 +85,7 @@ import sys
 sys.path.insert(0, %r)
 from tools.quick_bench import run
 model, prec, n = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-# candidates worth 1-3 % need a quiet number: 200 timed steps, best of 3
+# candidates worth a few per cent need a quiet number: 200 timed steps, best of 3
 best = max(run(n, prec, steps=200 if n <= 8192 else 60, warm=20, sigma=0.223, model=model)[1] for _ in range(3))
 print("RESULT", best)
 """

@@ -52,7 +52,8 @@ def main():
     differ = world == 1 or not torch.equal(obs_all[0], obs_all[-1])
     if rank == 0:
         fused = ppo._comm is not None
-        print(f"DIST_CHECK model={model} world={world} envs/rank={n} fused_exchange={fused} identical_weights={same} "
+        print(f"DIST_CHECK model={model} world={world} envs/rank={n} fused_exchange={fused} update_graph={ppo._ug is not None} "
+              f"identical_weights={same} "
               f"ranks_simulate_different_envs={differ} critic_loss={log[-1]['critic_loss']:.4f} fps={log[-1]['fps']:.0f} "
               f"wsum={flat.double().sum().item():.10f} wabs={flat.double().abs().sum().item():.10f}")
     dist.destroy_process_group()
