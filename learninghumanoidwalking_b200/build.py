@@ -1,40 +1,84 @@
 """Build liblhw_b200.so (hand-written sm_100a CUDA + the C-ABI of include/lhw_b200.h) in-tree with nvcc.
 
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot; there is no JIT and no fallback.
+Every build leaves `build_record.json` next to the library: the nvcc command lines, the nvcc version, the sha256 of every
+source / header that went in, the md5 of the library's SASS and where / when it was built.  `needs_build()` compares the
+CONTENT hashes of the sources with that record (file times do not survive a copy to another box); bench.py and the
+committed ncu counters (profiles/ncu_counters.json) use the same hashes to tell whether a capture belongs to the shipped
+kernels.
 """
 from __future__ import annotations
 
+import hashlib
+import json
 import os
+import platform
 import subprocess
 import sys
+import time
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "liblhw_b200.so")
+RECORD = os.path.join(PKG, "build_record.json")
 SOURCES = ["sim_kernels.cu", "ppo_kernels.cu", "comm_kernels.cu"]
 HEADERS = ["sim_core.h", "model_pack.h", os.path.join("..", "..", "include", "lhw_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
+def source_hashes() -> dict:
+    out = {}
+    for f in SOURCES + HEADERS:
+        path = os.path.normpath(os.path.join(CSRC, f))
+        out[os.path.relpath(path, os.path.dirname(PKG))] = hashlib.sha256(open(path, "rb").read()).hexdigest()
+    return out
+
+
+def kernel_source_hash() -> str:
+    """One hash over everything the step kernels are compiled from (sim_core.h, sim_kernels.cu, model_pack.h) + the flags:
+    the key that ties an ncu capture to a build."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in ("sim_core.h", "sim_kernels.cu", "model_pack.h"):
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def read_record() -> dict | None:
+    try:
+        return json.load(open(RECORD))
+    except Exception:
+        return None
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    rec = read_record()
+    return rec is None or rec.get("sources") != source_hashes() or rec.get("flags") != NVCC_FLAGS
+
+
+def _sass_md5(nvcc: str) -> str | None:
+    cuobjdump = os.path.join(os.path.dirname(nvcc), "cuobjdump")
+    try:
+        sass = subprocess.run([cuobjdump, "-sass", LIB], capture_output=True, timeout=600).stdout
+        return hashlib.md5(sass).hexdigest() if sass else None
+    except Exception:
+        return None
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objs = []
+    objs, procs, cmds = [], [], []
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
-    procs = []
+    t0 = time.time()
     for src in SOURCES:
         obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmds.append(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
@@ -44,7 +88,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
         with open(os.path.join(PKG, "build", src + ".ptxas.log"), "w") as f:
             f.write(out)
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    link = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    subprocess.check_call(link)
+    cmds.append(" ".join(link))
+    ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()
+    json.dump(dict(library=os.path.basename(LIB), commands=cmds, flags=NVCC_FLAGS, nvcc=ver[-2:] if ver else None,
+                   sources=source_hashes(), kernel_source_hash=kernel_source_hash(), sass_md5=_sass_md5(nvcc),
+                   library_sha256=hashlib.sha256(open(LIB, "rb").read()).hexdigest(), host=platform.node(),
+                   built_at=time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), seconds=round(time.time() - t0, 1)),
+              open(RECORD, "w"), indent=1)
     return LIB
 
 

@@ -30,23 +30,10 @@
 #include <math.h>
 #include <stdint.h>
 
-// Candidate rewrites that have passed the CPU tier (kernel-source emulation vs oracle) but have not been timed on a B200 yet
-// are compiled in with -DLHW_X_<name>=1 (tools/ab_variants.py builds and times one library per flag); default = the measured
-// kernel.  LHW_X_CF: lane-role operand selection by integer offsets and deferred pivot checks instead of branches.
-#ifndef LHW_X_CF
-#define LHW_X_CF 0
-#endif
-// LHW_X_RSQ: the single-precision seed of the fp64 reciprocal square root as the bare MUFU instruction.
-#ifndef LHW_X_RSQ
-#define LHW_X_RSQ 0
-#endif
-// LHW_X_GMODEL: model tables that are indexed by the LANE (per-link / per-dof constants of the per-substep phases) are read from
-// a global-memory twin of the model (LDG through L1) instead of the constant bank, which serialises a warp's distinct addresses
-// (~1 % of the instructions but ~4 % of the stall samples sit behind those LDCs in the end-of-round-1 capture).
-#ifndef LHW_X_GMODEL
-#define LHW_X_GMODEL 0
-#endif
-#if LHW_X_GMODEL && defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
+// Model tables that are indexed by the LANE (per-link / per-dof constants of the per-substep phases) are read from a
+// global-memory twin of the model (LDG through L1) instead of the constant bank, which serialises a warp's distinct addresses
+// (~1 % of the instructions but ~4 % of the stall samples sat behind those LDCs; measured +2 %, profiles/r02_ab_variants.md).
+#if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
 #define LHW_GLD(m, field) __ldg(&(m).gm->field)
 #else
 #define LHW_GLD(m, field) ((m).field)
@@ -81,20 +68,6 @@
 #ifndef LHW_BLOCK_SYNC
 #define LHW_BLOCK_SYNC(on) ((void)0)
 #endif
-// LHW_X_SPLITBAR (candidate): the rendez-vous as a split barrier.  A warp ARRIVES when its substep is done and only WAITS, just
-// before the solver of the next substep, for the others to have finished the previous one -- by then they normally have (the
-// pre-solver phases last longer than the spread of the solver), so the wait that costs 23 % of the warp time in lock step is only
-// paid when a warp would get more than about half a substep ahead, and the warps still stay within that window of code.
-// Selected at run time with LHW_BLOCK_SYNC_MODE=4 in a build that defines the two hooks (sim_kernels.cu); mode 8 puts the wait
-// after the solver instead (more slack, the warps spread further: tools/barrier_model.py).
-#ifndef LHW_X_SPLITBAR
-#define LHW_X_SPLITBAR 0
-#endif
-#ifndef LHW_BLOCK_ARRIVE
-#define LHW_BLOCK_ARRIVE(on) ((void)0)
-#define LHW_BLOCK_WAIT(on, parity) ((void)0)
-#endif
-
 #if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
 #define LHW_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 #else
@@ -270,9 +243,7 @@ template <class real, int NJ, int TK> struct Model {
   int delay_frames, nplan;
   int slab_contacts_are_floor;   // 0: reference behaviour (SURVEY C-2), foot-stone contacts invisible to GRF / contact z
   const real* plans;   // [nplan][PLAN_STRIDE] in global memory (host memory in the CPU emulation)
-#if LHW_X_GMODEL
   const Model* gm;     // the same record in global memory (device builds; unused by the CPU emulation)
-#endif
 };
 
 // Out-of-line device routines must not read the model through a generic reference (that turns every constant-bank
@@ -429,13 +400,9 @@ LHW_DEV double m_rsqrt(double x) {
 #if defined(__CUDA_ARCH__) && !defined(LHW_CPU_EMU)
   // single-precision seed (MUFU.RSQ) + one Newton step in double: relative error ~1.5 * (6e-8)^2 = 5e-15, a third of
   // the dependent-instruction chain of the library rsqrt(double); pivots and quaternion norms are far inside float range
-#if LHW_X_RSQ
   float y0;   // the bare MUFU.RSQ: rsqrtf() wraps it in a denormal-input rescale that these operands never need
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)x));
   const double y = (double)y0;
-#else
-  double y = (double)rsqrtf((float)x);
-#endif
   return y * (1.5 - 0.5 * x * y * y);
 #else
   return 1.0 / sqrt(x);
@@ -523,24 +490,18 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
   // column steps of both chains side by side.  lane = chain * 16 + row; rows 0..NJ-1: the chain block, NJ..NJ+5: the coupling
   // rows (X = B L^-T), NJ+6: the right-hand side (forward substitution).  All three kinds of row do the SAME arithmetic on
   // their own row pointer, so the step is one branch-free instruction stream (a per-kind if/else would run three times)
-#if LHW_X_CF
   // the three kinds of row live at three places of the same Work record: the lane's row is a word offset from &H.c[0][0][0],
   // chosen with integer selects (the pointer-valued ?: compiled to a jump table per column step), and a failed pivot is
   // only replaced here; it is reported once, from the stored reciprocal pivots, after the factorisation
   real* const hc0 = &H.c[0][0][0];
   const int ox = (int)(&H.x[0][0][0] - hc0), ob = (int)(x - hc0);
-#endif
 #pragma unroll
   for (int k = 0; k < NJ; k++) {
     LHW_LANES(l) {
       const int ch = l >> 4, r = l & 15;
       if (r < NJ + 7 && (r >= NJ || r >= k)) {
-#if LHW_X_CF
         const int o_c = (ch * NJ + r) * NJ, o_x = ox + (ch * 6 + r - NJ) * NJ, o_b = ob + 6 + ch * NJ;
         real* pr = hc0 + (r < NJ ? o_c : (r < NJ + 6 ? o_x : o_b));
-#else
-        real* pr = r < NJ ? H.c[ch][r] : (r < NJ + 6 ? H.x[ch][r - NJ] : x + 6 + ch * NJ);
-#endif
         const real* pk = H.c[ch][k];
         real dk = pk[k], t = pr[k];
 #pragma unroll
@@ -549,11 +510,7 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
           dk -= pkm * pkm;
           t -= pr[mm] * pkm;
         }
-#if LHW_X_CF
         dk = dk > 0 ? dk : (real)1e-30;
-#else
-        if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
-#endif
         const real inv = m_rsqrt(dk);
         if (r == k) w.hdinv[6 + ch * NJ + k] = inv;
         else pr[k] = t * inv;
@@ -582,11 +539,7 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
   for (int k = 0; k < 6; k++) {
     LHW_LANES(l) {
       if (l < 7 && l >= k) {   // rows 0..5 of the Schur complement, row 6 = the root right-hand side: same arithmetic
-#if LHW_X_CF
         real* pr = hc0 + (l < 6 ? (int)(&H.r[0][0] - hc0) + 6 * l : ob);
-#else
-        real* pr = l < 6 ? H.r[l] : x;
-#endif
         const real* pk = H.r[k];
         real dk = pk[k], t = pr[k];
 #pragma unroll
@@ -595,11 +548,7 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
           dk -= pkm * pkm;
           t -= pr[mm] * pkm;
         }
-#if LHW_X_CF
         dk = dk > 0 ? dk : (real)1e-30;
-#else
-        if (!(dk > 0)) { dk = (real)1e-30; w.status |= 2; }
-#endif
         const real inv = m_rsqrt(dk);
         if (l == k) w.hdinv[k] = inv;
         else pr[k] = t * inv;
@@ -631,9 +580,7 @@ template <class real, int NJ, int TK> LHW_DEVNI void arrow_factor_solve(Work<rea
       for (int r = 0; r < 6; r++) t -= H.x[ch][r][k] * x[r];
       x[6 + ch * NJ + k] = t;
     }
-#if LHW_X_CF
     if (l < 6 + 2 * NJ && w.hdinv[l] >= m_rsqrt((real)1e-30)) w.status |= 2;   // a pivot was not positive (or NaN)
-#endif
   }
   LHW_SYNC();
   LHW_LANES(l) {
@@ -804,11 +751,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           }
         } else {
           const int r = e - 9;
-#if LHW_X_GMODEL
           const real lp[3] = {LHW_GLD(m, link_pos[i][0]), LHW_GLD(m, link_pos[i][1]), LHW_GLD(m, link_pos[i][2])};
-#else
-          const real* lp = m.link_pos[i];
-#endif
           w.xr[i][r] = w.xr[p][r] + Rp[3 * r] * lp[0] + Rp[3 * r + 1] * lp[1] + Rp[3 * r + 2] * lp[2];
         }
       }
@@ -829,12 +772,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         S[3] = S[4] = S[5] = 0;
       } else {
         const int i = l - 5;
-#if LHW_X_GMODEL
         const real ax3[3] = {LHW_GLD(m, axis[i][0]), LHW_GLD(m, axis[i][1]), LHW_GLD(m, axis[i][2])};
         mv3(w.xmat[i], ax3, S);
-#else
-        mv3(w.xmat[i], m.axis[i], S);
-#endif
         cross(w.xr[i], S, S + 3);  // velocity at o of a rotation about the axis through xr: w x (o - p) = p x w
       }
     }
@@ -842,7 +781,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       const int i = l - (32 - NL);
       const real* R = w.xmat[i];
       real c[3];
-#if LHW_X_GMODEL
       real Ib[6];
 #pragma unroll
       for (int x = 0; x < 6; x++) Ib[x] = LHW_GLD(m, inertia[i][x]);
@@ -859,18 +797,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         mv3(R, cm, c);
         ms = LHW_GLD(m, mass[i]);
       }
-#else
-      const real* Ib = m.inertia[i];
-      real ms;
-      if constexpr (PERENV) {
-        mv3(R, w.p_com[i], c);
-        ms = w.p_mass[i];
-        if (i == 0) Ib = w.p_inertia0;
-      } else {
-        mv3(R, m.com[i], c);
-        ms = m.mass[i];
-      }
-#endif
 #pragma unroll
       for (int x = 0; x < 3; x++) c[x] += w.xr[i][x];
       const real B[9] = {Ib[0], Ib[3], Ib[4], Ib[3], Ib[1], Ib[5], Ib[4], Ib[5], Ib[2]};
@@ -1282,9 +1208,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
   }
   LHW_SYNC();
   LHW_BLOCK_SYNC(block_sync & 2);  // optional second rendez-vous of the block's warps, before the solver
-#if LHW_X_SPLITBAR
-  LHW_BLOCK_WAIT((block_sync & 4) && (block_sync >> 16) > 0, ((block_sync >> 16) - 1) & 1);   // bits 16..: the substep index
-#endif
   // ---------------- P9 Newton start: contact point maps Pm, then Ma = M a, ya = S_foot a and the row residuals
   if constexpr (!Cfg<NJ, TK>::SLABS)
   LHW_LANES(l) {
@@ -1505,9 +1428,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     if (alpha == 0) converged = true;
   }
 
-#if LHW_X_SPLITBAR
-  LHW_BLOCK_WAIT((block_sync & 8) && (block_sync >> 16) > 0, ((block_sync >> 16) - 1) & 1);   // mode 8: the wait after the solver
-#endif
   // ---------------- P11 what mjData keeps after mj_step (evaluated at the pre-integration state)
   LHW_LANES(l) {
     if (l < NU) {
@@ -2072,16 +1992,9 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
       if (l < NU) w.ctrl[l] = w.kp_step[l] * (w.target[l] - w.act_len[l]) + w.kd_step[l] * ((real)0 - w.act_vel[l]);
     }
     LHW_SYNC();
-#if LHW_X_SPLITBAR
-    if (alive) substep<real, NJ, TK>(w, m, sidx == m.frame_skip - 1, (block_sync & 0xffff) | (sidx << 16));
-    else { LHW_BLOCK_SYNC(block_sync & 2); LHW_BLOCK_WAIT((block_sync & 12) && sidx > 0, (sidx - 1) & 1); }
-    LHW_BLOCK_SYNC((block_sync & 1) && ((sidx + 1) % (((block_sync >> 4) & 0xfff) + 1) == 0));
-    LHW_BLOCK_ARRIVE(block_sync & 12);
-#else
     if (alive) substep<real, NJ, TK>(w, m, sidx == m.frame_skip - 1, block_sync);
     else LHW_BLOCK_SYNC(block_sync & 2);
     LHW_BLOCK_SYNC((block_sync & 1) && ((sidx + 1) % ((block_sync >> 4) + 1) == 0));   // every (block_sync>>4)+1 substeps
-#endif
   }
   if (!alive) return;
   // WalkingTask.step (tasks/walking_task.py:149-179)

@@ -16,30 +16,6 @@
 
 #include "../../include/lhw_b200.h"
 #define LHW_BLOCK_SYNC(on) do { if (on) __syncthreads(); } while (0)
-#if LHW_X_SPLITBAR
-// split rendez-vous of a lock-step block (sim_core.h): one mbarrier per block, one arrival per warp and phase (= substep)
-__shared__ unsigned long long lhw_block_mbar;
-__device__ __forceinline__ void lhw_block_arrive() {
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0)
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&lhw_block_mbar)) : "memory");
-}
-__device__ __forceinline__ void lhw_block_wait(int parity) {
-  if ((threadIdx.x & 31) == 0)
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LHW_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LHW_DONE;\n"
-        "bra LHW_WAIT;\n"
-        "LHW_DONE:\n"
-        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(&lhw_block_mbar)), "r"(parity) : "memory");
-  __syncwarp();
-}
-#define LHW_BLOCK_ARRIVE(on) do { if (on) lhw_block_arrive(); } while (0)
-#define LHW_BLOCK_WAIT(on, parity) do { if (on) lhw_block_wait(parity); } while (0)
-#endif
 #include "model_pack.h"
 
 using namespace lhw;
@@ -168,13 +144,6 @@ __global__ void __launch_bounds__(sizeof(real) == 8 ? 512 : 896, 1)
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * (blockDim.x >> 5) + warp;
   const int alive = env < n_envs;
-#if LHW_X_SPLITBAR
-  if (sync_mode & 12) {
-    if (threadIdx.x == 0)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&lhw_block_mbar)), "r"((int)(blockDim.x >> 5)) : "memory");
-    __syncthreads();
-  }
-#endif
   const int e = alive ? env : n_envs - 1;
   W& w = reinterpret_cast<W*>(smem_raw)[warp];
   const Model<real, NJ, TK>& m = cmodel<real, NJ, TK>();
@@ -202,22 +171,18 @@ struct lhw_sim {
   Model<double, NJ_JVRC, 2> mdt;
   Model<float, NJ_JVRC, 2> mft;
   void* d_plans = nullptr;   // SteppingTask footstep plans in HBM ([MAXPLAN][PLAN_STRIDE] reals of the sim's precision)
-  void* d_twin = nullptr;    // LHW_X_GMODEL builds: the active model record once more, in global memory
+  void* d_twin = nullptr;    // the active model record once more, in global memory (lane-indexed tables are read from there)
   size_t work_bytes;
   int state_reals, obs_dim;
 };
 
 namespace {
 
-// LHW_X_GMODEL: copy the model to global memory as well and leave its address in the record that goes to the constant bank
+// copy the model to global memory as well and leave its address in the record that goes to the constant bank
 template <class M> int upload_twin(lhw_sim* s, M& host, cudaStream_t st) {
-#if LHW_X_GMODEL
   if (!s->d_twin) CUDA_OK(cudaMalloc(&s->d_twin, sizeof(M)));
   host.gm = (const M*)s->d_twin;
   CUDA_OK(cudaMemcpyAsync(s->d_twin, &host, sizeof(M), cudaMemcpyHostToDevice, st));
-#else
-  (void)s; (void)host; (void)st;
-#endif
   return 0;
 }
 

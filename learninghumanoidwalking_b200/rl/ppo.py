@@ -44,6 +44,7 @@ class PPO:
         self.grad_clip, self.mirror_coeff = args.max_grad_norm, args.mirror_coeff
         self.eval_freq = getattr(args, "eval_freq", 100)
         self.eval_batches = getattr(args, "eval_batches", 5)     # evaluate(num_batches=5) in the reference
+        self.eval_at_start = getattr(args, "eval_at_start", True)  # the reference evaluates (and checkpoints) at iteration 0
         self.imitate_coeff = getattr(args, "imitate_coeff", 0.0)
         # opt-in: TF32 tensor-core GEMMs for the MLPs (the reference trains in fp32 with torch's default allow_tf32 = False, and
         # so does this build unless asked otherwise; at minibatches >= 32k the update is GEMM bound)
@@ -392,7 +393,7 @@ class PPO:
                                ("Time/sample_time", sample_time), ("Time/optimize_time", optimize_time),
                                ("Time/total_elapsed", total_time)):
                     writer.add_scalar(tag, v, itr)
-            if itr == 0 or (itr + 1) % self.eval_freq == 0:     # rl/algos/ppo.py:597-615
+            if (itr == 0 and getattr(self, "eval_at_start", True)) or (itr + 1) % self.eval_freq == 0:     # rl/algos/ppo.py:597-615
                 t2 = time.time()
                 _, eval_rew, eval_len = self.evaluate(env_fn, {"actor": self.policy, "critic": self.critic}, itr,
                                                       num_batches=self.eval_batches)

@@ -143,16 +143,18 @@ def test_diverged_environment_is_flagged_terminated_and_reset_without_touching_i
         assert (dd == ed).all() and (ee == een).all() and np.abs(oo - eo).max() < 1e-9
 
 
-def test_flagged_candidate_rewrites_still_match_the_oracle():
-    """The kernel candidates that wait for their B200 timing (sim_core.h LHW_X_*; tools/ab_variants.py) are kept honest on the
-    CPU tier: the same emulation-vs-oracle check, in a fresh process whose emulation is compiled with every flag on."""
+def test_candidate_defines_reach_the_emulation_build():
+    """Kernel candidates are compile-time flags of sim_core.h (-DLHW_X_<name>=1; tools/ab_variants.py builds and times one
+    library per flag) and are kept honest on the CPU tier through LHW_EMU_DEFINES: the emulation-vs-oracle check in a fresh
+    process whose emulation is compiled with the flags on.  No candidate is pending at the moment (round 2 promoted CF / RSQ /
+    GMODEL and deleted SPLITBAR, profiles/r02_ab_variants.md); this keeps the mechanism itself under test with an inert define."""
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, LHW_EMU_DEFINES="LHW_X_CF=1 LHW_X_RSQ=1 LHW_X_GMODEL=1 LHW_X_SPLITBAR=1")
+    env = dict(os.environ, LHW_EMU_DEFINES="LHW_X_NONE=1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.join(here, "test_kernel_source_emulation.py"), "-k",
-                        "env_level_parity or diverged or substep_parity"], env=env, capture_output=True, text=True, timeout=900)
+                        "diverged or substep_parity"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
 
 

@@ -18,31 +18,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "learninghumanoidwalking_b200")
 VDIR = os.path.join(PKG, "build", "variants")
 
-# name -> -D flags
+# name -> -D flags.  Round 2 ran the four round-1 candidates (profiles/r02_ab_variants.md): CF / RSQ / GMODEL won (+6.5 % together)
+# and are now simply the kernel; SPLITBAR and 4- / 5-warp blocks lost and were deleted.  New candidates go here.
 BUILDS = {
     "base": [],
-    "cf": ["-DLHW_X_CF=1"],
-    "rsq": ["-DLHW_X_RSQ=1"],
-    "gm": ["-DLHW_X_GMODEL=1"],
-    "all": ["-DLHW_X_CF=1", "-DLHW_X_RSQ=1", "-DLHW_X_GMODEL=1"],
-    "sb": ["-DLHW_X_SPLITBAR=1"],
-    "allsb": ["-DLHW_X_CF=1", "-DLHW_X_RSQ=1", "-DLHW_X_GMODEL=1", "-DLHW_X_SPLITBAR=1"],
 }
 # (build, env knobs) timed on (model, precision, n_envs); runs with knobs only time the headline workload
 RUNS = [
     ("base", {}),
-    ("cf", {}),
-    ("rsq", {}),
-    ("gm", {}),
-    ("all", {}),
-    ("base", {"LHW_WARPS_PER_BLOCK": "4"}),
-    ("base", {"LHW_WARPS_PER_BLOCK": "5"}),
-    ("all", {"LHW_WARPS_PER_BLOCK": "4"}),
-    ("all", {"LHW_WARPS_PER_BLOCK": "5"}),
-    ("sb", {"LHW_BLOCK_SYNC_MODE": "4"}),          # split barrier: arrive after the substep, wait before the next solver
-    ("allsb", {"LHW_BLOCK_SYNC_MODE": "4"}),
-    ("sb", {"LHW_BLOCK_SYNC_MODE": "4", "LHW_WARPS_PER_BLOCK": "4"}),
-    ("sb", {"LHW_BLOCK_SYNC_MODE": "8"}),          # ... wait after the solver instead
 ]
 WORKLOADS = [("jvrc_walk", 64, 4096), ("jvrc_walk", 64, 32768), ("jvrc_walk", 32, 4096), ("h1", 64, 4096), ("jvrc_step", 64, 4096)]
 PARITY = ["tests/test_gpu_parity.py", "tests/test_gpu_h1.py::test_h1_fp64_closed_loop_with_randomisation_and_resets",

@@ -2,7 +2,7 @@
 """Run the kernel-source emulation tests with the emulation compiled under AddressSanitizer + UndefinedBehaviorSanitizer
 (development tool, CPU only): every index into the per-environment Work record, every lane map and every variant
 (jvrc_walk / h1 / jvrc_step / terrain, fp64 and fp32, NaN and runaway states included) is then bounds- and UB-checked on the
-same source the GPU executes.  usage: python tools/emu_sanitize.py [--oracle] [-DLHW_X_CF=1 ...]   (exit code 0 = no finding;
+same source the GPU executes.  usage: python tools/emu_sanitize.py [--oracle] [-DLHW_X_<candidate>=1 ...]   (exit code 0 = no finding;
 --oracle also rebuilds oracle/sim_oracle.c under the sanitizers for the run and adds the oracle's own tests)"""
 import os
 import subprocess
