@@ -45,6 +45,8 @@ int lhw_sim_state_ints(const lhw_sim* sim);  /* int32 words per env in the state
 int lhw_sim_obs_dim(const lhw_sim* sim);     /* env.observation_space.shape[0] (37 jvrc_walk, 39 jvrc_step, 35 h1) */
 int lhw_sim_act_dim(const lhw_sim* sim);     /* env.action_space.shape[0] (12 jvrc_walk, 10 h1) */
 int lhw_sim_smem_bytes_per_env(const lhw_sim* sim);
+int lhw_sim_precision(const lhw_sim* sim);   /* 64 or 32 */
+int lhw_sim_device(const lhw_sim* sim);      /* CUDA device ordinal the sim was created on */
 
 /* lhw_sim_reset: MujocoEnv.reset + BaseHumanoidEnv.reset_model + WalkingTask.reset
  * (envs/common/mujoco_env.py:113-116, envs/common/base_humanoid_env.py:247-309,
@@ -136,6 +138,8 @@ const char* lhw_comm_last_error(void);
 int lhw_comm_handle_size(void);
 int lhw_comm_create(lhw_comm** out, long long n_floats, int rank, int world, int device);
 void* lhw_comm_grad_ptr(lhw_comm* comm);
+long long lhw_comm_size(const lhw_comm* comm);   /* n_floats */
+int lhw_comm_device(const lhw_comm* comm);
 int lhw_comm_export(lhw_comm* comm, void* handle_blob_host);
 int lhw_comm_import(lhw_comm* comm, const void* all_handle_blobs_host);
 int lhw_comm_destroy(lhw_comm* comm);

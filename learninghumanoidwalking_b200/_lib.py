@@ -23,6 +23,8 @@ SIGNATURES = {
     "lhw_sim_obs_dim": (c_int, [c_void_p]),
     "lhw_sim_act_dim": (c_int, [c_void_p]),
     "lhw_sim_smem_bytes_per_env": (c_int, [c_void_p]),
+    "lhw_sim_precision": (c_int, [c_void_p]),
+    "lhw_sim_device": (c_int, [c_void_p]),
     "lhw_sim_reset": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_void_p, c_int, c_void_p, c_void_p]),
     "lhw_sim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -39,6 +41,8 @@ SIGNATURES = {
     "lhw_comm_handle_size": (c_int, []),
     "lhw_comm_create": (c_int, [ctypes.POINTER(c_void_p), c_ll, c_int, c_int, c_int]),
     "lhw_comm_grad_ptr": (c_void_p, [c_void_p]),
+    "lhw_comm_size": (c_ll, [c_void_p]),
+    "lhw_comm_device": (c_int, [c_void_p]),
     "lhw_comm_export": (c_int, [c_void_p, c_void_p]),
     "lhw_comm_import": (c_int, [c_void_p, c_void_p]),
     "lhw_comm_destroy": (c_int, [c_void_p]),
@@ -72,6 +76,32 @@ def lib() -> ctypes.CDLL:
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+TORCH_LIB_PATH = os.path.join(_PKG, "liblhw_b200_torch.so")
+_ops = None
+
+
+def ops():
+    """torch.ops.lhw — the same entry points registered through PyTorch's C++ extension ABI (csrc/torch_ops.cpp): every call
+    checks device / dtype / shape of its tensors before it reaches the C-ABI, and takes the current stream itself.  This is the
+    path the product uses; like the C-ABI library it is mandatory (no fallback).  The only exception is LHW_B200_LIB (the A/B
+    harness timing another build of the C-ABI library): liblhw_b200_torch.so is linked against the in-tree library, so the
+    harness binds the candidate with ctypes instead (use_torch_ops() is False)."""
+    global _ops
+    if _ops is None:
+        import torch
+        if not os.path.exists(TORCH_LIB_PATH):
+            raise LhwError(f"{TORCH_LIB_PATH} is missing: build the extension (python -m learninghumanoidwalking_b200.build). "
+                           "There is no fallback for the torch.ops.lhw entry points.")
+        lib()      # the C-ABI library first: the op library resolves its symbols from it
+        torch.ops.load_library(TORCH_LIB_PATH)
+        _ops = torch.ops.lhw
+    return _ops
+
+
+def use_torch_ops() -> bool:
+    return not os.environ.get("LHW_B200_LIB") and os.environ.get("LHW_TORCH_OPS", "1") != "0"
 
 
 def check(rc: int, what: str = "") -> None:

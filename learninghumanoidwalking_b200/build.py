@@ -20,9 +20,10 @@ import time
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "liblhw_b200.so")
+TORCH_LIB = os.path.join(PKG, "liblhw_b200_torch.so")     # csrc/torch_ops.cpp: the same entry points as torch.ops.lhw.*
 RECORD = os.path.join(PKG, "build_record.json")
 SOURCES = ["sim_kernels.cu", "ppo_kernels.cu", "comm_kernels.cu"]
-HEADERS = ["sim_core.h", "model_pack.h", os.path.join("..", "..", "include", "lhw_b200.h")]
+HEADERS = ["sim_core.h", "model_pack.h", os.path.join("..", "..", "include", "lhw_b200.h"), "torch_ops.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -52,7 +53,7 @@ def read_record() -> dict | None:
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(TORCH_LIB):
         return True
     rec = read_record()
     return rec is None or rec.get("sources") != source_hashes() or rec.get("flags") != NVCC_FLAGS
@@ -65,6 +66,25 @@ def _sass_md5(nvcc: str) -> str | None:
         return hashlib.md5(sass).hexdigest() if sass else None
     except Exception:
         return None
+
+
+def build_torch_ops(verbose: bool = False) -> list:
+    """csrc/torch_ops.cpp -> liblhw_b200_torch.so: TORCH_LIBRARY registrations (torch.ops.lhw.*) over the C-ABI library, plain g++
+    against the torch headers of the running interpreter (no JIT cache: the .so stays in-tree and travels with the snapshot)."""
+    import torch
+    from torch.utils import cpp_extension as E
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = (["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+           + [f"-I{p}" for p in E.include_paths()] + [f"-I{cuda_inc}", os.path.join(CSRC, "torch_ops.cpp"), "-o", TORCH_LIB,
+              f"-L{PKG}", "-llhw_b200", f"-L{tlib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch",
+              "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed on torch_ops.cpp")
+    return cmd
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -91,6 +111,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     link = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(link)
     cmds.append(" ".join(link))
+    cmds.append(" ".join(build_torch_ops(verbose)))
     ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()
     json.dump(dict(library=os.path.basename(LIB), commands=cmds, flags=NVCC_FLAGS, nvcc=ver[-2:] if ver else None,
                    sources=source_hashes(), kernel_source_hash=kernel_source_hash(), sass_md5=_sass_md5(nvcc),

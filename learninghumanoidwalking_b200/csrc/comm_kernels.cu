@@ -248,6 +248,8 @@ int lhw_comm_create(lhw_comm** out, long long n_floats, int rank, int world, int
 }
 
 void* lhw_comm_grad_ptr(lhw_comm* c) { return c ? c->grad : nullptr; }
+long long lhw_comm_size(const lhw_comm* c) { return c ? c->n : 0; }
+int lhw_comm_device(const lhw_comm* c) { return c ? c->device : -1; }
 
 int lhw_comm_export(lhw_comm* c, void* blob_host) {
   if (!c || !blob_host) return cfail(-1, "null argument");

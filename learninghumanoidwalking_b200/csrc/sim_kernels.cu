@@ -357,6 +357,8 @@ int lhw_sim_state_ints(const lhw_sim*) { return NSTATE_I; }
 int lhw_sim_obs_dim(const lhw_sim* s) { return s ? s->obs_dim : Dims<double, NJ_JVRC, 0>::NOBS; }
 int lhw_sim_act_dim(const lhw_sim* s) { return 2 * (s ? s->nj : NJ_JVRC); }
 int lhw_sim_smem_bytes_per_env(const lhw_sim* s) { return (int)s->work_bytes; }
+int lhw_sim_precision(const lhw_sim* s) { return s ? s->precision : 0; }
+int lhw_sim_device(const lhw_sim* s) { return s ? s->device : -1; }
 
 int lhw_sim_bind(lhw_sim* s, void* stream) {
   if (!s) return fail(-1, "null argument");

@@ -131,10 +131,14 @@ class BatchedHumanoidEnv:
         L = _lib.lib()
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.int32).contiguous()
-        with torch.cuda.device(self.device):
-            _lib.check(L.lhw_sim_reset(self._h, self.state_r.data_ptr(), self.state_i.data_ptr(), self.num_envs, self.seed,
-                                       self.first_env_id, _lib.ptr(mask), int(self._fresh and mask is None),
-                                       self.obs.data_ptr(), _lib.current_stream_ptr()), "lhw_sim_reset")
+        if _lib.use_torch_ops():
+            _lib.ops().sim_reset(self._h.value, self.state_r, self.state_i, self.seed, self.first_env_id, mask,
+                                 bool(self._fresh and mask is None), self.obs)
+        else:
+            with torch.cuda.device(self.device):
+                _lib.check(L.lhw_sim_reset(self._h, self.state_r.data_ptr(), self.state_i.data_ptr(), self.num_envs, self.seed,
+                                           self.first_env_id, _lib.ptr(mask), int(self._fresh and mask is None),
+                                           self.obs.data_ptr(), _lib.current_stream_ptr()), "lhw_sim_reset")
         if mask is None:
             self._fresh = False
         return self.obs
@@ -144,6 +148,11 @@ class BatchedHumanoidEnv:
         With autoreset the RolloutWorker semantics apply (see include/lhw_b200.h: lhw_sim_step)."""
         if actions.dtype != self.dtype or not actions.is_contiguous() or actions.device != self.device:
             actions = actions.to(device=self.device, dtype=self.dtype).contiguous()
+        if _lib.use_torch_ops():     # torch.ops.lhw.sim_step: device / dtype / shape checks, then the C-ABI launch
+            _lib.ops().sim_step(self._h.value, self.state_r, self.state_i, self.seed, self.first_env_id, actions, self.max_traj_len,
+                                bool(autoreset), self.obs, self.term_obs, self.reward, self.rew_terms, self.done, self.ended,
+                                self.ep_len, self.ep_rew)
+            return self.obs, self.reward, self.done, self.ended
         assert actions.shape == (self.num_envs, self.act_dim), actions.shape
         L = _lib.lib()
         with torch.cuda.device(self.device):

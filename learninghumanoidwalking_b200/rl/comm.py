@@ -52,11 +52,7 @@ class PeerComm:
     def fused_step(self, param, exp_avg, exp_avg_sq, n_actor, lr, betas, eps, max_norm):
         """All-reduce (peer memory) + clip x2 + Adam x2: three plain launches on the current stream, capturable into a CUDA graph
         (the Adam step number and the barrier epoch live in device memory)."""
-        L = _lib.lib()
-        rc = L.lhw_fused_allreduce_clip_adam(self._h, param.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(n_actor),
-                                             self.n, lr, betas[0], betas[1], eps, max_norm, _lib.current_stream_ptr())
-        if rc:
-            raise _lib.LhwError(f"lhw_fused_allreduce_clip_adam failed: {L.lhw_comm_last_error().decode()}")
+        _lib.ops().fused_exchange(self._h.value, param, exp_avg, exp_avg_sq, int(n_actor), lr, betas[0], betas[1], eps, max_norm)
 
     def status(self):
         """(completed Adam steps, (actor grad norm, critic grad norm) of the last step); raises if a peer did not arrive at the

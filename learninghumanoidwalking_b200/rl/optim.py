@@ -77,15 +77,13 @@ class FusedClipAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         g = self.param_groups[0]
         self.step_count += 1
-        L, st = _lib.lib(), _lib.current_stream_ptr()
+        O = _lib.ops()
         scale = 1.0 / self.world
-        n = self.flat.numel()
-        _lib.check(L.lhw_grad_sumsq(self.grad.data_ptr(), self.norm.data_ptr(), n, scale, st), "lhw_grad_sumsq")
+        O.grad_sumsq(self.grad, self.norm, scale)
         # the step number lives on the device (bias corrections computed in the kernel), so that an eager step and a step
         # replayed from a CUDA graph (PPO._update_graphed) are the same launches with the same arguments
-        _lib.check(L.lhw_clip_adam_dev(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                       self.exp_avg_sq.data_ptr(), self.norm.data_ptr(), n, self.step_dev.data_ptr(), g["lr"],
-                                       g["betas"][0], g["betas"][1], g["eps"], g["max_norm"], scale, st), "lhw_clip_adam_dev")
+        O.clip_adam_dev(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.norm, self.step_dev, g["lr"], g["betas"][0],
+                        g["betas"][1], g["eps"], g["max_norm"], scale)
 
     def total_norm(self) -> torch.Tensor:
         return self.norm.sqrt()

@@ -262,15 +262,14 @@ class PPO:
     # ------------------------------------------------------------------ device data path helpers
     def normalize_advantages(self, returns: torch.Tensor, values: torch.Tensor) -> torch.Tensor:
         """rl/algos/ppo.py:484-485 on device; statistics are global across ranks."""
-        L, st = _lib.lib(), _lib.current_stream_ptr()
+        O = _lib.ops()
         n = returns.numel()
         adv = torch.empty_like(returns)
-        _lib.check(L.lhw_adv_stats(returns.data_ptr(), values.data_ptr(), self._adv_stats.data_ptr(), n, st), "lhw_adv_stats")
+        O.adv_stats(returns, values, self._adv_stats)
         if self.world > 1:
             dist.all_reduce(self._adv_stats[0:2], op=dist.ReduceOp.SUM)
         # equal shards are enforced in __init__, so the global count is n * world
-        _lib.check(L.lhw_adv_apply(returns.data_ptr(), values.data_ptr(), adv.data_ptr(), self._adv_stats.data_ptr(), n,
-                                   n * self.world, self.eps, st), "lhw_adv_apply")
+        O.adv_apply(returns, values, adv, self._adv_stats, n * self.world, self.eps)
         return adv
 
     def gather_minibatch(self, obs, act, ret, adv, idx: torch.Tensor):
@@ -280,9 +279,7 @@ class PPO:
             self._mb = (torch.empty(B, obs.shape[1], **f32), torch.empty(B, act.shape[1], **f32),
                         torch.empty(B, 1, **f32), torch.empty(B, 1, **f32))
         o, a, r, d = self._mb
-        _lib.check(_lib.lib().lhw_gather_minibatch(obs.data_ptr(), act.data_ptr(), ret.data_ptr(), adv.data_ptr(),
-                                                   idx.data_ptr(), o.data_ptr(), a.data_ptr(), r.data_ptr(), d.data_ptr(), B,
-                                                   obs.shape[1], act.shape[1], _lib.current_stream_ptr()), "lhw_gather_minibatch")
+        _lib.ops().gather_minibatch(obs, act, ret, adv, idx, o, a, r, d)
         return o, a, r, d
 
     def minibatch_indices(self, num_samples: int, itr: int, epoch: int):

@@ -45,9 +45,7 @@ class DeviceRolloutBuffer:
 
     def finish(self):
         """PPOBuffer.finish_path for every path of every env in one launch."""
-        _lib.check(_lib.lib().lhw_gae(self.rewards.data_ptr(), self.values.data_ptr(), self.ended.data_ptr(),
-                                      self.boot.data_ptr(), self.last_val.data_ptr(), self.returns.data_ptr(), self.T, self.N,
-                                      self.gamma, self.lam, _lib.current_stream_ptr()), "lhw_gae")
+        _lib.ops().gae(self.rewards, self.values, self.ended, self.boot, self.last_val, self.returns, self.gamma, self.lam)
 
     def get_data(self, env_major: bool = True) -> BatchData:
         """Flatten to [N*T, .].  env_major=True reproduces the reference's ordering (torch.cat over workers:

@@ -62,3 +62,24 @@ def test_run_experiment_keeps_the_reference_flags():
     if os.path.exists(ref_file):
         assert set(re.findall(r"\"(--[a-z-]+)\"", open(ref_file).read())) == ref_flags
     assert ref_flags <= ours, ref_flags - ours
+
+
+def test_torch_ops_library_registers_every_entry_point_and_rejects_bad_tensors():
+    """csrc/torch_ops.cpp (TORCH_LIBRARY): torch.ops.lhw.* exist after loading liblhw_b200_torch.so, and their argument checks
+    fire before anything reaches a kernel — here with CPU tensors (no GPU needed to see the TORCH_CHECK messages)."""
+    import pytest
+    import torch
+    import __graft_entry__
+    __graft_entry__.build()
+    from learninghumanoidwalking_b200 import _lib
+    O = _lib.ops()
+    for name in ("sim_reset", "sim_step", "gae", "adv_stats", "adv_apply", "gather_minibatch", "grad_sumsq", "clip_adam_dev",
+                 "fused_exchange"):
+        assert hasattr(O, name), name
+    r = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        O.gae(r, r, r.int(), r, torch.zeros(3), r.clone(), 0.99, 0.95)
+    with pytest.raises(RuntimeError, match="null sim handle"):
+        O.sim_step(0, r, r.int(), 0, 0, r, 400, True, r, None, r, None, r.int(), r.int(), None, None)
+    with pytest.raises(RuntimeError, match="null comm handle"):
+        O.fused_exchange(0, r, r, r, 0, 3e-4, 0.9, 0.999, 1e-5, 0.5)
