@@ -42,7 +42,7 @@ class BatchedHumanoidEnv:
                  first_env_id: int = 0, device: int | torch.device | None = None, max_traj_len: int = 400,
                  tolerance: float | None = None, max_iter: int | None = None, observation_noise: bool = True,
                  domain_randomization: bool = True, init_noise: bool = True, pd_gain_randomization: float = 0.0,
-                 iteration_count: float = float("inf")):
+                 iteration_count: float = float("inf"), path_to_yaml=None):
         if not torch.cuda.is_available():
             raise _lib.LhwError("BatchedHumanoidEnv needs a CUDA device (no CPU fallback on the rollout path)")
         if device is None:
@@ -53,6 +53,10 @@ class BatchedHumanoidEnv:
         self.dtype = torch.float64 if precision == 64 else torch.float32
         self.model_name = model
         self.mj = load_model(model)
+        if path_to_yaml is not None:
+            # partial(Env, path_to_yaml) (run_experiment.py:115): the user's YAML over the compiled model's cfg block
+            from .config import apply_config, load_yaml
+            self.mj = apply_config(self.mj, load_yaml(path_to_yaml))
         self._iteration_count = float(iteration_count)
         if tolerance is None and precision == 32:
             tolerance = 1e-6  # fp32 cannot reach the reference's 1e-10; gradient floor is ~1e-6 of the force scale
@@ -86,6 +90,11 @@ class BatchedHumanoidEnv:
         self.observation_space = np.zeros(self.obs_dim * self.history_len)
         self.nq, self.nv = 7 + self.act_dim, 6 + self.act_dim
         self._setup_reference_attributes(model, cfg)
+        # env.interface / env.task / env.model / env.data of the reference's env protocol, as views of env 0
+        from ..tasks.descriptors import DataView, DeviceRobotInterface, make_task, model_view
+        self.interface = DeviceRobotInterface(self, 0)
+        self.task = make_task(self, 0)
+        self.model, self.data = model_view(self), DataView(self, 0)
 
     def _setup_reference_attributes(self, model: str, cfg: dict) -> None:
         """obs_mean / obs_std, reward names and the robot's mirror lists exactly as the reference env classes set them

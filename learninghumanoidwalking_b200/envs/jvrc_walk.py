@@ -14,11 +14,10 @@ class JvrcWalkEnv:
 
     def __init__(self, path_to_yaml: str | None = None, precision: int = 64, seed: int = 0, env_id: int = 0, device=None,
                  **env_kwargs):
-        if path_to_yaml is not None:
-            raise NotImplementedError("custom YAML: recompile the model with tools/compile_model.py")
         self._b = BatchedHumanoidEnv(1, self.MODEL, precision=precision, seed=seed, first_env_id=env_id, device=device,
-                                     **env_kwargs)
-        for k in ("observation_space", "action_space", "obs_mean", "obs_std", "robot", "history_len", "base_obs_len", "dt"):
+                                     path_to_yaml=path_to_yaml, **env_kwargs)
+        for k in ("observation_space", "action_space", "obs_mean", "obs_std", "robot", "history_len", "base_obs_len", "dt",
+                  "interface", "task", "model", "data"):
             setattr(self, k, getattr(self._b, k))
 
     def reset(self) -> np.ndarray:

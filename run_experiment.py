@@ -116,8 +116,6 @@ def run_experiment(args):
     args.logdir = Path(args.logdir) / f"{timestamp}_{args.env}"
     if rank == 0:
         print_system_info(args)
-    if args.yaml is not None:
-        raise NotImplementedError("custom YAML: recompile the model constants with tools/compile_model.py")
     if args.recurrent or args.imitate:
         raise NotImplementedError("--recurrent / --imitate are outside the accelerated path (SURVEY.md §2)")
     Env = import_env(args.env)
@@ -127,7 +125,7 @@ def run_experiment(args):
     first, n_local = env_shard(rank, world, args.num_procs)
     seed = args.seed if args.seed is not None else 0
     env_fn = partial(Env, n_local, precision=args.precision, seed=seed, first_env_id=first, device=local,
-                     max_traj_len=args.max_traj_len)
+                     max_traj_len=args.max_traj_len, path_to_yaml=args.yaml)
     _env = env_fn()
     if not args.no_mirror:
         try:
@@ -143,6 +141,9 @@ def run_experiment(args):
         Path.mkdir(args.logdir, parents=True, exist_ok=True)
         with open(Path(args.logdir, "experiment.pkl"), "wb") as f:
             pickle.dump(args, f)
+        if args.yaml is not None:      # run_experiment.py:141-144: the YAML rides along with the run
+            import shutil
+            shutil.copyfile(args.yaml, Path(args.logdir, Path(args.yaml).name))
     algo = PPO(env_fn, args, seed=args.seed)
     if args.continued is not None:
         actor = torch.load(args.continued, weights_only=False)

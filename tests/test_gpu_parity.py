@@ -96,7 +96,32 @@ def test_single_env_reference_protocol():
         assert np.isfinite(obs).all()
     with pytest.raises(TypeError):
         env.step([0.0] * 12)
+    # env.task / env.interface / env.model / env.data of the env protocol (envs/jvrc/jvrc_walk.py:24-40)
+    from learninghumanoidwalking_b200.tasks.base_task import BaseTask
+    assert isinstance(env.task, BaseTask) and env.task._client is env.interface
+    assert env.task.calc_reward(None, None, None) == info and env.task.done() == d
+    assert env.interface.get_qpos().shape == (19,) and env.interface.get_qvel().shape == (18,) and env.interface.nu() == 12
+    assert np.array_equal(env.data.qpos, env.interface.get_qpos()) and env.model.opt.timestep == 0.001
+    assert env.interface.get_act_joint_positions().shape == (12,) and 0 <= env.task._phase < 88
     env.close()
+
+
+def test_path_to_yaml_changes_the_device_constants(tmp_path):
+    """partial(Env, path_to_yaml) (run_experiment.py:115): softer PD gains from a user YAML give a different trajectory from the
+    same seed; the reference's own values in a YAML give the identical one."""
+    from learninghumanoidwalking_b200.envs import JvrcWalkEnv
+    same, soft = tmp_path / "same.yaml", tmp_path / "soft.yaml"
+    same.write_text("kp: [200, 200, 200, 250, 80, 80, 200, 200, 200, 250, 80, 80]\naction_smoothing: 0.5\n")
+    soft.write_text("kp: [100, 100, 100, 125, 40, 40, 100, 100, 100, 125, 40, 40]\n")
+    outs = []
+    for y in (None, same, soft):
+        env = JvrcWalkEnv(y, seed=4)
+        env.reset()
+        for _ in range(5):
+            obs, _, _, _ = env.step(0.1 * np.ones(12))
+        outs.append(obs)
+        env.close()
+    assert np.array_equal(outs[0], outs[1]) and np.abs(outs[0] - outs[2]).max() > 1e-3
 
 
 def test_determinism_same_seed_bitwise():
