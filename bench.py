@@ -15,8 +15,8 @@ std_dev 0.223), synthetic, generated up front.
           the launches, against the measured HBM peak (MEASURED_PEAKS.json).  The kernel is ALU/latency bound;
           the honest secondary bound is reported beside it as roofline.issue (warp-instruction issue rate, instruction
           count per env-step from the committed ncu capture); roofline.traffic = DRAM bytes of that capture.  Both come
-          from profiles/ncu_counters.json and are only used when that capture was taken on the kernel sources of THIS
-          build (content hash, learninghumanoidwalking_b200/build.py); otherwise they are null and say why.
+          from profiles/ncu_counters.json and are only used when that capture was taken on the step kernels of THIS
+          build (md5 of their SASS, learninghumanoidwalking_b200/build.py); otherwise they are null and say why.
   train_iter  (every N) whole PPO iterations the way the reference defines fps (rl/algos/ppo.py:468-595: sampling +
           optimisation): 4096 envs/GPU x 400 steps, GAE, advantage normalisation, 3 epochs of minibatch updates with
           run_experiment.py's default flags, every optimiser step containing the gradient exchange across the N GPUs;
@@ -46,14 +46,15 @@ ALG_BYTES = {32: 1220, 64: 2288}   # state read+write, action re
 
 def ncu_counters(workload: str, precision: int):
     """(dram bytes, warp instructions) per 4096-env launch from the committed ncu capture, or (None, reason).  The capture is
-    only valid for the kernel sources it was taken on: profiles/ncu_counters.json records their content hash.  Under ncu the
+    only valid for the kernels it was taken on: profiles/ncu_counters.json records the md5 of their SASS (build_record.json).  Under ncu the
     state record is L2 resident when the launch starts (no flush between replays), so the DRAM traffic is BELOW the
     algorithmic bytes; nothing is re-read."""
     try:
-        from learninghumanoidwalking_b200.build import kernel_source_hash
+        from learninghumanoidwalking_b200.build import step_kernel_sass_md5
         c = json.load(open(os.path.join(ROOT, "profiles", "ncu_counters.json")))
-        if c.get("kernel_source_hash") != kernel_source_hash():
-            return None, f"profiles/ncu_counters.json was captured on kernel sources {c.get('kernel_source_hash')}, this build is {kernel_source_hash()}"
+        if c.get("step_kernel_sass_md5") != step_kernel_sass_md5():
+            return None, (f"profiles/ncu_counters.json was captured on step-kernel SASS {c.get('step_kernel_sass_md5')}, "
+                          f"this build is {step_kernel_sass_md5()}")
         w = c["launch_4096_envs"].get(f"{workload}/fp{precision}")
         if w is None:
             return None, "no capture of this workload / precision"

@@ -87,9 +87,14 @@ long long lhw_launch_count(void);
  * per env a reverse scan with the path broken wherever ended[t] != 0, bootstrapping with boot[t] there
  * ((not done) * critic(next_state), rl/workers/rollout_worker.py:166) and with last_val[n] after t = T-1
  * when the final transition did not end an episode (rollout_worker.py:183-186).
- * rewards, values, boot [T,N] f32; ended [T,N] int32; last_val [N]; returns [T,N] out. */
+ * rewards, values, boot [T,N] f32; ended [T,N] int32; last_val [N]; returns [T,N] out.
+ * adv_partials (may be NULL): lhw_gae_partial_words(N) doubles; the launch then also leaves per-block (sum, sumsq) of
+ * returns - values there, which lhw_adv_stats_from_gae folds into stats[0:2] — the advantage normalisation
+ * (rl/algos/ppo.py:484-485) then costs one 12 B/sample pass (lhw_adv_apply) instead of a statistics pass plus that. */
 int lhw_gae(const float* rewards, const float* values, const int32_t* ended, const float* boot, const float* last_val,
-            float* returns, int T, int N, float gamma, float lam, void* stream);
+            float* returns, int T, int N, float gamma, float lam, double* adv_partials_or_null, void* stream);
+int lhw_gae_partial_words(int N);
+int lhw_adv_stats_from_gae(const double* adv_partials, int N, double* stats, void* stream);
 
 /* lhw_adv_norm: rl/algos/ppo.py:484-485 — adv = returns - values; (adv - mean) / (std_unbiased + eps).
  * stats: device scratch of lhw_adv_stats_words() doubles, {sum, sumsq, mean, std, per-block partials...}

@@ -31,7 +31,10 @@ SIGNATURES = {
     "lhw_sim_bind": (c_int, [c_void_p, c_void_p]),
     "lhw_sim_set_step_height": (c_int, [c_void_p, ctypes.c_double]),
     "lhw_launch_count": (c_ll, []),
-    "lhw_gae": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
+    "lhw_gae": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
+                        c_void_p]),
+    "lhw_gae_partial_words": (c_int, [c_int]),
+    "lhw_adv_stats_from_gae": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "lhw_adv_stats_words": (c_int, []),
     "lhw_adv_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "lhw_adv_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_float, c_void_p]),

@@ -36,13 +36,12 @@ def source_hashes() -> dict:
     return out
 
 
-def kernel_source_hash() -> str:
-    """One hash over everything the step kernels are compiled from (sim_core.h, sim_kernels.cu, model_pack.h) + the flags:
-    the key that ties an ncu capture to a build."""
-    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    for f in ("sim_core.h", "sim_kernels.cu", "model_pack.h"):
-        h.update(open(os.path.join(CSRC, f), "rb").read())
-    return h.hexdigest()[:16]
+def step_kernel_sass_md5() -> str | None:
+    """md5 of the device code (SASS) of the step / reset kernels as built: the key that ties an ncu capture to a build.  Host-side
+    edits of sim_kernels.cu do not move it; any change of the kernels does.  Read from the build record (the GPU box reuses the
+    library that was built here), None when there is no record."""
+    rec = read_record()
+    return rec.get("step_kernel_sass_md5") if rec else None
 
 
 def read_record() -> dict | None:
@@ -59,10 +58,10 @@ def needs_build() -> bool:
     return rec is None or rec.get("sources") != source_hashes() or rec.get("flags") != NVCC_FLAGS
 
 
-def _sass_md5(nvcc: str) -> str | None:
+def _sass_md5(nvcc: str, target: str = LIB) -> str | None:
     cuobjdump = os.path.join(os.path.dirname(nvcc), "cuobjdump")
     try:
-        sass = subprocess.run([cuobjdump, "-sass", LIB], capture_output=True, timeout=600).stdout
+        sass = subprocess.run([cuobjdump, "-sass", target], capture_output=True, timeout=600).stdout
         return hashlib.md5(sass).hexdigest() if sass else None
     except Exception:
         return None
@@ -114,7 +113,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmds.append(" ".join(build_torch_ops(verbose)))
     ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()
     json.dump(dict(library=os.path.basename(LIB), commands=cmds, flags=NVCC_FLAGS, nvcc=ver[-2:] if ver else None,
-                   sources=source_hashes(), kernel_source_hash=kernel_source_hash(), sass_md5=_sass_md5(nvcc),
+                   sources=source_hashes(), sass_md5=_sass_md5(nvcc),
+                   step_kernel_sass_md5=_sass_md5(nvcc, os.path.join(PKG, "build", "sim_kernels.o")),
                    library_sha256=hashlib.sha256(open(LIB, "rb").read()).hexdigest(), host=platform.node(),
                    built_at=time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), seconds=round(time.time() - t0, 1)),
               open(RECORD, "w"), indent=1)

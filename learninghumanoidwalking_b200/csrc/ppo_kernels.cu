@@ -26,7 +26,7 @@ constexpr int GAE_SEG = 16;
 __global__ void __launch_bounds__(32 * GAE_SEG) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
                                                            const int32_t* __restrict__ ended, const float* __restrict__ boot,
                                                            const float* __restrict__ last_val, float* __restrict__ ret, int T,
-                                                           int N, double gamma, double lam) {
+                                                           int N, double gamma, double lam, double* __restrict__ adv_part) {
   __shared__ double shA[GAE_SEG][32], shC[GAE_SEG][32];
   const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
@@ -50,20 +50,51 @@ __global__ void __launch_bounds__(32 * GAE_SEG) gae_kernel(const float* __restri
   shA[seg][lane] = A;
   shC[seg][lane] = live ? C : 1.0;
   __syncthreads();
-  if (!live) return;
-  // carry into this segment = A of everything later, composed from the last segment backwards (fixed order)
-  double carry = 0.0;
-  for (int s2 = GAE_SEG - 1; s2 > seg; s2--) carry = shA[s2][lane] + shC[s2][lane] * carry;
-  double gae = carry;
-  double next_val = t_hi == T - 1 ? (double)last_val[n] : (double)val[(size_t)(t_hi + 1) * N + n];
-  for (int t = t_hi; t >= t_lo; t--) {
-    const size_t i = (size_t)t * N + n;
-    if (ended[i]) { next_val = (double)boot[i]; gae = 0.0; }
-    const double v = (double)val[i];
-    gae = ((double)rew[i] + gamma * next_val - v) + gl * gae;
-    ret[i] = (float)(gae + v);
-    next_val = v;
+  double s1 = 0.0, s2sum = 0.0;   // sum / sum of squares of the advantage (returns - values) of this thread's samples
+  if (live) {
+    // carry into this segment = A of everything later, composed from the last segment backwards (fixed order)
+    double carry = 0.0;
+    for (int s2 = GAE_SEG - 1; s2 > seg; s2--) carry = shA[s2][lane] + shC[s2][lane] * carry;
+    double gae = carry;
+    double next_val = t_hi == T - 1 ? (double)last_val[n] : (double)val[(size_t)(t_hi + 1) * N + n];
+    for (int t = t_hi; t >= t_lo; t--) {
+      const size_t i = (size_t)t * N + n;
+      if (ended[i]) { next_val = (double)boot[i]; gae = 0.0; }
+      const double v = (double)val[i];
+      gae = ((double)rew[i] + gamma * next_val - v) + gl * gae;
+      const float r = (float)(gae + v);
+      ret[i] = r;
+      const double a = (double)r - v;     // the advantage as the learner forms it: float32 returns - float32 values
+      s1 += a;
+      s2sum += a * a;
+      next_val = v;
+    }
   }
+  if (adv_part) {
+    // the statistics of rl/algos/ppo.py:484-485 as a by-product of the pass that produces the returns: fixed-order block
+    // reduction, one (sum, sumsq) pair per block -> the normalisation needs no statistics pass of its own
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2sum += __shfl_xor_sync(0xffffffffu, s2sum, o); }
+    if (lane == 0) { shA[seg][0] = s1; shC[seg][0] = s2sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int k = 0; k < GAE_SEG; k++) { a += shA[k][0]; b += shC[k][0]; }
+      adv_part[blockIdx.x] = a;
+      adv_part[gridDim.x + blockIdx.x] = b;
+    }
+  }
+}
+
+// stats[0:2] = (sum, sumsq) from the per-block pairs lhw_gae left behind; one warp, index order -> deterministic
+__global__ void adv_from_gae_kernel(const double* __restrict__ part, int nblk, double* __restrict__ stats) {
+  double a = 0.0, b = 0.0;
+  for (int k = threadIdx.x; k < nblk; k += 32) { a += part[k]; b += part[nblk + k]; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (threadIdx.x == 0) { stats[0] = a; stats[1] = b; }
 }
 
 // deterministic block reduction helper (fixed tree)
@@ -203,11 +234,20 @@ int perr(int code, const char* what, cudaError_t e) {
 extern "C" {
 
 int lhw_gae(const float* rewards, const float* values, const int32_t* ended, const float* boot, const float* last_val,
-            float* returns, int T, int N, float gamma, float lam, void* stream) {
+            float* returns, int T, int N, float gamma, float lam, double* adv_partials_or_null, void* stream) {
   if (T <= 0 || N <= 0) return 0;
   gae_kernel<<<(N + 31) / 32, 32 * GAE_SEG, 0, (cudaStream_t)stream>>>(rewards, values, ended, boot, last_val, returns, T, N,
-                                                                (double)gamma, (double)lam);
+                                                                (double)gamma, (double)lam, adv_partials_or_null);
   KCHECK("gae_kernel");
+  return 0;
+}
+
+int lhw_gae_partial_words(int N) { return 2 * ((N + 31) / 32); }
+
+int lhw_adv_stats_from_gae(const double* adv_partials, int N, double* stats, void* stream) {
+  if (!adv_partials || !stats || N <= 0) return 0;
+  adv_from_gae_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(adv_partials, (N + 31) / 32, stats);
+  KCHECK("adv_from_gae_kernel");
   return 0;
 }
 

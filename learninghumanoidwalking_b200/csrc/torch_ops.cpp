@@ -83,7 +83,7 @@ void sim_step(int64_t sim, Tensor state_r, Tensor state_i, int64_t seed, int64_t
 }
 
 void gae(const Tensor& rewards, const Tensor& values, const Tensor& ended, const Tensor& boot, const Tensor& last_val, Tensor returns,
-         double gamma, double lam) {
+         double gamma, double lam, const OptTensor& adv_partials) {
   TORCH_CHECK(rewards.dim() == 2, "lhw: rewards must be [T, N]");
   const int64_t T = rewards.size(0), N = rewards.size(1);
   const int dev = rewards.is_cuda() ? rewards.get_device() : -1;
@@ -92,9 +92,19 @@ void gae(const Tensor& rewards, const Tensor& values, const Tensor& ended, const
   check_cuda(boot, "boot", at::kFloat, dev); check_shape(boot, "boot", {T, N});
   check_cuda(last_val, "last_val", at::kFloat, dev); check_shape(last_val, "last_val", {N});
   check_cuda(returns, "returns", at::kFloat, dev); check_shape(returns, "returns", {T, N});
+  if (adv_partials) { check_cuda(*adv_partials, "adv_partials", at::kDouble, dev); check_shape(*adv_partials, "adv_partials", {lhw_gae_partial_words((int)N)}); }
   c10::cuda::CUDAGuard guard(dev);
   ok(lhw_gae(rewards.data_ptr<float>(), values.data_ptr<float>(), ended.data_ptr<int32_t>(), boot.data_ptr<float>(),
-             last_val.data_ptr<float>(), returns.data_ptr<float>(), (int)T, (int)N, (float)gamma, (float)lam, stream_of(rewards)), "lhw_gae");
+             last_val.data_ptr<float>(), returns.data_ptr<float>(), (int)T, (int)N, (float)gamma, (float)lam,
+             adv_partials ? adv_partials->data_ptr<double>() : nullptr, stream_of(rewards)), "lhw_gae");
+}
+
+void adv_stats_from_gae(const Tensor& adv_partials, int64_t n_envs, Tensor stats) {
+  const int dev = adv_partials.is_cuda() ? adv_partials.get_device() : -1;
+  check_cuda(adv_partials, "adv_partials", at::kDouble, dev); check_shape(adv_partials, "adv_partials", {lhw_gae_partial_words((int)n_envs)});
+  check_cuda(stats, "stats", at::kDouble, dev); check_shape(stats, "stats", {lhw_adv_stats_words()});
+  c10::cuda::CUDAGuard guard(dev);
+  ok(lhw_adv_stats_from_gae(adv_partials.data_ptr<double>(), (int)n_envs, stats.data_ptr<double>(), stream_of(adv_partials)), "lhw_adv_stats_from_gae");
 }
 
 void adv_stats(const Tensor& returns, const Tensor& values, Tensor stats) {
@@ -182,7 +192,9 @@ TORCH_LIBRARY(lhw, m) {
   m.def("sim_step(int sim, Tensor(a!) state_r, Tensor(b!) state_i, int seed, int first_env_id, Tensor actions, int max_traj_len, "
         "bool autoreset, Tensor(c!) obs, Tensor(d!)? term_obs, Tensor(e!) reward, Tensor(f!)? rew_terms, Tensor(g!) done, Tensor(h!) ended, "
         "Tensor(i!)? ep_len, Tensor(j!)? ep_rew) -> ()");
-  m.def("gae(Tensor rewards, Tensor values, Tensor ended, Tensor boot, Tensor last_val, Tensor(a!) returns, float gamma, float lam) -> ()");
+  m.def("gae(Tensor rewards, Tensor values, Tensor ended, Tensor boot, Tensor last_val, Tensor(a!) returns, float gamma, float lam, "
+        "Tensor(b!)? adv_partials) -> ()");
+  m.def("adv_stats_from_gae(Tensor adv_partials, int n_envs, Tensor(a!) stats) -> ()");
   m.def("adv_stats(Tensor returns, Tensor values, Tensor(a!) stats) -> ()");
   m.def("adv_apply(Tensor returns, Tensor values, Tensor(a!) adv, Tensor(b!) stats, int count_total, float eps) -> ()");
   m.def("gather_minibatch(Tensor obs, Tensor act, Tensor ret, Tensor adv, Tensor idx, Tensor(a!) obs_b, Tensor(b!) act_b, Tensor(c!) ret_b, "
@@ -200,6 +212,7 @@ TORCH_LIBRARY_IMPL(lhw, CompositeExplicitAutograd, m) {
   m.impl("sim_reset", &sim_reset);
   m.impl("sim_step", &sim_step);
   m.impl("gae", &gae);
+  m.impl("adv_stats_from_gae", &adv_stats_from_gae);
   m.impl("adv_stats", &adv_stats);
   m.impl("adv_apply", &adv_apply);
   m.impl("gather_minibatch", &gather_minibatch);

@@ -260,12 +260,19 @@ class PPO:
         self._ug, self._ug_calls = None, 0
 
     # ------------------------------------------------------------------ device data path helpers
-    def normalize_advantages(self, returns: torch.Tensor, values: torch.Tensor) -> torch.Tensor:
-        """rl/algos/ppo.py:484-485 on device; statistics are global across ranks."""
+    def normalize_advantages(self, returns: torch.Tensor, values: torch.Tensor, from_rollout: bool = False) -> torch.Tensor:
+        """rl/algos/ppo.py:484-485 on device; statistics are global across ranks.  from_rollout=True: `returns` / `values` are
+        the batch the device worker has just produced, whose GAE launch already left the advantage's (sum, sumsq) behind —
+        the normalisation is then a single 12 B/sample pass."""
         O = _lib.ops()
         n = returns.numel()
         adv = torch.empty_like(returns)
-        O.adv_stats(returns, values, self._adv_stats)
+        buf = getattr(self.workers[0], "_buf", None) if getattr(self, "workers", None) else None
+        if from_rollout and buf is not None and buf.T * buf.N == n:
+            # (sum, sumsq) of returns - values were produced by the GAE launch of this very batch: no statistics pass
+            O.adv_stats_from_gae(buf.adv_partials, buf.N, self._adv_stats)
+        else:
+            O.adv_stats(returns, values, self._adv_stats)
         if self.world > 1:
             dist.all_reduce(self._adv_stats[0:2], op=dist.ReduceOp.SUM)
         # equal shards are enforced in __init__, so the global count is n * world
@@ -346,7 +353,7 @@ class PPO:
             sample_time = time.time() - t0
             if verbose and self.rank == 0:
                 print(f"Sampling took {sample_time:.2f}s for {num_samples * self.world} steps.")
-            advantages = self.normalize_advantages(returns, values)
+            advantages = self.normalize_advantages(returns, values, from_rollout=True)
             self.total_steps += num_samples * self.world
             self.old_policy.load_state_dict(self.policy.state_dict())
             # in place: a captured update graph holds the addresses of these tensors

@@ -42,10 +42,15 @@ class DeviceRolloutBuffer:
         self.ep_len = torch.zeros(T, N, dtype=torch.int32, device=device)
         self.ep_rew = torch.zeros(T, N, **f32)
         self.last_val = torch.zeros(N, **f32)
+        # per-block (sum, sumsq) of returns - values, left behind by the GAE launch for the advantage normalisation
+        self.adv_partials = torch.zeros(_lib.lib().lhw_gae_partial_words(N), dtype=torch.float64, device=device)
+        self.generation = 0     # bumped by every finish(): tells the learner whether adv_partials belong to the batch it holds
 
     def finish(self):
         """PPOBuffer.finish_path for every path of every env in one launch."""
-        _lib.ops().gae(self.rewards, self.values, self.ended, self.boot, self.last_val, self.returns, self.gamma, self.lam)
+        _lib.ops().gae(self.rewards, self.values, self.ended, self.boot, self.last_val, self.returns, self.gamma, self.lam,
+                       self.adv_partials)
+        self.generation += 1
 
     def get_data(self, env_major: bool = True) -> BatchData:
         """Flatten to [N*T, .].  env_major=True reproduces the reference's ordering (torch.cat over workers:

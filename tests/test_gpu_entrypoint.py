@@ -31,7 +31,7 @@ def test_train_then_eval(tmp_path, env_name, obs_dim, act_dim, capsys):
     args = pickle.load(open(runs[0] / "experiment.pkl", "rb"))
     assert args.env == env_name and args.num_procs == 64
     actor = torch.load(runs[0] / "actor_1.pt", weights_only=False)
-    assert actor(torch.zeros(3, obs_dim, device="cuda")).shape == (3, act_dim)
+    assert actor(torch.zeros(3, obs_dim)).shape == (3, act_dim)        # a CPU copy (loadable on a box without a GPU)
     assert rx.get_latest_actor(runs[0]).name == "actor_1.pt"
     train_out = capsys.readouterr().out
     # the stdout lines scripts/benchmark_training.py:75-79 parses ARE the reference's metric definition

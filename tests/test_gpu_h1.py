@@ -141,7 +141,7 @@ def test_ppo_trains_on_the_h1_environment(tmp_path):
         ppo.env.close()
     assert torch.equal(finals[0], finals[1])     # same seed, bit-identical weights
     actor = torch.load(tmp_path / "actor_0.pt", weights_only=False)   # saved at eval_freq boundaries (itr 0)
-    assert actor(batch.states[:4]).shape == (4, 10)
+    assert actor.cuda()(batch.states[:4]).shape == (4, 10)
 
 
 def test_h1_pd_gain_randomisation_matches_oracle():

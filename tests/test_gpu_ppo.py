@@ -24,8 +24,14 @@ def _gae_gpu(rew, val, ended, boot, last, gamma, lam):
     d = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device="cuda")
     r, v, e, b, lv = d(rew), d(val), d(ended, torch.int32), d(boot), d(last)
     ret = torch.empty_like(r)
+    part = torch.zeros(L.lib().lhw_gae_partial_words(N), dtype=torch.float64, device="cuda")
     L.check(L.lib().lhw_gae(r.data_ptr(), v.data_ptr(), e.data_ptr(), b.data_ptr(), lv.data_ptr(), ret.data_ptr(), T, N,
-                            gamma, lam, L.current_stream_ptr()))
+                            gamma, lam, part.data_ptr(), L.current_stream_ptr()))
+    # the advantage statistics the launch leaves behind (sum, sumsq of returns - values per block) equal a direct reduction
+    adv = ret.double() - v.double()
+    nb = part.numel() // 2
+    assert abs(part[:nb].sum().item() - adv.sum().item()) < 1e-6 * max(1.0, adv.abs().sum().item())
+    assert abs(part[nb:].sum().item() - (adv * adv).sum().item()) < 1e-9 * max(1.0, (adv * adv).sum().item())
     return ret.cpu().numpy()
 
 
@@ -171,6 +177,9 @@ def test_ppo_update_changes_weights_and_returns_seven_scalars(tmp_path):
     before = ppo._flat_param.clone()
     batch = ppo.sample_parallel_with_workers()
     adv = ppo.normalize_advantages(batch.returns.contiguous(), batch.values.contiguous())
+    # the statistics left behind by the GAE launch of this batch (single 12 B/sample normalisation pass) give the same result
+    adv_fused = ppo.normalize_advantages(batch.returns.contiguous(), batch.values.contiguous(), from_rollout=True)
+    assert (adv - adv_fused).abs().max().item() < 1e-5 and abs(adv_fused.double().std().item() - 1) < 1e-4
     env = ppo.env
     out = ppo.update_actor_critic(batch.states[:256], batch.actions[:256], batch.returns[:256], adv[:256], 1,
                                   mirror_observation=env.mirror_clock_observation, mirror_action=env.mirror_action)
@@ -184,9 +193,13 @@ def test_ppo_update_changes_weights_and_returns_seven_scalars(tmp_path):
     assert np.isfinite(log[0]["eval_rew"]) and 0 < log[0]["eval_len"] <= 50
     assert (tmp_path / "actor.pt").exists() and (tmp_path / "critic.pt").exists() and ppo._best_eval == log[0]["eval_rew"]
     best = torch.load(tmp_path / "actor.pt", weights_only=False)
-    assert all(torch.equal(a, b) for a, b in zip(best.state_dict().values(), ppo.policy.state_dict().values()))
+    # checkpoints are self-contained CPU copies under the reference's class path (rl/policies/__init__.py: export_module)
+    assert type(best).__module__ == "rl.policies.actor" and all(not p.is_cuda for p in best.parameters())
+    assert list(best.state_dict()) == list(ppo.policy.state_dict())
+    assert all(torch.equal(a, b.cpu()) for a, b in zip(best.state_dict().values(), ppo.policy.state_dict().values()))
+    assert torch.equal(best.obs_mean, ppo.policy.obs_mean.cpu())
     actor = torch.load(tmp_path / "actor_0.pt", weights_only=False)
-    assert actor(batch.states[:4]).shape == (4, 12)
+    assert actor(batch.states[:4].cpu()).shape == (4, 12) and actor.cuda()(batch.states[:4]).shape == (4, 12)
 
 
 def test_same_seed_gives_bit_identical_weights():

@@ -41,7 +41,7 @@ def main():
     last, ret, adv = torch.randn(N, device=dev, generator=g), torch.empty(T, N, device=dev), torch.empty(T, N, device=dev)
     out = {"peak_gbs": peak, "T": T, "N": N}
 
-    ms = timed(lambda: L.lhw_gae(rew.data_ptr(), val.data_ptr(), ended.data_ptr(), boot.data_ptr(), last.data_ptr(), ret.data_ptr(), T, N, 0.99, 0.95, st), flush)
+    ms = timed(lambda: L.lhw_gae(rew.data_ptr(), val.data_ptr(), ended.data_ptr(), boot.data_ptr(), last.data_ptr(), ret.data_ptr(), T, N, 0.99, 0.95, None, st), flush)
     out["gae"] = {"ms": ms, "bytes": 20 * n, "gbs": 20 * n / ms / 1e6, "frac": 20 * n / ms / 1e6 / peak}
 
     stats = torch.zeros(L.lhw_adv_stats_words(), dtype=torch.float64, device=dev)
