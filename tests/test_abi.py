@@ -73,12 +73,12 @@ def test_torch_ops_library_registers_every_entry_point_and_rejects_bad_tensors()
     __graft_entry__.build()
     from learninghumanoidwalking_b200 import _lib
     O = _lib.ops()
-    for name in ("sim_reset", "sim_step", "gae", "adv_stats", "adv_apply", "gather_minibatch", "grad_sumsq", "clip_adam_dev",
+    for name in ("sim_reset", "sim_step", "gae", "adv_stats", "adv_stats_from_gae", "adv_apply", "gather_minibatch", "grad_sumsq", "clip_adam_dev",
                  "fused_exchange"):
         assert hasattr(O, name), name
     r = torch.zeros(4, 3)
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
-        O.gae(r, r, r.int(), r, torch.zeros(3), r.clone(), 0.99, 0.95)
+        O.gae(r, r, r.int(), r, torch.zeros(3), r.clone(), 0.99, 0.95, None)
     with pytest.raises(RuntimeError, match="null sim handle"):
         O.sim_step(0, r, r.int(), 0, 0, r, 400, True, r, None, r, None, r.int(), r.int(), None, None)
     with pytest.raises(RuntimeError, match="null comm handle"):
