@@ -93,7 +93,7 @@ def test_train_loop_host_logic_runs_end_to_end_with_the_device_operations_stubbe
         return torch.tensor([0.1, 0.2, 0.3, 0.01, 0.0, 0.0, 0.05])
 
     ppo.sample_parallel_with_workers = sample
-    ppo.normalize_advantages = lambda ret, val: (ret - val - (ret - val).mean()) / ((ret - val).std() + 1e-5)
+    ppo.normalize_advantages = lambda ret, val, from_rollout=False: (ret - val - (ret - val).mean()) / ((ret - val).std() + 1e-5)
     ppo.gather_minibatch = lambda o, a, r, d, idx: (o[idx], a[idx], r[idx], d[idx])
     ppo._update_step = update
     log = ppo.train(None, 4, verbose=True)
