@@ -144,6 +144,9 @@ template <class real, int NJ, int TK> int fill_model(Model<real, NJ, TK>& m, con
     }
     m.plans = plan_table;
   }
+  // assumption switches (model/*.json "assumptions"): bit 0 = explicit Euler instead of the implicit joint-damping solve
+  const int aflags = (int)rd();
+  m.explicit_euler = aflags & 1;
   if (p != n) return -3;
   return 0;
 }

@@ -226,6 +226,7 @@ template <class real, int NJ, int TK> struct Model {
   real head[3], fcap, goal_height;
   real clock[4][MAXPERIOD];  // r_frc r_vel l_frc l_vel
   int max_iter, frame_skip, period, any_damping;
+  int explicit_euler;   // model switch: 1 = integrate qacc as solved, no (M + h B) solve (default 0: MuJoCo's implicit joint damping)
   int ncap, npair, cap_link[MAXCAP];
   real cap_p0[MAXCAP][3], cap_p1[MAXCAP][3], cap_r[MAXCAP];
   unsigned char pair_a[MAXPAIR], pair_b[MAXPAIR];
@@ -1510,7 +1511,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     LHW_SYNC();
   }
   // ---------------- P12 mj_Euler: (M + h diag(damping)) a' = qfrc_smooth + qfrc_constraint ; integrate
-  if (PERENV || m.any_damping) {
+  if ((PERENV || m.any_damping) && !m.explicit_euler) {
     LHW_LANES(l) {
       constexpr int NW = (int)(sizeof(Arrow<real, NJ, TK>) / sizeof(real));
       const real* src = &w.M.r[0][0];

@@ -134,7 +134,16 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
             b.append(len(plan))
             for row in plan:
                 b += row
+    # assumption switches (model JSON "assumptions", SURVEY.md Appendix A warnings): bit 0 = explicit Euler
+    b.append(float(assumption_flags(mj)))
     return np.asarray(b, dtype=np.float64)
+
+
+def assumption_flags(mj: dict) -> int:
+    """The switchable modelling assumptions of model/*.json ("assumptions": SURVEY.md Appendix A, the details of mj_step that
+    could not be checked against MuJoCo here) as the flags word at the end of the packed model."""
+    a = mj.get("assumptions", {})
+    return 0 if a.get("implicit_damping", True) else 1
 
 
 def curriculum_height(iteration_count: float) -> float:

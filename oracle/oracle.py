@@ -141,7 +141,14 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
             b.append(len(plan))
             for row in plan:
                 b += row
+    # assumption switches (model JSON "assumptions", SURVEY.md Appendix A warnings): bit 0 = explicit Euler
+    b.append(float(assumption_flags(mj)))
     return np.array(b, dtype=np.float64)
+
+
+def assumption_flags(mj: dict) -> int:
+    a = mj.get("assumptions", {})
+    return 0 if a.get("implicit_damping", True) else 1
 
 
 def curriculum_height(iteration_count: float) -> float:

@@ -198,6 +198,8 @@ int orc_model_from_flat(orc_model* m, const double* b, int n) {
         for (int x = 0; x < 3; x++) m->plans[i][k][x] = RD();
     }
   }
+  /* assumption switches (model JSON "assumptions"): bit 0 = explicit Euler instead of the implicit joint-damping solve */
+  m->explicit_euler = ((int)RD()) & 1;
 #undef RD
   return p == n ? 0 : -100 - (p > n);
 }
@@ -981,7 +983,7 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
     if (P->damping[d] > 0) any_damp = 1;
   }
   if (efc.nrow == 0) memset(force, 0, sizeof(force));
-  if (any_damp) {
+  if (any_damp && !m->explicit_euler) {
     for (int a = 0; a < nv; a++)
       for (int c = 0; c < nv; c++) G[a * nv + c] = M[a * NV + c] + (a == c ? h * P->damping[a] : 0);
     chol(G, nv);

@@ -48,6 +48,21 @@ JVRC_ARM_EULER = {
 JVRC_COLLISION_BODIES = ["R_HIP_R_S", "R_HIP_Y_S", "R_KNEE_S", "L_HIP_R_S", "L_HIP_Y_S", "L_KNEE_S"]
 
 
+# the modelling assumptions SURVEY.md Appendix A could not check against MuJoCo, as switchable / traceable entries of every
+# compiled model (tests/test_assumption_switches.py measures what each one is worth)
+ASSUMPTIONS = {
+ "_doc": "Details of mujoco.mj_step / the MJCF export that SURVEY.md Appendix A could only take from MuJoCo's documentation (the library is not installable here). Each is a value in THIS file, so the day a MuJoCo recording exists (tools/record_reference.py) a mismatch can be traced by flipping one entry; tests/test_assumption_switches.py measures how far each one moves a trajectory.",
+ "implicit_damping": True,
+ "implicit_damping_doc": "mj_Euler solves (M + h diag(damping)) qacc' = M qacc before integrating (A.1). False = explicit Euler.",
+ "export_rounding_digits": 5,
+ "export_rounding_doc": "every number of links / geoms / opt above is already rounded with '%.5g' (dm_control export_with_assets(precision=5), envs/jvrc/gen_xml.py:161); carried by the numbers themselves.",
+ "contact_diagapprox_doc": "R_n = (1 - imp) / imp * link_invweight0[foot][0] * (1 + mu^2) (A.3); carried by link_invweight0 / dof_invweight0 (mj_setConst at qpos0, frozen).",
+ "pyramid_regulariser_doc": "every pyramid edge: R = 2 mu^2 R_n / impratio (A.3); carried by opt.impratio (1).",
+ "planebox_corners_doc": "mjc_PlaneBox keeps the first (at most) 4 corners below the plane on the plane side of the box centre, in corner-index order (A.5); at most 4 corners can qualify unless the box stands exactly on an edge, so the order cannot matter (tested).",
+ "solref_solimp_doc": "contacts and limits use the global defaults opt.solref (0.02, 1) / opt.solimp (0.9, 0.95, 0.001, 0.5, 2): nothing in the reference's XML overrides them (A.0)."
+}
+
+
 def r5(x: float) -> float:
     """dm_control export_with_assets(precision=5) writes every number as '%.5g'."""
     return float("%.5g" % float(x))
@@ -529,6 +544,7 @@ def main():
         old = json.load(open(path))
         if "self_collision" in old:
             m["self_collision"] = old["self_collision"]
+    m["assumptions"] = ASSUMPTIONS
     with open(path, "w") as f:
         json.dump(m, f, indent=1)
     print("wrote", path, "mass", m["total_mass"], "links", len(m["links"]), "meaninertia", m["meaninertia"])
@@ -538,6 +554,7 @@ def main():
     st = compile_jvrc(boxes=True)
     if "self_collision" in m:
         st["self_collision"] = m["self_collision"]
+    st["assumptions"] = ASSUMPTIONS
     json.dump(st, open(os.path.join(args.out, "jvrc_step.json"), "w"), indent=1)
     print("wrote jvrc_step.json plans", len(st["stepping"]["plans"]), "delay_frames", st["stepping"]["delay_frames"])
     # uneven / compliant terrain EXTENSION (BASELINE configs[4]; SURVEY F7: the reference has only the unused
@@ -550,6 +567,7 @@ def main():
                          interval=200, contact_solref=[0.04, 1.0])
     json.dump(tm, open(os.path.join(args.out, "jvrc_walk_terrain.json"), "w"), indent=1)
     h = compile_h1()
+    h["assumptions"] = ASSUMPTIONS
     json.dump(h, open(os.path.join(args.out, "h1.json"), "w"), indent=1)
     print("wrote h1.json mass", h["total_mass"], "links", len(h["links"]), "meaninertia", h["meaninertia"])
     for lk in h["links"]:
