@@ -115,6 +115,7 @@ template <class real, int NJ, int TK> int fill_model(Model<real, NJ, TK>& m, con
     m.side_tol = (real)rd(); m.terrain_pitch = (real)rd(); m.terrain_bump = (real)rd(); m.terrain_zlo = (real)rd();
     m.terrain_zhi = (real)rd(); m.terrain_xy = (real)rd(); m.terrain_interval = (int)rd();
     const double tc0 = rd(), zc = rd();
+    m.side_faces = (int)rd();
     if (m.terrain_interval < 1) return -10;
     if (tc0 > 0) {   // the foot-ground contact pairs carry their own solref (mj_makeImpedance with refsafe)
       const double tc = tc0 < 2 * h ? 2 * h : tc0;
@@ -133,6 +134,7 @@ template <class real, int NJ, int TK> int fill_model(Model<real, NJ, TK>& m, con
     for (int k = 0; k < 3; k++) m.slab_half[k] = (real)rd();
     m.target_radius = (real)rd(); m.side_tol = (real)rd(); m.delay_frames = (int)rd(); m.step_height = (real)rd();
     m.slab_contacts_are_floor = (int)rd();
+    m.side_faces = (int)rd();
     m.nplan = (int)rd();
     if (m.nplan < 1 || m.nplan > MAXPLAN || !plan_table) return -8;
     for (int i = 0; i < m.nplan; i++) {

@@ -243,6 +243,7 @@ template <class real, int NJ, int TK> struct Model {
   int terrain_interval;
   int delay_frames, nplan;
   int slab_contacts_are_floor;   // 0: reference behaviour (SURVEY C-2), foot-stone contacts invisible to GRF / contact z
+  int side_faces;                // 1: slab side faces (stair risers) stop foot-box corners that are inside a slab; 0: they pass through
   const real* plans;   // [nplan][PLAN_STRIDE] in global memory (host memory in the CPU emulation)
   const Model* gm;     // the same record in global memory (device builds; unused by the CPU emulation)
 };
@@ -320,13 +321,15 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   int ncon[2];
   // stepping stones: cos/sin of the slab yaws, per-corner multiplicity, crossing-slot distances
   real slab_cs[NSL][2], cmul[NST ? 16 : 1], xcd[NST ? NCON : 1];
-  int ncorner[2];
+  int ncorner[2], nside[2];
+  // riser contacts (slab side faces): horizontal outward normal per slot, (0, 0) = the slot's normal is +z
+  real cn[NST ? NCON : 1][2];
   real site[2][3], rquat[4], goal[8];   // lagged site_xpos / root xquat ; _goal_steps_{x,y,z,theta}
   real cpos[NCON][Cfg<NJ, TK>::SLABS ? 5 : 3], cD[NCON], cKid[NCON];   // SLABS: (px, py, pz, 1, 0), see pmap_sel
-  real earef[NEDGE], ejar[NEDGE];
+  real ejar[NEDGE];   // edge residuals J a - aref (P8 leaves aref here, P9 turns it into the residual in place)
   int lside[NU];
-  real laref[NU], lD[NU], ljar[NU];
-  real fD[NFL], flim[NFL], faref[NFL], fjar[NFL];  // dof friction-loss rows: 1/R, floss * R (half width of the quadratic zone)
+  real lD[NU], ljar[NU];
+  real fD[NFL], flim[NFL], fjar[NFL];  // dof friction-loss rows: 1/R, floss * R (half width of the quadratic zone)
   // two scratch groups with disjoint lifetimes share storage: rigid-body quantities live from P2 to P8 (the last
   // reader is qfrc_smooth), the Newton quantities from P9 to P11
   union {
@@ -336,13 +339,15 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
       real ccd[2 * NPTS];   // signed distance of each candidate point (box corner / sphere), > 0: not a candidate
       int cslot[NCON];
       real cwp[NST ? 16 : 1][3];   // SLABS: foot-box corners relative to o
+      real cside[NST ? 16 : 1], csn[NST ? 16 : 1][2];   // SLABS: per corner, inset behind the nearest side face of the first slab that
+                                                        // holds it unsupported (< 0: none) and that face's outward normal
     };
     struct {
       real T[2][NA][6], Af[2][6][6], Ff[2][6], ya[2][6], ys[2][6];
       // contact-frame point map: rows = unit wrenches of (n, t1, t2) applied at the contact.  The slab variants (16 slots)
       // rebuild the entries from cpos instead (pmap3): dropping the table is what lets 14 fp64 environments share an SM
       real Pm[Cfg<NJ, TK>::SLABS ? 1 : NCON][3][6];
-      real cF[NCON][3], cW[NCON][5];
+      real cF[NCON][3], cW[NCON][Cfg<NJ, TK>::SLABS ? 6 : 5];   // SLABS: + the (t1, t2) entry, non-zero for riser contacts only
       real ejv[NEDGE], ljv[NU], fjv[NFL];
     };
     real capE[MAXCAP][6];  // self-collision capsule end points; lives where T was (T is dead after the Hessian build)
@@ -414,6 +419,19 @@ template <class real> LHW_DEV void contact_u(const real* p, const real* y, real*
   u[0] = y[5] + y[0] * p[1] - y[1] * p[0];
   u[1] = y[4] + y[2] * p[0] - y[0] * p[2];
   u[2] = -(y[3] + y[1] * p[2] - y[2] * p[1]);
+}
+// contact-frame velocity of a RISER contact (slab side face, horizontal outward normal (nx, ny)): frame n = (nx, ny, 0),
+// t1 = +z, t2 = n x t1 = (ny, -nx, 0).  `u` comes in as contact_u gives it — the components of the world velocity along the
+// canonical frame C0 = (+z, +y, -x) of every floor / top-face contact — and leaves as (n.v, t1.v, t2.v) = Q' u with
+// Q = [[0, 1, 0], [ny, 0, -nx], [-nx, 0, -ny]] (the riser frame's vectors written in C0).  (0, 0) = a C0 contact: unchanged.
+template <class real> LHW_DEV void riser_u(const real* cn, real* u) {
+  const real nx = cn[0], ny = cn[1];
+  if (nx != 0 || ny != 0) {
+    const real a = u[0], b = u[1], c = u[2];
+    u[0] = ny * b - nx * c;
+    u[1] = a;
+    u[2] = -nx * b - ny * c;
+  }
 }
 // column a of the contact point map P(p) (see P9) without the table: with the contact record cp = (px, py, pz, 1, 0) the
 // entries are P[r][a] = sgn[r] * cp[idx[r]]; idx / sgn depend on the lane's column only and are hoisted out of the contact loops
@@ -669,6 +687,7 @@ LHW_DEVNI void constraint_images(Work<real, NJ, TK>& w, const Model<real, NJ, TK
       if (s - f * CPF < w.ncon[f]) {
         real u[3];
         contact_u(w.cpos[s], outY[f], u);
+        if constexpr (Cfg<NJ, TK>::SLABS) riser_u(w.cn[s], u);
         v = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)] - (e_sub ? e_sub[ed] : (real)0);
       }
       e_out[ed] = v;
@@ -976,6 +995,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         const real floor_z = (Cfg<NJ, TK>::STEP && w.mode == ST_FORWARD) ? (real)-2 : (real)0;   // stepping_task.py:332-334
         real best = 0;
         int have = 0, mult = 0, with_floor = 0;
+        real side_inset = -1, side_nx = 0, side_ny = 0;
         if (az - floor_z < 0) { best = floor_z; have = 1; mult = 1; with_floor = 1; }
 #pragma unroll 1
         for (unsigned mk = near_slabs[f]; mk; mk &= mk - 1) {
@@ -988,12 +1008,26 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           const real ix = m.slab_half[0] - m_abs(c * dx + sn * dy), iy = m.slab_half[1] - m_abs(-sn * dx + c * dy);
           if (ix < 0 || iy < 0) continue;
           const real inset = ix < iy ? ix : iy;
-          if (-d > m.side_tol && -d > inset) continue;
+          if (-d > m.side_tol && -d > inset) {
+            // inside the slab, too deep for its top face: the nearest SIDE face holds the corner (a stair riser); first such
+            // slab in index order, x' faces win ties
+            if (m.side_faces && side_inset < 0 && !(ld > 0)) {
+              const real xs = c * dx + sn * dy, ys = -sn * dx + c * dy;
+              real lx = 0, ly = 0;
+              if (ix <= iy) lx = xs < 0 ? (real)-1 : (real)1; else ly = ys < 0 ? (real)-1 : (real)1;
+              side_inset = inset;
+              side_nx = c * lx - sn * ly;
+              side_ny = sn * lx + c * ly;
+            }
+            continue;
+          }
           if (!have || sl[2] > best) { best = sl[2]; have = 1; mult = 1; with_floor = 0; }
           else if (sl[2] == best) mult++;
         }
         w.ccd[l - 16] = (have && !(ld > 0)) ? az - best : (real)1;
         w.cmul[l - 16] = with_floor ? (real)mult : (real)-mult;   // sign: the floor plane is one of the `mult` supports
+        w.cside[l - 16] = side_inset;
+        w.csn[l - 16][0] = side_nx; w.csn[l - 16][1] = side_ny;
       } else {
       const real dist0 = w.o[2] + w.xr[lk][2] + R[6] * m.foot_pos[f][0] + R[7] * m.foot_pos[f][1] + R[8] * m.foot_pos[f][2];
       w.ccd[l - 16] = (dist0 + ld > 0 || ld > 0) ? (real)1 : dist0 + ld;
@@ -1019,8 +1053,29 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
 #pragma unroll
       for (int i = 0; i < NPTS; i++)
         if (cnt < (Cfg<NJ, TK>::SLABS ? NCORNER : CPF) && !(w.ccd[f * NPTS + i] > 0)) { w.cslot[f * CPF + cnt] = i; cnt++; }
-      w.ncon[f] = cnt;
       w.ncorner[f] = cnt;
+      if constexpr (Cfg<NJ, TK>::SLABS) {
+        // riser contacts take the first of the foot's CPF - NCORNER extra slots, in corner order (the sole-edge crossings of
+        // P7x fill what is left)
+        int ns = 0;
+#pragma unroll 1
+        for (int i = 0; i < NPTS; i++) {
+          const real ins = w.cside[f * NPTS + i];
+          if (!(ins < 0) && ns < CPF - NCORNER) {
+            const int s = f * CPF + cnt + ns;
+            const real nx = w.csn[f * NPTS + i][0], ny = w.csn[f * NPTS + i][1];
+            w.cpos[s][0] = w.cwp[f * 8 + i][0] + (real)0.5 * ins * nx;
+            w.cpos[s][1] = w.cwp[f * 8 + i][1] + (real)0.5 * ins * ny;
+            w.cpos[s][2] = w.cwp[f * 8 + i][2];
+            w.xcd[s] = -ins;
+            w.cn[s][0] = nx; w.cn[s][1] = ny;
+            ns++;
+          }
+        }
+        cnt += ns;
+        w.nside[f] = ns;
+      }
+      w.ncon[f] = cnt;
     }
   }
   LHW_SYNC();
@@ -1031,7 +1086,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     // inside (0,1) is a polygon vertex.  Kept: the first CPF - NCORNER per foot in (slab, edge, entry-then-exit) order.
 #pragma unroll 1
     for (int f = 0; f < 2; f++) {
-      int run = 0;
+      int run = w.nside[f];     // the extra slots the riser contacts of P7 already took
       const int ntask = 4 * bit_count(near_slabs[f]);
 #pragma unroll 1
       for (int pass = 0; pass * 32 < ntask; pass++) {
@@ -1081,10 +1136,12 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           if (he && pos < CPF - NCORNER) {
             const int sl_ = f * CPF + w.ncorner[f] + pos;
             w.cpos[sl_][0] = pe[0]; w.cpos[sl_][1] = pe[1]; w.cpos[sl_][2] = pe[2]; w.xcd[sl_] = pe[3];
+            w.cn[sl_][0] = 0; w.cn[sl_][1] = 0;
           }
           if (hx && pos + he < CPF - NCORNER) {
             const int sl_ = f * CPF + w.ncorner[f] + pos + he;
             w.cpos[sl_][0] = px[0]; w.cpos[sl_][1] = px[1]; w.cpos[sl_][2] = px[2]; w.xcd[sl_] = px[3];
+            w.cn[sl_][0] = 0; w.cn[sl_][1] = 0;
           }
         }
       }
@@ -1106,10 +1163,11 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           mult = m_abs(w.cmul[f * NPTS + i]);
           w.cpos[l][0] = w.cwp[f * 8 + i][0]; w.cpos[l][1] = w.cwp[f * 8 + i][1];
           w.cpos[l][2] = w.cwp[f * 8 + i][2] - (real)0.5 * cd;
+          w.cn[l][0] = 0; w.cn[l][1] = 0;
           // share of this slot's force that the task's floor-contact queries see (xcd is free for corner slots)
           w.xcd[l] = (!Cfg<NJ, TK>::STEP || m.slab_contacts_are_floor) ? (real)1 : (w.cmul[f * NPTS + i] > 0 ? (real)1 / mult : (real)0);
         } else {
-          cd = w.xcd[l];   // crossing slot: position already written by P7x
+          cd = w.xcd[l];   // riser / crossing slot: position, distance and normal already written by P7 / P7x
           w.xcd[l] = (!Cfg<NJ, TK>::STEP || m.slab_contacts_are_floor) ? (real)1 : (real)0;
         }
         w.cpos[l][3] = 1; w.cpos[l][4] = 0;
@@ -1145,8 +1203,9 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       if (s - f * CPF < w.ncon[f]) {
         real u[3];
         contact_u(w.cpos[s], w.V[(f + 1) * NJ], u);
+        if constexpr (Cfg<NJ, TK>::SLABS) riser_u(w.cn[s], u);
         const real vel = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)];
-        w.earef[ed] = -m.Bc * vel - w.cKid[s];
+        w.ejar[ed] = -m.Bc * vel - w.cKid[s];
       }
     }
     if (l < NV) {
@@ -1195,7 +1254,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       if (side) {
         const real imp = impedance(m.solimp, dist);
         w.lD[u] = (real)1 / m_max((real)1e-15, (1 - imp) / imp * m.dof_invw[d]);
-        w.laref[u] = -m.B * (side * w.qvel[d]) - m.K * imp * dist;
+        w.ljar[u] = -m.B * (side * w.qvel[d]) - m.K * imp * dist;
       }
       if constexpr (FLOSS) {
         // dof friction loss: J = e_d, pos = 0 -> impedance solimp[0], aref = -B vel
@@ -1203,7 +1262,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         const real Rf = m_max((real)1e-15, (1 - imp) / imp * m.dof_invw[d]);
         w.fD[u] = (real)1 / Rf;
         w.flim[u] = w.p_floss[u] * Rf;
-        w.faref[u] = -m.B * w.qvel[d];
+        w.fjar[u] = -m.B * w.qvel[d];
       }
     }
   }
@@ -1221,7 +1280,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       P[12] = 0;  P[13] = -pz; P[14] = py; P[15] = -1; P[16] = 0; P[17] = 0;
     }
   }
-  constraint_images<real, NJ, TK>(w, m, w.qacc, w.Ma, w.ya, w.ejar, w.ljar, w.fjar, w.earef, w.laref, w.faref, (real)1);
+  // (the reference accelerations sit in ejar / ljar / fjar since P8: subtracted in place, every lane its own entries)
+  constraint_images<real, NJ, TK>(w, m, w.qacc, w.Ma, w.ya, w.ejar, w.ljar, w.fjar, w.ejar, w.ljar, w.fjar, (real)1);
 
   // ---------------- P10 primal Newton on  1/2 (a-a_s)' M (a-a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
   // residuals (Ma, ejar, ljar) are carried incrementally: x += alpha * (direction image)
@@ -1244,6 +1304,30 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         w.cW[l][2] = D * mu * (a2 - a3);
         w.cW[l][3] = D * mu * mu * (a0 + a1);
         w.cW[l][4] = D * mu * mu * (a2 + a3);
+        if constexpr (Cfg<NJ, TK>::SLABS) {
+          w.cW[l][5] = 0;
+          const real nx = w.cn[l][0], ny = w.cn[l][1];
+          if (nx != 0 || ny != 0) {
+            // everything downstream (Ff, Af) works in the canonical frame C0 = (+z, +y, -x): f0 = Q f, W0 = Q W Q' with the riser
+            // frame's vectors as the columns of Q (see riser_u)
+            const real Q[3][3] = {{0, 1, 0}, {ny, 0, -nx}, {-nx, 0, -ny}};
+            const real fc[3] = {w.cF[l][0], w.cF[l][1], w.cF[l][2]};
+            const real Wc[3][3] = {{w.cW[l][0], w.cW[l][1], w.cW[l][2]}, {w.cW[l][1], w.cW[l][3], 0}, {w.cW[l][2], 0, w.cW[l][4]}};
+            real QW[3][3], W0[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+              w.cF[l][r] = Q[r][0] * fc[0] + Q[r][1] * fc[1] + Q[r][2] * fc[2];
+#pragma unroll
+              for (int c = 0; c < 3; c++) QW[r][c] = Q[r][0] * Wc[0][c] + Q[r][1] * Wc[1][c] + Q[r][2] * Wc[2][c];
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+              for (int c = 0; c < 3; c++) W0[r][c] = QW[r][0] * Q[c][0] + QW[r][1] * Q[c][1] + QW[r][2] * Q[c][2];
+            w.cW[l][0] = W0[0][0]; w.cW[l][1] = W0[0][1]; w.cW[l][2] = W0[0][2];
+            w.cW[l][3] = W0[1][1]; w.cW[l][4] = W0[2][2]; w.cW[l][5] = W0[1][2];
+          }
+        }
       }
     }
     LHW_SYNC();
@@ -1312,7 +1396,10 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
             const real* P = &w.Pm[s][0][0];
             a0 = P[a]; a1 = P[6 + a]; a2 = P[12 + a]; b0 = P[b]; b1 = P[6 + b]; b2 = P[12 + b];
           }
-          acc += a0 * (W[0] * b0 + W[1] * b1 + W[2] * b2) + a1 * (W[1] * b0 + W[3] * b1) + a2 * (W[2] * b0 + W[4] * b2);
+          if constexpr (Cfg<NJ, TK>::SLABS)
+            acc += a0 * (W[0] * b0 + W[1] * b1 + W[2] * b2) + a1 * (W[1] * b0 + W[3] * b1 + W[5] * b2) + a2 * (W[2] * b0 + W[5] * b1 + W[4] * b2);
+          else
+            acc += a0 * (W[0] * b0 + W[1] * b1 + W[2] * b2) + a1 * (W[1] * b0 + W[3] * b1) + a2 * (W[2] * b0 + W[4] * b2);
         }
         w.Af[f][a][b] = acc;
         w.Af[f][b][a] = acc;

@@ -121,14 +121,14 @@ def pack_model(mj: dict, tolerance: float | None = None, max_iter: int | None = 
     b.append(float(pd_gain_randomization))     # RobotBase(pdrand_k) (robots/robot_base.py:5,43-47); 0 = off
     if terrain:
         b += terrain["strip_half"] + [terrain["side_tol"], terrain["pitch"], terrain["bump"], terrain["z_lo"], terrain["z_hi"],
-                                      terrain["xy"], terrain["interval"]] + terrain["contact_solref"]
+                                      terrain["xy"], terrain["interval"]] + terrain["contact_solref"] + [1 if terrain.get("side_faces", True) else 0]
     if step:
         st = mj["stepping"]
         for site in mj["foot_sites"]:
             b += site
         b += st["slab_half"]
         b += [st["target_radius"], st["side_tol"], st["delay_frames"], curriculum_height(iteration_count),
-              1 if st.get("slab_contacts_are_floor") else 0]
+              1 if st.get("slab_contacts_are_floor") else 0, 1 if st.get("side_faces", True) else 0]
         b.append(len(st["plans"]))
         for plan in st["plans"]:
             b.append(len(plan))

@@ -191,10 +191,12 @@ class PPO:
         After a few eager steps (cuBLAS / autograd warm-up — they are real updates) the whole step — losses, backward,
         gradient norms, clip + Adam with the step counter in device memory — is captured once and replayed.
         Every rank captures and replays the same step: the fused exchange (peer-memory all-reduce + clip + Adam) is three
-        ordinary launches whose epoch / step counters live in device memory, and the NCCL baseline (LHW_FUSED_EXCHANGE=0) is
-        capturable as well.  LHW_UPDATE_GRAPH=0 keeps the eager loop."""
+        ordinary launches whose epoch / step counters live in device memory.  LHW_UPDATE_GRAPH=0 keeps the eager loop."""
         import os
-        eager = (os.environ.get("LHW_UPDATE_GRAPH", "1") == "0" or self._mb is None or ob is not self._mb[0]
+        # the NCCL baseline (LHW_FUSED_EXCHANGE=0) on several ranks stays eager: a captured graph that holds NCCL work kept the
+        # process group from shutting down (observed: destroy_process_group never returned); it is the baseline, not the path
+        eager = ((self.world > 1 and self._comm is None) or os.environ.get("LHW_UPDATE_GRAPH", "1") == "0" or self._mb is None
+                 or ob is not self._mb[0]
                  or not isinstance(self.actor_optimizer, FusedClipAdam) or not isinstance(self.critic_optimizer, FusedClipAdam))
         if not eager and self._ug is not None and self._ug[2] == ob.data_ptr():
             self._ug[0].replay()

@@ -129,13 +129,14 @@ def pack_model(mj: dict, clocks: dict, tolerance: float | None = None, solver: i
     if tr:
         b += tr["strip_half"] + [tr["side_tol"], tr["pitch"], tr["bump"], tr["z_lo"], tr["z_hi"], tr["xy"], tr["interval"]]
         b += tr["contact_solref"]
+        b.append(1 if tr.get("side_faces", True) else 0)
     if mj["name"] == "jvrc_step":
         st = mj["stepping"]
         for site in mj["foot_sites"]:
             b += site
         b += st["slab_half"]
         b += [st["target_radius"], st["side_tol"], st["delay_frames"], curriculum_height(iteration_count),
-              1 if st.get("slab_contacts_are_floor") else 0]
+              1 if st.get("slab_contacts_are_floor") else 0, 1 if st.get("side_faces", True) else 0]
         b.append(len(st["plans"]))
         for plan in st["plans"]:
             b.append(len(plan))
@@ -185,7 +186,8 @@ class Oracle:
         self.lib.orc_set_step_height(self._model, ctypes.c_double(curriculum_height(iteration_count)))
 
     def contacts(self, envs, i=0):
-        """(pos [n,3], dist [n], foot [n], slab [n]) of the contacts at env i's current qpos."""
+        """(pos [n,3], dist [n], foot [n], slab [n]) of the contacts at env i's current qpos; slab: 0 floor plane, 1 top face of a
+        stepping stone, 3 side face of one (riser contact)."""
         pos, dist = np.zeros((128, 3)), np.zeros(128)
         foot, slab = np.zeros(128, dtype=np.int32), np.zeros(128, dtype=np.int32)
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)

@@ -182,6 +182,7 @@ int orc_model_from_flat(orc_model* m, const double* b, int n) {
     m->side_tol = RD(); m->terrain_pitch = RD(); m->terrain_bump = RD(); m->terrain_zlo = RD(); m->terrain_zhi = RD();
     m->terrain_xy = RD(); m->terrain_interval = (int)RD();
     for (int k = 0; k < 2; k++) m->contact_solref[k] = RD();
+    m->side_faces = (int)RD();
   }
   if (m->task == ORC_TASK_STEP) {
     for (int f = 0; f < 2; f++)
@@ -189,6 +190,7 @@ int orc_model_from_flat(orc_model* m, const double* b, int n) {
     for (int k = 0; k < 3; k++) m->slab_half[k] = RD();
     m->target_radius = RD(); m->side_tol = RD(); m->delay_frames = (int)RD(); m->step_height = RD();
     m->slab_contacts_are_floor = (int)RD();
+    m->side_faces = (int)RD();
     m->nplan = (int)RD();
     if (m->nplan > ORC_MAXPLAN) return -8;
     for (int i = 0; i < m->nplan; i++) {
@@ -404,6 +406,7 @@ typedef struct {
   double floss[ORC_MAXROW];
   int con_row[ORC_MAXCON], con_geom[ORC_MAXCON], con_slab[ORC_MAXCON];   /* con_slab: 1 = against a stepping stone, 0 = floor plane */
   double con_pos[ORC_MAXCON][3], con_dist[ORC_MAXCON];
+  double con_nrm[ORC_MAXCON][2];   /* horizontal outward normal of a slab SIDE face (riser contact); (0, 0): normal +z (floor / top face) */
 } efc_t;
 
 /* MuJoCo getimpedance(): power-law sigmoid between solimp[0] and solimp[1] over |pos|/width */
@@ -453,6 +456,30 @@ static int slab_supports(const orc_model* m, const double* sl, const double* p, 
   if (!(d < 0) || -d >= 2 * m->slab_half[2]) return 0;
   if (-d > m->side_tol && -d > inset) return 0;
   *dist = d;
+  return 1;
+}
+
+/* Side faces (stair risers).  A point INSIDE a slab's volume that its top face does not support (deeper than side_tol AND
+ * deeper than its inset from the side faces: slab_supports == 0) is in contact with the nearest side face: the face of
+ * minimum penetration of a box-box test.  Returns 1 and the outward horizontal normal of that face (world), the signed
+ * distance (-inset) and the contact point half way between the point and the face.  x' faces win ties. */
+static int slab_side(const orc_model* m, const double* sl, const double* p, double nrm[2], double* dist, double pos[3]) {
+  double c = cos(sl[3]), sn = sin(sl[3]);
+  double dx = p[0] - sl[0], dy = p[1] - sl[1];
+  double xs = c * dx + sn * dy, ys = -sn * dx + c * dy;
+  double ix = m->slab_half[0] - fabs(xs), iy = m->slab_half[1] - fabs(ys);
+  if (ix < 0 || iy < 0) return 0;
+  double d = p[2] - sl[2], inset = ix < iy ? ix : iy;
+  if (!(d < 0) || -d >= 2 * m->slab_half[2]) return 0;
+  if (!(-d > m->side_tol && -d > inset)) return 0;          /* the top face carries it (slab_supports) */
+  double lx = 0, ly = 0;                                   /* outward normal in the slab frame */
+  if (ix <= iy) lx = xs < 0 ? -1.0 : 1.0; else ly = ys < 0 ? -1.0 : 1.0;
+  nrm[0] = c * lx - sn * ly;
+  nrm[1] = sn * lx + c * ly;
+  *dist = -inset;
+  pos[0] = p[0] + 0.5 * inset * nrm[0];
+  pos[1] = p[1] + 0.5 * inset * nrm[1];
+  pos[2] = p[2];
   return 1;
 }
 
@@ -514,7 +541,7 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
         int ci = e->ncon++;
         e->con_slab[ci] = 0;
         e->con_geom[ci] = g;
-        e->con_dist[ci] = cd;
+        e->con_dist[ci] = cd; e->con_nrm[ci][0] = e->con_nrm[ci][1] = 0;
         e->con_pos[ci][0] = c[0]; e->con_pos[ci][1] = c[1];
         e->con_pos[ci][2] = c[2] - (m->geom_radius[g] + 0.5 * cd);
       }
@@ -554,7 +581,7 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
           int ci = e->ncon++;
           e->con_slab[ci] = sidx >= 0;
           e->con_geom[ci] = g;
-          e->con_dist[ci] = cd;
+          e->con_dist[ci] = cd; e->con_nrm[ci][0] = e->con_nrm[ci][1] = 0;
           e->con_pos[ci][0] = cw[i][0]; e->con_pos[ci][1] = cw[i][1];
           e->con_pos[ci][2] = cw[i][2] - 0.5 * cd;
         }
@@ -564,6 +591,32 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
        * polygon vertex.  At most ORC_MAXCROSS per foot, in (slab, edge, entry-then-exit) order. */
       static const int ea[4] = {0, 1, 3, 2}, eb[4] = {1, 3, 2, 0};
       int ncross = 0;
+      /* (A') riser contacts: the corners on the plane side of the box centre that sit inside a slab's volume unsupported by
+       * its top face push against the nearest side face (first such slab in index order; tasks/stepping_task.py:318-334 poses
+       * real boxes, mjc_BoxBox gives riser contacts).  They share the ORC_MAXCROSS extra slots of the foot with the crossings
+       * below and come first, in corner-index order. */
+      if (m->side_faces) {
+        for (int i = 0; i < 8; i++) {
+          double v2 = (i & 4 ? 1 : -1) * m->geom_size[g][2];
+          double cz = k->xmat[lk][6] * ((i & 1 ? 1 : -1) * m->geom_size[g][0]) + k->xmat[lk][7] * ((i & 2 ? 1 : -1) * m->geom_size[g][1]) +
+                      k->xmat[lk][8] * v2;
+          if (cz > 0) continue;
+          for (int sidx = 0; sidx < ORC_NSLAB; sidx++) {
+            double nrm[2], sd, sp[3];
+            if (!slab_side(m, env->seq[sidx], cw[i], nrm, &sd, sp)) continue;
+            if (ncross < ORC_MAXCROSS && e->ncon < ORC_MAXCON) {
+              ncross++;
+              int ci = e->ncon++;
+              e->con_slab[ci] = 1;
+              e->con_geom[ci] = g;
+              e->con_dist[ci] = sd;
+              e->con_nrm[ci][0] = nrm[0]; e->con_nrm[ci][1] = nrm[1];
+              for (int x = 0; x < 3; x++) e->con_pos[ci][x] = sp[x];
+            }
+            break;
+          }
+        }
+      }
       for (int sidx = 0; sidx < ORC_NSLAB; sidx++) {
         const double* sl = env->seq[sidx];
         double c = cos(sl[3]), sn = sin(sl[3]);
@@ -595,7 +648,7 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
             int ci = e->ncon++;
             e->con_slab[ci] = 1;
             e->con_geom[ci] = g;
-            e->con_dist[ci] = cd;
+            e->con_dist[ci] = cd; e->con_nrm[ci][0] = e->con_nrm[ci][1] = 0;
             e->con_pos[ci][0] = A[0] + t * (Bp[0] - A[0]);
             e->con_pos[ci][1] = A[1] + t * (Bp[1] - A[1]);
             e->con_pos[ci][2] = z - 0.5 * cd;
@@ -617,7 +670,7 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
       int ci = e->ncon++;
       e->con_slab[ci] = 0;
       e->con_geom[ci] = g;
-      e->con_dist[ci] = cd;
+      e->con_dist[ci] = cd; e->con_nrm[ci][0] = e->con_nrm[ci][1] = 0;
       e->con_pos[ci][0] = corner[0] + ctr[0];
       e->con_pos[ci][1] = corner[1] + ctr[1];
       e->con_pos[ci][2] = corner[2] + ctr[2] - 0.5 * cd;
@@ -644,8 +697,16 @@ static void make_constraints(const orc_model* m, const orc_params* P, const kin_
     for (int j = 0; j < 4; j++) {
       int r = e->nrow++;
       double vel = 0;
+      const double nx = e->con_nrm[ci][0], ny = e->con_nrm[ci][1];
+      const int side = nx != 0 || ny != 0;
       for (int d = 0; d < nv; d++) {
-        double jn = jp[2 * NV + d], jt = (j < 2) ? jp[1 * NV + d] : -jp[0 * NV + d];
+        double jn, jt;
+        if (!side) {   /* frame (n, t1, t2) = (+z, +y, -x) */
+          jn = jp[2 * NV + d]; jt = (j < 2) ? jp[1 * NV + d] : -jp[0 * NV + d];
+        } else {       /* riser: n = (nx, ny, 0), t1 = +z, t2 = n x t1 = (ny, -nx, 0) */
+          jn = nx * jp[0 * NV + d] + ny * jp[1 * NV + d];
+          jt = (j < 2) ? jp[2 * NV + d] : ny * jp[0 * NV + d] - nx * jp[1 * NV + d];
+        }
         e->J[r][d] = jn + ((j & 1) ? -m->mu : m->mu) * jt;
         vel += e->J[r][d] * qvel[d];
       }
@@ -1456,7 +1517,8 @@ int orc_test_contacts(const orc_model* m, const orc_env* e, double* pos /* [ORC_
     for (int x = 0; x < 3; x++) pos[3 * ci + x] = efc.con_pos[ci][x];
     dist[ci] = efc.con_dist[ci];
     foot[ci] = efc.con_geom[ci];
-    slab[ci] = efc.con_slab[ci];
+    /* bit 0: against a stepping stone; bit 1: against one of its SIDE faces (riser contact, horizontal normal) */
+    slab[ci] = efc.con_slab[ci] | ((efc.con_nrm[ci][0] != 0 || efc.con_nrm[ci][1] != 0) ? 2 : 0);
   }
   return efc.ncon;
 }

@@ -110,6 +110,7 @@ typedef struct {
   double target_radius, side_tol, step_height;   /* step_height: the curriculum's h for the current iteration_count */
   int delay_frames, nplan;
   int explicit_euler;              /* SURVEY App. A.1 switch: integrate qacc as solved (no (M + h B) solve); default 0 */
+  int side_faces;                  /* 1: slab side faces (stair risers) stop box corners that are inside a slab; 0: round-1 behaviour (pass through) */
   int slab_contacts_are_floor;     /* 0 (reference behaviour, see sim_oracle.c): foot-slab contacts are invisible to get_*_floor_contacts */
   int plan_len[ORC_MAXPLAN];
   double plans[ORC_MAXPLAN][ORC_MAXPLANLEN][3];  /* utils/footstep_plans.txt: x, y, theta */

@@ -324,6 +324,8 @@ def test_slab_contact_set_against_an_independent_polygon_clip(orc):
         o.set_field(envs, 0, "qpos", q); o.set_field(envs, 0, "seq", seq.reshape(-1)); o.set_field(envs, 0, "mode", 4)   # no floor
         pos, dist, foot, is_slab = o.contacts(envs, 0)
         assert is_slab.all()
+        top = is_slab == 1          # this test is about the top-face manifold; riser contacts (3) have their own test below
+        pos, dist, foot = pos[top], dist[top], foot[top]
         xpos, xmat = kinematics(mj, q)
         c, s = np.cos(slab[3]), np.sin(slab[3])
         for f, lk in enumerate((mj["rfoot_link"], mj["lfoot_link"])):
@@ -338,8 +340,9 @@ def test_slab_contact_set_against_an_independent_polygon_clip(orc):
             keep = lambda v: -2 * hz < v[2] - slab[2] < 0 and (slab[2] - v[2] <= tol or slab[2] - v[2] <= min(hx - abs(v[0]), hy - abs(v[1])) + 1e-15)
             is_corner = lambda v: any(np.abs(v - to_slab(p)).max() < 1e-13 for p in sole)
             crossings = [v for v in poly if keep(v) and not is_corner(v)]
-            if len(crossings) > 4:
-                continue                               # the per-foot crossing cap is order dependent; not this test's subject
+            n_riser = int(((is_slab == 3) & (o.contacts(envs, 0)[2] == f)).sum())
+            if len(crossings) + n_riser > 4:
+                continue                               # the per-foot cap of the extra slots is order dependent; not this test's subject
             # corners: mjc_PlaneBox's rule over all 8 box corners in index order (x sign = bit 0, y = bit 1, z = bit 2), 4 at
             # most: below the box centre, inside the footprint, supported by the top face (a tilted foot can offer a corner
             # of its TOP face as well, exactly as it would to the floor plane)
@@ -412,3 +415,89 @@ def test_fp32_kernel_source_tracks_oracle_on_stepping_stones_for_a_short_horizon
         eo, _, _, er, ed, een, _, _ = e.step(a)
         assert (ee == een).all()
         assert (np.abs(oo - eo) / std).max() < 5e-3 and np.abs(rr - er).max() < 5e-3
+
+
+def test_a_foot_inside_a_riser_is_pushed_out():
+    """Side faces of the stepping stones (tasks/stepping_task.py:318-334 poses real boxes; MuJoCo's box-box test gives riser
+    contacts).  The robot stands on the floor with both toes 1 cm INSIDE the near face of a 0.1 m stair (10 cm below its top:
+    the top face does not support them).  With `side_faces` the contact set holds riser contacts whose normal faces the robot
+    and the toes are pushed back out to the soft-contact equilibrium; without it (round-1 behaviour) nothing touches the
+    toes and they stay inside.  The push-out creates no energy beyond what the penetration stored."""
+    import copy
+    from oracle.oracle import Oracle, load_model_json
+    from tools.compile_model import kinematics
+    res = {}
+    for side in (True, False):
+        mj = copy.deepcopy(load_model_json("jvrc_step"))
+        mj["stepping"]["side_faces"] = side
+        mj["cfg"]["kp"] = [20 * k for k in mj["cfg"]["kp"]]      # quasi-rigid legs (see the static stance test)
+        mj["cfg"]["kd"] = [5 * k for k in mj["cfg"]["kd"]]
+        o = Oracle("jvrc_step", tolerance=1e-12, model_dict=mj)
+        envs = o.make_envs(1)
+        o.reset(envs)
+        o.set_field(envs, 0, "mode", 1)                          # STANDING: the floor stays at z = 0
+        size, gpos = np.array(mj["geoms"][0]["size"]), np.array(mj["geoms"][0]["pos"])
+
+        def toe_x():
+            xpos, xmat = kinematics(mj, o.field(envs, 0, "qpos"))
+            return max((np.array(xpos[lk]) + np.array(xmat[lk]).reshape(3, 3) @ (gpos + np.array([size[0], sy * size[1], -size[2]])))[0]
+                       for lk in (mj["rfoot_link"], mj["lfoot_link"]) for sy in (-1, 1))
+        face = toe_x() - 0.01                                    # near (-x) face of the stair: 1 cm behind the toe corners
+        seq = np.tile([0.0, 0.0, -1.0, 0.0], (20, 1))
+        seq[0] = [face + mj["stepping"]["slab_half"][0], 0.0, 0.1, 0.0]
+        o.set_field(envs, 0, "seq", seq.reshape(-1))
+        o.set_field(envs, 0, "seq_len", 1)
+        _, dist, foot, kind = o.contacts(envs, 0)
+        n_riser0 = int((kind == 3).sum())
+        ke_max = 0.0
+        for _ in range(12):                                      # 0.3 s of PD-held stance (a = 0: target = nominal pose)
+            o.step(envs, 0, np.zeros(12))
+            ke_max = max(ke_max, o.energy(o.field(envs, 0, "qpos"), o.field(envs, 0, "qvel"))[0])
+        res[side] = dict(inside=toe_x() - face, riser0=n_riser0, ke=ke_max)
+    assert res[True]["riser0"] == 4 and res[False]["riser0"] == 0, res       # two toe corners per foot
+    assert res[True]["inside"] < 0.002 < 0.006 < res[False]["inside"], res
+    assert res[True]["ke"] < 5.0, res
+
+
+def test_riser_contacts_kernel_source_matches_oracle():
+    """The kernel source (CPU emulation) against the oracle with riser contacts ACTIVE: every env gets a 0.1 m stair whose
+    near face sits 0.5 .. 2 cm behind its toe corners (yawed differently per env), then 12 closed-loop control steps."""
+    from emu import Emu
+    from learninghumanoidwalking_b200.model import load_model, pack_model
+    from oracle.oracle import Oracle
+    from tools.compile_model import kinematics
+    mj = load_model("jvrc_step")
+    o = Oracle("jvrc_step", tolerance=1e-14)
+    n = 4
+    e = Emu(pack_model(mj, tolerance=1e-14), 64, n, seed=11, first_id=2)
+    envs = o.make_envs(n, seed=11, first_id=2)
+    assert np.abs(e.reset() - o.batch_reset(envs, n)).max() < 1e-9
+    size, gpos = np.array(mj["geoms"][0]["size"]), np.array(mj["geoms"][0]["pos"])
+    hx = mj["stepping"]["slab_half"][0]
+    for i in range(n):
+        q = o.field(envs, i, "qpos")
+        xpos, xmat = kinematics(mj, q)
+        toe = max((np.array(xpos[lk]) + np.array(xmat[lk]).reshape(3, 3) @ (gpos + np.array([size[0], sy * size[1], -size[2]])))[0]
+                  for lk in (mj["rfoot_link"], mj["lfoot_link"]) for sy in (-1, 1))
+        yaw = 0.15 * (i - 1.5)
+        face = toe - 0.005 * (i + 1)
+        seq = np.tile([0.0, 0.0, -1.0, 0.0], (20, 1))
+        seq[0] = [face + hx * np.cos(yaw), q[1] + hx * np.sin(yaw), 0.1, yaw]
+        o.set_field(envs, i, "seq", seq.reshape(-1)); o.set_field(envs, i, "seq_len", 1)
+        o.set_field(envs, i, "t1", 0); o.set_field(envs, i, "t2", 0); o.set_field(envs, i, "mode", 1)      # STANDING: floor at z = 0
+        e.sr[i, 119:199] = seq.reshape(-1)
+        e.sr[i, 199:204] = [1, 0, 0, 0, 0]
+        e.si[i, 1] = 1
+    rng = np.random.RandomState(4)
+    n_riser = 0
+    for k in range(12):
+        for i in range(n):
+            n_riser += int((o.contacts(envs, i)[3] == 3).sum())
+        a = rng.normal(size=(n, 12)) * 0.1
+        oo, _, _, orew, odone, oend = o.batch_step(envs, n, a, 400)
+        r = e.step(a, max_traj_len=400)
+        assert (r[4] == odone).all() and (r[5] == oend).all(), k
+        assert np.abs(r[0] - oo).max() < 1e-8 and np.abs(r[3] - orew).max() < 1e-9, (k, np.abs(r[0] - oo).max())
+        oq = np.stack([o.field(envs, i, "qpos") for i in range(n)])
+        assert np.abs(e.sr[:, :19] - oq).max() < 1e-9
+    assert n_riser >= 8, n_riser

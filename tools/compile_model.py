@@ -270,6 +270,7 @@ def compile_jvrc(boxes: bool = False):
             # in MuJoCo's (type, id) pair ordering, so stone contacts are invisible to the task (GRF, contact_point_z).
             # True = count them as floor (the physically meant behaviour), False = the reference's behaviour
             slab_contacts_are_floor=False,
+            side_faces=True,         # slab side faces (stair risers) stop foot-box corners; False = round-1 behaviour (they pass through)
             mode_probs=[0.15, 0.05, 0.2, 0.3, 0.3],  # CURVED, STANDING, BACKWARD, LATERAL, FORWARD
             plans=plans)
     add_setconst(model)
@@ -564,7 +565,7 @@ def main():
     tm = dict(m)
     tm["name"] = "jvrc_walk_terrain"
     tm["terrain"] = dict(strip_half=[0.15, 1.0, 0.1], side_tol=0.02, pitch=0.3, bump=0.05, z_lo=-0.035, z_hi=-0.015, xy=0.5,
-                         interval=200, contact_solref=[0.04, 1.0])
+                         interval=200, contact_solref=[0.04, 1.0], side_faces=True)
     json.dump(tm, open(os.path.join(args.out, "jvrc_walk_terrain.json"), "w"), indent=1)
     h = compile_h1()
     h["assumptions"] = ASSUMPTIONS
