@@ -75,7 +75,7 @@ def test_self_collision_proxies_terminate_when_legs_cross(oracle_tight):
     """reference row S7 (check_self_collisions): capsule proxies flag leg-leg contact; oracle and kernel agree."""
     o = oracle_tight
     mj = load_model()
-    assert len(mj["self_collision"]["capsules"]) == 8 and len(mj["self_collision"]["pairs"]) == 16
+    assert len(mj["self_collision"]["capsules"]) == 12 and len(mj["self_collision"]["pairs"]) == 36     # two capsules per thigh / shin hull
     e = Emu(pack_model(mj, tolerance=1e-14), 64, 1, seed=2)
     envs = o.make_envs(1, seed=2)
     o.reset(envs)
