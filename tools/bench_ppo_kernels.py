@@ -41,8 +41,11 @@ def main():
     last, ret, adv = torch.randn(N, device=dev, generator=g), torch.empty(T, N, device=dev), torch.empty(T, N, device=dev)
     out = {"peak_gbs": peak, "T": T, "N": N}
 
-    ms = timed(lambda: L.lhw_gae(rew.data_ptr(), val.data_ptr(), ended.data_ptr(), boot.data_ptr(), last.data_ptr(), ret.data_ptr(), T, N, 0.99, 0.95, None, st), flush)
-    out["gae"] = {"ms": ms, "bytes": 20 * n, "gbs": 20 * n / ms / 1e6, "frac": 20 * n / ms / 1e6 / peak}
+    part = torch.zeros(L.lhw_gae_partial_words(N), dtype=torch.float64, device=dev)
+    ms = timed(lambda: L.lhw_gae(rew.data_ptr(), val.data_ptr(), ended.data_ptr(), boot.data_ptr(), last.data_ptr(), ret.data_ptr(), T, N, 0.99, 0.95,
+                                 part.data_ptr(), st), flush)
+    out["gae"] = {"ms": ms, "bytes": 20 * n, "gbs": 20 * n / ms / 1e6, "frac": 20 * n / ms / 1e6 / peak,
+                  "note": "incl. the advantage statistics (sum, sumsq per block) it leaves behind for the normalisation"}
 
     stats = torch.zeros(L.lhw_adv_stats_words(), dtype=torch.float64, device=dev)
     def advnorm():
@@ -50,8 +53,15 @@ def main():
         L.lhw_adv_apply(ret.data_ptr(), val.data_ptr(), adv.data_ptr(), stats.data_ptr(), n, n, 1e-5, st)
     ms = timed(advnorm, flush)
     # two passes over (returns, values) + one write of adv = 20 B/sample for this two-pass implementation (12 B is the one-pass ideal)
-    out["adv_norm"] = {"ms": ms, "bytes": 20 * n, "gbs": 20 * n / ms / 1e6, "frac": 20 * n / ms / 1e6 / peak,
-                       "note": "two-pass (stats, apply): 2 x 8 B read + 4 B write per sample; SURVEY's 12 B/sample is the fused ideal"}
+    out["adv_norm_two_pass"] = {"ms": ms, "bytes": 20 * n, "gbs": 20 * n / ms / 1e6, "frac": 20 * n / ms / 1e6 / peak,
+                                "note": "stand-alone statistics pass + apply (2 x 8 B read + 4 B write per sample): the path for batches that did not come from the rollout"}
+
+    def advnorm_fused():      # what PPO.train runs: statistics from the GAE launch, one 12 B/sample pass
+        L.lhw_adv_stats_from_gae(part.data_ptr(), N, stats.data_ptr(), st)
+        L.lhw_adv_apply(ret.data_ptr(), val.data_ptr(), adv.data_ptr(), stats.data_ptr(), n, n, 1e-5, st)
+    ms = timed(advnorm_fused, flush)
+    out["adv_norm"] = {"ms": ms, "bytes": 12 * n, "gbs": 12 * n / ms / 1e6, "frac": 12 * n / ms / 1e6 / peak,
+                       "note": "statistics from the GAE launch + one pass: 8 B read + 4 B write per sample (SURVEY 8d's 12 B/sample)"}
 
     obs, act = torch.randn(n, 37, device=dev, generator=g), torch.randn(n, 12, device=dev, generator=g)
     r1, a1 = ret.reshape(n, 1), adv.reshape(n, 1)
