@@ -105,6 +105,17 @@ int lhw_adv_stats(const float* returns, const float* values, double* stats, long
 int lhw_adv_apply(const float* returns, const float* values, float* adv, double* stats, long long count,
                   long long count_total, float eps, void* stream);
 
+/* lhw_ppo_loss: the loss tail of PPO.update_actor_critic (rl/algos/ppo.py:302-386), forward and backward in one launch, for a
+ * Gaussian policy with fixed per-action std: from the policy means mu / old_mu [B,A], the taken actions, advantages, returns,
+ * values and (optional) mirrored actions it writes out8 = {actor_loss, entropy_penalty, critic_loss, approx_kl_div, mirror_loss,
+ * imitation_loss (0), clip_fraction, total} and the gradients of total = actor + mirror_coeff * mirror + ent_coeff * entropy_penalty
+ * + critic w.r.t. mu (g_mu), the mirrored actions (g_mirr) and the values (g_val).  partials: lhw_ppo_loss_partial_words(B)
+ * doubles; ticket: one zero-initialised uint32.  Deterministic (block-ordered reduction). */
+int lhw_ppo_loss_partial_words(int B);
+int lhw_ppo_loss(const float* mu, const float* old_mu, const float* act, const float* adv, const float* ret, const float* val,
+                 const float* mirr_or_null, const float* stds, int B, int A, float clip, float mirror_coeff, float ent_coeff,
+                 float* g_mu, float* g_mirr_or_null, float* g_val, double* partials, unsigned int* ticket, float* out8, void* stream);
+
 /* lhw_gather_minibatch: the fancy-index gathers of rl/algos/ppo.py:535-538 in one launch.
  * idx [B] int64 sample indices into the flattened batch. */
 int lhw_gather_minibatch(const float* obs, const float* act, const float* ret, const float* adv, const int64_t* idx,

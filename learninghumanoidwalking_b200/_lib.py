@@ -38,6 +38,8 @@ SIGNATURES = {
     "lhw_adv_stats_words": (c_int, []),
     "lhw_adv_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "lhw_adv_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_float, c_void_p]),
+    "lhw_ppo_loss_partial_words": (c_int, [c_int]),
+    "lhw_ppo_loss": (c_int, [c_void_p] * 8 + [c_int, c_int, c_float, c_float, c_float] + [c_void_p] * 7),
     "lhw_gather_minibatch": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p]),
     "lhw_grad_sumsq": (c_int, [c_void_p, c_void_p, c_ll, c_float, c_void_p]),
     "lhw_comm_last_error": (ctypes.c_char_p, []),

@@ -319,3 +319,119 @@ int lhw_clip_adam_dev(float* param, const float* grad, float* exp_avg, float* ex
 }
 
 }  // extern "C"
+
+// ================================================================= fused PPO loss tail (rl/algos/ppo.py:302-386)
+// Everything between the network outputs and the scalar loss, forward AND backward, in one pass over the minibatch:
+//   log-probabilities of the taken actions under the new and the old policy (fixed per-action std), ratio, clipped surrogate,
+//   value MSE, entropy, mirror MSE, approximate KL, clip fraction -> 7 scalars; and the gradients of
+//   total = actor + mirror_coeff * mirror + ent_coeff * entropy_penalty + critic  w.r.t. the policy mean, the mirrored
+//   mean and the values.  torch autograd then only runs the three MLP backward passes (cuBLAS).  One thread per sample,
+//   per-block partial sums combined in block order by the last block (ticket) -> run-to-run deterministic.
+namespace {
+constexpr int LOSS_BLOCK = 256, LOSS_NS = 6;   // partial sums: surrogate, clipfrac, critic, kl, mirror, (spare)
+__global__ void __launch_bounds__(LOSS_BLOCK)
+    ppo_loss_kernel(const float* __restrict__ mu, const float* __restrict__ old_mu, const float* __restrict__ act,
+                    const float* __restrict__ adv, const float* __restrict__ ret, const float* __restrict__ val,
+                    const float* __restrict__ mirr /* [B,A] mirrored actions or null */, const float* __restrict__ stds, int B, int A,
+                    float clip, float mirror_coeff, float ent_coeff, float* __restrict__ g_mu, float* __restrict__ g_mirr,
+                    float* __restrict__ g_val, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                    float* __restrict__ out7) {
+  __shared__ double sh[LOSS_NS][LOSS_BLOCK / 32];
+  __shared__ int last;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  double s[LOSS_NS] = {0, 0, 0, 0, 0, 0};
+  const float invB = 1.0f / (float)B, invBA = 1.0f / ((float)B * (float)A);
+  if (b < B) {
+    const float* m = mu + (size_t)b * A;
+    const float* om = old_mu + (size_t)b * A;
+    const float* a = act + (size_t)b * A;
+    float lp = 0.f, olp = 0.f;
+    for (int k = 0; k < A; k++) {      // Normal(mu, sd).log_prob(a) summed over the action dims (the constant terms cancel in lp - olp)
+      const float sd = stds[k], z = (a[k] - m[k]) / sd, zo = (a[k] - om[k]) / sd;
+      lp += -0.5f * z * z;
+      olp += -0.5f * zo * zo;
+    }
+    const float dlp = lp - olp, ratio = expf(dlp), ad = adv[b];
+    const float cpi = ratio * ad, rc = fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip), cl = rc * ad;
+    s[0] = (double)fminf(cpi, cl);
+    s[1] = fabsf(ratio - 1.0f) > clip ? 1.0 : 0.0;
+    const float dv = val[b] - ret[b];
+    s[2] = (double)dv * dv;
+    s[3] = (double)((ratio - 1.0f) - dlp);
+    // d(-mean min(cpi, clip)) / d lp : the clamp passes the gradient inside [1-c, 1+c]; outside, only the unclipped branch
+    // has one, and torch.min hands it the gradient when it is the smaller of the two
+    const bool inside = ratio >= 1.0f - clip && ratio <= 1.0f + clip;
+    const float glp = (inside || cpi < cl) ? -invB * ratio * ad : 0.0f;
+    g_val[b] = 2.0f * dv * invB;
+    for (int k = 0; k < A; k++) {
+      const float sd = stds[k];
+      float g = glp * (a[k] - m[k]) / (sd * sd);
+      if (mirr) {
+        const float d = m[k] - mirr[(size_t)b * A + k];
+        s[4] += (double)d * d;
+        const float gm = mirror_coeff * 2.0f * d * invBA;
+        g += gm;
+        g_mirr[(size_t)b * A + k] = -gm;
+      }
+      g_mu[(size_t)b * A + k] = g;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < LOSS_NS; q++) {
+    double v = s[q];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < LOSS_NS; q++) {
+      double v = 0;
+      for (int w = 0; w < LOSS_BLOCK / 32; w++) v += sh[q][w];
+      partials[(size_t)blockIdx.x * LOSS_NS + q] = v;
+    }
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x >= 32) return;
+  __threadfence();
+  double t[LOSS_NS];
+#pragma unroll
+  for (int q = 0; q < LOSS_NS; q++) {
+    double v = 0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) v += __ldcg(partials + (size_t)k * LOSS_NS + q);
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    t[q] = v;
+  }
+  if (threadIdx.x == 0) {
+    float ent = 0.f;     // Normal.entropy() = 0.5 + 0.5 log(2 pi) + log sd per action dim, the same for every sample
+    for (int k = 0; k < A; k++) ent += 0.5f + 0.9189385332046727f + logf(stds[k]);
+    ent /= (float)A;
+    const float actor = (float)(-t[0] / B), critic = (float)(t[2] / B), mirror = mirr ? (float)(t[4] / ((double)B * A)) : 0.f;
+    out7[0] = actor;                    // actor_loss
+    out7[1] = -ent;                     // entropy_penalty
+    out7[2] = critic;                   // critic_loss
+    out7[3] = (float)(t[3] / B);        // approx_kl_div
+    out7[4] = mirror;                   // mirror_loss
+    out7[5] = 0.f;                      // imitation_loss (outside the accelerated path)
+    out7[6] = (float)(t[1] / B);        // clip_fraction
+    out7[7] = actor + mirror_coeff * mirror + ent_coeff * (-ent) + critic;   // total
+    *ticket = 0;
+  }
+}
+}  // namespace
+
+extern "C" int lhw_ppo_loss_partial_words(int B) { return LOSS_NS * ((B + LOSS_BLOCK - 1) / LOSS_BLOCK); }
+
+extern "C" int lhw_ppo_loss(const float* mu, const float* old_mu, const float* act, const float* adv, const float* ret, const float* val,
+                            const float* mirr_or_null, const float* stds, int B, int A, float clip, float mirror_coeff, float ent_coeff,
+                            float* g_mu, float* g_mirr_or_null, float* g_val, double* partials, unsigned int* ticket, float* out8,
+                            void* stream) {
+  if (B <= 0 || A <= 0) return 0;
+  if (mirr_or_null && !g_mirr_or_null) { g_perr = "lhw_ppo_loss: mirrored actions without a gradient buffer"; return -1; }
+  ppo_loss_kernel<<<(B + LOSS_BLOCK - 1) / LOSS_BLOCK, LOSS_BLOCK, 0, (cudaStream_t)stream>>>(
+      mu, old_mu, act, adv, ret, val, mirr_or_null, stds, B, A, clip, mirror_coeff, ent_coeff, g_mu, g_mirr_or_null, g_val, partials,
+      ticket, out8);
+  KCHECK("ppo_loss_kernel");
+  return 0;
+}

@@ -147,6 +147,32 @@ void gather_minibatch(const Tensor& obs, const Tensor& act, const Tensor& ret, c
                           adv_b.data_ptr<float>(), (int)B, (int)od, (int)ad, stream_of(obs)), "lhw_gather_minibatch");
 }
 
+void ppo_loss(const Tensor& mu, const Tensor& old_mu, const Tensor& act, const Tensor& adv, const Tensor& ret, const Tensor& val,
+              const OptTensor& mirr, const Tensor& stds, double clip, double mirror_coeff, double ent_coeff, Tensor g_mu,
+              const OptTensor& g_mirr, Tensor g_val, Tensor partials, Tensor ticket, Tensor out8) {
+  TORCH_CHECK(mu.dim() == 2, "lhw: mu must be [B, A]");
+  const int64_t B = mu.size(0), A = mu.size(1);
+  const int dev = mu.is_cuda() ? mu.get_device() : -1;
+  check_cuda(mu, "mu", at::kFloat, dev); check_cuda(old_mu, "old_mu", at::kFloat, dev); check_shape(old_mu, "old_mu", {B, A});
+  check_cuda(act, "act", at::kFloat, dev); check_shape(act, "act", {B, A});
+  check_cuda(adv, "adv", at::kFloat, dev); check_cuda(ret, "ret", at::kFloat, dev); check_cuda(val, "val", at::kFloat, dev);
+  TORCH_CHECK(adv.numel() == B && ret.numel() == B && val.numel() == B, "lhw: adv / ret / val must hold one value per sample");
+  check_cuda(stds, "stds", at::kFloat, dev); check_shape(stds, "stds", {A});
+  check_cuda(g_mu, "g_mu", at::kFloat, dev); check_shape(g_mu, "g_mu", {B, A});
+  check_cuda(g_val, "g_val", at::kFloat, dev); TORCH_CHECK(g_val.numel() == B, "lhw: g_val must hold one value per sample");
+  TORCH_CHECK(mirr.has_value() == g_mirr.has_value(), "lhw: mirr and g_mirr go together");
+  if (mirr) { check_cuda(*mirr, "mirr", at::kFloat, dev); check_shape(*mirr, "mirr", {B, A}); check_cuda(*g_mirr, "g_mirr", at::kFloat, dev); check_shape(*g_mirr, "g_mirr", {B, A}); }
+  check_cuda(partials, "partials", at::kDouble, dev); check_shape(partials, "partials", {lhw_ppo_loss_partial_words((int)B)});
+  check_cuda(ticket, "ticket", at::kInt, dev); TORCH_CHECK(ticket.numel() >= 1, "lhw: ticket is empty");
+  check_cuda(out8, "out8", at::kFloat, dev); check_shape(out8, "out8", {8});
+  c10::cuda::CUDAGuard guard(dev);
+  ok(lhw_ppo_loss(mu.data_ptr<float>(), old_mu.data_ptr<float>(), act.data_ptr<float>(), adv.data_ptr<float>(), ret.data_ptr<float>(),
+                  val.data_ptr<float>(), mirr ? mirr->data_ptr<float>() : nullptr, stds.data_ptr<float>(), (int)B, (int)A, (float)clip,
+                  (float)mirror_coeff, (float)ent_coeff, g_mu.data_ptr<float>(), g_mirr ? g_mirr->data_ptr<float>() : nullptr,
+                  g_val.data_ptr<float>(), partials.data_ptr<double>(), (unsigned int*)ticket.data_ptr<int>(), out8.data_ptr<float>(),
+                  stream_of(mu)), "lhw_ppo_loss");
+}
+
 void grad_sumsq(const Tensor& grad, Tensor norm, double grad_scale) {
   const int dev = grad.is_cuda() ? grad.get_device() : -1;
   check_cuda(grad, "grad", at::kFloat, dev); check_cuda(norm, "norm", at::kFloat, dev);
@@ -199,6 +225,9 @@ TORCH_LIBRARY(lhw, m) {
   m.def("adv_apply(Tensor returns, Tensor values, Tensor(a!) adv, Tensor(b!) stats, int count_total, float eps) -> ()");
   m.def("gather_minibatch(Tensor obs, Tensor act, Tensor ret, Tensor adv, Tensor idx, Tensor(a!) obs_b, Tensor(b!) act_b, Tensor(c!) ret_b, "
         "Tensor(d!) adv_b) -> ()");
+  m.def("ppo_loss(Tensor mu, Tensor old_mu, Tensor act, Tensor adv, Tensor ret, Tensor val, Tensor? mirr, Tensor stds, float clip, "
+        "float mirror_coeff, float ent_coeff, Tensor(a!) g_mu, Tensor(b!)? g_mirr, Tensor(c!) g_val, Tensor(d!) partials, Tensor(e!) ticket, "
+        "Tensor(f!) out8) -> ()");
   m.def("grad_sumsq(Tensor grad, Tensor(a!) norm, float grad_scale) -> ()");
   m.def("clip_adam_dev(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, Tensor norm, Tensor(d!) step_dev, float lr, "
         "float beta1, float beta2, float eps, float max_norm, float grad_scale) -> ()");
@@ -216,6 +245,7 @@ TORCH_LIBRARY_IMPL(lhw, CompositeExplicitAutograd, m) {
   m.impl("adv_stats", &adv_stats);
   m.impl("adv_apply", &adv_apply);
   m.impl("gather_minibatch", &gather_minibatch);
+  m.impl("ppo_loss", &ppo_loss);
   m.impl("grad_sumsq", &grad_sumsq);
   m.impl("clip_adam_dev", &clip_adam_dev);
   m.impl("fused_exchange", &fused_exchange);

@@ -29,6 +29,25 @@ from .storage import BatchData
 from .workers import DeviceRolloutWorker
 
 
+class _FusedPPOLoss(torch.autograd.Function):
+    """The loss tail of update_actor_critic (rl/algos/ppo.py:302-386) as ONE launch (csrc/ppo_kernels.cu: ppo_loss_kernel): the 7
+    scalars and d total / d (policy mean, mirrored actions, values) come out of the forward pass; backward hands those gradients
+    to autograd, which then only runs the MLP backward passes (cuBLAS)."""
+
+    @staticmethod
+    def forward(ctx, mu, values, mirr, old_mu, act, adv, ret, stds, clip, mirror_coeff, ent_coeff, bufs):
+        g_mu, g_mirr, g_val, partials, ticket, out8 = bufs
+        _lib.ops().ppo_loss(mu, old_mu, act, adv, ret, values, mirr, stds, clip, mirror_coeff, ent_coeff, g_mu,
+                            g_mirr if mirr is not None else None, g_val, partials, ticket, out8)
+        ctx.bufs, ctx.has_mirr = (g_mu, g_mirr, g_val), mirr is not None
+        return out8[7]
+
+    @staticmethod
+    def backward(ctx, gout):
+        g_mu, g_mirr, g_val = ctx.bufs
+        return (g_mu * gout, g_val * gout, (g_mirr * gout) if ctx.has_mirr else None) + (None,) * 9
+
+
 def get_worker_seed(master_seed: int, worker_id: int, offset: int = 0) -> int:
     """rl/utils/seeding.py:34-52 (the rank plays the worker's role)."""
     return (master_seed * 1_000_003 + offset * 10_007 + worker_id) % (2 ** 32 - 1)
@@ -131,8 +150,39 @@ class PPO:
         return w.sample(self.gamma, self.lam, self.steps_per_env, self.max_traj_len, deterministic)
 
     # ------------------------------------------------------------------ one optimiser step (rl/algos/ppo.py:299-406)
+    def _fused_loss_ok(self, obs_batch, mask) -> bool:
+        import os
+        return (os.environ.get("LHW_FUSED_LOSS", "1") != "0" and obs_batch.is_cuda and isinstance(mask, (int, float)) and mask == 1
+                and not getattr(self.policy, "learn_std", False) and self.imitate_coeff == 0.0 and isinstance(self.policy, Gaussian_FF_Actor))
+
+    def _loss_fused(self, obs_batch, action_batch, return_batch, advantage_batch, mirror_observation, mirror_action):
+        """total loss (with the backward graph attached) and the 7 scalars, the elementwise part in one launch."""
+        B, A = action_batch.shape
+        bufs = getattr(self, "_loss_bufs", None)
+        if bufs is None or bufs[0].shape != (B, A):
+            f32 = dict(dtype=torch.float32, device=obs_batch.device)
+            bufs = self._loss_bufs = (torch.empty(B, A, **f32), torch.empty(B, A, **f32), torch.empty(B, 1, **f32),
+                                      torch.zeros(_lib.lib().lhw_ppo_loss_partial_words(B), dtype=torch.float64, device=obs_batch.device),
+                                      torch.zeros(1, dtype=torch.int32, device=obs_batch.device), torch.zeros(8, **f32))
+        mu = self.policy(obs_batch, deterministic=True)
+        with torch.no_grad():
+            old_mu = self.old_policy(obs_batch, deterministic=True)
+        values = self.critic(obs_batch)
+        mirr = None
+        if mirror_observation is not None and mirror_action is not None:
+            mirr = mirror_action(self.policy(mirror_observation(obs_batch))).contiguous()
+        stds = self.policy.stds if torch.is_tensor(self.policy.stds) else torch.as_tensor(self.policy.stds)
+        total = _FusedPPOLoss.apply(mu, values, mirr, old_mu, action_batch, advantage_batch, return_batch,
+                                    stds.to(mu.device, torch.float32), float(self.clip), float(self.mirror_coeff), float(self.ent_coeff), bufs)
+        out = bufs[5].clone()       # the buffer is rewritten by the next update; callers may hold on to the scalars
+        return total, tuple(out[k] for k in range(7))
+
     def update_actor_critic(self, obs_batch, action_batch, return_batch, advantage_batch, mask,
                             mirror_observation=None, mirror_action=None):
+        if self._fused_loss_ok(obs_batch, mask):
+            total_loss, scalars = self._loss_fused(obs_batch, action_batch, return_batch, advantage_batch, mirror_observation,
+                                                   mirror_action)
+            return self._optimizer_step(total_loss, scalars)
         pdf = self.policy.distribution(obs_batch)
         log_probs = pdf.log_prob(action_batch).sum(-1, keepdim=True)
         with torch.no_grad():
@@ -156,6 +206,11 @@ class PPO:
             approx_kl_div = torch.mean((ratio - 1) - (log_probs - old_log_probs))
         total_loss = (actor_loss + self.mirror_coeff * mirror_loss + self.imitate_coeff * imitation_loss
                       + self.ent_coeff * entropy_penalty + critic_loss)
+        return self._optimizer_step(total_loss, (actor_loss, entropy_penalty, critic_loss, approx_kl_div, mirror_loss, imitation_loss,
+                                                 clip_fraction))
+
+    def _optimizer_step(self, total_loss, scalars):
+        """backward + the exchange / clip / Adam step (rl/algos/ppo.py:389-396); returns the 7 scalars detached."""
         self.actor_optimizer.zero_grad()
         self.critic_optimizer.zero_grad()
         total_loss.backward()
@@ -180,8 +235,7 @@ class PPO:
             c_opt.step()
         # detached: a caller holding on to the losses must not keep this step's autograd graph (and its AccumulateGrad nodes)
         # alive into the next one, which may be captured into a CUDA graph
-        return tuple(t.detach() for t in (actor_loss, entropy_penalty, critic_loss, approx_kl_div, mirror_loss, imitation_loss,
-                                          clip_fraction))
+        return tuple(t.detach() for t in scalars)
 
     # ------------------------------------------------------------------ one minibatch update, replayed from a CUDA graph
     def _update_step(self, ob, ab, rb, db, obs_mirr, act_mirr) -> torch.Tensor:

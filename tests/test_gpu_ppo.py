@@ -240,6 +240,65 @@ def test_fused_exchange_kernel_single_rank_matches_oracle_clip_adam():
     comm.close()
 
 
+def test_ppo_loss_kernel_matches_the_closed_form_oracle():
+    """lhw_ppo_loss against oracle/ppo_oracle.py: ppo_loss_and_grads (itself equal to torch autograd on the reference's
+    formulation, tests/test_ppo_loss_oracle.py): 8 scalars and the three gradients, with and without the mirror term."""
+    from oracle.ppo_oracle import ppo_loss_and_grads
+    L = _lib()
+    rng = np.random.RandomState(3)
+    for B, with_mirr in ((21845, True), (300, False)):
+        A = 12
+        stds = np.full(A, 0.223, dtype=np.float32)
+        mu = (rng.normal(size=(B, A)) * 0.2).astype(np.float32)
+        old_mu = (mu + rng.normal(size=(B, A)) * 0.05).astype(np.float32)
+        act = (old_mu + rng.normal(size=(B, A)) * 0.223).astype(np.float32)
+        adv, ret, val = (rng.normal(size=(B, 1)).astype(np.float32) for _ in range(3))
+        mirr = (mu + rng.normal(size=(B, A)) * 0.05).astype(np.float32) if with_mirr else None
+        d = lambda a: None if a is None else torch.as_tensor(a, device="cuda")
+        g_mu, g_mirr, g_val = torch.empty(B, A, device="cuda"), torch.empty(B, A, device="cuda"), torch.empty(B, 1, device="cuda")
+        part = torch.zeros(L.lib().lhw_ppo_loss_partial_words(B), dtype=torch.float64, device="cuda")
+        ticket, out8 = torch.zeros(1, dtype=torch.int32, device="cuda"), torch.zeros(8, device="cuda")
+        for _ in range(2):      # twice: the ticket counter must come back to zero
+            L.ops().ppo_loss(d(mu), d(old_mu), d(act), d(adv), d(ret), d(val), d(mirr), d(stds), 0.2, 0.4, 0.01, g_mu,
+                             g_mirr if with_mirr else None, g_val, part, ticket, out8)
+        exp = ppo_loss_and_grads(mu, old_mu, act, adv, ret, val, mirr, stds, 0.2, 0.4, 0.01)
+        assert np.abs(out8.cpu().numpy() - exp[0]).max() < 2e-5 and int(ticket.item()) == 0
+        assert 0.02 < exp[0][6] < 0.98
+        assert np.abs(g_mu.cpu().numpy() - exp[1]).max() < 1e-6 * max(1.0, np.abs(exp[1]).max() * B)
+        assert np.abs(g_mu.cpu().numpy() - exp[1]).max() < 2e-5 * np.abs(exp[1]).max()
+        assert np.abs(g_val.cpu().numpy().reshape(-1) - exp[3]).max() < 2e-6 * np.abs(exp[3]).max() + 1e-12
+        if with_mirr:
+            assert np.abs(g_mirr.cpu().numpy() - exp[2]).max() < 2e-6 * np.abs(exp[2]).max() + 1e-12
+
+
+def test_fused_loss_kernel_matches_the_torch_loss_graph(monkeypatch):
+    """lhw_ppo_loss (forward + backward of the loss tail in one launch) against the torch graph it replaces
+    (rl/algos/ppo.py:302-386 restated with autograd): the 7 scalars and the weights after one and two optimiser steps."""
+    from learninghumanoidwalking_b200.rl import PPO
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LHW_FUSED_LOSS", mode)
+        monkeypatch.setenv("LHW_UPDATE_GRAPH", "0")
+        ppo = PPO(_env_fn(seed=8), _args(), seed=8)
+        ppo.make_optimizers()
+        batch = ppo.sample_parallel_with_workers()
+        adv = ppo.normalize_advantages(batch.returns.contiguous(), batch.values.contiguous())
+        env = ppo.env
+        outs = []
+        for k in range(2):
+            sl = slice(300 * k, 300 * k + 300)      # 300: not a multiple of the kernel's block size
+            o = ppo.update_actor_critic(batch.states[sl].contiguous(), batch.actions[sl].contiguous(), batch.returns[sl].contiguous(),
+                                        (adv[sl] * (3.0 if k else 1.0)).contiguous(), 1,     # larger advantages: some ratios leave the clip range
+                                        mirror_observation=env.mirror_clock_observation, mirror_action=env.mirror_action)
+            outs.append(torch.stack([x.float() for x in o]).cpu())
+        res[mode] = (outs, ppo._flat_param.clone().cpu())
+        ppo.env.close()
+    for a, b in zip(res["0"][0], res["1"][0]):
+        assert (a - b).abs().max().item() < 2e-5 * max(1.0, a.abs().max().item()), (a, b)
+    assert (res["0"][1] - res["1"][1]).abs().max().item() < 2e-6
+    assert res["1"][0][1][6] > 0 or res["1"][0][1][3].abs() > 0      # the second step really moved the ratio away from 1
+
+
 def test_rollout_graph_follows_the_weights_after_make_optimizers():
     """The public sequence PPO(...); sample_parallel_with_workers(); train() (the reference's tests use it): the rollout
     graph captured by the first call holds the parameter addresses of BEFORE make_optimizers() re-homes them into the flat
