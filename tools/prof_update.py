@@ -49,3 +49,8 @@ torch.cuda.synchronize()
 wall_g = (time.time() - t0) / N
 print(f"minibatch {mb}: graph-replayed update {wall_g*1e3:.3f} ms/update (captured: {ppo._ug is not None})")
 print(f"minibatch {mb}: wall {wall*1e3:.3f} ms/update, summed CUDA kernel time {cuda_us/N/1e3:.3f} ms/update, ~{nk/N:.0f} kernels/update")
+rows = sorted(((getattr(e, "self_device_time_total", getattr(e, "self_cuda_time_total", 0)), e.count, e.key) for e in ev), reverse=True)
+print("top kernels by device time (us per update, launches per update, name):")
+for us, cnt, key in rows[:14]:
+    if us > 0:
+        print(f"  {us / N:9.1f} {cnt / N:6.1f}  {key[:110]}")
