@@ -173,6 +173,29 @@ class BatchedHumanoidEnv:
                        "lhw_sim_step")
         return self.obs, self.reward, self.done, self.ended
 
+    def step_slice(self, lo: int, hi: int, actions: torch.Tensor, autoreset: bool = True):
+        """One control step of environments [lo, hi) only (their records, outputs and Philox ids are the same as in a full-batch
+        step: an environment's trajectory does not depend on what it is launched with).  The rollout worker advances two halves
+        of the batch on two streams with this, so that the tail of one half's launch overlaps the other half's work."""
+        sl = slice(lo, hi)
+        if actions.dtype != self.dtype or not actions.is_contiguous() or actions.device != self.device:
+            actions = actions.to(device=self.device, dtype=self.dtype).contiguous()
+        out = (self.obs[sl], self.reward[sl], self.done[sl], self.ended[sl])
+        if _lib.use_torch_ops():
+            _lib.ops().sim_step(self._h.value, self.state_r[sl], self.state_i[sl], self.seed, self.first_env_id + lo, actions,
+                                self.max_traj_len, bool(autoreset), out[0], self.term_obs[sl], out[1], self.rew_terms[sl], out[2], out[3],
+                                self.ep_len[sl], self.ep_rew[sl])
+            return out
+        assert actions.shape == (hi - lo, self.act_dim), actions.shape
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().lhw_sim_step(self._h, self.state_r[sl].data_ptr(), self.state_i[sl].data_ptr(), hi - lo, self.seed,
+                                               self.first_env_id + lo, actions.data_ptr(), self.max_traj_len, int(autoreset),
+                                               out[0].data_ptr(), self.term_obs[sl].data_ptr(), out[1].data_ptr(),
+                                               self.rew_terms[sl].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                               self.ep_len[sl].data_ptr(), self.ep_rew[sl].data_ptr(), _lib.current_stream_ptr()),
+                       "lhw_sim_step")
+        return out
+
     def bind(self):
         """Upload this env's model constants if another env of the same precision used the constant bank last
         (needed before replaying CUDA graphs that contain lhw_sim_step launches)."""

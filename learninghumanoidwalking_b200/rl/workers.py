@@ -47,23 +47,36 @@ class DeviceRolloutWorker:
         self.env.robot.iteration_count = iteration_count
 
     # ------------------------------------------------------------------ one control step of the rollout loop
-    def _step_body(self, buf, state, noise, t_idx, deterministic):
-        """policy -> action -> critic -> env.step -> bootstrap -> buffer writes, all on device tensors; `t_idx` is a
-        1-element device index so the same code can be replayed from a CUDA graph (no host-side loop counter)."""
+    def _parts(self, N: int):
+        """The batch as one part, or as two halves that advance independently on two streams: a control step of one half does
+        not wait for the other half's, so the tail of one half's step launch (4096 fp64 environments are 1.7 resident waves)
+        and its MLP / buffer kernels overlap the other half's step kernel.  Every per-environment result is unchanged (an
+        environment's trajectory does not depend on what it is launched with); LHW_ROLLOUT_SPLIT=0 keeps one part."""
+        import os
+        if os.environ.get("LHW_ROLLOUT_SPLIT", "1") == "0" or N < 1024:
+            return [(0, N)]
+        return [(0, N // 2), (N // 2, N)]
+
+    def _step_body(self, buf, part, state, noise, t_idx, deterministic):
+        """policy -> action -> critic -> env.step -> bootstrap -> buffer writes for the environments [lo, hi) of `part`, all on
+        device tensors; `t_idx` is a 1-element device index so the same code can be replayed from a CUDA graph (no host-side
+        loop counter).  `state` is the [hi - lo, obs] view of the worker's current observations."""
         env = self.env
+        lo, hi = part
+        V = lambda t: t[:, lo:hi]          # the part's columns of a time-major [T, N, ...] buffer
         mu = self.policy(state, deterministic=True)
-        action = mu if deterministic else mu + self.policy.stds * noise.index_select(0, t_idx)[0]
-        buf.states.index_copy_(0, t_idx, state.unsqueeze(0))
-        buf.actions.index_copy_(0, t_idx, action.unsqueeze(0))
-        buf.values.index_copy_(0, t_idx, self.critic(state).squeeze(-1).unsqueeze(0))
-        obs, reward, done, ended = env.step(action if env.dtype == torch.float32 else action.double())
-        buf.rewards.index_copy_(0, t_idx, reward.float().unsqueeze(0))
-        buf.ended.index_copy_(0, t_idx, ended.unsqueeze(0))
-        buf.ep_len.index_copy_(0, t_idx, env.ep_len.unsqueeze(0))
-        buf.ep_rew.index_copy_(0, t_idx, env.ep_rew.float().unsqueeze(0))
+        action = mu if deterministic else mu + self.policy.stds * V(noise).index_select(0, t_idx)[0]
+        V(buf.states).index_copy_(0, t_idx, state.unsqueeze(0))
+        V(buf.actions).index_copy_(0, t_idx, action.unsqueeze(0))
+        V(buf.values).index_copy_(0, t_idx, self.critic(state).squeeze(-1).unsqueeze(0))
+        obs, reward, done, ended = env.step_slice(lo, hi, action if env.dtype == torch.float32 else action.double())
+        V(buf.rewards).index_copy_(0, t_idx, reward.float().unsqueeze(0))
+        V(buf.ended).index_copy_(0, t_idx, ended.unsqueeze(0))
+        V(buf.ep_len).index_copy_(0, t_idx, env.ep_len[lo:hi].unsqueeze(0))
+        V(buf.ep_rew).index_copy_(0, t_idx, env.ep_rew[lo:hi].float().unsqueeze(0))
         # truncation bootstrap: (not done) * critic(pre-reset next_state) where the episode ended
-        v_term = self.critic(env.term_obs.float()).squeeze(-1)
-        buf.boot.index_copy_(0, t_idx, torch.where((ended != 0) & (done == 0), v_term, torch.zeros_like(v_term)).unsqueeze(0))
+        v_term = self.critic(env.term_obs[lo:hi].float()).squeeze(-1)
+        V(buf.boot).index_copy_(0, t_idx, torch.where((ended != 0) & (done == 0), v_term, torch.zeros_like(v_term)).unsqueeze(0))
         state.copy_(obs.float())
         t_idx.add_(1)
 
@@ -80,41 +93,59 @@ class DeviceRolloutWorker:
             self._graphs = {}
         buf = self._buf
         buf.gamma, buf.lam = gamma, lam
+        parts = self._parts(N)
         if self.current_state is None:
             self.current_state = env.reset().float().clone()
-            self._t_idx = torch.zeros(1, dtype=torch.long, device=self.device)
             self._noise = torch.zeros(T, N, env.act_dim, device=self.device)
+        if getattr(self, "_t_idx", None) is None or len(self._t_idx) != len(parts):
+            self._t_idx = [torch.zeros(1, dtype=torch.long, device=self.device) for _ in parts]
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in parts]
         if self._noise.shape[0] != T:
             self._noise = torch.zeros(T, N, env.act_dim, device=self.device)
-        state, t_idx, noise = self.current_state, self._t_idx, self._noise
-        t_idx.zero_()
+        noise = self._noise
+        states = [self.current_state[lo:hi] for lo, hi in parts]
+        for t in self._t_idx:
+            t.zero_()
         if not deterministic:
             noise.copy_(torch.randn(noise.shape, device=self.device, generator=self.gen))
+        cur = torch.cuda.current_stream(self.device)
         use_graph = os.environ.get("LHW_ROLLOUT_GRAPH", "1") != "0"
         if use_graph:
-            key = (bool(deterministic), env.max_traj_len)
-            g = self._graphs.get(key)
+            key = (bool(deterministic), int(max_traj_len), len(parts))
+            graphs = self._graphs.get(key)
             first = 0
-            if g is None:
-                # warm-up on a side stream (cuBLAS workspaces, constant-memory upload), then capture ONE control step
-                s = torch.cuda.Stream(device=self.device)
-                s.wait_stream(torch.cuda.current_stream(self.device))
-                with torch.cuda.stream(s):
-                    self._step_body(buf, state, noise, t_idx, deterministic)
-                torch.cuda.current_stream(self.device).wait_stream(s)
+            if graphs is None:
+                # warm-up on the side streams (cuBLAS workspaces, constant-memory upload), then capture ONE control step per part
+                graphs = []
+                for p, part in enumerate(parts):
+                    s = self._streams[p]
+                    s.wait_stream(cur)
+                    with torch.cuda.stream(s):
+                        self._step_body(buf, part, states[p], noise, self._t_idx[p], deterministic)
+                    cur.wait_stream(s)
                 first = 1
                 if T > 1:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._step_body(buf, state, noise, t_idx, deterministic)
-                    self._graphs[key] = g   # capturing does not execute: warm-up did step 0, replays do the rest
+                    for p, part in enumerate(parts):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=self._streams[p]):
+                            self._step_body(buf, part, states[p], noise, self._t_idx[p], deterministic)
+                        graphs.append(g)
+                    self._graphs[key] = graphs   # capturing does not execute: warm-up did step 0, replays do the rest
             env.bind()   # make sure THIS env's model constants are the resident ones before replaying launches
-            for _ in range(first, T):
-                g.replay()
+            if graphs:
+                for p, g in enumerate(graphs):     # each part runs its T steps on its own stream; they only meet at the end
+                    s = self._streams[p]
+                    s.wait_stream(cur)
+                    with torch.cuda.stream(s):
+                        for _ in range(first, T):
+                            g.replay()
+                for s in self._streams:
+                    cur.wait_stream(s)
         else:
             for _ in range(T):
-                self._step_body(buf, state, noise, t_idx, deterministic)
-        buf.last_val.copy_(self.critic(state).squeeze(-1))
+                for p, part in enumerate(parts):
+                    self._step_body(buf, part, states[p], noise, self._t_idx[p], deterministic)
+        buf.last_val.copy_(self.critic(self.current_state).squeeze(-1))
         buf.finish()
         self.total_steps += T * N
         return buf.get_data(env_major=env_major)

@@ -331,6 +331,29 @@ def test_graph_replayed_rollout_is_bitwise_equal_to_the_eager_loop(monkeypatch):
         assert torch.equal(a, b)
 
 
+def test_two_stream_rollout_halves_equal_the_eager_loop_and_track_the_single_stream_rollout(monkeypatch):
+    """Batches of >= 1024 environments advance as two halves on two streams (DeviceRolloutWorker._parts).  The replayed graphs
+    must give bit-identical batches to the eager loop over the same halves, two calls in a row (episodes persist), and the same
+    environment trajectories as the single-stream rollout up to the MLP's batch-size-dependent rounding."""
+    from learninghumanoidwalking_b200.rl import PPO
+    outs = {}
+    for name, graph, split in (("graph", "1", "1"), ("eager", "0", "1"), ("single", "1", "0")):
+        monkeypatch.setenv("LHW_ROLLOUT_GRAPH", graph)
+        monkeypatch.setenv("LHW_ROLLOUT_SPLIT", split)
+        ppo = PPO(_env_fn(n=2048, seed=4), _args(num_procs=2048, steps_per_env=12), seed=4)
+        assert len(ppo.workers[0]._parts(2048)) == (2 if split == "1" else 1)
+        b1 = ppo.sample_parallel_with_workers()
+        b2 = ppo.sample_parallel_with_workers()
+        outs[name] = [t.clone() for b in (b1, b2) for t in (b.states, b.actions, b.rewards, b.values, b.returns, b.dones)]
+        ppo.env.close()
+    for a, b in zip(outs["graph"], outs["eager"]):
+        assert torch.equal(a, b)
+    # first call, first few steps: the single-stream rollout sees the same environments (same seeds, same noise stream)
+    st_g, st_s = outs["graph"][0].view(2048, 12, -1), outs["single"][0].view(2048, 12, -1)
+    assert (st_g[:, :4] - st_s[:, :4]).abs().max().item() < 1e-3
+    assert torch.equal(outs["graph"][5].view(2048, 12)[:, :4], outs["single"][5].view(2048, 12)[:, :4])
+
+
 def test_graph_replayed_update_matches_the_eager_update(monkeypatch):
     """PPO._update_step: after three eager warm-up updates the optimiser step (losses, backward, clip + Adam with the step
     counter in device memory) is captured once and replayed; same seed, same data => the same weights as the eager loop."""
