@@ -133,7 +133,12 @@ __global__ void __launch_bounds__(32, sizeof(real) == 4 ? (TK ? 24 : 28) : (TK ?
 // the shipped carving: W warps per block (one env each), a __syncthreads() per substep so the warps of an SM share
 // instruction-cache fills (profiles/: stall_no_inst 24 % -> 3 %); W from LHW_WARPS_PER_BLOCK or the measured defaults below
 template <class real, int NJ, int TK>
-__global__ void __launch_bounds__(sizeof(real) == 8 ? 512 : 896, 1)
+// LHW_X_REGCAP (candidate, tools/ab_variants.py): the register budget of the fp64 lock-step kernel as "threads per SM" — 512 = 127
+// registers (16 warps per SM, the shipped kernel), 576 = 112 (18 warps), 640 = 96 (20 warps)
+#ifndef LHW_X_REGCAP
+#define LHW_X_REGCAP 512
+#endif
+__global__ void __launch_bounds__(sizeof(real) == 8 ? LHW_X_REGCAP : 896, 1)
     step_kernel_mw(real* __restrict__ state_r, int32_t* __restrict__ state_i, int n_envs, uint32_t seed, uint32_t first_id,
                    const real* __restrict__ actions, int max_traj_len, int autoreset, real* __restrict__ obs,
                    real* __restrict__ term_obs, real* __restrict__ reward, real* __restrict__ rew_terms,
@@ -226,7 +231,7 @@ template <class real, int NJ, int TK> int prepare_variant(lhw_sim* s) {
   int maxsmem = 0;
   CUDA_OK(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
   // lock-step blocks: as many warps as the launch bound and the shared memory of one SM allow, two blocks per SM
-  const int cap_threads = (sizeof(real) == 8 ? 512 : 896) / 32;
+  const int cap_threads = (sizeof(real) == 8 ? LHW_X_REGCAP : 896) / 32;
   if (s->warps_per_block > cap_threads) s->warps_per_block = cap_threads;
   while (s->warps_per_block > 1 && s->work_bytes * s->warps_per_block > (size_t)maxsmem) s->warps_per_block--;
   if (s->warps_per_block < 1) s->warps_per_block = 1;
