@@ -279,7 +279,7 @@ template <class real, int NJ, int TK> struct alignas(16) Arrow {
 // persistent state (mirrors the HBM record, same order); variants with per-env model parameters append them
 template <class real, int NJ, int TK> struct Persist {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ;
-  real qpos[NQ], qvel[NV], qacc_warm[NV], act_len[NU], act_vel[NU], prev_pred[NU], prev_action[NU], prev_torque[NU];
+  real qpos[NQ], qvel[NV], qacc[NV], act_len[NU], act_vel[NU], prev_pred[NU], prev_action[NU], prev_torque[NU];
   real mode_ref[3], ep_rew;
 };
 template <class real, int NJ, int TK> struct PersistRand : Persist<real, NJ, TK> {
@@ -308,7 +308,7 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   int phase, mode, traj_len, ep_len, have_prev, status;
   uint32_t rng_ctr, env_id;
   // ---- control-step scratch
-  real target[NU], ctrl[NU], act_force[NU], kp_step[NU], kd_step[NU];
+  real target[NU], ctrl[NU], kp_step[NU], kd_step[NU];   // ctrl doubles as mjData.actuator_force (gear 1): the last substep's torques
   // ---- kinematics / dynamics
   real sc[NU][2];
   real o[3], xr[NL][3], xmat[NL][9];
@@ -316,7 +316,8 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   real V[NL][6];
   Arrow<real, NJ, TK> M, H;
   real hdinv[NV];
-  real qfs[NV], qacc[NV], Ma[NV], grad[NV], sdir[NV], Ms[NV], vec[NV];
+  real qfs[NV], Ma[NV], grad[NV], sdir[NV], Ms[NV];   // qacc lives in the persistent block (it IS the next substep's warm start);
+                                                     // the right-hand side of the implicit-damping solve reuses Ms
   // ---- contacts (slot = foot*4 + k), expressed through the foot's spatial motion: J_contact = P(p) S_foot
   int ncon[2];
   // stepping stones: cos/sin of the slab yaws, per-corner multiplicity, crossing-slot distances
@@ -325,7 +326,7 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   // riser contacts (slab side faces): horizontal outward normal per slot, (0, 0) = the slot's normal is +z
   real cn[NST ? NCON : 1][2];
   real site[2][3], rquat[4], goal[8];   // lagged site_xpos / root xquat ; _goal_steps_{x,y,z,theta}
-  real cpos[NCON][Cfg<NJ, TK>::SLABS ? 5 : 3], cD[NCON], cKid[NCON];   // SLABS: (px, py, pz, 1, 0), see pmap_sel
+  real cpos[NCON][5], cD[NCON], cKid[NCON];   // (px, py, pz, 1, 0): the entries of the contact point map are +- these, see pmap_sel
   real ejar[NEDGE];   // edge residuals J a - aref (P8 leaves aref here, P9 turns it into the residual in place)
   int lside[NU];
   real lD[NU], ljar[NU];
@@ -335,7 +336,7 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   union {
     struct {
       real inert[NL][10], comp[NL][10];
-      real A[NL][6], F[NL][6];
+      real A[NL][6];   // bias accelerations (P4-P5); P6 turns each link's row into its force in place (`F`)
       real ccd[2 * NPTS];   // signed distance of each candidate point (box corner / sphere), > 0: not a candidate
       int cslot[NCON];
       real cwp[NST ? 16 : 1][3];   // SLABS: foot-box corners relative to o
@@ -344,9 +345,9 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
     };
     struct {
       real T[2][NA][6], Af[2][6][6], Ff[2][6], ya[2][6], ys[2][6];
-      // contact-frame point map: rows = unit wrenches of (n, t1, t2) applied at the contact.  The slab variants (16 slots)
-      // rebuild the entries from cpos instead (pmap3): dropping the table is what lets 14 fp64 environments share an SM
-      real Pm[Cfg<NJ, TK>::SLABS ? 1 : NCON][3][6];
+      // (the contact-frame point map — rows = unit wrenches of (n, t1, t2) applied at the contact — is not stored: its entries
+      // are +- components of cpos, selected per column by pmap_sel; the 144-word table it replaced cost more shared memory
+      // than the selects cost instructions)
       real cF[NCON][3], cW[NCON][Cfg<NJ, TK>::SLABS ? 6 : 5];   // SLABS: + the (t1, t2) entry, non-zero for riser contacts only
       real ejv[NEDGE], ljv[NU], fjv[NFL];
     };
@@ -951,7 +952,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       });
     }
   }
-  // ---------------- P6 link forces f_i = I A + V x* (I V) (lane = link) ; foot-box corner candidates (lanes 16..31)
+  // ---------------- P6 link forces f_i = I A + V x* (I V) (lane = link; written over A_i, which nothing reads afterwards) ; foot-box corner candidates (lanes 16..31)
   LHW_LANES(l) {
     if (l < NL) {
       real IA[6], IV[6], t1[3], t2[3], t3[3];
@@ -963,8 +964,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       cross(V, IV + 3, t3);      // w x f
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        w.F[l][c] = IA[c] + t1[c] + t2[c];
-        w.F[l][3 + c] = IA[3 + c] + t3[c];
+        w.A[l][c] = IA[c] + t1[c] + t2[c];
+        w.A[l][3 + c] = IA[3 + c] + t3[c];
       }
     } else if (Cfg<NJ, TK>::SPHERES && l >= 16 && l < 16 + 2 * NPTS) {
       // mjc_PlaneCapsule = two mjc_PlaneSphere: dist = centre height - radius, contact iff dist < 0
@@ -1044,8 +1045,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
 #pragma unroll
       for (int k = NJ - 1; k >= 0; k--) {
         const int i = 1 + ch * NJ + k;
-        acc += w.F[i][e];
-        w.F[i][e] = acc;
+        acc += w.A[i][e];
+        w.A[i][e] = acc;
       }
     } else if (l < 14) {
       const int f = l - 12;
@@ -1170,7 +1171,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           cd = w.xcd[l];   // riser / crossing slot: position, distance and normal already written by P7 / P7x
           w.xcd[l] = (!Cfg<NJ, TK>::STEP || m.slab_contacts_are_floor) ? (real)1 : (real)0;
         }
-        w.cpos[l][3] = 1; w.cpos[l][4] = 0;
       } else {
       const int i = w.cslot[l];
       cd = w.ccd[f * NPTS + i];
@@ -1188,6 +1188,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       // contact point: half way through the penetration (box corner), resp. sphere centre - n (r + dist/2)
       w.cpos[l][2] = corner[2] + w.xr[lk][2] - (Cfg<NJ, TK>::SPHERES ? m.foot_radius[f] + (real)0.5 * cd : (real)0.5 * cd);
       }
+      w.cpos[l][3] = 1; w.cpos[l][4] = 0;
       const real imp = impedance(m.solimp, cd);
       const real Rn = m_max((real)1e-15, (1 - imp) / imp * (m.foot_invw[f] * (1 + m.mu * m.mu)));
       w.cD[l] = mult / (2 * m.mu_reg * m.mu_reg * Rn);
@@ -1213,10 +1214,10 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       real Ft[6];
       if (lk == 0) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) Ft[c] = w.F[0][c] + w.F[1][c] + w.F[1 + NJ][c];
+        for (int c = 0; c < 6; c++) Ft[c] = w.A[0][c] + w.A[1][c] + w.A[1 + NJ][c];
       } else {
 #pragma unroll
-        for (int c = 0; c < 6; c++) Ft[c] = w.F[lk][c];
+        for (int c = 0; c < 6; c++) Ft[c] = w.A[lk][c];
       }
       real q;
       if constexpr (PERENV) {
@@ -1241,7 +1242,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       }
       if (l >= 6) q += w.ctrl[l - 6];
       w.qfs[l] = q;
-      w.qacc[l] = w.qacc_warm[l];
     } else if (l < NV + NU) {
       const int u = l - NV, d = 6 + u;
       const real q = w.qpos[7 + u];
@@ -1268,18 +1268,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
   }
   LHW_SYNC();
   LHW_BLOCK_SYNC(block_sync & 2);  // optional second rendez-vous of the block's warps, before the solver
-  // ---------------- P9 Newton start: contact point maps Pm, then Ma = M a, ya = S_foot a and the row residuals
-  if constexpr (!Cfg<NJ, TK>::SLABS)
-  LHW_LANES(l) {
-    if (l < NCON && l - (l / CPF) * CPF < w.ncon[l / CPF]) {
-      // rows of P: spatial wrench [p x e ; e] of a unit force along e = n (+z), t1 (+y), t2 (-x) applied at p
-      const real px = w.cpos[l][0], py = w.cpos[l][1], pz = w.cpos[l][2];
-      real* P = &w.Pm[l][0][0];
-      P[0] = py;  P[1] = -px; P[2] = 0;   P[3] = 0;  P[4] = 0; P[5] = 1;
-      P[6] = -pz; P[7] = 0;   P[8] = px;  P[9] = 0;  P[10] = 1; P[11] = 0;
-      P[12] = 0;  P[13] = -pz; P[14] = py; P[15] = -1; P[16] = 0; P[17] = 0;
-    }
-  }
+  // ---------------- P9 Newton start: Ma = M a, ya = S_foot a and the row residuals
   // (the reference accelerations sit in ejar / ljar / fjar since P8: subtracted in place, every lane its own entries)
   constraint_images<real, NJ, TK>(w, m, w.qacc, w.Ma, w.ya, w.ejar, w.ljar, w.fjar, w.ejar, w.ljar, w.fjar, (real)1);
 
@@ -1341,13 +1330,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         pmap_sel(a, ia, sa);
         for (int k = 0; k < w.ncon[f]; k++) {
           const real* cf = w.cF[f * CPF + k];
-          if constexpr (Cfg<NJ, TK>::SLABS) {
-            const real* cp = w.cpos[f * CPF + k];
-            acc += sflip(cp[ia[0]], sa[0]) * cf[0] + sflip(cp[ia[1]], sa[1]) * cf[1] + sflip(cp[ia[2]], sa[2]) * cf[2];
-          } else {
-            const real* P = &w.Pm[f * CPF + k][0][0];
-            acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
-          }
+          const real* cp = w.cpos[f * CPF + k];
+          acc += sflip(cp[ia[0]], sa[0]) * cf[0] + sflip(cp[ia[1]], sa[1]) * cf[1] + sflip(cp[ia[2]], sa[2]) * cf[2];
         }
         w.Ff[f][a] = acc;
       }
@@ -1387,15 +1371,9 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         for (int k = 0; k < w.ncon[f]; k++) {
           const int s = f * CPF + k;
           const real* W = w.cW[s];
-          real a0, a1, a2, b0, b1, b2;
-          if constexpr (Cfg<NJ, TK>::SLABS) {
-            const real* cp = w.cpos[s];
-            a0 = sflip(cp[ia[0]], sa[0]); a1 = sflip(cp[ia[1]], sa[1]); a2 = sflip(cp[ia[2]], sa[2]);
-            b0 = sflip(cp[ib[0]], sb[0]); b1 = sflip(cp[ib[1]], sb[1]); b2 = sflip(cp[ib[2]], sb[2]);
-          } else {
-            const real* P = &w.Pm[s][0][0];
-            a0 = P[a]; a1 = P[6 + a]; a2 = P[12 + a]; b0 = P[b]; b1 = P[6 + b]; b2 = P[12 + b];
-          }
+          const real* cp = w.cpos[s];
+          const real a0 = sflip(cp[ia[0]], sa[0]), a1 = sflip(cp[ia[1]], sa[1]), a2 = sflip(cp[ia[2]], sa[2]);
+          const real b0 = sflip(cp[ib[0]], sb[0]), b1 = sflip(cp[ib[1]], sb[1]), b2 = sflip(cp[ib[2]], sb[2]);
           if constexpr (Cfg<NJ, TK>::SLABS)
             acc += a0 * (W[0] * b0 + W[1] * b1 + W[2] * b2) + a1 * (W[1] * b0 + W[3] * b1 + W[5] * b2) + a2 * (W[2] * b0 + W[5] * b1 + W[4] * b2);
           else
@@ -1521,7 +1499,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     if (l < NU) {
       w.act_len[l] = w.qpos[7 + l];
       w.act_vel[l] = w.qvel[6 + l];
-      w.act_force[l] = w.ctrl[l];
     }
     if (last) {
       if (l >= 12 && l < 15) { w.root_vlin[l - 12] = w.qvel[l - 12]; w.qacc_lag[l - 12] = w.qacc[l - 12]; }
@@ -1565,7 +1542,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       }
     }
     // rhs of the implicit-damping solve: qfrc_smooth + J' f = M a - grad
-    if (l < NV) w.vec[l] = w.Ma[l] - w.grad[l];
+    if (l < NV) w.Ms[l] = w.Ma[l] - w.grad[l];
     if (last) {
       // self-collision capsules: end points relative to o
       // lanes 22..31 take capsules 0..9 (the dof lanes are busy above), lanes 0..5 the rest
@@ -1615,18 +1592,17 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       }
     }
     LHW_SYNC();
-    arrow_factor_solve<real, NJ, TK>(w, w.vec);
+    arrow_factor_solve<real, NJ, TK>(w, w.Ms);
   } else {
     LHW_LANES(l) {
-      if (l < NV) w.vec[l] = w.qacc[l];
+      if (l < NV) w.Ms[l] = w.qacc[l];
     }
     LHW_SYNC();
   }
   LHW_LANES(l) {
     if (l < NV) {
-      const real a = w.vec[l];
+      const real a = w.Ms[l];
       if (!(m_abs(a) < (real)1e10)) w.status |= 1;
-      w.qacc_warm[l] = w.qacc[l];
       w.qvel[l] += m.h * a;
     }
   }
@@ -1748,7 +1724,7 @@ template <class real, int NJ, int TK> LHW_DEV void env_obs(Work<real, NJ, TK>& w
     } else if (l >= 8 && l < 8 + NU) {
       w.obs[5 + l - 8] = w.act_len[l - 8];
       w.obs[5 + NU + l - 8] = w.act_vel[l - 8];
-      if constexpr (Cfg<NJ, TK>::STAND) w.obs[5 + 2 * NU + l - 8] = w.act_force[l - 8];   // motor torques (h1_base.py:97)
+      if constexpr (Cfg<NJ, TK>::STAND) w.obs[5 + 2 * NU + l - 8] = w.ctrl[l - 8];   // motor torques (h1_base.py:97)
     }
   }
   LHW_SYNC();
@@ -1967,7 +1943,7 @@ template <class real, int NJ, int TK> LHW_DEV void env_reset(Work<real, NJ, TK>&
   LHW_LANES(l) {
     if (l == 0) w.rng_ctr++;
     if (l < NQ) w.qpos[l] = m.nominal[l];
-    if (l < NV) { w.qvel[l] = 0; w.qacc_warm[l] = 0; }
+    if (l < NV) { w.qvel[l] = 0; w.qacc[l] = 0; }
     if (l < NU) { w.ctrl[l] = 0; w.prev_pred[l] = 0; }
     if constexpr (Cfg<NJ, TK>::PERENV) {
       if (l >= 20) (&w.xfrc[0][0])[l - 20] = 0;   // mj_resetData clears xfrc_applied
@@ -2200,7 +2176,7 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
           r = (real)0.1 * m_exp(-40 * (m.head[0] * m.head[0] + m.head[1] * m.head[1]));  // torso welded to the pelvis
         } else if (l == 4) {
           real te = 0;
-          for (int u = 0; u < NU; u++) te += w.act_force[u] * w.act_force[u];
+          for (int u = 0; u < NU; u++) te += w.ctrl[u] * w.ctrl[u];
           r = (real)0.1 * m_exp((real)-5e-5 * te);
         } else if (l == 5) {
           real pe = 0;
@@ -2255,7 +2231,7 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
         r = (real)0.05 * m_exp(-m_sqrt(pe));
       } else if (l == 8) {
         real te = 0;
-        for (int u = 0; u < NU; u++) te += m_abs(w.prev_torque[u] - w.act_force[u]);
+        for (int u = 0; u < NU; u++) te += m_abs(w.prev_torque[u] - w.ctrl[u]);
         r = (real)0.025 * m_exp((real)-0.25 * (te / NU));
       } else {
         real ae = 0;
@@ -2279,7 +2255,7 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
   LHW_LANES(l) {
     if (l < NU) {
       w.prev_action[l] = w.target[l];
-      w.prev_torque[l] = w.act_force[l];
+      w.prev_torque[l] = w.ctrl[l];
       w.prev_pred[l] = action[l];
     }
     if (l == 12) { w.traj_len += 1; w.ep_len += 1; w.ep_rew += total; }
