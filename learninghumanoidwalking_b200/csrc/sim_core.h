@@ -310,10 +310,9 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   // ---- control-step scratch
   real target[NU], ctrl[NU], kp_step[NU], kd_step[NU];   // ctrl doubles as mjData.actuator_force (gear 1): the last substep's torques
   // ---- kinematics / dynamics
-  real sc[NU][2];
   real o[3], xr[NL][3], xmat[NL][9];
   real S[NV][6];
-  real V[NL][6];
+  real Vf[2][6];   // spatial velocity of the two foot links (edge reference accelerations, lagged foot velocity)
   Arrow<real, NJ, TK> M, H;
   real hdinv[NV];
   real qfs[NV], Ma[NV], grad[NV], sdir[NV], Ms[NV];   // qacc lives in the persistent block (it IS the next substep's warm start);
@@ -335,7 +334,9 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   // reader is qfrc_smooth), the Newton quantities from P9 to P11
   union {
     struct {
-      real inert[NL][10], comp[NL][10];
+      real sc[NU][2];   // sin / cos of the joint angles: P1 only
+      real inert[NL][10];   // link spatial inertias about o (P2-P6), then the composite ones in place (after the link forces)
+      real V[NL][6];        // link spatial velocities (P3-P6)
       real A[NL][6];   // bias accelerations (P4-P5); P6 turns each link's row into its force in place (`F`)
       real ccd[2 * NPTS];   // signed distance of each candidate point (box corner / sphere), > 0: not a candidate
       int cslot[NCON];
@@ -839,19 +840,11 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
   }
   LHW_SYNC();
-  // ---------------- P3 composite inertias (suffix sums, lane = chain*10 + component) ; link velocities V
-  // (prefix sums, lanes 20..31 = chain*6 + component) ; velocity-product terms need V first -> next phase
+  // ---------------- P3 link velocities V (prefix sums, lanes 20..31 = chain*6 + component) ; velocity-product terms need V
+  // first -> next phase.  (The composite inertias are formed later, in place of the link inertias, once the link forces of
+  // P6 have used them: one 130-word table instead of two.)
   LHW_LANES(l) {
-    if (l < 20) {
-      const int ch = l / 10, e = l - ch * 10;
-      real acc = 0;
-#pragma unroll
-      for (int k = NJ - 1; k >= 0; k--) {
-        const int i = 1 + ch * NJ + k;
-        acc += w.inert[i][e];
-        w.comp[i][e] = acc;
-      }
-    } else {
+    if (l >= 20) {
       const int ch = (l - 20) / 6, e = (l - 20) - ch * 6;
       real acc = e < 3 ? w.xmat[0][3 * e] * w.qvel[3] + w.xmat[0][3 * e + 1] * w.qvel[4] + w.xmat[0][3 * e + 2] * w.qvel[5]
                        : w.qvel[e - 3];
@@ -862,13 +855,13 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         acc += w.S[5 + i][e] * w.qvel[5 + i];
         w.V[i][e] = acc;
       }
+      w.Vf[ch][e] = acc;   // the chain's last link is the foot
     }
   }
   LHW_SYNC();
-  // ---------------- P4 root composite (lanes 0..9) ; per-joint velocity-product acceleration (V x S) qd (lanes 10..)
+  // ---------------- P4 per-joint velocity-product acceleration (V x S) qd (lanes 10..)
   LHW_LANES(l) {
-    if (l < 10) w.comp[0][l] = w.inert[0][l] + w.comp[1][l] + w.comp[1 + NJ][l];
-    else if (l < 10 + NU) {
+    if (l >= 10 && l < 10 + NU) {
       const int i = 1 + (l - 10);
       const real* Vi = w.V[i];
       const real* S = w.S[5 + i];
@@ -892,31 +885,9 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
   }
   LHW_SYNC();
-  // ---------------- P5 mass matrix (CRBA), lane = dof ; bias accelerations A (prefix sums, lanes 20..31)
+  // ---------------- P5 bias accelerations A (prefix sums, lanes 20..31)
   LHW_LANES(l) {
-    if (l < NV) {
-      real f[6];
-      inert_mul(w.comp[dof_link<NJ>(l)], w.S[l], f);
-      if (l < 6) {
-#pragma unroll
-        for (int j = 0; j < 6; j++)
-          if (j <= l) {
-            const real v = dot6(w.S[j], f);
-            w.M.r[l][j] = v; w.M.r[j][l] = v;
-          }
-      } else {
-        const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ;
-#pragma unroll
-        for (int kk = 0; kk < NJ; kk++)
-          if (kk <= k) {
-            real v = dot6(w.S[6 + ch * NJ + kk], f);
-            if (kk == k) v += LHW_GLD(m, armature[l]);
-            w.M.c[ch][k][kk] = v; w.M.c[ch][kk][k] = v;
-          }
-#pragma unroll
-        for (int j = 0; j < 6; j++) w.M.x[ch][j][k] = dot6(w.S[j], f);
-      }
-    } else if (l >= 20) {
+    if (l >= 20) {
       const int ch = (l - 20) / 6, e = (l - 20) - ch * 6;
       real acc = w.A[0][e];
 #pragma unroll
@@ -1036,8 +1007,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
   }
   LHW_SYNC();
-  // ---------------- P7 subtree forces (suffix sums, lane = chain*6 + comp) ; contact slots: the first (at most) 4
-  // candidate corners of each foot in corner-index order, as mjc_PlaneBox returns them (lanes 12, 13)
+  // ---------------- P7 subtree forces (suffix sums, lanes 0..11 = chain*6 + comp) ; composite inertias IN PLACE of the link
+  // inertias (suffix sums, lanes 12..31 = chain*10 + component): the link forces above were their last reader
   LHW_LANES(l) {
     if (l < 12) {
       const int ch = l / 6, e = l - ch * 6;
@@ -1048,7 +1019,23 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         acc += w.A[i][e];
         w.A[i][e] = acc;
       }
-    } else if (l < 14) {
+    } else {
+      const int ch = (l - 12) / 10, e = (l - 12) - ch * 10;
+      real acc = 0;
+#pragma unroll
+      for (int k = NJ - 1; k >= 0; k--) {
+        const int i = 1 + ch * NJ + k;
+        acc += w.inert[i][e];
+        w.inert[i][e] = acc;
+      }
+    }
+  }
+  LHW_SYNC();
+  // ---------------- P7a root composite (lanes 0..9) ; contact slots: the first (at most) 4 candidate corners of each foot in
+  // corner-index order, as mjc_PlaneBox returns them (lanes 12, 13)
+  LHW_LANES(l) {
+    if (l < 10) w.inert[0][l] = w.inert[0][l] + w.inert[1][l] + w.inert[1 + NJ][l];
+    else if (l >= 12 && l < 14) {
       const int f = l - 12;
       int cnt = 0;
 #pragma unroll
@@ -1077,6 +1064,33 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         w.nside[f] = ns;
       }
       w.ncon[f] = cnt;
+    }
+  }
+  LHW_SYNC();
+  // ---------------- P7c mass matrix (CRBA), lane = dof
+  LHW_LANES(l) {
+    if (l < NV) {
+      real f[6];
+      inert_mul(w.inert[dof_link<NJ>(l)], w.S[l], f);   // composite inertia of the dof's link
+      if (l < 6) {
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+          if (j <= l) {
+            const real v = dot6(w.S[j], f);
+            w.M.r[l][j] = v; w.M.r[j][l] = v;
+          }
+      } else {
+        const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ;
+#pragma unroll
+        for (int kk = 0; kk < NJ; kk++)
+          if (kk <= k) {
+            real v = dot6(w.S[6 + ch * NJ + kk], f);
+            if (kk == k) v += LHW_GLD(m, armature[l]);
+            w.M.c[ch][k][kk] = v; w.M.c[ch][kk][k] = v;
+          }
+#pragma unroll
+        for (int j = 0; j < 6; j++) w.M.x[ch][j][k] = dot6(w.S[j], f);
+      }
     }
   }
   LHW_SYNC();
@@ -1203,7 +1217,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       const int s = ed >> 2, e = ed & 3, f = s / CPF;
       if (s - f * CPF < w.ncon[f]) {
         real u[3];
-        contact_u(w.cpos[s], w.V[(f + 1) * NJ], u);
+        contact_u(w.cpos[s], w.Vf[f], u);
         if constexpr (Cfg<NJ, TK>::SLABS) riser_u(w.cn[s], u);
         const real vel = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)];
         w.ejar[ed] = -m.Bc * vel - w.cKid[s];
@@ -1505,10 +1519,10 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       if (l >= 16 && l < 18) {
         const int f = l - 16, lk = (f + 1) * NJ;
         real t[3];
-        cross(w.V[lk], w.xr[lk], t);  // velocity of the link origin: v_o + w x r
+        cross(w.Vf[f], w.xr[lk], t);  // velocity of the link origin: v_o + w x r
         real g = 0;
 #pragma unroll
-        for (int c = 0; c < 3; c++) w.foot_vel[f][c] = w.V[lk][3 + c] + t[c];
+        for (int c = 0; c < 3; c++) w.foot_vel[f][c] = w.Vf[f][3 + c] + t[c];
         if constexpr (Cfg<NJ, TK>::STEP) {
           real st[3];
           mv3(w.xmat[lk], m.foot_site[f], st);
