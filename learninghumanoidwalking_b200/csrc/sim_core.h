@@ -324,7 +324,8 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   int ncorner[2], nside[2];
   // riser contacts (slab side faces): horizontal outward normal per slot, (0, 0) = the slot's normal is +z
   real cn[NST ? NCON : 1][2];
-  real site[2][3], rquat[4], goal[8];   // lagged site_xpos / root xquat ; _goal_steps_{x,y,z,theta}
+  // SteppingTask only (one word each elsewhere): lagged site_xpos / root xquat ; _goal_steps_{x,y,z,theta}
+  real site[Cfg<NJ, TK>::STEP ? 2 : 1][3], rquat[Cfg<NJ, TK>::STEP ? 4 : 1], goal[Cfg<NJ, TK>::STEP ? 8 : 1];
   real cpos[NCON][5], cD[NCON], cKid[NCON];   // (px, py, pz, 1, 0): the entries of the contact point map are +- these, see pmap_sel
   real ejar[NEDGE];   // edge residuals J a - aref (P8 leaves aref here, P9 turns it into the residual in place)
   int lside[NU];
