@@ -279,7 +279,7 @@ template <class real, int NJ, int TK> struct alignas(16) Arrow {
 // persistent state (mirrors the HBM record, same order); variants with per-env model parameters append them
 template <class real, int NJ, int TK> struct Persist {
   static constexpr int NL = 1 + 2 * NJ, NV = 6 + 2 * NJ, NQ = NV + 1, NU = 2 * NJ;
-  real qpos[NQ], qvel[NV], qacc[NV], act_len[NU], act_vel[NU], prev_pred[NU], prev_action[NU], prev_torque[NU];
+  real qpos[NQ], qvel[NV], qacc_warm[NV], act_len[NU], act_vel[NU], prev_pred[NU], prev_action[NU], prev_torque[NU];
   real mode_ref[3], ep_rew;
 };
 template <class real, int NJ, int TK> struct PersistRand : Persist<real, NJ, TK> {
@@ -308,15 +308,15 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   int phase, mode, traj_len, ep_len, have_prev, status;
   uint32_t rng_ctr, env_id;
   // ---- control-step scratch
-  real target[NU], ctrl[NU], kp_step[NU], kd_step[NU];   // ctrl doubles as mjData.actuator_force (gear 1): the last substep's torques
+  real target[NU], ctrl[NU], act_force[NU], kp_step[NU], kd_step[NU];
   // ---- kinematics / dynamics
+  real sc[NU][2];
   real o[3], xr[NL][3], xmat[NL][9];
   real S[NV][6];
-  real Vf[2][6];   // spatial velocity of the two foot links (edge reference accelerations, lagged foot velocity)
+  real V[NL][6];
   Arrow<real, NJ, TK> M, H;
   real hdinv[NV];
-  real qfs[NV], Ma[NV], grad[NV], sdir[NV], Ms[NV];   // qacc lives in the persistent block (it IS the next substep's warm start);
-                                                     // the right-hand side of the implicit-damping solve reuses Ms
+  real qfs[NV], qacc[NV], Ma[NV], grad[NV], sdir[NV], Ms[NV], vec[NV];
   // ---- contacts (slot = foot*4 + k), expressed through the foot's spatial motion: J_contact = P(p) S_foot
   int ncon[2];
   // stepping stones: cos/sin of the slab yaws, per-corner multiplicity, crossing-slot distances
@@ -324,9 +324,8 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   int ncorner[2], nside[2];
   // riser contacts (slab side faces): horizontal outward normal per slot, (0, 0) = the slot's normal is +z
   real cn[NST ? NCON : 1][2];
-  // SteppingTask only (one word each elsewhere): lagged site_xpos / root xquat ; _goal_steps_{x,y,z,theta}
-  real site[Cfg<NJ, TK>::STEP ? 2 : 1][3], rquat[Cfg<NJ, TK>::STEP ? 4 : 1], goal[Cfg<NJ, TK>::STEP ? 8 : 1];
-  real cpos[NCON][5], cD[NCON], cKid[NCON];   // (px, py, pz, 1, 0): the entries of the contact point map are +- these, see pmap_sel
+  real site[2][3], rquat[4], goal[8];   // lagged site_xpos / root xquat ; _goal_steps_{x,y,z,theta}
+  real cpos[NCON][Cfg<NJ, TK>::SLABS ? 5 : 3], cD[NCON], cKid[NCON];   // SLABS: (px, py, pz, 1, 0), see pmap_sel
   real ejar[NEDGE];   // edge residuals J a - aref (P8 leaves aref here, P9 turns it into the residual in place)
   int lside[NU];
   real lD[NU], ljar[NU];
@@ -335,10 +334,8 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
   // reader is qfrc_smooth), the Newton quantities from P9 to P11
   union {
     struct {
-      real sc[NU][2];   // sin / cos of the joint angles: P1 only
-      real inert[NL][10];   // link spatial inertias about o (P2-P6), then the composite ones in place (after the link forces)
-      real V[NL][6];        // link spatial velocities (P3-P6)
-      real A[NL][6];   // bias accelerations (P4-P5); P6 turns each link's row into its force in place (`F`)
+      real inert[NL][10], comp[NL][10];
+      real A[NL][6], F[NL][6];
       real ccd[2 * NPTS];   // signed distance of each candidate point (box corner / sphere), > 0: not a candidate
       int cslot[NCON];
       real cwp[NST ? 16 : 1][3];   // SLABS: foot-box corners relative to o
@@ -347,9 +344,9 @@ struct alignas(16) Work : Select<Cfg<NJ, TK>::PERENV, PersistRand<real, NJ, TK>,
     };
     struct {
       real T[2][NA][6], Af[2][6][6], Ff[2][6], ya[2][6], ys[2][6];
-      // (the contact-frame point map — rows = unit wrenches of (n, t1, t2) applied at the contact — is not stored: its entries
-      // are +- components of cpos, selected per column by pmap_sel; the 144-word table it replaced cost more shared memory
-      // than the selects cost instructions)
+      // contact-frame point map: rows = unit wrenches of (n, t1, t2) applied at the contact.  The slab variants (16 slots)
+      // rebuild the entries from cpos instead (pmap3): dropping the table is what lets 14 fp64 environments share an SM
+      real Pm[Cfg<NJ, TK>::SLABS ? 1 : NCON][3][6];
       real cF[NCON][3], cW[NCON][Cfg<NJ, TK>::SLABS ? 6 : 5];   // SLABS: + the (t1, t2) entry, non-zero for riser contacts only
       real ejv[NEDGE], ljv[NU], fjv[NFL];
     };
@@ -841,11 +838,19 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
   }
   LHW_SYNC();
-  // ---------------- P3 link velocities V (prefix sums, lanes 20..31 = chain*6 + component) ; velocity-product terms need V
-  // first -> next phase.  (The composite inertias are formed later, in place of the link inertias, once the link forces of
-  // P6 have used them: one 130-word table instead of two.)
+  // ---------------- P3 composite inertias (suffix sums, lane = chain*10 + component) ; link velocities V
+  // (prefix sums, lanes 20..31 = chain*6 + component) ; velocity-product terms need V first -> next phase
   LHW_LANES(l) {
-    if (l >= 20) {
+    if (l < 20) {
+      const int ch = l / 10, e = l - ch * 10;
+      real acc = 0;
+#pragma unroll
+      for (int k = NJ - 1; k >= 0; k--) {
+        const int i = 1 + ch * NJ + k;
+        acc += w.inert[i][e];
+        w.comp[i][e] = acc;
+      }
+    } else {
       const int ch = (l - 20) / 6, e = (l - 20) - ch * 6;
       real acc = e < 3 ? w.xmat[0][3 * e] * w.qvel[3] + w.xmat[0][3 * e + 1] * w.qvel[4] + w.xmat[0][3 * e + 2] * w.qvel[5]
                        : w.qvel[e - 3];
@@ -856,13 +861,13 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         acc += w.S[5 + i][e] * w.qvel[5 + i];
         w.V[i][e] = acc;
       }
-      w.Vf[ch][e] = acc;   // the chain's last link is the foot
     }
   }
   LHW_SYNC();
-  // ---------------- P4 per-joint velocity-product acceleration (V x S) qd (lanes 10..)
+  // ---------------- P4 root composite (lanes 0..9) ; per-joint velocity-product acceleration (V x S) qd (lanes 10..)
   LHW_LANES(l) {
-    if (l >= 10 && l < 10 + NU) {
+    if (l < 10) w.comp[0][l] = w.inert[0][l] + w.comp[1][l] + w.comp[1 + NJ][l];
+    else if (l < 10 + NU) {
       const int i = 1 + (l - 10);
       const real* Vi = w.V[i];
       const real* S = w.S[5 + i];
@@ -886,9 +891,31 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
   }
   LHW_SYNC();
-  // ---------------- P5 bias accelerations A (prefix sums, lanes 20..31)
+  // ---------------- P5 mass matrix (CRBA), lane = dof ; bias accelerations A (prefix sums, lanes 20..31)
   LHW_LANES(l) {
-    if (l >= 20) {
+    if (l < NV) {
+      real f[6];
+      inert_mul(w.comp[dof_link<NJ>(l)], w.S[l], f);
+      if (l < 6) {
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+          if (j <= l) {
+            const real v = dot6(w.S[j], f);
+            w.M.r[l][j] = v; w.M.r[j][l] = v;
+          }
+      } else {
+        const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ;
+#pragma unroll
+        for (int kk = 0; kk < NJ; kk++)
+          if (kk <= k) {
+            real v = dot6(w.S[6 + ch * NJ + kk], f);
+            if (kk == k) v += LHW_GLD(m, armature[l]);
+            w.M.c[ch][k][kk] = v; w.M.c[ch][kk][k] = v;
+          }
+#pragma unroll
+        for (int j = 0; j < 6; j++) w.M.x[ch][j][k] = dot6(w.S[j], f);
+      }
+    } else if (l >= 20) {
       const int ch = (l - 20) / 6, e = (l - 20) - ch * 6;
       real acc = w.A[0][e];
 #pragma unroll
@@ -924,7 +951,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       });
     }
   }
-  // ---------------- P6 link forces f_i = I A + V x* (I V) (lane = link; written over A_i, which nothing reads afterwards) ; foot-box corner candidates (lanes 16..31)
+  // ---------------- P6 link forces f_i = I A + V x* (I V) (lane = link) ; foot-box corner candidates (lanes 16..31)
   LHW_LANES(l) {
     if (l < NL) {
       real IA[6], IV[6], t1[3], t2[3], t3[3];
@@ -936,8 +963,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       cross(V, IV + 3, t3);      // w x f
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        w.A[l][c] = IA[c] + t1[c] + t2[c];
-        w.A[l][3 + c] = IA[3 + c] + t3[c];
+        w.F[l][c] = IA[c] + t1[c] + t2[c];
+        w.F[l][3 + c] = IA[3 + c] + t3[c];
       }
     } else if (Cfg<NJ, TK>::SPHERES && l >= 16 && l < 16 + 2 * NPTS) {
       // mjc_PlaneCapsule = two mjc_PlaneSphere: dist = centre height - radius, contact iff dist < 0
@@ -1008,8 +1035,8 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     }
   }
   LHW_SYNC();
-  // ---------------- P7 subtree forces (suffix sums, lanes 0..11 = chain*6 + comp) ; composite inertias IN PLACE of the link
-  // inertias (suffix sums, lanes 12..31 = chain*10 + component): the link forces above were their last reader
+  // ---------------- P7 subtree forces (suffix sums, lane = chain*6 + comp) ; contact slots: the first (at most) 4
+  // candidate corners of each foot in corner-index order, as mjc_PlaneBox returns them (lanes 12, 13)
   LHW_LANES(l) {
     if (l < 12) {
       const int ch = l / 6, e = l - ch * 6;
@@ -1017,26 +1044,10 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
 #pragma unroll
       for (int k = NJ - 1; k >= 0; k--) {
         const int i = 1 + ch * NJ + k;
-        acc += w.A[i][e];
-        w.A[i][e] = acc;
+        acc += w.F[i][e];
+        w.F[i][e] = acc;
       }
-    } else {
-      const int ch = (l - 12) / 10, e = (l - 12) - ch * 10;
-      real acc = 0;
-#pragma unroll
-      for (int k = NJ - 1; k >= 0; k--) {
-        const int i = 1 + ch * NJ + k;
-        acc += w.inert[i][e];
-        w.inert[i][e] = acc;
-      }
-    }
-  }
-  LHW_SYNC();
-  // ---------------- P7a root composite (lanes 0..9) ; contact slots: the first (at most) 4 candidate corners of each foot in
-  // corner-index order, as mjc_PlaneBox returns them (lanes 12, 13)
-  LHW_LANES(l) {
-    if (l < 10) w.inert[0][l] = w.inert[0][l] + w.inert[1][l] + w.inert[1 + NJ][l];
-    else if (l >= 12 && l < 14) {
+    } else if (l < 14) {
       const int f = l - 12;
       int cnt = 0;
 #pragma unroll
@@ -1065,33 +1076,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         w.nside[f] = ns;
       }
       w.ncon[f] = cnt;
-    }
-  }
-  LHW_SYNC();
-  // ---------------- P7c mass matrix (CRBA), lane = dof
-  LHW_LANES(l) {
-    if (l < NV) {
-      real f[6];
-      inert_mul(w.inert[dof_link<NJ>(l)], w.S[l], f);   // composite inertia of the dof's link
-      if (l < 6) {
-#pragma unroll
-        for (int j = 0; j < 6; j++)
-          if (j <= l) {
-            const real v = dot6(w.S[j], f);
-            w.M.r[l][j] = v; w.M.r[j][l] = v;
-          }
-      } else {
-        const int ch = (l - 6) / NJ, k = l - 6 - ch * NJ;
-#pragma unroll
-        for (int kk = 0; kk < NJ; kk++)
-          if (kk <= k) {
-            real v = dot6(w.S[6 + ch * NJ + kk], f);
-            if (kk == k) v += LHW_GLD(m, armature[l]);
-            w.M.c[ch][k][kk] = v; w.M.c[ch][kk][k] = v;
-          }
-#pragma unroll
-        for (int j = 0; j < 6; j++) w.M.x[ch][j][k] = dot6(w.S[j], f);
-      }
     }
   }
   LHW_SYNC();
@@ -1186,6 +1170,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
           cd = w.xcd[l];   // riser / crossing slot: position, distance and normal already written by P7 / P7x
           w.xcd[l] = (!Cfg<NJ, TK>::STEP || m.slab_contacts_are_floor) ? (real)1 : (real)0;
         }
+        w.cpos[l][3] = 1; w.cpos[l][4] = 0;
       } else {
       const int i = w.cslot[l];
       cd = w.ccd[f * NPTS + i];
@@ -1203,7 +1188,6 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       // contact point: half way through the penetration (box corner), resp. sphere centre - n (r + dist/2)
       w.cpos[l][2] = corner[2] + w.xr[lk][2] - (Cfg<NJ, TK>::SPHERES ? m.foot_radius[f] + (real)0.5 * cd : (real)0.5 * cd);
       }
-      w.cpos[l][3] = 1; w.cpos[l][4] = 0;
       const real imp = impedance(m.solimp, cd);
       const real Rn = m_max((real)1e-15, (1 - imp) / imp * (m.foot_invw[f] * (1 + m.mu * m.mu)));
       w.cD[l] = mult / (2 * m.mu_reg * m.mu_reg * Rn);
@@ -1218,7 +1202,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       const int s = ed >> 2, e = ed & 3, f = s / CPF;
       if (s - f * CPF < w.ncon[f]) {
         real u[3];
-        contact_u(w.cpos[s], w.Vf[f], u);
+        contact_u(w.cpos[s], w.V[(f + 1) * NJ], u);
         if constexpr (Cfg<NJ, TK>::SLABS) riser_u(w.cn[s], u);
         const real vel = u[0] + ((e & 1) ? -m.mu : m.mu) * u[1 + (e >> 1)];
         w.ejar[ed] = -m.Bc * vel - w.cKid[s];
@@ -1229,10 +1213,10 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       real Ft[6];
       if (lk == 0) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) Ft[c] = w.A[0][c] + w.A[1][c] + w.A[1 + NJ][c];
+        for (int c = 0; c < 6; c++) Ft[c] = w.F[0][c] + w.F[1][c] + w.F[1 + NJ][c];
       } else {
 #pragma unroll
-        for (int c = 0; c < 6; c++) Ft[c] = w.A[lk][c];
+        for (int c = 0; c < 6; c++) Ft[c] = w.F[lk][c];
       }
       real q;
       if constexpr (PERENV) {
@@ -1257,6 +1241,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       }
       if (l >= 6) q += w.ctrl[l - 6];
       w.qfs[l] = q;
+      w.qacc[l] = w.qacc_warm[l];
     } else if (l < NV + NU) {
       const int u = l - NV, d = 6 + u;
       const real q = w.qpos[7 + u];
@@ -1283,7 +1268,18 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
   }
   LHW_SYNC();
   LHW_BLOCK_SYNC(block_sync & 2);  // optional second rendez-vous of the block's warps, before the solver
-  // ---------------- P9 Newton start: Ma = M a, ya = S_foot a and the row residuals
+  // ---------------- P9 Newton start: contact point maps Pm, then Ma = M a, ya = S_foot a and the row residuals
+  if constexpr (!Cfg<NJ, TK>::SLABS)
+  LHW_LANES(l) {
+    if (l < NCON && l - (l / CPF) * CPF < w.ncon[l / CPF]) {
+      // rows of P: spatial wrench [p x e ; e] of a unit force along e = n (+z), t1 (+y), t2 (-x) applied at p
+      const real px = w.cpos[l][0], py = w.cpos[l][1], pz = w.cpos[l][2];
+      real* P = &w.Pm[l][0][0];
+      P[0] = py;  P[1] = -px; P[2] = 0;   P[3] = 0;  P[4] = 0; P[5] = 1;
+      P[6] = -pz; P[7] = 0;   P[8] = px;  P[9] = 0;  P[10] = 1; P[11] = 0;
+      P[12] = 0;  P[13] = -pz; P[14] = py; P[15] = -1; P[16] = 0; P[17] = 0;
+    }
+  }
   // (the reference accelerations sit in ejar / ljar / fjar since P8: subtracted in place, every lane its own entries)
   constraint_images<real, NJ, TK>(w, m, w.qacc, w.Ma, w.ya, w.ejar, w.ljar, w.fjar, w.ejar, w.ljar, w.fjar, (real)1);
 
@@ -1345,8 +1341,13 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         pmap_sel(a, ia, sa);
         for (int k = 0; k < w.ncon[f]; k++) {
           const real* cf = w.cF[f * CPF + k];
-          const real* cp = w.cpos[f * CPF + k];
-          acc += sflip(cp[ia[0]], sa[0]) * cf[0] + sflip(cp[ia[1]], sa[1]) * cf[1] + sflip(cp[ia[2]], sa[2]) * cf[2];
+          if constexpr (Cfg<NJ, TK>::SLABS) {
+            const real* cp = w.cpos[f * CPF + k];
+            acc += sflip(cp[ia[0]], sa[0]) * cf[0] + sflip(cp[ia[1]], sa[1]) * cf[1] + sflip(cp[ia[2]], sa[2]) * cf[2];
+          } else {
+            const real* P = &w.Pm[f * CPF + k][0][0];
+            acc += P[a] * cf[0] + P[6 + a] * cf[1] + P[12 + a] * cf[2];
+          }
         }
         w.Ff[f][a] = acc;
       }
@@ -1386,9 +1387,15 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
         for (int k = 0; k < w.ncon[f]; k++) {
           const int s = f * CPF + k;
           const real* W = w.cW[s];
-          const real* cp = w.cpos[s];
-          const real a0 = sflip(cp[ia[0]], sa[0]), a1 = sflip(cp[ia[1]], sa[1]), a2 = sflip(cp[ia[2]], sa[2]);
-          const real b0 = sflip(cp[ib[0]], sb[0]), b1 = sflip(cp[ib[1]], sb[1]), b2 = sflip(cp[ib[2]], sb[2]);
+          real a0, a1, a2, b0, b1, b2;
+          if constexpr (Cfg<NJ, TK>::SLABS) {
+            const real* cp = w.cpos[s];
+            a0 = sflip(cp[ia[0]], sa[0]); a1 = sflip(cp[ia[1]], sa[1]); a2 = sflip(cp[ia[2]], sa[2]);
+            b0 = sflip(cp[ib[0]], sb[0]); b1 = sflip(cp[ib[1]], sb[1]); b2 = sflip(cp[ib[2]], sb[2]);
+          } else {
+            const real* P = &w.Pm[s][0][0];
+            a0 = P[a]; a1 = P[6 + a]; a2 = P[12 + a]; b0 = P[b]; b1 = P[6 + b]; b2 = P[12 + b];
+          }
           if constexpr (Cfg<NJ, TK>::SLABS)
             acc += a0 * (W[0] * b0 + W[1] * b1 + W[2] * b2) + a1 * (W[1] * b0 + W[3] * b1 + W[5] * b2) + a2 * (W[2] * b0 + W[5] * b1 + W[4] * b2);
           else
@@ -1514,16 +1521,17 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
     if (l < NU) {
       w.act_len[l] = w.qpos[7 + l];
       w.act_vel[l] = w.qvel[6 + l];
+      w.act_force[l] = w.ctrl[l];
     }
     if (last) {
       if (l >= 12 && l < 15) { w.root_vlin[l - 12] = w.qvel[l - 12]; w.qacc_lag[l - 12] = w.qacc[l - 12]; }
       if (l >= 16 && l < 18) {
         const int f = l - 16, lk = (f + 1) * NJ;
         real t[3];
-        cross(w.Vf[f], w.xr[lk], t);  // velocity of the link origin: v_o + w x r
+        cross(w.V[lk], w.xr[lk], t);  // velocity of the link origin: v_o + w x r
         real g = 0;
 #pragma unroll
-        for (int c = 0; c < 3; c++) w.foot_vel[f][c] = w.Vf[f][3 + c] + t[c];
+        for (int c = 0; c < 3; c++) w.foot_vel[f][c] = w.V[lk][3 + c] + t[c];
         if constexpr (Cfg<NJ, TK>::STEP) {
           real st[3];
           mv3(w.xmat[lk], m.foot_site[f], st);
@@ -1557,7 +1565,7 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       }
     }
     // rhs of the implicit-damping solve: qfrc_smooth + J' f = M a - grad
-    if (l < NV) w.Ms[l] = w.Ma[l] - w.grad[l];
+    if (l < NV) w.vec[l] = w.Ma[l] - w.grad[l];
     if (last) {
       // self-collision capsules: end points relative to o
       // lanes 22..31 take capsules 0..9 (the dof lanes are busy above), lanes 0..5 the rest
@@ -1607,17 +1615,18 @@ LHW_DEVNI void substep(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m_arg, 
       }
     }
     LHW_SYNC();
-    arrow_factor_solve<real, NJ, TK>(w, w.Ms);
+    arrow_factor_solve<real, NJ, TK>(w, w.vec);
   } else {
     LHW_LANES(l) {
-      if (l < NV) w.Ms[l] = w.qacc[l];
+      if (l < NV) w.vec[l] = w.qacc[l];
     }
     LHW_SYNC();
   }
   LHW_LANES(l) {
     if (l < NV) {
-      const real a = w.Ms[l];
+      const real a = w.vec[l];
       if (!(m_abs(a) < (real)1e10)) w.status |= 1;
+      w.qacc_warm[l] = w.qacc[l];
       w.qvel[l] += m.h * a;
     }
   }
@@ -1739,7 +1748,7 @@ template <class real, int NJ, int TK> LHW_DEV void env_obs(Work<real, NJ, TK>& w
     } else if (l >= 8 && l < 8 + NU) {
       w.obs[5 + l - 8] = w.act_len[l - 8];
       w.obs[5 + NU + l - 8] = w.act_vel[l - 8];
-      if constexpr (Cfg<NJ, TK>::STAND) w.obs[5 + 2 * NU + l - 8] = w.ctrl[l - 8];   // motor torques (h1_base.py:97)
+      if constexpr (Cfg<NJ, TK>::STAND) w.obs[5 + 2 * NU + l - 8] = w.act_force[l - 8];   // motor torques (h1_base.py:97)
     }
   }
   LHW_SYNC();
@@ -1958,7 +1967,7 @@ template <class real, int NJ, int TK> LHW_DEV void env_reset(Work<real, NJ, TK>&
   LHW_LANES(l) {
     if (l == 0) w.rng_ctr++;
     if (l < NQ) w.qpos[l] = m.nominal[l];
-    if (l < NV) { w.qvel[l] = 0; w.qacc[l] = 0; }
+    if (l < NV) { w.qvel[l] = 0; w.qacc_warm[l] = 0; }
     if (l < NU) { w.ctrl[l] = 0; w.prev_pred[l] = 0; }
     if constexpr (Cfg<NJ, TK>::PERENV) {
       if (l >= 20) (&w.xfrc[0][0])[l - 20] = 0;   // mj_resetData clears xfrc_applied
@@ -2191,7 +2200,7 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
           r = (real)0.1 * m_exp(-40 * (m.head[0] * m.head[0] + m.head[1] * m.head[1]));  // torso welded to the pelvis
         } else if (l == 4) {
           real te = 0;
-          for (int u = 0; u < NU; u++) te += w.ctrl[u] * w.ctrl[u];
+          for (int u = 0; u < NU; u++) te += w.act_force[u] * w.act_force[u];
           r = (real)0.1 * m_exp((real)-5e-5 * te);
         } else if (l == 5) {
           real pe = 0;
@@ -2246,7 +2255,7 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
         r = (real)0.05 * m_exp(-m_sqrt(pe));
       } else if (l == 8) {
         real te = 0;
-        for (int u = 0; u < NU; u++) te += m_abs(w.prev_torque[u] - w.ctrl[u]);
+        for (int u = 0; u < NU; u++) te += m_abs(w.prev_torque[u] - w.act_force[u]);
         r = (real)0.025 * m_exp((real)-0.25 * (te / NU));
       } else {
         real ae = 0;
@@ -2270,7 +2279,7 @@ LHW_DEV void env_step(Work<real, NJ, TK>& w, const Model<real, NJ, TK>& m, const
   LHW_LANES(l) {
     if (l < NU) {
       w.prev_action[l] = w.target[l];
-      w.prev_torque[l] = w.ctrl[l];
+      w.prev_torque[l] = w.act_force[l];
       w.prev_pred[l] = action[l];
     }
     if (l == 12) { w.traj_len += 1; w.ep_len += 1; w.ep_rew += total; }
