@@ -264,15 +264,15 @@ def main():
     def timed_steps(env, regime, warm, steps, seed_off=0, do_flush=True):
         """`steps` control steps of `env` after `warm` untimed ones; returns the per-step CUDA-event times (the event pair
         brackets the step launch only; action generation and the L2 flush sit outside it)."""
-        A = env.act_dim
+        A, nn = env.act_dim, env.num_envs
         g = torch.Generator(device=dev).manual_seed(args.seed * 1000 + rank + seed_off)
-        noise = torch.randn(warm + steps, n, A, device=dev, generator=g, dtype=env.dtype) * SIGMA
+        noise = torch.randn(warm + steps, nn, A, device=dev, generator=g, dtype=env.dtype) * SIGMA
         pol = make_policy(env)[0] if regime == "policy" else None
         obs = env.obs
 
         def action(k):
             if regime == "zero":
-                return torch.zeros(n, A, device=dev, dtype=env.dtype)
+                return torch.zeros(nn, A, device=dev, dtype=env.dtype)
             if regime == "noise":
                 return noise[k]
             with torch.no_grad():
@@ -343,6 +343,13 @@ def main():
         env32.reset()
         ms32, _, _ = timed_steps(env32, args.actions, 30, Kx, do_flush=False)
         extras["fp32_kernel_env_steps_per_s_per_gpu"] = n * Kx / (sum(ms32) * 1e-3)
+        if n < 32768:      # the upper end of the north-star's batch range on this GPU (same fp64 kernel, 13.8 resident waves)
+            big = BatchedHumanoidEnv(32768, model=wl["model"], precision=args.precision, seed=args.seed, first_env_id=rank * 32768,
+                                     device=local_rank)
+            big.reset()
+            msb, _, _ = timed_steps(big, args.actions, 60, 30, do_flush=False)
+            extras["envs_32768_env_steps_per_s_per_gpu"] = 32768 * 30 / (sum(msb) * 1e-3)
+            big.close()
         # how long the fp32 kernel tracks the fp64 kernel (both product code, same seeds, a = 0): control steps until the
         # relative difference of qpos / qvel leaves 1e-4 (the parity bar applies to fp64; this is what fp32 costs)
         e64 = BatchedHumanoidEnv(64, model=wl["model"], precision=64, seed=args.seed + 1, device=local_rank)
@@ -370,7 +377,9 @@ def main():
         f1.record()
         barrier()
         extras["rollout_with_policy_env_steps_per_s_per_gpu"] = n * T / (f0.elapsed_time(f1) * 1e-3)
-        extras["rollout_note"] = f"DeviceRolloutWorker.sample: {T} control steps incl. actor+critic forward, sampling, buffer writes, GAE"
+        extras["rollout_note"] = (f"DeviceRolloutWorker.sample: {T} control steps incl. actor+critic forward, sampling, buffer writes, GAE; batches of "
+                                  ">= 1024 envs advance as two halves on two streams (one half's launch tail overlaps the other half's work), so "
+                                  "this can exceed the isolated step-launch rate of `value`")
     env.close()
     # ---- train_iter: the PPO iteration as the reference defines fps, gradient exchange included, at every N
     train_iter = None

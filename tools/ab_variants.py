@@ -22,15 +22,12 @@ VDIR = os.path.join(PKG, "build", "variants")
 # and are now simply the kernel; SPLITBAR and 4- / 5-warp blocks lost and were deleted.  New candidates go here.
 BUILDS = {
     "base": [],
-    "reg112": ["-DLHW_X_REGCAP=576"],     # 18 warps per SM: 2 x 9- or 3 x 6-warp lock-step blocks (11.3 KB of shared memory per env allow it)
-    "reg96": ["-DLHW_X_REGCAP=640"],      # 20 warps per SM: 2 x 10 or 4 x 5
+    # round 2, second batch (profiles/r02_ab_variants.md): "-DLHW_X_REGCAP=576 | 640 | 896" = 112 / 96 / 72 registers per thread of the
+    # fp64 lock-step kernel (18 / 20 / 28 warps per SM) — measured, not adopted
 }
 # (build, env knobs) timed on (model, precision, n_envs); runs with knobs only time the headline workload
 RUNS = [
     ("base", {}),
-    ("reg112", {"LHW_WARPS_PER_BLOCK": "9"}),
-    ("reg112", {"LHW_WARPS_PER_BLOCK": "6"}),
-    ("reg96", {"LHW_WARPS_PER_BLOCK": "10"}),
 ]
 WORKLOADS = [("jvrc_walk", 64, 4096), ("jvrc_walk", 64, 32768)]
 PARITY = ["tests/test_gpu_parity.py", "tests/test_gpu_h1.py::test_h1_fp64_closed_loop_with_randomisation_and_resets",
