@@ -37,13 +37,16 @@ __global__ void __launch_bounds__(32 * GAE_SEG) gae_kernel(const float* __restri
   double A = 0.0, C = 1.0;
   if (live) {
     double next_val = t_hi == T - 1 ? (double)last_val[n] : (double)val[(size_t)(t_hi + 1) * N + n];
+    // branch-free body, unrolled: the four loads of a time step do not depend on the previous step's arithmetic, so the
+    // unrolled iterations' loads are in flight together (one DRAM latency per group instead of one per step)
+#pragma unroll 5
     for (int t = t_hi; t >= t_lo; t--) {
       const size_t i = (size_t)t * N + n;
-      if (ended[i]) { next_val = (double)boot[i]; A = 0.0; C = 0.0; }
-      const double v = (double)val[i];
-      A = ((double)rew[i] + gamma * next_val - v) + gl * A;
-      C *= gl;
-
+      const int e = ended[i];
+      const double v = (double)val[i], r = (double)rew[i], b = (double)boot[i];
+      const double nv = e ? b : next_val, Ap = e ? 0.0 : A;
+      A = (r + gamma * nv - v) + gl * Ap;
+      C = (e ? 0.0 : C) * gl;
       next_val = v;
     }
   }
@@ -57,11 +60,12 @@ __global__ void __launch_bounds__(32 * GAE_SEG) gae_kernel(const float* __restri
     for (int s2 = GAE_SEG - 1; s2 > seg; s2--) carry = shA[s2][lane] + shC[s2][lane] * carry;
     double gae = carry;
     double next_val = t_hi == T - 1 ? (double)last_val[n] : (double)val[(size_t)(t_hi + 1) * N + n];
+#pragma unroll 5
     for (int t = t_hi; t >= t_lo; t--) {
       const size_t i = (size_t)t * N + n;
-      if (ended[i]) { next_val = (double)boot[i]; gae = 0.0; }
-      const double v = (double)val[i];
-      gae = ((double)rew[i] + gamma * next_val - v) + gl * gae;
+      const int e = ended[i];
+      const double v = (double)val[i], rw = (double)rew[i], b = (double)boot[i];
+      gae = (rw + gamma * (e ? b : next_val) - v) + gl * (e ? 0.0 : gae);
       const float r = (float)(gae + v);
       ret[i] = r;
       const double a = (double)r - v;     // the advantage as the learner forms it: float32 returns - float32 values
