@@ -354,6 +354,42 @@ def test_two_stream_rollout_halves_equal_the_eager_loop_and_track_the_single_str
     assert torch.equal(outs["graph"][5].view(2048, 12)[:, :4], outs["single"][5].view(2048, 12)[:, :4])
 
 
+def test_two_envs_of_one_variant_with_different_constants_can_alternate_graph_replays(tmp_path):
+    """The model constants of a (variant, precision) live in ONE __constant__ object per process.  Two environments of the same
+    variant with different constants (here: PD gains from a YAML) whose captured rollout graphs are replayed alternately must
+    each see their own constants (DeviceRolloutWorker binds the env's model before it replays): alternating gives bit-identical
+    batches to running each worker alone."""
+    from learninghumanoidwalking_b200.envs import BatchedHumanoidEnv
+    from learninghumanoidwalking_b200.rl import DeviceRolloutWorker, FF_V, Gaussian_FF_Actor
+    soft = tmp_path / "soft.yaml"
+    soft.write_text("kp: [100, 100, 100, 125, 40, 40, 100, 100, 100, 125, 40, 40]\n")
+
+    def worker(yaml):
+        env = BatchedHumanoidEnv(64, precision=32, seed=3, path_to_yaml=yaml)
+        torch.manual_seed(5)
+        pol, cri = Gaussian_FF_Actor(37, 12, init_std=0.223).cuda(), FF_V(37).cuda()
+        pol.obs_mean = cri.obs_mean = torch.tensor(env.obs_mean, dtype=torch.float32, device="cuda")
+        pol.obs_std = cri.obs_std = torch.tensor(env.obs_std, dtype=torch.float32, device="cuda")
+        return DeviceRolloutWorker(env, pol, cri, seed=9)
+
+    grab = lambda b: [t.clone() for t in (b.states, b.actions, b.rewards, b.returns, b.dones)]
+    alone = {}
+    for name, y in (("a", None), ("b", soft)):
+        w = worker(y)
+        alone[name] = [grab(w.sample(0.99, 0.95, 6, 50)) for _ in range(2)]
+        w.env.close()
+    wa, wb = worker(None), worker(soft)
+    inter = {"a": [], "b": []}
+    for _ in range(2):
+        inter["a"].append(grab(wa.sample(0.99, 0.95, 6, 50)))
+        inter["b"].append(grab(wb.sample(0.99, 0.95, 6, 50)))
+    for name in ("a", "b"):
+        for x, y in zip(alone[name], inter[name]):
+            assert all(torch.equal(p, q) for p, q in zip(x, y)), name
+    assert not torch.equal(alone["a"][0][0], alone["b"][0][0])      # the YAML really changed the dynamics
+    wa.env.close(); wb.env.close()
+
+
 def test_graph_replayed_update_matches_the_eager_update(monkeypatch):
     """PPO._update_step: after three eager warm-up updates the optimiser step (losses, backward, clip + Adam with the step
     counter in device memory) is captured once and replayed; same seed, same data => the same weights as the eager loop."""
