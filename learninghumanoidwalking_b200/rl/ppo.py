@@ -164,13 +164,17 @@ class PPO:
             bufs = self._loss_bufs = (torch.empty(B, A, **f32), torch.empty(B, A, **f32), torch.empty(B, 1, **f32),
                                       torch.zeros(_lib.lib().lhw_ppo_loss_partial_words(B), dtype=torch.float64, device=obs_batch.device),
                                       torch.zeros(1, dtype=torch.int32, device=obs_batch.device), torch.zeros(8, **f32))
-        mu = self.policy(obs_batch, deterministic=True)
+        mirr = None
+        if mirror_observation is not None and mirror_action is not None:
+            # the policy on the observations and on their mirror images in ONE pass (twice the rows per GEMM, half the launches)
+            both = self.policy(torch.cat((obs_batch, mirror_observation(obs_batch)), 0), deterministic=True)
+            mu = both[:B]
+            mirr = mirror_action(both[B:]).contiguous()
+        else:
+            mu = self.policy(obs_batch, deterministic=True)
         with torch.no_grad():
             old_mu = self.old_policy(obs_batch, deterministic=True)
         values = self.critic(obs_batch)
-        mirr = None
-        if mirror_observation is not None and mirror_action is not None:
-            mirr = mirror_action(self.policy(mirror_observation(obs_batch))).contiguous()
         stds = self.policy.stds if torch.is_tensor(self.policy.stds) else torch.as_tensor(self.policy.stds)
         total = _FusedPPOLoss.apply(mu, values, mirr, old_mu, action_batch, advantage_batch, return_batch,
                                     stds.to(mu.device, torch.float32), float(self.clip), float(self.mirror_coeff), float(self.ent_coeff), bufs)
