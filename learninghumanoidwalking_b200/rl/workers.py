@@ -48,14 +48,17 @@ class DeviceRolloutWorker:
 
     # ------------------------------------------------------------------ one control step of the rollout loop
     def _parts(self, N: int):
-        """The batch as one part, or as two halves that advance independently on two streams: a control step of one half does
-        not wait for the other half's, so the tail of one half's step launch (4096 fp64 environments are 1.7 resident waves)
-        and its MLP / buffer kernels overlap the other half's step kernel.  Every per-environment result is unchanged (an
-        environment's trajectory does not depend on what it is launched with); LHW_ROLLOUT_SPLIT=0 keeps one part."""
+        """The batch as one part, or as two halves (LHW_ROLLOUT_PARTS, default 2) that advance independently on their own streams:
+        a control step of one half does not wait for the other half's, so the tail of one half's step launch (4096 fp64
+        environments are 1.7 resident waves) and its MLP / buffer kernels overlap the other half's step kernel.  Every
+        per-environment result is unchanged (an environment's trajectory does not depend on what it is launched with);
+        LHW_ROLLOUT_SPLIT=0 keeps one part."""
         import os
-        if os.environ.get("LHW_ROLLOUT_SPLIT", "1") == "0" or N < 1024:
+        k = 1 if os.environ.get("LHW_ROLLOUT_SPLIT", "1") == "0" else int(os.environ.get("LHW_ROLLOUT_PARTS", "2"))
+        if k <= 1 or N < 512 * k:
             return [(0, N)]
-        return [(0, N // 2), (N // 2, N)]
+        cuts = [N * i // k for i in range(k + 1)]
+        return [(cuts[i], cuts[i + 1]) for i in range(k)]
 
     def _step_body(self, buf, part, state, noise, t_idx, deterministic):
         """policy -> action -> critic -> env.step -> bootstrap -> buffer writes for the environments [lo, hi) of `part`, all on
