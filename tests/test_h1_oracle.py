@@ -273,6 +273,45 @@ def test_kernel_source_h1_self_collision_flag(h1):
     assert n_done > 30 and n_self >= 2, (n_done, n_self)
 
 
+def test_kernel_source_h1_thigh_against_the_torso_hip_capsule():
+    """The torso's "hip" capsule (h1.xml:154, welded to the pelvis) against thighs / shins: the self-contact large actions reach
+    first (tests/golden/h1_self_collision_eval.json).  Spreading both hips ends the episode on that pair while every leg-vs-leg
+    pair is still open; kernel source and oracle terminate on the same step."""
+    import json
+    from emu import Emu
+    from learninghumanoidwalking_b200.model import load_model, pack_model
+    from tools.eval_h1_self_collision import seg_seg
+    from tools.shin_clearance import link_poses
+    mj = load_model("h1")
+    sc = mj["self_collision"]
+    assert len(sc["capsules"]) == 15 and len(sc["pairs"]) == 57 and sc["capsules"][14]["link"] == 0
+    ev = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "h1_self_collision_eval.json")))
+    assert ev["rollout_sigma_1.0"]["false_negative_rate"] == 0.0 and ev["uniform_joint_ranges"]["false_negative_rate"] == 0.0
+    assert ev["before_the_hip_capsule_pairs_were_added"]["rollout_sigma_1.0"]["false_negative_rate"] == 1.0
+    o = O.Oracle("h1", tolerance=1e-14)
+    e = Emu(pack_model(mj, tolerance=1e-14), 64, 1, seed=2, first_id=0)
+    envs = o.make_envs(1, seed=2, first_id=0)
+    o.reset(envs)
+    e.reset()
+    a = np.zeros(10)
+    a[1], a[6] = 2.0, -2.0      # left / right hip roll targets outwards
+    hit = None
+    for k in range(20):
+        _, _, d, _ = o.step(envs, 0, a)
+        out = e.step(a[None], autoreset=0)
+        assert bool(out[4][0]) == d, k
+        if d:
+            hit = k
+            break
+    q = np.asarray(o.field(envs, 0, "qpos"))
+    assert hit is not None and int(o.field(envs, 0, "self_collision")[0]) == 1 and 0.9 < q[2] < 1.4
+    R, p = link_poses(mj["links"], q)
+    E = [(p[c["link"]] + R[c["link"]] @ np.array(c["p0"]), p[c["link"]] + R[c["link"]] @ np.array(c["p1"]), c["radius"])
+         for c in sc["capsules"]]
+    gap = lambda a_, b_: seg_seg(E[a_][0], E[a_][1], E[b_][0], E[b_][1]) - E[a_][2] - E[b_][2]
+    assert min(gap(a_, b_) for a_, b_ in sc["pairs"] if b_ == 14) < 0 < min(gap(a_, b_) for a_, b_ in sc["pairs"] if b_ != 14)
+
+
 def test_kernel_source_h1_fp32_stays_close(h1):
     from emu import Emu
     from learninghumanoidwalking_b200.model import load_model, pack_model

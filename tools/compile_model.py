@@ -412,6 +412,7 @@ def compile_h1():
     parts = {}      # xml body name -> dict(link, mass0, mass, com (link frame), Ic (link frame))
     foot_pts = {}
     leg_caps = []   # exact capsule / sphere collision primitives of the leg links (self-collision termination flag)
+    root_caps = []  # ... and the torso's "hip" capsule, the one upper-body primitive the legs reach before termination
 
     def walk(body, link_idx, pos_in_link, rot_in_link):
         name = body.attrib["name"]
@@ -448,6 +449,10 @@ def compile_h1():
                 ft = vec(g.attrib["fromto"], 6)
                 leg_caps.append(dict(link=link_idx, p0=r5v(pos_in_link + rot_in_link @ ft[0:3]),
                                      p1=r5v(pos_in_link + rot_in_link @ ft[3:6]), radius=r5(g.attrib["size"]), name=name + ":capsule"))
+            elif c == "collision" and link_idx == 0 and g.attrib.get("name") == "hip":     # h1.xml:154, on the welded torso
+                ft = vec(g.attrib["fromto"], 6)
+                root_caps.append(dict(link=0, p0=r5v(pos_in_link + rot_in_link @ ft[0:3]),
+                                      p1=r5v(pos_in_link + rot_in_link @ ft[3:6]), radius=r5(g.attrib["size"]), name="torso_link:hip"))
             elif c == "collision" and link_idx > 0 and g.attrib.get("type") == "sphere":
                 ctr = r5v(pos_in_link + rot_in_link @ vec(g.attrib["pos"], 3))
                 leg_caps.append(dict(link=link_idx, p0=ctr, p1=ctr, radius=r5(g.attrib["size"]), name=name + ":sphere"))
@@ -506,14 +511,21 @@ def compile_h1():
     model["total_mass"] = float(sum(lk.mass for lk in links))
     # self-collision (StandingTask.done -> check_self_collisions, robot_interface.py:472-484): MuJoCo collides every pair of
     # collision geoms on different, non-adjacent (weld-aware) bodies.  Modelled exactly: all capsule / sphere primitives of one
-    # leg against those of the other leg (thigh x2, shin, knee sphere, 3 foot capsules = 7 per leg, 49 pairs).  Not modelled:
-    # the hip cylinders, the torso box and the welded upper body (head, arms) against the legs.
+    # leg against those of the other leg (thigh x2, shin, knee sphere, 3 foot capsules = 7 per leg, 49 pairs), and the torso's
+    # "hip" capsule (welded to the pelvis, h1.xml:154) against the thigh / shin / knee primitives of both legs (8 pairs): the
+    # contact that ends episodes under large actions (tools/eval_h1_self_collision.py: every self-contact an oracle rollout
+    # at sigma = 1.0 reaches before the 0.9 m height termination involves it).  Not modelled: the hip cylinders, the torso box,
+    # head and the welded arms (no pose of that study reaches them without also closing a modelled pair).
     nj = len(H1_LEG_JOINTS) // 2
     left = [i for i, c_ in enumerate(leg_caps) if c_["link"] <= nj]
     right = [i for i, c_ in enumerate(leg_caps) if c_["link"] > nj]
-    assert len(left) == len(right) == 7, (len(left), len(right))
-    model["self_collision"] = dict(capsules=leg_caps, pairs=[[a, b] for a in left for b in right],
-                                   source="exact primitives from unitree_h1/h1.xml (capsule and sphere geoms of the leg bodies)")
+    assert len(left) == len(right) == 7 and len(root_caps) == 1, (len(left), len(right), len(root_caps))
+    caps = leg_caps + root_caps
+    hip = len(leg_caps)
+    upper_leg = [i for i, c_ in enumerate(leg_caps) if ":foot" not in c_["name"]]
+    model["self_collision"] = dict(capsules=caps, pairs=[[a, b] for a in left for b in right] + [[a, hip] for a in upper_leg],
+                                   source="exact primitives from unitree_h1/h1.xml (capsule and sphere geoms of the leg bodies, "
+                                          "the torso's hip capsule)")
     # the root link is pelvis + torso + arms welded; randomize_dynamics (domain_randomization.py:46-56) only touches the
     # pelvis BODY (mass x U(.95,1.05), ipos + U(+-.01)) and the leg bodies, so keep the pelvis separable from the rest
     pel = parts["pelvis"]
@@ -528,8 +540,8 @@ def compile_h1():
                       "dynamics use the overridden ones (8.89, 21.289) with unchanged inertia tensors (h1_base.py:40-41)",
                       "ground contacts: the 3 foot capsules per foot (6 end spheres, radius 0.014); other collision primitives "
                       "(legs, torso, arms) only touch the floor after the 0.9 m termination height and are not modelled",
-                      "self-collision flag: leg-vs-leg capsule / sphere primitives (exact); hip cylinders, torso box and the welded "
-                      "upper body are not modelled"]
+                      "self-collision flag: leg-vs-leg capsule / sphere primitives and the torso's hip capsule vs thighs / shins (exact); "
+                      "hip cylinders, torso box, head and the welded arms are not modelled (tests/golden/h1_self_collision_eval.json)"]
     return model
 
 
