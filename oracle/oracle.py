@@ -325,6 +325,7 @@ def _layout():
         ("seq", 80, "f8"), ("goal_steps", 8, "f8"), ("site_pos", 6, "f8"), ("foot_xpos", 6, "f8"), ("root_quat", 4, "f8"),
         ("seq_len", 1, "i4"), ("t1", 1, "i4"), ("t2", 1, "i4"), ("target_reached", 1, "i4"),
         ("target_reached_frames", 1, "i4"), ("con_overflow", 1, "i4"),
+        ("iter_trace", 32, "i4"), ("nrow_trace", 32, "i4"),
     ]
     out, off = {}, 0
     for name, cnt, typ in fields:

@@ -977,6 +977,8 @@ void orc_mj_step(const orc_model* m, orc_env* e, const double* ctrl) {
     e->last_solver_iter = solve_newton(m, M, &efc, qfs, qacc, force, &kkt);
   }
   e->last_kkt_residual = kkt;
+  e->iter_trace[e->nsubsteps & 31] = e->last_solver_iter;
+  e->nrow_trace[e->nsubsteps & 31] = efc.nrow;
   /* ---- quantities mjData keeps after mj_step (all refer to the pre-integration state) */
   memcpy(e->qacc, qacc, nv * sizeof(double));
   for (int u = 0; u < nu; u++) {

@@ -161,6 +161,8 @@ typedef struct {
   double foot_xpos[2][3];          /* foot body xpos (lagged) */
   double root_quat[4];             /* data.xquat of the root body (lagged, normalised) */
   int seq_len, t1, t2, target_reached, target_reached_frames, con_overflow;
+  /* diagnostics: ring of the last 32 substeps (index nsubsteps & 31): solver iterations, contact rows */
+  int iter_trace[32], nrow_trace[32];
 } orc_env;
 
 /* fill a model from a flat double array (layout documented in oracle/oracle.py:pack_model) */
