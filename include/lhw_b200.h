@@ -116,6 +116,15 @@ int lhw_ppo_loss(const float* mu, const float* old_mu, const float* act, const f
                  const float* mirr_or_null, const float* stds, int B, int A, float clip, float mirror_coeff, float ent_coeff,
                  float* g_mu, float* g_mirr_or_null, float* g_val, double* partials, unsigned int* ticket, float* out8, void* stream);
 
+/* lhw_linear_wgrad: what `loss.backward()` (rl/algos/ppo.py:389-392) does per Linear layer of the actor / critic MLPs
+ * (rl/policies/actor.py:122-189, critic.py) for its parameters: gW [N,K] = gy [M,N]^T x [M,K] and gb [N] = column sums of gy
+ * (gb_or_null = NULL: weights only), M = minibatch rows, row-major contiguous operands.  One streaming launch over (gy, x) plus
+ * an ordered reduction of the batch slices (deterministic).  workspace: lhw_linear_wgrad_workspace_floats(M, N, K) floats of
+ * device scratch, free to reuse once the call's work has run on `stream`.  M = 0 zero-fills the outputs. */
+long long lhw_linear_wgrad_workspace_floats(int M, int N, int K);
+int lhw_linear_wgrad(const float* gy, const float* x, int M, int N, int K, float* gW, float* gb_or_null, float* workspace,
+                     void* stream);
+
 /* lhw_gather_minibatch: the fancy-index gathers of rl/algos/ppo.py:535-538 in one launch.
  * idx [B] int64 sample indices into the flattened batch. */
 int lhw_gather_minibatch(const float* obs, const float* act, const float* ret, const float* adv, const int64_t* idx,

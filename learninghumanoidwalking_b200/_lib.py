@@ -42,6 +42,8 @@ SIGNATURES = {
     "lhw_ppo_loss": (c_int, [c_void_p] * 8 + [c_int, c_int, c_float, c_float, c_float] + [c_void_p] * 7),
     "lhw_gather_minibatch": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p]),
     "lhw_grad_sumsq": (c_int, [c_void_p, c_void_p, c_ll, c_float, c_void_p]),
+    "lhw_linear_wgrad_workspace_floats": (c_ll, [c_int, c_int, c_int]),
+    "lhw_linear_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lhw_comm_last_error": (ctypes.c_char_p, []),
     "lhw_comm_handle_size": (c_int, []),
     "lhw_comm_create": (c_int, [ctypes.POINTER(c_void_p), c_ll, c_int, c_int, c_int]),

@@ -22,7 +22,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "liblhw_b200.so")
 TORCH_LIB = os.path.join(PKG, "liblhw_b200_torch.so")     # csrc/torch_ops.cpp: the same entry points as torch.ops.lhw.*
 RECORD = os.path.join(PKG, "build_record.json")
-SOURCES = ["sim_kernels.cu", "ppo_kernels.cu", "comm_kernels.cu"]
+SOURCES = ["sim_kernels.cu", "ppo_kernels.cu", "comm_kernels.cu", "wgrad_kernels.cu"]
 HEADERS = ["sim_core.h", "model_pack.h", os.path.join("..", "..", "include", "lhw_b200.h"), "torch_ops.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

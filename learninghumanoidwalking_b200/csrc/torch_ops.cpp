@@ -173,6 +173,21 @@ void ppo_loss(const Tensor& mu, const Tensor& old_mu, const Tensor& act, const T
                   stream_of(mu)), "lhw_ppo_loss");
 }
 
+void linear_wgrad(const Tensor& gy, const Tensor& x, Tensor gw, const OptTensor& gb, Tensor workspace) {
+  TORCH_CHECK(gy.dim() == 2 && x.dim() == 2 && gy.size(0) == x.size(0), "lhw: gy [M, N] and x [M, K] must share their rows");
+  const int64_t M = gy.size(0), N = gy.size(1), K = x.size(1);
+  const int dev = gy.is_cuda() ? gy.get_device() : -1;
+  check_cuda(gy, "gy", at::kFloat, dev); check_cuda(x, "x", at::kFloat, dev);
+  check_cuda(gw, "gw", at::kFloat, dev); check_shape(gw, "gw", {N, K});
+  if (gb) { check_cuda(*gb, "gb", at::kFloat, dev); check_shape(*gb, "gb", {N}); }
+  check_cuda(workspace, "workspace", at::kFloat, dev);
+  TORCH_CHECK(M < (1LL << 31) && N * K < (1LL << 31), "lhw: linear_wgrad operands too large");
+  TORCH_CHECK(workspace.numel() >= lhw_linear_wgrad_workspace_floats((int)M, (int)N, (int)K), "lhw: linear_wgrad workspace too small");
+  c10::cuda::CUDAGuard guard(dev);
+  ok(lhw_linear_wgrad(gy.data_ptr<float>(), x.data_ptr<float>(), (int)M, (int)N, (int)K, gw.data_ptr<float>(),
+                      gb ? gb->data_ptr<float>() : nullptr, workspace.data_ptr<float>(), stream_of(gy)), "lhw_linear_wgrad");
+}
+
 void grad_sumsq(const Tensor& grad, Tensor norm, double grad_scale) {
   const int dev = grad.is_cuda() ? grad.get_device() : -1;
   check_cuda(grad, "grad", at::kFloat, dev); check_cuda(norm, "norm", at::kFloat, dev);
@@ -228,6 +243,7 @@ TORCH_LIBRARY(lhw, m) {
   m.def("ppo_loss(Tensor mu, Tensor old_mu, Tensor act, Tensor adv, Tensor ret, Tensor val, Tensor? mirr, Tensor stds, float clip, "
         "float mirror_coeff, float ent_coeff, Tensor(a!) g_mu, Tensor(b!)? g_mirr, Tensor(c!) g_val, Tensor(d!) partials, Tensor(e!) ticket, "
         "Tensor(f!) out8) -> ()");
+  m.def("linear_wgrad(Tensor gy, Tensor x, Tensor(a!) gw, Tensor(b!)? gb, Tensor(c!) workspace) -> ()");
   m.def("grad_sumsq(Tensor grad, Tensor(a!) norm, float grad_scale) -> ()");
   m.def("clip_adam_dev(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, Tensor norm, Tensor(d!) step_dev, float lr, "
         "float beta1, float beta2, float eps, float max_norm, float grad_scale) -> ()");
@@ -246,6 +262,7 @@ TORCH_LIBRARY_IMPL(lhw, CompositeExplicitAutograd, m) {
   m.impl("adv_apply", &adv_apply);
   m.impl("gather_minibatch", &gather_minibatch);
   m.impl("ppo_loss", &ppo_loss);
+  m.impl("linear_wgrad", &linear_wgrad);
   m.impl("grad_sumsq", &grad_sumsq);
   m.impl("clip_adam_dev", &clip_adam_dev);
   m.impl("fused_exchange", &fused_exchange);

@@ -8,7 +8,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .base import Net
+from .base import Net, linear
 
 
 class Actor(Net):
@@ -38,8 +38,8 @@ class Gaussian_FF_Actor(Actor):
     def _get_dist_params(self, state):
         x = (state - self.obs_mean) / self.obs_std
         for layer in self.actor_layers:
-            x = self.nonlinearity(layer(x))
-        mean = self.means(x)
+            x = self.nonlinearity(linear(layer, x))
+        mean = linear(self.means, x)
         if self.bounded:
             mean = torch.tanh(mean)
         return mean, self.stds

@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .base import Net
+from .base import Net, linear
 
 
 class Critic(Net):
@@ -31,5 +31,5 @@ class FF_V(Critic):
     def forward(self, state):
         x = (state - self.obs_mean) / self.obs_std
         for layer in self.critic_layers:
-            x = self.nonlinearity(layer(x))
-        return self.network_out(x)
+            x = self.nonlinearity(linear(layer, x))
+        return linear(self.network_out, x)
