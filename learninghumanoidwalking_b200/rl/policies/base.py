@@ -47,8 +47,8 @@ def _use_wgrad_kernel(x, layer):
     if layer.bias is None or not (layer.weight.requires_grad and layer.bias.requires_grad) or layer.weight.dtype != torch.float32:
         return False
     import os
-    if os.environ.get("LHW_WGRAD_KERNEL", "1") == "0":
-        return False
+    if os.environ.get("LHW_WGRAD_KERNEL", "1") == "0" or torch.backends.cuda.matmul.allow_tf32:
+        return False      # --tf32 hands every GEMM of the update to the tensor cores; this kernel is the fp32 FFMA path
     from ... import _lib
     return _lib.use_torch_ops()
 
