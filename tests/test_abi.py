@@ -74,7 +74,7 @@ def test_torch_ops_library_registers_every_entry_point_and_rejects_bad_tensors()
     from learninghumanoidwalking_b200 import _lib
     O = _lib.ops()
     for name in ("sim_reset", "sim_step", "gae", "adv_stats", "adv_stats_from_gae", "adv_apply", "gather_minibatch", "grad_sumsq", "clip_adam_dev",
-                 "fused_exchange"):
+                 "fused_exchange", "ppo_loss", "linear_wgrad"):
         assert hasattr(O, name), name
     r = torch.zeros(4, 3)
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
@@ -83,3 +83,13 @@ def test_torch_ops_library_registers_every_entry_point_and_rejects_bad_tensors()
         O.sim_step(0, r, r.int(), 0, 0, r, 400, True, r, None, r, None, r.int(), r.int(), None, None)
     with pytest.raises(RuntimeError, match="null comm handle"):
         O.fused_exchange(0, r, r, r, 0, 3e-4, 0.9, 0.999, 1e-5, 0.5)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        O.linear_wgrad(r, r, torch.zeros(3, 3), None, torch.zeros(64))
+    with pytest.raises(RuntimeError, match="must share their rows"):
+        O.linear_wgrad(r, torch.zeros(5, 3), torch.zeros(3, 3), None, torch.zeros(64))
+    # the workspace query is host arithmetic: slices x (N*K + N) floats, a few hundred slices at most, nothing for an empty problem
+    L = _lib.lib()
+    for M, N, K in ((43690, 256, 256), (21845, 256, 37), (21845, 1, 256), (5, 3, 7)):
+        w = L.lhw_linear_wgrad_workspace_floats(M, N, K)
+        assert w % (N * K + N) == 0 and 1 <= w // (N * K + N) <= 300, (M, N, K, w)
+    assert L.lhw_linear_wgrad_workspace_floats(0, 4, 4) == 0
