@@ -10,6 +10,7 @@ kernels.
 from __future__ import annotations
 
 import hashlib
+import re
 import json
 import os
 import platform
@@ -62,7 +63,13 @@ def _sass_md5(nvcc: str, target: str = LIB) -> str | None:
     cuobjdump = os.path.join(os.path.dirname(nvcc), "cuobjdump")
     try:
         sass = subprocess.run([cuobjdump, "-sass", target], capture_output=True, timeout=600).stdout
-        return hashlib.md5(sass).hexdigest() if sass else None
+        if not sass:
+            return None
+        # the dump names the source file ("identifier = <absolute path>") and nvcc derives the anonymous-namespace prefix of
+        # every kernel symbol from that path: strip both, so that the same sources give the same md5 in any checkout directory
+        sass = re.sub(rb"(?m)^identifier = .*$", b"", sass)
+        sass = re.sub(rb"_GLOBAL__N__[0-9a-f]+_\d+_(\w+?)_cu_[0-9a-f]+", rb"_GLOBAL__N__\1_cu", sass)
+        return hashlib.md5(sass).hexdigest()
     except Exception:
         return None
 
