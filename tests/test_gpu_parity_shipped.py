@@ -8,6 +8,7 @@ h1 and the terrain extension, 64 environments (8+ lock-step blocks), 1000 contro
   zero     a = 0 (standing; the contact-heavy steady state of SURVEY.md §8d regime ii), truncation + auto-reset at 400
   policy   closed loop: each side feeds ITS OWN observation through the same fixed tanh policy + the same exploration noise
            (the early-training regime: falls, terminations, resets), so any disagreement is fed back
+  trained  (jvrc_walk) closed loop through the actor of a finished training run: 400-step walking episodes
 
 Bar (BASELINE.json north_star): qpos / qvel within 1e-4 relative over the 1000 steps, identical done / ended flags.
 The achieved figures go to gpurun_out/parity_shipped.json (DESIGN.md §2 quotes them).
@@ -36,6 +37,21 @@ def _policy(obs_dim, act_dim, mean, std, seed):
     return lambda obs: 0.3 * np.tanh(((obs - mean) / std) @ W)
 
 
+def _trained_policy(model):
+    """The actor of a 40-iteration `run_experiment.py train --env jvrc_walk --num-procs 4096 --seed 0` run of this build
+    (tests/golden/trained_actor_jvrc_walk.pt; mean episode length 398 of 400: it walks), evaluated in float64 on each side's own
+    observation: a smooth function, so a 1e-13 difference in the observation is not blown up by a float32 rounding boundary."""
+    from learninghumanoidwalking_b200.rl.policies import install_reference_aliases
+    install_reference_aliases()
+    actor = torch.load(os.path.join(ROOT, "tests", "golden", f"trained_actor_{model}.pt"), map_location="cpu", weights_only=False).double()
+    actor.eval()
+
+    def pol(obs):
+        with torch.no_grad():
+            return actor(torch.from_numpy(np.ascontiguousarray(obs, dtype=np.float64)), deterministic=True).numpy()
+    return pol
+
+
 def _run(model, regime, precision=64, n=N_ENVS, steps=STEPS, stop_outside=None):
     """Kernel (C-ABI, shipped tolerance) and oracle (the model's own tolerance) side by side; returns the worst relative
     errors, the number of ended episodes and, for `stop_outside`, the first step at which qpos / qvel left that band."""
@@ -49,7 +65,8 @@ def _run(model, regime, precision=64, n=N_ENVS, steps=STEPS, stop_outside=None):
     o_obs = o.batch_reset(envs, n)
     g_obs = env.reset().double().cpu().numpy()
     A, nq, nv = env.act_dim, env.nq, env.nv
-    pol = _policy(env.obs_dim, A, env.obs_mean, env.obs_std, seed=7)
+    pol = _trained_policy(model) if regime == "trained" else _policy(env.obs_dim, A, env.obs_mean, env.obs_std, seed=7)
+    sigma = 0.05 if regime == "trained" else 0.223
     rng = np.random.RandomState(3)
     worst = dict(qpos=0.0, qvel=0.0, obs=0.0, reward=0.0)
     n_end, first_out = 0, None
@@ -57,7 +74,7 @@ def _run(model, regime, precision=64, n=N_ENVS, steps=STEPS, stop_outside=None):
         if regime == "zero":
             a_o = a_g = np.zeros((n, A))
         else:
-            noise = rng.normal(size=(n, A)) * 0.223
+            noise = rng.normal(size=(n, A)) * sigma
             a_o, a_g = pol(o_obs) + noise, pol(g_obs) + noise
         o_obs, o_tobs, o_terms, o_rew, o_done, o_end = o.batch_step(envs, n, a_o, max_traj_len=400)
         t_obs, t_rew, t_done, t_end = env.step(torch.as_tensor(a_g, device="cuda", dtype=env.dtype))
@@ -98,6 +115,18 @@ def test_fp64_shipped_tolerance_1000_steps_64_envs(model, regime):
     assert n_end >= N_ENVS, "every env should at least hit one truncation / termination in 1000 steps"
     assert worst["qpos"] < BAR and worst["qvel"] < BAR, worst
     assert worst["obs"] < BAR and worst["reward"] < BAR, worst
+
+
+def test_fp64_shipped_tolerance_under_a_trained_walking_policy():
+    """The regime the trainer converges to: a policy that WALKS for the whole 400-step horizon (heel strikes, double-support
+    phases, mode switches) instead of falling after 50 steps.  Same bar, same settings; episodes end by truncation only."""
+    worst, n_end, _, iters, tol = _run("jvrc_walk", "trained")
+    _results["jvrc_walk/trained/fp64"] = dict(worst, ended_episodes=n_end, envs=N_ENVS, control_steps=STEPS, newton_iters_last_step=iters,
+                                              tolerance=tol)
+    _save()
+    print("\n[parity shipped] jvrc_walk trained policy fp64: " + "  ".join(f"{k} {v:.2e}" for k, v in worst.items()) + f"  ended {n_end}")
+    assert N_ENVS * 2 <= n_end <= N_ENVS * 2 + N_ENVS // 2, n_end      # truncations at 400 and 800, (almost) no falls
+    assert worst["qpos"] < BAR and worst["qvel"] < BAR and worst["obs"] < BAR and worst["reward"] < BAR, worst
 
 
 @pytest.mark.parametrize("model", ["jvrc_walk", "h1"])

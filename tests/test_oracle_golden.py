@@ -220,3 +220,33 @@ def test_walking_task_matches_the_reference_class():
             assert ((z < 0.6) or (z > 1.4) or st["selfcol"]) == s["done"]    # the bounds oracle.pack_model / model.loader pack
             n_done += s["done"]
     assert seen_modes == {0, 1, 2} and n_switch >= 30 and n_hook >= 15 and 5 <= n_done < 80
+
+
+def test_policy_trained_on_the_gpu_simulator_walks_in_the_oracle():
+    """tests/golden/trained_actor_jvrc_walk.pt is the actor of a 40-iteration `run_experiment.py train --env jvrc_walk --num-procs 4096
+    --seed 0` run on the fp32 CUDA simulator (mean episode length 398 of 400 there).  Driven by the same actor (float64 forward,
+    deterministic mean + 0.05 exploration noise), the CPU oracle's environments also survive the 400-step horizon: the two
+    implementations agree at the level of behaviour, not only step by step (tests/test_gpu_parity_shipped.py holds them to 1e-4
+    along such trajectories)."""
+    import torch
+    from learninghumanoidwalking_b200.rl.policies import install_reference_aliases
+    from oracle.oracle import Oracle
+    install_reference_aliases()
+    actor = torch.load(os.path.join(os.path.dirname(__file__), "golden", "trained_actor_jvrc_walk.pt"), map_location="cpu",
+                       weights_only=False).double().eval()
+    o = Oracle("jvrc_walk")
+    n = 8
+    envs = o.make_envs(n, seed=31, first_id=5)
+    obs = o.batch_reset(envs, n)
+    rng = np.random.RandomState(3)
+    ended_at = []
+    total = np.zeros(n)
+    for k in range(400):
+        with torch.no_grad():
+            act = actor(torch.from_numpy(obs), deterministic=True).numpy()
+        obs, _, _, rew, done, end = o.batch_step(envs, n, act + 0.05 * rng.normal(size=(n, 12)), max_traj_len=400)
+        total += rew * (len(ended_at) == 0)
+        if end.any():
+            ended_at.append(k)
+            assert k == 399 and end.all() and not done.any()      # truncation, not a fall
+    assert ended_at == [399] and total.mean() > 200.0, (ended_at, total.mean())
