@@ -20,6 +20,9 @@ def test_committed_evaluation_bounds_the_proxy_error():
         # cross-leg: the proxies disagree with the hulls on < 2 % of the poses in either direction
         assert d["cross_leg"]["fp"] < 0.02 and d["cross_leg"]["fn"] < 0.02, (name, d["cross_leg"])
         assert abs(d["cross_leg"]["proxy"] - d["cross_leg"]["hull"]) < 0.01
+    # on the poses of an actual gait (a trained policy walking in the oracle) neither the hulls nor the proxies touch
+    gait = [d for name, d in ev["distributions"].items() if name.startswith("states of a trained walking policy")]
+    assert len(gait) == 1 and gait[0]["cross_leg"] == {"hull": 0.0, "proxy": 0.0, "fp": 0.0, "fn": 0.0}
     from learninghumanoidwalking_b200.model import load_model
     for model in ("jvrc_walk", "jvrc_step", "jvrc_walk_terrain"):
         sc = load_model(model)["self_collision"]

@@ -91,12 +91,40 @@ def main():
     nominal = np.array(mj["cfg"]["nominal_qpos"])
     rng = np.random.RandomState(0)
     out = {"n_samples": n_samples, "pairs": {"cross_leg": len(cross), "same_leg": len(same)}, "distributions": {}}
-    for dist_name in ("nominal + N(0, 0.35 rad) (what an untrained / exploring policy visits)", "uniform inside the joint ranges"):
+    def gait_poses():
+        """states the CPU oracle visits under the actor of a finished training run (tests/golden/trained_actor_jvrc_walk.pt,
+        deterministic mean + N(0, 0.05^2)): the poses of an actual gait.  The policy was trained WITH the proxies ending its episodes,
+        so proxy hits are absent by selection; what this distribution measures is whether the hulls touch where the proxies do not."""
+        import torch
+        from learninghumanoidwalking_b200.rl.policies import install_reference_aliases
+        from oracle.oracle import Oracle
+        install_reference_aliases()
+        actor = torch.load(os.path.join(ROOT, "tests", "golden", "trained_actor_jvrc_walk.pt"), map_location="cpu", weights_only=False).double().eval()
+        o = Oracle("jvrc_walk")
+        n = 16
+        envs = o.make_envs(n, seed=31, first_id=5)
+        obs = o.batch_reset(envs, n)
+        r2 = np.random.RandomState(3)
+        poses = []
+        while len(poses) < n_samples:
+            with torch.no_grad():
+                act = actor(torch.from_numpy(obs), deterministic=True).numpy()
+            obs = o.batch_step(envs, n, act + 0.05 * r2.normal(size=(n, 12)), max_traj_len=400)[0]
+            poses += [np.asarray(o.field(envs, i, "qpos")).copy() for i in range(n)]
+        return poses[:n_samples]
+
+    dists = ["nominal + N(0, 0.35 rad) (what an untrained / exploring policy visits)", "uniform inside the joint ranges"]
+    if os.path.exists(os.path.join(ROOT, "tests", "golden", "trained_actor_jvrc_walk.pt")):
+        dists.append("states of a trained walking policy in the oracle (400-step episodes, no falls)")
+    for dist_name in dists:
         stats = {k: dict(hull=0, proxy=0, fp=0, fn=0) for k in ("cross_leg", "same_leg")}
-        for _ in range(n_samples):
+        gait = gait_poses() if dist_name.startswith("states of") else None
+        for si in range(n_samples):
             q = nominal.copy()
             if dist_name.startswith("nominal"):
                 q[7:] = np.clip(nominal[7:] + rng.normal(size=12) * 0.35, lo, hi)
+            elif gait is not None:
+                q = gait[si]
             else:
                 q[7:] = rng.uniform(lo, hi)
             xpos, xmat = kinematics(mj, q)
