@@ -44,6 +44,9 @@ SIGMA = 0.223
 ALG_BYTES = {32: 1220, 64: 2288}   # state read+write, action read, obs/reward/done write
 
 
+TRAINED_ACTOR = os.path.join(ROOT, "tests", "golden", "trained_actor_jvrc_walk.pt")
+
+
 def ncu_counters(workload: str, precision: int):
     """(dram bytes, warp instructions) per 4096-env launch from the committed ncu capture, or (None, reason).  The capture is
     only valid for the kernels it was taken on: profiles/ncu_counters.json records the md5 of their SASS (build_record.json).  Under ncu the
@@ -268,6 +271,11 @@ def main():
         g = torch.Generator(device=dev).manual_seed(args.seed * 1000 + rank + seed_off)
         noise = torch.randn(warm + steps, nn, A, device=dev, generator=g, dtype=env.dtype) * SIGMA
         pol = make_policy(env)[0] if regime == "policy" else None
+        if regime == "trained":      # the actor of a finished training run (tests/golden): a walking gait, 400-step episodes
+            from learninghumanoidwalking_b200.rl.policies import install_reference_aliases
+            install_reference_aliases()
+            pol = torch.load(TRAINED_ACTOR, map_location="cpu", weights_only=False).to(dev).eval()
+            noise = noise * (0.05 / SIGMA)
         obs = env.obs
 
         def action(k):
@@ -339,6 +347,11 @@ def main():
             extras[f"regime_{regime}_env_steps_per_s_per_gpu"] = n * Kx / (sum(ms) * 1e-3)
         extras["regime_note"] = (f"device-resident, same kernel, {Kx} timed steps each (the headline regime: {K}); zero = standing with 8 "
                                  "contacts, policy = freshly initialised actor in the loop (its MLP is outside the event pair)")
+        if wl["model"] == "jvrc_walk" and os.path.exists(TRAINED_ACTOR):
+            ms, _, _ = timed_steps(env, "trained", 200, Kx, seed_off=23)
+            extras["regime_trained_env_steps_per_s_per_gpu"] = n * Kx / (sum(ms) * 1e-3)
+            extras["regime_trained_note"] = ("closed loop through tests/golden/trained_actor_jvrc_walk.pt (40 iterations of run_experiment.py "
+                                             "train) + N(0, 0.05^2): the walking gait a training run converges to, after a 200-step warm-up")
         env32 = BatchedHumanoidEnv(n, model=wl["model"], precision=32, seed=args.seed, first_env_id=rank * n, device=local_rank)
         env32.reset()
         ms32, _, _ = timed_steps(env32, args.actions, 30, Kx, do_flush=False)
