@@ -100,7 +100,13 @@ def _run(model, regime, precision=64, n=N_ENVS, steps=STEPS, stop_outside=None):
 def _save():
     out = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out):
-        json.dump(_results, open(os.path.join(out, "parity_shipped.json"), "w"), indent=1, sort_keys=True)
+        path = os.path.join(out, "parity_shipped.json")
+        try:
+            merged = json.load(open(path))       # a partial run (-k ...) adds to what an earlier run left, it does not erase it
+        except Exception:
+            merged = {}
+        merged.update(_results)
+        json.dump(merged, open(path, "w"), indent=1, sort_keys=True)
 
 
 @pytest.mark.parametrize("regime", ["zero", "policy"])
