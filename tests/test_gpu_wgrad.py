@@ -33,6 +33,10 @@ def test_wgrad_matches_float64_products(M, N, K):
     ref = gy.double().t().mm(x.double())
     scale = gy.abs().double().t().mm(x.abs().double()).max().item()
     assert torch.isfinite(gw).all() and (gw.double() - ref).abs().max().item() < 2e-6 * scale
+    if M * N * K <= 1 << 24:      # the numpy oracle (pinned to torch autograd on the CPU) where it is quick
+        from oracle.ppo_oracle import linear_param_grads
+        ow, ob = linear_param_grads(gy.cpu().numpy(), x.cpu().numpy())
+        assert np.abs(gw.double().cpu().numpy() - ow).max() < 2e-6 * scale
     refb = gy.double().sum(0)
     assert torch.isfinite(gb).all() and (gb.double() - refb).abs().max().item() < 2e-6 * gy.abs().double().sum(0).max().item()
     gw2, gb2 = _run(gy, x)

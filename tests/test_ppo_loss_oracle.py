@@ -45,3 +45,17 @@ def test_closed_form_loss_and_gradients_equal_autograd_on_the_reference_formulat
         assert np.abs(got[3].reshape(-1) - exp[3].reshape(-1)).max() < 1e-14
         if scale == 0.3:
             assert 0.1 < got[0][6] < 0.9        # the clip fraction says the case exercises the clipped branches
+
+
+def test_linear_param_grads_equal_autograd_of_nn_linear():
+    """oracle.ppo_oracle.linear_param_grads (the checker of lhw_linear_wgrad) against torch's own backward of the reference's layer
+    type, float64, for the four layer shapes of the actor / critic and a ragged one."""
+    import torch
+    from oracle.ppo_oracle import linear_param_grads
+    torch.manual_seed(0)
+    for M, N, K in ((64, 256, 37), (64, 256, 256), (64, 12, 256), (64, 1, 256), (7, 3, 5)):
+        layer = torch.nn.Linear(K, N).double()
+        x, gy = torch.randn(M, K, dtype=torch.float64), torch.randn(M, N, dtype=torch.float64)
+        layer(x).backward(gy)
+        gw, gb = linear_param_grads(gy.numpy(), x.numpy())
+        assert np.abs(gw - layer.weight.grad.numpy()).max() < 1e-12 and np.abs(gb - layer.bias.grad.numpy()).max() < 1e-12
