@@ -106,3 +106,18 @@ def test_env_attributes_match_the_reference_env_classes():
             assert env.robot.iteration_count == float("inf")                 # robots/robot_base.py:35
         else:
             assert not hasattr(env.robot, "mirrored_obs")
+
+
+def test_linear_helper_is_the_plain_layer_off_the_cuda_training_path():
+    """rl/policies/base.py:linear routes ONLY CUDA float32 training forwards to the weight-gradient kernel; on the CPU (these tests,
+    the reference's own checkpoints in a CPU process) it is `layer(x)` with torch's own backward, bit for bit."""
+    import torch
+    from learninghumanoidwalking_b200.rl.policies.base import _use_wgrad_kernel, linear
+    torch.manual_seed(0)
+    layer = torch.nn.Linear(37, 256)
+    x = torch.randn(16, 37)
+    assert not _use_wgrad_kernel(x, layer)
+    y = linear(layer, x)
+    assert torch.equal(y, layer(x)) and type(y.grad_fn).__name__ == "AddmmBackward0"
+    with torch.no_grad():
+        assert linear(layer, x).grad_fn is None
